@@ -1,0 +1,276 @@
+/*
+ * restir_b200.h — C ABI of the B200-native ReSTIR DI hot path.
+ *
+ * Drop-in boundary for the per-pixel frame loop of Tonz24/restir-embree.
+ * Path prefix P/ = template/src/pg/pg1_embree/ in the reference checkout.
+ *
+ *   Frame seam : replaces the body of SimpleGuiDX11::produceRestir(float t)
+ *                (P/simpleguidx11.cpp:359-487, declared P/simpleguidx11.h:87).
+ *   Ray seam   : replaces Intersection::intersectEmbree / testOcclusion
+ *                (P/Intersection.h:8-41, 43-60), i.e. Embree's rtcIntersect1 /
+ *                rtcOccluded1 (embree3/rtcore_scene.h:99,123), in the batched
+ *                stream form of rtcIntersect1M / rtcOccluded1M (:111,135).
+ *
+ * Plain C, POD only: no C++ types, no torch types.  All functions return
+ * RB_OK (0) or a negative RbStatus; none throws across the boundary.
+ * rb_last_error() gives the text the reference would have thrown from its
+ * Embree error callback (P/tutorials.cpp:6-24).
+ *
+ * Threading: one caller thread per handle (the reference's Producer thread,
+ * P/simpleguidx11.cpp:223,499); not re-entrant; one frame in flight.
+ * Parameters and camera are snapshotted at rb_render_frame entry.
+ */
+#ifndef RESTIR_B200_H_
+#define RESTIR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+typedef enum RbStatus {
+  RB_OK = 0,
+  RB_ERR_INVALID_ARGUMENT = -1,
+  RB_ERR_CUDA = -2,
+  RB_ERR_NO_SCENE = -3,
+  RB_ERR_UNSUPPORTED = -4,
+  RB_ERR_OUT_OF_MEMORY = -5,
+  RB_ERR_COMM = -6
+} RbStatus;
+
+/* MaterialType, P/enums.h:3-11 (same numeric values). */
+typedef enum RbMaterialType {
+  RB_MAT_NORMAL = 0,
+  RB_MAT_LAMBERT = 1,
+  RB_MAT_PHONG = 2,
+  RB_MAT_MIRROR = 3,
+  RB_MAT_DIELECTRIC = 4,
+  RB_MAT_DIELECTRIC_TRANSPARENT = 5,
+  RB_MAT_UNSUPPORTED = 6
+} RbMaterialType;
+
+/* ReSTIRIntegrator::SpatialWeightCalculation, P/ReSTIRIntegrator.h:19-25
+ * (same order, same numeric values). */
+typedef enum RbSpatialWeightCalc {
+  RB_SW_CONSTANT = 0,
+  RB_SW_CONSTANT_DEBIAS_CONTRIB = 1,
+  RB_SW_CONSTANT_DEBIAS_Z_TERM = 2,
+  RB_SW_BALANCE_HEURISTIC = 3,
+  RB_SW_PAIRWISE_MIS = 4
+} RbSpatialWeightCalc;
+
+/* Light-sampler seam: the reference inverts a float CDF with
+ * std::lower_bound (P/TriangleCDF.cpp:36-54); north_star asks for an alias
+ * table.  Both are implemented; both pick emissive triangles ∝ area. */
+typedef enum RbLightSampler {
+  RB_LS_CDF = 0,  /* P/TriangleCDF.cpp semantics, pdf = cdf[i]-cdf[i-1]      */
+  RB_LS_ALIAS = 1 /* Vose alias table, single-draw, pdf = area_i/total_area   */
+} RbLightSampler;
+
+/* Material constants read by the path: Material::{diffuse,specular,emission,
+ * shininess_,ior}, P/material.h:104-115; type from getType(). */
+typedef struct RbMaterial {
+  uint32_t type; /* RbMaterialType */
+  float diffuse[3];
+  float specular[3];
+  float emission[3];
+  float shininess;
+  float ior;
+} RbMaterial;
+
+/* One surface == one Embree geometry (geomID = index, attach order),
+ * exactly what ModelLoader::loadScene hands Embree, P/ModelLoader.cpp:227-318:
+ * non-indexed triangle soup, 3*n_tris vertices, identity index buffer (:297-299).
+ * uv / tangent may be NULL (treated as zero; only used by textured / normal-
+ * mapped materials, which are out of scope of this ABI version). */
+typedef struct RbSurface {
+  uint32_t n_tris;
+  uint32_t material;    /* index into RbSceneDesc.materials */
+  const float* pos;     /* [3*n_tris][3] */
+  const float* normal;  /* [3*n_tris][3] */
+  const float* uv;      /* [3*n_tris][2] or NULL */
+  const float* tangent; /* [3*n_tris][3] or NULL */
+} RbSurface;
+
+typedef struct RbSceneDesc {
+  uint32_t n_surfaces;
+  const RbSurface* surfaces;
+  uint32_t n_materials;
+  const RbMaterial* materials;
+} RbSceneDesc;
+
+/* 1:1 with the ReSTIRIntegrator statics (P/ReSTIRIntegrator.cpp:13-35,
+ * P/ReSTIRIntegrator.h:91-113) and the RenderParams fields the path reads
+ * (P/RenderParams.h:8-17).  rb_default_params() fills the reference defaults. */
+typedef struct RbParams {
+  int32_t M_Area;                    /* 1  */
+  int32_t M_Brdf;                    /* 1  */
+  int32_t spatialReuseNeighborCount; /* 5  */
+  int32_t spatialPassCount;          /* 1  */
+  int32_t confidenceCap;             /* 20 */
+  float spatialReuseRadius;          /* 30 (reach is floor(sqrt(radius)) px, P/Sampling.cpp:78-87) */
+  float minNormalSimilarity;         /* 0.85 */
+  float maxDepthDifference;          /* 0.2  */
+  int32_t doSpatialReuse;            /* 0 */
+  int32_t doTemporalReuse;           /* 0 */
+  int32_t doVisibilityPass;          /* 0 */
+  int32_t rejectDissimilarNeighbors; /* 0 */
+  int32_t spatialWeightCalc;         /* RbSpatialWeightCalc, CONSTANT */
+  float tnearOffset;                 /* 0.01  */
+  float tfarOffset;                  /* 0.001 */
+  float normalOffset;                /* 0.001 */
+  float bgColor[3];                  /* 0.5   */
+  int32_t useSkybox;                 /* reference default 1; sky texture is not part of ABI v1 -> must be 0 */
+  int32_t lightSampler;              /* RbLightSampler; reference = CDF */
+  int32_t wavefront;                 /* 0: every pass traces its rays inline; 1: stream->trace->resolve split */
+} RbParams;
+
+/* What produceRestir copies out of Camera into GBuffer each frame
+ * (P/simpleguidx11.cpp:362-365): position, view matrix, inverse view matrix
+ * (column-major like glm::mat4), focal length in pixels (P/camera.cpp:81-84). */
+typedef struct RbCamera {
+  float pos[3];
+  float focal_px;
+  float viewMat[16];
+  float invViewMat[16];
+} RbCamera;
+
+/* The reference's per-pass millisecond timers (P/simpleguidx11.h:120-127),
+ * here from CUDA events, plus ray counters for Mrays/s. */
+typedef struct RbTimings {
+  float ms_gbuffer;
+  float ms_initial;
+  float ms_visibility;
+  float ms_temporal;
+  float ms_spatial;
+  float ms_shade;
+  float ms_total;
+  float ms_trace_any;           /* sum of any-hit traversal kernels (wavefront mode) */
+  uint64_t rays_closest;        /* closest-hit rays traced this frame  */
+  uint64_t rays_any_as_written; /* shadow rays the reference would issue */
+  uint64_t rays_any_traced;     /* after exact-duplicate / zero-contribution elimination */
+  uint32_t kernel_launches;
+  uint32_t reserved;
+} RbTimings;
+
+typedef struct RbCreateInfo {
+  int32_t width;   /* full image, SimpleGuiDX11::width_  */
+  int32_t height;  /* full image, SimpleGuiDX11::height_ */
+  int32_t device;  /* CUDA ordinal */
+  uint32_t seed;   /* counter-RNG seed (reference: mt19937{123}, P/utils.cpp:175) */
+  int32_t band_y0; /* first image row rendered by this handle (multi-GPU bands); 0 */
+  int32_t band_y1; /* one past the last row; height for a single GPU */
+  int32_t collect_timings; /* record CUDA events per pass (adds syncs at readout only) */
+  int32_t reserved;
+} RbCreateInfo;
+
+/* Device buffers readable for parity checks (rb_readback). */
+typedef enum RbBufferId {
+  RB_BUF_GBUF_POS_DEPTH = 0,   /* float4 {pos.xyz, depth}            per px */
+  RB_BUF_GBUF_NORMAL_SHIN = 1, /* float4 {normal.xyz, shininess}     per px */
+  RB_BUF_GBUF_DIFFUSE_IIM = 2, /* float4 {diffuse.rgb, 1/I_M}        per px */
+  RB_BUF_GBUF_SPEC_TYPE = 3,   /* float4 {specular.rgb, bits(matType|emissive<<8)} */
+  RB_BUF_GBUF_EMISSION = 4,    /* float4 {emission.rgb, 0}           per px */
+  RB_BUF_HIT_IDS = 5,          /* uint2  {geomID, primID} of the primary hit (~0u = miss) */
+  RB_BUF_RES_POINT_WSUM = 6,   /* float4 {samplePoint.xyz, w_sum}   final reservoir of the frame */
+  RB_BUF_RES_NORMAL_W = 7,     /* float4 {sampleNormal.xyz, W}      */
+  RB_BUF_RES_LI_CONF = 8,      /* float4 {L_i.rgb, bits(confidence)} */
+  RB_BUF_RES_LIGHT_IDX = 9,    /* int32  emissive-triangle id of bestSample (-1 none) */
+  RB_BUF_FRAME_RGB = 10,       /* float3 frame_data (linear HDR)    */
+  RB_BUF_ALIAS_PROB = 11,      /* float  [n_emissive]                */
+  RB_BUF_ALIAS_IDX = 12,       /* uint32 [n_emissive]                */
+  RB_BUF_LIGHT_CDF = 13        /* float  [n_emissive]                */
+} RbBufferId;
+
+/* Ray seam records.  RbRay has the 48-byte layout of RTCRay
+ * (embree3/rtcore_ray.h:11-27) so a host can pass its Embree rays unchanged. */
+typedef struct RbRay {
+  float org_x, org_y, org_z, tnear;
+  float dir_x, dir_y, dir_z, time;
+  float tfar;
+  uint32_t mask, id, flags;
+} RbRay;
+
+/* Subset of RTCHit (rtcore_ray.h:30-42) the path consumes. */
+typedef struct RbHit {
+  float t, u, v;
+  uint32_t primID; /* triangle index within its surface; 0xFFFFFFFF = miss */
+  uint32_t geomID; /* surface index (attach order);      0xFFFFFFFF = miss */
+} RbHit;
+
+typedef struct RbContext* RbHandle;
+
+uint32_t rb_abi_version(void);
+const char* rb_last_error(RbHandle h); /* h may be NULL: error of the last failed rb_create */
+void rb_default_params(RbParams* out);
+
+/* replaces SimpleGuiDX11::Init buffer allocation, P/simpleguidx11.cpp:113-119 */
+int rb_create(const RbCreateInfo* info, RbHandle* out);
+void rb_destroy(RbHandle h);
+
+/* replaces ModelLoader::loadScene + TriangleCDF ctor + rtcCommitScene
+ * (P/ModelLoader.cpp:218-321, P/TriangleCDF.cpp:8-34, P/Scene.cpp:8-16):
+ * copies the scene to the GPU, builds the light tables and the wide BVH there. */
+int rb_upload_scene(RbHandle h, const RbSceneDesc* scene);
+
+/* replaces the ImGui edits of the statics, P/ReSTIRIntegrator.cpp:37-87 */
+int rb_set_params(RbHandle h, const RbParams* params);
+
+/* replaces SimpleGuiDX11::produceRestir, P/simpleguidx11.cpp:359-487.
+ * frame_idx plays the role of frameCtr (temporal reuse only when > 0, :408).
+ * frame_rgb_out: w*h*3 floats (band rows only are written), host pointer or
+ * NULL (keep the frame on the device; fetch later with rb_readback).
+ * timings may be NULL. */
+int rb_render_frame(RbHandle h, const RbCamera* cam, uint32_t frame_idx,
+                    float* frame_rgb_out, RbTimings* timings);
+
+/* Same, output left in / written to DEVICE memory (frame_rgb_dev may be NULL). */
+int rb_render_frame_device(RbHandle h, const RbCamera* cam, uint32_t frame_idx,
+                           float* frame_rgb_dev, RbTimings* timings);
+
+int rb_readback(RbHandle h, int buffer_id /*RbBufferId*/, void* dst, size_t bytes);
+int rb_synchronize(RbHandle h);
+
+/* replaces Intersection::intersectEmbree's rtcIntersect1 (P/Intersection.h:63-83)
+ * and Intersection::testOcclusion's rtcOccluded1 (:43-60); host pointers. */
+int rb_trace_closest(RbHandle h, const RbRay* rays, RbHit* hits, uint32_t n);
+int rb_trace_occluded(RbHandle h, const RbRay* rays, uint8_t* occluded, uint32_t n);
+/* device-pointer variants (no copies; timed with CUDA events → *ms_out) */
+int rb_trace_closest_device(RbHandle h, const RbRay* rays_dev, RbHit* hits_dev, uint32_t n, float* ms_out);
+int rb_trace_occluded_device(RbHandle h, const RbRay* rays_dev, uint8_t* occ_dev, uint32_t n, float* ms_out);
+
+/* Scene statistics after upload. */
+typedef struct RbSceneStats {
+  uint32_t n_triangles;
+  uint32_t n_emissive;
+  uint32_t n_bvh_nodes;
+  uint32_t bvh_depth;
+  float build_ms;
+  float total_emissive_area;
+  float bounds_lo[3];
+  float bounds_hi[3];
+} RbSceneStats;
+int rb_scene_stats(RbHandle h, RbSceneStats* out);
+
+/* Multi-GPU bands: NCCL communicator over the handles of all
+ * ranks; nccl_unique_id is the 128-byte ncclUniqueId created by rank 0 and
+ * distributed by the launcher (torch.distributed / MPI / files). After this,
+ * rb_render_frame exchanges reservoir halo rows with rank±1 each frame. */
+int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes);
+int rb_comm_unique_id(void* out_id, size_t id_bytes); /* rank 0: ncclGetUniqueId */
+
+/* Transport-agnostic halo access used by single-process band emulation and tests:
+ * copies `rows` image rows starting at global row y of the current reservoir
+ * read buffer (4 planes, 52 B/px) to/from a packed device or host buffer. */
+size_t rb_halo_bytes(RbHandle h, int32_t rows);
+int rb_halo_export(RbHandle h, int32_t y, int32_t rows, void* dst_host);
+int rb_halo_import(RbHandle h, int32_t y, int32_t rows, const void* src_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESTIR_B200_H_ */

@@ -1,0 +1,206 @@
+"""ctypes mirror of include/restir_b200.h (the C ABI of the hot path).
+
+Every structure here has the same field order and types as the C header; the
+layout is asserted against the shared library at load time (rb_abi_version and
+sizeof checks in tests/test_abi.py).
+"""
+import ctypes as C
+
+import numpy as np
+
+RB_OK = 0
+
+# RbMaterialType — P/enums.h:3-11
+MAT_NORMAL, MAT_LAMBERT, MAT_PHONG, MAT_MIRROR, MAT_DIELECTRIC, MAT_DIELECTRIC_TRANSPARENT, MAT_UNSUPPORTED = range(7)
+# RbSpatialWeightCalc — P/ReSTIRIntegrator.h:19-25
+SW_CONSTANT, SW_CONSTANT_DEBIAS_CONTRIB, SW_CONSTANT_DEBIAS_Z_TERM, SW_BALANCE_HEURISTIC, SW_PAIRWISE_MIS = range(5)
+LS_CDF, LS_ALIAS = 0, 1
+
+(BUF_GBUF_POS_DEPTH, BUF_GBUF_NORMAL_SHIN, BUF_GBUF_DIFFUSE_IIM, BUF_GBUF_SPEC_TYPE, BUF_GBUF_EMISSION, BUF_HIT_IDS,
+ BUF_RES_POINT_WSUM, BUF_RES_NORMAL_W, BUF_RES_LI_CONF, BUF_RES_LIGHT_IDX, BUF_FRAME_RGB, BUF_ALIAS_PROB, BUF_ALIAS_IDX,
+ BUF_LIGHT_CDF) = range(14)
+
+# (dtype, channels) of each readback buffer, per pixel unless noted
+BUFFER_LAYOUT = {
+    BUF_GBUF_POS_DEPTH: (np.float32, 4),
+    BUF_GBUF_NORMAL_SHIN: (np.float32, 4),
+    BUF_GBUF_DIFFUSE_IIM: (np.float32, 4),
+    BUF_GBUF_SPEC_TYPE: (np.float32, 4),
+    BUF_GBUF_EMISSION: (np.float32, 4),
+    BUF_HIT_IDS: (np.uint32, 2),
+    BUF_RES_POINT_WSUM: (np.float32, 4),
+    BUF_RES_NORMAL_W: (np.float32, 4),
+    BUF_RES_LI_CONF: (np.float32, 4),
+    BUF_RES_LIGHT_IDX: (np.int32, 1),
+    BUF_FRAME_RGB: (np.float32, 3),
+}
+
+
+class RbMaterial(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("diffuse", C.c_float * 3), ("specular", C.c_float * 3),
+                ("emission", C.c_float * 3), ("shininess", C.c_float), ("ior", C.c_float)]
+
+
+class RbSurface(C.Structure):
+    _fields_ = [("n_tris", C.c_uint32), ("material", C.c_uint32), ("pos", C.POINTER(C.c_float)),
+                ("normal", C.POINTER(C.c_float)), ("uv", C.POINTER(C.c_float)), ("tangent", C.POINTER(C.c_float))]
+
+
+class RbSceneDesc(C.Structure):
+    _fields_ = [("n_surfaces", C.c_uint32), ("surfaces", C.POINTER(RbSurface)), ("n_materials", C.c_uint32),
+                ("materials", C.POINTER(RbMaterial))]
+
+
+class RbParams(C.Structure):
+    _fields_ = [("M_Area", C.c_int32), ("M_Brdf", C.c_int32), ("spatialReuseNeighborCount", C.c_int32),
+                ("spatialPassCount", C.c_int32), ("confidenceCap", C.c_int32), ("spatialReuseRadius", C.c_float),
+                ("minNormalSimilarity", C.c_float), ("maxDepthDifference", C.c_float), ("doSpatialReuse", C.c_int32),
+                ("doTemporalReuse", C.c_int32), ("doVisibilityPass", C.c_int32),
+                ("rejectDissimilarNeighbors", C.c_int32), ("spatialWeightCalc", C.c_int32),
+                ("tnearOffset", C.c_float), ("tfarOffset", C.c_float), ("normalOffset", C.c_float),
+                ("bgColor", C.c_float * 3), ("useSkybox", C.c_int32), ("lightSampler", C.c_int32),
+                ("wavefront", C.c_int32)]
+
+
+def default_params(**overrides):
+    """Reference defaults (P/ReSTIRIntegrator.cpp:13-35, P/RenderParams.h:8-17) except useSkybox=0
+    (the sky texture is not part of ABI v1)."""
+    p = RbParams()
+    p.M_Area, p.M_Brdf = 1, 1
+    p.spatialReuseNeighborCount, p.spatialPassCount, p.confidenceCap = 5, 1, 20
+    p.spatialReuseRadius, p.minNormalSimilarity, p.maxDepthDifference = 30.0, 0.85, 0.2
+    p.doSpatialReuse = p.doTemporalReuse = p.doVisibilityPass = p.rejectDissimilarNeighbors = 0
+    p.spatialWeightCalc = SW_CONSTANT
+    p.tnearOffset, p.tfarOffset, p.normalOffset = 0.01, 0.001, 0.001
+    p.bgColor[0] = p.bgColor[1] = p.bgColor[2] = 0.5
+    p.useSkybox = 0
+    p.lightSampler = LS_CDF
+    p.wavefront = 0
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def copy_params(p, **overrides):
+    q = RbParams()
+    C.memmove(C.byref(q), C.byref(p), C.sizeof(RbParams))
+    for k, v in overrides.items():
+        if not hasattr(q, k):
+            raise AttributeError(k)
+        setattr(q, k, v)
+    return q
+
+
+class RbCamera(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("focal_px", C.c_float), ("viewMat", C.c_float * 16),
+                ("invViewMat", C.c_float * 16)]
+
+
+class RbTimings(C.Structure):
+    _fields_ = [("ms_gbuffer", C.c_float), ("ms_initial", C.c_float), ("ms_visibility", C.c_float),
+                ("ms_temporal", C.c_float), ("ms_spatial", C.c_float), ("ms_shade", C.c_float),
+                ("ms_total", C.c_float), ("ms_trace_any", C.c_float), ("rays_closest", C.c_uint64),
+                ("rays_any_as_written", C.c_uint64), ("rays_any_traced", C.c_uint64), ("kernel_launches", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class RbCreateInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint32),
+                ("band_y0", C.c_int32), ("band_y1", C.c_int32), ("collect_timings", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class RbRay(C.Structure):
+    _fields_ = [("org_x", C.c_float), ("org_y", C.c_float), ("org_z", C.c_float), ("tnear", C.c_float),
+                ("dir_x", C.c_float), ("dir_y", C.c_float), ("dir_z", C.c_float), ("time", C.c_float),
+                ("tfar", C.c_float), ("mask", C.c_uint32), ("id", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class RbHit(C.Structure):
+    _fields_ = [("t", C.c_float), ("u", C.c_float), ("v", C.c_float), ("primID", C.c_uint32), ("geomID", C.c_uint32)]
+
+
+class RbSceneStats(C.Structure):
+    _fields_ = [("n_triangles", C.c_uint32), ("n_emissive", C.c_uint32), ("n_bvh_nodes", C.c_uint32),
+                ("bvh_depth", C.c_uint32), ("build_ms", C.c_float), ("total_emissive_area", C.c_float),
+                ("bounds_lo", C.c_float * 3), ("bounds_hi", C.c_float * 3)]
+
+
+RAY_DTYPE = np.dtype([("org", np.float32, 3), ("tnear", np.float32), ("dir", np.float32, 3), ("time", np.float32),
+                      ("tfar", np.float32), ("mask", np.uint32), ("id", np.uint32), ("flags", np.uint32)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("primID", np.uint32),
+                      ("geomID", np.uint32)])
+assert RAY_DTYPE.itemsize == C.sizeof(RbRay) == 48
+assert HIT_DTYPE.itemsize == C.sizeof(RbHit) == 20
+
+# Every symbol include/restir_b200.h declares (checked by tests/test_abi.py).
+EXPORTED_SYMBOLS = [
+    "rb_abi_version", "rb_last_error", "rb_default_params", "rb_create", "rb_destroy", "rb_upload_scene",
+    "rb_set_params", "rb_render_frame", "rb_render_frame_device", "rb_readback", "rb_synchronize", "rb_trace_closest",
+    "rb_trace_occluded", "rb_trace_closest_device", "rb_trace_occluded_device", "rb_scene_stats", "rb_comm_init",
+    "rb_comm_unique_id", "rb_halo_bytes", "rb_halo_export", "rb_halo_import",
+]
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class SceneArrays:
+    """Host-side scene in the layout ModelLoader::loadScene hands Embree (P/ModelLoader.cpp:227-318):
+    a list of surfaces, each a non-indexed triangle soup with per-vertex normals and one material."""
+
+    def __init__(self):
+        self.materials = []  # dicts: type, diffuse, specular, emission, shininess, ior
+        self.surfaces = []   # (pos[n,3,3] f32, normal[n,3,3] f32, material_index)
+        self.meta = {}
+
+    def add_material(self, type=MAT_PHONG, diffuse=(0.5, 0.5, 0.5), specular=(0.0, 0.0, 0.0), emission=(0, 0, 0),
+                     shininess=10.0, ior=1.0):
+        self.materials.append(dict(type=type, diffuse=tuple(map(float, diffuse)), specular=tuple(map(float, specular)),
+                                   emission=tuple(map(float, emission)), shininess=float(shininess), ior=float(ior)))
+        return len(self.materials) - 1
+
+    def add_surface(self, pos, normal, material):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3, 3)
+        normal = np.ascontiguousarray(normal, dtype=np.float32).reshape(-1, 3, 3)
+        assert pos.shape == normal.shape and pos.shape[0] > 0
+        assert 0 <= material < len(self.materials)
+        self.surfaces.append((pos, normal, int(material)))
+        return len(self.surfaces) - 1
+
+    @property
+    def n_triangles(self):
+        return sum(s[0].shape[0] for s in self.surfaces)
+
+    @property
+    def n_emissive(self):
+        return sum(s[0].shape[0] for s in self.surfaces if sum(self.materials[s[2]]["emission"]) > 0)
+
+    def desc(self):
+        """Returns (RbSceneDesc, keepalive) — keepalive owns the ctypes arrays."""
+        mats = (RbMaterial * len(self.materials))()
+        for i, m in enumerate(self.materials):
+            mats[i].type = m["type"]
+            for c in range(3):
+                mats[i].diffuse[c] = m["diffuse"][c]
+                mats[i].specular[c] = m["specular"][c]
+                mats[i].emission[c] = m["emission"][c]
+            mats[i].shininess = m["shininess"]
+            mats[i].ior = m["ior"]
+        surfs = (RbSurface * len(self.surfaces))()
+        for i, (pos, nrm, mat) in enumerate(self.surfaces):
+            surfs[i].n_tris = pos.shape[0]
+            surfs[i].material = mat
+            surfs[i].pos = fptr(pos)
+            surfs[i].normal = fptr(nrm)
+            surfs[i].uv = None
+            surfs[i].tangent = None
+        d = RbSceneDesc()
+        d.n_surfaces = len(self.surfaces)
+        d.surfaces = surfs
+        d.n_materials = len(self.materials)
+        d.materials = mats
+        return d, (mats, surfs, self)
