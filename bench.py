@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — ReSTIR DI frames/s (and Mrays/s) at 1080p on the 1M-triangle / 10k-emitter synthetic scene.
+
+One "step" = one frame of the hot path (G-buffer, initial RIS A=32 B=1, visibility, temporal, spatial
+k=5, shade) with an orbiting camera. N GPUs = N horizontal image bands (weak in per-GPU image size only
+when N divides the workload; here the frame is fixed, so scaling is STRONG: same 1080p frame, N bands).
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (CUDA through the C ABI)
+  python bench.py --impl reference --steps K --warmup W   # the reference algorithm on the host cores
+                                                         # (oracle port; the Embree binary is Windows-only)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WIDTH, HEIGHT = 1920, 1080
+WORKLOAD = "configs[1]: synthetic 1M-triangle room, 10k emissive triangles, 1920x1080, ReSTIR DI A=32 B=1, " \
+           "visibility pass, temporal + 1 spatial pass k=5 r=30, alias light sampler, orbit camera 0.5 deg/frame"
+# algorithmic bytes per pixel per pass (reference record sizes R=48, G=69)
+PASS_BYTES = dict(gbuffer=69, initial=117, visibility=64, temporal=306, spatial=465, shade=129)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device=0):
+        self.samples, self.proc, self.device = [], None, device
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bench_params():
+    from restir_embree_b200 import abi
+    return abi.default_params(M_Area=32, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1,
+                              spatialReuseNeighborCount=5, spatialPassCount=1, spatialReuseRadius=30.0,
+                              lightSampler=abi.LS_ALIAS)
+
+
+def camera_at(scene, t):
+    from restir_embree_b200 import Camera, scenes
+    c = scene.meta["center"]
+    return Camera(WIDTH, HEIGHT, 55, scenes.orbit_position(c, t), c)
+
+
+def cpu_reference(steps, warmup, rows=32):
+    """The reference algorithm as written (Phong I_M re-evaluated on every BRDF call, one thread per image
+    row via OpenMP like P/simpleguidx11.cpp:369-452) on a bounded sample: a band of `rows` rows of the same
+    1080p frames. Returned fps is scaled to the full frame."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from restir_embree_b200 import scenes
+    scene = scenes.scene_config("1m")
+    o = ob.Oracle(WIDTH, HEIGHT, seed=123, tracer=ob.TRACER_BVH2, cache_iim=0)
+    o.upload_scene(scene)
+    o.set_params(bench_params())
+    y0 = HEIGHT // 2 - rows // 2
+    o.set_band(y0, y0 + rows)
+    times = []
+    rays = []
+    for f in range(warmup + steps):
+        o.counters()
+        _, t = o.render_frame(camera_at(scene, f), f, want_times=True)
+        c = o.counters()
+        if f >= warmup:
+            times.append(t[7])
+            rays.append(c["closest"] + c["any_as_written"])
+    sec = float(np.median(times))
+    fps = 1.0 / (sec * HEIGHT / rows)
+    cores = os.cpu_count()
+    return dict(value=fps, unit="frames/s", cores=cores, kind="port",
+                sample=f"{rows} of {HEIGHT} rows of the same 1080p frames (median of {steps} frames, scaled x{HEIGHT / rows:.1f}); "
+                       f"reference algorithm as written, substitute CPU BVH2 (Embree 3.13.5 binary unavailable), OpenMP {cores} threads",
+                ms_per_band_frame=sec * 1e3, mrays_s=float(np.median(rays)) / sec / 1e6)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    cb = cpu_reference(args.steps, args.warmup)
+    line = {"metric": "frames/sec at 1080p ReSTIR DI", "value": cb["value"], "unit": "frames/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from restir_embree_b200 import abi, scenes
+    from restir_embree_b200.renderer import Renderer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    scene = scenes.scene_config("1m")
+    rows = (HEIGHT + world - 1) // world
+    band = (rank * rows, min(HEIGHT, (rank + 1) * rows))
+    r = Renderer(WIDTH, HEIGHT, device=local, seed=123, band=band, collect_timings=True)
+    stats = r.upload_scene(scene)
+    p = bench_params()
+    r.set_params(p)
+    pinned = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32, pin_memory=True)
+    out = pinned.numpy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    frame = 0
+    # ---- device-resident throughput ("value") ---------------------------------------------------
+    for _ in range(args.warmup):
+        r.render_frame_device(camera_at(scene, frame), frame)
+        frame += 1
+    r.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    r.timer_begin()
+    for _ in range(args.steps):
+        r.render_frame_device(camera_at(scene, frame), frame)
+        frame += 1
+    ms = r.timer_end()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- per-pass device times + ray counts over further frames (same stream, CUDA events) -------
+    per = {k: [] for k in ("gbuffer", "initial", "visibility", "temporal", "spatial", "shade", "total")}
+    rays = {"closest": [], "any_w": [], "any_t": []}
+    launches = 0
+    for _ in range(max(3, min(args.steps, 10))):
+        t = r.render_frame_device(camera_at(scene, frame), frame, want_timings=True)
+        frame += 1
+        for k in per:
+            per[k].append(t["ms_" + k])
+        rays["closest"].append(t["rays_closest"])
+        rays["any_w"].append(t["rays_any_as_written"])
+        rays["any_t"].append(t["rays_any_traced"])
+        launches = t["kernel_launches"]
+    # ---- end to end through the public call with a HOST frame buffer ---------------------------------
+    for _ in range(2):
+        r.render_frame(camera_at(scene, frame), frame, out=out)
+        frame += 1
+    barrier()
+    t0 = time.perf_counter()
+    r.timer_begin()
+    for _ in range(args.steps):
+        r.render_frame(camera_at(scene, frame), frame, out=out)  # H2D: camera; D2H: the band of frame_data
+        frame += 1
+    ms_e2e_dev = r.timer_end()
+    barrier()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(ms_e2e_dev, wall_e2e)
+
+    def maxr(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def sumr(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return float(tt.item())
+
+    ms = maxr(ms)
+    ms_e2e = maxr(ms_e2e)
+    med = {k: float(np.median(v)) for k, v in per.items()}
+    n_closest = sumr(float(np.median(rays["closest"])))
+    n_any_w = sumr(float(np.median(rays["any_w"])))
+    n_any_t = sumr(float(np.median(rays["any_t"])))
+    if rank != 0:
+        return
+    ms_step = ms / args.steps
+    fps = 1e3 / ms_step
+    hbm, hbm_src = peaks()
+    band_px = WIDTH * (band[1] - band[0])
+    dom = max(("gbuffer", "initial", "visibility", "temporal", "spatial", "shade"), key=lambda k: med[k])
+    achieved = PASS_BYTES[dom] * band_px / (med[dom] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+            "algorithmic_bytes_per_px": PASS_BYTES[dom],
+            "note": "pass kernels trace their shadow rays inline, so the dominant kernel is traversal-(latency-)bound, "
+                    "not a streaming pass; see traversal{}",
+            "share_of_frame": med[dom] / max(med["total"], 1e-9),
+            "per_pass_ms": med,
+            "per_pass_gbs": {k: PASS_BYTES[k] * band_px / (med[k] * 1e-3) / 1e9 for k in PASS_BYTES if med[k] > 0}}
+    frame_s = med["total"] * 1e-3
+    trav = {"mrays_s_as_written": (n_closest + n_any_w) / frame_s / 1e6 / max(world, 1) * world,
+            "mrays_s_traced": (n_closest + n_any_t) / frame_s / 1e6,
+            "closest_per_frame": n_closest, "any_as_written_per_frame": n_any_w, "any_traced_per_frame": n_any_t}
+    cb = cpu_reference(3, 1) if (world == 1 and not args.no_cpu) else None
+    line = {"metric": "frames/sec at 1080p ReSTIR DI", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2_note": "per-frame working set (G-buffer + reservoirs 0.5 GB, BVH 0.1 GB) "
+                       "exceeds the 126 MB L2; camera moves every frame", "bands": world,
+                       "scene": {k: stats[k] for k in ("n_triangles", "n_emissive", "n_bvh_nodes", "bvh_depth", "build_ms")}},
+            "roofline": roof, "traversal": trav, "cpu_baseline": cb, "clocks": clocks,
+            "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "frames/s", "h2d_bytes_per_step": 144,
+                    "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
+                    "note": "rb_render_frame with a pinned host frame_data buffer; scene resident (uploaded once like the reference)"},
+            "gpu_launches": int(launches) * args.steps}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

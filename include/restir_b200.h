@@ -235,6 +235,12 @@ int rb_render_frame_device(RbHandle h, const RbCamera* cam, uint32_t frame_idx,
 int rb_readback(RbHandle h, int buffer_id /*RbBufferId*/, void* dst, size_t bytes);
 int rb_synchronize(RbHandle h);
 
+/* Device-side stopwatch on the handle's stream (CUDA events): the per-frame timers of the
+ * reference (P/simpleguidx11.h:120-127) cover one frame; these bracket any number of frames
+ * without a host synchronisation in between. rb_timer_end waits for the stream. */
+int rb_timer_begin(RbHandle h);
+int rb_timer_end(RbHandle h, float* ms_out);
+
 /* replaces Intersection::intersectEmbree's rtcIntersect1 (P/Intersection.h:63-83)
  * and Intersection::testOcclusion's rtcOccluded1 (:43-60); host pointers. */
 int rb_trace_closest(RbHandle h, const RbRay* rays, RbHit* hits, uint32_t n);

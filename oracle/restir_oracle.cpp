@@ -795,7 +795,8 @@ struct Oracle {
       e.shininess = m.shininess;
       e.geomID = T.geom;
       e.primID = T.prim;
-      if (cache_iim && !emissive(e.emission)) e.invIM = inv_I_M(e, gBuffer.cameraPosWS);
+      if (cache_iim && !emissive(e.emission) && (e.materialType == RB_MAT_PHONG || e.materialType == RB_MAT_DIELECTRIC))
+        e.invIM = inv_I_M(e, gBuffer.cameraPosWS);
     } else {
       e.emission = {P.bgColor[0], P.bgColor[1], P.bgColor[2]};  // useSkybox == 0 in ABI v1
     }

@@ -1,0 +1,400 @@
+// rb_build.cuh — GPU BVH construction (replaces rtcCommitScene, P/Scene.cpp:15).
+//
+//   1. bounds_body   : triangle boxes (padded) + scene bounds (atomic min/max)
+//   2. morton_body   : 63-bit Morton code of the box centre
+//   3. radix sort of (code, triangle) — device: cub::DeviceRadixSort; emulation: std::stable_sort
+//   4. karras_body   : binary radix tree over the sorted codes (Karras 2012), one thread per internal node
+//   5. fit_body      : bottom-up box fit, one thread per leaf, second arrival at a node proceeds
+//   6. collapse_body : top-down, level-synchronous collapse of the binary tree into 8-wide nodes:
+//                      open the child with the largest surface area until 8 children; subtrees with
+//                      <= RB_LEAF_MAX triangles become leaf children; choose child slots for octant
+//                      ordering; quantise child boxes to 8 bits outward; emit leaf triangles in node order
+// Every body is a __host__ __device__ function of a thread index so the emulation harness
+// in tests/emu can run the identical code sequentially on the CPU.
+#ifndef RB_BUILD_CUH_
+#define RB_BUILD_CUH_
+
+#include "rb_scene.cuh"
+
+namespace rb {
+
+RB_HD int atomic_add_i(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  int o = *p;
+  *p += v;
+  return o;
+#endif
+}
+RB_HD void atomic_min_i(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+  atomicMin(p, v);
+#else
+  if (v < *p) *p = v;
+#endif
+}
+RB_HD void atomic_max_i(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+  atomicMax(p, v);
+#else
+  if (v > *p) *p = v;
+#endif
+}
+RB_HD void fence_() {
+#if defined(__CUDA_ARCH__)
+  __threadfence();
+#endif
+}
+// monotone float <-> int map for atomic min/max
+RB_HD int f2ord(float f) {
+  int k = (int)f2u(f);
+  return k < 0 ? (k ^ 0x7FFFFFFF) : k;
+}
+RB_HD float ord2f(int k) { return u2f((uint32_t)(k < 0 ? (k ^ 0x7FFFFFFF) : k)); }
+
+RB_HD int clz32_(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+RB_HD int clz64_(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return x ? __builtin_clzll(x) : 64;
+#endif
+}
+
+struct BuildCtx {
+  uint32_t n;            // triangles
+  const float* tri_pos;  // [n][9] scene order
+  float pad;             // box padding (absolute)
+  int* scene_bounds;     // [6] ordered ints: lo.xyz (min), hi.xyz (max)
+  // per triangle, scene order
+  F4* tbox_lo;
+  F4* tbox_hi;
+  // sorted
+  uint64_t* morton;
+  uint32_t* order;  // sorted position -> scene triangle
+  // binary radix tree: internal nodes [0, n-2]; child refs: >= 0 internal, < 0 leaf ~sortedIndex
+  int* left;
+  int* right;
+  int* parent;       // [n-1] parent of internal (root: -1)
+  int* leaf_parent;  // [n]
+  int* range_lo;     // [n-1] first sorted leaf covered
+  int* range_hi;     // [n-1] last sorted leaf covered
+  F4* ibox_lo;       // [n-1]
+  F4* ibox_hi;
+  int* visit;  // [n-1] arrival counters
+  // collapse
+  F4* node8;       // [5 * max_nodes]
+  F4* tri_isect;   // [3 * n]
+  int* counters;   // [0] nodes allocated, [1] leaf triangles emitted, [2] next-queue length
+  const int* q_in;  // pairs (binary node, out node8 index)
+  int* q_out;
+  int q_in_len;
+};
+
+RB_HD void bounds_body(const BuildCtx& c, uint32_t i) {
+  const float* p = c.tri_pos + 9 * (size_t)i;
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = fminf(p[a], fminf(p[3 + a], p[6 + a])) - c.pad;
+    hi[a] = fmaxf(p[a], fmaxf(p[3 + a], p[6 + a])) + c.pad;
+  }
+  c.tbox_lo[i] = F4{lo[0], lo[1], lo[2], 0};
+  c.tbox_hi[i] = F4{hi[0], hi[1], hi[2], 0};
+  for (int a = 0; a < 3; ++a) {
+    atomic_min_i(c.scene_bounds + a, f2ord(lo[a]));
+    atomic_max_i(c.scene_bounds + 3 + a, f2ord(hi[a]));
+  }
+}
+
+RB_HD uint64_t spread21(uint32_t v) {  // 21 bits -> every third bit
+  uint64_t x = v & 0x1FFFFFu;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+RB_HD void morton_body(const BuildCtx& c, uint32_t i) {
+  const float blo[3] = {ord2f(c.scene_bounds[0]), ord2f(c.scene_bounds[1]), ord2f(c.scene_bounds[2])};
+  const float bhi[3] = {ord2f(c.scene_bounds[3]), ord2f(c.scene_bounds[4]), ord2f(c.scene_bounds[5])};
+  const F4 lo = c.tbox_lo[i], hi = c.tbox_hi[i];
+  const float ctr[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+  uint32_t q[3];
+  for (int a = 0; a < 3; ++a) {
+    float ext = bhi[a] - blo[a];
+    float u = ext > 0 ? (ctr[a] - blo[a]) / ext : 0.0f;
+    u = fminf(fmaxf(u, 0.0f), 1.0f);
+    float s = u * 2097151.0f;
+    q[a] = (uint32_t)s;
+  }
+  c.morton[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+  c.order[i] = i;
+}
+
+RB_HD int karras_delta(const BuildCtx& c, int i, int j) {
+  if (j < 0 || j >= (int)c.n) return -1;
+  const uint64_t a = c.morton[i], b = c.morton[j];
+  if (a == b) return 64 + clz32_((uint32_t)i ^ (uint32_t)j);
+  return clz64_(a ^ b);
+}
+RB_HD void karras_body(const BuildCtx& c, uint32_t ii) {
+  const int i = (int)ii;
+  const int d = (karras_delta(c, i, i + 1) - karras_delta(c, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = karras_delta(c, i, i - d);
+  int lmax = 2;
+  while (karras_delta(c, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2)
+    if (karras_delta(c, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = karras_delta(c, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (karras_delta(c, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + (d < 0 ? d : 0);
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  int L, R;
+  if (lo == gamma) {
+    L = ~gamma;
+    c.leaf_parent[gamma] = i;
+  } else {
+    L = gamma;
+    c.parent[gamma] = i;
+  }
+  if (hi == gamma + 1) {
+    R = ~(gamma + 1);
+    c.leaf_parent[gamma + 1] = i;
+  } else {
+    R = gamma + 1;
+    c.parent[gamma + 1] = i;
+  }
+  c.left[i] = L;
+  c.right[i] = R;
+  c.range_lo[i] = lo;
+  c.range_hi[i] = hi;
+  if (i == 0) c.parent[0] = -1;
+}
+
+RB_HD void child_box(const BuildCtx& c, int ref, F4* lo, F4* hi) {
+  if (ref < 0) {
+    const uint32_t t = c.order[~ref];
+    *lo = c.tbox_lo[t];
+    *hi = c.tbox_hi[t];
+  } else {
+    *lo = c.ibox_lo[ref];
+    *hi = c.ibox_hi[ref];
+  }
+}
+RB_HD void fit_body(const BuildCtx& c, uint32_t leaf) {
+  int node = c.leaf_parent[leaf];
+  while (node >= 0) {
+    fence_();
+    if (atomic_add_i(c.visit + node, 1) == 0) return;  // first arrival waits for the sibling subtree
+    fence_();
+    F4 alo, ahi, blo, bhi;
+#if defined(__CUDA_ARCH__)
+    // children boxes were written by other threads: bypass L1
+    const int L = c.left[node], R = c.right[node];
+    if (L < 0) {
+      const uint32_t t = c.order[~L];
+      alo = c.tbox_lo[t], ahi = c.tbox_hi[t];
+    } else {
+      float4 x = __ldcg(reinterpret_cast<const float4*>(c.ibox_lo + L)), y = __ldcg(reinterpret_cast<const float4*>(c.ibox_hi + L));
+      alo = F4{x.x, x.y, x.z, x.w}, ahi = F4{y.x, y.y, y.z, y.w};
+    }
+    if (R < 0) {
+      const uint32_t t = c.order[~R];
+      blo = c.tbox_lo[t], bhi = c.tbox_hi[t];
+    } else {
+      float4 x = __ldcg(reinterpret_cast<const float4*>(c.ibox_lo + R)), y = __ldcg(reinterpret_cast<const float4*>(c.ibox_hi + R));
+      blo = F4{x.x, x.y, x.z, x.w}, bhi = F4{y.x, y.y, y.z, y.w};
+    }
+#else
+    child_box(c, c.left[node], &alo, &ahi);
+    child_box(c, c.right[node], &blo, &bhi);
+#endif
+    c.ibox_lo[node] = F4{fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0};
+    c.ibox_hi[node] = F4{fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0};
+    node = c.parent[node];
+  }
+}
+
+RB_HD int ref_count(const BuildCtx& c, int ref) { return ref < 0 ? 1 : (c.range_hi[ref] - c.range_lo[ref] + 1); }
+RB_HD int ref_first(const BuildCtx& c, int ref) { return ref < 0 ? ~ref : c.range_lo[ref]; }
+RB_HD float box_area(const F4& lo, const F4& hi) {
+  const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+// biased exponent e such that 255 * 2^(e-127) >= extent
+RB_HD uint32_t grid_exponent(float extent) {
+  if (!(extent > 0.0f)) return 1u;
+  const float step = extent / 255.0f;
+  uint32_t bits = f2u(step);
+  uint32_t e = (bits >> 23) & 0xFFu;
+  if (bits & 0x7FFFFFu) e += 1;  // round the step up to a power of two
+  if (e < 1u) e = 1u;
+  if (e > 254u) e = 254u;
+  // guard against the rounding of extent/255
+  while (e < 254u && u2f(e << 23) * 255.0f < extent) e += 1;
+  return e;
+}
+RB_HD void write_tri(const BuildCtx& c, uint32_t dst, uint32_t tri) {
+  const float* p = c.tri_pos + 9 * (size_t)tri;
+  const float e1x = p[3] - p[0], e1y = p[4] - p[1], e1z = p[5] - p[2];
+  const float e2x = p[6] - p[0], e2y = p[7] - p[1], e2z = p[8] - p[2];
+  F4* o = c.tri_isect + 3 * (size_t)dst;
+  o[0] = F4{p[0], p[1], p[2], e1x};
+  o[1] = F4{e1y, e1z, e2x, e2y};
+  o[2] = F4{e2z, u2f(tri), 0, 0};
+}
+
+RB_HD uint32_t pack4(const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); }
+
+// Emit one Node8 at out_index from the children `refs` (binary-tree refs), whose union box is lo..hi.
+RB_HD void emit_node8(const BuildCtx& c, int out_index, const int* refs, int n_items, const F4& nlo, const F4& nhi) {
+  F4 clo[8], chi[8];
+  bool internal[8];
+  int n_int = 0, n_leaf_tris = 0;
+  for (int k = 0; k < n_items; ++k) {
+    child_box(c, refs[k], &clo[k], &chi[k]);
+    internal[k] = refs[k] >= 0 && ref_count(c, refs[k]) > RB_LEAF_MAX;
+    if (internal[k])
+      n_int++;
+    else
+      n_leaf_tris += ref_count(c, refs[k]);
+  }
+  // slot assignment: greedily give each child the free slot whose octant direction best matches
+  // its offset from the node centre, so that (slot ^ ray octant) sorts children front to back
+  const float cx = 0.5f * (nlo.x + nhi.x), cy = 0.5f * (nlo.y + nhi.y), cz = 0.5f * (nlo.z + nhi.z);
+  int slot_of[8];
+  int child_in_slot[8];
+  for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
+  for (int k = 0; k < n_items; ++k) slot_of[k] = -1;
+  for (int round = 0; round < n_items; ++round) {
+    float bestc = -FLT_MAX;
+    int bk = -1, bs = -1;
+    for (int k = 0; k < n_items; ++k) {
+      if (slot_of[k] >= 0) continue;
+      const float ox = 0.5f * (clo[k].x + chi[k].x) - cx, oy = 0.5f * (clo[k].y + chi[k].y) - cy,
+                  oz = 0.5f * (clo[k].z + chi[k].z) - cz;
+      for (int s = 0; s < 8; ++s) {
+        if (child_in_slot[s] >= 0) continue;
+        const float cost = ((s & 1) ? ox : -ox) + ((s & 2) ? oy : -oy) + ((s & 4) ? oz : -oz);
+        if (cost > bestc) {
+          bestc = cost;
+          bk = k;
+          bs = s;
+        }
+      }
+    }
+    slot_of[bk] = bs;
+    child_in_slot[bs] = bk;
+  }
+  const int child_base = n_int ? atomic_add_i(c.counters + 0, n_int) : 0;
+  const int tri_base = n_leaf_tris ? atomic_add_i(c.counters + 1, n_leaf_tris) : 0;
+  const uint32_t ex = grid_exponent(nhi.x - nlo.x), ey = grid_exponent(nhi.y - nlo.y), ez = grid_exponent(nhi.z - nlo.z);
+  const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
+  uint32_t imask = 0;
+  uint32_t meta[8], qlo[3][8], qhi[3][8];
+  int int_cursor = 0, tri_cursor = 0;
+  int q_base = 0;
+  if (n_int) q_base = atomic_add_i(c.counters + 2, n_int);
+  for (int s = 0; s < 8; ++s) {
+    meta[s] = 0;
+    for (int a = 0; a < 3; ++a) qlo[a][s] = qhi[a][s] = 0;
+    const int k = child_in_slot[s];
+    if (k < 0) continue;
+    const float l3[3] = {clo[k].x, clo[k].y, clo[k].z}, h3[3] = {chi[k].x, chi[k].y, chi[k].z};
+    const float o3[3] = {nlo.x, nlo.y, nlo.z}, s3[3] = {sx, sy, sz};
+    for (int a = 0; a < 3; ++a) {
+      float fl = floorf((l3[a] - o3[a]) / s3[a]);
+      float fh = ceilf((h3[a] - o3[a]) / s3[a]);
+      // outward rounding must survive the subtraction's own rounding
+      while (fl > 0.0f && o3[a] + fl * s3[a] > l3[a]) fl -= 1.0f;
+      while (fh < 255.0f && o3[a] + fh * s3[a] < h3[a]) fh += 1.0f;
+      fl = fminf(fmaxf(fl, 0.0f), 255.0f);
+      fh = fminf(fmaxf(fh, 0.0f), 255.0f);
+      qlo[a][s] = (uint32_t)fl;
+      qhi[a][s] = (uint32_t)fh;
+    }
+    if (internal[k]) {
+      imask |= 1u << s;
+      meta[s] = (1u << 5) | (24u + (uint32_t)s);
+      // children of this node occupy consecutive node8 indices in slot order
+      c.q_out[2 * (q_base + int_cursor) + 0] = refs[k];
+      c.q_out[2 * (q_base + int_cursor) + 1] = child_base + int_cursor;
+      int_cursor++;
+    } else {
+      const int cnt = ref_count(c, refs[k]), first = ref_first(c, refs[k]);
+      meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)tri_cursor;
+      for (int t = 0; t < cnt; ++t) write_tri(c, (uint32_t)(tri_base + tri_cursor + t), c.order[first + t]);
+      tri_cursor += cnt;
+    }
+  }
+  F4* o = c.node8 + 5 * (size_t)out_index;
+  o[0] = F4{nlo.x, nlo.y, nlo.z, u2f(ex | (ey << 8) | (ez << 16) | (imask << 24))};
+  o[1] = F4{u2f((uint32_t)child_base), u2f((uint32_t)tri_base), u2f(pack4(meta)), u2f(pack4(meta + 4))};
+  o[2] = F4{u2f(pack4(qlo[0])), u2f(pack4(qlo[0] + 4)), u2f(pack4(qlo[1])), u2f(pack4(qlo[1] + 4))};
+  o[3] = F4{u2f(pack4(qlo[2])), u2f(pack4(qlo[2] + 4)), u2f(pack4(qhi[0])), u2f(pack4(qhi[0] + 4))};
+  o[4] = F4{u2f(pack4(qhi[1])), u2f(pack4(qhi[1] + 4)), u2f(pack4(qhi[2])), u2f(pack4(qhi[2] + 4))};
+}
+
+RB_HD void collapse_body(const BuildCtx& c, uint32_t w) {
+  const int bnode = c.q_in[2 * w], out_index = c.q_in[2 * w + 1];
+  int refs[8];
+  int n_items = 2;
+  refs[0] = c.left[bnode];
+  refs[1] = c.right[bnode];
+  while (n_items < 8) {
+    float best = -1.0f;
+    int bk = -1;
+    for (int k = 0; k < n_items; ++k) {
+      if (refs[k] < 0 || ref_count(c, refs[k]) <= RB_LEAF_MAX) continue;
+      const float a = box_area(c.ibox_lo[refs[k]], c.ibox_hi[refs[k]]);
+      if (a > best) {
+        best = a;
+        bk = k;
+      }
+    }
+    if (bk < 0) break;
+    const int r = refs[bk];
+    refs[bk] = c.left[r];
+    refs[n_items++] = c.right[r];
+  }
+  emit_node8(c, out_index, refs, n_items, c.ibox_lo[bnode], c.ibox_hi[bnode]);
+}
+
+// Scenes with <= RB_LEAF_MAX triangles: one node, one leaf child holding them all (sorted order).
+RB_HD void tiny_root_body(const BuildCtx& c) {
+  F4 lo = c.tbox_lo[c.order[0]], hi = c.tbox_hi[c.order[0]];
+  for (uint32_t i = 1; i < c.n; ++i) {
+    const F4 a = c.tbox_lo[c.order[i]], b = c.tbox_hi[c.order[i]];
+    lo = F4{fminf(lo.x, a.x), fminf(lo.y, a.y), fminf(lo.z, a.z), 0};
+    hi = F4{fmaxf(hi.x, b.x), fmaxf(hi.y, b.y), fmaxf(hi.z, b.z), 0};
+  }
+  const uint32_t ex = grid_exponent(hi.x - lo.x), ey = grid_exponent(hi.y - lo.y), ez = grid_exponent(hi.z - lo.z);
+  for (uint32_t i = 0; i < c.n; ++i) write_tri(c, i, c.order[i]);
+  const uint32_t meta0 = (((1u << c.n) - 1u) << 5) | 0u;
+  F4* o = c.node8;
+  o[0] = F4{lo.x, lo.y, lo.z, u2f(ex | (ey << 8) | (ez << 16))};
+  o[1] = F4{u2f(0u), u2f(0u), u2f(meta0), u2f(0u)};
+  o[2] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
+  o[3] = F4{u2f(0u), u2f(0u), u2f(255u), u2f(0u)};
+  o[4] = F4{u2f(255u), u2f(0u), u2f(255u), u2f(0u)};
+  c.counters[0] = 1;
+  c.counters[1] = (int)c.n;
+}
+
+}  // namespace rb
+#endif

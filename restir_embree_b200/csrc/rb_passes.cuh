@@ -1,0 +1,651 @@
+// rb_passes.cuh — per-pixel logic of the six ReSTIR passes (the body of
+// SimpleGuiDX11::produceRestir's loops, P/simpleguidx11.cpp:359-487, and the
+// ReSTIRIntegrator statics they call, P/ReSTIRIntegrator.cpp:89-732).
+//
+// GPU-first restructuring relative to the reference, all result-preserving:
+//   * 1/I_M (Phong normalisation: incomplete beta + 2 lgamma + pow,
+//     P/MaterialPhong.cpp:228-248) is evaluated once per pixel in the G-buffer
+//     pass and stored, instead of on every BRDF evaluation (it depends only on
+//     the element and its own frame's camera at every call site).
+//   * identical p-hat evaluations inside a pass are computed once (temporal 7 -> 4,
+//     spatial k+2 -> k+1, initial M+1 -> M); shadow rays whose unshadowed
+//     contribution is exactly zero are not traced (x*V is x either way).
+//   * visibility is obtained through a policy object so the same code runs with
+//     inline traversal, or as the generate / resolve halves of the wavefront split.
+#ifndef RB_PASSES_CUH_
+#define RB_PASSES_CUH_
+
+#include "rb_scene.cuh"
+
+namespace rb {
+
+#define RB_MAX_NEIGHBORS 32
+
+struct FrameCtx {
+  int width, height;
+  int y0, y1;  // rows rendered by this handle (band)
+  SceneDev sc;
+  RbParams P;
+  CamState cam, prevCam;
+  GBufPlanes G, Gprev;
+  ResPlanes Rread, Rwrite, Rlast;
+  float* frame;  // w*h*3
+  uint32_t frame_key;
+  int spatial_iter;
+  unsigned long long* counters;  // [0] closest, [1] any-hit as written, [2] any-hit traced
+};
+
+struct Cnt {
+  uint32_t closest, anyW, anyT;
+};
+
+// ---- visibility policies ----------------------------------------------------------
+struct InlineVis {
+  const FrameCtx* fc;
+  RB_HD bool visible(int /*slot*/, const V3& from, const V3& to) const {
+    return !test_occlusion(fc->sc, from, to, fc->P.tnearOffset, fc->P.tfarOffset);
+  }
+};
+
+// ---- Phong / Lambert statics (P/MaterialPhong.cpp:122-248, P/MaterialLambert.cpp:33-53,
+//      P/Distribution.h) ------------------------------------------------------------
+RB_HD float max_component(const V3& v) { return gmax(gmax(v.x, v.y), v.z); }  // P/utils.h:61-63
+
+RB_HD_NOINLINE float calc_I_M(float nDotV, float n) {  // MaterialPhong::calc_I_M, :228-244
+  float costerm = nDotV;
+  float sinterm_sq = 1.0f - costerm * costerm;
+  float halfn = 0.5f * n;
+  float negterm = costerm;
+  sinterm_sq = gclamp(sinterm_sq, 0.0f, 1.0f);
+  if (n >= 1e-18f) negterm *= halfn * dm::ibetaf_(halfn, 0.5f, sinterm_sq);
+  float gq = dm::expf_(dm::lgammaf_(halfn + 0.5f) - dm::lgammaf_(halfn + 1.0f));  // gamma_quot, :224-226
+  return (RB_TWO_PI * costerm + RB_ROOT_PI * gq * (dm::powf_(sinterm_sq, halfn) - negterm)) / (n + 2.0f);
+}
+RB_HD float inv_I_M(const V3& pos, const V3& normal, float shininess, const V3& camPos) {
+  const V3 V = normalize(camPos - pos);
+  float nDotV = dot(V, normal);
+  return 1.0f / calc_I_M(nDotV, shininess);
+}
+RB_HD bool uses_phong_brdf(uint32_t t) { return t == RB_MAT_PHONG || t == RB_MAT_DIELECTRIC; }
+
+// reflection direction omega_r = normalize(reflect(omega_o, n)), omega_o = normalize(pos - cam)
+// (evalBRDF spells it reflect(-V, n) with V = normalize(cam - pos): the same bits)
+RB_HD V3 omega_r_of(const GElem& g, const V3& camPos) {
+  const V3 omega_o = normalize(g.pos - camPos);
+  return normalize(reflect(omega_o, g.normal));
+}
+// getMaterialBRDFEvalFunc dispatch, P/ReSTIRIntegrator.h:32-41
+RB_HD V3 brdf_eval(const GElem& g, const V3& camPos, const V3& omega_i) {
+  V3 f_r = g.diffuse * RB_ONE_OVER_PI;
+  if (uses_phong_brdf(g.matType)) {
+    const V3 V = normalize(camPos - g.pos);
+    const V3 omega_r = normalize(reflect(-V, g.normal));
+    f_r = f_r + g.specular * g.invIM * dm::powf_(gmax(dot(omega_i, omega_r), 0.0f), g.shininess);
+  }
+  return f_r;
+}
+RB_HD float cosw_pdf(const V3& n, const V3& wi) { return gmax(dot(n, wi), 0.0f) * RB_ONE_OVER_PI; }
+RB_HD float lobe_pdf(const V3& wi, const V3& wr, float gamma) {
+  return (gamma + 1.0f) * RB_ONE_OVER_TWO_PI * dm::powf_(gmax(0.0f, dot(wi, wr)), gamma);
+}
+// MaterialPhong::evalPdf, :150-172 (getMaterialPDFEvalFunc always returns it, P/ReSTIRIntegrator.h:54-59)
+RB_HD float phong_pdf(const GElem& g, const V3& camPos, const V3& wi) {
+  float maxDiffuse = max_component(g.diffuse);
+  float maxSpecular = max_component(g.specular);
+  float pdfFactor = maxDiffuse / (maxDiffuse + maxSpecular);
+  float pdf = cosw_pdf(g.normal, wi) * pdfFactor;
+  const V3 wr = omega_r_of(g, camPos);
+  pdf += lobe_pdf(wi, wr, g.shininess) * (1.0f - pdfFactor);
+  return pdf;
+}
+RB_HD V3 orthogonal(const V3& v) {  // Utils::orthogonal, P/utils.cpp:204-207
+  return fabsf_(v.x) > fabsf_(v.z) ? v3(v.y, -v.x, 0.0f) : v3(0.0f, v.z, -v.y);
+}
+RB_HD V3 to_world(const V3& n, const V3& s) {  // glm::mat3{o1,o2,n} * s with the basis of P/Distribution.h:21-28
+  V3 o2 = normalize(orthogonal(n));
+  V3 o1 = normalize(cross(n, o2));
+  o2 = normalize(cross(o1, n));
+  return v3(o1.x * s.x + o2.x * s.y + n.x * s.z, o1.y * s.x + o2.y * s.y + n.y * s.z, o1.z * s.x + o2.z * s.y + n.z * s.z);
+}
+RB_HD V3 cosw_sample(const V3& n, float r1, float r2) {  // CosineWeightedDistribution::sample, :10-31
+  float sn, cs;
+  dm::sincosf_(RB_PI * 2.0f * r1, &sn, &cs);
+  float x = cs * sqrtf_(1.0f - r2);
+  float y = sn * sqrtf_(1.0f - r2);
+  float z = sqrtf_(r2);
+  return to_world(n, normalize(v3(x, y, z)));
+}
+RB_HD V3 lobe_sample(const V3& wr, float gamma, float r1, float r2) {  // CosineLobeDistribution::sample, :43-63
+  float sn, cs;
+  dm::sincosf_(2.0f * RB_PI * r1, &sn, &cs);
+  float pw = dm::powf_(r2, 2.0f / (gamma + 1.0f));
+  float x = cs * sqrtf_(1.0f - pw);
+  float y = sn * sqrtf_(1.0f - pw);
+  float z = dm::powf_(r2, 1.0f / (gamma + 1.0f));
+  return to_world(wr, normalize(v3(x, y, z)));
+}
+// getMaterialSampleFunc dispatch (:43-52): Lambert for LAMBERT, Phong for everything else.
+// Returns omega_i and its pdf (the f_r the reference also computes is unused by its ReSTIR caller).
+RB_HD V3 brdf_sample(const GElem& g, const V3& camPos, uint32_t key, uint32_t base, float* pdf) {
+  const float r1 = rng_value(key, base + 1, 0, 1), r2 = rng_value(key, base + 2, 0, 1);
+  if (g.matType == RB_MAT_LAMBERT) {  // MaterialLambert::sampleBRDF, P/MaterialLambert.cpp:43-53
+    V3 wi = cosw_sample(g.normal, r1, r2);
+    *pdf = cosw_pdf(g.normal, wi);
+    return wi;
+  }
+  // MaterialPhong::sampleBRDF, P/MaterialPhong.cpp:174-222
+  float maxDiffuse = max_component(g.diffuse);
+  float maxSpecular = max_component(g.specular);
+  float r0 = rng_value(key, base + 0, 0.0f, maxDiffuse + maxSpecular);
+  float pdfFactor = maxDiffuse / (maxDiffuse + maxSpecular);
+  const V3 wr = omega_r_of(g, camPos);
+  V3 wi = (r0 < maxDiffuse) ? cosw_sample(g.normal, r1, r2) : lobe_sample(wr, g.shininess, r1, r2);
+  float pdfDiffuse = cosw_pdf(g.normal, wi) * pdfFactor;
+  float pdfSpecular = lobe_pdf(wi, wr, g.shininess) * (1.0f - pdfFactor);
+  *pdf = pdfDiffuse + pdfSpecular;
+  return wi;
+}
+
+// ---- evaluateF / evaluatePHat (P/ReSTIRIntegrator.cpp:180-211) ---------------------
+// Unshadowed value L_i * f_r * G; *wants_ray tells whether the reference would trace here.
+RB_HD V3 eval_F0(const LightSample& s, const V3& camPos, const GElem& g, bool* wants_ray) {
+  *wants_ray = false;
+  if (!sample_valid(s) || g.isEmissive) return v3(0);
+  V3 lightDir = s.samplePoint - g.pos;
+  float r_sqr = dot(lightDir, lightDir);
+  lightDir = normalize(lightDir);
+  float cosThetaI = gmax(dot(lightDir, g.normal), 0.0f);
+  float cosThetaY = fabsf_(dot(-lightDir, s.sampleNormal));
+  float G = cosThetaI * cosThetaY / r_sqr;
+  V3 f_r = brdf_eval(g, camPos, lightDir);
+  *wants_ray = true;
+  return s.L_i * f_r * G;
+}
+template <class Vis>
+RB_HD V3 eval_F(const LightSample& s, const V3& camPos, const GElem& g, bool testVisibility, const Vis& vis, int slot,
+                Cnt& cnt, int written_copies, bool* wants_out = nullptr) {
+  bool wants;
+  V3 F0 = eval_F0(s, camPos, g, &wants);
+  if (wants_out) *wants_out = wants;
+  if (!wants || !testVisibility) return F0;
+  cnt.anyW += (uint32_t)written_copies;
+  if (F0.x == 0.0f && F0.y == 0.0f && F0.z == 0.0f) return F0;  // F0 * V == F0 for V in {0,1}
+  cnt.anyT++;
+  float V = vis.visible(slot, g.pos, s.samplePoint) ? 1.0f : 0.0f;
+  return F0 * V;
+}
+template <class Vis>
+RB_HD float eval_phat(const LightSample& s, const V3& camPos, const GElem& g, bool testVisibility, const Vis& vis,
+                      int slot, Cnt& cnt, int written_copies, bool* wants_out = nullptr) {
+  return length(eval_F(s, camPos, g, testVisibility, vis, slot, cnt, written_copies, wants_out));
+}
+
+// ---- light sampling (P/TriangleCDF.cpp:36-54 / alias seam) --------------------------
+struct LightPick {
+  uint32_t idx;
+  float pdf;  // probability of choosing this triangle
+};
+RB_HD LightPick pick_light(const SceneDev& sc, int sampler, uint32_t key, uint32_t slot) {
+  LightPick p;
+  const uint32_t N = sc.n_lights;
+  if (sampler == RB_LS_ALIAS) {
+    const uint32_t h = rng_bits(key, slot);
+    const uint32_t i = (uint32_t)(((uint64_t)h * (uint64_t)N) >> 32);
+    const float frac = bits_to_unit(rng_bits(key, slot | 0x40000000u));
+    p.idx = (frac < sc.alias_prob[i]) ? i : sc.alias_idx[i];
+    p.pdf = ldg4(sc.light + 6 * (size_t)p.idx + 1).w;  // area / total
+    return p;
+  }
+  const float ksi = rng_value(key, slot, 0.0f, 1.0f);
+  // std::lower_bound: first element >= ksi
+  uint32_t lo = 0, hi = N;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (sc.cdf[mid] < ksi)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  uint32_t index = lo;
+  if (index >= N) index = N - 1;
+  p.idx = index;
+  p.pdf = index == 0 ? sc.cdf[0] : sc.cdf[index] - sc.cdf[index - 1];
+  return p;
+}
+RB_HD float m_area(const RbParams& P, float pdfArea, float pdfBrdf) {  // P/ReSTIRIntegrator.h:62-67
+  if (pdfArea == 0.0f && pdfBrdf == 0.0f) return 0.0f;
+  return pdfArea / ((float)P.M_Area * pdfArea + (float)P.M_Brdf * pdfBrdf);
+}
+RB_HD float m_brdf(const RbParams& P, float pdfBrdf, float pdfArea) {  // :69-74
+  if (pdfArea == 0.0f && pdfBrdf == 0.0f) return 0.0f;
+  return pdfBrdf / ((float)P.M_Area * pdfArea + (float)P.M_Brdf * pdfBrdf);
+}
+
+// =====================================================================================
+// Pass 0: G-buffer (ReSTIRIntegrator::gBufferFillPass, :213-234; Camera::GenerateRay,
+// P/camera.cpp:20-42 — pixel corner, the two discarded aperture draws have no effect)
+// =====================================================================================
+RB_HD void primary_ray(const CamState& cam, int width, int height, int x, int y, V3* dir) {
+  const V3 d_c = v3((float)x - (float)width / 2.0f, (float)height / 2.0f - (float)y, -cam.focal);
+  const float* m = cam.invViewMat;
+  V3 d_w = v3(m[0] * d_c.x + m[4] * d_c.y + m[8] * d_c.z, m[1] * d_c.x + m[5] * d_c.y + m[9] * d_c.z,
+              m[2] * d_c.x + m[6] * d_c.y + m[10] * d_c.z);
+  *dir = normalize(d_w);
+}
+RB_HD GElem gbuffer_element(const FrameCtx& fc, const CamState& cam, int x, int y, uint32_t* geomID, uint32_t* primID,
+                            Cnt& cnt) {
+  V3 dir;
+  primary_ray(cam, fc.width, fc.height, x, y, &dir);
+  cnt.closest++;
+  const SurfaceHit h = intersect_surface(fc.sc, cam.pos, dir, FLT_MIN + 0.01f, FLT_MAX);  // Ray ctor defaults, P/Ray.h:8
+  GElem e;
+  e.pos = e.normal = e.diffuse = e.specular = e.emission = v3(0);
+  e.shininess = e.depth = e.invIM = 0;
+  e.matType = 0;
+  *geomID = *primID = 0xFFFFFFFFu;
+  if (h.didHit) {
+    const F4 m0 = ldg4(fc.sc.mat + 3 * (size_t)h.material), m1 = ldg4(fc.sc.mat + 3 * (size_t)h.material + 1),
+             m2 = ldg4(fc.sc.mat + 3 * (size_t)h.material + 2);
+    e.pos = h.hitPoint;
+    e.normal = h.normal;
+    e.depth = length(h.hitPoint - cam.pos);
+    e.matType = f2u(m1.w);
+    e.diffuse = xyz(m0);
+    e.specular = xyz(m1);
+    e.emission = xyz(m2);
+    e.shininess = m0.w;
+    *geomID = h.geomID;
+    *primID = h.primID;
+  } else {
+    e.emission = v3(fc.P.bgColor[0], fc.P.bgColor[1], fc.P.bgColor[2]);
+  }
+  e.isEmissive = emissive3(e.emission);
+  if (h.didHit && !e.isEmissive && uses_phong_brdf(e.matType)) e.invIM = inv_I_M(e.pos, e.normal, e.shininess, cam.pos);
+  return e;
+}
+RB_HD void gbuffer_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
+  uint32_t g, p;
+  const GElem e = gbuffer_element(fc, fc.cam, x, y, &g, &p, cnt);
+  store_gelem(fc.G, (size_t)y * fc.width + x, e, g, p);
+}
+
+// =====================================================================================
+// Pass 1: initial candidates (ReSTIRIntegrator::initialRenderPass, :236-298;
+// areaSampleLight :89-124; brdfSampleLight :126-177; Sampling::sampleTriangle P/Sampling.cpp:63-76)
+// RNG slots: candidate c uses 4c..4c+3 = {pick | lobe, r1, r2, accept}.
+// =====================================================================================
+template <class Vis>
+RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const GElem g = load_gelem(fc.G, pi);
+  Reservoir r = empty_reservoir();
+  if (g.isEmissive || fc.sc.n_lights == 0) {
+    store_reservoir(fc.Rwrite, pi, r);
+    return;
+  }
+  const RbParams& P = fc.P;
+  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+  const V3 cam = fc.cam.pos;
+  const bool testVis = !P.doVisibilityPass;
+  float p_sel = 0.0f;  // p-hat of the currently selected sample (== the final evaluatePHat, :289)
+  bool sel_wants = false;
+
+  const float inv_MArea = P.M_Area > 0 ? 1.0f / (float)P.M_Area : 0.0f;
+  for (int i = 0; i < P.M_Area; ++i) {
+    const uint32_t base = 4u * (uint32_t)i;
+    const LightPick pick = pick_light(fc.sc, P.lightSampler, key, base);
+    const F4* L = fc.sc.light + 6 * (size_t)pick.idx;
+    const F4 l0 = ldg4(L), l1 = ldg4(L + 1), l2 = ldg4(L + 2), l3 = ldg4(L + 3), l4 = ldg4(L + 4), l5 = ldg4(L + 5);
+    const float r1 = rng_value(key, base + 1, 0, 1), r2 = rng_value(key, base + 2, 0, 1);
+    const float bx = 1.0f - sqrtf_(r1);
+    const float by = sqrtf_(r1) * (1.0f - r2);
+    const float bz = sqrtf_(r1) * r2;
+    LightSample s;
+    s.samplePoint = xyz(l0) * bx + xyz(l1) * by + xyz(l2) * bz;
+    s.sampleNormal = normalize(xyz(l3) * bx + xyz(l4) * by + xyz(l5) * bz);
+    s.L_i = v3(l3.w, l4.w, l5.w);
+    s.lightIdx = (int)pick.idx;
+    const float triPointPdf = 1.0f / l0.w;
+    const float pdf_area = pick.pdf * triPointPdf;
+    V3 lightDir = s.samplePoint - g.pos;
+    const float r_sqr = dot(lightDir, lightDir);
+    lightDir = normalize(lightDir);
+    const float cosThetaY = gmax(dot(-lightDir, s.sampleNormal), 0.0f);
+    const float areaMeasureFactor = cosThetaY / r_sqr;
+    const float pdfAsIfBrdfAreaMeasure = phong_pdf(g, cam, lightDir) * areaMeasureFactor;
+    const float W = 1.0f / pdf_area;
+    const float misWeight = m_area(P, pdf_area, pdfAsIfBrdfAreaMeasure);
+    bool wants;
+    const float p_hat = eval_phat(s, cam, g, testVis, vis, i, cnt, 1, &wants);
+    const float w = (P.M_Brdf > 0) ? misWeight * p_hat * W : inv_MArea * p_hat * W;
+    if (add_sample(r, s, w, 1, key, base + 3)) {
+      p_sel = p_hat;
+      sel_wants = wants;
+    }
+  }
+  const float inv_MBrdf = P.M_Brdf > 0 ? 1.0f / (float)P.M_Brdf : 0.0f;
+  for (int i = 0; i < P.M_Brdf; ++i) {
+    const uint32_t base = 4u * (uint32_t)(P.M_Area + i);
+    float pdf;
+    const V3 wi = brdf_sample(g, cam, key, base, &pdf);
+    const V3 org = g.pos + P.normalOffset * g.normal;
+    cnt.closest++;
+    const SurfaceHit h = intersect_surface(fc.sc, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
+    LightSample s = invalid_sample();
+    float W = 0, misWeight = 0;
+    if (h.didHit && h.emissiveId >= 0) {
+      V3 lightDir = h.hitPoint - g.pos;
+      const float r_sqr = dot(lightDir, lightDir);
+      lightDir = normalize(lightDir);
+      const float cosThetaY = gmax(dot(-lightDir, h.normal), 0.0f);
+      const float areaMeasureFactor = cosThetaY / r_sqr;
+      const F4* L = fc.sc.light + 6 * (size_t)h.emissiveId;
+      const F4 l0 = ldg4(L);
+      float pdf_area = l0.w / fc.sc.total_area;  // TriangleCDF::getPDFForTriangle, P/TriangleCDF.h:25-31
+      pdf_area *= 1.0f / l0.w;
+      const float brdfPdfAreaMeasure = pdf * areaMeasureFactor;
+      s.samplePoint = h.hitPoint;
+      s.sampleNormal = h.normal;
+      const F4 m2 = ldg4(fc.sc.mat + 3 * (size_t)h.material + 2);
+      s.L_i = xyz(m2);
+      s.lightIdx = h.emissiveId;
+      W = 1.0f / brdfPdfAreaMeasure;
+      misWeight = m_brdf(P, brdfPdfAreaMeasure, pdf_area);
+    }
+    bool wants;
+    const float p_hat = eval_phat(s, cam, g, testVis, vis, P.M_Area + i, cnt, 1, &wants);
+    const float w = (P.M_Area > 0) ? misWeight * p_hat * W : inv_MBrdf * p_hat * W;
+    if (add_sample(r, s, w, 1, key, base + 3)) {
+      p_sel = p_hat;
+      sel_wants = wants;
+    }
+  }
+  // final evaluatePHat(r.bestSample) — the selected candidate's value again (:289)
+  if (testVis && sel_wants) cnt.anyW++;
+  const float p_hat = p_sel;
+  r.W = p_hat > 0.0f ? 1.0f / p_hat * r.w_sum : 0.0f;
+  r.confidence = imin(r.confidence, P.confidenceCap);
+  store_reservoir(fc.Rwrite, pi, r);
+}
+
+// =====================================================================================
+// Pass 2: visibility (ReSTIRIntegrator::visibilityPass, :302-312) — traces even for an
+// empty reservoir (sample point = -FLT_MAX sentinel), exactly like the reference.
+// =====================================================================================
+template <class Vis>
+RB_HD void visibility_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const F4 pw = ld4(fc.Rwrite.point_wsum + pi);
+  const F4 pd = ld4(fc.G.pos_depth + pi);
+  cnt.anyW++;
+  cnt.anyT++;
+  const bool V = vis.visible(0, xyz(pd), xyz(pw));
+  if (!V) {
+    F4 nw = ld4(fc.Rwrite.normal_W + pi);
+    nw.w = 0.0f;
+    st4(fc.Rwrite.normal_W + pi, nw);
+  }
+}
+
+// =====================================================================================
+// Pass 3: temporal reuse (ReSTIRIntegrator::temporalReusePass, :625-732;
+// reprojectBackward / reprojectForward :544-587)
+// =====================================================================================
+RB_HD bool reproject(const CamState& cam, int width, int height, const V3& wsPos, int* sx, int* sy) {
+  const float* m = cam.viewMat;  // glm mat4*vec4: (m0*x + m1*y) + (m2*z + m3*w)
+  const float vx = (m[0] * wsPos.x + m[4] * wsPos.y) + (m[8] * wsPos.z + m[12] * 1.0f);
+  const float vy = (m[1] * wsPos.x + m[5] * wsPos.y) + (m[9] * wsPos.z + m[13] * 1.0f);
+  const float vz = (m[2] * wsPos.x + m[6] * wsPos.y) + (m[10] * wsPos.z + m[14] * 1.0f);
+  if (vz >= 0) return false;
+  const float fx = roundf((-vx / vz) * cam.focal + (float)width / 2.0f);  // glm::round: half away from zero
+  const float fy = roundf((vy / vz) * cam.focal + (float)height / 2.0f);
+  if (!(fx >= -1.0f)) return false;
+  if (!(fy >= -1.0f)) return false;
+  if (fx > (float)width || fy > (float)height) return false;
+  const int screenX = (int)fx, screenY = (int)fy;
+  if (screenX < 0 || screenX > width - 1 || screenY < 0 || screenY > height - 1) return false;
+  *sx = screenX;
+  *sy = screenY;
+  return true;
+}
+
+template <class Vis>
+RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const RbParams& P = fc.P;
+  const Reservoir cur = load_reservoir(fc.Rread, pi);
+  const GElem curElem = load_gelem(fc.G, pi);
+  int px, py;
+  if (!reproject(fc.prevCam, fc.width, fc.height, curElem.pos, &px, &py)) {
+    store_reservoir(fc.Rwrite, pi, cur);
+    return;
+  }
+  const GElem prevElem = load_gelem(fc.Gprev, (size_t)py * fc.width + px);
+  const V3 curCam = fc.cam.pos, prevCam = fc.prevCam.pos;
+  const float currentDepth = length(curElem.pos - curCam);
+  const float prevDepth = length(prevElem.pos - prevCam);
+  const float depthRatio = currentDepth > prevDepth ? prevDepth / currentDepth : currentDepth / prevDepth;
+  if (depthRatio < 0.9f) {
+    store_reservoir(fc.Rwrite, pi, cur);
+    return;
+  }
+  const V3 prevPosAtCurrent = xyz(ld4(fc.Gprev.pos_depth + pi));
+  int fx, fy;
+  if (!reproject(fc.cam, fc.width, fc.height, prevPosAtCurrent, &fx, &fy)) {
+    store_reservoir(fc.Rwrite, pi, cur);
+    return;
+  }
+  const V3 fwPos = xyz(ld4(fc.G.pos_depth + (size_t)fy * fc.width + fx));
+  const float currentDepthP = length(prevPosAtCurrent - prevCam);
+  const float prevDepthP = length(fwPos - curCam);
+  const float depthRatioP = currentDepthP > prevDepthP ? prevDepthP / currentDepthP : currentDepthP / prevDepthP;
+  if (depthRatioP < 0.9f) {
+    store_reservoir(fc.Rwrite, pi, cur);
+    return;
+  }
+  const Reservoir prev = load_reservoir(fc.Rlast, pi);  // same pixel, not the reprojected one (:641)
+  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+
+  // four distinct p-hat values feed the seven evaluations of the reference
+  bool wA, wC;
+  const float A = eval_phat(cur.bestSample, curCam, curElem, true, vis, 0, cnt, 2, &wA);   // p_cur, p_hat_cur
+  const float B = eval_phat(cur.bestSample, prevCam, prevElem, true, vis, 1, cnt, 1);      // p_prev
+  const float C = eval_phat(prev.bestSample, curCam, curElem, true, vis, 2, cnt, 2, &wC);  // p_cur', p_hat_prev
+  const float D = eval_phat(prev.bestSample, prevCam, prevElem, true, vis, 3, cnt, 1);  // p_prev'
+
+  Reservoir out = empty_reservoir();
+  float m_cur = A * (float)cur.confidence / (A * (float)cur.confidence + B * (float)prev.confidence);
+  if (!(m_cur > 0)) m_cur = 0.0f;
+  const float w_cur = m_cur * A * cur.W;
+  int selected = -1;
+  if (add_sample(out, cur.bestSample, w_cur, cur.confidence, key, 0)) selected = 0;
+  float m_prev = D * (float)prev.confidence / (C * (float)cur.confidence + D * (float)prev.confidence);
+  if (!(m_prev > 0)) m_prev = 0.0f;
+  const float w_prev = m_prev * C * prev.W;
+  if (add_sample(out, prev.bestSample, w_prev, prev.confidence, key, 1)) selected = 1;
+  out.confidence = imin(out.confidence, P.confidenceCap);
+  float final_p_hat = 0.0f;
+  if (selected == 0) {
+    final_p_hat = A;
+    if (wA) cnt.anyW++;
+  } else if (selected == 1) {
+    final_p_hat = C;
+    if (wC) cnt.anyW++;
+  }
+  out.W = final_p_hat > 0.0f ? out.w_sum / final_p_hat : 0.0f;
+  store_reservoir(fc.Rwrite, pi, out);
+}
+
+// =====================================================================================
+// Pass 4: spatial reuse (ReSTIRIntegrator::spatialReusePass, :316-542;
+// Sampling::sampleDiskUniform P/Sampling.cpp:78-87)
+// RNG slots: neighbour i uses 2i (theta) and 2i+1 (radius); candidate j accepts on 2k+j.
+// =====================================================================================
+template <class Vis>
+RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const RbParams& P = fc.P;
+  const GElem thisElem = load_gelem(fc.G, pi);
+  if (thisElem.isEmissive) {
+    store_reservoir(fc.Rwrite, pi, load_reservoir(fc.Rread, pi));
+    return;
+  }
+  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+  const V3 cam = fc.cam.pos;
+  const int k = P.spatialReuseNeighborCount;
+  uint32_t nb[RB_MAX_NEIGHBORS + 1];  // pixel index of every resampling source; [0] = this pixel
+  nb[0] = (uint32_t)pi;
+  int M = 1;
+  for (int i = 0; i < k; ++i) {
+    const float theta = rng_value(key, 2u * i, 0, 2.0f) * RB_PI;
+    const float r = sqrtf_(rng_value(key, 2u * i + 1, 0, P.spatialReuseRadius));
+    float sn, cs;
+    dm::sincosf_(theta, &sn, &cs);
+    const float ox = r * cs, oy = r * sn;
+    int nx = x + (int)ox, ny = y + (int)oy;
+    nx = imin(imax(nx, 0), fc.width - 1);
+    ny = imin(imax(ny, 0), fc.height - 1);
+    const size_t ni = (size_t)ny * fc.width + nx;
+    const F4 st = ld4(fc.G.spec_type + ni);
+    if (f2u(st.w) & 0x100u) continue;  // emissive neighbours never hold a reservoir (:345)
+    if (P.rejectDissimilarNeighbors) {
+      const F4 nn = ld4(fc.G.normal_shin + ni);
+      const float normalSimilarity = dot(xyz(nn), thisElem.normal);
+      if (normalSimilarity < P.minNormalSimilarity) continue;
+      const float ndepth = ld4(fc.G.pos_depth + ni).w;
+      float depthRatio = 0;
+      if (ndepth > 0) depthRatio = thisElem.depth / ndepth;
+      const float halfDepthDiff = P.maxDepthDifference * 0.5f;
+      if (depthRatio < 1.0f - halfDepthDiff || depthRatio > 1.0f + halfDepthDiff) continue;
+    }
+    nb[M++] = (uint32_t)ni;
+  }
+  const int n = M;
+  const float rcpM = M > 0 ? 1.0f / (float)M : 0.0f;
+  const int mode = P.spatialWeightCalc;
+
+  int confidenceSum = 0, confidenceSumNonCanonical = 0;
+  if (mode == RB_SW_PAIRWISE_MIS) {
+    for (int i = 0; i < n; ++i) {
+      const int c = (int)f2u(ld4(fc.Rread.Li_conf + nb[i]).w);
+      confidenceSum += c;
+      if (i != 0) confidenceSumNonCanonical += c;
+    }
+  }
+
+  Reservoir out = empty_reservoir();
+  int selectedSampleIndex = 0;
+  bool any_selected = false;
+  float p_sel = 0.0f;
+  bool sel_wants = false;
+  for (int i = 0; i < n; ++i) {
+    const Reservoir ri = load_reservoir(fc.Rread, nb[i]);
+    const LightSample& si = ri.bestSample;
+    float misWeight = rcpM;
+    if (mode == RB_SW_BALANCE_HEURISTIC) {
+      float misNom = 0, misDenom = 0;
+      misWeight = 0.0f;
+      for (int j = 0; j < n; ++j) {
+        const GElem gj = load_gelem(fc.G, nb[j]);
+        const int cj = (int)f2u(ld4(fc.Rread.Li_conf + nb[j]).w);
+        const float p_hat = eval_phat(si, cam, gj, true, vis, 0, cnt, 1);
+        misDenom += p_hat * cj;
+        if (i == j) misNom = p_hat * ri.confidence;
+      }
+      if (misDenom > 0) misWeight = misNom / misDenom;
+    }
+    if (mode == RB_SW_PAIRWISE_MIS) {
+      misWeight = 0.0f;
+      if (i == 0) {
+        float sum = 0.0f;
+        const float p_hat_c = eval_phat(si, cam, thisElem, true, vis, 0, cnt, 1) * (float)ri.confidence;
+        for (int j = 1; j < n; ++j) {
+          const GElem gj = load_gelem(fc.G, nb[j]);
+          const int cj = (int)f2u(ld4(fc.Rread.Li_conf + nb[j]).w);
+          const float p_hat_j = eval_phat(si, cam, gj, true, vis, 0, cnt, 1);
+          const float denom = p_hat_c + p_hat_j * (float)confidenceSumNonCanonical;
+          if (denom > 0) {
+            const float confFract = (float)cj / (float)confidenceSum;
+            sum += confFract * (p_hat_c / denom);
+          }
+        }
+        misWeight = ((float)ri.confidence / (float)confidenceSum) + sum;
+      } else {
+        const GElem gi = load_gelem(fc.G, nb[i]);
+        float p_hat_i = eval_phat(si, cam, gi, true, vis, 0, cnt, 1);
+        const float p_hat_c = eval_phat(si, cam, thisElem, true, vis, 0, cnt, 1);
+        p_hat_i *= (float)confidenceSumNonCanonical;
+        const int c0 = (int)f2u(ld4(fc.Rread.Li_conf + nb[0]).w);
+        const float denom = p_hat_i + p_hat_c * (float)c0;
+        if (denom > 0 && confidenceSum > 0) misWeight = ((float)ri.confidence / (float)confidenceSum) * (p_hat_i / denom);
+      }
+    }
+    bool wants;
+    const float resamplingPhat = eval_phat(si, cam, thisElem, true, vis, i, cnt, 1, &wants);
+    const float resamplingWeight = misWeight * resamplingPhat * ri.W;
+    if (add_sample(out, si, resamplingWeight, ri.confidence, key, 2u * k + i)) {
+      selectedSampleIndex = i;
+      any_selected = true;
+      p_sel = resamplingPhat;
+      sel_wants = wants;
+    }
+  }
+  // final evaluatePHat(resultReservoir.bestSample @ this pixel): the selected candidate's value again (:481)
+  if (any_selected && sel_wants) cnt.anyW++;
+  const float final_p_hat = any_selected ? p_sel : 0.0f;
+  if (mode == RB_SW_CONSTANT || mode == RB_SW_BALANCE_HEURISTIC || mode == RB_SW_PAIRWISE_MIS) {
+    out.W = final_p_hat > 0.0f ? out.w_sum / final_p_hat : 0.0f;
+  } else if (mode == RB_SW_CONSTANT_DEBIAS_Z_TERM) {
+    int Z = 0;
+    float correctionFactor = 1.0f;
+    for (int i = 0; i < n; ++i) {
+      const V3 pj = xyz(ld4(fc.G.pos_depth + nb[i]));
+      cnt.anyW++;
+      cnt.anyT++;
+      if (vis.visible(0, pj, out.bestSample.samplePoint)) Z += 1;
+    }
+    if (Z > 0 && M > 0) correctionFactor = (1.0f / (float)Z) / rcpM;
+    out.W = final_p_hat > 0.0f ? correctionFactor * out.w_sum / final_p_hat : 0.0f;
+  } else if (mode == RB_SW_CONSTANT_DEBIAS_CONTRIB) {
+    const Reservoir rs = load_reservoir(fc.Rread, nb[selectedSampleIndex]);
+    float misNom = 0, misDenom = 0, contribWeight = 0, correctionFactor = 0;
+    for (int i = 0; i < n; ++i) {
+      const GElem gi = load_gelem(fc.G, nb[i]);
+      const int ci = (int)f2u(ld4(fc.Rread.Li_conf + nb[i]).w);
+      const float p_hat = eval_phat(rs.bestSample, cam, gi, true, vis, 0, cnt, 1);
+      misDenom += p_hat * (float)ci;
+      if (i == selectedSampleIndex) misNom = p_hat * (float)ci;
+    }
+    if (misDenom > 0) contribWeight = misNom / misDenom;
+    if (M > 0) correctionFactor = contribWeight / rcpM;
+    out.W = final_p_hat > 0.0f ? correctionFactor * out.w_sum / final_p_hat : 0.0f;
+  }
+  out.confidence = imin(out.confidence, P.confidenceCap);
+  store_reservoir(fc.Rwrite, pi, out);
+}
+
+// =====================================================================================
+// Pass 5: final shading (P/simpleguidx11.cpp:452-472) + Integrator::sanitize (P/Integrator.cpp:6-23)
+// =====================================================================================
+template <class Vis>
+RB_HD void shade_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const Reservoir r = load_reservoir(fc.Rread, pi);
+  V3 pixel;
+  if (r.w_sum > 0.0f) {  // Reservoir::hasSample
+    const GElem g = load_gelem(fc.G, pi);
+    const V3 f = eval_F(r.bestSample, fc.cam.pos, g, true, vis, 0, cnt, 1);
+    pixel = f * r.W;
+  } else {
+    pixel = xyz(ld4(fc.G.emission + pi));
+  }
+  if (pixel.x != pixel.x || pixel.y != pixel.y || pixel.z != pixel.z) pixel = v3(0);
+  if (pixel.x < 0 || pixel.y < 0 || pixel.z < 0) pixel = v3(0);
+  float* o = fc.frame + 3 * pi;
+  o[0] = pixel.x;
+  o[1] = pixel.y;
+  o[2] = pixel.z;
+}
+
+}  // namespace rb
+#endif

@@ -1,0 +1,871 @@
+// restir_b200.cu — kernels and the extern "C" shim of include/restir_b200.h.
+//
+// Hand-written CUDA for sm_100a (nvcc -gencode arch=compute_100a,code=sm_100a
+// -fmad=false). No OptiX, no Triton, no CPU fallback: every entry point either
+// runs on the GPU or returns an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "rb_build.cuh"
+#include "rb_host_scene.h"
+#include "rb_passes.cuh"
+
+using namespace rb;
+
+// =====================================================================================
+// kernels
+// =====================================================================================
+namespace {
+
+constexpr int kTileW = 8, kTileH = 32;  // one warp = 8x4 pixels, one CTA = 8x32
+
+__device__ __forceinline__ void flush_counts(unsigned long long* ctr, const Cnt& c) {
+  const unsigned a = __reduce_add_sync(0xFFFFFFFFu, c.closest);
+  const unsigned b = __reduce_add_sync(0xFFFFFFFFu, c.anyW);
+  const unsigned d = __reduce_add_sync(0xFFFFFFFFu, c.anyT);
+  if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0) {
+    if (a) atomicAdd(ctr + 0, (unsigned long long)a);
+    if (b) atomicAdd(ctr + 1, (unsigned long long)b);
+    if (d) atomicAdd(ctr + 2, (unsigned long long)d);
+  }
+}
+
+#define RB_PIXEL_KERNEL(NAME, CALL)                                   \
+  __global__ void __launch_bounds__(kTileW* kTileH) NAME(FrameCtx fc) { \
+    const int x = blockIdx.x * kTileW + threadIdx.x;                  \
+    const int y = fc.y0 + blockIdx.y * kTileH + threadIdx.y;          \
+    Cnt cnt = {0, 0, 0};                                              \
+    const InlineVis vis = {&fc};                                      \
+    (void)vis;                                                        \
+    if (x < fc.width && y < fc.y1) {                                  \
+      CALL;                                                           \
+    }                                                                 \
+    flush_counts(fc.counters, cnt);                                   \
+  }
+
+RB_PIXEL_KERNEL(k_gbuffer, gbuffer_pixel(fc, x, y, cnt))
+RB_PIXEL_KERNEL(k_initial, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_visibility, visibility_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal, temporal_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial, spatial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_shade, shade_pixel(fc, x, y, vis, cnt))
+
+// ---- ray seam ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_trace_closest(SceneDev sc, const RbRay* rays, RbHit* hits, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RbRay r = rays[i];
+  HitRec h;
+  const bool hit = trace8<false>(sc, v3(r.org_x, r.org_y, r.org_z), v3(r.dir_x, r.dir_y, r.dir_z), r.tnear, r.tfar, &h);
+  RbHit o;
+  if (hit) {
+    const U4 info = sc.tri_info[h.tri];
+    o.t = h.t, o.u = h.u, o.v = h.v, o.primID = info.y, o.geomID = info.x;
+  } else {
+    o.t = r.tfar, o.u = 0, o.v = 0, o.primID = 0xFFFFFFFFu, o.geomID = 0xFFFFFFFFu;
+  }
+  hits[i] = o;
+}
+__global__ void __launch_bounds__(256) k_trace_any(SceneDev sc, const RbRay* rays, uint8_t* occ, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RbRay r = rays[i];
+  occ[i] = trace8<true>(sc, v3(r.org_x, r.org_y, r.org_z), v3(r.dir_x, r.dir_y, r.dir_z), r.tnear, r.tfar, nullptr) ? 1 : 0;
+}
+
+// ---- BVH build -----------------------------------------------------------------------
+__global__ void k_bounds(BuildCtx c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c.n) bounds_body(c, i);
+}
+__global__ void k_morton(BuildCtx c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c.n) morton_body(c, i);
+}
+__global__ void k_karras(BuildCtx c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 < c.n) karras_body(c, i);
+}
+__global__ void k_fit(BuildCtx c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c.n) fit_body(c, i);
+}
+__global__ void k_collapse(BuildCtx c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (uint32_t)c.q_in_len) collapse_body(c, i);
+}
+__global__ void k_tiny_root(BuildCtx c) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) tiny_root_body(c);
+}
+
+// implicit FMA contraction must be off for CPU/GPU parity: a*b+c with a single rounding differs here
+__global__ void k_selfcheck(float a, float b, float c, float* out) { out[0] = a * b + c; }
+
+}  // namespace
+
+// =====================================================================================
+// context
+// =====================================================================================
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct RbContext {
+  RbCreateInfo info{};
+  RbParams params{};
+  std::string err;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+
+  // frame state
+  GBufPlanes G[2]{};
+  int gCur = 0;
+  ResPlanes R[3]{};
+  int rRead = 0, rWrite = 1, rLast = 2;
+  float* frame = nullptr;
+  unsigned long long* counters = nullptr;
+  CamState prevCam{};
+  bool havePrev = false;
+
+  // scene
+  bool haveScene = false;
+  SceneDev sc{};
+  std::vector<void*> sceneAllocs;
+  RbSceneStats stats{};
+
+  cudaEvent_t ev[16]{};
+  bool evCreated = false;
+};
+
+static thread_local std::string g_create_error;
+
+#define RB_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+      return e__ == cudaErrorMemoryAllocation ? RB_ERR_OUT_OF_MEMORY : RB_ERR_CUDA;        \
+    }                                                                                      \
+  } while (0)
+
+template <class T>
+static int dev_alloc(RbContext* h, T** out, size_t count, std::vector<void*>& owner) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  RB_CUDA(cudaMalloc(&p, bytes));
+  owner.push_back(p);
+  *out = (T*)p;
+  return RB_OK;
+}
+#define RB_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != RB_OK) return rc__; \
+  } while (0)
+
+static void free_list(std::vector<void*>& l) {
+  for (void* p : l) cudaFree(p);
+  l.clear();
+}
+
+extern "C" {
+
+uint32_t rb_abi_version(void) { return RB_ABI_VERSION; }
+
+const char* rb_last_error(RbHandle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void rb_default_params(RbParams* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->M_Area = 1;
+  p->M_Brdf = 1;
+  p->spatialReuseNeighborCount = 5;
+  p->spatialPassCount = 1;
+  p->confidenceCap = 20;
+  p->spatialReuseRadius = 30.0f;
+  p->minNormalSimilarity = 0.85f;
+  p->maxDepthDifference = 0.2f;
+  p->spatialWeightCalc = RB_SW_CONSTANT;
+  p->tnearOffset = 0.01f;
+  p->tfarOffset = 0.001f;
+  p->normalOffset = 0.001f;
+  p->bgColor[0] = p->bgColor[1] = p->bgColor[2] = 0.5f;
+  p->useSkybox = 0;
+  p->lightSampler = RB_LS_CDF;
+  p->wavefront = 0;
+}
+
+int rb_create(const RbCreateInfo* info, RbHandle* out) {
+  if (!info || !out || info->width <= 0 || info->height <= 0 || info->band_y0 < 0 || info->band_y1 > info->height ||
+      info->band_y0 >= info->band_y1) {
+    g_create_error = "rb_create: invalid RbCreateInfo";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("rb_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+    return RB_ERR_CUDA;
+  }
+  if (info->device < 0 || info->device >= ndev) {
+    g_create_error = "rb_create: device ordinal out of range";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  RbContext* h = new RbContext();
+  h->info = *info;
+  rb_default_params(&h->params);
+  auto fail = [&](int rc) {
+    g_create_error = h->err;
+    free_list(h->allocs);
+    delete h;
+    return rc;
+  };
+  auto body = [&]() -> int {
+    RB_CUDA(cudaSetDevice(info->device));
+    RB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t n = (size_t)info->width * info->height;
+    for (int i = 0; i < 2; ++i) {
+      RB_TRY(dev_alloc(h, &h->G[i].pos_depth, n, h->allocs));
+      RB_TRY(dev_alloc(h, &h->G[i].normal_shin, n, h->allocs));
+      RB_TRY(dev_alloc(h, &h->G[i].diffuse_iim, n, h->allocs));
+      RB_TRY(dev_alloc(h, &h->G[i].spec_type, n, h->allocs));
+      RB_TRY(dev_alloc(h, &h->G[i].emission, n, h->allocs));
+      RB_TRY(dev_alloc(h, &h->G[i].hit_ids, n, h->allocs));
+      RB_CUDA(cudaMemsetAsync(h->G[i].pos_depth, 0, n * 16, h->stream));
+      RB_CUDA(cudaMemsetAsync(h->G[i].normal_shin, 0, n * 16, h->stream));
+      RB_CUDA(cudaMemsetAsync(h->G[i].diffuse_iim, 0, n * 16, h->stream));
+      RB_CUDA(cudaMemsetAsync(h->G[i].spec_type, 0, n * 16, h->stream));
+      RB_CUDA(cudaMemsetAsync(h->G[i].emission, 0, n * 16, h->stream));
+      RB_CUDA(cudaMemsetAsync(h->G[i].hit_ids, 0xFF, n * 8, h->stream));
+    }
+    for (int i = 0; i < 3; ++i) {
+      RB_TRY(dev_alloc(h, &h->R[i].point_wsum, n, h->allocs));
+      RB_TRY(dev_alloc(h, &h->R[i].normal_W, n, h->allocs));
+      RB_TRY(dev_alloc(h, &h->R[i].Li_conf, n, h->allocs));
+      RB_TRY(dev_alloc(h, &h->R[i].light_idx, n, h->allocs));
+      RB_CUDA(cudaMemsetAsync(h->R[i].point_wsum, 0, n * 16, h->stream));
+      RB_CUDA(cudaMemsetAsync(h->R[i].normal_W, 0, n * 16, h->stream));
+      RB_CUDA(cudaMemsetAsync(h->R[i].Li_conf, 0, n * 16, h->stream));
+      RB_CUDA(cudaMemsetAsync(h->R[i].light_idx, 0xFF, n * 4, h->stream));
+    }
+    RB_TRY(dev_alloc(h, &h->frame, n * 3, h->allocs));
+    RB_CUDA(cudaMemsetAsync(h->frame, 0, n * 12, h->stream));
+    RB_TRY(dev_alloc(h, &h->counters, 8, h->allocs));
+    RB_CUDA(cudaMemsetAsync(h->counters, 0, 64, h->stream));
+    for (auto& ev : h->ev) RB_CUDA(cudaEventCreate(&ev));
+    h->evCreated = true;
+    // arithmetic self-check: implicit contraction must be off
+    float* d = nullptr;
+    RB_TRY(dev_alloc(h, &d, 1, h->allocs));
+    const float a = 1.0f + 1.0f / 4096.0f;
+    k_selfcheck<<<1, 1, 0, h->stream>>>(a, a, -1.0f, d);
+    float r = 0;
+    RB_CUDA(cudaMemcpyAsync(&r, d, 4, cudaMemcpyDeviceToHost, h->stream));
+    RB_CUDA(cudaStreamSynchronize(h->stream));
+    if (r != 1.0f / 2048.0f) {
+      h->err = "rb_create: kernels were built with FMA contraction enabled (need nvcc -fmad=false)";
+      return RB_ERR_UNSUPPORTED;
+    }
+    return RB_OK;
+  };
+  int rc = body();
+  if (rc != RB_OK) return fail(rc);
+  *out = h;
+  return RB_OK;
+}
+
+void rb_destroy(RbHandle h) {
+  if (!h) return;
+  cudaSetDevice(h->info.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_list(h->allocs);
+  free_list(h->sceneAllocs);
+  if (h->evCreated)
+    for (auto& ev : h->ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int rb_set_params(RbHandle h, const RbParams* p) {
+  if (!h || !p) return RB_ERR_INVALID_ARGUMENT;
+  if (p->useSkybox) {
+    h->err = "rb_set_params: useSkybox=1 needs the sky texture (not part of ABI v1)";
+    return RB_ERR_UNSUPPORTED;
+  }
+  if (p->M_Area < 0 || p->M_Brdf < 0 || p->spatialReuseNeighborCount < 0 || p->spatialPassCount < 0 ||
+      p->spatialWeightCalc < 0 || p->spatialWeightCalc > 4 || p->lightSampler < 0 || p->lightSampler > 1) {
+    h->err = "rb_set_params: parameter out of range";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  if (p->spatialReuseNeighborCount > RB_MAX_NEIGHBORS) {
+    h->err = "rb_set_params: spatialReuseNeighborCount > 32 is not supported";
+    return RB_ERR_UNSUPPORTED;
+  }
+  h->params = *p;
+  return RB_OK;
+}
+
+// -------------------------------------------------------------------------------------
+// scene upload + BVH build
+// -------------------------------------------------------------------------------------
+static int build_bvh(RbContext* h, const float* d_tri_pos, uint32_t n, float maxabs, F4** node8_out, F4** tri_isect_out,
+                     uint32_t* n_nodes_out, uint32_t* depth_out) {
+  std::vector<void*> tmp;
+  auto cleanup = [&]() { free_list(tmp); };
+  BuildCtx c{};
+  c.n = n;
+  c.tri_pos = d_tri_pos;
+  c.pad = maxabs * (1.0f / 262144.0f) + 1e-30f;  // 2^-18 of the scene scale (DESIGN.md "conservative culling")
+  auto body = [&]() -> int {
+    RB_TRY(dev_alloc(h, &c.scene_bounds, 6, tmp));
+    RB_TRY(dev_alloc(h, &c.tbox_lo, n, tmp));
+    RB_TRY(dev_alloc(h, &c.tbox_hi, n, tmp));
+    uint64_t* morton_in = nullptr;
+    uint32_t* order_in = nullptr;
+    RB_TRY(dev_alloc(h, &morton_in, n, tmp));
+    RB_TRY(dev_alloc(h, &order_in, n, tmp));
+    RB_TRY(dev_alloc(h, &c.morton, n, tmp));
+    RB_TRY(dev_alloc(h, &c.order, n, tmp));
+    RB_TRY(dev_alloc(h, &c.left, n, tmp));
+    RB_TRY(dev_alloc(h, &c.right, n, tmp));
+    RB_TRY(dev_alloc(h, &c.parent, n, tmp));
+    RB_TRY(dev_alloc(h, &c.leaf_parent, n, tmp));
+    RB_TRY(dev_alloc(h, &c.range_lo, n, tmp));
+    RB_TRY(dev_alloc(h, &c.range_hi, n, tmp));
+    RB_TRY(dev_alloc(h, &c.ibox_lo, n, tmp));
+    RB_TRY(dev_alloc(h, &c.ibox_hi, n, tmp));
+    RB_TRY(dev_alloc(h, &c.visit, n, tmp));
+    RB_TRY(dev_alloc(h, &c.counters, 4, tmp));
+    int* q[2] = {nullptr, nullptr};
+    RB_TRY(dev_alloc(h, &q[0], 2 * (size_t)n + 2, tmp));
+    RB_TRY(dev_alloc(h, &q[1], 2 * (size_t)n + 2, tmp));
+    const size_t max_nodes = (size_t)n / 2 + 8;
+    F4* node8_big = nullptr;
+    RB_TRY(dev_alloc(h, &node8_big, 5 * max_nodes, tmp));
+    F4* tri_isect = nullptr;
+    RB_TRY(dev_alloc(h, &tri_isect, 3 * (size_t)n, h->sceneAllocs));
+    c.node8 = node8_big;
+    c.tri_isect = tri_isect;
+
+    const int B = 256;
+    const unsigned grid = (n + B - 1) / B;
+    const int init_bounds[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+    RB_CUDA(cudaMemcpyAsync(c.scene_bounds, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice, h->stream));
+    RB_CUDA(cudaMemsetAsync(c.visit, 0, sizeof(int) * (size_t)n, h->stream));
+    k_bounds<<<grid, B, 0, h->stream>>>(c);
+    // Morton codes go to the sort inputs
+    BuildCtx cm = c;
+    cm.morton = morton_in;
+    cm.order = order_in;
+    k_morton<<<grid, B, 0, h->stream>>>(cm);
+    size_t sort_bytes = 0;
+    RB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, morton_in, c.morton, order_in, c.order, (int)n, 0, 63,
+                                            h->stream));
+    void* sort_tmp = nullptr;
+    RB_CUDA(cudaMalloc(&sort_tmp, std::max<size_t>(sort_bytes, 16)));
+    tmp.push_back(sort_tmp);
+    RB_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, morton_in, c.morton, order_in, c.order, (int)n, 0, 63,
+                                            h->stream));
+    uint32_t n_nodes = 0, depth = 0;
+    if (n <= RB_LEAF_MAX) {
+      k_tiny_root<<<1, 1, 0, h->stream>>>(c);
+      n_nodes = 1;
+      depth = 1;
+    } else {
+      k_karras<<<grid, B, 0, h->stream>>>(c);
+      k_fit<<<grid, B, 0, h->stream>>>(c);
+      // level-synchronous collapse, root binary node 0 -> node8 0
+      const int first[2] = {0, 0};
+      RB_CUDA(cudaMemcpyAsync(q[0], first, sizeof(first), cudaMemcpyHostToDevice, h->stream));
+      const int init_counters[4] = {1, 0, 0, 0};
+      RB_CUDA(cudaMemcpyAsync(c.counters, init_counters, sizeof(init_counters), cudaMemcpyHostToDevice, h->stream));
+      int len = 1, cur = 0;
+      while (len > 0) {
+        c.q_in = q[cur];
+        c.q_out = q[cur ^ 1];
+        c.q_in_len = len;
+        RB_CUDA(cudaMemsetAsync(c.counters + 2, 0, sizeof(int), h->stream));
+        k_collapse<<<(len + 127) / 128, 128, 0, h->stream>>>(c);
+        int hc[4];
+        RB_CUDA(cudaMemcpyAsync(hc, c.counters, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
+        RB_CUDA(cudaStreamSynchronize(h->stream));
+        if ((size_t)hc[0] > max_nodes) {
+          h->err = "build_bvh: node pool overflow";
+          return RB_ERR_CUDA;
+        }
+        len = hc[2];
+        n_nodes = (uint32_t)hc[0];
+        cur ^= 1;
+        depth++;
+        if (depth > 4096) {
+          h->err = "build_bvh: collapse did not terminate";
+          return RB_ERR_CUDA;
+        }
+      }
+      int hc[4];
+      RB_CUDA(cudaMemcpyAsync(hc, c.counters, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
+      RB_CUDA(cudaStreamSynchronize(h->stream));
+      if ((uint32_t)hc[1] != n) {
+        h->err = "build_bvh: emitted " + std::to_string(hc[1]) + " leaf triangles for " + std::to_string(n);
+        return RB_ERR_CUDA;
+      }
+    }
+    RB_CUDA(cudaGetLastError());
+    if (depth >= RB_STACK_MAX) {
+      h->err = "build_bvh: tree depth " + std::to_string(depth) + " exceeds the traversal stack";
+      return RB_ERR_UNSUPPORTED;
+    }
+    F4* node8 = nullptr;
+    RB_TRY(dev_alloc(h, &node8, 5 * (size_t)n_nodes, h->sceneAllocs));
+    RB_CUDA(cudaMemcpyAsync(node8, node8_big, 80 * (size_t)n_nodes, cudaMemcpyDeviceToDevice, h->stream));
+    RB_CUDA(cudaStreamSynchronize(h->stream));
+    *node8_out = node8;
+    *tri_isect_out = tri_isect;
+    *n_nodes_out = n_nodes;
+    *depth_out = depth;
+    return RB_OK;
+  };
+  int rc = body();
+  cudaStreamSynchronize(h->stream);
+  cleanup();
+  return rc;
+}
+
+int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
+  if (!h || !sd || (sd->n_surfaces && !sd->surfaces) || (sd->n_materials && !sd->materials)) return RB_ERR_INVALID_ARGUMENT;
+  RB_CUDA(cudaSetDevice(h->info.device));
+  RB_CUDA(cudaStreamSynchronize(h->stream));
+  free_list(h->sceneAllocs);
+  h->haveScene = false;
+  h->havePrev = false;
+
+  HostScene hs;
+  {
+    int frc = flatten_scene(sd, hs, h->err);
+    if (frc != RB_OK) return frc;
+  }
+  const size_t n = hs.n;
+  const size_t NL = hs.emissive.size();
+  const float maxabs = hs.maxabs, totalSurface = hs.totalSurface;
+  std::vector<float>& pos = hs.pos;
+  std::vector<F4>&nrm = hs.nrm, &mat = hs.mat, &light = hs.light;
+  std::vector<U4>& info = hs.info;
+  std::vector<float>&cdf = hs.cdf, &alias_prob = hs.alias_prob;
+  std::vector<uint32_t>& alias_idx = hs.alias_idx;
+
+  // ---- upload -------------------------------------------------------------------------------
+  cudaEvent_t t0, t1;
+  RB_CUDA(cudaEventCreate(&t0));
+  RB_CUDA(cudaEventCreate(&t1));
+  float* d_pos = nullptr;
+  F4 *d_nrm = nullptr, *d_mat = nullptr, *d_light = nullptr;
+  U4* d_info = nullptr;
+  float *d_cdf = nullptr, *d_ap = nullptr;
+  uint32_t* d_ai = nullptr;
+  std::vector<void*> tmp;
+  auto body = [&]() -> int {
+    RB_TRY(dev_alloc(h, &d_pos, 9 * n, tmp));
+    RB_TRY(dev_alloc(h, &d_nrm, 3 * n, h->sceneAllocs));
+    RB_TRY(dev_alloc(h, &d_info, n, h->sceneAllocs));
+    RB_TRY(dev_alloc(h, &d_mat, mat.size(), h->sceneAllocs));
+    RB_TRY(dev_alloc(h, &d_light, light.size(), h->sceneAllocs));
+    RB_TRY(dev_alloc(h, &d_cdf, NL, h->sceneAllocs));
+    RB_TRY(dev_alloc(h, &d_ap, NL, h->sceneAllocs));
+    RB_TRY(dev_alloc(h, &d_ai, NL, h->sceneAllocs));
+    auto up = [&](void* d, const void* s, size_t bytes) -> cudaError_t {
+      return bytes ? cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
+    };
+    RB_CUDA(up(d_pos, pos.data(), pos.size() * 4));
+    RB_CUDA(up(d_nrm, nrm.data(), nrm.size() * 16));
+    RB_CUDA(up(d_info, info.data(), info.size() * 16));
+    RB_CUDA(up(d_mat, mat.data(), mat.size() * 16));
+    RB_CUDA(up(d_light, light.data(), light.size() * 16));
+    RB_CUDA(up(d_cdf, cdf.data(), NL * 4));
+    RB_CUDA(up(d_ap, alias_prob.data(), NL * 4));
+    RB_CUDA(up(d_ai, alias_idx.data(), NL * 4));
+    RB_CUDA(cudaStreamSynchronize(h->stream));
+    F4 *node8 = nullptr, *tri_isect = nullptr;
+    uint32_t n_nodes = 0, depth = 0;
+    RB_CUDA(cudaEventRecord(t0, h->stream));
+    if (n > 0) RB_TRY(build_bvh(h, d_pos, (uint32_t)n, maxabs, &node8, &tri_isect, &n_nodes, &depth));
+    RB_CUDA(cudaEventRecord(t1, h->stream));
+    RB_CUDA(cudaEventSynchronize(t1));
+    float ms = 0;
+    RB_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+    SceneDev& sc = h->sc;
+    sc.node8 = node8;
+    sc.tri_isect = tri_isect;
+    sc.tri_normals = d_nrm;
+    sc.tri_info = d_info;
+    sc.mat = d_mat;
+    sc.light = d_light;
+    sc.cdf = d_cdf;
+    sc.alias_prob = d_ap;
+    sc.alias_idx = d_ai;
+    sc.n_lights = (uint32_t)NL;
+    sc.n_tris = (uint32_t)n;
+    sc.n_nodes = n_nodes;
+    sc.total_area = totalSurface;
+    RbSceneStats& st = h->stats;
+    memset(&st, 0, sizeof(st));
+    st.n_triangles = (uint32_t)n;
+    st.n_emissive = (uint32_t)NL;
+    st.n_bvh_nodes = n_nodes;
+    st.bvh_depth = depth;
+    st.build_ms = ms;
+    st.total_emissive_area = totalSurface;
+    for (int a = 0; a < 3; ++a) st.bounds_lo[a] = FLT_MAX, st.bounds_hi[a] = -FLT_MAX;
+    for (size_t i = 0; i < pos.size(); ++i) {
+      st.bounds_lo[i % 3] = std::min(st.bounds_lo[i % 3], pos[i]);
+      st.bounds_hi[i % 3] = std::max(st.bounds_hi[i % 3], pos[i]);
+    }
+    return RB_OK;
+  };
+  int rc = body();
+  cudaStreamSynchronize(h->stream);
+  free_list(tmp);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  if (rc != RB_OK) {
+    free_list(h->sceneAllocs);
+    return rc;
+  }
+  h->haveScene = true;
+  return RB_OK;
+}
+
+int rb_scene_stats(RbHandle h, RbSceneStats* out) {
+  if (!h || !out) return RB_ERR_INVALID_ARGUMENT;
+  if (!h->haveScene) {
+    h->err = "rb_scene_stats: no scene";
+    return RB_ERR_NO_SCENE;
+  }
+  *out = h->stats;
+  return RB_OK;
+}
+
+// -------------------------------------------------------------------------------------
+// frame
+// -------------------------------------------------------------------------------------
+static CamState cam_state(const RbCamera* c) {
+  CamState s;
+  s.pos = v3(c->pos[0], c->pos[1], c->pos[2]);
+  s.focal = c->focal_px;
+  memcpy(s.viewMat, c->viewMat, sizeof(s.viewMat));
+  memcpy(s.invViewMat, c->invViewMat, sizeof(s.invViewMat));
+  return s;
+}
+
+static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx, RbTimings* timings) {
+  if (!h || !cam) return RB_ERR_INVALID_ARGUMENT;
+  if (!h->haveScene) {
+    h->err = "rb_render_frame: no scene uploaded";
+    return RB_ERR_NO_SCENE;
+  }
+  RB_CUDA(cudaSetDevice(h->info.device));
+  const RbParams P = h->params;  // snapshot (the GUI thread may edit the host copy)
+  const bool timed = h->info.collect_timings != 0 && timings != nullptr;
+  cudaStream_t st = h->stream;
+
+  FrameCtx fc{};
+  fc.width = h->info.width;
+  fc.height = h->info.height;
+  fc.y0 = h->info.band_y0;
+  fc.y1 = h->info.band_y1;
+  fc.sc = h->sc;
+  fc.P = P;
+  fc.cam = cam_state(cam);
+  fc.prevCam = h->havePrev ? h->prevCam : fc.cam;
+  fc.G = h->G[h->gCur];
+  fc.Gprev = h->G[h->gCur ^ 1];
+  fc.frame = h->frame;
+  fc.counters = h->counters;
+  const dim3 block(kTileW, kTileH);
+  const dim3 grid((fc.width + kTileW - 1) / kTileW, (fc.y1 - fc.y0 + kTileH - 1) / kTileH);
+  uint32_t launches = 0;
+  int evi = 0;
+  auto mark = [&]() {
+    if (timed) cudaEventRecord(h->ev[evi], st);
+    evi++;
+  };
+  auto bind = [&]() {
+    fc.Rread = h->R[h->rRead];
+    fc.Rwrite = h->R[h->rWrite];
+    fc.Rlast = h->R[h->rLast];
+  };
+  auto swap_rw = [&]() { std::swap(h->rRead, h->rWrite); };  // swapReservoirBuffers, P/simpleguidx11.h:116
+
+  RB_CUDA(cudaMemsetAsync(h->counters, 0, 64, st));
+  mark();  // 0
+  bind();
+  fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_GBUF, 0);
+  k_gbuffer<<<grid, block, 0, st>>>(fc);
+  launches++;
+  mark();  // 1
+  fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_INITIAL, 0);
+  k_initial<<<grid, block, 0, st>>>(fc);
+  launches++;
+  mark();  // 2
+  if (P.doVisibilityPass) {
+    k_visibility<<<grid, block, 0, st>>>(fc);
+    launches++;
+  }
+  mark();  // 3
+  if (P.doTemporalReuse && frame_idx > 0 && h->havePrev) {
+    swap_rw();
+    bind();
+    fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_TEMPORAL, 0);
+    k_temporal<<<grid, block, 0, st>>>(fc);
+    launches++;
+  }
+  mark();  // 4
+  if (P.doSpatialReuse) {
+    for (int i = 0; i < P.spatialPassCount; ++i) {
+      swap_rw();
+      bind();
+      fc.spatial_iter = i;
+      fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_SPATIAL, (uint32_t)i);
+      k_spatial<<<grid, block, 0, st>>>(fc);
+      launches++;
+    }
+  }
+  mark();  // 5
+  swap_rw();
+  bind();
+  k_shade<<<grid, block, 0, st>>>(fc);
+  launches++;
+  mark();  // 6
+  RB_CUDA(cudaGetLastError());
+  // memcpy(reservoirsLastFrame, ...) + gBufferLastFrame.setDataFrom(gBuffer) (P/simpleguidx11.cpp:478-481) by rotation
+  std::swap(h->rLast, h->rRead);
+  h->gCur ^= 1;
+  h->prevCam = fc.cam;
+  h->havePrev = true;
+
+  if (timings) {
+    memset(timings, 0, sizeof(*timings));
+    unsigned long long hc[8];
+    RB_CUDA(cudaMemcpyAsync(hc, h->counters, 64, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    timings->rays_closest = hc[0];
+    timings->rays_any_as_written = hc[1];
+    timings->rays_any_traced = hc[2];
+    timings->kernel_launches = launches;
+    if (timed) {
+      float ms[6];
+      for (int i = 0; i < 6; ++i) RB_CUDA(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+      timings->ms_gbuffer = ms[0];
+      timings->ms_initial = ms[1];
+      timings->ms_visibility = ms[2];
+      timings->ms_temporal = ms[3];
+      timings->ms_spatial = ms[4];
+      timings->ms_shade = ms[5];
+      RB_CUDA(cudaEventElapsedTime(&timings->ms_total, h->ev[0], h->ev[6]));
+    }
+  }
+  return RB_OK;
+}
+
+int rb_render_frame(RbHandle h, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_out, RbTimings* timings) {
+  int rc = render_frame_impl(h, cam, frame_idx, timings);
+  if (rc != RB_OK) return rc;
+  if (frame_rgb_out) {
+    const size_t row = (size_t)h->info.width * 3;
+    const size_t off = row * h->info.band_y0, cnt = row * (h->info.band_y1 - h->info.band_y0);
+    RB_CUDA(cudaMemcpyAsync(frame_rgb_out + off, h->frame + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return RB_OK;
+}
+
+int rb_render_frame_device(RbHandle h, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_dev, RbTimings* timings) {
+  int rc = render_frame_impl(h, cam, frame_idx, timings);
+  if (rc != RB_OK) return rc;
+  if (frame_rgb_dev) {
+    const size_t row = (size_t)h->info.width * 3;
+    const size_t off = row * h->info.band_y0, cnt = row * (h->info.band_y1 - h->info.band_y0);
+    RB_CUDA(cudaMemcpyAsync(frame_rgb_dev + off, h->frame + off, cnt * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return RB_OK;
+}
+
+int rb_synchronize(RbHandle h) {
+  if (!h) return RB_ERR_INVALID_ARGUMENT;
+  RB_CUDA(cudaSetDevice(h->info.device));
+  RB_CUDA(cudaStreamSynchronize(h->stream));
+  return RB_OK;
+}
+
+int rb_timer_begin(RbHandle h) {
+  if (!h) return RB_ERR_INVALID_ARGUMENT;
+  RB_CUDA(cudaSetDevice(h->info.device));
+  RB_CUDA(cudaEventRecord(h->ev[12], h->stream));
+  return RB_OK;
+}
+int rb_timer_end(RbHandle h, float* ms_out) {
+  if (!h || !ms_out) return RB_ERR_INVALID_ARGUMENT;
+  RB_CUDA(cudaSetDevice(h->info.device));
+  RB_CUDA(cudaEventRecord(h->ev[13], h->stream));
+  RB_CUDA(cudaEventSynchronize(h->ev[13]));
+  RB_CUDA(cudaEventElapsedTime(ms_out, h->ev[12], h->ev[13]));
+  return RB_OK;
+}
+
+int rb_readback(RbHandle h, int id, void* dst, size_t bytes) {
+  if (!h || !dst) return RB_ERR_INVALID_ARGUMENT;
+  RB_CUDA(cudaSetDevice(h->info.device));
+  const size_t n = (size_t)h->info.width * h->info.height;
+  const GBufPlanes& G = h->G[h->gCur ^ 1];  // the frame just rendered (rotated to "previous")
+  const ResPlanes& R = h->R[h->rLast];
+  const void* src = nullptr;
+  size_t need = 0;
+  switch (id) {
+    case RB_BUF_GBUF_POS_DEPTH: src = G.pos_depth, need = n * 16; break;
+    case RB_BUF_GBUF_NORMAL_SHIN: src = G.normal_shin, need = n * 16; break;
+    case RB_BUF_GBUF_DIFFUSE_IIM: src = G.diffuse_iim, need = n * 16; break;
+    case RB_BUF_GBUF_SPEC_TYPE: src = G.spec_type, need = n * 16; break;
+    case RB_BUF_GBUF_EMISSION: src = G.emission, need = n * 16; break;
+    case RB_BUF_HIT_IDS: src = G.hit_ids, need = n * 8; break;
+    case RB_BUF_RES_POINT_WSUM: src = R.point_wsum, need = n * 16; break;
+    case RB_BUF_RES_NORMAL_W: src = R.normal_W, need = n * 16; break;
+    case RB_BUF_RES_LI_CONF: src = R.Li_conf, need = n * 16; break;
+    case RB_BUF_RES_LIGHT_IDX: src = R.light_idx, need = n * 4; break;
+    case RB_BUF_FRAME_RGB: src = h->frame, need = n * 12; break;
+    case RB_BUF_ALIAS_PROB: src = h->sc.alias_prob, need = (size_t)h->sc.n_lights * 4; break;
+    case RB_BUF_ALIAS_IDX: src = h->sc.alias_idx, need = (size_t)h->sc.n_lights * 4; break;
+    case RB_BUF_LIGHT_CDF: src = h->sc.cdf, need = (size_t)h->sc.n_lights * 4; break;
+    default: h->err = "rb_readback: unknown buffer id"; return RB_ERR_INVALID_ARGUMENT;
+  }
+  if (id >= RB_BUF_ALIAS_PROB && !h->haveScene) {
+    h->err = "rb_readback: no scene";
+    return RB_ERR_NO_SCENE;
+  }
+  if (bytes < need) {
+    h->err = "rb_readback: destination too small";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  if (need) RB_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, h->stream));
+  RB_CUDA(cudaStreamSynchronize(h->stream));
+  return RB_OK;
+}
+
+// -------------------------------------------------------------------------------------
+// ray seam
+// -------------------------------------------------------------------------------------
+static int trace_device(RbHandle h, const RbRay* rays, void* out, uint32_t n, bool any, float* ms_out) {
+  if (!h || (n && (!rays || !out))) return RB_ERR_INVALID_ARGUMENT;
+  if (!h->haveScene) {
+    h->err = "rb_trace: no scene uploaded";
+    return RB_ERR_NO_SCENE;
+  }
+  RB_CUDA(cudaSetDevice(h->info.device));
+  if (n == 0) {
+    if (ms_out) *ms_out = 0;
+    return RB_OK;
+  }
+  if (ms_out) RB_CUDA(cudaEventRecord(h->ev[14], h->stream));
+  const unsigned grid = (n + 255) / 256;
+  if (any)
+    k_trace_any<<<grid, 256, 0, h->stream>>>(h->sc, rays, (uint8_t*)out, n);
+  else
+    k_trace_closest<<<grid, 256, 0, h->stream>>>(h->sc, rays, (RbHit*)out, n);
+  RB_CUDA(cudaGetLastError());
+  if (ms_out) {
+    RB_CUDA(cudaEventRecord(h->ev[15], h->stream));
+    RB_CUDA(cudaEventSynchronize(h->ev[15]));
+    RB_CUDA(cudaEventElapsedTime(ms_out, h->ev[14], h->ev[15]));
+  }
+  return RB_OK;
+}
+static int trace_host(RbHandle h, const RbRay* rays, void* out, size_t out_elem, uint32_t n, bool any) {
+  if (!h || (n && (!rays || !out))) return RB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return RB_OK;
+  RB_CUDA(cudaSetDevice(h->info.device));
+  RbRay* d_rays = nullptr;
+  void* d_out = nullptr;
+  RB_CUDA(cudaMalloc(&d_rays, (size_t)n * sizeof(RbRay)));
+  cudaError_t e = cudaMalloc(&d_out, (size_t)n * out_elem);
+  if (e != cudaSuccess) {
+    cudaFree(d_rays);
+    h->err = "rb_trace: out of device memory";
+    return RB_ERR_OUT_OF_MEMORY;
+  }
+  int rc = RB_OK;
+  auto body = [&]() -> int {
+    RB_CUDA(cudaMemcpyAsync(d_rays, rays, (size_t)n * sizeof(RbRay), cudaMemcpyHostToDevice, h->stream));
+    RB_TRY(trace_device(h, d_rays, d_out, n, any, nullptr));
+    RB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * out_elem, cudaMemcpyDeviceToHost, h->stream));
+    RB_CUDA(cudaStreamSynchronize(h->stream));
+    return RB_OK;
+  };
+  rc = body();
+  cudaFree(d_rays);
+  cudaFree(d_out);
+  return rc;
+}
+int rb_trace_closest(RbHandle h, const RbRay* rays, RbHit* hits, uint32_t n) {
+  return trace_host(h, rays, hits, sizeof(RbHit), n, false);
+}
+int rb_trace_occluded(RbHandle h, const RbRay* rays, uint8_t* occluded, uint32_t n) {
+  return trace_host(h, rays, occluded, 1, n, true);
+}
+int rb_trace_closest_device(RbHandle h, const RbRay* rays_dev, RbHit* hits_dev, uint32_t n, float* ms_out) {
+  return trace_device(h, rays_dev, hits_dev, n, false, ms_out);
+}
+int rb_trace_occluded_device(RbHandle h, const RbRay* rays_dev, uint8_t* occ_dev, uint32_t n, float* ms_out) {
+  return trace_device(h, rays_dev, occ_dev, n, true, ms_out);
+}
+
+// -------------------------------------------------------------------------------------
+// multi-GPU bands: halo rows of the current reservoir read buffer
+// -------------------------------------------------------------------------------------
+size_t rb_halo_bytes(RbHandle h, int32_t rows) {
+  if (!h || rows < 0) return 0;
+  return (size_t)rows * h->info.width * 52;
+}
+static int halo_copy(RbHandle h, int32_t y, int32_t rows, void* host, bool to_host) {
+  if (!h || !host || y < 0 || rows < 0 || y + rows > h->info.height) return RB_ERR_INVALID_ARGUMENT;
+  RB_CUDA(cudaSetDevice(h->info.device));
+  const ResPlanes& R = h->R[h->rLast];
+  const size_t px = (size_t)rows * h->info.width, off = (size_t)y * h->info.width;
+  char* p = (char*)host;
+  void* planes[4] = {R.point_wsum + off, R.normal_W + off, R.Li_conf + off, R.light_idx + off};
+  const size_t sz[4] = {px * 16, px * 16, px * 16, px * 4};
+  for (int i = 0; i < 4; ++i) {
+    if (to_host)
+      RB_CUDA(cudaMemcpyAsync(p, planes[i], sz[i], cudaMemcpyDeviceToHost, h->stream));
+    else
+      RB_CUDA(cudaMemcpyAsync(planes[i], p, sz[i], cudaMemcpyHostToDevice, h->stream));
+    p += sz[i];
+  }
+  RB_CUDA(cudaStreamSynchronize(h->stream));
+  return RB_OK;
+}
+int rb_halo_export(RbHandle h, int32_t y, int32_t rows, void* dst_host) { return halo_copy(h, y, rows, dst_host, true); }
+int rb_halo_import(RbHandle h, int32_t y, int32_t rows, const void* src_host) {
+  return halo_copy(h, y, rows, const_cast<void*>(src_host), false);
+}
+
+int rb_comm_unique_id(void* out_id, size_t id_bytes) {
+  (void)out_id;
+  (void)id_bytes;
+  return RB_ERR_UNSUPPORTED;
+}
+int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes) {
+  (void)rank;
+  (void)nranks;
+  (void)nccl_unique_id;
+  (void)id_bytes;
+  if (h) h->err = "rb_comm_init: NCCL band exchange not built yet";
+  return RB_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

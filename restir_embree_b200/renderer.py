@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference's frame driver for the ReSTIR path.
+
+`Renderer` plays the role SimpleGuiDX11 plays around produceRestir
+(P/simpleguidx11.cpp:359-487): it owns the handle whose device state persists across
+frames (reservoir ping-pong + last frame, G-buffer + last frame), takes the scene the way
+ModelLoader::loadScene produces it, the ReSTIRIntegrator statics as RbParams, and one Camera
+per frame, and returns `frame_data` (linear HDR, float3 per pixel).
+
+All compute happens in restir_embree_b200/librestir_b200.so (hand-written CUDA behind the
+C ABI of include/restir_b200.h). There is no CPU fallback: a missing library or a missing
+GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librestir_b200.so")
+
+_lib = None
+
+
+class RestirError(RuntimeError):
+    """Raised where the reference's Embree error callback would throw (P/tutorials.cpp:6-24)."""
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RestirError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). This package has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    L.rb_abi_version.restype = C.c_uint32
+    L.rb_last_error.restype = C.c_char_p
+    L.rb_last_error.argtypes = [H]
+    L.rb_default_params.argtypes = [C.POINTER(abi.RbParams)]
+    L.rb_create.argtypes = [C.POINTER(abi.RbCreateInfo), C.POINTER(H)]
+    L.rb_destroy.argtypes = [H]
+    L.rb_upload_scene.argtypes = [H, C.POINTER(abi.RbSceneDesc)]
+    L.rb_set_params.argtypes = [H, C.POINTER(abi.RbParams)]
+    L.rb_render_frame.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
+    L.rb_render_frame_device.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
+    L.rb_readback.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
+    L.rb_synchronize.argtypes = [H]
+    L.rb_timer_begin.argtypes = [H]
+    L.rb_timer_end.argtypes = [H, C.POINTER(C.c_float)]
+    L.rb_trace_closest.argtypes = [H, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.rb_trace_occluded.argtypes = [H, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.rb_trace_closest_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    L.rb_trace_occluded_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    L.rb_scene_stats.argtypes = [H, C.POINTER(abi.RbSceneStats)]
+    L.rb_comm_init.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]
+    L.rb_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+    L.rb_halo_bytes.restype = C.c_size_t
+    L.rb_halo_bytes.argtypes = [H, C.c_int32]
+    L.rb_halo_export.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
+    L.rb_halo_import.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
+    if L.rb_abi_version() != 1:
+        raise RestirError("librestir_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+class Renderer:
+    def __init__(self, width, height, device=0, seed=123, band=None, collect_timings=True):
+        self.L = load_library()
+        self.width, self.height = int(width), int(height)
+        info = abi.RbCreateInfo()
+        info.width, info.height, info.device, info.seed = self.width, self.height, int(device), int(seed)
+        info.band_y0, info.band_y1 = band if band is not None else (0, self.height)
+        info.collect_timings = 1 if collect_timings else 0
+        self.band = (info.band_y0, info.band_y1)
+        self.h = C.c_void_p()
+        rc = self.L.rb_create(C.byref(info), C.byref(self.h))
+        if rc != abi.RB_OK:
+            msg = self.L.rb_last_error(None)
+            self.h = None
+            raise RestirError(f"rb_create failed ({rc}): {msg.decode() if msg else ''}")
+        self._scene_keep = None
+        self.params = abi.default_params()
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != abi.RB_OK:
+            msg = self.L.rb_last_error(self.h)
+            raise RestirError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # -- scene / params ---------------------------------------------------------------
+    def upload_scene(self, scene):
+        d, keep = scene.desc()
+        self._check(self.L.rb_upload_scene(self.h, C.byref(d)), "rb_upload_scene")
+        self._scene_keep = None  # arrays are copied by the library
+        del keep
+        return self.scene_stats()
+
+    def scene_stats(self):
+        s = abi.RbSceneStats()
+        self._check(self.L.rb_scene_stats(self.h, C.byref(s)), "rb_scene_stats")
+        return dict(n_triangles=s.n_triangles, n_emissive=s.n_emissive, n_bvh_nodes=s.n_bvh_nodes,
+                    bvh_depth=s.bvh_depth, build_ms=s.build_ms, total_emissive_area=s.total_emissive_area,
+                    bounds_lo=tuple(s.bounds_lo), bounds_hi=tuple(s.bounds_hi))
+
+    def set_params(self, p):
+        self._check(self.L.rb_set_params(self.h, C.byref(p)), "rb_set_params")
+        self.params = p
+
+    # -- frames -------------------------------------------------------------------------
+    def render_frame(self, cam, frame_idx, out=None, want_timings=False, fetch=True):
+        """produceRestir: returns frame_data [h, w, 3] float32 (host). `out` may be a pinned numpy view."""
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        t = abi.RbTimings() if want_timings else None
+        ptr = None
+        if fetch:
+            if out is None:
+                out = np.zeros((self.height, self.width, 3), dtype=np.float32)
+            assert out.dtype == np.float32 and out.size == self.width * self.height * 3 and out.flags["C_CONTIGUOUS"]
+            ptr = out.ctypes.data
+        rc = self.L.rb_render_frame(self.h, C.byref(c), int(frame_idx), ptr, C.byref(t) if t is not None else None)
+        self._check(rc, "rb_render_frame")
+        if want_timings:
+            return out, {k: getattr(t, k) for k, _ in abi.RbTimings._fields_ if k != "reserved"}
+        return out
+
+    def render_frame_device(self, cam, frame_idx, dev_ptr=None, want_timings=False):
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        t = abi.RbTimings() if want_timings else None
+        rc = self.L.rb_render_frame_device(self.h, C.byref(c), int(frame_idx), dev_ptr,
+                                           C.byref(t) if t is not None else None)
+        self._check(rc, "rb_render_frame_device")
+        if want_timings:
+            return {k: getattr(t, k) for k, _ in abi.RbTimings._fields_ if k != "reserved"}
+        return None
+
+    def synchronize(self):
+        self._check(self.L.rb_synchronize(self.h), "rb_synchronize")
+
+    def timer_begin(self):
+        self._check(self.L.rb_timer_begin(self.h), "rb_timer_begin")
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        self._check(self.L.rb_timer_end(self.h, C.byref(ms)), "rb_timer_end")
+        return ms.value
+
+    def readback(self, buf):
+        dt, ch = abi.BUFFER_LAYOUT[buf]
+        a = np.empty((self.height, self.width, ch), dtype=dt)
+        self._check(self.L.rb_readback(self.h, buf, a.ctypes.data, a.nbytes), "rb_readback")
+        return a
+
+    def light_table(self, buf):
+        n = self.scene_stats()["n_emissive"]
+        a = np.empty(n, dtype=np.uint32 if buf == abi.BUF_ALIAS_IDX else np.float32)
+        self._check(self.L.rb_readback(self.h, buf, a.ctypes.data, a.nbytes), "rb_readback")
+        return a
+
+    # -- ray seam -------------------------------------------------------------------------
+    def trace_closest(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=abi.RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=abi.HIT_DTYPE)
+        self._check(self.L.rb_trace_closest(self.h, rays.ctypes.data, hits.ctypes.data, rays.shape[0]), "rb_trace_closest")
+        return hits
+
+    def trace_occluded(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=abi.RAY_DTYPE)
+        occ = np.empty(rays.shape[0], dtype=np.uint8)
+        self._check(self.L.rb_trace_occluded(self.h, rays.ctypes.data, occ.ctypes.data, rays.shape[0]), "rb_trace_occluded")
+        return occ
+
+    def trace_device(self, rays_ptr, out_ptr, n, any_hit):
+        ms = C.c_float(0)
+        fn = self.L.rb_trace_occluded_device if any_hit else self.L.rb_trace_closest_device
+        self._check(fn(self.h, rays_ptr, out_ptr, int(n), C.byref(ms)), "rb_trace_*_device")
+        return ms.value
+
+    # -- band halos -------------------------------------------------------------------------
+    def halo_export(self, y, rows):
+        buf = np.empty(self.L.rb_halo_bytes(self.h, rows), dtype=np.uint8)
+        self._check(self.L.rb_halo_export(self.h, y, rows, buf.ctypes.data), "rb_halo_export")
+        return buf
+
+    def halo_import(self, y, rows, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        assert buf.nbytes == self.L.rb_halo_bytes(self.h, rows)
+        self._check(self.L.rb_halo_import(self.h, y, rows, buf.ctypes.data), "rb_halo_import")
+
+
+def make_rays(org, target=None, direction=None, tnear=0.01, tfar=None, tfar_offset=0.001):
+    """Rays in the RTCRay layout. With `target`: shadow rays as Intersection::testOcclusion builds them
+    (P/Intersection.h:43-60): dir = normalize(to-from), tnear = FLT_MIN + 0.01, tfar = dist - 0.001."""
+    org = np.asarray(org, dtype=np.float32).reshape(-1, 3)
+    n = org.shape[0]
+    rays = np.zeros(n, dtype=abi.RAY_DTYPE)
+    rays["org"] = org
+    if target is not None:
+        d = np.asarray(target, dtype=np.float32).reshape(-1, 3) - org
+        dist = np.sqrt((d * d).sum(1, dtype=np.float32), dtype=np.float32)
+        rays["dir"] = d * (np.float32(1.0) / dist)[:, None]
+        rays["tfar"] = dist - np.float32(tfar_offset)
+    else:
+        rays["dir"] = np.asarray(direction, dtype=np.float32).reshape(-1, 3)
+        rays["tfar"] = np.float32(3.4028235e38) if tfar is None else np.asarray(tfar, dtype=np.float32)
+    rays["tnear"] = np.float32(1.17549435e-38) + np.float32(tnear)
+    return rays

@@ -1,0 +1,380 @@
+// emu.cpp — TEST-ONLY host emulation of the CUDA kernel bodies.
+//
+// The product's per-thread kernel bodies (rb_build.cuh, rb_scene.cuh, rb_passes.cuh) are
+// __host__ __device__ functions; this harness compiles the SAME source with g++ and runs
+// each "kernel" as a plain loop over thread indices, so the CPU-only test tier
+// (pytest -m "not gpu") can check the kernel logic — BVH build, traversal, all passes —
+// bit for bit against the oracle before any GPU time is spent.
+//
+// It is NOT part of the product: nothing under restir_embree_b200/ loads it, bench.py never
+// touches it, and the shipped library (librestir_b200.so) has no CPU path at all.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../restir_embree_b200/csrc/rb_build.cuh"
+#include "../../restir_embree_b200/csrc/rb_host_scene.h"
+#include "../../restir_embree_b200/csrc/rb_passes.cuh"
+
+using namespace rb;
+
+struct Emu {
+  int width = 0, height = 0, y0 = 0, y1 = 0;
+  uint32_t seed = 123;
+  RbParams P{};
+  HostScene hs;
+  std::vector<F4> node8, tri_isect;
+  uint32_t n_nodes = 0, depth = 0;
+  SceneDev sc{};
+  bool haveScene = false, havePrev = false;
+  // frame state
+  struct GStore {
+    std::vector<F4> a, b, c, d, e;
+    std::vector<U2> ids;
+  } gs[2];
+  struct RStore {
+    std::vector<F4> a, b, c;
+    std::vector<int> li;
+  } rs[3];
+  int gCur = 0, rRead = 0, rWrite = 1, rLast = 2;
+  std::vector<float> frame;
+  unsigned long long counters[8] = {0};
+  CamState prevCam{};
+  std::string err;
+
+  GBufPlanes gp(int i) { return GBufPlanes{gs[i].a.data(), gs[i].b.data(), gs[i].c.data(), gs[i].d.data(), gs[i].e.data(), gs[i].ids.data()}; }
+  ResPlanes rp(int i) { return ResPlanes{rs[i].a.data(), rs[i].b.data(), rs[i].c.data(), rs[i].li.data()}; }
+};
+
+static int emu_build_bvh(Emu* E) {
+  const uint32_t n = (uint32_t)E->hs.n;
+  BuildCtx c{};
+  c.n = n;
+  c.tri_pos = E->hs.pos.data();
+  c.pad = E->hs.maxabs * (1.0f / 262144.0f) + 1e-30f;
+  int bounds[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+  c.scene_bounds = bounds;
+  std::vector<F4> tlo(n), thi(n), ilo(n), ihi(n);
+  std::vector<uint64_t> morton(n), morton_sorted(n);
+  std::vector<uint32_t> order(n), order_sorted(n);
+  std::vector<int> left(n), right(n), parent(n), leaf_parent(n), rlo(n), rhi(n), visit(n, 0);
+  c.tbox_lo = tlo.data(), c.tbox_hi = thi.data();
+  c.morton = morton.data(), c.order = order.data();
+  c.left = left.data(), c.right = right.data(), c.parent = parent.data(), c.leaf_parent = leaf_parent.data();
+  c.range_lo = rlo.data(), c.range_hi = rhi.data(), c.ibox_lo = ilo.data(), c.ibox_hi = ihi.data(), c.visit = visit.data();
+  int counters[4] = {1, 0, 0, 0};
+  c.counters = counters;
+  const size_t max_nodes = (size_t)n / 2 + 8;
+  std::vector<F4> node8(5 * max_nodes);
+  E->tri_isect.assign(3 * (size_t)n, F4{0, 0, 0, 0});
+  c.node8 = node8.data();
+  c.tri_isect = E->tri_isect.data();
+  for (uint32_t i = 0; i < n; ++i) bounds_body(c, i);
+  for (uint32_t i = 0; i < n; ++i) morton_body(c, i);
+  // radix sort stand-in: stable sort by key (cub::DeviceRadixSort is stable too)
+  std::vector<uint32_t> perm(n);
+  std::iota(perm.begin(), perm.end(), 0u);
+  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return morton[a] < morton[b]; });
+  for (uint32_t i = 0; i < n; ++i) morton_sorted[i] = morton[perm[i]], order_sorted[i] = order[perm[i]];
+  c.morton = morton_sorted.data();
+  c.order = order_sorted.data();
+  uint32_t depth = 0, n_nodes = 0;
+  if (n <= RB_LEAF_MAX) {
+    tiny_root_body(c);
+    n_nodes = 1, depth = 1;
+  } else {
+    // run the per-thread bodies in a scrambled order to mimic unordered GPU scheduling
+    for (uint32_t i = 0; i + 1 < n; ++i) karras_body(c, n - 2 - i);
+    for (uint32_t i = 0; i < n; ++i) fit_body(c, n - 1 - i);
+    std::vector<int> q[2];
+    q[0].assign(2 * (size_t)n + 2, 0);
+    q[1].assign(2 * (size_t)n + 2, 0);
+    int len = 1, cur = 0;
+    while (len > 0) {
+      c.q_in = q[cur].data();
+      c.q_out = q[cur ^ 1].data();
+      c.q_in_len = len;
+      counters[2] = 0;
+      for (int w = len - 1; w >= 0; --w) collapse_body(c, (uint32_t)w);
+      if ((size_t)counters[0] > max_nodes) return -2;
+      len = counters[2];
+      n_nodes = (uint32_t)counters[0];
+      cur ^= 1;
+      depth++;
+      if (depth > 4096) return -2;
+    }
+    if ((uint32_t)counters[1] != n) return -2;
+  }
+  if (depth >= RB_STACK_MAX) return -4;
+  node8.resize(5 * (size_t)n_nodes);
+  E->node8 = node8;
+  E->n_nodes = n_nodes;
+  E->depth = depth;
+  return 0;
+}
+
+extern "C" {
+
+void* emu_create(int width, int height, uint32_t seed, int y0, int y1) {
+  Emu* E = new Emu();
+  E->width = width, E->height = height, E->seed = seed, E->y0 = y0, E->y1 = y1;
+  const size_t n = (size_t)width * height;
+  for (auto& g : E->gs) {
+    g.a.assign(n, F4{0, 0, 0, 0}), g.b = g.a, g.c = g.a, g.d = g.a, g.e = g.a;
+    g.ids.assign(n, U2{0xFFFFFFFFu, 0xFFFFFFFFu});
+  }
+  for (auto& r : E->rs) {
+    r.a.assign(n, F4{0, 0, 0, 0}), r.b = r.a, r.c = r.a;
+    r.li.assign(n, -1);
+  }
+  E->frame.assign(n * 3, 0.0f);
+  return E;
+}
+void emu_destroy(void* h) { delete (Emu*)h; }
+const char* emu_last_error(void* h) { return ((Emu*)h)->err.c_str(); }
+
+int emu_upload_scene(void* h, const RbSceneDesc* sd) {
+  Emu* E = (Emu*)h;
+  int rc = flatten_scene(sd, E->hs, E->err);
+  if (rc != RB_OK) return rc;
+  E->n_nodes = 0;
+  if (E->hs.n > 0) {
+    rc = emu_build_bvh(E);
+    if (rc != 0) {
+      E->err = "emu_build_bvh failed";
+      return rc;
+    }
+  }
+  SceneDev& sc = E->sc;
+  sc.node8 = E->node8.data();
+  sc.tri_isect = E->tri_isect.data();
+  sc.tri_normals = E->hs.nrm.data();
+  sc.tri_info = E->hs.info.data();
+  sc.mat = E->hs.mat.data();
+  sc.light = E->hs.light.data();
+  sc.cdf = E->hs.cdf.data();
+  sc.alias_prob = E->hs.alias_prob.data();
+  sc.alias_idx = E->hs.alias_idx.data();
+  sc.n_lights = (uint32_t)E->hs.emissive.size();
+  sc.n_tris = (uint32_t)E->hs.n;
+  sc.n_nodes = E->n_nodes;
+  sc.total_area = E->hs.totalSurface;
+  E->haveScene = true;
+  E->havePrev = false;
+  return 0;
+}
+int emu_set_params(void* h, const RbParams* p) {
+  Emu* E = (Emu*)h;
+  if (p->useSkybox) return RB_ERR_UNSUPPORTED;
+  if (p->spatialReuseNeighborCount > RB_MAX_NEIGHBORS) return RB_ERR_UNSUPPORTED;
+  E->P = *p;
+  return 0;
+}
+void emu_scene_stats(void* h, uint32_t* out4) {
+  Emu* E = (Emu*)h;
+  out4[0] = (uint32_t)E->hs.n, out4[1] = (uint32_t)E->hs.emissive.size(), out4[2] = E->n_nodes, out4[3] = E->depth;
+}
+
+}  // extern "C"
+
+template <class F>
+static void for_pixels(Emu* E, FrameCtx& fc, F&& f) {
+  unsigned long long c0 = 0, c1 = 0, c2 = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : c0, c1, c2)
+  for (int y = fc.y0; y < fc.y1; ++y)
+    for (int x = 0; x < fc.width; ++x) {
+      Cnt cnt = {0, 0, 0};
+      f(x, y, cnt);
+      c0 += cnt.closest, c1 += cnt.anyW, c2 += cnt.anyT;
+    }
+  E->counters[0] += c0, E->counters[1] += c1, E->counters[2] += c2;
+}
+
+extern "C" {
+
+// mirrors render_frame_impl of restir_b200.cu (the host-side pass schedule)
+int emu_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rgb_out) {
+  Emu* E = (Emu*)h;
+  if (!E->haveScene) return RB_ERR_NO_SCENE;
+  const RbParams P = E->P;
+  FrameCtx fc{};
+  fc.width = E->width, fc.height = E->height, fc.y0 = E->y0, fc.y1 = E->y1;
+  fc.sc = E->sc;
+  fc.P = P;
+  fc.cam.pos = v3(cam->pos[0], cam->pos[1], cam->pos[2]);
+  fc.cam.focal = cam->focal_px;
+  memcpy(fc.cam.viewMat, cam->viewMat, 64);
+  memcpy(fc.cam.invViewMat, cam->invViewMat, 64);
+  fc.prevCam = E->havePrev ? E->prevCam : fc.cam;
+  fc.G = E->gp(E->gCur);
+  fc.Gprev = E->gp(E->gCur ^ 1);
+  fc.frame = E->frame.data();
+  fc.counters = E->counters;
+  memset(E->counters, 0, sizeof(E->counters));
+  auto bind = [&]() { fc.Rread = E->rp(E->rRead), fc.Rwrite = E->rp(E->rWrite), fc.Rlast = E->rp(E->rLast); };
+  auto swap_rw = [&]() { std::swap(E->rRead, E->rWrite); };
+  const InlineVis vis = {&fc};
+  bind();
+  fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_GBUF, 0);
+  for_pixels(E, fc, [&](int x, int y, Cnt& c) { gbuffer_pixel(fc, x, y, c); });
+  fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_INITIAL, 0);
+  for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, vis, c); });
+  if (P.doVisibilityPass) for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, vis, c); });
+  if (P.doTemporalReuse && frame_idx > 0 && E->havePrev) {
+    swap_rw();
+    bind();
+    fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_TEMPORAL, 0);
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, vis, c); });
+  }
+  if (P.doSpatialReuse) {
+    for (int i = 0; i < P.spatialPassCount; ++i) {
+      swap_rw();
+      bind();
+      fc.spatial_iter = i;
+      fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_SPATIAL, (uint32_t)i);
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, vis, c); });
+    }
+  }
+  swap_rw();
+  bind();
+  for_pixels(E, fc, [&](int x, int y, Cnt& c) { shade_pixel(fc, x, y, vis, c); });
+  std::swap(E->rLast, E->rRead);
+  E->gCur ^= 1;
+  E->prevCam = fc.cam;
+  E->havePrev = true;
+  if (rgb_out) memcpy(rgb_out, E->frame.data(), E->frame.size() * sizeof(float));
+  return 0;
+}
+
+void emu_counters(void* h, uint64_t* out3) {
+  Emu* E = (Emu*)h;
+  out3[0] = E->counters[0], out3[1] = E->counters[1], out3[2] = E->counters[2];
+}
+
+int emu_readback(void* h, int id, void* dst, size_t bytes) {
+  Emu* E = (Emu*)h;
+  const Emu::GStore& G = E->gs[E->gCur ^ 1];
+  const Emu::RStore& R = E->rs[E->rLast];
+  const void* src = nullptr;
+  size_t need = 0;
+  switch (id) {
+    case RB_BUF_GBUF_POS_DEPTH: src = G.a.data(), need = G.a.size() * 16; break;
+    case RB_BUF_GBUF_NORMAL_SHIN: src = G.b.data(), need = G.b.size() * 16; break;
+    case RB_BUF_GBUF_DIFFUSE_IIM: src = G.c.data(), need = G.c.size() * 16; break;
+    case RB_BUF_GBUF_SPEC_TYPE: src = G.d.data(), need = G.d.size() * 16; break;
+    case RB_BUF_GBUF_EMISSION: src = G.e.data(), need = G.e.size() * 16; break;
+    case RB_BUF_HIT_IDS: src = G.ids.data(), need = G.ids.size() * 8; break;
+    case RB_BUF_RES_POINT_WSUM: src = R.a.data(), need = R.a.size() * 16; break;
+    case RB_BUF_RES_NORMAL_W: src = R.b.data(), need = R.b.size() * 16; break;
+    case RB_BUF_RES_LI_CONF: src = R.c.data(), need = R.c.size() * 16; break;
+    case RB_BUF_RES_LIGHT_IDX: src = R.li.data(), need = R.li.size() * 4; break;
+    case RB_BUF_FRAME_RGB: src = E->frame.data(), need = E->frame.size() * 4; break;
+    case RB_BUF_ALIAS_PROB: src = E->hs.alias_prob.data(), need = E->hs.alias_prob.size() * 4; break;
+    case RB_BUF_ALIAS_IDX: src = E->hs.alias_idx.data(), need = E->hs.alias_idx.size() * 4; break;
+    case RB_BUF_LIGHT_CDF: src = E->hs.cdf.data(), need = E->hs.cdf.size() * 4; break;
+    default: return -1;
+  }
+  if (bytes < need) return -1;
+  if (need) memcpy(dst, src, need);
+  return 0;
+}
+
+int emu_trace_closest(void* h, const RbRay* rays, RbHit* hits, uint32_t n) {
+  Emu* E = (Emu*)h;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {
+    const RbRay& r = rays[i];
+    HitRec hr;
+    const bool hit = trace8<false>(E->sc, v3(r.org_x, r.org_y, r.org_z), v3(r.dir_x, r.dir_y, r.dir_z), r.tnear, r.tfar, &hr);
+    RbHit o;
+    if (hit) {
+      const U4 info = E->sc.tri_info[hr.tri];
+      o.t = hr.t, o.u = hr.u, o.v = hr.v, o.primID = info.y, o.geomID = info.x;
+    } else {
+      o.t = r.tfar, o.u = 0, o.v = 0, o.primID = 0xFFFFFFFFu, o.geomID = 0xFFFFFFFFu;
+    }
+    hits[i] = o;
+  }
+  return 0;
+}
+int emu_trace_occluded(void* h, const RbRay* rays, uint8_t* occ, uint32_t n) {
+  Emu* E = (Emu*)h;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {
+    const RbRay& r = rays[i];
+    occ[i] = trace8<true>(E->sc, v3(r.org_x, r.org_y, r.org_z), v3(r.dir_x, r.dir_y, r.dir_z), r.tnear, r.tfar, nullptr) ? 1 : 0;
+  }
+  return 0;
+}
+
+// structural check of the wide BVH: every triangle reachable exactly once, every child box
+// (decoded from the 8-bit grid) contains its subtree's triangles. Returns 0 if sound.
+int emu_validate_bvh(void* h) {
+  Emu* E = (Emu*)h;
+  if (E->n_nodes == 0) return 0;
+  std::vector<int> seen(E->hs.n, 0);
+  struct Item {
+    uint32_t node;
+    float lo[3], hi[3];
+  };
+  std::vector<Item> st;
+  st.push_back({0, {-FLT_MAX, -FLT_MAX, -FLT_MAX}, {FLT_MAX, FLT_MAX, FLT_MAX}});
+  while (!st.empty()) {
+    Item it = st.back();
+    st.pop_back();
+    const F4* np = E->node8.data() + 5 * (size_t)it.node;
+    const uint32_t eb = f2u(np[0].w), imask = eb >> 24;
+    const float org[3] = {np[0].x, np[0].y, np[0].z};
+    const float sc3[3] = {u2f(byte_of(eb, 0) << 23), u2f(byte_of(eb, 1) << 23), u2f(byte_of(eb, 2) << 23)};
+    const uint32_t child_base = f2u(np[1].x), tri_base = f2u(np[1].y);
+    const uint32_t metaw[2] = {f2u(np[1].z), f2u(np[1].w)};
+    const uint32_t q[6][2] = {{f2u(np[2].x), f2u(np[2].y)}, {f2u(np[2].z), f2u(np[2].w)}, {f2u(np[3].x), f2u(np[3].y)},
+                              {f2u(np[3].z), f2u(np[3].w)}, {f2u(np[4].x), f2u(np[4].y)}, {f2u(np[4].z), f2u(np[4].w)}};
+    int rel = 0;
+    for (int s = 0; s < 8; ++s) {
+      const uint32_t meta = byte_of(metaw[s >> 2], s & 3);
+      if (!meta) {
+        if ((imask >> s) & 1) return 10;
+        continue;
+      }
+      float lo[3], hi[3];
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = org[a] + (float)byte_of(q[a][s >> 2], s & 3) * sc3[a];
+        hi[a] = org[a] + (float)byte_of(q[3 + a][s >> 2], s & 3) * sc3[a];
+        // carry the intersection of all ancestor boxes: triangles must lie inside every one of them
+        lo[a] = fmaxf(lo[a], it.lo[a]);
+        hi[a] = fminf(hi[a], it.hi[a]);
+        if (lo[a] > hi[a]) return 11;
+      }
+      if ((imask >> s) & 1) {
+        if ((meta & 31u) != 24u + (uint32_t)s || (meta >> 5) != 1u) return 12;
+        Item ch;
+        ch.node = child_base + rel++;
+        if (ch.node >= E->n_nodes) return 13;
+        memcpy(ch.lo, lo, 12), memcpy(ch.hi, hi, 12);
+        st.push_back(ch);
+      } else {
+        const uint32_t off = meta & 31u, un = meta >> 5;
+        const int cnt = un == 1 ? 1 : un == 3 ? 2 : un == 7 ? 3 : -1;
+        if (cnt < 0 || off + cnt > 24) return 14;
+        for (int t = 0; t < cnt; ++t) {
+          const F4* tp = E->tri_isect.data() + 3 * (size_t)(tri_base + off + t);
+          const uint32_t id = f2u(tp[2].y);
+          if (id >= E->hs.n) return 15;
+          seen[id]++;
+          const float* p = E->hs.pos.data() + 9 * (size_t)id;
+          for (int v = 0; v < 3; ++v)
+            for (int a = 0; a < 3; ++a)
+              if (p[3 * v + a] < lo[a] || p[3 * v + a] > hi[a]) return 16;
+        }
+      }
+    }
+  }
+  for (size_t i = 0; i < seen.size(); ++i)
+    if (seen[i] != 1) return 17;
+  return 0;
+}
+}
