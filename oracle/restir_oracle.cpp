@@ -1426,13 +1426,15 @@ float orc_phong_evalPdf(int math_mode, const float* elem, const float* cam, cons
 }
 // legacy-stream leaf samplers: run with a caller-seeded mt19937 so they can be compared
 // draw-for-draw with the reference sources compiled in oracle/_ref
-void orc_legacy_phong_sampleBRDF(int math_mode, uint32_t mt_seed, int n, const float* elem, const float* cam, float* out4n) {
+// n calls on one stream; elems = n x 13 floats, cams = n x 3 floats
+void orc_legacy_phong_sampleBRDF(int math_mode, uint32_t mt_seed, int n, const float* elems, const float* cams, float* out4n) {
   Oracle o = make_leaf(math_mode);
   o.rng_mode = 1;
   o.legacy_gen.seed(mt_seed);
-  GBufferElement g = elem_from(elem);
   Rng rng = o.rngFor(0, 0, 0, 0);
   for (int i = 0; i < n; ++i) {
+    GBufferElement g = elem_from(elems + 13 * i);
+    const float* cam = cams + 3 * i;
     auto s = o.phong_sampleBRDF(g, {cam[0], cam[1], cam[2]}, rng, 0);
     out4n[4 * i] = s.omega_i.x, out4n[4 * i + 1] = s.omega_i.y, out4n[4 * i + 2] = s.omega_i.z, out4n[4 * i + 3] = s.pdf;
   }
