@@ -45,6 +45,9 @@ struct InlineVis {
   RB_HD bool visible(int /*slot*/, const V3& from, const V3& to) const {
     return !test_occlusion(fc->sc, from, to, fc->P.tnearOffset, fc->P.tfarOffset);
   }
+  RB_HD SurfaceHit closest(int /*slot*/, const V3& org, const V3& dir, float tnear, float tfar) const {
+    return intersect_surface(fc->sc, org, dir, tnear, tfar);
+  }
 };
 
 // ---- Phong / Lambert statics (P/MaterialPhong.cpp:122-248, P/MaterialLambert.cpp:33-53,
@@ -68,34 +71,52 @@ RB_HD float inv_I_M(const V3& pos, const V3& normal, float shininess, const V3& 
 }
 RB_HD bool uses_phong_brdf(uint32_t t) { return t == RB_MAT_PHONG || t == RB_MAT_DIELECTRIC; }
 
-// reflection direction omega_r = normalize(reflect(omega_o, n)), omega_o = normalize(pos - cam)
-// (evalBRDF spells it reflect(-V, n) with V = normalize(cam - pos): the same bits)
-RB_HD V3 omega_r_of(const GElem& g, const V3& camPos) {
+// Per-pixel shading context: the sub-expressions of evalBRDF / evalPdf / sampleBRDF that depend only on the
+// G-buffer element and its own frame's camera, hoisted out of the per-candidate code. omega_r is
+// normalize(reflect(omega_o, n)) with omega_o = normalize(pos - cam); evalBRDF spells it reflect(-V, n) with
+// V = normalize(cam - pos), which is the same bits (x - y == -(y - x) exactly).
+struct Shading {
+  V3 omega_r;
+  float pdfFactor;  // maxDiffuse / (maxDiffuse + maxSpecular), P/MaterialPhong.cpp:159
+  bool phong;       // BRDF has the Phong lobe (PHONG, DIELECTRIC); otherwise Lambert (P/ReSTIRIntegrator.h:32-41)
+  bool finite;      // 1/I_M, pdfFactor and shininess are finite numbers
+};
+RB_HD bool finitef_(float x) { return (f2u(x) & 0x7F800000u) != 0x7F800000u; }
+RB_HD Shading make_shading(const GElem& g, const V3& camPos) {
+  Shading sh;
   const V3 omega_o = normalize(g.pos - camPos);
-  return normalize(reflect(omega_o, g.normal));
+  sh.omega_r = normalize(reflect(omega_o, g.normal));
+  const float maxDiffuse = max_component(g.diffuse);
+  const float maxSpecular = max_component(g.specular);
+  sh.pdfFactor = maxDiffuse / (maxDiffuse + maxSpecular);
+  sh.phong = uses_phong_brdf(g.matType);
+  sh.finite = finitef_(g.invIM) && finitef_(sh.pdfFactor) && finitef_(g.shininess);
+  return sh;
+}
+// The Phong lobe term pow(max(dot(omega_i, omega_r), 0), n) is shared by evalBRDF (:144) and evalPdf's
+// CosineLobeDistribution::getPdf (P/Distribution.h:65-67). The two spell the clamp as max(d,0) and max(0,d):
+// identical except for NaN d, which is kept apart.
+struct Lobe {
+  float brdf, pdf;
+};
+RB_HD Lobe phong_lobe(const GElem& g, const Shading& sh, const V3& omega_i) {
+  const float d = dot(omega_i, sh.omega_r);
+  Lobe l;
+  l.brdf = dm::powf_(gmax(d, 0.0f), g.shininess);
+  l.pdf = (d != d) ? dm::powf_(gmax(0.0f, d), g.shininess) : l.brdf;
+  return l;
 }
 // getMaterialBRDFEvalFunc dispatch, P/ReSTIRIntegrator.h:32-41
-RB_HD V3 brdf_eval(const GElem& g, const V3& camPos, const V3& omega_i) {
+RB_HD V3 brdf_from_lobe(const GElem& g, const Shading& sh, float lobe) {
   V3 f_r = g.diffuse * RB_ONE_OVER_PI;
-  if (uses_phong_brdf(g.matType)) {
-    const V3 V = normalize(camPos - g.pos);
-    const V3 omega_r = normalize(reflect(-V, g.normal));
-    f_r = f_r + g.specular * g.invIM * dm::powf_(gmax(dot(omega_i, omega_r), 0.0f), g.shininess);
-  }
+  if (sh.phong) f_r = f_r + g.specular * g.invIM * lobe;
   return f_r;
 }
 RB_HD float cosw_pdf(const V3& n, const V3& wi) { return gmax(dot(n, wi), 0.0f) * RB_ONE_OVER_PI; }
-RB_HD float lobe_pdf(const V3& wi, const V3& wr, float gamma) {
-  return (gamma + 1.0f) * RB_ONE_OVER_TWO_PI * dm::powf_(gmax(0.0f, dot(wi, wr)), gamma);
-}
 // MaterialPhong::evalPdf, :150-172 (getMaterialPDFEvalFunc always returns it, P/ReSTIRIntegrator.h:54-59)
-RB_HD float phong_pdf(const GElem& g, const V3& camPos, const V3& wi) {
-  float maxDiffuse = max_component(g.diffuse);
-  float maxSpecular = max_component(g.specular);
-  float pdfFactor = maxDiffuse / (maxDiffuse + maxSpecular);
-  float pdf = cosw_pdf(g.normal, wi) * pdfFactor;
-  const V3 wr = omega_r_of(g, camPos);
-  pdf += lobe_pdf(wi, wr, g.shininess) * (1.0f - pdfFactor);
+RB_HD float pdf_from_lobe(const GElem& g, const Shading& sh, const V3& wi, float lobe) {
+  float pdf = cosw_pdf(g.normal, wi) * sh.pdfFactor;
+  pdf += ((g.shininess + 1.0f) * RB_ONE_OVER_TWO_PI * lobe) * (1.0f - sh.pdfFactor);
   return pdf;
 }
 RB_HD V3 orthogonal(const V3& v) {  // Utils::orthogonal, P/utils.cpp:204-207
@@ -126,7 +147,7 @@ RB_HD V3 lobe_sample(const V3& wr, float gamma, float r1, float r2) {  // Cosine
 }
 // getMaterialSampleFunc dispatch (:43-52): Lambert for LAMBERT, Phong for everything else.
 // Returns omega_i and its pdf (the f_r the reference also computes is unused by its ReSTIR caller).
-RB_HD V3 brdf_sample(const GElem& g, const V3& camPos, uint32_t key, uint32_t base, float* pdf) {
+RB_HD V3 brdf_sample(const GElem& g, const Shading& sh, uint32_t key, uint32_t base, float* pdf) {
   const float r1 = rng_value(key, base + 1, 0, 1), r2 = rng_value(key, base + 2, 0, 1);
   if (g.matType == RB_MAT_LAMBERT) {  // MaterialLambert::sampleBRDF, P/MaterialLambert.cpp:43-53
     V3 wi = cosw_sample(g.normal, r1, r2);
@@ -137,18 +158,33 @@ RB_HD V3 brdf_sample(const GElem& g, const V3& camPos, uint32_t key, uint32_t ba
   float maxDiffuse = max_component(g.diffuse);
   float maxSpecular = max_component(g.specular);
   float r0 = rng_value(key, base + 0, 0.0f, maxDiffuse + maxSpecular);
-  float pdfFactor = maxDiffuse / (maxDiffuse + maxSpecular);
-  const V3 wr = omega_r_of(g, camPos);
-  V3 wi = (r0 < maxDiffuse) ? cosw_sample(g.normal, r1, r2) : lobe_sample(wr, g.shininess, r1, r2);
-  float pdfDiffuse = cosw_pdf(g.normal, wi) * pdfFactor;
-  float pdfSpecular = lobe_pdf(wi, wr, g.shininess) * (1.0f - pdfFactor);
+  V3 wi = (r0 < maxDiffuse) ? cosw_sample(g.normal, r1, r2) : lobe_sample(sh.omega_r, g.shininess, r1, r2);
+  float pdfDiffuse = cosw_pdf(g.normal, wi) * sh.pdfFactor;
+  // CosineLobeDistribution::getPdf(omega_i, omega_r, gamma), P/Distribution.h:65-67
+  float pdfSpecular = ((g.shininess + 1.0f) * RB_ONE_OVER_TWO_PI * dm::powf_(gmax(0.0f, dot(wi, sh.omega_r)), g.shininess)) *
+                      (1.0f - sh.pdfFactor);
   *pdf = pdfDiffuse + pdfSpecular;
   return wi;
 }
 
 // ---- evaluateF / evaluatePHat (P/ReSTIRIntegrator.cpp:180-211) ---------------------
+// What is already known about the visibility term of an evaluation (all exact, DESIGN.md "ray elimination"):
+//   VIS_TRACE      nothing: trace the shadow ray.
+//   VIS_KNOWN      the sample is the reservoir this very pixel produced in the previous pass of this frame and
+//                  its W is > 0. W = w_sum / p-hat(sample) with the shadowed p-hat, so W > 0 implies that the
+//                  identical ray (same origin, same target) was found unoccluded: V = 1.
+//   VIS_IRRELEVANT the value is only ever multiplied by a reservoir weight W that is exactly 0: any finite value
+//                  gives the same product, so the ray is skipped when the unshadowed value is finite.
+enum VisMode { VIS_TRACE = 0, VIS_KNOWN = 1, VIS_IRRELEVANT = 2 };
+RB_HD VisMode vis_mode_from_W(float W, bool own_pixel_this_frame) {
+  if (W == 0.0f) return VIS_IRRELEVANT;
+  if (own_pixel_this_frame && W > 0.0f) return VIS_KNOWN;
+  return VIS_TRACE;  // includes NaN W
+}
+RB_HD bool finite3(const V3& v) { return finitef_(v.x) && finitef_(v.y) && finitef_(v.z); }
+
 // Unshadowed value L_i * f_r * G; *wants_ray tells whether the reference would trace here.
-RB_HD V3 eval_F0(const LightSample& s, const V3& camPos, const GElem& g, bool* wants_ray) {
+RB_HD V3 eval_F0(const LightSample& s, const GElem& g, const Shading& sh, bool* wants_ray) {
   *wants_ray = false;
   if (!sample_valid(s) || g.isEmissive) return v3(0);
   V3 lightDir = s.samplePoint - g.pos;
@@ -157,27 +193,36 @@ RB_HD V3 eval_F0(const LightSample& s, const V3& camPos, const GElem& g, bool* w
   float cosThetaI = gmax(dot(lightDir, g.normal), 0.0f);
   float cosThetaY = fabsf_(dot(-lightDir, s.sampleNormal));
   float G = cosThetaI * cosThetaY / r_sqr;
-  V3 f_r = brdf_eval(g, camPos, lightDir);
+  float lobe = 0.0f;
+  if (sh.phong) lobe = dm::powf_(gmax(dot(lightDir, sh.omega_r), 0.0f), g.shininess);
+  V3 f_r = brdf_from_lobe(g, sh, lobe);
   *wants_ray = true;
   return s.L_i * f_r * G;
 }
 template <class Vis>
-RB_HD V3 eval_F(const LightSample& s, const V3& camPos, const GElem& g, bool testVisibility, const Vis& vis, int slot,
-                Cnt& cnt, int written_copies, bool* wants_out = nullptr) {
-  bool wants;
-  V3 F0 = eval_F0(s, camPos, g, &wants);
-  if (wants_out) *wants_out = wants;
-  if (!wants || !testVisibility) return F0;
+RB_HD V3 shadow_F0(const V3& F0, const V3& from, const V3& to, const Vis& vis, int slot, Cnt& cnt, int written_copies,
+                   VisMode mode) {
   cnt.anyW += (uint32_t)written_copies;
   if (F0.x == 0.0f && F0.y == 0.0f && F0.z == 0.0f) return F0;  // F0 * V == F0 for V in {0,1}
+  if (mode == VIS_KNOWN) return F0;
+  if (mode == VIS_IRRELEVANT && finite3(F0)) return F0;
   cnt.anyT++;
-  float V = vis.visible(slot, g.pos, s.samplePoint) ? 1.0f : 0.0f;
+  float V = vis.visible(slot, from, to) ? 1.0f : 0.0f;
   return F0 * V;
 }
 template <class Vis>
-RB_HD float eval_phat(const LightSample& s, const V3& camPos, const GElem& g, bool testVisibility, const Vis& vis,
-                      int slot, Cnt& cnt, int written_copies, bool* wants_out = nullptr) {
-  return length(eval_F(s, camPos, g, testVisibility, vis, slot, cnt, written_copies, wants_out));
+RB_HD V3 eval_F(const LightSample& s, const GElem& g, const Shading& sh, bool testVisibility, const Vis& vis, int slot,
+                Cnt& cnt, int written_copies, VisMode mode = VIS_TRACE, bool* wants_out = nullptr) {
+  bool wants;
+  V3 F0 = eval_F0(s, g, sh, &wants);
+  if (wants_out) *wants_out = wants;
+  if (!wants || !testVisibility) return F0;
+  return shadow_F0(F0, g.pos, s.samplePoint, vis, slot, cnt, written_copies, mode);
+}
+template <class Vis>
+RB_HD float eval_phat(const LightSample& s, const GElem& g, const Shading& sh, bool testVisibility, const Vis& vis,
+                      int slot, Cnt& cnt, int written_copies, VisMode mode = VIS_TRACE, bool* wants_out = nullptr) {
+  return length(eval_F(s, g, sh, testVisibility, vis, slot, cnt, written_copies, mode, wants_out));
 }
 
 // ---- light sampling (P/TriangleCDF.cpp:36-54 / alias seam) --------------------------
@@ -285,7 +330,7 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   }
   const RbParams& P = fc.P;
   const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
-  const V3 cam = fc.cam.pos;
+  const Shading sh = make_shading(g, fc.cam.pos);
   const bool testVis = !P.doVisibilityPass;
   float p_sel = 0.0f;  // p-hat of the currently selected sample (== the final evaluatePHat, :289)
   bool sel_wants = false;
@@ -297,40 +342,65 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
     const F4* L = fc.sc.light + 6 * (size_t)pick.idx;
     const F4 l0 = ldg4(L), l1 = ldg4(L + 1), l2 = ldg4(L + 2), l3 = ldg4(L + 3), l4 = ldg4(L + 4), l5 = ldg4(L + 5);
     const float r1 = rng_value(key, base + 1, 0, 1), r2 = rng_value(key, base + 2, 0, 1);
-    const float bx = 1.0f - sqrtf_(r1);
-    const float by = sqrtf_(r1) * (1.0f - r2);
-    const float bz = sqrtf_(r1) * r2;
+    const float sq = sqrtf_(r1);
+    const float bx = 1.0f - sq;
+    const float by = sq * (1.0f - r2);
+    const float bz = sq * r2;
     LightSample s;
     s.samplePoint = xyz(l0) * bx + xyz(l1) * by + xyz(l2) * bz;
     s.sampleNormal = normalize(xyz(l3) * bx + xyz(l4) * by + xyz(l5) * bz);
     s.L_i = v3(l3.w, l4.w, l5.w);
     s.lightIdx = (int)pick.idx;
-    const float triPointPdf = 1.0f / l0.w;
-    const float pdf_area = pick.pdf * triPointPdf;
+    // shared by areaSampleLight (:102-107) and evaluateF (:192-199): same expressions, same bits
     V3 lightDir = s.samplePoint - g.pos;
     const float r_sqr = dot(lightDir, lightDir);
     lightDir = normalize(lightDir);
-    const float cosThetaY = gmax(dot(-lightDir, s.sampleNormal), 0.0f);
-    const float areaMeasureFactor = cosThetaY / r_sqr;
-    const float pdfAsIfBrdfAreaMeasure = phong_pdf(g, cam, lightDir) * areaMeasureFactor;
+    const float d_ny = dot(-lightDir, s.sampleNormal);
+    const float cosThetaI = gmax(dot(lightDir, g.normal), 0.0f);
+    const bool valid = sample_valid(s);  // false only for a non-positive emission
+    if (valid && testVis) cnt.anyW++;
+    // A light below the horizon has G == 0: with finite BRDF, pdf and weights the candidate's w is exactly +0,
+    // so addSample only counts it (w_sum += 0; no draw consumed affects the result: rand < 0 is false).
+    if (sh.finite && cosThetaI == 0.0f && r_sqr > 0.0f && finitef_(r_sqr) && pick.pdf > 0.0f && finitef_(l2.w) && l2.w > 0.0f &&
+        finitef_(d_ny) && finite3(s.L_i)) {
+      r.confidence += 1;
+      continue;
+    }
+    const float triPointPdf = l2.w;  // 1.0f / area, computed with the same division at upload
+    const float pdf_area = pick.pdf * triPointPdf;
+    const float cosThetaY_pdf = gmax(d_ny, 0.0f);
+    const float areaMeasureFactor = cosThetaY_pdf / r_sqr;
+    const Lobe lobe = phong_lobe(g, sh, lightDir);
+    const float pdfAsIfBrdfAreaMeasure = pdf_from_lobe(g, sh, lightDir, lobe.pdf) * areaMeasureFactor;
     const float W = 1.0f / pdf_area;
     const float misWeight = m_area(P, pdf_area, pdfAsIfBrdfAreaMeasure);
-    bool wants;
-    const float p_hat = eval_phat(s, cam, g, testVis, vis, i, cnt, 1, &wants);
+    // evaluatePHat(sample, pixel)
+    float p_hat = 0.0f;
+    if (valid) {
+      const float cosThetaY = fabsf_(d_ny);
+      const float G = cosThetaI * cosThetaY / r_sqr;
+      const V3 f_r = brdf_from_lobe(g, sh, lobe.brdf);
+      V3 F = s.L_i * f_r * G;
+      if (testVis) {
+        cnt.anyW--;  // shadow_F0 counts it again
+        F = shadow_F0(F, g.pos, s.samplePoint, vis, i, cnt, 1, VIS_TRACE);
+      }
+      p_hat = length(F);
+    }
     const float w = (P.M_Brdf > 0) ? misWeight * p_hat * W : inv_MArea * p_hat * W;
     if (add_sample(r, s, w, 1, key, base + 3)) {
       p_sel = p_hat;
-      sel_wants = wants;
+      sel_wants = valid;
     }
   }
   const float inv_MBrdf = P.M_Brdf > 0 ? 1.0f / (float)P.M_Brdf : 0.0f;
   for (int i = 0; i < P.M_Brdf; ++i) {
     const uint32_t base = 4u * (uint32_t)(P.M_Area + i);
     float pdf;
-    const V3 wi = brdf_sample(g, cam, key, base, &pdf);
+    const V3 wi = brdf_sample(g, sh, key, base, &pdf);
     const V3 org = g.pos + P.normalOffset * g.normal;
     cnt.closest++;
-    const SurfaceHit h = intersect_surface(fc.sc, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
+    const SurfaceHit h = vis.closest(P.M_Area + i, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
     LightSample s = invalid_sample();
     float W = 0, misWeight = 0;
     if (h.didHit && h.emissiveId >= 0) {
@@ -353,7 +423,7 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
       misWeight = m_brdf(P, brdfPdfAreaMeasure, pdf_area);
     }
     bool wants;
-    const float p_hat = eval_phat(s, cam, g, testVis, vis, P.M_Area + i, cnt, 1, &wants);
+    const float p_hat = eval_phat(s, g, sh, testVis, vis, P.M_Area + i, cnt, 1, VIS_TRACE, &wants);
     const float w = (P.M_Area > 0) ? misWeight * p_hat * W : inv_MBrdf * p_hat * W;
     if (add_sample(r, s, w, 1, key, base + 3)) {
       p_sel = p_hat;
@@ -369,19 +439,21 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
 }
 
 // =====================================================================================
-// Pass 2: visibility (ReSTIRIntegrator::visibilityPass, :302-312) — traces even for an
-// empty reservoir (sample point = -FLT_MAX sentinel), exactly like the reference.
+// Pass 2: visibility (ReSTIRIntegrator::visibilityPass, :302-312). The reference traces for every pixel, even
+// with an empty reservoir (sample point = -FLT_MAX sentinel); the only effect of the ray is W = 0, so it is
+// not traced where W is already exactly 0.
 // =====================================================================================
 template <class Vis>
 RB_HD void visibility_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
   const size_t pi = (size_t)y * fc.width + x;
+  cnt.anyW++;
+  F4 nw = ld4(fc.Rwrite.normal_W + pi);
+  if (nw.w == 0.0f) return;
   const F4 pw = ld4(fc.Rwrite.point_wsum + pi);
   const F4 pd = ld4(fc.G.pos_depth + pi);
-  cnt.anyW++;
   cnt.anyT++;
   const bool V = vis.visible(0, xyz(pd), xyz(pw));
   if (!V) {
-    F4 nw = ld4(fc.Rwrite.normal_W + pi);
     nw.w = 0.0f;
     st4(fc.Rwrite.normal_W + pi, nw);
   }
@@ -445,13 +517,19 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
   }
   const Reservoir prev = load_reservoir(fc.Rlast, pi);  // same pixel, not the reprojected one (:641)
   const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+  const Shading shCur = make_shading(curElem, curCam), shPrev = make_shading(prevElem, prevCam);
 
-  // four distinct p-hat values feed the seven evaluations of the reference
+  // Four distinct p-hat values feed the seven evaluations of the reference. A and B only reach the output through
+  // w_cur = m_cur * A * cur.W, C and D only through w_prev = m_prev * C * prev.W (and the final p-hat, which is A or C
+  // and only when that sample was selected, i.e. its W is not 0).
+  const VisMode modeA = vis_mode_from_W(cur.W, true);
+  const VisMode modeB = cur.W == 0.0f ? VIS_IRRELEVANT : VIS_TRACE;
+  const VisMode modeCD = prev.W == 0.0f ? VIS_IRRELEVANT : VIS_TRACE;
   bool wA, wC;
-  const float A = eval_phat(cur.bestSample, curCam, curElem, true, vis, 0, cnt, 2, &wA);   // p_cur, p_hat_cur
-  const float B = eval_phat(cur.bestSample, prevCam, prevElem, true, vis, 1, cnt, 1);      // p_prev
-  const float C = eval_phat(prev.bestSample, curCam, curElem, true, vis, 2, cnt, 2, &wC);  // p_cur', p_hat_prev
-  const float D = eval_phat(prev.bestSample, prevCam, prevElem, true, vis, 3, cnt, 1);  // p_prev'
+  const float A = eval_phat(cur.bestSample, curElem, shCur, true, vis, 0, cnt, 2, modeA, &wA);     // p_cur, p_hat_cur
+  const float B = eval_phat(cur.bestSample, prevElem, shPrev, true, vis, 1, cnt, 1, modeB);        // p_prev
+  const float C = eval_phat(prev.bestSample, curElem, shCur, true, vis, 2, cnt, 2, modeCD, &wC);   // p_cur', p_hat_prev
+  const float D = eval_phat(prev.bestSample, prevElem, shPrev, true, vis, 3, cnt, 1, modeCD);      // p_prev'
 
   Reservoir out = empty_reservoir();
   float m_cur = A * (float)cur.confidence / (A * (float)cur.confidence + B * (float)prev.confidence);
@@ -492,6 +570,7 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   }
   const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
   const V3 cam = fc.cam.pos;
+  const Shading shThis = make_shading(thisElem, cam);
   const int k = P.spatialReuseNeighborCount;
   uint32_t nb[RB_MAX_NEIGHBORS + 1];  // pixel index of every resampling source; [0] = this pixel
   nb[0] = (uint32_t)pi;
@@ -547,8 +626,9 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
       misWeight = 0.0f;
       for (int j = 0; j < n; ++j) {
         const GElem gj = load_gelem(fc.G, nb[j]);
+        const Shading shj = make_shading(gj, cam);
         const int cj = (int)f2u(ld4(fc.Rread.Li_conf + nb[j]).w);
-        const float p_hat = eval_phat(si, cam, gj, true, vis, 0, cnt, 1);
+        const float p_hat = eval_phat(si, gj, shj, true, vis, 0, cnt, 1);
         misDenom += p_hat * cj;
         if (i == j) misNom = p_hat * ri.confidence;
       }
@@ -558,11 +638,12 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
       misWeight = 0.0f;
       if (i == 0) {
         float sum = 0.0f;
-        const float p_hat_c = eval_phat(si, cam, thisElem, true, vis, 0, cnt, 1) * (float)ri.confidence;
+        const float p_hat_c = eval_phat(si, thisElem, shThis, true, vis, 0, cnt, 1) * (float)ri.confidence;
         for (int j = 1; j < n; ++j) {
           const GElem gj = load_gelem(fc.G, nb[j]);
+          const Shading shj = make_shading(gj, cam);
           const int cj = (int)f2u(ld4(fc.Rread.Li_conf + nb[j]).w);
-          const float p_hat_j = eval_phat(si, cam, gj, true, vis, 0, cnt, 1);
+          const float p_hat_j = eval_phat(si, gj, shj, true, vis, 0, cnt, 1);
           const float denom = p_hat_c + p_hat_j * (float)confidenceSumNonCanonical;
           if (denom > 0) {
             const float confFract = (float)cj / (float)confidenceSum;
@@ -572,16 +653,20 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
         misWeight = ((float)ri.confidence / (float)confidenceSum) + sum;
       } else {
         const GElem gi = load_gelem(fc.G, nb[i]);
-        float p_hat_i = eval_phat(si, cam, gi, true, vis, 0, cnt, 1);
-        const float p_hat_c = eval_phat(si, cam, thisElem, true, vis, 0, cnt, 1);
+        const Shading shi = make_shading(gi, cam);
+        float p_hat_i = eval_phat(si, gi, shi, true, vis, 0, cnt, 1);
+        const float p_hat_c = eval_phat(si, thisElem, shThis, true, vis, 0, cnt, 1);
         p_hat_i *= (float)confidenceSumNonCanonical;
         const int c0 = (int)f2u(ld4(fc.Rread.Li_conf + nb[0]).w);
         const float denom = p_hat_i + p_hat_c * (float)c0;
         if (denom > 0 && confidenceSum > 0) misWeight = ((float)ri.confidence / (float)confidenceSum) * (p_hat_i / denom);
       }
     }
+    // resampling weight misWeight * p-hat(sample_i @ this pixel) * W_i: the ray is irrelevant when W_i is exactly 0, and
+    // already known unoccluded when the sample is this pixel's own reservoir with W > 0
+    const VisMode vm = vis_mode_from_W(ri.W, nb[i] == (uint32_t)pi);
     bool wants;
-    const float resamplingPhat = eval_phat(si, cam, thisElem, true, vis, i, cnt, 1, &wants);
+    const float resamplingPhat = eval_phat(si, thisElem, shThis, true, vis, i, cnt, 1, vm, &wants);
     const float resamplingWeight = misWeight * resamplingPhat * ri.W;
     if (add_sample(out, si, resamplingWeight, ri.confidence, key, 2u * k + i)) {
       selectedSampleIndex = i;
@@ -611,8 +696,9 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
     float misNom = 0, misDenom = 0, contribWeight = 0, correctionFactor = 0;
     for (int i = 0; i < n; ++i) {
       const GElem gi = load_gelem(fc.G, nb[i]);
+      const Shading shi = make_shading(gi, cam);
       const int ci = (int)f2u(ld4(fc.Rread.Li_conf + nb[i]).w);
-      const float p_hat = eval_phat(rs.bestSample, cam, gi, true, vis, 0, cnt, 1);
+      const float p_hat = eval_phat(rs.bestSample, gi, shi, true, vis, 0, cnt, 1);
       misDenom += p_hat * (float)ci;
       if (i == selectedSampleIndex) misNom = p_hat * (float)ci;
     }
@@ -625,7 +711,9 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
 }
 
 // =====================================================================================
-// Pass 5: final shading (P/simpleguidx11.cpp:452-472) + Integrator::sanitize (P/Integrator.cpp:6-23)
+// Pass 5: final shading (P/simpleguidx11.cpp:452-472) + Integrator::sanitize (P/Integrator.cpp:6-23).
+// The reservoir read here is this pixel's own output of the last pass: W > 0 means its sample was found
+// unoccluded there, W == 0 zeroes the pixel — the reference's shadow ray never changes the result.
 // =====================================================================================
 template <class Vis>
 RB_HD void shade_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
@@ -634,7 +722,8 @@ RB_HD void shade_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cn
   V3 pixel;
   if (r.w_sum > 0.0f) {  // Reservoir::hasSample
     const GElem g = load_gelem(fc.G, pi);
-    const V3 f = eval_F(r.bestSample, fc.cam.pos, g, true, vis, 0, cnt, 1);
+    const Shading sh = make_shading(g, fc.cam.pos);
+    const V3 f = eval_F(r.bestSample, g, sh, true, vis, 0, cnt, 1, vis_mode_from_W(r.W, true));
     pixel = f * r.W;
   } else {
     pixel = xyz(ld4(fc.G.emission + pi));
