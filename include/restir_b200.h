@@ -149,7 +149,11 @@ typedef struct RbTimings {
   float ms_spatial;
   float ms_shade;
   float ms_total;
-  float ms_trace_any;           /* sum of any-hit traversal kernels (wavefront mode) */
+  float ms_trace_any;           /* sum of the traversal kernels of the frame (wavefront mode) */
+  /* wavefront mode, per pass (0 gbuffer, 1 initial, 2 visibility, 3 temporal, 4 spatial, 5 shade):
+   * time in the streaming kernels (stream + resolve halves) and in the traversal kernel */
+  float ms_stream[6];
+  float ms_trace[6];
   uint64_t rays_closest;        /* closest-hit rays traced this frame  */
   uint64_t rays_any_as_written; /* shadow rays the reference would issue */
   uint64_t rays_any_traced;     /* after exact-duplicate / zero-contribution elimination */

@@ -101,7 +101,8 @@ class RbCamera(C.Structure):
 class RbTimings(C.Structure):
     _fields_ = [("ms_gbuffer", C.c_float), ("ms_initial", C.c_float), ("ms_visibility", C.c_float),
                 ("ms_temporal", C.c_float), ("ms_spatial", C.c_float), ("ms_shade", C.c_float),
-                ("ms_total", C.c_float), ("ms_trace_any", C.c_float), ("rays_closest", C.c_uint64),
+                ("ms_total", C.c_float), ("ms_trace_any", C.c_float), ("ms_stream", C.c_float * 6),
+                ("ms_trace", C.c_float * 6), ("rays_closest", C.c_uint64),
                 ("rays_any_as_written", C.c_uint64), ("rays_any_traced", C.c_uint64), ("kernel_launches", C.c_uint32),
                 ("reserved", C.c_uint32)]
 

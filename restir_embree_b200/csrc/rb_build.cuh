@@ -236,18 +236,33 @@ RB_HD float box_area(const F4& lo, const F4& hi) {
   const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
   return dx * dy + dy * dz + dz * dx;
 }
-// biased exponent e such that 255 * 2^(e-127) >= extent
+// Child boxes are stored as 7-bit grid coordinates q in [0,127]; the traversal decodes a plane as
+// origin' + (128 + q) * step, where 128 + q is built directly as the float 0x43000000 | q << 16 (one byte
+// permute, no integer-to-float conversion). origin' = node_lo - 128 * step.
+#define RB_QMAX 127.0f
+// biased exponent e of the grid step 2^(e-127) such that 126 steps cover the extent (one step of slack for the
+// rounding of origin')
 RB_HD uint32_t grid_exponent(float extent) {
   if (!(extent > 0.0f)) return 1u;
-  const float step = extent / 255.0f;
+  const float step = extent / 126.0f;
   uint32_t bits = f2u(step);
   uint32_t e = (bits >> 23) & 0xFFu;
   if (bits & 0x7FFFFFu) e += 1;  // round the step up to a power of two
   if (e < 1u) e = 1u;
   if (e > 254u) e = 254u;
-  // guard against the rounding of extent/255
-  while (e < 254u && u2f(e << 23) * 255.0f < extent) e += 1;
+  while (e < 254u && u2f(e << 23) * 126.0f < extent) e += 1;
   return e;
+}
+RB_HD float float_prev(float x) {  // next representable float below x
+  if (x == 0.0f) return -1.401298464e-45f;
+  uint32_t b = f2u(x);
+  return u2f(x > 0.0f ? b - 1u : b + 1u);
+}
+// origin' for one axis: the largest float with origin' + 128*step <= lo
+RB_HD float grid_origin(float lo, float step) {
+  float o = lo - 128.0f * step;
+  while (o + 128.0f * step > lo) o = float_prev(o);
+  return o;
 }
 RB_HD void write_tri(const BuildCtx& c, uint32_t dst, uint32_t tri) {
   const float* p = c.tri_pos + 9 * (size_t)tri;
@@ -305,6 +320,7 @@ RB_HD void emit_node8(const BuildCtx& c, int out_index, const int* refs, int n_i
   const int tri_base = n_leaf_tris ? atomic_add_i(c.counters + 1, n_leaf_tris) : 0;
   const uint32_t ex = grid_exponent(nhi.x - nlo.x), ey = grid_exponent(nhi.y - nlo.y), ez = grid_exponent(nhi.z - nlo.z);
   const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
+  const float gox = grid_origin(nlo.x, sx), goy = grid_origin(nlo.y, sy), goz = grid_origin(nlo.z, sz);
   uint32_t imask = 0;
   uint32_t meta[8], qlo[3][8], qhi[3][8];
   int int_cursor = 0, tri_cursor = 0;
@@ -316,15 +332,15 @@ RB_HD void emit_node8(const BuildCtx& c, int out_index, const int* refs, int n_i
     const int k = child_in_slot[s];
     if (k < 0) continue;
     const float l3[3] = {clo[k].x, clo[k].y, clo[k].z}, h3[3] = {chi[k].x, chi[k].y, chi[k].z};
-    const float o3[3] = {nlo.x, nlo.y, nlo.z}, s3[3] = {sx, sy, sz};
+    const float o3[3] = {gox, goy, goz}, s3[3] = {sx, sy, sz};
     for (int a = 0; a < 3; ++a) {
-      float fl = floorf((l3[a] - o3[a]) / s3[a]);
-      float fh = ceilf((h3[a] - o3[a]) / s3[a]);
-      // outward rounding must survive the subtraction's own rounding
-      while (fl > 0.0f && o3[a] + fl * s3[a] > l3[a]) fl -= 1.0f;
-      while (fh < 255.0f && o3[a] + fh * s3[a] < h3[a]) fh += 1.0f;
-      fl = fminf(fmaxf(fl, 0.0f), 255.0f);
-      fh = fminf(fmaxf(fh, 0.0f), 255.0f);
+      float fl = floorf((l3[a] - o3[a]) / s3[a]) - 128.0f;
+      float fh = ceilf((h3[a] - o3[a]) / s3[a]) - 128.0f;
+      fl = fminf(fmaxf(fl, 0.0f), RB_QMAX);
+      fh = fminf(fmaxf(fh, 0.0f), RB_QMAX);
+      // outward rounding must survive the rounding of the float expressions themselves
+      while (fl > 0.0f && o3[a] + (128.0f + fl) * s3[a] > l3[a]) fl -= 1.0f;
+      while (fh < RB_QMAX && o3[a] + (128.0f + fh) * s3[a] < h3[a]) fh += 1.0f;
       qlo[a][s] = (uint32_t)fl;
       qhi[a][s] = (uint32_t)fh;
     }
@@ -343,7 +359,7 @@ RB_HD void emit_node8(const BuildCtx& c, int out_index, const int* refs, int n_i
     }
   }
   F4* o = c.node8 + 5 * (size_t)out_index;
-  o[0] = F4{nlo.x, nlo.y, nlo.z, u2f(ex | (ey << 8) | (ez << 16) | (imask << 24))};
+  o[0] = F4{gox, goy, goz, u2f(ex | (ey << 8) | (ez << 16) | (imask << 24))};
   o[1] = F4{u2f((uint32_t)child_base), u2f((uint32_t)tri_base), u2f(pack4(meta)), u2f(pack4(meta + 4))};
   o[2] = F4{u2f(pack4(qlo[0])), u2f(pack4(qlo[0] + 4)), u2f(pack4(qlo[1])), u2f(pack4(qlo[1] + 4))};
   o[3] = F4{u2f(pack4(qlo[2])), u2f(pack4(qlo[2] + 4)), u2f(pack4(qhi[0])), u2f(pack4(qhi[0] + 4))};
@@ -387,11 +403,12 @@ RB_HD void tiny_root_body(const BuildCtx& c) {
   for (uint32_t i = 0; i < c.n; ++i) write_tri(c, i, c.order[i]);
   const uint32_t meta0 = (((1u << c.n) - 1u) << 5) | 0u;
   F4* o = c.node8;
-  o[0] = F4{lo.x, lo.y, lo.z, u2f(ex | (ey << 8) | (ez << 16))};
+  o[0] = F4{grid_origin(lo.x, u2f(ex << 23)), grid_origin(lo.y, u2f(ey << 23)), grid_origin(lo.z, u2f(ez << 23)),
+            u2f(ex | (ey << 8) | (ez << 16))};
   o[1] = F4{u2f(0u), u2f(0u), u2f(meta0), u2f(0u)};
   o[2] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
-  o[3] = F4{u2f(0u), u2f(0u), u2f(255u), u2f(0u)};
-  o[4] = F4{u2f(255u), u2f(0u), u2f(255u), u2f(0u)};
+  o[3] = F4{u2f(0u), u2f(0u), u2f(127u), u2f(0u)};
+  o[4] = F4{u2f(127u), u2f(0u), u2f(127u), u2f(0u)};
   c.counters[0] = 1;
   c.counters[1] = (int)c.n;
 }

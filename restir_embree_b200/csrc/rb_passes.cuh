@@ -21,6 +21,21 @@ namespace rb {
 
 #define RB_MAX_NEIGHBORS 32
 
+// Wavefront buffers (stream -> trace -> resolve split): a compact ray queue filled by the "stream" half of a
+// pass, traced by the persistent traversal kernels, and per-(slot, pixel) results read by the "resolve" half.
+struct RayQ {
+  F4 o_tfar;  // origin.xyz, tfar
+  F4 d_dest;  // dir.xyz, bits(destination index = slot * npix + pixel)
+};
+struct WaveBufs {
+  RayQ* rays;
+  uint32_t* count;  // number of rays queued (device counter)
+  uint32_t capacity;
+  uint8_t* occ;  // any-hit results   [slot * npix + pixel]
+  HitRec* hits;  // closest results   [slot * npix + pixel]
+  uint32_t npix;
+};
+
 struct FrameCtx {
   int width, height;
   int y0, y1;  // rows rendered by this handle (band)
@@ -33,20 +48,91 @@ struct FrameCtx {
   uint32_t frame_key;
   int spatial_iter;
   unsigned long long* counters;  // [0] closest, [1] any-hit as written, [2] any-hit traced
+  WaveBufs wave;
 };
 
 struct Cnt {
   uint32_t closest, anyW, anyT;
 };
 
-// ---- visibility policies ----------------------------------------------------------
+RB_HD SurfaceHit no_hit() {
+  SurfaceHit h;
+  h.didHit = false;
+  h.normal = v3(0);
+  h.hitPoint = v3(0);
+  h.t = FLT_MAX;
+  h.tri = h.geomID = h.primID = 0xFFFFFFFFu;
+  h.material = 0;
+  h.emissiveId = -1;
+  return h;
+}
+// reserve one queue slot; on the device the atomic is aggregated over the currently converged lanes
+RB_HD uint32_t queue_reserve(uint32_t* counter) {
+#if defined(__CUDA_ARCH__)
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x + threadIdx.y * blockDim.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+#else
+  return __atomic_fetch_add(counter, 1u, __ATOMIC_RELAXED);
+#endif
+}
+
+// ---- visibility / closest-hit policies ----------------------------------------------
+// InlineVis: every query is traced on the spot by the calling thread.
 struct InlineVis {
+  static constexpr bool kStore = true;
   const FrameCtx* fc;
+  uint32_t pixel;
   RB_HD bool visible(int /*slot*/, const V3& from, const V3& to) const {
     return !test_occlusion(fc->sc, from, to, fc->P.tnearOffset, fc->P.tfarOffset);
   }
   RB_HD SurfaceHit closest(int /*slot*/, const V3& org, const V3& dir, float tnear, float tfar) const {
     return intersect_surface(fc->sc, org, dir, tnear, tfar);
+  }
+};
+// GenVis: the stream half. Queries are appended to the ray queue and answered "visible" / "miss"; the pass body
+// runs only to enumerate its rays, its stores are suppressed (kStore).
+struct GenVis {
+  static constexpr bool kStore = false;
+  const FrameCtx* fc;
+  uint32_t pixel;
+  RB_HD void push(int slot, const V3& o, const V3& d, float tfar) const {
+    const WaveBufs& w = fc->wave;
+    const uint32_t i = queue_reserve(w.count);
+    if (i < w.capacity) {
+      st4(&w.rays[i].o_tfar, f4(o, tfar));
+      st4(&w.rays[i].d_dest, f4(d, u2f((uint32_t)slot * w.npix + pixel)));
+    }
+  }
+  RB_HD bool visible(int slot, const V3& from, const V3& to) const {
+    V3 dir;
+    float tfar;
+    shadow_ray(from, to, fc->P.tfarOffset, &dir, &tfar);
+    push(slot, from, dir, tfar);
+    return true;
+  }
+  RB_HD SurfaceHit closest(int slot, const V3& org, const V3& dir, float /*tnear*/, float tfar) const {
+    push(slot, org, dir, tfar);
+    return no_hit();
+  }
+};
+// ResolveVis: the resolve half. The same queries, in the same order, read the traced results.
+struct ResolveVis {
+  static constexpr bool kStore = true;
+  const FrameCtx* fc;
+  uint32_t pixel;
+  RB_HD bool visible(int slot, const V3& from, const V3& to) const {
+    const WaveBufs& w = fc->wave;
+    if (w.occ == nullptr) return !test_occlusion(fc->sc, from, to, fc->P.tnearOffset, fc->P.tfarOffset);
+    return w.occ[(size_t)slot * w.npix + pixel] == 0;
+  }
+  RB_HD SurfaceHit closest(int slot, const V3& org, const V3& dir, float /*tnear*/, float /*tfar*/) const {
+    const WaveBufs& w = fc->wave;
+    return surface_from_hit(fc->sc, org, dir, w.hits[(size_t)slot * w.npix + pixel]);
   }
 };
 
@@ -325,7 +411,7 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   const GElem g = load_gelem(fc.G, pi);
   Reservoir r = empty_reservoir();
   if (g.isEmissive || fc.sc.n_lights == 0) {
-    store_reservoir(fc.Rwrite, pi, r);
+    if (Vis::kStore) store_reservoir(fc.Rwrite, pi, r);
     return;
   }
   const RbParams& P = fc.P;
@@ -400,7 +486,7 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
     const V3 wi = brdf_sample(g, sh, key, base, &pdf);
     const V3 org = g.pos + P.normalOffset * g.normal;
     cnt.closest++;
-    const SurfaceHit h = vis.closest(P.M_Area + i, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
+    const SurfaceHit h = vis.closest(i, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
     LightSample s = invalid_sample();
     float W = 0, misWeight = 0;
     if (h.didHit && h.emissiveId >= 0) {
@@ -435,7 +521,26 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   const float p_hat = p_sel;
   r.W = p_hat > 0.0f ? 1.0f / p_hat * r.w_sum : 0.0f;
   r.confidence = imin(r.confidence, P.confidenceCap);
-  store_reservoir(fc.Rwrite, pi, r);
+  if (Vis::kStore) store_reservoir(fc.Rwrite, pi, r);
+}
+
+// Stream half of the initial pass: only the BRDF-sampled closest-hit rays (brdfSampleLight, :136-141). The
+// directions depend on the G-buffer element and the RNG alone, so they are emitted up front, traced by the
+// closest-hit kernel, and consumed by initial_pixel through ResolveVis::closest.
+RB_HD void initial_brdf_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const GElem g = load_gelem(fc.G, pi);
+  if (g.isEmissive || fc.sc.n_lights == 0) return;
+  const RbParams& P = fc.P;
+  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+  const Shading sh = make_shading(g, fc.cam.pos);
+  for (int i = 0; i < P.M_Brdf; ++i) {
+    const uint32_t base = 4u * (uint32_t)(P.M_Area + i);
+    float pdf;
+    const V3 wi = brdf_sample(g, sh, key, base, &pdf);
+    const V3 org = g.pos + P.normalOffset * g.normal;
+    (void)vis.closest(i, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
+  }
 }
 
 // =====================================================================================
@@ -455,7 +560,7 @@ RB_HD void visibility_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cn
   const bool V = vis.visible(0, xyz(pd), xyz(pw));
   if (!V) {
     nw.w = 0.0f;
-    st4(fc.Rwrite.normal_W + pi, nw);
+    if (Vis::kStore) st4(fc.Rwrite.normal_W + pi, nw);
   }
 }
 
@@ -489,7 +594,7 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
   const GElem curElem = load_gelem(fc.G, pi);
   int px, py;
   if (!reproject(fc.prevCam, fc.width, fc.height, curElem.pos, &px, &py)) {
-    store_reservoir(fc.Rwrite, pi, cur);
+    if (Vis::kStore) store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
   const GElem prevElem = load_gelem(fc.Gprev, (size_t)py * fc.width + px);
@@ -498,13 +603,13 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
   const float prevDepth = length(prevElem.pos - prevCam);
   const float depthRatio = currentDepth > prevDepth ? prevDepth / currentDepth : currentDepth / prevDepth;
   if (depthRatio < 0.9f) {
-    store_reservoir(fc.Rwrite, pi, cur);
+    if (Vis::kStore) store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
   const V3 prevPosAtCurrent = xyz(ld4(fc.Gprev.pos_depth + pi));
   int fx, fy;
   if (!reproject(fc.cam, fc.width, fc.height, prevPosAtCurrent, &fx, &fy)) {
-    store_reservoir(fc.Rwrite, pi, cur);
+    if (Vis::kStore) store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
   const V3 fwPos = xyz(ld4(fc.G.pos_depth + (size_t)fy * fc.width + fx));
@@ -512,7 +617,7 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
   const float prevDepthP = length(fwPos - curCam);
   const float depthRatioP = currentDepthP > prevDepthP ? prevDepthP / currentDepthP : currentDepthP / prevDepthP;
   if (depthRatioP < 0.9f) {
-    store_reservoir(fc.Rwrite, pi, cur);
+    if (Vis::kStore) store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
   const Reservoir prev = load_reservoir(fc.Rlast, pi);  // same pixel, not the reprojected one (:641)
@@ -551,7 +656,7 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
     if (wC) cnt.anyW++;
   }
   out.W = final_p_hat > 0.0f ? out.w_sum / final_p_hat : 0.0f;
-  store_reservoir(fc.Rwrite, pi, out);
+  if (Vis::kStore) store_reservoir(fc.Rwrite, pi, out);
 }
 
 // =====================================================================================
@@ -565,7 +670,7 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   const RbParams& P = fc.P;
   const GElem thisElem = load_gelem(fc.G, pi);
   if (thisElem.isEmissive) {
-    store_reservoir(fc.Rwrite, pi, load_reservoir(fc.Rread, pi));
+    if (Vis::kStore) store_reservoir(fc.Rwrite, pi, load_reservoir(fc.Rread, pi));
     return;
   }
   const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
@@ -707,7 +812,7 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
     out.W = final_p_hat > 0.0f ? correctionFactor * out.w_sum / final_p_hat : 0.0f;
   }
   out.confidence = imin(out.confidence, P.confidenceCap);
-  store_reservoir(fc.Rwrite, pi, out);
+  if (Vis::kStore) store_reservoir(fc.Rwrite, pi, out);
 }
 
 // =====================================================================================

@@ -5,16 +5,18 @@
 // (:85-113). B200 has no RT cores: this is ordinary SM code.
 //
 // Node8 (80 B = 5 x 16 B, AoSoA, 16-byte aligned):
-//   n0 = { origin.xyz, bits: ex | ey<<8 | ez<<16 | imask<<24 }   ex.. = biased exponents of the grid step
+//   n0 = { origin'.xyz, bits: ex | ey<<8 | ez<<16 | imask<<24 }   ex.. = biased exponents of the grid step
 //   n1 = { child_base, tri_base, meta[0..3], meta[4..7] }
 //   n2 = { qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7] }
 //   n3 = { qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7] }
 //   n4 = { qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7] }
-// Child boxes are 8-bit grid coordinates relative to the node origin, rounded
-// outwards. meta[s] of slot s: 0 = empty; internal child: (1<<5) | (24+s);
-// leaf: (unary triangle count in bits 5..7) | triangle offset (0..23).
-// Children sit in slots chosen at build time so that (slot ^ ray octant) orders
-// them front to back (compressed-wide-BVH scheme of Ylitie, Karras & Laine 2017).
+// Child boxes are 7-bit grid coordinates q (one per byte), rounded outwards; a plane sits at
+// origin' + (128 + q) * step and the float 128 + q is assembled with ONE byte permute
+// (0x43000000 | q << 16) — no integer-to-float conversion on the quarter-rate pipe.
+// meta[s] of slot s: 0 = empty; internal child: (1<<5) | (24+s); leaf: (unary triangle count in
+// bits 5..7) | triangle offset (0..23). Children sit in slots chosen at build time so that
+// (slot ^ ray octant) orders them front to back (compressed-wide-BVH scheme of Ylitie, Karras &
+// Laine 2017).
 #ifndef RB_SCENE_CUH_
 #define RB_SCENE_CUH_
 
@@ -90,117 +92,159 @@ RB_HD int popc(uint32_t x) {
   return __builtin_popcount(x);
 #endif
 }
+// 128 + (byte k of w) as a float, for 7-bit bytes
+template <int K>
+RB_HD float q7f(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(__byte_perm(w, 0x43000000u, 0x7044u | (K << 8)));
+#else
+  return u2f(0x43000000u | (((w >> (8 * K)) & 0xFFu) << 16));
+#endif
+}
+// bits 0..3 of m -> bytes 0..3 set to 0xFF
+RB_HD uint32_t expand_nibble(uint32_t m) { return (((m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
-// One ray against the BVH. ANY = true: stop at the first hit with tnear < t < tfar
-// (rtcOccluded1); ANY = false: closest hit, ties by smaller scene-order index.
-template <bool ANY>
-RB_HD bool trace8(const SceneDev& sc, const V3& o, const V3& d, float tnear, float tfar, HitRec* out) {
+// Traversal state of one ray (registers + a per-thread stack).
+struct Trav {
+  V3 o, d;
+  float dx, dy, dz;     // direction with zero components replaced by +-1e-30 (finite slopes)
+  float idx, idy, idz;  // 1 / (dx,dy,dz)
+  float tnear, tfar;
+  uint32_t oct_inv;
+  U2 ngroup;
+  int sp;
   HitRec best;
-  best.t = tfar;
-  best.u = best.v = 0;
-  best.tri = 0xFFFFFFFFu;
-  if (sc.n_nodes == 0) {
-    if (out) *out = best;
-    return false;
-  }
+  bool hit_any;
+  U2 stack[RB_STACK_MAX];
+};
+
+// returns false when the ray cannot hit anything (empty scene, NaN direction)
+RB_HD bool trav_init(Trav& T, const SceneDev& sc, const V3& o, const V3& d, float tnear, float tfar) {
+  T.o = o;
+  T.d = d;
+  T.tnear = tnear;
+  T.tfar = tfar;
+  T.best.t = tfar;
+  T.best.u = T.best.v = 0;
+  T.best.tri = 0xFFFFFFFFu;
+  T.hit_any = false;
+  T.sp = 0;
+  T.ngroup = U2{0u, 0x80000000u};  // root: one pending internal child at bit 31 with imask 0 -> node index 0
+  if (sc.n_nodes == 0) return false;
+  if (!(d.x == d.x && d.y == d.y && d.z == d.z)) return false;  // NaN direction (from == to)
   // safe reciprocal: a zero component becomes a huge finite slope (keeps the slab test conservative, no NaN)
   const float tiny = 1e-30f;
-  float dx = fabsf_(d.x) < tiny ? (dm::f2u(d.x) >> 31 ? -tiny : tiny) : d.x;
-  float dy = fabsf_(d.y) < tiny ? (dm::f2u(d.y) >> 31 ? -tiny : tiny) : d.y;
-  float dz = fabsf_(d.z) < tiny ? (dm::f2u(d.z) >> 31 ? -tiny : tiny) : d.z;
-  const float idx = fdiv_(1.0f, dx), idy = fdiv_(1.0f, dy), idz = fdiv_(1.0f, dz);
-  const uint32_t oct_inv = (dx < 0 ? 0u : 1u) | (dy < 0 ? 0u : 2u) | (dz < 0 ? 0u : 4u);  // 7 - octant
-
-  if (!(d.x == d.x && d.y == d.y && d.z == d.z)) {  // NaN direction (from == to): nothing can be hit
-    if (out) *out = best;
-    return false;
-  }
-
-  U2 stack[RB_STACK_MAX];
-  int sp = 0;
-  // root: one pending internal child at bit 31 with imask 0 -> node index 0
-  U2 ngroup = U2{0u, 0x80000000u};
-
-  while (true) {
-    // ---- descend into the nearest pending child of the current node group -------------
-    const uint32_t hits = ngroup.y;
-    const int bit = bfind(hits);
-    ngroup.y &= ~(1u << bit);
-    if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
-    const uint32_t slot = ((uint32_t)(bit - 24)) ^ oct_inv;
-    const uint32_t node_index = ngroup.x + popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
-
-    const F4* np = sc.node8 + 5 * (size_t)node_index;
-    const F4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4);
-    const uint32_t ebits = f2u(n0.w);
-    const uint32_t imask = ebits >> 24;
-    const float ax = u2f(byte_of(ebits, 0) << 23) * idx, ay = u2f(byte_of(ebits, 1) << 23) * idy,
-                az = u2f(byte_of(ebits, 2) << 23) * idz;
-    const float bx = (n0.x - o.x) * idx, by = (n0.y - o.y) * idy, bz = (n0.z - o.z) * idz;
-    const float tcull = ANY ? tfar : best.t * 1.000001f;
-    uint32_t hitmask = 0;
-    const uint32_t metaw[2] = {f2u(n1.z), f2u(n1.w)};
-    const uint32_t qlx[2] = {f2u(n2.x), f2u(n2.y)}, qly[2] = {f2u(n2.z), f2u(n2.w)}, qlz[2] = {f2u(n3.x), f2u(n3.y)};
-    const uint32_t qhx[2] = {f2u(n3.z), f2u(n3.w)}, qhy[2] = {f2u(n4.x), f2u(n4.y)}, qhz[2] = {f2u(n4.z), f2u(n4.w)};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint32_t meta = byte_of(metaw[i >> 2], i & 3);
-      if (meta == 0) continue;
-      const float lx = (float)byte_of(qlx[i >> 2], i & 3), hx = (float)byte_of(qhx[i >> 2], i & 3);
-      const float ly = (float)byte_of(qly[i >> 2], i & 3), hy = (float)byte_of(qhy[i >> 2], i & 3);
-      const float lz = (float)byte_of(qlz[i >> 2], i & 3), hz = (float)byte_of(qhz[i >> 2], i & 3);
-      const float t0x = fmaf_(dx < 0 ? hx : lx, ax, bx), t1x = fmaf_(dx < 0 ? lx : hx, ax, bx);
-      const float t0y = fmaf_(dy < 0 ? hy : ly, ay, by), t1y = fmaf_(dy < 0 ? ly : hy, ay, by);
-      const float t0z = fmaf_(dz < 0 ? hz : lz, az, bz), t1z = fmaf_(dz < 0 ? lz : hz, az, bz);
-      const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tnear));
-      const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tcull));
-      if (tmin <= tmax) {
-        const uint32_t internal = (imask >> i) & 1u;
-        const uint32_t shift = (meta & 31u) ^ (internal ? oct_inv : 0u);
-        hitmask |= (meta >> 5) << shift;
-      }
-    }
-    ngroup.x = f2u(n1.x);
-    ngroup.y = (hitmask & 0xFF000000u) | imask;
-    const uint32_t tbase = f2u(n1.y);
-    uint32_t tbits = hitmask & 0x00FFFFFFu;
-
-    // ---- leaf triangles of this node ---------------------------------------------------
-    while (tbits != 0) {
-      const int ti = bfind(tbits);
-      tbits &= ~(1u << ti);
-      const F4* tp = sc.tri_isect + 3 * (size_t)(tbase + (uint32_t)ti);
-      const F4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
-      float t, u, v;
-      if (tri_test(o, d, a, b, c, tnear, tfar, &t, &u, &v)) {
-        const uint32_t id = f2u(c.y);
-        if (ANY) {
-          if (out) {
-            out->t = t, out->u = u, out->v = v, out->tri = id;
-          }
-          return true;
-        }
-        if (best.tri == 0xFFFFFFFFu || t < best.t || (t == best.t && id < best.tri)) {
-          best.t = t, best.u = u, best.v = v, best.tri = id;
-        }
-      }
-    }
-
-    if (ngroup.y <= 0x00FFFFFFu) {
-      if (sp == 0) break;
-      ngroup = stack[--sp];
-    }
-  }
-  if (out) *out = best;
-  return best.tri != 0xFFFFFFFFu;
+  T.dx = fabsf_(d.x) < tiny ? (f2u(d.x) >> 31 ? -tiny : tiny) : d.x;
+  T.dy = fabsf_(d.y) < tiny ? (f2u(d.y) >> 31 ? -tiny : tiny) : d.y;
+  T.dz = fabsf_(d.z) < tiny ? (f2u(d.z) >> 31 ? -tiny : tiny) : d.z;
+  T.idx = fdiv_(1.0f, T.dx), T.idy = fdiv_(1.0f, T.dy), T.idz = fdiv_(1.0f, T.dz);
+  T.oct_inv = (T.dx < 0 ? 0u : 1u) | (T.dy < 0 ? 0u : 2u) | (T.dz < 0 ? 0u : 4u);  // 7 - octant
+  return true;
 }
 
-// Intersection::testOcclusion, P/Intersection.h:43-60 (no normal offset; tnear = FLT_MIN + tnearOffset;
+#define RB_CHILD_TEST(I, WX0, WX1, WY0, WY1, WZ0, WZ1, MB, MI)                                    \
+  {                                                                                               \
+    const float t0x = fmaf_(q7f<(I)&3>(WX0), ax, bx), t1x = fmaf_(q7f<(I)&3>(WX1), ax, bx);       \
+    const float t0y = fmaf_(q7f<(I)&3>(WY0), ay, by), t1y = fmaf_(q7f<(I)&3>(WY1), ay, by);       \
+    const float t0z = fmaf_(q7f<(I)&3>(WZ0), az, bz), t1z = fmaf_(q7f<(I)&3>(WZ1), az, bz);       \
+    const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, T.tnear));                               \
+    const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tcull));                                 \
+    if (tmin <= tmax) hitmask |= byte_of(MB, (I)&3) << byte_of(MI, (I)&3);                        \
+  }
+
+// One traversal step: descend into the nearest pending child of the current node group, test its eight child
+// boxes, then its leaf triangles. ANY: stop at the first hit (rtcOccluded1); otherwise keep the closest hit,
+// ties by smaller scene-order index. Returns false when the ray is finished.
+template <bool ANY>
+RB_HD bool trav_step(Trav& T, const SceneDev& sc) {
+  const uint32_t hits = T.ngroup.y;
+  const int bit = bfind(hits);
+  T.ngroup.y &= ~(1u << bit);
+  if (T.ngroup.y > 0x00FFFFFFu) T.stack[T.sp++] = T.ngroup;
+  const uint32_t slot = ((uint32_t)(bit - 24)) ^ T.oct_inv;
+  const uint32_t node_index = T.ngroup.x + popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
+
+  const F4* np = sc.node8 + 5 * (size_t)node_index;
+  const F4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4);
+  const uint32_t ebits = f2u(n0.w);
+  const uint32_t imask = ebits >> 24;
+  const float ax = u2f(byte_of(ebits, 0) << 23) * T.idx, ay = u2f(byte_of(ebits, 1) << 23) * T.idy,
+              az = u2f(byte_of(ebits, 2) << 23) * T.idz;
+  const float bx = (n0.x - T.o.x) * T.idx, by = (n0.y - T.o.y) * T.idy, bz = (n0.z - T.o.z) * T.idz;
+  const float tcull = ANY ? T.tfar : T.best.t * 1.000001f;
+  // near / far plane words per axis, chosen once per node by the ray direction sign
+  const bool nx = T.dx < 0, ny = T.dy < 0, nz = T.dz < 0;
+  const uint32_t x0a = f2u(nx ? n3.z : n2.x), x0b = f2u(nx ? n3.w : n2.y), x1a = f2u(nx ? n2.x : n3.z), x1b = f2u(nx ? n2.y : n3.w);
+  const uint32_t y0a = f2u(ny ? n4.x : n2.z), y0b = f2u(ny ? n4.y : n2.w), y1a = f2u(ny ? n2.z : n4.x), y1b = f2u(ny ? n2.w : n4.y);
+  const uint32_t z0a = f2u(nz ? n4.z : n3.x), z0b = f2u(nz ? n4.w : n3.y), z1a = f2u(nz ? n3.x : n4.z), z1b = f2u(nz ? n3.y : n4.w);
+  // per-child hit-mask contribution: (meta >> 5) << ((meta & 31) ^ (internal ? oct_inv : 0)), 4 children per word
+  const uint32_t meta_a = f2u(n1.z), meta_b = f2u(n1.w);
+  const uint32_t oct4 = T.oct_inv * 0x01010101u;
+  const uint32_t mia = (meta_a ^ (oct4 & expand_nibble(imask))) & 0x1F1F1F1Fu;
+  const uint32_t mib = (meta_b ^ (oct4 & expand_nibble(imask >> 4))) & 0x1F1F1F1Fu;
+  const uint32_t mba = (meta_a >> 5) & 0x07070707u, mbb = (meta_b >> 5) & 0x07070707u;
+  uint32_t hitmask = 0;
+  RB_CHILD_TEST(0, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
+  RB_CHILD_TEST(1, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
+  RB_CHILD_TEST(2, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
+  RB_CHILD_TEST(3, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
+  RB_CHILD_TEST(4, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
+  RB_CHILD_TEST(5, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
+  RB_CHILD_TEST(6, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
+  RB_CHILD_TEST(7, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
+  T.ngroup.x = f2u(n1.x);
+  T.ngroup.y = (hitmask & 0xFF000000u) | imask;
+  const uint32_t tbase = f2u(n1.y);
+  uint32_t tbits = hitmask & 0x00FFFFFFu;
+
+  while (tbits != 0) {
+    const int ti = bfind(tbits);
+    tbits &= ~(1u << ti);
+    const F4* tp = sc.tri_isect + 3 * (size_t)(tbase + (uint32_t)ti);
+    const F4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+    float t, u, v;
+    if (tri_test(T.o, T.d, a, b, c, T.tnear, T.tfar, &t, &u, &v)) {
+      const uint32_t id = f2u(c.y);
+      if (ANY) {
+        T.best.t = t, T.best.u = u, T.best.v = v, T.best.tri = id;
+        T.hit_any = true;
+        return false;
+      }
+      if (T.best.tri == 0xFFFFFFFFu || t < T.best.t || (t == T.best.t && id < T.best.tri)) {
+        T.best.t = t, T.best.u = u, T.best.v = v, T.best.tri = id;
+      }
+    }
+  }
+  if (T.ngroup.y <= 0x00FFFFFFu) {
+    if (T.sp == 0) return false;
+    T.ngroup = T.stack[--T.sp];
+  }
+  return true;
+}
+
+// One ray to completion.
+template <bool ANY>
+RB_HD bool trace8(const SceneDev& sc, const V3& o, const V3& d, float tnear, float tfar, HitRec* out) {
+  Trav T;
+  if (trav_init(T, sc, o, d, tnear, tfar)) {
+    while (trav_step<ANY>(T, sc)) {
+    }
+  }
+  if (out) *out = T.best;
+  return T.best.tri != 0xFFFFFFFFu;
+}
+
+// Shadow ray of Intersection::testOcclusion, P/Intersection.h:43-60 (no normal offset; tnear = FLT_MIN + tnearOffset;
 // tfar = dist - tfarOffset)
+RB_HD void shadow_ray(const V3& from, const V3& to, float tfarOffset, V3* dir, float* tfar) {
+  *tfar = length(to - from) - tfarOffset;
+  *dir = normalize(to - from);
+}
 RB_HD bool test_occlusion(const SceneDev& sc, const V3& from, const V3& to, float tnearOffset, float tfarOffset) {
-  const float dist = length(to - from);
-  const V3 dir = normalize(to - from);
-  return trace8<true>(sc, from, dir, FLT_MIN + tnearOffset, dist - tfarOffset, nullptr);
+  V3 dir;
+  float tfar;
+  shadow_ray(from, to, tfarOffset, &dir, &tfar);
+  return trace8<true>(sc, from, dir, FLT_MIN + tnearOffset, tfar, nullptr);
 }
 
 // Intersection::intersectEmbree + getGeometryAttributes, :8-41, 85-113, for untextured materials:
@@ -212,7 +256,7 @@ struct SurfaceHit {
   uint32_t tri, geomID, primID, material;
   int emissiveId;
 };
-RB_HD SurfaceHit intersect_surface(const SceneDev& sc, const V3& org, const V3& dir, float tnear, float tfar) {
+RB_HD SurfaceHit surface_from_hit(const SceneDev& sc, const V3& org, const V3& dir, const HitRec& r) {
   SurfaceHit h;
   h.didHit = false;
   h.normal = v3(0);
@@ -221,8 +265,7 @@ RB_HD SurfaceHit intersect_surface(const SceneDev& sc, const V3& org, const V3& 
   h.tri = h.geomID = h.primID = 0xFFFFFFFFu;
   h.material = 0;
   h.emissiveId = -1;
-  HitRec r;
-  if (!trace8<false>(sc, org, dir, tnear, tfar, &r)) return h;
+  if (r.tri == 0xFFFFFFFFu) return h;
   const F4* np = sc.tri_normals + 3 * (size_t)r.tri;
   const F4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
   const V3 n0 = xyz(a), n1 = v3(a.w, b.x, b.y), n2 = v3(b.z, b.w, c.x);
@@ -241,6 +284,11 @@ RB_HD SurfaceHit intersect_surface(const SceneDev& sc, const V3& org, const V3& 
   h.material = info.z;
   h.emissiveId = (int)info.w;
   return h;
+}
+RB_HD SurfaceHit intersect_surface(const SceneDev& sc, const V3& org, const V3& dir, float tnear, float tfar) {
+  HitRec r;
+  trace8<false>(sc, org, dir, tnear, tfar, &r);
+  return surface_from_hit(sc, org, dir, r);
 }
 
 }  // namespace rb

@@ -37,25 +37,104 @@ __device__ __forceinline__ void flush_counts(unsigned long long* ctr, const Cnt&
   }
 }
 
-#define RB_PIXEL_KERNEL(NAME, CALL)                                   \
-  __global__ void __launch_bounds__(kTileW* kTileH) NAME(FrameCtx fc) { \
-    const int x = blockIdx.x * kTileW + threadIdx.x;                  \
-    const int y = fc.y0 + blockIdx.y * kTileH + threadIdx.y;          \
-    Cnt cnt = {0, 0, 0};                                              \
-    const InlineVis vis = {&fc};                                      \
-    (void)vis;                                                        \
-    if (x < fc.width && y < fc.y1) {                                  \
-      CALL;                                                           \
-    }                                                                 \
-    flush_counts(fc.counters, cnt);                                   \
+// One thread per pixel, 8x4 pixels per warp. VIS is the visibility policy: InlineVis (trace on the spot),
+// GenVis (stream half: emit rays), ResolveVis (resolve half: read traced results). COUNT: whether this launch
+// contributes to the ray counters (the stream half of a pass does not: the resolve half counts the same rays).
+#define RB_PIXEL_KERNEL(NAME, VIS, COUNT, MINB, CALL)                          \
+  __global__ void __launch_bounds__(kTileW* kTileH, MINB) NAME(FrameCtx fc) {   \
+    const int x = blockIdx.x * kTileW + threadIdx.x;                           \
+    const int y = fc.y0 + blockIdx.y * kTileH + threadIdx.y;                   \
+    Cnt cnt = {0, 0, 0};                                                       \
+    if (x < fc.width && y < fc.y1) {                                           \
+      const VIS vis = {&fc, (uint32_t)(y * fc.width + x)};                     \
+      (void)vis;                                                               \
+      CALL;                                                                    \
+    }                                                                          \
+    if (COUNT) flush_counts(fc.counters, cnt);                                 \
   }
 
-RB_PIXEL_KERNEL(k_gbuffer, gbuffer_pixel(fc, x, y, cnt))
-RB_PIXEL_KERNEL(k_initial, initial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_visibility, visibility_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal, temporal_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_spatial, spatial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_shade, shade_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_gbuffer, InlineVis, true, 1, gbuffer_pixel(fc, x, y, cnt))
+RB_PIXEL_KERNEL(k_initial, InlineVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_visibility, InlineVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal, InlineVis, true, 1, temporal_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial, InlineVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_shade, InlineVis, true, 1, shade_pixel(fc, x, y, vis, cnt))
+// wavefront halves
+RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
+RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal_stream, GenVis, false, 1, temporal_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 1, temporal_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial_stream, GenVis, false, 1, spatial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
+
+// ---- persistent traversal kernels over the ray queue ------------------------------------------------
+// One ray per lane; warps pull rays from the queue with one aggregated atomic and refill the lanes whose rays
+// have terminated once fewer than kRefill lanes are still busy (dynamic fetch), so that long traversals do not
+// leave most of the warp idle. Grid = a multiple of the SM count, sized by the host.
+constexpr int kTraceThreads = 128;
+constexpr int kRefill = 22;
+
+template <bool ANY>
+__global__ void __launch_bounds__(kTraceThreads) k_trace_queue(SceneDev sc, const RayQ* __restrict__ rays,
+                                                               const uint32_t* __restrict__ count_ptr, uint32_t capacity,
+                                                               uint32_t* __restrict__ next, uint8_t* __restrict__ occ,
+                                                               HitRec* __restrict__ hits, float tnear) {
+  const uint32_t count = min(*count_ptr, capacity);
+  const unsigned lane = threadIdx.x & 31u;
+  Trav T;
+  bool active = false;
+  bool exhausted = false;  // warp-uniform
+  uint32_t dest = 0;
+  while (true) {
+    // ---- refill idle lanes ---------------------------------------------------------------------
+    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (!exhausted && idle != 0) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(next, (uint32_t)__popc(idle));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (base + __popc(idle) >= count) exhausted = true;
+      if (!active) {
+        const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+        if (i < count) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(&rays[i].o_tfar));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(&rays[i].d_dest));
+          dest = __float_as_uint(b.w);
+          active = trav_init(T, sc, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), tnear, a.w);
+          if (!active) {  // cannot hit anything
+            if (ANY)
+              occ[dest] = 0;
+            else
+              hits[dest] = T.best;
+          }
+        }
+      }
+    }
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- traverse until too few lanes are busy ----------------------------------------------------
+    while (true) {
+      if (active) {
+        if (!trav_step<ANY>(T, sc)) {
+          if (ANY)
+            occ[dest] = T.hit_any ? 1 : 0;
+          else
+            hits[dest] = T.best;
+          active = false;
+        }
+      }
+      const int busy = __popc(__ballot_sync(0xFFFFFFFFu, active));
+      if (busy == 0 || (busy < kRefill && !exhausted)) break;
+    }
+  }
+}
+__global__ void k_reset_queue(uint32_t* count, uint32_t* next) {
+  *count = 0;
+  *next = 0;
+}
 
 // ---- ray seam ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_trace_closest(SceneDev sc, const RbRay* rays, RbHit* hits, uint32_t n) {
@@ -142,7 +221,14 @@ struct RbContext {
   RbSceneStats stats{};
 
   cudaEvent_t ev[16]{};
+  static constexpr int kMaxEvents = 96;
+  cudaEvent_t fev[kMaxEvents]{};  // per-kernel frame events
   bool evCreated = false;
+  int numSMs = 148;
+
+  // wavefront buffers
+  WaveBufs wave{};
+  size_t waveRayCap = 0, waveOccCap = 0, waveHitCap = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -261,7 +347,9 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     RB_TRY(dev_alloc(h, &h->counters, 8, h->allocs));
     RB_CUDA(cudaMemsetAsync(h->counters, 0, 64, h->stream));
     for (auto& ev : h->ev) RB_CUDA(cudaEventCreate(&ev));
+    for (auto& ev : h->fev) RB_CUDA(cudaEventCreate(&ev));
     h->evCreated = true;
+    RB_CUDA(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, info->device));
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
     RB_TRY(dev_alloc(h, &d, 1, h->allocs));
@@ -288,8 +376,14 @@ void rb_destroy(RbHandle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   free_list(h->allocs);
   free_list(h->sceneAllocs);
-  if (h->evCreated)
+  if (h->evCreated) {
     for (auto& ev : h->ev) cudaEventDestroy(ev);
+    for (auto& ev : h->fev) cudaEventDestroy(ev);
+  }
+  if (h->wave.rays) cudaFree(h->wave.rays);
+  if (h->wave.occ) cudaFree(h->wave.occ);
+  if (h->wave.hits) cudaFree(h->wave.hits);
+  if (h->wave.count) cudaFree(h->wave.count);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -564,6 +658,42 @@ static CamState cam_state(const RbCamera* c) {
   return s;
 }
 
+// wavefront buffers sized for `slots` rays per band pixel
+static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots) {
+  const size_t npix = (size_t)h->info.width * h->info.height;
+  const size_t band_px = (size_t)h->info.width * (h->info.band_y1 - h->info.band_y0);
+  const size_t need_rays = band_px * std::max<uint32_t>(slots, brdf_slots);
+  if (need_rays > h->waveRayCap) {
+    if (h->wave.rays) cudaFree(h->wave.rays);
+    h->wave.rays = nullptr;
+    h->waveRayCap = 0;
+    if (need_rays > 0xFFFFFFF0ull) {
+      h->err = "wavefront ray queue would exceed 2^32 rays";
+      return RB_ERR_UNSUPPORTED;
+    }
+    RB_CUDA(cudaMalloc((void**)&h->wave.rays, need_rays * sizeof(RayQ)));
+    h->waveRayCap = need_rays;
+  }
+  if ((size_t)slots * npix > h->waveOccCap) {
+    if (h->wave.occ) cudaFree(h->wave.occ);
+    h->wave.occ = nullptr;
+    RB_CUDA(cudaMalloc((void**)&h->wave.occ, (size_t)slots * npix));
+    h->waveOccCap = (size_t)slots * npix;
+  }
+  if ((size_t)brdf_slots * npix > h->waveHitCap) {
+    if (h->wave.hits) cudaFree(h->wave.hits);
+    h->wave.hits = nullptr;
+    RB_CUDA(cudaMalloc((void**)&h->wave.hits, (size_t)brdf_slots * npix * sizeof(HitRec)));
+    h->waveHitCap = (size_t)brdf_slots * npix;
+  }
+  if (!h->wave.count) {
+    RB_CUDA(cudaMalloc((void**)&h->wave.count, 2 * sizeof(uint32_t)));
+  }
+  h->wave.capacity = (uint32_t)h->waveRayCap;
+  h->wave.npix = (uint32_t)npix;
+  return RB_OK;
+}
+
 static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx, RbTimings* timings) {
   if (!h || !cam) return RB_ERR_INVALID_ARGUMENT;
   if (!h->haveScene) {
@@ -574,6 +704,14 @@ static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx
   const RbParams P = h->params;  // snapshot (the GUI thread may edit the host copy)
   const bool timed = h->info.collect_timings != 0 && timings != nullptr;
   cudaStream_t st = h->stream;
+  // The stream -> trace -> resolve split covers the passes whose rays do not depend on visibility results:
+  // BRDF-candidate rays, the visibility pass, temporal reuse, spatial reuse with constant weights.
+  const bool wave = P.wavefront != 0;
+  const bool wave_spatial = wave && P.spatialWeightCalc == RB_SW_CONSTANT;
+  if (wave) {
+    const uint32_t slots = std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u);
+    RB_TRY(ensure_wave(h, slots, (uint32_t)std::max(P.M_Brdf, 1)));
+  }
 
   FrameCtx fc{};
   fc.width = h->info.width;
@@ -588,12 +726,20 @@ static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx
   fc.Gprev = h->G[h->gCur ^ 1];
   fc.frame = h->frame;
   fc.counters = h->counters;
+  fc.wave = h->wave;
   const dim3 block(kTileW, kTileH);
   const dim3 grid((fc.width + kTileW - 1) / kTileW, (fc.y1 - fc.y0 + kTileH - 1) / kTileH);
   uint32_t launches = 0;
+  // event log: (pass, kind) per interval; kind 0 = streaming kernel, 1 = traversal kernel
+  struct Mark {
+    int pass, kind;
+  };
+  std::vector<Mark> marks;
   int evi = 0;
-  auto mark = [&]() {
-    if (timed) cudaEventRecord(h->ev[evi], st);
+  auto mark = [&](int pass, int kind) {
+    if (!timed || evi + 1 >= RbContext::kMaxEvents) return;
+    cudaEventRecord(h->fev[evi + 1], st);
+    marks.push_back({pass, kind});
     evi++;
   };
   auto bind = [&]() {
@@ -602,47 +748,111 @@ static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx
     fc.Rlast = h->R[h->rLast];
   };
   auto swap_rw = [&]() { std::swap(h->rRead, h->rWrite); };  // swapReservoirBuffers, P/simpleguidx11.h:116
+  const int trace_grid = h->numSMs * 8;
+  auto trace = [&](bool any, int pass) {
+    if (any)
+      k_trace_queue<true><<<trace_grid, kTraceThreads, 0, st>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
+                                                                 h->wave.count + 1, h->wave.occ, h->wave.hits,
+                                                                 FLT_MIN + P.tnearOffset);
+    else
+      k_trace_queue<false><<<trace_grid, kTraceThreads, 0, st>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
+                                                                  h->wave.count + 1, h->wave.occ, h->wave.hits,
+                                                                  FLT_MIN + P.tnearOffset);
+    launches++;
+    mark(pass, 1);
+  };
+  auto reset_queue = [&]() {
+    k_reset_queue<<<1, 1, 0, st>>>(h->wave.count, h->wave.count + 1);
+    launches++;
+  };
 
   RB_CUDA(cudaMemsetAsync(h->counters, 0, 64, st));
-  mark();  // 0
+  if (timed) cudaEventRecord(h->fev[0], st);
   bind();
+  // ---- G-buffer ------------------------------------------------------------------------------------
   fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_GBUF, 0);
   k_gbuffer<<<grid, block, 0, st>>>(fc);
   launches++;
-  mark();  // 1
+  mark(0, 0);
+  // ---- initial candidates ----------------------------------------------------------------------------
   fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_INITIAL, 0);
-  k_initial<<<grid, block, 0, st>>>(fc);
-  launches++;
-  mark();  // 2
-  if (P.doVisibilityPass) {
-    k_visibility<<<grid, block, 0, st>>>(fc);
-    launches++;
+  if (wave) {
+    if (P.M_Brdf > 0 && h->sc.n_lights > 0) {
+      reset_queue();
+      k_initial_brdf_stream<<<grid, block, 0, st>>>(fc);
+      launches++;
+      mark(1, 0);
+      trace(false, 1);
+    }
+    // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel
+    FrameCtx f2 = fc;
+    f2.wave.occ = nullptr;
+    k_initial_resolve<<<grid, block, 0, st>>>(f2);
+  } else {
+    k_initial<<<grid, block, 0, st>>>(fc);
   }
-  mark();  // 3
+  launches++;
+  mark(1, 0);
+  // ---- visibility ---------------------------------------------------------------------------------
+  if (P.doVisibilityPass) {
+    if (wave) {
+      reset_queue();
+      k_visibility_stream<<<grid, block, 0, st>>>(fc);
+      launches++;
+      mark(2, 0);
+      trace(true, 2);
+      k_visibility_resolve<<<grid, block, 0, st>>>(fc);
+    } else {
+      k_visibility<<<grid, block, 0, st>>>(fc);
+    }
+    launches++;
+    mark(2, 0);
+  }
+  // ---- temporal reuse ----------------------------------------------------------------------------------
   if (P.doTemporalReuse && frame_idx > 0 && h->havePrev) {
     swap_rw();
     bind();
     fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_TEMPORAL, 0);
-    k_temporal<<<grid, block, 0, st>>>(fc);
+    if (wave) {
+      reset_queue();
+      k_temporal_stream<<<grid, block, 0, st>>>(fc);
+      launches++;
+      mark(3, 0);
+      trace(true, 3);
+      k_temporal_resolve<<<grid, block, 0, st>>>(fc);
+    } else {
+      k_temporal<<<grid, block, 0, st>>>(fc);
+    }
     launches++;
+    mark(3, 0);
   }
-  mark();  // 4
+  // ---- spatial reuse -------------------------------------------------------------------------------------
   if (P.doSpatialReuse) {
     for (int i = 0; i < P.spatialPassCount; ++i) {
       swap_rw();
       bind();
       fc.spatial_iter = i;
       fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_SPATIAL, (uint32_t)i);
-      k_spatial<<<grid, block, 0, st>>>(fc);
+      if (wave_spatial) {
+        reset_queue();
+        k_spatial_stream<<<grid, block, 0, st>>>(fc);
+        launches++;
+        mark(4, 0);
+        trace(true, 4);
+        k_spatial_resolve<<<grid, block, 0, st>>>(fc);
+      } else {
+        k_spatial<<<grid, block, 0, st>>>(fc);
+      }
       launches++;
+      mark(4, 0);
     }
   }
-  mark();  // 5
+  // ---- shade -------------------------------------------------------------------------------------------
   swap_rw();
   bind();
   k_shade<<<grid, block, 0, st>>>(fc);
   launches++;
-  mark();  // 6
+  mark(5, 0);
   RB_CUDA(cudaGetLastError());
   // memcpy(reservoirsLastFrame, ...) + gBufferLastFrame.setDataFrom(gBuffer) (P/simpleguidx11.cpp:478-481) by rotation
   std::swap(h->rLast, h->rRead);
@@ -660,15 +870,20 @@ static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx
     timings->rays_any_traced = hc[2];
     timings->kernel_launches = launches;
     if (timed) {
-      float ms[6];
-      for (int i = 0; i < 6; ++i) RB_CUDA(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
-      timings->ms_gbuffer = ms[0];
-      timings->ms_initial = ms[1];
-      timings->ms_visibility = ms[2];
-      timings->ms_temporal = ms[3];
-      timings->ms_spatial = ms[4];
-      timings->ms_shade = ms[5];
-      RB_CUDA(cudaEventElapsedTime(&timings->ms_total, h->ev[0], h->ev[6]));
+      float* per_pass[6] = {&timings->ms_gbuffer, &timings->ms_initial, &timings->ms_visibility,
+                            &timings->ms_temporal, &timings->ms_spatial, &timings->ms_shade};
+      for (size_t i = 0; i < marks.size(); ++i) {
+        float ms = 0;
+        RB_CUDA(cudaEventElapsedTime(&ms, h->fev[i], h->fev[i + 1]));
+        *per_pass[marks[i].pass] += ms;
+        if (marks[i].kind == 1) {
+          timings->ms_trace[marks[i].pass] += ms;
+          timings->ms_trace_any += ms;
+        } else {
+          timings->ms_stream[marks[i].pass] += ms;
+        }
+      }
+      RB_CUDA(cudaEventElapsedTime(&timings->ms_total, h->fev[0], h->fev[marks.size()]));
     }
   }
   return RB_OK;

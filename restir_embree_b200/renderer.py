@@ -67,6 +67,16 @@ def load_library():
     return L
 
 
+def _timings_dict(t):
+    d = {}
+    for k, _ in abi.RbTimings._fields_:
+        if k == "reserved":
+            continue
+        v = getattr(t, k)
+        d[k] = list(v) if hasattr(v, "__len__") else v
+    return d
+
+
 class Renderer:
     def __init__(self, width, height, device=0, seed=123, band=None, collect_timings=True):
         self.L = load_library()
@@ -141,7 +151,7 @@ class Renderer:
         rc = self.L.rb_render_frame(self.h, C.byref(c), int(frame_idx), ptr, C.byref(t) if t is not None else None)
         self._check(rc, "rb_render_frame")
         if want_timings:
-            return out, {k: getattr(t, k) for k, _ in abi.RbTimings._fields_ if k != "reserved"}
+            return out, _timings_dict(t)
         return out
 
     def render_frame_device(self, cam, frame_idx, dev_ptr=None, want_timings=False):
@@ -151,7 +161,7 @@ class Renderer:
                                            C.byref(t) if t is not None else None)
         self._check(rc, "rb_render_frame_device")
         if want_timings:
-            return {k: getattr(t, k) for k, _ in abi.RbTimings._fields_ if k != "reserved"}
+            return _timings_dict(t)
         return None
 
     def synchronize(self):

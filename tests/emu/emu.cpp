@@ -216,18 +216,83 @@ int emu_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rg
   memset(E->counters, 0, sizeof(E->counters));
   auto bind = [&]() { fc.Rread = E->rp(E->rRead), fc.Rwrite = E->rp(E->rWrite), fc.Rlast = E->rp(E->rLast); };
   auto swap_rw = [&]() { std::swap(E->rRead, E->rWrite); };
-  const InlineVis vis = {&fc};
+  // wavefront mode: same stream -> trace -> resolve schedule as render_frame_impl, with host loops
+  const bool wave = P.wavefront != 0;
+  const bool wave_spatial = wave && P.spatialWeightCalc == RB_SW_CONSTANT;
+  const uint32_t npix = (uint32_t)(E->width * E->height);
+  const uint32_t slots = std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u);
+  std::vector<RayQ> rays;
+  std::vector<uint8_t> occ;
+  std::vector<HitRec> hits;
+  uint32_t qcount = 0;
+  if (wave) {
+    rays.resize((size_t)npix * std::max<uint32_t>(slots, (uint32_t)std::max(P.M_Brdf, 1)));
+    occ.assign((size_t)npix * slots, 0xCD);
+    hits.resize((size_t)npix * std::max(P.M_Brdf, 1));
+    fc.wave.rays = rays.data();
+    fc.wave.count = &qcount;
+    fc.wave.capacity = (uint32_t)rays.size();
+    fc.wave.occ = occ.data();
+    fc.wave.hits = hits.data();
+    fc.wave.npix = npix;
+  }
+  auto px = [&](int x, int y) { return (uint32_t)(y * fc.width + x); };
+  auto trace_queue = [&](bool any) {
+    const float tnear = FLT_MIN + P.tnearOffset;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < (int64_t)qcount; ++i) {
+      const RayQ& r = rays[i];
+      const uint32_t dest = f2u(r.d_dest.w);
+      HitRec hr;
+      const bool hit = any ? trace8<true>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr)
+                           : trace8<false>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr);
+      if (any)
+        occ[dest] = hit ? 1 : 0;
+      else
+        hits[dest] = hr;
+    }
+  };
+  auto stream = [&](auto&& body) {  // stream half: emits rays, counts nothing
+    qcount = 0;
+    unsigned long long save[3] = {E->counters[0], E->counters[1], E->counters[2]};
+    for_pixels(E, fc, body);
+    E->counters[0] = save[0], E->counters[1] = save[1], E->counters[2] = save[2];
+  };
   bind();
   fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_GBUF, 0);
   for_pixels(E, fc, [&](int x, int y, Cnt& c) { gbuffer_pixel(fc, x, y, c); });
   fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_INITIAL, 0);
-  for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, vis, c); });
-  if (P.doVisibilityPass) for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, vis, c); });
+  if (wave) {
+    if (P.M_Brdf > 0 && fc.sc.n_lights > 0) {
+      stream([&](int x, int y, Cnt&) { initial_brdf_gen_pixel(fc, x, y, GenVis{&fc, px(x, y)}); });
+      trace_queue(false);
+    }
+    FrameCtx f2 = fc;
+    f2.wave.occ = nullptr;
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(f2, x, y, ResolveVis{&f2, px(x, y)}, c); });
+  } else {
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
+  }
+  if (P.doVisibilityPass) {
+    if (wave) {
+      stream([&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, GenVis{&fc, px(x, y)}, c); });
+      trace_queue(true);
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, ResolveVis{&fc, px(x, y)}, c); });
+    } else {
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
+    }
+  }
   if (P.doTemporalReuse && frame_idx > 0 && E->havePrev) {
     swap_rw();
     bind();
     fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_TEMPORAL, 0);
-    for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, vis, c); });
+    if (wave) {
+      stream([&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, GenVis{&fc, px(x, y)}, c); });
+      trace_queue(true);
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, ResolveVis{&fc, px(x, y)}, c); });
+    } else {
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
+    }
   }
   if (P.doSpatialReuse) {
     for (int i = 0; i < P.spatialPassCount; ++i) {
@@ -235,12 +300,18 @@ int emu_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rg
       bind();
       fc.spatial_iter = i;
       fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_SPATIAL, (uint32_t)i);
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, vis, c); });
+      if (wave_spatial) {
+        stream([&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, GenVis{&fc, px(x, y)}, c); });
+        trace_queue(true);
+        for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, ResolveVis{&fc, px(x, y)}, c); });
+      } else {
+        for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
+      }
     }
   }
   swap_rw();
   bind();
-  for_pixels(E, fc, [&](int x, int y, Cnt& c) { shade_pixel(fc, x, y, vis, c); });
+  for_pixels(E, fc, [&](int x, int y, Cnt& c) { shade_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
   std::swap(E->rLast, E->rRead);
   E->gCur ^= 1;
   E->prevCam = fc.cam;
@@ -342,8 +413,9 @@ int emu_validate_bvh(void* h) {
       }
       float lo[3], hi[3];
       for (int a = 0; a < 3; ++a) {
-        lo[a] = org[a] + (float)byte_of(q[a][s >> 2], s & 3) * sc3[a];
-        hi[a] = org[a] + (float)byte_of(q[3 + a][s >> 2], s & 3) * sc3[a];
+        lo[a] = org[a] + (128.0f + (float)byte_of(q[a][s >> 2], s & 3)) * sc3[a];
+        hi[a] = org[a] + (128.0f + (float)byte_of(q[3 + a][s >> 2], s & 3)) * sc3[a];
+        if (byte_of(q[a][s >> 2], s & 3) > 127u || byte_of(q[3 + a][s >> 2], s & 3) > 127u) return 18;
         // carry the intersection of all ancestor boxes: triangles must lie inside every one of them
         lo[a] = fmaxf(lo[a], it.lo[a]);
         hi[a] = fminf(hi[a], it.hi[a]);

@@ -20,6 +20,12 @@ CONFIGS = [
     dict(M_Area=0, M_Brdf=3, doTemporalReuse=1),
     dict(M_Area=5, M_Brdf=0, doSpatialReuse=1, spatialReuseRadius=100.0, spatialReuseNeighborCount=8),
     dict(),  # reference defaults
+    # stream -> trace -> resolve split
+    dict(M_Area=8, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1, lightSampler=1, wavefront=1),
+    dict(M_Area=3, M_Brdf=2, doSpatialReuse=1, doTemporalReuse=1, spatialPassCount=2, wavefront=1),
+    dict(M_Area=2, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, spatialWeightCalc=4, doVisibilityPass=1, wavefront=1),
+    dict(M_Area=4, M_Brdf=0, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1, spatialReuseNeighborCount=8,
+         rejectDissimilarNeighbors=1, wavefront=1),
 ]
 
 ALL_BUFS = (abi.BUF_HIT_IDS, abi.BUF_GBUF_POS_DEPTH, abi.BUF_GBUF_NORMAL_SHIN, abi.BUF_GBUF_DIFFUSE_IIM,
