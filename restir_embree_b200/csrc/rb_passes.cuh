@@ -121,13 +121,16 @@ struct GenVis {
   }
 };
 // ResolveVis: the resolve half. The same queries, in the same order, read the traced results.
-struct ResolveVis {
+// INLINE_SHADOW: shadow rays are traced on the spot instead (initial pass with the visibility pass off, whose
+// 33 rays per pixel are not queued); closest-hit queries are always looked up.
+template <bool INLINE_SHADOW>
+struct ResolveVisT {
   static constexpr bool kStore = true;
   const FrameCtx* fc;
   uint32_t pixel;
   RB_HD bool visible(int slot, const V3& from, const V3& to) const {
     const WaveBufs& w = fc->wave;
-    if (w.occ == nullptr) return !test_occlusion(fc->sc, from, to, fc->P.tnearOffset, fc->P.tfarOffset);
+    if (INLINE_SHADOW) return !test_occlusion(fc->sc, from, to, fc->P.tnearOffset, fc->P.tfarOffset);
     return w.occ[(size_t)slot * w.npix + pixel] == 0;
   }
   RB_HD SurfaceHit closest(int slot, const V3& org, const V3& dir, float /*tnear*/, float /*tfar*/) const {
@@ -135,6 +138,8 @@ struct ResolveVis {
     return surface_from_hit(fc->sc, org, dir, w.hits[(size_t)slot * w.npix + pixel]);
   }
 };
+typedef ResolveVisT<false> ResolveVis;
+typedef ResolveVisT<true> ResolveInlineShadowVis;
 
 // ---- Phong / Lambert statics (P/MaterialPhong.cpp:122-248, P/MaterialLambert.cpp:33-53,
 //      P/Distribution.h) ------------------------------------------------------------

@@ -61,7 +61,8 @@ RB_PIXEL_KERNEL(k_spatial, InlineVis, true, 1, spatial_pixel(fc, x, y, vis, cnt)
 RB_PIXEL_KERNEL(k_shade, InlineVis, true, 1, shade_pixel(fc, x, y, vis, cnt))
 // wavefront halves
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
-RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 2, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_temporal_stream, GenVis, false, 1, temporal_pixel(fc, x, y, vis, cnt))
@@ -74,16 +75,17 @@ RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 1, spatial_pixel(fc, x, y, 
 // have terminated once fewer than kRefill lanes are still busy (dynamic fetch), so that long traversals do not
 // leave most of the warp idle. Grid = a multiple of the SM count, sized by the host.
 constexpr int kTraceThreads = 128;
-constexpr int kRefill = 22;
 
 template <bool ANY>
 __global__ void __launch_bounds__(kTraceThreads) k_trace_queue(SceneDev sc, const RayQ* __restrict__ rays,
                                                                const uint32_t* __restrict__ count_ptr, uint32_t capacity,
                                                                uint32_t* __restrict__ next, uint8_t* __restrict__ occ,
-                                                               HitRec* __restrict__ hits, float tnear) {
+                                                               HitRec* __restrict__ hits, float tnear, int refill_lanes,
+                                                               int postpone_lanes) {
   const uint32_t count = min(*count_ptr, capacity);
   const unsigned lane = threadIdx.x & 31u;
   Trav T;
+  U2 stack[RB_STACK_MAX];
   bool active = false;
   bool exhausted = false;  // warp-uniform
   uint32_t dest = 0;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_queue(SceneDev sc, cons
     // ---- traverse until too few lanes are busy ----------------------------------------------------
     while (true) {
       if (active) {
-        if (!trav_step<ANY>(T, sc)) {
+        if (!trav_step<ANY, true>(T, stack, sc, postpone_lanes)) {
           if (ANY)
             occ[dest] = T.hit_any ? 1 : 0;
           else
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_queue(SceneDev sc, cons
         }
       }
       const int busy = __popc(__ballot_sync(0xFFFFFFFFu, active));
-      if (busy == 0 || (busy < kRefill && !exhausted)) break;
+      if (busy == 0 || (busy < refill_lanes && !exhausted)) break;
     }
   }
 }
@@ -225,6 +227,8 @@ struct RbContext {
   cudaEvent_t fev[kMaxEvents]{};  // per-kernel frame events
   bool evCreated = false;
   int numSMs = 148;
+  // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
+  int refillLanes = 22, postponeLanes = 10, traceBlocksPerSM = 8;
 
   // wavefront buffers
   WaveBufs wave{};
@@ -350,6 +354,9 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     for (auto& ev : h->fev) RB_CUDA(cudaEventCreate(&ev));
     h->evCreated = true;
     RB_CUDA(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, info->device));
+    if (const char* e = getenv("RB_REFILL")) h->refillLanes = atoi(e);
+    if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
+    if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
     RB_TRY(dev_alloc(h, &d, 1, h->allocs));
@@ -513,7 +520,7 @@ static int build_bvh(RbContext* h, const float* d_tri_pos, uint32_t n, float max
       }
     }
     RB_CUDA(cudaGetLastError());
-    if (depth >= RB_STACK_MAX) {
+    if (2 * depth + 2 > RB_STACK_MAX) {
       h->err = "build_bvh: tree depth " + std::to_string(depth) + " exceeds the traversal stack";
       return RB_ERR_UNSUPPORTED;
     }
@@ -748,16 +755,16 @@ static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx
     fc.Rlast = h->R[h->rLast];
   };
   auto swap_rw = [&]() { std::swap(h->rRead, h->rWrite); };  // swapReservoirBuffers, P/simpleguidx11.h:116
-  const int trace_grid = h->numSMs * 8;
+  const int trace_grid = h->numSMs * h->traceBlocksPerSM;
   auto trace = [&](bool any, int pass) {
     if (any)
       k_trace_queue<true><<<trace_grid, kTraceThreads, 0, st>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
                                                                  h->wave.count + 1, h->wave.occ, h->wave.hits,
-                                                                 FLT_MIN + P.tnearOffset);
+                                                                 FLT_MIN + P.tnearOffset, h->refillLanes, h->postponeLanes);
     else
       k_trace_queue<false><<<trace_grid, kTraceThreads, 0, st>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
                                                                   h->wave.count + 1, h->wave.occ, h->wave.hits,
-                                                                  FLT_MIN + P.tnearOffset);
+                                                                  FLT_MIN + P.tnearOffset, h->refillLanes, h->postponeLanes);
     launches++;
     mark(pass, 1);
   };
@@ -785,9 +792,10 @@ static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx
       trace(false, 1);
     }
     // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel
-    FrameCtx f2 = fc;
-    f2.wave.occ = nullptr;
-    k_initial_resolve<<<grid, block, 0, st>>>(f2);
+    if (P.doVisibilityPass)
+      k_initial_resolve<<<grid, block, 0, st>>>(fc);
+    else
+      k_initial_resolve_inline_shadow<<<grid, block, 0, st>>>(fc);
   } else {
     k_initial<<<grid, block, 0, st>>>(fc);
   }

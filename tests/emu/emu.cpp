@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <functional>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -86,6 +88,93 @@ static int emu_build_bvh(Emu* E) {
     tiny_root_body(c);
     n_nodes = 1, depth = 1;
   } else {
+    if (getenv("EMU_SAH")) {
+      // EXPERIMENT (host only): binned-SAH binary tree instead of the Morton radix tree, to measure how much
+      // traversal work a better topology would save. Not part of the product build.
+      int next = 0;
+      struct Job {
+        int lo, hi, parent, is_right;
+      };
+      std::function<int(int, int, int)> build = [&](int lo, int hi, int par) -> int {
+        const int id = next++;
+        parent[id] = par;
+        rlo[id] = lo, rhi[id] = hi;
+        float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        auto cen = [&](int k, int a) {
+          const uint32_t t = order_sorted[k];
+          const float* L = &tlo[t].x;
+          const float* H = &thi[t].x;
+          return 0.5f * (L[a] + H[a]);
+        };
+        for (int k = lo; k <= hi; ++k)
+          for (int a = 0; a < 3; ++a) cmin[a] = std::min(cmin[a], cen(k, a)), cmax[a] = std::max(cmax[a], cen(k, a));
+        int mid = (lo + hi + 1) / 2;
+        int bestAxis = -1;
+        float bestCost = FLT_MAX;
+        int bestBin = 0;
+        const int NB = 16;
+        for (int a = 0; a < 3; ++a) {
+          if (!(cmax[a] > cmin[a])) continue;
+          F4 blo[NB], bhi[NB];
+          int cnt[NB];
+          for (int b = 0; b < NB; ++b) blo[b] = F4{FLT_MAX, FLT_MAX, FLT_MAX, 0}, bhi[b] = F4{-FLT_MAX, -FLT_MAX, -FLT_MAX, 0}, cnt[b] = 0;
+          const float sc = NB / (cmax[a] - cmin[a]);
+          for (int k = lo; k <= hi; ++k) {
+            int b = std::min(NB - 1, (int)((cen(k, a) - cmin[a]) * sc));
+            const uint32_t t = order_sorted[k];
+            blo[b] = F4{std::min(blo[b].x, tlo[t].x), std::min(blo[b].y, tlo[t].y), std::min(blo[b].z, tlo[t].z), 0};
+            bhi[b] = F4{std::max(bhi[b].x, thi[t].x), std::max(bhi[b].y, thi[t].y), std::max(bhi[b].z, thi[t].z), 0};
+            cnt[b]++;
+          }
+          float la[NB], ra[NB];
+          int lc[NB], rc[NB];
+          F4 l = blo[0], h = bhi[0];
+          int cc = 0;
+          for (int b = 0; b < NB; ++b) {
+            if (cnt[b]) l = F4{std::min(l.x, blo[b].x), std::min(l.y, blo[b].y), std::min(l.z, blo[b].z), 0}, h = F4{std::max(h.x, bhi[b].x), std::max(h.y, bhi[b].y), std::max(h.z, bhi[b].z), 0};
+            cc += cnt[b];
+            la[b] = cc ? box_area(l, h) : 0, lc[b] = cc;
+          }
+          l = F4{FLT_MAX, FLT_MAX, FLT_MAX, 0}, h = F4{-FLT_MAX, -FLT_MAX, -FLT_MAX, 0};
+          cc = 0;
+          for (int b = NB - 1; b >= 0; --b) {
+            if (cnt[b]) l = F4{std::min(l.x, blo[b].x), std::min(l.y, blo[b].y), std::min(l.z, blo[b].z), 0}, h = F4{std::max(h.x, bhi[b].x), std::max(h.y, bhi[b].y), std::max(h.z, bhi[b].z), 0};
+            cc += cnt[b];
+            ra[b] = cc ? box_area(l, h) : 0, rc[b] = cc;
+          }
+          for (int b = 0; b + 1 < NB; ++b) {
+            if (lc[b] == 0 || rc[b + 1] == 0) continue;
+            const float cost = la[b] * lc[b] + ra[b + 1] * rc[b + 1];
+            if (cost < bestCost) bestCost = cost, bestAxis = a, bestBin = b;
+          }
+        }
+        if (bestAxis >= 0) {
+          const int a = bestAxis;
+          const float sc = NB / (cmax[a] - cmin[a]);
+          auto it = std::partition(order_sorted.begin() + lo, order_sorted.begin() + hi + 1, [&](uint32_t t) {
+            const float* L = &tlo[t].x;
+            const float* H = &thi[t].x;
+            int b = std::min(NB - 1, (int)((0.5f * (L[a] + H[a]) - cmin[a]) * sc));
+            return b <= bestBin;
+          });
+          mid = (int)(it - order_sorted.begin());
+          if (mid <= lo || mid > hi) mid = (lo + hi + 1) / 2;
+        }
+        // children: [lo, mid-1], [mid, hi]
+        if (mid - 1 == lo) {
+          left[id] = ~lo;
+          leaf_parent[lo] = id;
+        } else
+          left[id] = build(lo, mid - 1, id);
+        if (mid == hi) {
+          right[id] = ~hi;
+          leaf_parent[hi] = id;
+        } else
+          right[id] = build(mid, hi, id);
+        return id;
+      };
+      build(0, (int)n - 1, -1);
+    } else
     // run the per-thread bodies in a scrambled order to mimic unordered GPU scheduling
     for (uint32_t i = 0; i + 1 < n; ++i) karras_body(c, n - 2 - i);
     for (uint32_t i = 0; i < n; ++i) fit_body(c, n - 1 - i);
@@ -108,7 +197,7 @@ static int emu_build_bvh(Emu* E) {
     }
     if ((uint32_t)counters[1] != n) return -2;
   }
-  if (depth >= RB_STACK_MAX) return -4;
+  if (2 * depth + 2 > RB_STACK_MAX) return -4;
   node8.resize(5 * (size_t)n_nodes);
   E->node8 = node8;
   E->n_nodes = n_nodes;
@@ -267,9 +356,10 @@ int emu_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rg
       stream([&](int x, int y, Cnt&) { initial_brdf_gen_pixel(fc, x, y, GenVis{&fc, px(x, y)}); });
       trace_queue(false);
     }
-    FrameCtx f2 = fc;
-    f2.wave.occ = nullptr;
-    for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(f2, x, y, ResolveVis{&f2, px(x, y)}, c); });
+    if (P.doVisibilityPass)
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveVis{&fc, px(x, y)}, c); });
+    else
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveInlineShadowVis{&fc, px(x, y)}, c); });
   } else {
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
   }
@@ -379,6 +469,31 @@ int emu_trace_occluded(void* h, const RbRay* rays, uint8_t* occ, uint32_t n) {
     occ[i] = trace8<true>(E->sc, v3(r.org_x, r.org_y, r.org_z), v3(r.dir_x, r.dir_y, r.dir_z), r.tnear, r.tfar, nullptr) ? 1 : 0;
   }
   return 0;
+}
+
+// traversal statistics for BVH-quality work: average node visits (trav_step calls) per ray
+double g_tri_tests = 0;
+double emu_last_tri_tests() { return g_tri_tests; }
+double emu_trace_steps(void* h, const RbRay* rays, uint32_t n, int any) {
+  Emu* E = (Emu*)h;
+  double steps = 0, tris = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : steps, tris)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {
+    const RbRay& r = rays[i];
+    Trav T;
+    U2 stack[RB_STACK_MAX];
+    if (!trav_init(T, E->sc, v3(r.org_x, r.org_y, r.org_z), v3(r.dir_x, r.dir_y, r.dir_z), r.tnear, r.tfar)) continue;
+    bool more = true;
+    while (more) {
+      more = any ? trav_step<true, false>(T, stack, E->sc) : trav_step<false, false>(T, stack, E->sc);
+      steps += 1;
+    }
+#ifdef RB_TRAV_STATS
+    tris += T.n_tri_tests;
+#endif
+  }
+  g_tri_tests = tris / (n ? n : 1);
+  return steps / (n ? n : 1);
 }
 
 // structural check of the wide BVH: every triangle reachable exactly once, every child box
