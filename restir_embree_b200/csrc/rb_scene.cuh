@@ -159,93 +159,89 @@ RB_HD bool trav_init(Trav& T, const SceneDev& sc, const V3& o, const V3& d, floa
     if (tmin <= tmax) hitmask |= byte_of(MB, (I)&3) << byte_of(MI, (I)&3);                        \
   }
 
-// One traversal step. The current group T.ngroup is either a node group {child_base, hit bits << 24 | imask} —
-// then the nearest pending child is visited: its eight child boxes are tested, giving a new node group and a
-// triangle group {tri_base, triangle hit bits} — or a postponed triangle group. Triangle groups are tested one
-// triangle at a time; with POSTPONE (device only) a lane that still has node work pushes its triangle group onto
-// the stack instead of testing it while fewer than postpone_lanes lanes of the warp have triangles to test, so that
-// the triangle code runs with well-filled warps (postponed-triangle scheme of the compressed wide BVH paper).
-// ANY: stop at the first hit (rtcOccluded1); otherwise keep the closest hit, ties by smaller scene-order index.
-// Returns false when the ray is finished. The result does not depend on the order in which groups are processed.
-template <bool ANY, bool POSTPONE>
-RB_HD bool trav_step(Trav& T, U2* stack, const SceneDev& sc, int postpone_lanes = 0) {
-  U2 tgroup;
-  if (T.ngroup.y > 0x00FFFFFFu) {
-    const uint32_t hits = T.ngroup.y;
-    const int bit = bfind(hits);
-    T.ngroup.y &= ~(1u << bit);
-    if (T.ngroup.y > 0x00FFFFFFu) stack[T.sp++] = T.ngroup;
-    const uint32_t slot = ((uint32_t)(bit - 24)) ^ T.oct_inv;
-    const uint32_t node_index = T.ngroup.x + popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
+// ---- traversal primitives ---------------------------------------------------------------------------
+// A node group is {child_base, hit bits << 24 | imask}; a triangle group is {tri_base, triangle hit bits}.
+// The result of a traversal does not depend on the order in which groups are processed (any-hit: some hit
+// exists; closest: minimum with an index tie-break), which is what lets the device kernel reschedule them.
+RB_HD bool has_node_work(const Trav& T) { return T.ngroup.y > 0x00FFFFFFu; }
 
-    const F4* np = sc.node8 + 5 * (size_t)node_index;
-    const F4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4);
-    const uint32_t ebits = f2u(n0.w);
-    const uint32_t imask = ebits >> 24;
-    const float ax = u2f(byte_of(ebits, 0) << 23) * T.idx, ay = u2f(byte_of(ebits, 1) << 23) * T.idy,
-                az = u2f(byte_of(ebits, 2) << 23) * T.idz;
-    const float bx = (n0.x - T.o.x) * T.idx, by = (n0.y - T.o.y) * T.idy, bz = (n0.z - T.o.z) * T.idz;
-    const float tcull = ANY ? T.tfar : T.best.t * 1.000001f;
-    // near / far plane words per axis, chosen once per node by the ray direction sign
-    const bool nx = T.dx < 0, ny = T.dy < 0, nz = T.dz < 0;
-    const uint32_t x0a = f2u(nx ? n3.z : n2.x), x0b = f2u(nx ? n3.w : n2.y), x1a = f2u(nx ? n2.x : n3.z), x1b = f2u(nx ? n2.y : n3.w);
-    const uint32_t y0a = f2u(ny ? n4.x : n2.z), y0b = f2u(ny ? n4.y : n2.w), y1a = f2u(ny ? n2.z : n4.x), y1b = f2u(ny ? n2.w : n4.y);
-    const uint32_t z0a = f2u(nz ? n4.z : n3.x), z0b = f2u(nz ? n4.w : n3.y), z1a = f2u(nz ? n3.x : n4.z), z1b = f2u(nz ? n3.y : n4.w);
-    // per-child hit-mask contribution: (meta >> 5) << ((meta & 31) ^ (internal ? oct_inv : 0)), 4 children per word
-    const uint32_t meta_a = f2u(n1.z), meta_b = f2u(n1.w);
-    const uint32_t oct4 = T.oct_inv * 0x01010101u;
-    const uint32_t mia = (meta_a ^ (oct4 & expand_nibble(imask))) & 0x1F1F1F1Fu;
-    const uint32_t mib = (meta_b ^ (oct4 & expand_nibble(imask >> 4))) & 0x1F1F1F1Fu;
-    const uint32_t mba = (meta_a >> 5) & 0x07070707u, mbb = (meta_b >> 5) & 0x07070707u;
-    uint32_t hitmask = 0;
-    RB_CHILD_TEST(0, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
-    RB_CHILD_TEST(1, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
-    RB_CHILD_TEST(2, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
-    RB_CHILD_TEST(3, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
-    RB_CHILD_TEST(4, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
-    RB_CHILD_TEST(5, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
-    RB_CHILD_TEST(6, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
-    RB_CHILD_TEST(7, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
-    T.ngroup.x = f2u(n1.x);
-    T.ngroup.y = (hitmask & 0xFF000000u) | imask;
-    tgroup.x = f2u(n1.y);
-    tgroup.y = hitmask & 0x00FFFFFFu;
-  } else {
-    tgroup = T.ngroup;  // a postponed triangle group
-    T.ngroup = U2{0u, 0u};
-  }
+// Visit the nearest pending child of the current node group: test its eight child boxes. Leaves the hit
+// internal children in T.ngroup (pushing the remainder of the old group), returns the hit leaf triangles.
+template <bool ANY>
+RB_HD U2 trav_node_step(Trav& T, U2* stack, const SceneDev& sc) {
+  const uint32_t hits = T.ngroup.y;
+  const int bit = bfind(hits);
+  T.ngroup.y &= ~(1u << bit);
+  if (T.ngroup.y > 0x00FFFFFFu) stack[T.sp++] = T.ngroup;
+  const uint32_t slot = ((uint32_t)(bit - 24)) ^ T.oct_inv;
+  const uint32_t node_index = T.ngroup.x + popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
 
-  while (tgroup.y != 0) {
-#if defined(__CUDA_ARCH__)
-    if (POSTPONE) {
-      const unsigned here = __activemask();
-      if (T.ngroup.y > 0x00FFFFFFu && __popc(here) < postpone_lanes) {
-        stack[T.sp++] = tgroup;
-        break;
-      }
-    }
-#endif
-    const int ti = bfind(tgroup.y);
-    tgroup.y &= ~(1u << ti);
-    const F4* tp = sc.tri_isect + 3 * (size_t)(tgroup.x + (uint32_t)ti);
-    const F4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
-    float t, u, v;
+  const F4* np = sc.node8 + 5 * (size_t)node_index;
+  const F4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4);
+  const uint32_t ebits = f2u(n0.w);
+  const uint32_t imask = ebits >> 24;
+  const float ax = u2f(byte_of(ebits, 0) << 23) * T.idx, ay = u2f(byte_of(ebits, 1) << 23) * T.idy,
+              az = u2f(byte_of(ebits, 2) << 23) * T.idz;
+  const float bx = (n0.x - T.o.x) * T.idx, by = (n0.y - T.o.y) * T.idy, bz = (n0.z - T.o.z) * T.idz;
+  const float tcull = ANY ? T.tfar : T.best.t * 1.000001f;
+  // near / far plane words per axis, chosen once per node by the ray direction sign
+  const bool nx = T.dx < 0, ny = T.dy < 0, nz = T.dz < 0;
+  const uint32_t x0a = f2u(nx ? n3.z : n2.x), x0b = f2u(nx ? n3.w : n2.y), x1a = f2u(nx ? n2.x : n3.z), x1b = f2u(nx ? n2.y : n3.w);
+  const uint32_t y0a = f2u(ny ? n4.x : n2.z), y0b = f2u(ny ? n4.y : n2.w), y1a = f2u(ny ? n2.z : n4.x), y1b = f2u(ny ? n2.w : n4.y);
+  const uint32_t z0a = f2u(nz ? n4.z : n3.x), z0b = f2u(nz ? n4.w : n3.y), z1a = f2u(nz ? n3.x : n4.z), z1b = f2u(nz ? n3.y : n4.w);
+  // per-child hit-mask contribution: (meta >> 5) << ((meta & 31) ^ (internal ? oct_inv : 0)), 4 children per word
+  const uint32_t meta_a = f2u(n1.z), meta_b = f2u(n1.w);
+  const uint32_t oct4 = T.oct_inv * 0x01010101u;
+  const uint32_t mia = (meta_a ^ (oct4 & expand_nibble(imask))) & 0x1F1F1F1Fu;
+  const uint32_t mib = (meta_b ^ (oct4 & expand_nibble(imask >> 4))) & 0x1F1F1F1Fu;
+  const uint32_t mba = (meta_a >> 5) & 0x07070707u, mbb = (meta_b >> 5) & 0x07070707u;
+  uint32_t hitmask = 0;
+  RB_CHILD_TEST(0, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
+  RB_CHILD_TEST(1, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
+  RB_CHILD_TEST(2, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
+  RB_CHILD_TEST(3, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
+  RB_CHILD_TEST(4, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
+  RB_CHILD_TEST(5, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
+  RB_CHILD_TEST(6, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
+  RB_CHILD_TEST(7, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
+  T.ngroup.x = f2u(n1.x);
+  T.ngroup.y = (hitmask & 0xFF000000u) | imask;
+  return U2{f2u(n1.y), hitmask & 0x00FFFFFFu};
+}
+
+// Test ONE triangle of a triangle group (clears its bit). Returns true when the ray is finished by it (ANY hit).
+template <bool ANY>
+RB_HD bool trav_tri_one(Trav& T, U2& tgroup, const SceneDev& sc) {
+  const int ti = bfind(tgroup.y);
+  tgroup.y &= ~(1u << ti);
+  const F4* tp = sc.tri_isect + 3 * (size_t)(tgroup.x + (uint32_t)ti);
+  const F4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+  float t, u, v;
 #ifdef RB_TRAV_STATS
-    T.n_tri_tests++;
+  T.n_tri_tests++;
 #endif
-    if (tri_test(T.o, T.d, a, b, c, T.tnear, T.tfar, &t, &u, &v)) {
-      const uint32_t id = f2u(c.y);
-      if (ANY) {
-        T.best.t = t, T.best.u = u, T.best.v = v, T.best.tri = id;
-        T.hit_any = true;
-        return false;
-      }
-      if (T.best.tri == 0xFFFFFFFFu || t < T.best.t || (t == T.best.t && id < T.best.tri)) {
-        T.best.t = t, T.best.u = u, T.best.v = v, T.best.tri = id;
-      }
+  if (tri_test(T.o, T.d, a, b, c, T.tnear, T.tfar, &t, &u, &v)) {
+    const uint32_t id = f2u(c.y);
+    if (ANY) {
+      T.best.t = t, T.best.u = u, T.best.v = v, T.best.tri = id;
+      T.hit_any = true;
+      return true;
+    }
+    if (T.best.tri == 0xFFFFFFFFu || t < T.best.t || (t == T.best.t && id < T.best.tri)) {
+      T.best.t = t, T.best.u = u, T.best.v = v, T.best.tri = id;
     }
   }
-  if (T.ngroup.y <= 0x00FFFFFFu) {
+  return false;
+}
+
+// Sequential step (one ray per thread, no rescheduling): node visit, then its triangles, then the next group.
+// Returns false when the ray is finished.
+template <bool ANY>
+RB_HD bool trav_step(Trav& T, U2* stack, const SceneDev& sc) {
+  U2 tgroup = trav_node_step<ANY>(T, stack, sc);
+  while (tgroup.y != 0)
+    if (trav_tri_one<ANY>(T, tgroup, sc)) return false;
+  if (!has_node_work(T)) {
     if (T.sp == 0) return false;
     T.ngroup = stack[--T.sp];
   }
@@ -258,7 +254,7 @@ RB_HD bool trace8(const SceneDev& sc, const V3& o, const V3& d, float tnear, flo
   Trav T;
   U2 stack[RB_STACK_MAX];
   if (trav_init(T, sc, o, d, tnear, tfar)) {
-    while (trav_step<ANY, false>(T, stack, sc)) {
+    while (trav_step<ANY>(T, stack, sc)) {
     }
   }
   if (out) *out = T.best;

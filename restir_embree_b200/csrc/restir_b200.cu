@@ -71,9 +71,16 @@ RB_PIXEL_KERNEL(k_spatial_stream, GenVis, false, 1, spatial_pixel(fc, x, y, vis,
 RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
 
 // ---- persistent traversal kernels over the ray queue ------------------------------------------------
-// One ray per lane; warps pull rays from the queue with one aggregated atomic and refill the lanes whose rays
-// have terminated once fewer than kRefill lanes are still busy (dynamic fetch), so that long traversals do not
-// leave most of the warp idle. Grid = a multiple of the SM count, sized by the host.
+// One ray per lane. Three things keep the warps full in this divergent workload:
+//   * dynamic fetch: warps pull rays from the queue with one aggregated atomic and refill the lanes whose rays
+//     have terminated as soon as fewer than refill_lanes lanes are busy;
+//   * phase scheduling: every iteration runs a NODE phase (all lanes with a pending node group test eight child
+//     boxes in lockstep) and, only when at least tri_lanes lanes hold pending leaf triangles (or node work is
+//     running out), a TRIANGLE phase in which each of those lanes tests one triangle. Leaf hits wait in a
+//     per-lane triangle stack (the top end of the traversal stack) until then. Traversal results do not depend on
+//     the processing order, so this is invisible to parity;
+//   * a short per-lane stack in local memory (L1-resident), ray state in registers.
+// Grid = SM count x resident blocks, sized by the host.
 constexpr int kTraceThreads = 128;
 
 template <bool ANY>
@@ -81,21 +88,24 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_queue(SceneDev sc, cons
                                                                const uint32_t* __restrict__ count_ptr, uint32_t capacity,
                                                                uint32_t* __restrict__ next, uint8_t* __restrict__ occ,
                                                                HitRec* __restrict__ hits, float tnear, int refill_lanes,
-                                                               int postpone_lanes) {
+                                                               int tri_lanes) {
   const uint32_t count = min(*count_ptr, capacity);
   const unsigned lane = threadIdx.x & 31u;
+  const unsigned FULL = 0xFFFFFFFFu;
   Trav T;
-  U2 stack[RB_STACK_MAX];
+  U2 stack[RB_STACK_MAX];  // node groups grow up from 0 (T.sp), pending triangle groups grow down from the top (tsp)
+  int tsp = RB_STACK_MAX;
+  U2 tg = U2{0u, 0u};  // triangle group currently being consumed
   bool active = false;
   bool exhausted = false;  // warp-uniform
   uint32_t dest = 0;
   while (true) {
     // ---- refill idle lanes ---------------------------------------------------------------------
-    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+    const unsigned idle = __ballot_sync(FULL, !active);
     if (!exhausted && idle != 0) {
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(next, (uint32_t)__popc(idle));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      base = __shfl_sync(FULL, base, 0);
       if (base + __popc(idle) >= count) exhausted = true;
       if (!active) {
         const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
@@ -104,6 +114,8 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_queue(SceneDev sc, cons
           const float4 b = __ldg(reinterpret_cast<const float4*>(&rays[i].d_dest));
           dest = __float_as_uint(b.w);
           active = trav_init(T, sc, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), tnear, a.w);
+          tsp = RB_STACK_MAX;
+          tg = U2{0u, 0u};
           if (!active) {  // cannot hit anything
             if (ANY)
               occ[dest] = 0;
@@ -113,22 +125,44 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_queue(SceneDev sc, cons
         }
       }
     }
-    if (__ballot_sync(0xFFFFFFFFu, active) == 0) {
+    if (__ballot_sync(FULL, active) == 0) {
       if (exhausted) break;
       continue;
     }
-    // ---- traverse until too few lanes are busy ----------------------------------------------------
     while (true) {
-      if (active) {
-        if (!trav_step<ANY, true>(T, stack, sc, postpone_lanes)) {
-          if (ANY)
-            occ[dest] = T.hit_any ? 1 : 0;
-          else
-            hits[dest] = T.best;
-          active = false;
+      bool done = false;
+      // ---- NODE phase ------------------------------------------------------------------------------
+      if (active && has_node_work(T)) {
+        U2 g = trav_node_step<ANY>(T, stack, sc);
+        if (g.y != 0) {
+          if (tg.y == 0)
+            tg = g;
+          else if (tsp - T.sp > 2)
+            stack[--tsp] = g;
+          else  // stack almost full: drain this group right away
+            while (g.y != 0 && !done) done = trav_tri_one<ANY>(T, g, sc);
+        }
+        if (!has_node_work(T) && T.sp > 0) T.ngroup = stack[--T.sp];
+      }
+      // ---- TRIANGLE phase, when it is worth a warp-wide pass ---------------------------------------------
+      const bool has_tri = active && !done && tg.y != 0;
+      const int n_tri = __popc(__ballot_sync(FULL, has_tri));
+      const int n_node = __popc(__ballot_sync(FULL, active && !done && has_node_work(T)));
+      if (n_tri != 0 && (n_tri >= tri_lanes || n_node < tri_lanes)) {
+        if (has_tri) {
+          done = trav_tri_one<ANY>(T, tg, sc);
+          if (!done && tg.y == 0 && tsp < RB_STACK_MAX) tg = stack[tsp++];
         }
       }
-      const int busy = __popc(__ballot_sync(0xFFFFFFFFu, active));
+      // ---- finished rays ------------------------------------------------------------------------------------
+      if (active && (done || (!has_node_work(T) && tg.y == 0))) {
+        if (ANY)
+          occ[dest] = T.hit_any ? 1 : 0;
+        else
+          hits[dest] = T.best;
+        active = false;
+      }
+      const int busy = __popc(__ballot_sync(FULL, active));
       if (busy == 0 || (busy < refill_lanes && !exhausted)) break;
     }
   }
@@ -228,7 +262,7 @@ struct RbContext {
   bool evCreated = false;
   int numSMs = 148;
   // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
-  int refillLanes = 22, postponeLanes = 10, traceBlocksPerSM = 8;
+  int refillLanes = 26, postponeLanes = 8, traceBlocksPerSM = 8;
 
   // wavefront buffers
   WaveBufs wave{};

@@ -485,7 +485,7 @@ double emu_trace_steps(void* h, const RbRay* rays, uint32_t n, int any) {
     if (!trav_init(T, E->sc, v3(r.org_x, r.org_y, r.org_z), v3(r.dir_x, r.dir_y, r.dir_z), r.tnear, r.tfar)) continue;
     bool more = true;
     while (more) {
-      more = any ? trav_step<true, false>(T, stack, E->sc) : trav_step<false, false>(T, stack, E->sc);
+      more = any ? trav_step<true>(T, stack, E->sc) : trav_step<false>(T, stack, E->sc);
       steps += 1;
     }
 #ifdef RB_TRAV_STATS
