@@ -156,12 +156,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
 
     scene = scenes.scene_config("1m")
-    rows = (HEIGHT + world - 1) // world
-    band = (rank * rows, min(HEIGHT, (rank + 1) * rows))
+    from restir_embree_b200.renderer import band_rows
+    band = band_rows(HEIGHT, world, rank)
     r = Renderer(WIDTH, HEIGHT, device=local, seed=123, band=band, collect_timings=True)
     stats = r.upload_scene(scene)
     p = bench_params()
     r.set_params(p)
+    if world > 1:
+        # band halo exchange runs inside rb_render_frame over NCCL: share rank 0's ncclUniqueId
+        from restir_embree_b200.renderer import comm_unique_id
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        r.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
     pinned = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32, pin_memory=True)
     out = pinned.numpy()
 

@@ -266,16 +266,33 @@ typedef struct RbSceneStats {
 } RbSceneStats;
 int rb_scene_stats(RbHandle h, RbSceneStats* out);
 
-/* Multi-GPU bands: NCCL communicator over the handles of all
- * ranks; nccl_unique_id is the 128-byte ncclUniqueId created by rank 0 and
- * distributed by the launcher (torch.distributed / MPI / files). After this,
- * rb_render_frame exchanges reservoir halo rows with rank±1 each frame. */
+/* ---- Multi-GPU bands -----------------------------------------------------------------
+ * One handle per GPU renders the image rows [band_y0, band_y1); scene and BVH are replicated. The only
+ * cross-band data are the reservoir rows within the spatial-reuse reach of a band edge ("halo rows"), which are
+ * exchanged before every spatial pass. G-buffer elements of other bands that temporal reprojection may touch
+ * are re-derived locally (they are a pure function of camera, pixel and scene), so temporal reuse needs no
+ * communication. The counter RNG is keyed on the global pixel index: the image is bit-identical for any
+ * number of bands.
+ *
+ * rb_comm_init attaches an NCCL communicator over the handles of all ranks (rank r owns band r; bands ordered
+ * top to bottom); afterwards rb_render_frame performs the halo exchange itself with grouped ncclSend/ncclRecv
+ * on a side stream, overlapped with the spatial pass over the interior rows. nccl_unique_id is the 128-byte
+ * ncclUniqueId made by rb_comm_unique_id on rank 0 and distributed by the launcher (torch.distributed, MPI,
+ * a file). NCCL is loaded with dlopen at that point; single-GPU use needs no NCCL at all. */
+int rb_comm_unique_id(void* out_id, size_t id_bytes);
 int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes);
-int rb_comm_unique_id(void* out_id, size_t id_bytes); /* rank 0: ncclGetUniqueId */
 
-/* Transport-agnostic halo access used by single-process band emulation and tests:
- * copies `rows` image rows starting at global row y of the current reservoir
- * read buffer (4 planes, 52 B/px) to/from a packed device or host buffer. */
+/* The same frame in phases, for hosts that move the halo rows themselves (another transport, or several
+ * bands in one process):  rb_frame_begin  (G-buffer, initial candidates, visibility, temporal)
+ *                         { exchange halos; rb_frame_spatial(i) }  for each spatial pass
+ *                         rb_frame_end    (shade, buffer rotation; frame_rgb_out host pointer or NULL).
+ * Between phases rb_halo_export / rb_halo_import copy `rows` image rows starting at global row y of the
+ * reservoirs the next spatial pass will read (4 planes packed back to back: 16+16+16+4 bytes per pixel) to /
+ * from host memory. rb_halo_rows gives the reach in rows for the current parameters. */
+int rb_frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx);
+int rb_frame_spatial(RbHandle h, int32_t pass_index);
+int rb_frame_end(RbHandle h, float* frame_rgb_out, RbTimings* timings);
+int32_t rb_halo_rows(RbHandle h);
 size_t rb_halo_bytes(RbHandle h, int32_t rows);
 int rb_halo_export(RbHandle h, int32_t y, int32_t rows, void* dst_host);
 int rb_halo_import(RbHandle h, int32_t y, int32_t rows, const void* src_host);

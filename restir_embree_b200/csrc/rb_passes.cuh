@@ -47,6 +47,9 @@ struct FrameCtx {
   float* frame;  // w*h*3
   uint32_t frame_key;
   int spatial_iter;
+  // image rows for which this handle holds the G-buffer of the current / previous frame (its band plus a margin);
+  // elements outside are re-derived on demand (they are a pure function of camera, pixel and scene)
+  int gy0, gy1, gpy0, gpy1;
   unsigned long long* counters;  // [0] closest, [1] any-hit as written, [2] any-hit traced
   WaveBufs wave;
 };
@@ -399,6 +402,38 @@ RB_HD GElem gbuffer_element(const FrameCtx& fc, const CamState& cam, int x, int 
   if (h.didHit && !e.isEmissive && uses_phong_brdf(e.matType)) e.invIM = inv_I_M(e.pos, e.normal, e.shininess, cam.pos);
   return e;
 }
+// G-buffer access for pixels that may lie outside this handle's rows (multi-GPU bands, SURVEY §8e "local
+// re-trace"): the element is recomputed from that frame's camera, bit-identical to what its owner stored.
+// (the slow paths are kept out of line so that they do not inflate the register budget of the callers)
+RB_HD_NOINLINE void retrace_gelem(const FrameCtx& fc, bool prev, int x, int y, GElem* out, uint32_t* n_closest) {
+  uint32_t g, p;
+  Cnt c = {0, 0, 0};
+  *out = gbuffer_element(fc, prev ? fc.prevCam : fc.cam, x, y, &g, &p, c);
+  *n_closest += c.closest;
+}
+RB_HD_NOINLINE void retrace_gpos(const FrameCtx& fc, bool prev, int x, int y, V3* out, uint32_t* n_closest) {
+  const CamState& cam = prev ? fc.prevCam : fc.cam;
+  V3 dir;
+  primary_ray(cam, fc.width, fc.height, x, y, &dir);
+  *n_closest += 1;
+  HitRec r;
+  *out = trace8<false>(fc.sc, cam.pos, dir, FLT_MIN + 0.01f, FLT_MAX, &r) ? cam.pos + dir * r.t : v3(0);
+}
+RB_HD GElem fetch_gelem(const FrameCtx& fc, bool prev, int x, int y, Cnt& cnt) {
+  const int r0 = prev ? fc.gpy0 : fc.gy0, r1 = prev ? fc.gpy1 : fc.gy1;
+  if (y >= r0 && y < r1) return load_gelem(prev ? fc.Gprev : fc.G, (size_t)y * fc.width + x);
+  GElem e;
+  retrace_gelem(fc, prev, x, y, &e, &cnt.closest);
+  return e;
+}
+RB_HD V3 fetch_gpos(const FrameCtx& fc, bool prev, int x, int y, Cnt& cnt) {
+  const int r0 = prev ? fc.gpy0 : fc.gy0, r1 = prev ? fc.gpy1 : fc.gy1;
+  if (y >= r0 && y < r1) return xyz(ld4((prev ? fc.Gprev : fc.G).pos_depth + (size_t)y * fc.width + x));
+  V3 p;
+  retrace_gpos(fc, prev, x, y, &p, &cnt.closest);
+  return p;
+}
+
 RB_HD void gbuffer_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
   uint32_t g, p;
   const GElem e = gbuffer_element(fc, fc.cam, x, y, &g, &p, cnt);
@@ -602,7 +637,7 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
     if (Vis::kStore) store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
-  const GElem prevElem = load_gelem(fc.Gprev, (size_t)py * fc.width + px);
+  const GElem prevElem = fetch_gelem(fc, true, px, py, cnt);
   const V3 curCam = fc.cam.pos, prevCam = fc.prevCam.pos;
   const float currentDepth = length(curElem.pos - curCam);
   const float prevDepth = length(prevElem.pos - prevCam);
@@ -617,7 +652,7 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
     if (Vis::kStore) store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
-  const V3 fwPos = xyz(ld4(fc.G.pos_depth + (size_t)fy * fc.width + fx));
+  const V3 fwPos = fetch_gpos(fc, false, fx, fy, cnt);
   const float currentDepthP = length(prevPosAtCurrent - prevCam);
   const float prevDepthP = length(fwPos - curCam);
   const float depthRatioP = currentDepthP > prevDepthP ? prevDepthP / currentDepthP : currentDepthP / prevDepthP;

@@ -233,6 +233,17 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+struct FrameMark {
+  int pass, kind;  // kind 0 = streaming kernel, 1 = traversal kernel
+};
+struct FrameState {
+  FrameCtx fc{};
+  RbParams P{};
+  bool open = false, timed = false, wave = false, wave_spatial = false;
+  uint32_t launches = 0, frame_idx = 0;
+  std::vector<FrameMark> marks;
+};
+
 struct RbContext {
   RbCreateInfo info{};
   RbParams params{};
@@ -249,6 +260,14 @@ struct RbContext {
   unsigned long long* counters = nullptr;
   CamState prevCam{};
   bool havePrev = false;
+  int prevGy0 = 0, prevGy1 = 0;  // G-buffer rows held for the previous frame
+  FrameState fs;
+
+  // multi-GPU bands: NCCL communicator (loaded with dlopen, see rb_comm_init), comm stream and events
+  void* comm = nullptr;
+  int commRank = 0, commSize = 1;
+  cudaStream_t commStream = nullptr;
+  cudaEvent_t evHaloReady = nullptr, evHaloDone = nullptr;
 
   // scene
   bool haveScene = false;
@@ -299,6 +318,101 @@ static void free_list(std::vector<void*>& l) {
   for (void* p : l) cudaFree(p);
   l.clear();
 }
+
+static int spatial_reach(const RbParams& P) { return (int)sqrtf(std::max(P.spatialReuseRadius, 0.0f)) + 1; }
+
+// ---- NCCL, loaded at run time so that the library has no link-time dependency on it ------------------------
+#include <dlfcn.h>
+namespace {
+struct NcclId128 {
+  char b[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId128 /*ncclUniqueId by value*/, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool load_nccl(std::string& err) {
+  if (g_nccl.lib) return true;
+  // torch's bundled libnccl.so.2 is reused when it is already in the process; otherwise the system one
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) {
+    err = std::string("rb_comm: cannot load libnccl: ") + dlerror();
+    return false;
+  }
+  auto sym = [&](const char* n) { return dlsym(lib, n); };
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+  g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
+  g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+    err = "rb_comm: libnccl lacks a required symbol";
+    return false;
+  }
+  g_nccl.lib = lib;
+  return true;
+}
+}  // namespace
+
+#define RB_NCCL(call)                                                                                   \
+  do {                                                                                                  \
+    int r__ = (call);                                                                                   \
+    if (r__ != 0) {                                                                                     \
+      h->err = std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?");  \
+      return RB_ERR_COMM;                                                                               \
+    }                                                                                                   \
+  } while (0)
+
+// Exchange the halo rows of R[rWrite] with rank-1 / rank+1: one grouped send/recv pair per neighbour and plane
+// (rows of a plane are contiguous and live at the same offsets on every rank). Runs on the comm stream after the
+// producing kernels; frame_spatial streams the interior rows meanwhile.
+static int halo_exchange_begin(RbContext* h) {
+  if (!h->comm) return RB_OK;
+  const int y0 = h->info.band_y0, y1 = h->info.band_y1, W = h->info.width, H = h->info.height;
+  const int R = spatial_reach(h->fs.P);
+  const ResPlanes& P = h->R[h->rWrite];
+  RB_CUDA(cudaEventRecord(h->evHaloReady, h->stream));
+  RB_CUDA(cudaStreamWaitEvent(h->commStream, h->evHaloReady, 0));
+  char* planes[4] = {(char*)P.point_wsum, (char*)P.normal_W, (char*)P.Li_conf, (char*)P.light_idx};
+  const size_t esz[4] = {16, 16, 16, 4};
+  RB_NCCL(g_nccl.GroupStart());
+  for (int i = 0; i < 4; ++i) {
+    if (h->commRank > 0) {  // neighbour above owns rows < y0
+      const int r = std::min(R, y1 - y0), ru = std::min(R, y0);
+      RB_NCCL(g_nccl.Send(planes[i] + (size_t)y0 * W * esz[i], (size_t)r * W * esz[i], /*ncclChar*/ 0, h->commRank - 1, h->comm,
+                          h->commStream));
+      RB_NCCL(g_nccl.Recv(planes[i] + (size_t)(y0 - ru) * W * esz[i], (size_t)ru * W * esz[i], 0, h->commRank - 1, h->comm,
+                          h->commStream));
+    }
+    if (h->commRank + 1 < h->commSize) {  // neighbour below owns rows >= y1
+      const int r = std::min(R, y1 - y0), rd = std::min(R, H - y1);
+      RB_NCCL(g_nccl.Send(planes[i] + (size_t)(y1 - r) * W * esz[i], (size_t)r * W * esz[i], 0, h->commRank + 1, h->comm,
+                          h->commStream));
+      RB_NCCL(g_nccl.Recv(planes[i] + (size_t)y1 * W * esz[i], (size_t)rd * W * esz[i], 0, h->commRank + 1, h->comm, h->commStream));
+    }
+  }
+  RB_NCCL(g_nccl.GroupEnd());
+  RB_CUDA(cudaEventRecord(h->evHaloDone, h->commStream));
+  return RB_OK;
+}
+static int halo_exchange_wait(RbContext* h) {
+  if (!h->comm) return RB_OK;
+  RB_CUDA(cudaStreamWaitEvent(h->stream, h->evHaloDone, 0));
+  return RB_OK;
+}
+
 
 extern "C" {
 
@@ -425,6 +539,10 @@ void rb_destroy(RbHandle h) {
   if (h->wave.occ) cudaFree(h->wave.occ);
   if (h->wave.hits) cudaFree(h->wave.hits);
   if (h->wave.count) cudaFree(h->wave.count);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->commStream) cudaStreamDestroy(h->commStream);
+  if (h->evHaloReady) cudaEventDestroy(h->evHaloReady);
+  if (h->evHaloDone) cudaEventDestroy(h->evHaloDone);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -735,30 +853,94 @@ static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots) {
   return RB_OK;
 }
 
-static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx, RbTimings* timings) {
+}  // extern "C"
+
+// ---- frame phases -----------------------------------------------------------------------------------
+// A frame is: begin (G-buffer, initial candidates, visibility, temporal) -> spatial pass x N -> end (shade,
+// buffer rotation). Between phases the reservoirs every later pass reads sit in R[rWrite]; that is where
+// band halos are exchanged (NCCL inside rb_render_frame, or rb_halo_export/import by a host that drives the
+// phases itself).
+
+static void fs_mark(RbContext* h, int pass, int kind) {
+  FrameState& F = h->fs;
+  if (!F.timed || (int)F.marks.size() + 1 >= RbContext::kMaxEvents) return;
+  cudaEventRecord(h->fev[F.marks.size() + 1], h->stream);
+  F.marks.push_back({pass, kind});
+}
+static void fs_bind(RbContext* h) {
+  FrameCtx& fc = h->fs.fc;
+  fc.Rread = h->R[h->rRead];
+  fc.Rwrite = h->R[h->rWrite];
+  fc.Rlast = h->R[h->rLast];
+}
+static dim3 rows_grid(const FrameCtx& fc, int ry0, int ry1) {
+  return dim3((fc.width + kTileW - 1) / kTileW, (std::max(ry1 - ry0, 0) + kTileH - 1) / kTileH);
+}
+// launch a pixel kernel over image rows [ry0, ry1)
+template <class K>
+static void launch_rows(RbContext* h, K kernel, int ry0, int ry1) {
+  if (ry1 <= ry0) return;
+  FrameCtx f = h->fs.fc;
+  f.y0 = ry0;
+  f.y1 = ry1;
+  kernel<<<rows_grid(f, ry0, ry1), dim3(kTileW, kTileH), 0, h->stream>>>(f);
+  h->fs.launches++;
+}
+static void fs_trace(RbContext* h, bool any, int pass) {
+  const RbParams& P = h->fs.P;
+  const int trace_grid = h->numSMs * h->traceBlocksPerSM;
+  if (any)
+    k_trace_queue<true><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
+                                                                      h->wave.count + 1, h->wave.occ, h->wave.hits,
+                                                                      FLT_MIN + P.tnearOffset, h->refillLanes, h->postponeLanes);
+  else
+    k_trace_queue<false><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
+                                                                       h->wave.count + 1, h->wave.occ, h->wave.hits,
+                                                                       FLT_MIN + P.tnearOffset, h->refillLanes, h->postponeLanes);
+  h->fs.launches++;
+  fs_mark(h, pass, 1);
+}
+static void fs_reset_queue(RbContext* h) {
+  k_reset_queue<<<1, 1, 0, h->stream>>>(h->wave.count, h->wave.count + 1);
+  h->fs.launches++;
+}
+
+static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool timed) {
   if (!h || !cam) return RB_ERR_INVALID_ARGUMENT;
   if (!h->haveScene) {
     h->err = "rb_render_frame: no scene uploaded";
     return RB_ERR_NO_SCENE;
   }
   RB_CUDA(cudaSetDevice(h->info.device));
-  const RbParams P = h->params;  // snapshot (the GUI thread may edit the host copy)
-  const bool timed = h->info.collect_timings != 0 && timings != nullptr;
-  cudaStream_t st = h->stream;
+  FrameState& F = h->fs;
+  F.P = h->params;  // snapshot (the GUI thread may edit the host copy)
+  const RbParams& P = F.P;
+  const int y0 = h->info.band_y0, y1 = h->info.band_y1, H = h->info.height;
+  const bool banded = !(y0 == 0 && y1 == H);
+  if (banded && P.doSpatialReuse && (y1 - y0) < spatial_reach(P)) {
+    h->err = "rb_render_frame: band is thinner than the spatial reuse reach";
+    return RB_ERR_UNSUPPORTED;
+  }
+  F.timed = timed;
+  F.marks.clear();
+  F.launches = 0;
+  F.frame_idx = frame_idx;
+  F.open = true;
   // The stream -> trace -> resolve split covers the passes whose rays do not depend on visibility results:
   // BRDF-candidate rays, the visibility pass, temporal reuse, spatial reuse with constant weights.
-  const bool wave = P.wavefront != 0;
-  const bool wave_spatial = wave && P.spatialWeightCalc == RB_SW_CONSTANT;
-  if (wave) {
+  F.wave = P.wavefront != 0;
+  F.wave_spatial = F.wave && P.spatialWeightCalc == RB_SW_CONSTANT;
+  if (F.wave) {
     const uint32_t slots = std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u);
     RB_TRY(ensure_wave(h, slots, (uint32_t)std::max(P.M_Brdf, 1)));
   }
-
-  FrameCtx fc{};
+  cudaStream_t st = h->stream;
+  FrameCtx& fc = F.fc;
+  fc = FrameCtx{};
   fc.width = h->info.width;
-  fc.height = h->info.height;
-  fc.y0 = h->info.band_y0;
-  fc.y1 = h->info.band_y1;
+  fc.height = H;
+  fc.y0 = y0;
+  fc.y1 = y1;
   fc.sc = h->sc;
   fc.P = P;
   fc.cam = cam_state(cam);
@@ -768,139 +950,130 @@ static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx
   fc.frame = h->frame;
   fc.counters = h->counters;
   fc.wave = h->wave;
-  const dim3 block(kTileW, kTileH);
-  const dim3 grid((fc.width + kTileW - 1) / kTileW, (fc.y1 - fc.y0 + kTileH - 1) / kTileH);
-  uint32_t launches = 0;
-  // event log: (pass, kind) per interval; kind 0 = streaming kernel, 1 = traversal kernel
-  struct Mark {
-    int pass, kind;
-  };
-  std::vector<Mark> marks;
-  int evi = 0;
-  auto mark = [&](int pass, int kind) {
-    if (!timed || evi + 1 >= RbContext::kMaxEvents) return;
-    cudaEventRecord(h->fev[evi + 1], st);
-    marks.push_back({pass, kind});
-    evi++;
-  };
-  auto bind = [&]() {
-    fc.Rread = h->R[h->rRead];
-    fc.Rwrite = h->R[h->rWrite];
-    fc.Rlast = h->R[h->rLast];
-  };
-  auto swap_rw = [&]() { std::swap(h->rRead, h->rWrite); };  // swapReservoirBuffers, P/simpleguidx11.h:116
-  const int trace_grid = h->numSMs * h->traceBlocksPerSM;
-  auto trace = [&](bool any, int pass) {
-    if (any)
-      k_trace_queue<true><<<trace_grid, kTraceThreads, 0, st>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
-                                                                 h->wave.count + 1, h->wave.occ, h->wave.hits,
-                                                                 FLT_MIN + P.tnearOffset, h->refillLanes, h->postponeLanes);
-    else
-      k_trace_queue<false><<<trace_grid, kTraceThreads, 0, st>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
-                                                                  h->wave.count + 1, h->wave.occ, h->wave.hits,
-                                                                  FLT_MIN + P.tnearOffset, h->refillLanes, h->postponeLanes);
-    launches++;
-    mark(pass, 1);
-  };
-  auto reset_queue = [&]() {
-    k_reset_queue<<<1, 1, 0, st>>>(h->wave.count, h->wave.count + 1);
-    launches++;
-  };
+  // G-buffer rows kept by this handle: the band plus a margin that covers the spatial reach and most reprojections
+  const int margin = banded ? std::max(16, spatial_reach(P)) : 0;
+  fc.gy0 = std::max(0, y0 - margin);
+  fc.gy1 = std::min(H, y1 + margin);
+  fc.gpy0 = h->havePrev ? h->prevGy0 : 0;
+  fc.gpy1 = h->havePrev ? h->prevGy1 : 0;
 
   RB_CUDA(cudaMemsetAsync(h->counters, 0, 64, st));
   if (timed) cudaEventRecord(h->fev[0], st);
-  bind();
+  fs_bind(h);
   // ---- G-buffer ------------------------------------------------------------------------------------
   fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_GBUF, 0);
-  k_gbuffer<<<grid, block, 0, st>>>(fc);
-  launches++;
-  mark(0, 0);
+  launch_rows(h, k_gbuffer, fc.gy0, fc.gy1);
+  fs_mark(h, 0, 0);
   // ---- initial candidates ----------------------------------------------------------------------------
   fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_INITIAL, 0);
-  if (wave) {
+  if (F.wave) {
     if (P.M_Brdf > 0 && h->sc.n_lights > 0) {
-      reset_queue();
-      k_initial_brdf_stream<<<grid, block, 0, st>>>(fc);
-      launches++;
-      mark(1, 0);
-      trace(false, 1);
+      fs_reset_queue(h);
+      launch_rows(h, k_initial_brdf_stream, y0, y1);
+      fs_mark(h, 1, 0);
+      fs_trace(h, false, 1);
     }
     // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel
     if (P.doVisibilityPass)
-      k_initial_resolve<<<grid, block, 0, st>>>(fc);
+      launch_rows(h, k_initial_resolve, y0, y1);
     else
-      k_initial_resolve_inline_shadow<<<grid, block, 0, st>>>(fc);
+      launch_rows(h, k_initial_resolve_inline_shadow, y0, y1);
   } else {
-    k_initial<<<grid, block, 0, st>>>(fc);
+    launch_rows(h, k_initial, y0, y1);
   }
-  launches++;
-  mark(1, 0);
+  fs_mark(h, 1, 0);
   // ---- visibility ---------------------------------------------------------------------------------
   if (P.doVisibilityPass) {
-    if (wave) {
-      reset_queue();
-      k_visibility_stream<<<grid, block, 0, st>>>(fc);
-      launches++;
-      mark(2, 0);
-      trace(true, 2);
-      k_visibility_resolve<<<grid, block, 0, st>>>(fc);
+    if (F.wave) {
+      fs_reset_queue(h);
+      launch_rows(h, k_visibility_stream, y0, y1);
+      fs_mark(h, 2, 0);
+      fs_trace(h, true, 2);
+      launch_rows(h, k_visibility_resolve, y0, y1);
     } else {
-      k_visibility<<<grid, block, 0, st>>>(fc);
+      launch_rows(h, k_visibility, y0, y1);
     }
-    launches++;
-    mark(2, 0);
+    fs_mark(h, 2, 0);
   }
   // ---- temporal reuse ----------------------------------------------------------------------------------
   if (P.doTemporalReuse && frame_idx > 0 && h->havePrev) {
-    swap_rw();
-    bind();
+    std::swap(h->rRead, h->rWrite);  // swapReservoirBuffers, P/simpleguidx11.h:116
+    fs_bind(h);
     fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_TEMPORAL, 0);
-    if (wave) {
-      reset_queue();
-      k_temporal_stream<<<grid, block, 0, st>>>(fc);
-      launches++;
-      mark(3, 0);
-      trace(true, 3);
-      k_temporal_resolve<<<grid, block, 0, st>>>(fc);
+    if (F.wave) {
+      fs_reset_queue(h);
+      launch_rows(h, k_temporal_stream, y0, y1);
+      fs_mark(h, 3, 0);
+      fs_trace(h, true, 3);
+      launch_rows(h, k_temporal_resolve, y0, y1);
     } else {
-      k_temporal<<<grid, block, 0, st>>>(fc);
+      launch_rows(h, k_temporal, y0, y1);
     }
-    launches++;
-    mark(3, 0);
+    fs_mark(h, 3, 0);
   }
-  // ---- spatial reuse -------------------------------------------------------------------------------------
-  if (P.doSpatialReuse) {
-    for (int i = 0; i < P.spatialPassCount; ++i) {
-      swap_rw();
-      bind();
-      fc.spatial_iter = i;
-      fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_SPATIAL, (uint32_t)i);
-      if (wave_spatial) {
-        reset_queue();
-        k_spatial_stream<<<grid, block, 0, st>>>(fc);
-        launches++;
-        mark(4, 0);
-        trace(true, 4);
-        k_spatial_resolve<<<grid, block, 0, st>>>(fc);
-      } else {
-        k_spatial<<<grid, block, 0, st>>>(fc);
-      }
-      launches++;
-      mark(4, 0);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
+
+// One spatial pass. With `overlap_halo` the interior rows (which need no halo) are streamed while the halo rows
+// of the neighbouring bands are in flight; the boundary rows follow once they have arrived.
+static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
+  if (!h || !h->fs.open) return RB_ERR_INVALID_ARGUMENT;
+  FrameState& F = h->fs;
+  const RbParams& P = F.P;
+  FrameCtx& fc = F.fc;
+  const int y0 = h->info.band_y0, y1 = h->info.band_y1;
+  const int R = spatial_reach(P);
+  const int iy0 = (overlap_halo && y0 > 0) ? std::min(y0 + R, y1) : y0;
+  const int iy1 = (overlap_halo && y1 < h->info.height) ? std::max(y1 - R, iy0) : y1;
+  if (overlap_halo) RB_TRY(halo_exchange_begin(h));
+  std::swap(h->rRead, h->rWrite);
+  fs_bind(h);
+  fc.spatial_iter = i;
+  fc.frame_key = rng_frame_key(h->info.seed, F.frame_idx, PASS_SPATIAL, (uint32_t)i);
+  if (F.wave_spatial) {
+    fs_reset_queue(h);
+    launch_rows(h, k_spatial_stream, iy0, iy1);
+    if (overlap_halo) {
+      RB_TRY(halo_exchange_wait(h));
+      launch_rows(h, k_spatial_stream, y0, iy0);
+      launch_rows(h, k_spatial_stream, iy1, y1);
+    }
+    fs_mark(h, 4, 0);
+    fs_trace(h, true, 4);
+    launch_rows(h, k_spatial_resolve, y0, y1);
+  } else {
+    launch_rows(h, k_spatial, iy0, iy1);
+    if (overlap_halo) {
+      RB_TRY(halo_exchange_wait(h));
+      launch_rows(h, k_spatial, y0, iy0);
+      launch_rows(h, k_spatial, iy1, y1);
     }
   }
-  // ---- shade -------------------------------------------------------------------------------------------
-  swap_rw();
-  bind();
-  k_shade<<<grid, block, 0, st>>>(fc);
-  launches++;
-  mark(5, 0);
+  fs_mark(h, 4, 0);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
+static int frame_end(RbHandle h, RbTimings* timings) {
+  if (!h || !h->fs.open) return RB_ERR_INVALID_ARGUMENT;
+  FrameState& F = h->fs;
+  FrameCtx& fc = F.fc;
+  cudaStream_t st = h->stream;
+  std::swap(h->rRead, h->rWrite);
+  fs_bind(h);
+  launch_rows(h, k_shade, h->info.band_y0, h->info.band_y1);
+  fs_mark(h, 5, 0);
   RB_CUDA(cudaGetLastError());
   // memcpy(reservoirsLastFrame, ...) + gBufferLastFrame.setDataFrom(gBuffer) (P/simpleguidx11.cpp:478-481) by rotation
   std::swap(h->rLast, h->rRead);
   h->gCur ^= 1;
   h->prevCam = fc.cam;
+  h->prevGy0 = fc.gy0;
+  h->prevGy1 = fc.gy1;
   h->havePrev = true;
+  F.open = false;
 
   if (timings) {
     memset(timings, 0, sizeof(*timings));
@@ -910,23 +1083,50 @@ static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx
     timings->rays_closest = hc[0];
     timings->rays_any_as_written = hc[1];
     timings->rays_any_traced = hc[2];
-    timings->kernel_launches = launches;
-    if (timed) {
+    timings->kernel_launches = F.launches;
+    if (F.timed) {
       float* per_pass[6] = {&timings->ms_gbuffer, &timings->ms_initial, &timings->ms_visibility,
                             &timings->ms_temporal, &timings->ms_spatial, &timings->ms_shade};
-      for (size_t i = 0; i < marks.size(); ++i) {
+      for (size_t i = 0; i < F.marks.size(); ++i) {
         float ms = 0;
         RB_CUDA(cudaEventElapsedTime(&ms, h->fev[i], h->fev[i + 1]));
-        *per_pass[marks[i].pass] += ms;
-        if (marks[i].kind == 1) {
-          timings->ms_trace[marks[i].pass] += ms;
+        *per_pass[F.marks[i].pass] += ms;
+        if (F.marks[i].kind == 1) {
+          timings->ms_trace[F.marks[i].pass] += ms;
           timings->ms_trace_any += ms;
         } else {
-          timings->ms_stream[marks[i].pass] += ms;
+          timings->ms_stream[F.marks[i].pass] += ms;
         }
       }
-      RB_CUDA(cudaEventElapsedTime(&timings->ms_total, h->fev[0], h->fev[marks.size()]));
+      RB_CUDA(cudaEventElapsedTime(&timings->ms_total, h->fev[0], h->fev[F.marks.size()]));
     }
+  }
+  return RB_OK;
+}
+
+static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx, RbTimings* timings) {
+  if (!h) return RB_ERR_INVALID_ARGUMENT;
+  const bool timed = h->info.collect_timings != 0 && timings != nullptr;
+  RB_TRY(frame_begin(h, cam, frame_idx, timed));
+  if (h->fs.P.doSpatialReuse)
+    for (int i = 0; i < h->fs.P.spatialPassCount; ++i) RB_TRY(frame_spatial(h, i, h->comm != nullptr));
+  return frame_end(h, timings);
+}
+
+extern "C" {
+
+int rb_frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx) {
+  return frame_begin(h, cam, frame_idx, h && h->info.collect_timings != 0);
+}
+int rb_frame_spatial(RbHandle h, int32_t pass_index) { return frame_spatial(h, pass_index, false); }
+int rb_frame_end(RbHandle h, float* frame_rgb_out, RbTimings* timings) {
+  int rc = frame_end(h, timings);
+  if (rc != RB_OK) return rc;
+  if (frame_rgb_out) {
+    const size_t row = (size_t)h->info.width * 3;
+    const size_t off = row * h->info.band_y0, cnt = row * (h->info.band_y1 - h->info.band_y0);
+    RB_CUDA(cudaMemcpyAsync(frame_rgb_out + off, h->frame + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RB_CUDA(cudaStreamSynchronize(h->stream));
   }
   return RB_OK;
 }
@@ -1082,16 +1282,17 @@ int rb_trace_occluded_device(RbHandle h, const RbRay* rays_dev, uint8_t* occ_dev
 }
 
 // -------------------------------------------------------------------------------------
-// multi-GPU bands: halo rows of the current reservoir read buffer
+// multi-GPU bands: reservoir halo rows
 // -------------------------------------------------------------------------------------
 size_t rb_halo_bytes(RbHandle h, int32_t rows) {
   if (!h || rows < 0) return 0;
   return (size_t)rows * h->info.width * 52;
 }
+// rows [y, y+rows) of the reservoirs the next spatial pass reads (R[rWrite] between frame phases)
 static int halo_copy(RbHandle h, int32_t y, int32_t rows, void* host, bool to_host) {
   if (!h || !host || y < 0 || rows < 0 || y + rows > h->info.height) return RB_ERR_INVALID_ARGUMENT;
   RB_CUDA(cudaSetDevice(h->info.device));
-  const ResPlanes& R = h->R[h->rLast];
+  const ResPlanes& R = h->R[h->fs.open ? h->rWrite : h->rLast];
   const size_t px = (size_t)rows * h->info.width, off = (size_t)y * h->info.width;
   char* p = (char*)host;
   void* planes[4] = {R.point_wsum + off, R.normal_W + off, R.Li_conf + off, R.light_idx + off};
@@ -1110,19 +1311,30 @@ int rb_halo_export(RbHandle h, int32_t y, int32_t rows, void* dst_host) { return
 int rb_halo_import(RbHandle h, int32_t y, int32_t rows, const void* src_host) {
   return halo_copy(h, y, rows, const_cast<void*>(src_host), false);
 }
+int32_t rb_halo_rows(RbHandle h) { return h ? spatial_reach(h->fs.open ? h->fs.P : h->params) : 0; }
 
 int rb_comm_unique_id(void* out_id, size_t id_bytes) {
-  (void)out_id;
-  (void)id_bytes;
-  return RB_ERR_UNSUPPORTED;
+  if (!out_id || id_bytes < 128) return RB_ERR_INVALID_ARGUMENT;
+  std::string err;
+  if (!load_nccl(err)) {
+    g_create_error = err;
+    return RB_ERR_COMM;
+  }
+  return g_nccl.GetUniqueId(out_id) == 0 ? RB_OK : RB_ERR_COMM;
 }
 int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes) {
-  (void)rank;
-  (void)nranks;
-  (void)nccl_unique_id;
-  (void)id_bytes;
-  if (h) h->err = "rb_comm_init: NCCL band exchange not built yet";
-  return RB_ERR_UNSUPPORTED;
+  if (!h || !nccl_unique_id || id_bytes < 128 || rank < 0 || rank >= nranks) return RB_ERR_INVALID_ARGUMENT;
+  if (!load_nccl(h->err)) return RB_ERR_COMM;
+  RB_CUDA(cudaSetDevice(h->info.device));
+  NcclId128 id;
+  memcpy(id.b, nccl_unique_id, 128);
+  RB_NCCL(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+  h->commRank = rank;
+  h->commSize = nranks;
+  RB_CUDA(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
+  RB_CUDA(cudaEventCreateWithFlags(&h->evHaloReady, cudaEventDisableTiming));
+  RB_CUDA(cudaEventCreateWithFlags(&h->evHaloDone, cudaEventDisableTiming));
+  return RB_OK;
 }
 
 }  // extern "C"

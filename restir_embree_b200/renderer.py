@@ -61,6 +61,11 @@ def load_library():
     L.rb_halo_bytes.argtypes = [H, C.c_int32]
     L.rb_halo_export.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
     L.rb_halo_import.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
+    L.rb_halo_rows.restype = C.c_int32
+    L.rb_halo_rows.argtypes = [H]
+    L.rb_frame_begin.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32]
+    L.rb_frame_spatial.argtypes = [H, C.c_int32]
+    L.rb_frame_end.argtypes = [H, C.c_void_p, C.POINTER(abi.RbTimings)]
     if L.rb_abi_version() != 1:
         raise RestirError("librestir_b200.so ABI version mismatch")
     _lib = L
@@ -206,6 +211,25 @@ class Renderer:
         self._check(fn(self.h, rays_ptr, out_ptr, int(n), C.byref(ms)), "rb_trace_*_device")
         return ms.value
 
+    # -- frame in phases (hosts that move the halo rows themselves) ------------------------------------
+    def frame_begin(self, cam, frame_idx):
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        self._check(self.L.rb_frame_begin(self.h, C.byref(c), int(frame_idx)), "rb_frame_begin")
+
+    def frame_spatial(self, i):
+        self._check(self.L.rb_frame_spatial(self.h, int(i)), "rb_frame_spatial")
+
+    def frame_end(self, out=None):
+        ptr = out.ctypes.data if out is not None else None
+        self._check(self.L.rb_frame_end(self.h, ptr, None), "rb_frame_end")
+
+    def halo_rows(self):
+        return int(self.L.rb_halo_rows(self.h))
+
+    def comm_init(self, rank, nranks, unique_id_bytes):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id_bytes)[:128])
+        self._check(self.L.rb_comm_init(self.h, int(rank), int(nranks), buf, 128), "rb_comm_init")
+
     # -- band halos -------------------------------------------------------------------------
     def halo_export(self, y, rows):
         buf = np.empty(self.L.rb_halo_bytes(self.h, rows), dtype=np.uint8)
@@ -216,6 +240,39 @@ class Renderer:
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         assert buf.nbytes == self.L.rb_halo_bytes(self.h, rows)
         self._check(self.L.rb_halo_import(self.h, y, rows, buf.ctypes.data), "rb_halo_import")
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0); 128 bytes to hand to every rank's Renderer.comm_init."""
+    L = load_library()
+    buf = (C.c_char * 128)()
+    rc = L.rb_comm_unique_id(buf, 128)
+    if rc != abi.RB_OK:
+        raise RestirError(f"rb_comm_unique_id failed ({rc})")
+    return bytes(buf)
+
+
+def band_rows(height, nranks, rank):
+    """Rows [y0, y1) of band `rank` of `nranks` contiguous horizontal bands of ceil(height/nranks) rows."""
+    rows = (height + nranks - 1) // nranks
+    return min(height, rank * rows), min(height, (rank + 1) * rows)
+
+
+def exchange_halos(renderers):
+    """Single-process band emulation: move the halo rows between neighbouring handles through host memory
+    (what rb_render_frame does with NCCL send/recv when rb_comm_init was called). `renderers` top to bottom."""
+    if len(renderers) < 2:
+        return
+    R = renderers[0].halo_rows()
+    for up, dn in zip(renderers[:-1], renderers[1:]):
+        y = up.band[1]
+        assert dn.band[0] == y
+        r_up = min(R, up.band[1] - up.band[0])
+        r_dn = min(R, dn.band[1] - dn.band[0])
+        a = up.halo_export(y - r_up, r_up)      # bottom rows of the upper band -> lower band's top halo
+        b = dn.halo_export(y, r_dn)             # top rows of the lower band -> upper band's bottom halo
+        dn.halo_import(y - r_up, r_up, a)
+        up.halo_import(y, r_dn, b)
 
 
 def make_rays(org, target=None, direction=None, tnear=0.01, tfar=None, tfar_offset=0.001):

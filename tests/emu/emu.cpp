@@ -46,6 +46,15 @@ struct Emu {
   unsigned long long counters[8] = {0};
   CamState prevCam{};
   std::string err;
+  // in-flight frame (phases) and band bookkeeping
+  FrameCtx fc{};
+  RbParams Pf{};
+  bool open = false, wave = false, wave_spatial = false;
+  uint32_t frame_idx = 0, qcount = 0;
+  int prevGy0 = 0, prevGy1 = 0;
+  std::vector<RayQ> rays;
+  std::vector<uint8_t> occ;
+  std::vector<HitRec> hits;
 
   GBufPlanes gp(int i) { return GBufPlanes{gs[i].a.data(), gs[i].b.data(), gs[i].c.data(), gs[i].d.data(), gs[i].e.data(), gs[i].ids.data()}; }
   ResPlanes rp(int i) { return ResPlanes{rs[i].a.data(), rs[i].b.data(), rs[i].c.data(), rs[i].li.data()}; }
@@ -284,12 +293,54 @@ static void for_pixels(Emu* E, FrameCtx& fc, F&& f) {
 
 extern "C" {
 
-// mirrors render_frame_impl of restir_b200.cu (the host-side pass schedule)
-int emu_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rgb_out) {
+}  // extern "C"
+
+// mirrors frame_begin / frame_spatial / frame_end of restir_b200.cu (the host-side pass schedule)
+static int spatial_reach(const RbParams& P) { return (int)sqrtf(std::max(P.spatialReuseRadius, 0.0f)) + 1; }
+static uint32_t PX(const FrameCtx& fc, int x, int y) { return (uint32_t)(y * fc.width + x); }
+
+static void emu_trace_queue(Emu* E, bool any) {
+  FrameCtx& fc = E->fc;
+  const float tnear = FLT_MIN + E->Pf.tnearOffset;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t i = 0; i < (int64_t)E->qcount; ++i) {
+    const RayQ& r = E->rays[i];
+    const uint32_t dest = f2u(r.d_dest.w);
+    HitRec hr;
+    const bool hit = any ? trace8<true>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr)
+                         : trace8<false>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr);
+    if (any)
+      E->occ[dest] = hit ? 1 : 0;
+    else
+      E->hits[dest] = hr;
+  }
+}
+template <class F>
+static void emu_stream(Emu* E, F&& body) {  // stream half: emits rays, counts nothing
+  E->qcount = 0;
+  unsigned long long save[3] = {E->counters[0], E->counters[1], E->counters[2]};
+  for_pixels(E, E->fc, body);
+  E->counters[0] = save[0], E->counters[1] = save[1], E->counters[2] = save[2];
+}
+template <class F>
+static void emu_rows(Emu* E, int ry0, int ry1, F&& body) {
+  FrameCtx f = E->fc;
+  f.y0 = ry0, f.y1 = ry1;
+  for_pixels(E, f, body);
+}
+static void emu_bind(Emu* E) { E->fc.Rread = E->rp(E->rRead), E->fc.Rwrite = E->rp(E->rWrite), E->fc.Rlast = E->rp(E->rLast); }
+
+extern "C" {
+
+int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
   Emu* E = (Emu*)h;
   if (!E->haveScene) return RB_ERR_NO_SCENE;
-  const RbParams P = E->P;
-  FrameCtx fc{};
+  E->Pf = E->P;
+  const RbParams& P = E->Pf;
+  const bool banded = !(E->y0 == 0 && E->y1 == E->height);
+  if (banded && P.doSpatialReuse && (E->y1 - E->y0) < spatial_reach(P)) return RB_ERR_UNSUPPORTED;
+  FrameCtx& fc = E->fc;
+  fc = FrameCtx{};
   fc.width = E->width, fc.height = E->height, fc.y0 = E->y0, fc.y1 = E->y1;
   fc.sc = E->sc;
   fc.P = P;
@@ -302,113 +353,133 @@ int emu_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rg
   fc.Gprev = E->gp(E->gCur ^ 1);
   fc.frame = E->frame.data();
   fc.counters = E->counters;
+  const int margin = banded ? std::max(16, spatial_reach(P)) : 0;
+  fc.gy0 = std::max(0, E->y0 - margin);
+  fc.gy1 = std::min(E->height, E->y1 + margin);
+  fc.gpy0 = E->havePrev ? E->prevGy0 : 0;
+  fc.gpy1 = E->havePrev ? E->prevGy1 : 0;
   memset(E->counters, 0, sizeof(E->counters));
-  auto bind = [&]() { fc.Rread = E->rp(E->rRead), fc.Rwrite = E->rp(E->rWrite), fc.Rlast = E->rp(E->rLast); };
-  auto swap_rw = [&]() { std::swap(E->rRead, E->rWrite); };
-  // wavefront mode: same stream -> trace -> resolve schedule as render_frame_impl, with host loops
-  const bool wave = P.wavefront != 0;
-  const bool wave_spatial = wave && P.spatialWeightCalc == RB_SW_CONSTANT;
+  E->frame_idx = frame_idx;
+  E->wave = P.wavefront != 0;
+  E->wave_spatial = E->wave && P.spatialWeightCalc == RB_SW_CONSTANT;
   const uint32_t npix = (uint32_t)(E->width * E->height);
   const uint32_t slots = std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u);
-  std::vector<RayQ> rays;
-  std::vector<uint8_t> occ;
-  std::vector<HitRec> hits;
-  uint32_t qcount = 0;
-  if (wave) {
-    rays.resize((size_t)npix * std::max<uint32_t>(slots, (uint32_t)std::max(P.M_Brdf, 1)));
-    occ.assign((size_t)npix * slots, 0xCD);
-    hits.resize((size_t)npix * std::max(P.M_Brdf, 1));
-    fc.wave.rays = rays.data();
-    fc.wave.count = &qcount;
-    fc.wave.capacity = (uint32_t)rays.size();
-    fc.wave.occ = occ.data();
-    fc.wave.hits = hits.data();
+  if (E->wave) {
+    E->rays.resize((size_t)npix * std::max<uint32_t>(slots, (uint32_t)std::max(P.M_Brdf, 1)));
+    E->occ.assign((size_t)npix * slots, 0xCD);
+    E->hits.resize((size_t)npix * std::max(P.M_Brdf, 1));
+    fc.wave.rays = E->rays.data();
+    fc.wave.count = &E->qcount;
+    fc.wave.capacity = (uint32_t)E->rays.size();
+    fc.wave.occ = E->occ.data();
+    fc.wave.hits = E->hits.data();
     fc.wave.npix = npix;
   }
-  auto px = [&](int x, int y) { return (uint32_t)(y * fc.width + x); };
-  auto trace_queue = [&](bool any) {
-    const float tnear = FLT_MIN + P.tnearOffset;
-#pragma omp parallel for schedule(dynamic, 64)
-    for (int64_t i = 0; i < (int64_t)qcount; ++i) {
-      const RayQ& r = rays[i];
-      const uint32_t dest = f2u(r.d_dest.w);
-      HitRec hr;
-      const bool hit = any ? trace8<true>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr)
-                           : trace8<false>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr);
-      if (any)
-        occ[dest] = hit ? 1 : 0;
-      else
-        hits[dest] = hr;
-    }
-  };
-  auto stream = [&](auto&& body) {  // stream half: emits rays, counts nothing
-    qcount = 0;
-    unsigned long long save[3] = {E->counters[0], E->counters[1], E->counters[2]};
-    for_pixels(E, fc, body);
-    E->counters[0] = save[0], E->counters[1] = save[1], E->counters[2] = save[2];
-  };
-  bind();
+  const bool wave = E->wave;
+  emu_bind(E);
   fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_GBUF, 0);
-  for_pixels(E, fc, [&](int x, int y, Cnt& c) { gbuffer_pixel(fc, x, y, c); });
+  emu_rows(E, fc.gy0, fc.gy1, [&](int x, int y, Cnt& c) { gbuffer_pixel(fc, x, y, c); });
   fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_INITIAL, 0);
   if (wave) {
     if (P.M_Brdf > 0 && fc.sc.n_lights > 0) {
-      stream([&](int x, int y, Cnt&) { initial_brdf_gen_pixel(fc, x, y, GenVis{&fc, px(x, y)}); });
-      trace_queue(false);
+      emu_stream(E, [&](int x, int y, Cnt&) { initial_brdf_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}); });
+      emu_trace_queue(E, false);
     }
     if (P.doVisibilityPass)
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveVis{&fc, px(x, y)}, c); });
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
     else
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveInlineShadowVis{&fc, px(x, y)}, c); });
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveInlineShadowVis{&fc, PX(fc, x, y)}, c); });
   } else {
-    for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
   }
   if (P.doVisibilityPass) {
     if (wave) {
-      stream([&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, GenVis{&fc, px(x, y)}, c); });
-      trace_queue(true);
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, ResolveVis{&fc, px(x, y)}, c); });
+      emu_stream(E, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+      emu_trace_queue(E, true);
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
     } else {
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
     }
   }
   if (P.doTemporalReuse && frame_idx > 0 && E->havePrev) {
-    swap_rw();
-    bind();
+    std::swap(E->rRead, E->rWrite);
+    emu_bind(E);
     fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_TEMPORAL, 0);
     if (wave) {
-      stream([&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, GenVis{&fc, px(x, y)}, c); });
-      trace_queue(true);
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, ResolveVis{&fc, px(x, y)}, c); });
+      emu_stream(E, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+      emu_trace_queue(E, true);
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
     } else {
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
     }
   }
-  if (P.doSpatialReuse) {
-    for (int i = 0; i < P.spatialPassCount; ++i) {
-      swap_rw();
-      bind();
-      fc.spatial_iter = i;
-      fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_SPATIAL, (uint32_t)i);
-      if (wave_spatial) {
-        stream([&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, GenVis{&fc, px(x, y)}, c); });
-        trace_queue(true);
-        for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, ResolveVis{&fc, px(x, y)}, c); });
-      } else {
-        for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
-      }
-    }
+  E->open = true;
+  return 0;
+}
+
+int emu_frame_spatial(void* h, int i) {
+  Emu* E = (Emu*)h;
+  if (!E->open) return -1;
+  FrameCtx& fc = E->fc;
+  std::swap(E->rRead, E->rWrite);
+  emu_bind(E);
+  fc.spatial_iter = i;
+  fc.frame_key = rng_frame_key(E->seed, E->frame_idx, PASS_SPATIAL, (uint32_t)i);
+  if (E->wave_spatial) {
+    emu_stream(E, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+    emu_trace_queue(E, true);
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
+  } else {
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
   }
-  swap_rw();
-  bind();
-  for_pixels(E, fc, [&](int x, int y, Cnt& c) { shade_pixel(fc, x, y, InlineVis{&fc, px(x, y)}, c); });
+  return 0;
+}
+
+int emu_frame_end(void* h, float* rgb_out) {
+  Emu* E = (Emu*)h;
+  if (!E->open) return -1;
+  FrameCtx& fc = E->fc;
+  std::swap(E->rRead, E->rWrite);
+  emu_bind(E);
+  for_pixels(E, fc, [&](int x, int y, Cnt& c) { shade_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
   std::swap(E->rLast, E->rRead);
   E->gCur ^= 1;
   E->prevCam = fc.cam;
+  E->prevGy0 = fc.gy0, E->prevGy1 = fc.gy1;
   E->havePrev = true;
+  E->open = false;
   if (rgb_out) memcpy(rgb_out, E->frame.data(), E->frame.size() * sizeof(float));
   return 0;
 }
+
+int emu_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rgb_out) {
+  Emu* E = (Emu*)h;
+  int rc = emu_frame_begin(h, cam, frame_idx);
+  if (rc) return rc;
+  if (E->Pf.doSpatialReuse)
+    for (int i = 0; i < E->Pf.spatialPassCount; ++i) emu_frame_spatial(h, i);
+  return emu_frame_end(h, rgb_out);
+}
+
+int emu_halo_rows(void* h) { return spatial_reach(((Emu*)h)->open ? ((Emu*)h)->Pf : ((Emu*)h)->P); }
+// rows [y, y+rows) of the reservoirs the next spatial pass reads: 4 planes packed back to back (52 B / px)
+static int emu_halo_copy(Emu* E, int y, int rows, char* host, bool to_host) {
+  if (y < 0 || rows < 0 || y + rows > E->height) return -1;
+  Emu::RStore& R = E->rs[E->open ? E->rWrite : E->rLast];
+  const size_t px = (size_t)rows * E->width, off = (size_t)y * E->width;
+  char* planes[4] = {(char*)(R.a.data() + off), (char*)(R.b.data() + off), (char*)(R.c.data() + off), (char*)(R.li.data() + off)};
+  const size_t sz[4] = {px * 16, px * 16, px * 16, px * 4};
+  for (int i = 0; i < 4; ++i) {
+    if (to_host)
+      memcpy(host, planes[i], sz[i]);
+    else
+      memcpy(planes[i], host, sz[i]);
+    host += sz[i];
+  }
+  return 0;
+}
+int emu_halo_export(void* h, int y, int rows, void* dst) { return emu_halo_copy((Emu*)h, y, rows, (char*)dst, true); }
+int emu_halo_import(void* h, int y, int rows, const void* src) { return emu_halo_copy((Emu*)h, y, rows, (char*)src, false); }
 
 void emu_counters(void* h, uint64_t* out3) {
   Emu* E = (Emu*)h;

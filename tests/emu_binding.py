@@ -42,6 +42,12 @@ def lib():
         L.emu_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.emu_trace_occluded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.emu_validate_bvh.argtypes = [C.c_void_p]
+        L.emu_frame_begin.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32]
+        L.emu_frame_spatial.argtypes = [C.c_void_p, C.c_int]
+        L.emu_frame_end.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_halo_rows.argtypes = [C.c_void_p]
+        L.emu_halo_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.emu_halo_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -51,6 +57,7 @@ class Emu:
         self.L = lib()
         self.width, self.height = width, height
         y0, y1 = band if band else (0, height)
+        self.band = (y0, y1)
         self.h = self.L.emu_create(width, height, seed, y0, y1)
         self._keep = None
 
@@ -88,6 +95,30 @@ class Emu:
         rc = self.L.emu_render_frame(self.h, C.byref(c), frame_idx, out.ctypes.data)
         assert rc == 0, rc
         return out
+
+    # frame in phases + halo rows: same surface as restir_embree_b200.renderer.Renderer
+    def frame_begin(self, cam, frame_idx):
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        assert self.L.emu_frame_begin(self.h, C.byref(c), frame_idx) == 0
+
+    def frame_spatial(self, i):
+        assert self.L.emu_frame_spatial(self.h, i) == 0
+
+    def frame_end(self, out=None):
+        assert self.L.emu_frame_end(self.h, out.ctypes.data if out is not None else None) == 0
+
+    def halo_rows(self):
+        return int(self.L.emu_halo_rows(self.h))
+
+    def halo_export(self, y, rows):
+        buf = np.empty(rows * self.width * 52, dtype=np.uint8)
+        assert self.L.emu_halo_export(self.h, y, rows, buf.ctypes.data) == 0
+        return buf
+
+    def halo_import(self, y, rows, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        assert buf.nbytes == rows * self.width * 52
+        assert self.L.emu_halo_import(self.h, y, rows, buf.ctypes.data) == 0
 
     def counters(self):
         c = np.zeros(3, dtype=np.uint64)
