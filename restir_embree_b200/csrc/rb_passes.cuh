@@ -626,7 +626,9 @@ RB_HD bool reproject(const CamState& cam, int width, int height, const V3& wsPos
   return true;
 }
 
-template <class Vis>
+// BANDED: the handle renders a band of the image, so reprojected pixels may lie outside its G-buffer rows and are
+// re-derived (fetch_*); the single-band instantiation reads the planes directly and carries no traversal code.
+template <class Vis, bool BANDED>
 RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
   const size_t pi = (size_t)y * fc.width + x;
   const RbParams& P = fc.P;
@@ -637,7 +639,7 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
     if (Vis::kStore) store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
-  const GElem prevElem = fetch_gelem(fc, true, px, py, cnt);
+  const GElem prevElem = BANDED ? fetch_gelem(fc, true, px, py, cnt) : load_gelem(fc.Gprev, (size_t)py * fc.width + px);
   const V3 curCam = fc.cam.pos, prevCam = fc.prevCam.pos;
   const float currentDepth = length(curElem.pos - curCam);
   const float prevDepth = length(prevElem.pos - prevCam);
@@ -652,7 +654,7 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
     if (Vis::kStore) store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
-  const V3 fwPos = fetch_gpos(fc, false, fx, fy, cnt);
+  const V3 fwPos = BANDED ? fetch_gpos(fc, false, fx, fy, cnt) : xyz(ld4(fc.G.pos_depth + (size_t)fy * fc.width + fx));
   const float currentDepthP = length(prevPosAtCurrent - prevCam);
   const float prevDepthP = length(fwPos - curCam);
   const float depthRatioP = currentDepthP > prevDepthP ? prevDepthP / currentDepthP : currentDepthP / prevDepthP;

@@ -56,7 +56,8 @@ __device__ __forceinline__ void flush_counts(unsigned long long* ctr, const Cnt&
 RB_PIXEL_KERNEL(k_gbuffer, InlineVis, true, 1, gbuffer_pixel(fc, x, y, cnt))
 RB_PIXEL_KERNEL(k_initial, InlineVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility, InlineVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal, InlineVis, true, 1, temporal_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal, InlineVis, true, 1, (temporal_pixel<InlineVis, false>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_banded, InlineVis, true, 1, (temporal_pixel<InlineVis, true>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_spatial, InlineVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_shade, InlineVis, true, 1, shade_pixel(fc, x, y, vis, cnt))
 // wavefront halves
@@ -65,8 +66,10 @@ RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 2, initial_pixel(fc, x, y, 
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_stream, GenVis, false, 1, temporal_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 1, temporal_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal_stream, GenVis, false, 1, (temporal_pixel<GenVis, false>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 1, (temporal_pixel<ResolveVis, false>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, false, 1, (temporal_pixel<GenVis, true>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_resolve_banded, ResolveVis, true, 1, (temporal_pixel<ResolveVis, true>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_spatial_stream, GenVis, false, 1, spatial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
 
@@ -1002,12 +1005,21 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_TEMPORAL, 0);
     if (F.wave) {
       fs_reset_queue(h);
-      launch_rows(h, k_temporal_stream, y0, y1);
+      if (banded)
+        launch_rows(h, k_temporal_stream_banded, y0, y1);
+      else
+        launch_rows(h, k_temporal_stream, y0, y1);
       fs_mark(h, 3, 0);
       fs_trace(h, true, 3);
-      launch_rows(h, k_temporal_resolve, y0, y1);
+      if (banded)
+        launch_rows(h, k_temporal_resolve_banded, y0, y1);
+      else
+        launch_rows(h, k_temporal_resolve, y0, y1);
     } else {
-      launch_rows(h, k_temporal, y0, y1);
+      if (banded)
+        launch_rows(h, k_temporal_banded, y0, y1);
+      else
+        launch_rows(h, k_temporal, y0, y1);
     }
     fs_mark(h, 3, 0);
   }

@@ -406,11 +406,19 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     emu_bind(E);
     fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_TEMPORAL, 0);
     if (wave) {
-      emu_stream(E, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
-      emu_trace_queue(E, true);
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
+      if (banded) {
+        emu_stream(E, [&](int x, int y, Cnt& c) { temporal_pixel<GenVis, true>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+        emu_trace_queue(E, true);
+        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel<ResolveVis, true>(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
+      } else {
+        emu_stream(E, [&](int x, int y, Cnt& c) { temporal_pixel<GenVis, false>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+        emu_trace_queue(E, true);
+        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel<ResolveVis, false>(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
+      }
+    } else if (banded) {
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel<InlineVis, true>(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
     } else {
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel<InlineVis, false>(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
     }
   }
   E->open = true;
