@@ -154,3 +154,13 @@ def test_full_hd_frame_sampled_rows_and_properties(gpu, scene_1m):
             emissive = (r.readback(abi.BUF_GBUF_SPEC_TYPE)[..., 3].view(np.uint32) & 0x100) != 0
             assert t["rays_closest"] == Wf * Hf + int((~emissive).sum()) * p.M_Brdf
             assert ob.relmse(b[rows], a[rows]) <= 1e-3
+
+
+def test_cpp_host_mirror_example(gpu):
+    """The C++ mirror of the reference interface (restir_embree_b200/host/restir_b200.hpp) renders through the C ABI."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "restir_embree_b200", "host", "example_main")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "OK" in out.stdout
