@@ -265,37 +265,39 @@ DM_HD float lgammaf_(float x) {
 // Non-regularised incomplete beta B(x; a, b) = int_0^x t^(a-1) (1-t)^(b-1) dt,
 // a > 0, b > 0, 0 <= x <= 1: boost::math::beta(a, b, x). Continued fraction
 // (modified Lentz) on the side where it converges fast, complement otherwise.
+// The continued fraction 1/(1+ d1/(1+ d2/(1+ ...))) of the incomplete beta function, evaluated with the forward
+// (Wallis) recurrence on numerators/denominators scaled by the denominators of the rational coefficients, so that a
+// step costs a handful of multiplies and NO division (the classic modified-Lentz form needs six per iteration);
+// one division at the end. Both sequences are rescaled together by exact powers of two.
 DM_HD double ibeta_cf(double a, double b, double x) {
-  const double tiny = 1e-300;
-  const double eps = 1e-16;
-  double qab = a + b, qap = a + 1.0, qam = a - 1.0;
-  double c = 1.0;
-  double d = 1.0 - qab * x / qap;
-  if (d < tiny && d > -tiny) d = tiny;
-  d = 1.0 / d;
-  double h = d;
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  // f = A/B with A_{-1} = 1, B_{-1} = 0, A_0 = 0... use the standard form h = 1 / (1 + d1 / (1 + d2 / ...)):
+  // start from the tail-free pair (A0, B0) = (1, 1 - qab*x/qap) written as numerators over the common denominator qap
+  double A0 = 1.0, B0 = 1.0;              // A_{j-1}, B_{j-1}  (convergent before d1: 1/1)
+  double A1 = qap, B1 = qap - qab * x;    // A_j, B_j scaled by Den_1 = qap  (h_1 = 1 / (1 - qab*x/qap))
+  double denPrev = qap;                   // Den_j: scale carried by (A1, B1) relative to (A0, B0)
   for (int m = 1; m <= 400; ++m) {
-    double md = (double)m;
-    double m2 = 2.0 * md;
-    double aa = md * (b - md) * x / ((qam + m2) * (a + m2));
-    d = 1.0 + aa * d;
-    if (d < tiny && d > -tiny) d = tiny;
-    c = 1.0 + aa / c;
-    if (c < tiny && c > -tiny) c = tiny;
-    d = 1.0 / d;
-    h *= d * c;
-    aa = -(a + md) * (qab + md) * x / ((a + m2) * (qap + m2));
-    d = 1.0 + aa * d;
-    if (d < tiny && d > -tiny) d = tiny;
-    c = 1.0 + aa / c;
-    if (c < tiny && c > -tiny) c = tiny;
-    d = 1.0 / d;
-    double del = d * c;
-    h *= del;
-    double e = del - 1.0;
-    if (e < eps && e > -eps) break;
+    const double md = (double)m, m2 = 2.0 * md;
+    // even step: coefficient  aa = md (b - md) x / ((qam + m2)(a + m2))
+    double num = md * (b - md) * x, den = (qam + m2) * (a + m2);
+    double A2 = fma_(den, A1, num * denPrev * A0), B2 = fma_(den, B1, num * denPrev * B0);
+    A0 = A1, B0 = B1, A1 = A2, B1 = B2, denPrev = den;
+    // odd step: aa = -(a + md)(qab + md) x / ((a + m2)(qap + m2))
+    num = -(a + md) * (qab + md) * x, den = (a + m2) * (qap + m2);
+    A2 = fma_(den, A1, num * denPrev * A0), B2 = fma_(den, B1, num * denPrev * B0);
+    A0 = A1, B0 = B1, A1 = A2, B1 = B2, denPrev = den;
+    // keep magnitudes in range: scale both pairs by the same exact power of two
+    const uint64_t eb = (d2u(B1) >> 52) & 0x7FF;
+    if (eb > 1023 + 200 || eb < 1023 - 200) {
+      const double sc = u2d((uint64_t)(2046 - (int64_t)eb) << 52);  // 2^-(exponent of B1)
+      A0 *= sc, B0 *= sc, A1 *= sc, B1 *= sc;
+    }
+    // converged when successive convergents agree to ~1e-16:  |A1 B0 - A0 B1| <= eps |A1 B0|
+    const double cross = A1 * B0, diff = cross - A0 * B1;
+    const double tol = 1e-16 * (cross < 0 ? -cross : cross);
+    if ((diff < 0 ? -diff : diff) <= tol) break;
   }
-  return h;
+  return A1 / B1;
 }
 DM_HD_NOINLINE double ibeta_full(double a, double b, double x) {
   if (x <= 0.0) return 0.0;
