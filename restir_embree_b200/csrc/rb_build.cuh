@@ -4,11 +4,14 @@
 //   2. morton_body   : 63-bit Morton code of the box centre
 //   3. radix sort of (code, triangle) — device: cub::DeviceRadixSort; emulation: std::stable_sort
 //   4. karras_body   : binary radix tree over the sorted codes (Karras 2012), one thread per internal node
-//   5. fit_body      : bottom-up box fit, one thread per leaf, second arrival at a node proceeds
-//   6. collapse_body : top-down, level-synchronous collapse of the binary tree into 8-wide nodes:
-//                      open the child with the largest surface area until 8 children; subtrees with
-//                      <= RB_LEAF_MAX triangles become leaf children; choose child slots for octant
-//                      ordering; quantise child boxes to 8 bits outward; emit leaf triangles in node order
+//   5. fit_body      : bottom-up box fit, one thread per leaf, second arrival at a node proceeds; the same sweep
+//                      fills the collapse table C(node, i) = cheapest SAH cost of the subtree represented as at
+//                      most i roots (wide nodes or leaves), i = 1..7 (the dynamic program of Ylitie, Karras &
+//                      Laine 2017, section 3.1)
+//   6. collapse_body : top-down, level-synchronous collapse of the binary tree into 8-wide nodes following the
+//                      table's decisions (which subtrees become the <= 8 children of a wide node; subtrees with
+//                      <= RB_LEAF_MAX triangles may become leaf children); choose child slots for octant
+//                      ordering; quantise child boxes to 7 bits outward; emit leaf triangles in node order
 // Every body is a __host__ __device__ function of a thread index so the emulation harness
 // in tests/emu can run the identical code sequentially on the CPU.
 #ifndef RB_BUILD_CUH_
@@ -68,6 +71,10 @@ RB_HD int clz64_(uint64_t x) {
 #endif
 }
 
+#ifndef RB_COLLAPSE_C_PRIM
+#define RB_COLLAPSE_C_PRIM 0.3f
+#endif
+
 struct BuildCtx {
   uint32_t n;            // triangles
   const float* tri_pos;  // [n][9] scene order
@@ -89,8 +96,12 @@ struct BuildCtx {
   F4* ibox_lo;       // [n-1]
   F4* ibox_hi;
   int* visit;  // [n-1] arrival counters
+  // optimal collapse (dynamic program over the binary tree, filled bottom-up by fit_body)
+  float* dp_cost;     // [7 * (n-1)]: C(node, i), i = 1..7 — SAH cost of the subtree as a forest of at most i roots
+  uint32_t* dp_dec;   // [2 * (n-1)]: 8 decision bytes, byte j-1 for j = 1..8 (see dp_node)
+  float c_prim;       // cost of a triangle test relative to a node visit
   // collapse
-  F4* node8;       // [5 * max_nodes]
+  F4* node8;       // [RB_NODE_F4 * max_nodes]
   F4* tri_isect;   // [3 * n]
   int* counters;   // [0] nodes allocated, [1] leaf triangles emitted, [2] next-queue length
   const int* q_in;  // pairs (binary node, out node8 index)
@@ -196,6 +207,70 @@ RB_HD void child_box(const BuildCtx& c, int ref, F4* lo, F4* hi) {
     *hi = c.ibox_hi[ref];
   }
 }
+RB_HD float box_area(const F4& lo, const F4& hi) {
+  const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+// Collapse table of one child: a single triangle costs area * c_prim however many roots it may use.
+RB_HD void dp_load(const BuildCtx& c, int ref, const F4& lo, const F4& hi, float* C /*[8], 1..7 used*/) {
+  if (ref < 0) {
+    const float v = box_area(lo, hi) * c.c_prim;
+    for (int i = 1; i <= 7; ++i) C[i] = v;
+    return;
+  }
+  for (int i = 1; i <= 7; ++i) {
+#if defined(__CUDA_ARCH__)
+    C[i] = __ldcg(c.dp_cost + 7 * (size_t)ref + (i - 1));  // written by another thread: bypass L1
+#else
+    C[i] = c.dp_cost[7 * (size_t)ref + (i - 1)];
+#endif
+  }
+}
+// C(n,1) = min(leaf, internal) with leaf = A*P*c_prim (P <= RB_LEAF_MAX) and internal = distribute(n,8) + A;
+// C(n,i) = min(distribute(n,i), C(n,i-1)); distribute(n,j) = min_k C(left,k) + C(right,j-k).
+// Decision byte j-1 (j = 2..8): low 3 bits = the k of distribute(n,j), bit 7 = "C(n,j) is C(n,j-1)".
+// Decision byte 0: 1 = the subtree is a leaf when it is a single root.
+RB_HD void dp_node(const BuildCtx& c, int node, const F4& alo, const F4& ahi, const F4& blo, const F4& bhi, const F4& nlo,
+                   const F4& nhi) {
+  float CL[8], CR[8];
+  dp_load(c, c.left[node], alo, ahi, CL);
+  dp_load(c, c.right[node], blo, bhi, CR);
+  float dist[9];
+  uint32_t dec[8];
+  for (int j = 2; j <= 8; ++j) {
+    float best = FLT_MAX;
+    int bk = 1;
+    for (int k = 1; k < j; ++k) {
+      if (k > 7 || j - k > 7) continue;
+      const float v = CL[k] + CR[j - k];
+      if (v < best) best = v, bk = k;
+    }
+    dist[j] = best;
+    dec[j - 1] = (uint32_t)bk;
+  }
+  const float A = box_area(nlo, nhi);
+  const int P = c.range_hi[node] - c.range_lo[node] + 1;
+  float C[8];
+  const float internal = dist[8] + A;
+  const float leaf = P <= RB_LEAF_MAX ? A * (float)P * c.c_prim : FLT_MAX;
+  C[1] = leaf <= internal ? leaf : internal;
+  dec[0] = leaf <= internal ? 1u : 0u;
+  for (int i = 2; i <= 7; ++i) {
+    if (dist[i] < C[i - 1]) {
+      C[i] = dist[i];
+    } else {
+      C[i] = C[i - 1];
+      dec[i - 1] |= 0x80u;
+    }
+  }
+  for (int i = 1; i <= 7; ++i) c.dp_cost[7 * (size_t)node + (i - 1)] = C[i];
+  c.dp_dec[2 * (size_t)node + 0] = dec[0] | (dec[1] << 8) | (dec[2] << 16) | (dec[3] << 24);
+  c.dp_dec[2 * (size_t)node + 1] = dec[4] | (dec[5] << 8) | (dec[6] << 16) | (dec[7] << 24);
+}
+RB_HD uint32_t dp_decision(const BuildCtx& c, int node, int j) {  // decision byte of "j roots", j = 1..8
+  return (c.dp_dec[2 * (size_t)node + ((j - 1) >> 2)] >> (8 * ((j - 1) & 3))) & 0xFFu;
+}
+
 RB_HD void fit_body(const BuildCtx& c, uint32_t leaf) {
   int node = c.leaf_parent[leaf];
   while (node >= 0) {
@@ -224,18 +299,17 @@ RB_HD void fit_body(const BuildCtx& c, uint32_t leaf) {
     child_box(c, c.left[node], &alo, &ahi);
     child_box(c, c.right[node], &blo, &bhi);
 #endif
-    c.ibox_lo[node] = F4{fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0};
-    c.ibox_hi[node] = F4{fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0};
+    const F4 nlo = F4{fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0};
+    const F4 nhi = F4{fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0};
+    c.ibox_lo[node] = nlo;
+    c.ibox_hi[node] = nhi;
+    dp_node(c, node, alo, ahi, blo, bhi, nlo, nhi);
     node = c.parent[node];
   }
 }
 
 RB_HD int ref_count(const BuildCtx& c, int ref) { return ref < 0 ? 1 : (c.range_hi[ref] - c.range_lo[ref] + 1); }
 RB_HD int ref_first(const BuildCtx& c, int ref) { return ref < 0 ? ~ref : c.range_lo[ref]; }
-RB_HD float box_area(const F4& lo, const F4& hi) {
-  const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
-  return dx * dy + dy * dz + dz * dx;
-}
 // Child boxes are stored as 7-bit grid coordinates q in [0,127]; the traversal decodes a plane as
 // origin' + (128 + q) * step, where 128 + q is built directly as the float 0x43000000 | q << 16 (one byte
 // permute, no integer-to-float conversion). origin' = node_lo - 128 * step.
@@ -283,7 +357,7 @@ RB_HD void emit_node8(const BuildCtx& c, int out_index, const int* refs, int n_i
   int n_int = 0, n_leaf_tris = 0;
   for (int k = 0; k < n_items; ++k) {
     child_box(c, refs[k], &clo[k], &chi[k]);
-    internal[k] = refs[k] >= 0 && ref_count(c, refs[k]) > RB_LEAF_MAX;
+    internal[k] = refs[k] >= 0 && !(dp_decision(c, refs[k], 1) & 1u);
     if (internal[k])
       n_int++;
     else
@@ -322,12 +396,12 @@ RB_HD void emit_node8(const BuildCtx& c, int out_index, const int* refs, int n_i
   const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
   const float gox = grid_origin(nlo.x, sx), goy = grid_origin(nlo.y, sy), goz = grid_origin(nlo.z, sz);
   uint32_t imask = 0;
-  uint32_t meta[8], qlo[3][8], qhi[3][8];
+  uint32_t hitw[8], qlo[3][8], qhi[3][8];
   int int_cursor = 0, tri_cursor = 0;
   int q_base = 0;
   if (n_int) q_base = atomic_add_i(c.counters + 2, n_int);
   for (int s = 0; s < 8; ++s) {
-    meta[s] = 0;
+    hitw[s] = 0;
     for (int a = 0; a < 3; ++a) qlo[a][s] = qhi[a][s] = 0;
     const int k = child_in_slot[s];
     if (k < 0) continue;
@@ -346,47 +420,57 @@ RB_HD void emit_node8(const BuildCtx& c, int out_index, const int* refs, int n_i
     }
     if (internal[k]) {
       imask |= 1u << s;
-      meta[s] = (1u << 5) | (24u + (uint32_t)s);
+      hitw[s] = 1u << (24 + s);
       // children of this node occupy consecutive node8 indices in slot order
       c.q_out[2 * (q_base + int_cursor) + 0] = refs[k];
       c.q_out[2 * (q_base + int_cursor) + 1] = child_base + int_cursor;
       int_cursor++;
     } else {
       const int cnt = ref_count(c, refs[k]), first = ref_first(c, refs[k]);
-      meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)tri_cursor;
+      hitw[s] = ((1u << cnt) - 1u) << tri_cursor;
       for (int t = 0; t < cnt; ++t) write_tri(c, (uint32_t)(tri_base + tri_cursor + t), c.order[first + t]);
       tri_cursor += cnt;
     }
   }
-  F4* o = c.node8 + 5 * (size_t)out_index;
+  F4* o = c.node8 + RB_NODE_F4 * (size_t)out_index;
   o[0] = F4{gox, goy, goz, u2f(ex | (ey << 8) | (ez << 16) | (imask << 24))};
-  o[1] = F4{u2f((uint32_t)child_base), u2f((uint32_t)tri_base), u2f(pack4(meta)), u2f(pack4(meta + 4))};
+  o[1] = F4{u2f((uint32_t)child_base), u2f((uint32_t)tri_base), u2f(0u), u2f(0u)};
   o[2] = F4{u2f(pack4(qlo[0])), u2f(pack4(qlo[0] + 4)), u2f(pack4(qlo[1])), u2f(pack4(qlo[1] + 4))};
   o[3] = F4{u2f(pack4(qlo[2])), u2f(pack4(qlo[2] + 4)), u2f(pack4(qhi[0])), u2f(pack4(qhi[0] + 4))};
   o[4] = F4{u2f(pack4(qhi[1])), u2f(pack4(qhi[1] + 4)), u2f(pack4(qhi[2])), u2f(pack4(qhi[2] + 4))};
+  o[5] = F4{u2f(hitw[0]), u2f(hitw[1]), u2f(hitw[2]), u2f(hitw[3])};
+  o[6] = F4{u2f(hitw[4]), u2f(hitw[5]), u2f(hitw[6]), u2f(hitw[7])};
+  o[7] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
 }
 
 RB_HD void collapse_body(const BuildCtx& c, uint32_t w) {
   const int bnode = c.q_in[2 * w], out_index = c.q_in[2 * w + 1];
+  // the children of this wide node: follow distribute(bnode, 8) down to single roots
   int refs[8];
-  int n_items = 2;
-  refs[0] = c.left[bnode];
-  refs[1] = c.right[bnode];
-  while (n_items < 8) {
-    float best = -1.0f;
-    int bk = -1;
-    for (int k = 0; k < n_items; ++k) {
-      if (refs[k] < 0 || ref_count(c, refs[k]) <= RB_LEAF_MAX) continue;
-      const float a = box_area(c.ibox_lo[refs[k]], c.ibox_hi[refs[k]]);
-      if (a > best) {
-        best = a;
-        bk = k;
-      }
+  int n_items = 0;
+  int st_ref[16], st_budget[16];
+  int sp = 0;
+  {
+    const int k = (int)(dp_decision(c, bnode, 8) & 7u);
+    st_ref[sp] = c.right[bnode], st_budget[sp++] = 8 - k;
+    st_ref[sp] = c.left[bnode], st_budget[sp++] = k;
+  }
+  while (sp > 0) {
+    const int ref = st_ref[--sp];
+    int budget = st_budget[sp];
+    if (ref < 0) {
+      refs[n_items++] = ref;
+      continue;
     }
-    if (bk < 0) break;
-    const int r = refs[bk];
-    refs[bk] = c.left[r];
-    refs[n_items++] = c.right[r];
+    uint32_t d = 0;
+    while (budget > 1 && ((d = dp_decision(c, ref, budget)) & 0x80u)) budget--;
+    if (budget == 1) {
+      refs[n_items++] = ref;
+      continue;
+    }
+    const int k = (int)(d & 7u);
+    st_ref[sp] = c.right[ref], st_budget[sp++] = budget - k;
+    st_ref[sp] = c.left[ref], st_budget[sp++] = k;
   }
   emit_node8(c, out_index, refs, n_items, c.ibox_lo[bnode], c.ibox_hi[bnode]);
 }
@@ -401,14 +485,16 @@ RB_HD void tiny_root_body(const BuildCtx& c) {
   }
   const uint32_t ex = grid_exponent(hi.x - lo.x), ey = grid_exponent(hi.y - lo.y), ez = grid_exponent(hi.z - lo.z);
   for (uint32_t i = 0; i < c.n; ++i) write_tri(c, i, c.order[i]);
-  const uint32_t meta0 = (((1u << c.n) - 1u) << 5) | 0u;
   F4* o = c.node8;
   o[0] = F4{grid_origin(lo.x, u2f(ex << 23)), grid_origin(lo.y, u2f(ey << 23)), grid_origin(lo.z, u2f(ez << 23)),
             u2f(ex | (ey << 8) | (ez << 16))};
-  o[1] = F4{u2f(0u), u2f(0u), u2f(meta0), u2f(0u)};
+  o[1] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
   o[2] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
   o[3] = F4{u2f(0u), u2f(0u), u2f(127u), u2f(0u)};
   o[4] = F4{u2f(127u), u2f(0u), u2f(127u), u2f(0u)};
+  o[5] = F4{u2f((1u << c.n) - 1u), u2f(0u), u2f(0u), u2f(0u)};
+  o[6] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
+  o[7] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
   c.counters[0] = 1;
   c.counters[1] = (int)c.n;
 }

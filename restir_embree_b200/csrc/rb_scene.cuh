@@ -4,19 +4,22 @@
 // P/Intersection.h:43-83) plus the attribute fetch of getGeometryAttributes
 // (:85-113). B200 has no RT cores: this is ordinary SM code.
 //
-// Node8 (80 B = 5 x 16 B, AoSoA, 16-byte aligned):
+// Node8 (128 B = one cache line, 8 x 16 B, AoSoA; the traversal reads the first seven):
 //   n0 = { origin'.xyz, bits: ex | ey<<8 | ez<<16 | imask<<24 }   ex.. = biased exponents of the grid step
-//   n1 = { child_base, tri_base, meta[0..3], meta[4..7] }
+//   n1 = { child_base, tri_base, 0, 0 }
 //   n2 = { qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7] }
 //   n3 = { qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7] }
 //   n4 = { qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7] }
+//   n5 = { hit word of slot 0..3 }   n6 = { hit word of slot 4..7 }   n7 = unused
 // Child boxes are 7-bit grid coordinates q (one per byte), rounded outwards; a plane sits at
 // origin' + (128 + q) * step and the float 128 + q is assembled with ONE byte permute
 // (0x43000000 | q << 16) — no integer-to-float conversion on the quarter-rate pipe.
-// meta[s] of slot s: 0 = empty; internal child: (1<<5) | (24+s); leaf: (unary triangle count in
-// bits 5..7) | triangle offset (0..23). Children sit in slots chosen at build time so that
-// (slot ^ ray octant) orders them front to back (compressed-wide-BVH scheme of Ylitie, Karras &
-// Laine 2017).
+// The hit word of a slot is what a box hit ORs into the node's hit mask (one predicated LOP3 per child):
+// 0 = empty slot; internal child in slot s: 1 << (24 + s); leaf: (unary triangle count) << triangle offset
+// (offsets 0..23 within the node's triangle run). Children sit in slots chosen at build time so that
+// (slot ^ ray octant) orders them front to back (compressed-wide-BVH scheme of Ylitie, Karras & Laine 2017);
+// closest-hit rays apply that order to the internal hit byte with a 2 KB table (SceneDev::perm_lut), any-hit
+// rays take the slot order as it is (their result and, for unoccluded rays, their cost do not depend on it).
 #ifndef RB_SCENE_CUH_
 #define RB_SCENE_CUH_
 
@@ -27,11 +30,12 @@ namespace rb {
 #ifndef RB_LEAF_MAX
 #define RB_LEAF_MAX 3
 #endif
+#define RB_NODE_F4 8  // 16-byte records per node
 #define RB_STACK_MAX 48  // >= 2 * tree depth + 2: a node visit pushes at most a node group and a triangle group
 
 struct SceneDev {
   // geometry
-  const F4* node8;        // [5 * n_nodes]
+  const F4* node8;        // [RB_NODE_F4 * n_nodes]
   const F4* tri_isect;    // [3 * n_leaf_tris] leaf order: {v0.xyz,e1.x} {e1.y,e1.z,e2.x,e2.y} {e2.z,bits(tri id),0,0}
   const F4* tri_normals;  // [3 * n_tris] scene order: {n0.xyz,n1.x} {n1.y,n1.z,n2.x,n2.y} {n2.z,0,0,0}
   const U4* tri_info;     // [n_tris] scene order: {geomID, primID, material, emissive id (int, -1 none)}
@@ -45,6 +49,8 @@ struct SceneDev {
   uint32_t n_tris;
   uint32_t n_nodes;
   float total_area;
+  uint32_t q7_base;  // 0x43000000 (see q7f)
+  const uint8_t* perm_lut;  // [8 * 256]: perm_lut[o * 256 + x] has bit (s ^ o) set iff bit s of x is set
 };
 
 struct HitRec {
@@ -80,6 +86,23 @@ RB_HD bool tri_test(const V3& o, const V3& d, const F4& a, const F4& b, const F4
 }
 
 RB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+RB_HD uint32_t ldg_u8(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__ldg(p);
+#else
+  return (uint32_t)*p;
+#endif
+}
+// the child-order table: out[o * 256 + x] has bit (s ^ o) set iff bit s of x is set
+inline void fill_perm_lut(uint8_t* out) {
+  for (uint32_t o = 0; o < 8; ++o)
+    for (uint32_t x = 0; x < 256; ++x) {
+      uint32_t y = 0;
+      for (uint32_t b = 0; b < 8; ++b)
+        if ((x >> b) & 1u) y |= 1u << (b ^ o);
+      out[o * 256 + x] = (uint8_t)y;
+    }
+}
 RB_HD int bfind(uint32_t x) {  // index of the highest set bit, x != 0
 #if defined(__CUDA_ARCH__)
   return 31 - __clz((int)x);
@@ -94,17 +117,18 @@ RB_HD int popc(uint32_t x) {
   return __builtin_popcount(x);
 #endif
 }
-// 128 + (byte k of w) as a float, for 7-bit bytes
+// 128 + (byte k of w) as a float, for 7-bit bytes. c43 is SceneDev::q7_base = 0x43000000, read from the
+// kernel parameters: PRMT takes one immediate, and it should be the selector — with a literal constant the compiler
+// keeps the constant as the immediate and re-materialises the selector into a register before every permute
+// (~50 extra moves per node visit).
 template <int K>
-RB_HD float q7f(uint32_t w) {
+RB_HD float q7f(uint32_t w, uint32_t c43) {
 #if defined(__CUDA_ARCH__)
-  return __uint_as_float(__byte_perm(w, 0x43000000u, 0x7044u | (K << 8)));
+  return __uint_as_float(__byte_perm(w, c43, 0x7044u | (K << 8)));
 #else
-  return u2f(0x43000000u | (((w >> (8 * K)) & 0xFFu) << 16));
+  return u2f(c43 | (((w >> (8 * K)) & 0xFFu) << 16));
 #endif
 }
-// bits 0..3 of m -> bytes 0..3 set to 0xFF
-RB_HD uint32_t expand_nibble(uint32_t m) { return (((m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
 // Traversal state of one ray (registers + a per-thread stack).
 struct Trav {
@@ -149,14 +173,14 @@ RB_HD bool trav_init(Trav& T, const SceneDev& sc, const V3& o, const V3& d, floa
   return true;
 }
 
-#define RB_CHILD_TEST(I, WX0, WX1, WY0, WY1, WZ0, WZ1, MB, MI)                                    \
-  {                                                                                               \
-    const float t0x = fmaf_(q7f<(I)&3>(WX0), ax, bx), t1x = fmaf_(q7f<(I)&3>(WX1), ax, bx);       \
-    const float t0y = fmaf_(q7f<(I)&3>(WY0), ay, by), t1y = fmaf_(q7f<(I)&3>(WY1), ay, by);       \
-    const float t0z = fmaf_(q7f<(I)&3>(WZ0), az, bz), t1z = fmaf_(q7f<(I)&3>(WZ1), az, bz);       \
-    const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, T.tnear));                               \
-    const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tcull));                                 \
-    if (tmin <= tmax) hitmask |= byte_of(MB, (I)&3) << byte_of(MI, (I)&3);                        \
+#define RB_CHILD_TEST(I, WX0, WX1, WY0, WY1, WZ0, WZ1, HW)                                             \
+  {                                                                                                   \
+    const float t0x = fmaf_(q7f<(I)&3>(WX0, c43), ax, bx), t1x = fmaf_(q7f<(I)&3>(WX1, c43), ax, bx); \
+    const float t0y = fmaf_(q7f<(I)&3>(WY0, c43), ay, by), t1y = fmaf_(q7f<(I)&3>(WY1, c43), ay, by); \
+    const float t0z = fmaf_(q7f<(I)&3>(WZ0, c43), az, bz), t1z = fmaf_(q7f<(I)&3>(WZ1, c43), az, bz); \
+    const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, T.tnear));                                   \
+    const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tcull));                                     \
+    if (tmin <= tmax) hitmask |= f2u(HW);                                                             \
   }
 
 // ---- traversal primitives ---------------------------------------------------------------------------
@@ -169,15 +193,17 @@ RB_HD bool has_node_work(const Trav& T) { return T.ngroup.y > 0x00FFFFFFu; }
 // internal children in T.ngroup (pushing the remainder of the old group), returns the hit leaf triangles.
 template <bool ANY>
 RB_HD U2 trav_node_step(Trav& T, U2* stack, const SceneDev& sc) {
+  const uint32_t ord = ANY ? 0u : T.oct_inv;  // child order: slot ^ ord, highest first
   const uint32_t hits = T.ngroup.y;
   const int bit = bfind(hits);
   T.ngroup.y &= ~(1u << bit);
   if (T.ngroup.y > 0x00FFFFFFu) stack[T.sp++] = T.ngroup;
-  const uint32_t slot = ((uint32_t)(bit - 24)) ^ T.oct_inv;
+  const uint32_t slot = ((uint32_t)(bit - 24)) ^ ord;
   const uint32_t node_index = T.ngroup.x + popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
 
-  const F4* np = sc.node8 + 5 * (size_t)node_index;
-  const F4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4);
+  const F4* np = sc.node8 + RB_NODE_F4 * (size_t)node_index;
+  const F4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4), n5 = ldg4(np + 5),
+           n6 = ldg4(np + 6);
   const uint32_t ebits = f2u(n0.w);
   const uint32_t imask = ebits >> 24;
   const float ax = u2f(byte_of(ebits, 0) << 23) * T.idx, ay = u2f(byte_of(ebits, 1) << 23) * T.idy,
@@ -189,23 +215,21 @@ RB_HD U2 trav_node_step(Trav& T, U2* stack, const SceneDev& sc) {
   const uint32_t x0a = f2u(nx ? n3.z : n2.x), x0b = f2u(nx ? n3.w : n2.y), x1a = f2u(nx ? n2.x : n3.z), x1b = f2u(nx ? n2.y : n3.w);
   const uint32_t y0a = f2u(ny ? n4.x : n2.z), y0b = f2u(ny ? n4.y : n2.w), y1a = f2u(ny ? n2.z : n4.x), y1b = f2u(ny ? n2.w : n4.y);
   const uint32_t z0a = f2u(nz ? n4.z : n3.x), z0b = f2u(nz ? n4.w : n3.y), z1a = f2u(nz ? n3.x : n4.z), z1b = f2u(nz ? n3.y : n4.w);
-  // per-child hit-mask contribution: (meta >> 5) << ((meta & 31) ^ (internal ? oct_inv : 0)), 4 children per word
-  const uint32_t meta_a = f2u(n1.z), meta_b = f2u(n1.w);
-  const uint32_t oct4 = T.oct_inv * 0x01010101u;
-  const uint32_t mia = (meta_a ^ (oct4 & expand_nibble(imask))) & 0x1F1F1F1Fu;
-  const uint32_t mib = (meta_b ^ (oct4 & expand_nibble(imask >> 4))) & 0x1F1F1F1Fu;
-  const uint32_t mba = (meta_a >> 5) & 0x07070707u, mbb = (meta_b >> 5) & 0x07070707u;
   uint32_t hitmask = 0;
-  RB_CHILD_TEST(0, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
-  RB_CHILD_TEST(1, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
-  RB_CHILD_TEST(2, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
-  RB_CHILD_TEST(3, x0a, x1a, y0a, y1a, z0a, z1a, mba, mia)
-  RB_CHILD_TEST(4, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
-  RB_CHILD_TEST(5, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
-  RB_CHILD_TEST(6, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
-  RB_CHILD_TEST(7, x0b, x1b, y0b, y1b, z0b, z1b, mbb, mib)
+  const uint32_t c43 = sc.q7_base;
+  RB_CHILD_TEST(0, x0a, x1a, y0a, y1a, z0a, z1a, n5.x)
+  RB_CHILD_TEST(1, x0a, x1a, y0a, y1a, z0a, z1a, n5.y)
+  RB_CHILD_TEST(2, x0a, x1a, y0a, y1a, z0a, z1a, n5.z)
+  RB_CHILD_TEST(3, x0a, x1a, y0a, y1a, z0a, z1a, n5.w)
+  RB_CHILD_TEST(4, x0b, x1b, y0b, y1b, z0b, z1b, n6.x)
+  RB_CHILD_TEST(5, x0b, x1b, y0b, y1b, z0b, z1b, n6.y)
+  RB_CHILD_TEST(6, x0b, x1b, y0b, y1b, z0b, z1b, n6.z)
+  RB_CHILD_TEST(7, x0b, x1b, y0b, y1b, z0b, z1b, n6.w)
+  // internal hits arrive in slot order; closest-hit rays reorder them front to back
+  uint32_t ihits = hitmask >> 24;
+  if (!ANY && ihits != 0) ihits = ldg_u8(sc.perm_lut + (ord << 8) + ihits);
   T.ngroup.x = f2u(n1.x);
-  T.ngroup.y = (hitmask & 0xFF000000u) | imask;
+  T.ngroup.y = (ihits << 24) | imask;
   return U2{f2u(n1.y), hitmask & 0x00FFFFFFu};
 }
 

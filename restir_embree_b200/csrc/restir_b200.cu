@@ -59,19 +59,25 @@ RB_PIXEL_KERNEL(k_visibility, InlineVis, true, 1, visibility_pixel(fc, x, y, vis
 RB_PIXEL_KERNEL(k_temporal, InlineVis, true, 1, (temporal_pixel<InlineVis, false>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_temporal_banded, InlineVis, true, 1, (temporal_pixel<InlineVis, true>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_spatial, InlineVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_shade, InlineVis, true, 1, shade_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_shade, InlineVis, true, 4, shade_pixel(fc, x, y, vis, cnt))
 // wavefront halves
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 2, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_stream, GenVis, false, 1, (temporal_pixel<GenVis, false>(fc, x, y, vis, cnt)))
-RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 1, (temporal_pixel<ResolveVis, false>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_stream, GenVis, false, 2, (temporal_pixel<GenVis, false>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 2, (temporal_pixel<ResolveVis, false>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, false, 1, (temporal_pixel<GenVis, true>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_temporal_resolve_banded, ResolveVis, true, 1, (temporal_pixel<ResolveVis, true>(fc, x, y, vis, cnt)))
-RB_PIXEL_KERNEL(k_spatial_stream, GenVis, false, 1, spatial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial_stream, GenVis, false, 2, spatial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 2, spatial_pixel(fc, x, y, vis, cnt))
+// occupancy experiments (RB_OCC3=1): three resident CTAs per SM (<= 85 registers)
+RB_PIXEL_KERNEL(k_initial_resolve_o3, ResolveVis, true, 3, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial_stream_o3, GenVis, false, 3, spatial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial_resolve_o3, ResolveVis, true, 3, spatial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal_stream_o3, GenVis, false, 3, (temporal_pixel<GenVis, false>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_resolve_o3, ResolveVis, true, 3, (temporal_pixel<ResolveVis, false>(fc, x, y, vis, cnt)))
 
 // ---- persistent traversal kernels over the ray queue ------------------------------------------------
 // One ray per lane. Three things keep the warps full in this divergent workload:
@@ -285,6 +291,7 @@ struct RbContext {
   int numSMs = 148;
   // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
   int refillLanes = 26, postponeLanes = 8, traceBlocksPerSM = 8;
+  bool occ3 = false;  // RB_OCC3: use the 3-CTAs-per-SM instantiations of the streaming kernels
 
   // wavefront buffers
   WaveBufs wave{};
@@ -508,6 +515,7 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     if (const char* e = getenv("RB_REFILL")) h->refillLanes = atoi(e);
     if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
     if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
+    if (const char* e = getenv("RB_OCC3")) h->occ3 = atoi(e) != 0;
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
     RB_TRY(dev_alloc(h, &d, 1, h->allocs));
@@ -599,13 +607,16 @@ static int build_bvh(RbContext* h, const float* d_tri_pos, uint32_t n, float max
     RB_TRY(dev_alloc(h, &c.ibox_lo, n, tmp));
     RB_TRY(dev_alloc(h, &c.ibox_hi, n, tmp));
     RB_TRY(dev_alloc(h, &c.visit, n, tmp));
+    RB_TRY(dev_alloc(h, &c.dp_cost, 7 * (size_t)n, tmp));
+    RB_TRY(dev_alloc(h, &c.dp_dec, 2 * (size_t)n, tmp));
+    c.c_prim = RB_COLLAPSE_C_PRIM;
     RB_TRY(dev_alloc(h, &c.counters, 4, tmp));
     int* q[2] = {nullptr, nullptr};
     RB_TRY(dev_alloc(h, &q[0], 2 * (size_t)n + 2, tmp));
     RB_TRY(dev_alloc(h, &q[1], 2 * (size_t)n + 2, tmp));
     const size_t max_nodes = (size_t)n / 2 + 8;
     F4* node8_big = nullptr;
-    RB_TRY(dev_alloc(h, &node8_big, 5 * max_nodes, tmp));
+    RB_TRY(dev_alloc(h, &node8_big, RB_NODE_F4 * max_nodes, tmp));
     F4* tri_isect = nullptr;
     RB_TRY(dev_alloc(h, &tri_isect, 3 * (size_t)n, h->sceneAllocs));
     c.node8 = node8_big;
@@ -680,8 +691,8 @@ static int build_bvh(RbContext* h, const float* d_tri_pos, uint32_t n, float max
       return RB_ERR_UNSUPPORTED;
     }
     F4* node8 = nullptr;
-    RB_TRY(dev_alloc(h, &node8, 5 * (size_t)n_nodes, h->sceneAllocs));
-    RB_CUDA(cudaMemcpyAsync(node8, node8_big, 80 * (size_t)n_nodes, cudaMemcpyDeviceToDevice, h->stream));
+    RB_TRY(dev_alloc(h, &node8, RB_NODE_F4 * (size_t)n_nodes, h->sceneAllocs));
+    RB_CUDA(cudaMemcpyAsync(node8, node8_big, 16 * RB_NODE_F4 * (size_t)n_nodes, cudaMemcpyDeviceToDevice, h->stream));
     RB_CUDA(cudaStreamSynchronize(h->stream));
     *node8_out = node8;
     *tri_isect_out = tri_isect;
@@ -736,6 +747,10 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     RB_TRY(dev_alloc(h, &d_cdf, NL, h->sceneAllocs));
     RB_TRY(dev_alloc(h, &d_ap, NL, h->sceneAllocs));
     RB_TRY(dev_alloc(h, &d_ai, NL, h->sceneAllocs));
+    uint8_t* d_lut = nullptr;
+    RB_TRY(dev_alloc(h, &d_lut, 8 * 256, h->sceneAllocs));
+    uint8_t lut[8 * 256];
+    fill_perm_lut(lut);
     auto up = [&](void* d, const void* s, size_t bytes) -> cudaError_t {
       return bytes ? cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
     };
@@ -747,6 +762,7 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     RB_CUDA(up(d_cdf, cdf.data(), NL * 4));
     RB_CUDA(up(d_ap, alias_prob.data(), NL * 4));
     RB_CUDA(up(d_ai, alias_idx.data(), NL * 4));
+    RB_CUDA(up(d_lut, lut, sizeof(lut)));
     RB_CUDA(cudaStreamSynchronize(h->stream));
     F4 *node8 = nullptr, *tri_isect = nullptr;
     uint32_t n_nodes = 0, depth = 0;
@@ -770,6 +786,8 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     sc.n_tris = (uint32_t)n;
     sc.n_nodes = n_nodes;
     sc.total_area = totalSurface;
+    sc.q7_base = 0x43000000u;
+    sc.perm_lut = d_lut;
     RbSceneStats& st = h->stats;
     memset(&st, 0, sizeof(st));
     st.n_triangles = (uint32_t)n;
@@ -978,7 +996,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     }
     // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel
     if (P.doVisibilityPass)
-      launch_rows(h, k_initial_resolve, y0, y1);
+      launch_rows(h, h->occ3 ? k_initial_resolve_o3 : k_initial_resolve, y0, y1);
     else
       launch_rows(h, k_initial_resolve_inline_shadow, y0, y1);
   } else {
@@ -1008,13 +1026,13 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       if (banded)
         launch_rows(h, k_temporal_stream_banded, y0, y1);
       else
-        launch_rows(h, k_temporal_stream, y0, y1);
+        launch_rows(h, h->occ3 ? k_temporal_stream_o3 : k_temporal_stream, y0, y1);
       fs_mark(h, 3, 0);
       fs_trace(h, true, 3);
       if (banded)
         launch_rows(h, k_temporal_resolve_banded, y0, y1);
       else
-        launch_rows(h, k_temporal_resolve, y0, y1);
+        launch_rows(h, h->occ3 ? k_temporal_resolve_o3 : k_temporal_resolve, y0, y1);
     } else {
       if (banded)
         launch_rows(h, k_temporal_banded, y0, y1);
@@ -1046,15 +1064,16 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
   fc.frame_key = rng_frame_key(h->info.seed, F.frame_idx, PASS_SPATIAL, (uint32_t)i);
   if (F.wave_spatial) {
     fs_reset_queue(h);
-    launch_rows(h, k_spatial_stream, iy0, iy1);
+    auto kss = h->occ3 ? k_spatial_stream_o3 : k_spatial_stream;
+    launch_rows(h, kss, iy0, iy1);
     if (overlap_halo) {
       RB_TRY(halo_exchange_wait(h));
-      launch_rows(h, k_spatial_stream, y0, iy0);
-      launch_rows(h, k_spatial_stream, iy1, y1);
+      launch_rows(h, kss, y0, iy0);
+      launch_rows(h, kss, iy1, y1);
     }
     fs_mark(h, 4, 0);
     fs_trace(h, true, 4);
-    launch_rows(h, k_spatial_resolve, y0, y1);
+    launch_rows(h, h->occ3 ? k_spatial_resolve_o3 : k_spatial_resolve, y0, y1);
   } else {
     launch_rows(h, k_spatial, iy0, iy1);
     if (overlap_halo) {

@@ -29,6 +29,7 @@ struct Emu {
   RbParams P{};
   HostScene hs;
   std::vector<F4> node8, tri_isect;
+  std::vector<uint8_t> perm_lut;
   uint32_t n_nodes = 0, depth = 0;
   SceneDev sc{};
   bool haveScene = false, havePrev = false;
@@ -76,10 +77,14 @@ static int emu_build_bvh(Emu* E) {
   c.morton = morton.data(), c.order = order.data();
   c.left = left.data(), c.right = right.data(), c.parent = parent.data(), c.leaf_parent = leaf_parent.data();
   c.range_lo = rlo.data(), c.range_hi = rhi.data(), c.ibox_lo = ilo.data(), c.ibox_hi = ihi.data(), c.visit = visit.data();
+  std::vector<float> dp_cost(7 * (size_t)n);
+  std::vector<uint32_t> dp_dec(2 * (size_t)n);
+  c.dp_cost = dp_cost.data(), c.dp_dec = dp_dec.data();
+  c.c_prim = getenv("EMU_CPRIM") ? (float)atof(getenv("EMU_CPRIM")) : RB_COLLAPSE_C_PRIM;
   int counters[4] = {1, 0, 0, 0};
   c.counters = counters;
   const size_t max_nodes = (size_t)n / 2 + 8;
-  std::vector<F4> node8(5 * max_nodes);
+  std::vector<F4> node8(RB_NODE_F4 * max_nodes);
   E->tri_isect.assign(3 * (size_t)n, F4{0, 0, 0, 0});
   c.node8 = node8.data();
   c.tri_isect = E->tri_isect.data();
@@ -207,7 +212,7 @@ static int emu_build_bvh(Emu* E) {
     if ((uint32_t)counters[1] != n) return -2;
   }
   if (2 * depth + 2 > RB_STACK_MAX) return -4;
-  node8.resize(5 * (size_t)n_nodes);
+  node8.resize(RB_NODE_F4 * (size_t)n_nodes);
   E->node8 = node8;
   E->n_nodes = n_nodes;
   E->depth = depth;
@@ -260,6 +265,10 @@ int emu_upload_scene(void* h, const RbSceneDesc* sd) {
   sc.n_tris = (uint32_t)E->hs.n;
   sc.n_nodes = E->n_nodes;
   sc.total_area = E->hs.totalSurface;
+  sc.q7_base = 0x43000000u;
+  E->perm_lut.resize(8 * 256);
+  fill_perm_lut(E->perm_lut.data());
+  sc.perm_lut = E->perm_lut.data();
   E->haveScene = true;
   E->havePrev = false;
   return 0;
@@ -590,18 +599,20 @@ int emu_validate_bvh(void* h) {
   while (!st.empty()) {
     Item it = st.back();
     st.pop_back();
-    const F4* np = E->node8.data() + 5 * (size_t)it.node;
+    const F4* np = E->node8.data() + RB_NODE_F4 * (size_t)it.node;
     const uint32_t eb = f2u(np[0].w), imask = eb >> 24;
     const float org[3] = {np[0].x, np[0].y, np[0].z};
     const float sc3[3] = {u2f(byte_of(eb, 0) << 23), u2f(byte_of(eb, 1) << 23), u2f(byte_of(eb, 2) << 23)};
     const uint32_t child_base = f2u(np[1].x), tri_base = f2u(np[1].y);
-    const uint32_t metaw[2] = {f2u(np[1].z), f2u(np[1].w)};
+    const uint32_t hitw[8] = {f2u(np[5].x), f2u(np[5].y), f2u(np[5].z), f2u(np[5].w),
+                              f2u(np[6].x), f2u(np[6].y), f2u(np[6].z), f2u(np[6].w)};
     const uint32_t q[6][2] = {{f2u(np[2].x), f2u(np[2].y)}, {f2u(np[2].z), f2u(np[2].w)}, {f2u(np[3].x), f2u(np[3].y)},
                               {f2u(np[3].z), f2u(np[3].w)}, {f2u(np[4].x), f2u(np[4].y)}, {f2u(np[4].z), f2u(np[4].w)}};
     int rel = 0;
+    uint32_t tri_bits_seen = 0;
     for (int s = 0; s < 8; ++s) {
-      const uint32_t meta = byte_of(metaw[s >> 2], s & 3);
-      if (!meta) {
+      const uint32_t hw = hitw[s];
+      if (!hw) {
         if ((imask >> s) & 1) return 10;
         continue;
       }
@@ -616,16 +627,19 @@ int emu_validate_bvh(void* h) {
         if (lo[a] > hi[a]) return 11;
       }
       if ((imask >> s) & 1) {
-        if ((meta & 31u) != 24u + (uint32_t)s || (meta >> 5) != 1u) return 12;
+        if (hw != (1u << (24 + s))) return 12;
         Item ch;
         ch.node = child_base + rel++;
         if (ch.node >= E->n_nodes) return 13;
         memcpy(ch.lo, lo, 12), memcpy(ch.hi, hi, 12);
         st.push_back(ch);
       } else {
-        const uint32_t off = meta & 31u, un = meta >> 5;
-        const int cnt = un == 1 ? 1 : un == 3 ? 2 : un == 7 ? 3 : -1;
-        if (cnt < 0 || off + cnt > 24) return 14;
+        // a leaf's hit word: a run of 1..3 one-bits inside the low 24 bits, disjoint from the other leaves' runs
+        if (hw >> 24) return 14;
+        if (hw & tri_bits_seen) return 19;
+        tri_bits_seen |= hw;
+        const int off = __builtin_ctz(hw), cnt = __builtin_popcount(hw);
+        if (cnt > RB_LEAF_MAX || hw != (((1u << cnt) - 1u) << off)) return 14;
         for (int t = 0; t < cnt; ++t) {
           const F4* tp = E->tri_isect.data() + 3 * (size_t)(tri_base + off + t);
           const uint32_t id = f2u(tp[2].y);

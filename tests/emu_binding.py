@@ -19,7 +19,7 @@ def build_emu(force=False):
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-fPIC",
-                           "-std=c++17", "-x", "c++", "-shared", "-o", LIB_PATH, SRC])
+                           "-std=c++17", "-DRB_TRAV_STATS", "-x", "c++", "-shared", "-o", LIB_PATH, SRC])
 
 
 _lib = None
