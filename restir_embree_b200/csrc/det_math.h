@@ -165,6 +165,18 @@ DM_HD double exp_(double x) {
 
 // ---- float-facing functions -------------------------------------------------
 
+// x^n for finite x > 0 and an integer 1 <= n <= 2048
+DM_HD float powi_(float x, uint32_t n) {
+  double b = (double)x, r = 1.0;
+  while (true) {
+    if (n & 1u) r *= b;
+    n >>= 1;
+    if (n == 0) break;
+    b *= b;
+  }
+  return (float)r;
+}
+
 // std::pow(float,float) for x >= 0 (the only domain the path uses).
 DM_HD float powf_(float x, float y) {
   if (y == 0.0f) return 1.0f;
@@ -176,6 +188,13 @@ DM_HD float powf_(float x, float y) {
   if (x == finf) return y > 0.0f ? finf : 0.0f;
   if (y == finf) return x < 1.0f ? 0.0f : finf;
   if (y == -finf) return x < 1.0f ? finf : 0.0f;
+  // Integer exponents 1..2048 (Phong shininess values: MTL "Ns" is integral in practice, P/MaterialPhong.cpp:144):
+  // binary exponentiation in double — at most 22 multiplies, relative error <= y * 2^-53, i.e. the correctly rounded
+  // float except in ~1e-6 of the cases. Overflow gives +inf and underflow 0 exactly where the float result is that.
+  if (y >= 1.0f && y <= 2048.0f) {
+    const uint32_t n = (uint32_t)y;
+    if ((float)n == y) return powi_(x, n);
+  }
   double l = log_pos((double)x);  // float denormals are normal doubles
   return (float)exp_((double)y * l);
 }

@@ -396,12 +396,14 @@ RB_HD void emit_node8(const BuildCtx& c, int out_index, const int* refs, int n_i
   const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
   const float gox = grid_origin(nlo.x, sx), goy = grid_origin(nlo.y, sy), goz = grid_origin(nlo.z, sz);
   uint32_t imask = 0;
-  uint32_t hitw[8], qlo[3][8], qhi[3][8];
+  uint32_t half[8], qlo[3][8], qhi[3][8];
+  int tri_shift = 0;  // triangles in slots 0..3
   int int_cursor = 0, tri_cursor = 0;
   int q_base = 0;
   if (n_int) q_base = atomic_add_i(c.counters + 2, n_int);
   for (int s = 0; s < 8; ++s) {
-    hitw[s] = 0;
+    half[s] = 0;
+    if (s == 4) tri_shift = tri_cursor;
     for (int a = 0; a < 3; ++a) qlo[a][s] = qhi[a][s] = 0;
     const int k = child_in_slot[s];
     if (k < 0) continue;
@@ -420,27 +422,26 @@ RB_HD void emit_node8(const BuildCtx& c, int out_index, const int* refs, int n_i
     }
     if (internal[k]) {
       imask |= 1u << s;
-      hitw[s] = 1u << (24 + s);
+      half[s] = 1u << (12 + (s & 3));
       // children of this node occupy consecutive node8 indices in slot order
       c.q_out[2 * (q_base + int_cursor) + 0] = refs[k];
       c.q_out[2 * (q_base + int_cursor) + 1] = child_base + int_cursor;
       int_cursor++;
     } else {
       const int cnt = ref_count(c, refs[k]), first = ref_first(c, refs[k]);
-      hitw[s] = ((1u << cnt) - 1u) << tri_cursor;
+      half[s] = ((1u << cnt) - 1u) << (tri_cursor - (s >= 4 ? tri_shift : 0));
       for (int t = 0; t < cnt; ++t) write_tri(c, (uint32_t)(tri_base + tri_cursor + t), c.order[first + t]);
       tri_cursor += cnt;
     }
   }
   F4* o = c.node8 + RB_NODE_F4 * (size_t)out_index;
   o[0] = F4{gox, goy, goz, u2f(ex | (ey << 8) | (ez << 16) | (imask << 24))};
-  o[1] = F4{u2f((uint32_t)child_base), u2f((uint32_t)tri_base), u2f(0u), u2f(0u)};
+  o[1] = F4{u2f((uint32_t)child_base), u2f((uint32_t)tri_base), u2f((uint32_t)tri_shift), u2f(0u)};
   o[2] = F4{u2f(pack4(qlo[0])), u2f(pack4(qlo[0] + 4)), u2f(pack4(qlo[1])), u2f(pack4(qlo[1] + 4))};
   o[3] = F4{u2f(pack4(qlo[2])), u2f(pack4(qlo[2] + 4)), u2f(pack4(qhi[0])), u2f(pack4(qhi[0] + 4))};
   o[4] = F4{u2f(pack4(qhi[1])), u2f(pack4(qhi[1] + 4)), u2f(pack4(qhi[2])), u2f(pack4(qhi[2] + 4))};
-  o[5] = F4{u2f(hitw[0]), u2f(hitw[1]), u2f(hitw[2]), u2f(hitw[3])};
-  o[6] = F4{u2f(hitw[4]), u2f(hitw[5]), u2f(hitw[6]), u2f(hitw[7])};
-  o[7] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
+  o[5] = F4{u2f(half[0] | (half[4] << 16)), u2f(half[1] | (half[5] << 16)), u2f(half[2] | (half[6] << 16)),
+            u2f(half[3] | (half[7] << 16))};
 }
 
 RB_HD void collapse_body(const BuildCtx& c, uint32_t w) {
@@ -488,13 +489,11 @@ RB_HD void tiny_root_body(const BuildCtx& c) {
   F4* o = c.node8;
   o[0] = F4{grid_origin(lo.x, u2f(ex << 23)), grid_origin(lo.y, u2f(ey << 23)), grid_origin(lo.z, u2f(ez << 23)),
             u2f(ex | (ey << 8) | (ez << 16))};
-  o[1] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
+  o[1] = F4{u2f(0u), u2f(0u), u2f(c.n), u2f(0u)};
   o[2] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
   o[3] = F4{u2f(0u), u2f(0u), u2f(127u), u2f(0u)};
   o[4] = F4{u2f(127u), u2f(0u), u2f(127u), u2f(0u)};
   o[5] = F4{u2f((1u << c.n) - 1u), u2f(0u), u2f(0u), u2f(0u)};
-  o[6] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
-  o[7] = F4{u2f(0u), u2f(0u), u2f(0u), u2f(0u)};
   c.counters[0] = 1;
   c.counters[1] = (int)c.n;
 }

@@ -4,22 +4,24 @@
 // P/Intersection.h:43-83) plus the attribute fetch of getGeometryAttributes
 // (:85-113). B200 has no RT cores: this is ordinary SM code.
 //
-// Node8 (128 B = one cache line, 8 x 16 B, AoSoA; the traversal reads the first seven):
-//   n0 = { origin'.xyz, bits: ex | ey<<8 | ez<<16 | imask<<24 }   ex.. = biased exponents of the grid step
-//   n1 = { child_base, tri_base, 0, 0 }
-//   n2 = { qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7] }
-//   n3 = { qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7] }
-//   n4 = { qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7] }
-//   n5 = { hit word of slot 0..3 }   n6 = { hit word of slot 4..7 }   n7 = unused
-// Child boxes are 7-bit grid coordinates q (one per byte), rounded outwards; a plane sits at
-// origin' + (128 + q) * step and the float 128 + q is assembled with ONE byte permute
+// Node8 (96 B = three 32-byte records, each fetched with ONE 256-bit load — LDG.E.ENL2.256, new on sm_100):
+//   r0 = { origin'.xyz, bits: ex | ey<<8 | ez<<16 | imask<<24 | child_base, tri_base, tri_shift, 0 }
+//   r1 = { qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7] | qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7] }
+//   r2 = { qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7] | hit halves: word k = half(slot k) | half(slot k+4) << 16 }
+// ex.. = biased exponents of the grid step. Child boxes are 7-bit grid coordinates q (one per byte), rounded
+// outwards; a plane sits at origin' + (128 + q) * step and the float 128 + q is assembled with ONE byte permute
 // (0x43000000 | q << 16) — no integer-to-float conversion on the quarter-rate pipe.
-// The hit word of a slot is what a box hit ORs into the node's hit mask (one predicated LOP3 per child):
-// 0 = empty slot; internal child in slot s: 1 << (24 + s); leaf: (unary triangle count) << triangle offset
-// (offsets 0..23 within the node's triangle run). Children sit in slots chosen at build time so that
-// (slot ^ ray octant) orders them front to back (compressed-wide-BVH scheme of Ylitie, Karras & Laine 2017);
-// closest-hit rays apply that order to the internal hit byte with a 2 KB table (SceneDev::perm_lut), any-hit
-// rays take the slot order as it is (their result and, for unoccluded rays, their cost do not depend on it).
+// The 16-bit hit half of a slot is what a box hit ORs into the node's hit accumulator (one LOP3 per child):
+// 0 = empty slot; internal child in slot s: 1 << (12 + (s & 3)); leaf: (unary triangle count) << offset, the
+// offset counted within the slot's group of four (0..9), so that
+//   triangle bits = (acc & 0xFFF) | ((acc >> 16 & 0xFFF) << tri_shift),   tri_shift = triangles in slots 0..3
+//   internal hits = (acc >> 12 & 0xF) | (acc >> 28) << 4                  (slot order)
+// Children sit in slots chosen at build time so that (slot ^ ray octant) orders them front to back (compressed-
+// wide-BVH scheme of Ylitie, Karras & Laine 2017); the internal hit byte is put into that order with three
+// conditional bit swaps (perm8) — no table, no memory access.
+// Why this shape: the traversal kernels are bound by the L1 data pipe (wavefronts = load instructions x distinct
+// lines, profiles/), so a node visit is three loads, and by the half-rate ALU pipe, so the hit mask costs ~2 ops
+// per child instead of 7.
 #ifndef RB_SCENE_CUH_
 #define RB_SCENE_CUH_
 
@@ -30,7 +32,7 @@ namespace rb {
 #ifndef RB_LEAF_MAX
 #define RB_LEAF_MAX 3
 #endif
-#define RB_NODE_F4 8  // 16-byte records per node
+#define RB_NODE_F4 6  // 16-byte records per node (96 B)
 #define RB_STACK_MAX 48  // >= 2 * tree depth + 2: a node visit pushes at most a node group and a triangle group
 
 struct SceneDev {
@@ -50,7 +52,6 @@ struct SceneDev {
   uint32_t n_nodes;
   float total_area;
   uint32_t q7_base;  // 0x43000000 (see q7f)
-  const uint8_t* perm_lut;  // [8 * 256]: perm_lut[o * 256 + x] has bit (s ^ o) set iff bit s of x is set
 };
 
 struct HitRec {
@@ -86,22 +87,22 @@ RB_HD bool tri_test(const V3& o, const V3& d, const F4& a, const F4& b, const F4
 }
 
 RB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
-RB_HD uint32_t ldg_u8(const uint8_t* p) {
-#if defined(__CUDA_ARCH__)
-  return (uint32_t)__ldg(p);
-#else
-  return (uint32_t)*p;
-#endif
+// x permuted so that bit (s ^ o) of the result is bit s of x (8-bit x, 3-bit o)
+RB_HD uint32_t perm8(uint32_t x, uint32_t o) {
+  if (o & 4u) x = ((x << 4) | (x >> 4)) & 0xFFu;
+  if (o & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+  if (o & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+  return x;
 }
-// the child-order table: out[o * 256 + x] has bit (s ^ o) set iff bit s of x is set
-inline void fill_perm_lut(uint8_t* out) {
-  for (uint32_t o = 0; o < 8; ++o)
-    for (uint32_t x = 0; x < 256; ++x) {
-      uint32_t y = 0;
-      for (uint32_t b = 0; b < 8; ++b)
-        if ((x >> b) & 1u) y |= 1u << (b ^ o);
-      out[o * 256 + x] = (uint8_t)y;
-    }
+struct alignas(32) F8 {
+  F4 a, b;
+};
+RB_HD F8 ldg8(const F4* p) {  // 32-byte aligned
+#if defined(__CUDA_ARCH__)
+  return *reinterpret_cast<const F8*>(__builtin_assume_aligned(p, 32));
+#else
+  return F8{p[0], p[1]};
+#endif
 }
 RB_HD int bfind(uint32_t x) {  // index of the highest set bit, x != 0
 #if defined(__CUDA_ARCH__)
@@ -180,7 +181,7 @@ RB_HD bool trav_init(Trav& T, const SceneDev& sc, const V3& o, const V3& d, floa
     const float t0z = fmaf_(q7f<(I)&3>(WZ0, c43), az, bz), t1z = fmaf_(q7f<(I)&3>(WZ1, c43), az, bz); \
     const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, T.tnear));                                   \
     const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tcull));                                     \
-    if (tmin <= tmax) hitmask |= f2u(HW);                                                             \
+    if (tmin <= tmax) acc |= f2u(HW) & ((I) < 4 ? 0x0000FFFFu : 0xFFFF0000u);                         \
   }
 
 // ---- traversal primitives ---------------------------------------------------------------------------
@@ -193,17 +194,16 @@ RB_HD bool has_node_work(const Trav& T) { return T.ngroup.y > 0x00FFFFFFu; }
 // internal children in T.ngroup (pushing the remainder of the old group), returns the hit leaf triangles.
 template <bool ANY>
 RB_HD U2 trav_node_step(Trav& T, U2* stack, const SceneDev& sc) {
-  const uint32_t ord = ANY ? 0u : T.oct_inv;  // child order: slot ^ ord, highest first
   const uint32_t hits = T.ngroup.y;
   const int bit = bfind(hits);
   T.ngroup.y &= ~(1u << bit);
   if (T.ngroup.y > 0x00FFFFFFu) stack[T.sp++] = T.ngroup;
-  const uint32_t slot = ((uint32_t)(bit - 24)) ^ ord;
+  const uint32_t slot = ((uint32_t)(bit - 24)) ^ T.oct_inv;
   const uint32_t node_index = T.ngroup.x + popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
 
   const F4* np = sc.node8 + RB_NODE_F4 * (size_t)node_index;
-  const F4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3), n4 = ldg4(np + 4), n5 = ldg4(np + 5),
-           n6 = ldg4(np + 6);
+  const F8 r0 = ldg8(np), r1 = ldg8(np + 2), r2 = ldg8(np + 4);
+  const F4 &n0 = r0.a, &n1 = r0.b, &n2 = r1.a, &n3 = r1.b, &n4 = r2.a, &n5 = r2.b;
   const uint32_t ebits = f2u(n0.w);
   const uint32_t imask = ebits >> 24;
   const float ax = u2f(byte_of(ebits, 0) << 23) * T.idx, ay = u2f(byte_of(ebits, 1) << 23) * T.idy,
@@ -215,22 +215,21 @@ RB_HD U2 trav_node_step(Trav& T, U2* stack, const SceneDev& sc) {
   const uint32_t x0a = f2u(nx ? n3.z : n2.x), x0b = f2u(nx ? n3.w : n2.y), x1a = f2u(nx ? n2.x : n3.z), x1b = f2u(nx ? n2.y : n3.w);
   const uint32_t y0a = f2u(ny ? n4.x : n2.z), y0b = f2u(ny ? n4.y : n2.w), y1a = f2u(ny ? n2.z : n4.x), y1b = f2u(ny ? n2.w : n4.y);
   const uint32_t z0a = f2u(nz ? n4.z : n3.x), z0b = f2u(nz ? n4.w : n3.y), z1a = f2u(nz ? n3.x : n4.z), z1b = f2u(nz ? n3.y : n4.w);
-  uint32_t hitmask = 0;
+  uint32_t acc = 0;
   const uint32_t c43 = sc.q7_base;
   RB_CHILD_TEST(0, x0a, x1a, y0a, y1a, z0a, z1a, n5.x)
   RB_CHILD_TEST(1, x0a, x1a, y0a, y1a, z0a, z1a, n5.y)
   RB_CHILD_TEST(2, x0a, x1a, y0a, y1a, z0a, z1a, n5.z)
   RB_CHILD_TEST(3, x0a, x1a, y0a, y1a, z0a, z1a, n5.w)
-  RB_CHILD_TEST(4, x0b, x1b, y0b, y1b, z0b, z1b, n6.x)
-  RB_CHILD_TEST(5, x0b, x1b, y0b, y1b, z0b, z1b, n6.y)
-  RB_CHILD_TEST(6, x0b, x1b, y0b, y1b, z0b, z1b, n6.z)
-  RB_CHILD_TEST(7, x0b, x1b, y0b, y1b, z0b, z1b, n6.w)
-  // internal hits arrive in slot order; closest-hit rays reorder them front to back
-  uint32_t ihits = hitmask >> 24;
-  if (!ANY && ihits != 0) ihits = ldg_u8(sc.perm_lut + (ord << 8) + ihits);
+  RB_CHILD_TEST(4, x0b, x1b, y0b, y1b, z0b, z1b, n5.x)
+  RB_CHILD_TEST(5, x0b, x1b, y0b, y1b, z0b, z1b, n5.y)
+  RB_CHILD_TEST(6, x0b, x1b, y0b, y1b, z0b, z1b, n5.z)
+  RB_CHILD_TEST(7, x0b, x1b, y0b, y1b, z0b, z1b, n5.w)
+  const uint32_t tri_bits = (acc & 0xFFFu) | (((acc >> 16) & 0xFFFu) << (f2u(n1.z) & 31u));
+  const uint32_t ihits = perm8(((acc >> 12) & 0xFu) | ((acc >> 28) << 4), T.oct_inv);  // front to back
   T.ngroup.x = f2u(n1.x);
   T.ngroup.y = (ihits << 24) | imask;
-  return U2{f2u(n1.y), hitmask & 0x00FFFFFFu};
+  return U2{f2u(n1.y), tri_bits};
 }
 
 // Test ONE triangle of a triangle group (clears its bit). Returns true when the ray is finished by it (ANY hit).

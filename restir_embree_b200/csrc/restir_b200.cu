@@ -92,8 +92,11 @@ RB_PIXEL_KERNEL(k_temporal_resolve_o3, ResolveVis, true, 3, (temporal_pixel<Reso
 // Grid = SM count x resident blocks, sized by the host.
 constexpr int kTraceThreads = 128;
 
+#ifndef RB_TRACE_MINB
+#define RB_TRACE_MINB 8
+#endif
 template <bool ANY>
-__global__ void __launch_bounds__(kTraceThreads) k_trace_queue(SceneDev sc, const RayQ* __restrict__ rays,
+__global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(SceneDev sc, const RayQ* __restrict__ rays,
                                                                const uint32_t* __restrict__ count_ptr, uint32_t capacity,
                                                                uint32_t* __restrict__ next, uint8_t* __restrict__ occ,
                                                                HitRec* __restrict__ hits, float tnear, int refill_lanes,
@@ -747,10 +750,7 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     RB_TRY(dev_alloc(h, &d_cdf, NL, h->sceneAllocs));
     RB_TRY(dev_alloc(h, &d_ap, NL, h->sceneAllocs));
     RB_TRY(dev_alloc(h, &d_ai, NL, h->sceneAllocs));
-    uint8_t* d_lut = nullptr;
-    RB_TRY(dev_alloc(h, &d_lut, 8 * 256, h->sceneAllocs));
-    uint8_t lut[8 * 256];
-    fill_perm_lut(lut);
+
     auto up = [&](void* d, const void* s, size_t bytes) -> cudaError_t {
       return bytes ? cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
     };
@@ -762,7 +762,6 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     RB_CUDA(up(d_cdf, cdf.data(), NL * 4));
     RB_CUDA(up(d_ap, alias_prob.data(), NL * 4));
     RB_CUDA(up(d_ai, alias_idx.data(), NL * 4));
-    RB_CUDA(up(d_lut, lut, sizeof(lut)));
     RB_CUDA(cudaStreamSynchronize(h->stream));
     F4 *node8 = nullptr, *tri_isect = nullptr;
     uint32_t n_nodes = 0, depth = 0;
@@ -787,7 +786,6 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     sc.n_nodes = n_nodes;
     sc.total_area = totalSurface;
     sc.q7_base = 0x43000000u;
-    sc.perm_lut = d_lut;
     RbSceneStats& st = h->stats;
     memset(&st, 0, sizeof(st));
     st.n_triangles = (uint32_t)n;

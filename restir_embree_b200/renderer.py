@@ -31,10 +31,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    lib_path = os.environ.get("RB_LIB", LIB_PATH)  # RB_LIB: an experimental build of the same CUDA sources
+    if not os.path.exists(lib_path):
         raise RestirError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(nvcc, sm_100a). This package has no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(lib_path)
     H = C.c_void_p
     L.rb_abi_version.restype = C.c_uint32
     L.rb_last_error.restype = C.c_char_p

@@ -29,7 +29,6 @@ struct Emu {
   RbParams P{};
   HostScene hs;
   std::vector<F4> node8, tri_isect;
-  std::vector<uint8_t> perm_lut;
   uint32_t n_nodes = 0, depth = 0;
   SceneDev sc{};
   bool haveScene = false, havePrev = false;
@@ -266,9 +265,6 @@ int emu_upload_scene(void* h, const RbSceneDesc* sd) {
   sc.n_nodes = E->n_nodes;
   sc.total_area = E->hs.totalSurface;
   sc.q7_base = 0x43000000u;
-  E->perm_lut.resize(8 * 256);
-  fill_perm_lut(E->perm_lut.data());
-  sc.perm_lut = E->perm_lut.data();
   E->haveScene = true;
   E->havePrev = false;
   return 0;
@@ -604,8 +600,23 @@ int emu_validate_bvh(void* h) {
     const float org[3] = {np[0].x, np[0].y, np[0].z};
     const float sc3[3] = {u2f(byte_of(eb, 0) << 23), u2f(byte_of(eb, 1) << 23), u2f(byte_of(eb, 2) << 23)};
     const uint32_t child_base = f2u(np[1].x), tri_base = f2u(np[1].y);
-    const uint32_t hitw[8] = {f2u(np[5].x), f2u(np[5].y), f2u(np[5].z), f2u(np[5].w),
-                              f2u(np[6].x), f2u(np[6].y), f2u(np[6].z), f2u(np[6].w)};
+    const uint32_t tri_shift = f2u(np[1].z);
+    uint32_t hitw[8];  // per-slot hit word in the traversal's hit-mask layout: internal 1 << (24 + s), leaf tri bits
+    {
+      const uint32_t pw[4] = {f2u(np[5].x), f2u(np[5].y), f2u(np[5].z), f2u(np[5].w)};
+      uint32_t low_tris = 0;
+      for (int s = 0; s < 8; ++s) {
+        const uint32_t half = (pw[s & 3] >> (s < 4 ? 0 : 16)) & 0xFFFFu;
+        if (half >> 12) {
+          if (half != (1u << (12 + (s & 3)))) return 20;
+          hitw[s] = 1u << (24 + s);
+        } else {
+          hitw[s] = s < 4 ? half : half << tri_shift;
+          if (s < 4) low_tris += (uint32_t)__builtin_popcount(half);
+        }
+      }
+      if (low_tris != tri_shift && (hitw[4] | hitw[5] | hitw[6] | hitw[7]) & 0xFFFFFFu) return 21;
+    }
     const uint32_t q[6][2] = {{f2u(np[2].x), f2u(np[2].y)}, {f2u(np[2].z), f2u(np[2].w)}, {f2u(np[3].x), f2u(np[3].y)},
                               {f2u(np[3].z), f2u(np[3].w)}, {f2u(np[4].x), f2u(np[4].y)}, {f2u(np[4].z), f2u(np[4].w)}};
     int rel = 0;

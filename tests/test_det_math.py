@@ -27,6 +27,22 @@ def test_pow():
     assert L.orc_dm_pow(0.0, 0.0) == 1.0 and L.orc_dm_pow(0.5, float("inf")) == 0.0
 
 
+def test_pow_integer_exponents():
+    """Integral exponents (Phong shininess) take the binary-exponentiation path of powf_."""
+    L = ob.lib()
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.random(20000, dtype=np.float32), (1 - rng.random(5000) * 1e-3).astype(np.float32),
+                        (rng.random(2000) * 1e-6).astype(np.float32)])
+    n = rng.choice(np.array([1, 2, 3, 5, 7, 10, 20, 33, 80, 127, 250, 500, 1000, 2048]), x.shape[0]).astype(np.float32)
+    got = np.array([L.orc_dm_pow(float(a), float(b)) for a, b in zip(x, n)], dtype=np.float32)
+    with np.errstate(under="ignore"):
+        ref = np.power(x.astype(np.float64), n.astype(np.float64)).astype(np.float32)
+    u = _ulps(got, ref)
+    assert u.max() <= 1 and (u > 0).mean() < 1e-4
+    assert L.orc_dm_pow(0.999, 1.0) == np.float32(0.999) and L.orc_dm_pow(2.0, 10.0) == 1024.0
+    assert L.orc_dm_pow(1e-30, 250.0) == 0.0 and L.orc_dm_pow(3e38, 2048.0) == float("inf")
+
+
 def test_sin_cos():
     L = ob.lib()
     rng = np.random.default_rng(2)
