@@ -62,6 +62,13 @@ RB_HD float fdiv_(float a, float b) {
   return a / b;
 #endif
 }
+RB_HD float frcp_(float x) {  // 1.0f / x, correctly rounded (same bits as the division, shorter on the device)
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
 RB_HD float fabsf_(float x) { return dm::u2f(dm::f2u(x) & 0x7FFFFFFFu); }
 RB_HD uint32_t f2u(float x) { return dm::f2u(x); }
 RB_HD float u2f(uint32_t x) { return dm::u2f(x); }
@@ -83,7 +90,7 @@ RB_HD float dot(V3 a, V3 b) {
 }
 RB_HD V3 cross(V3 x, V3 y) { return {x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y}; }
 RB_HD float length(V3 v) { return sqrtf_(dot(v, v)); }
-RB_HD V3 normalize(V3 v) { return v * fdiv_(1.0f, sqrtf_(dot(v, v))); }
+RB_HD V3 normalize(V3 v) { return v * frcp_(sqrtf_(dot(v, v))); }
 RB_HD V3 reflect(V3 I, V3 N) { return I - N * dot(N, I) * 2.0f; }
 RB_HD float gmax(float a, float b) { return (a < b) ? b : a; }  // glm::max
 RB_HD float gmin(float a, float b) { return (b < a) ? b : a; }  // glm::min
@@ -203,6 +210,14 @@ RB_HD F4 ldg4(const F4* p) {
 #if defined(__CUDA_ARCH__)
   float4 v = __ldg(reinterpret_cast<const float4*>(p));
   return {v.x, v.y, v.z, v.w};
+#else
+  return *p;
+#endif
+}
+RB_HD U2 ldg2(const U2* p) {
+#if defined(__CUDA_ARCH__)
+  uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  return {v.x, v.y};
 #else
   return *p;
 #endif

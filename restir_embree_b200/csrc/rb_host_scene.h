@@ -23,6 +23,7 @@ struct HostScene {
   std::vector<uint32_t> emissive;
   std::vector<float> cdf, alias_prob;
   std::vector<uint32_t> alias_idx;
+  std::vector<uint32_t> alias_pair;  // [2 * n_lights]: {bits(alias_prob[i]), alias_idx[i]} — one 8-byte load per pick
   std::vector<F4> light;  // [6 * n_lights]
   float maxabs = 0, totalSurface = 0;
 };
@@ -128,6 +129,13 @@ inline int flatten_scene(const RbSceneDesc* sd, HostScene& hs, std::string& err)
       q[l] = (q[l] + q[s]) - 1.0f;
       (q[l] < 1.0f ? small : large).push_back(l);
     }
+  }
+  hs.alias_pair.resize(2 * NL);
+  for (size_t i = 0; i < NL; ++i) {
+    uint32_t bits;
+    memcpy(&bits, &alias_prob[i], 4);
+    hs.alias_pair[2 * i] = bits;
+    hs.alias_pair[2 * i + 1] = alias_idx[i];
   }
   for (size_t i = 0; i < NL; ++i) {
     const size_t t = emissive[i];

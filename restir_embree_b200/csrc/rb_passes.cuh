@@ -161,7 +161,7 @@ RB_HD_NOINLINE float calc_I_M(float nDotV, float n) {  // MaterialPhong::calc_I_
 RB_HD float inv_I_M(const V3& pos, const V3& normal, float shininess, const V3& camPos) {
   const V3 V = normalize(camPos - pos);
   float nDotV = dot(V, normal);
-  return 1.0f / calc_I_M(nDotV, shininess);
+  return frcp_(calc_I_M(nDotV, shininess));
 }
 RB_HD bool uses_phong_brdf(uint32_t t) { return t == RB_MAT_PHONG || t == RB_MAT_DIELECTRIC; }
 
@@ -331,8 +331,9 @@ RB_HD LightPick pick_light(const SceneDev& sc, int sampler, uint32_t key, uint32
     const uint32_t h = rng_bits(key, slot);
     const uint32_t i = (uint32_t)(((uint64_t)h * (uint64_t)N) >> 32);
     const float frac = bits_to_unit(rng_bits(key, slot | 0x40000000u));
-    p.idx = (frac < sc.alias_prob[i]) ? i : sc.alias_idx[i];
-    p.pdf = ldg4(sc.light + 6 * (size_t)p.idx + 1).w;  // area / total
+    const U2 a = ldg2(sc.alias_pair + i);
+    p.idx = (frac < u2f(a.x)) ? i : a.y;
+    p.pdf = -1.0f;  // area / total: word 3 of the light's second record, which the caller loads anyway
     return p;
   }
   const float ksi = rng_value(key, slot, 0.0f, 1.0f);
@@ -462,11 +463,17 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   bool sel_wants = false;
 
   const float inv_MArea = P.M_Area > 0 ? 1.0f / (float)P.M_Area : 0.0f;
+  // The pick of candidate i + 1 is issued before candidate i is evaluated: the alias-table lookup and the light
+  // record gather are dependent loads, and the counter RNG makes the next pick independent of this candidate.
+  LightPick next_pick = {0u, 0.0f};
+  if (P.M_Area > 0) next_pick = pick_light(fc.sc, P.lightSampler, key, 0u);
   for (int i = 0; i < P.M_Area; ++i) {
     const uint32_t base = 4u * (uint32_t)i;
-    const LightPick pick = pick_light(fc.sc, P.lightSampler, key, base);
+    const LightPick pick = next_pick;
     const F4* L = fc.sc.light + 6 * (size_t)pick.idx;
     const F4 l0 = ldg4(L), l1 = ldg4(L + 1), l2 = ldg4(L + 2), l3 = ldg4(L + 3), l4 = ldg4(L + 4), l5 = ldg4(L + 5);
+    if (i + 1 < P.M_Area) next_pick = pick_light(fc.sc, P.lightSampler, key, base + 4u);
+    const float pick_pdf = P.lightSampler == RB_LS_ALIAS ? l1.w : pick.pdf;
     const float r1 = rng_value(key, base + 1, 0, 1), r2 = rng_value(key, base + 2, 0, 1);
     const float sq = sqrtf_(r1);
     const float bx = 1.0f - sq;
@@ -487,18 +494,18 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
     if (valid && testVis) cnt.anyW++;
     // A light below the horizon has G == 0: with finite BRDF, pdf and weights the candidate's w is exactly +0,
     // so addSample only counts it (w_sum += 0; no draw consumed affects the result: rand < 0 is false).
-    if (sh.finite && cosThetaI == 0.0f && r_sqr > 0.0f && finitef_(r_sqr) && pick.pdf > 0.0f && finitef_(l2.w) && l2.w > 0.0f &&
+    if (sh.finite && cosThetaI == 0.0f && r_sqr > 0.0f && finitef_(r_sqr) && pick_pdf > 0.0f && finitef_(l2.w) && l2.w > 0.0f &&
         finitef_(d_ny) && finite3(s.L_i)) {
       r.confidence += 1;
       continue;
     }
     const float triPointPdf = l2.w;  // 1.0f / area, computed with the same division at upload
-    const float pdf_area = pick.pdf * triPointPdf;
+    const float pdf_area = pick_pdf * triPointPdf;
     const float cosThetaY_pdf = gmax(d_ny, 0.0f);
     const float areaMeasureFactor = cosThetaY_pdf / r_sqr;
     const Lobe lobe = phong_lobe(g, sh, lightDir);
     const float pdfAsIfBrdfAreaMeasure = pdf_from_lobe(g, sh, lightDir, lobe.pdf) * areaMeasureFactor;
-    const float W = 1.0f / pdf_area;
+    const float W = frcp_(pdf_area);
     const float misWeight = m_area(P, pdf_area, pdfAsIfBrdfAreaMeasure);
     // evaluatePHat(sample, pixel)
     float p_hat = 0.0f;
@@ -538,14 +545,14 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
       const F4* L = fc.sc.light + 6 * (size_t)h.emissiveId;
       const F4 l0 = ldg4(L);
       float pdf_area = l0.w / fc.sc.total_area;  // TriangleCDF::getPDFForTriangle, P/TriangleCDF.h:25-31
-      pdf_area *= 1.0f / l0.w;
+      pdf_area *= frcp_(l0.w);
       const float brdfPdfAreaMeasure = pdf * areaMeasureFactor;
       s.samplePoint = h.hitPoint;
       s.sampleNormal = h.normal;
       const F4 m2 = ldg4(fc.sc.mat + 3 * (size_t)h.material + 2);
       s.L_i = xyz(m2);
       s.lightIdx = h.emissiveId;
-      W = 1.0f / brdfPdfAreaMeasure;
+      W = frcp_(brdfPdfAreaMeasure);
       misWeight = m_brdf(P, brdfPdfAreaMeasure, pdf_area);
     }
     bool wants;
@@ -559,7 +566,7 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   // final evaluatePHat(r.bestSample) — the selected candidate's value again (:289)
   if (testVis && sel_wants) cnt.anyW++;
   const float p_hat = p_sel;
-  r.W = p_hat > 0.0f ? 1.0f / p_hat * r.w_sum : 0.0f;
+  r.W = p_hat > 0.0f ? frcp_(p_hat) * r.w_sum : 0.0f;
   r.confidence = imin(r.confidence, P.confidenceCap);
   if (Vis::kStore) store_reservoir(fc.Rwrite, pi, r);
 }

@@ -47,6 +47,7 @@ struct SceneDev {
   const float* cdf;
   const float* alias_prob;
   const uint32_t* alias_idx;
+  const U2* alias_pair;  // {bits(alias_prob[i]), alias_idx[i]}
   uint32_t n_lights;
   uint32_t n_tris;
   uint32_t n_nodes;
@@ -69,7 +70,7 @@ RB_HD bool tri_test(const V3& o, const V3& d, const F4& a, const F4& b, const F4
   float pz = fmaf_(d.x, e2y, -(d.y * e2x));
   float det = fmaf_(e1z, pz, fmaf_(e1y, py, e1x * px));
   if (det == 0.0f) return false;
-  float inv = fdiv_(1.0f, det);
+  float inv = frcp_(det);
   float tx = o.x - a.x, ty = o.y - a.y, tz = o.z - a.z;
   float uu = fmaf_(tz, pz, fmaf_(ty, py, tx * px)) * inv;
   if (!(uu >= 0.0f && uu <= 1.0f)) return false;
@@ -169,7 +170,7 @@ RB_HD bool trav_init(Trav& T, const SceneDev& sc, const V3& o, const V3& d, floa
   T.dx = fabsf_(d.x) < tiny ? (f2u(d.x) >> 31 ? -tiny : tiny) : d.x;
   T.dy = fabsf_(d.y) < tiny ? (f2u(d.y) >> 31 ? -tiny : tiny) : d.y;
   T.dz = fabsf_(d.z) < tiny ? (f2u(d.z) >> 31 ? -tiny : tiny) : d.z;
-  T.idx = fdiv_(1.0f, T.dx), T.idy = fdiv_(1.0f, T.dy), T.idz = fdiv_(1.0f, T.dz);
+  T.idx = frcp_(T.dx), T.idy = frcp_(T.dy), T.idz = frcp_(T.dz);
   T.oct_inv = (T.dx < 0 ? 0u : 1u) | (T.dy < 0 ? 0u : 2u) | (T.dz < 0 ? 0u : 4u);  // 7 - octant
   return true;
 }

@@ -750,6 +750,8 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     RB_TRY(dev_alloc(h, &d_cdf, NL, h->sceneAllocs));
     RB_TRY(dev_alloc(h, &d_ap, NL, h->sceneAllocs));
     RB_TRY(dev_alloc(h, &d_ai, NL, h->sceneAllocs));
+    U2* d_pair = nullptr;
+    RB_TRY(dev_alloc(h, &d_pair, NL, h->sceneAllocs));
 
     auto up = [&](void* d, const void* s, size_t bytes) -> cudaError_t {
       return bytes ? cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
@@ -762,6 +764,7 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     RB_CUDA(up(d_cdf, cdf.data(), NL * 4));
     RB_CUDA(up(d_ap, alias_prob.data(), NL * 4));
     RB_CUDA(up(d_ai, alias_idx.data(), NL * 4));
+    RB_CUDA(up(d_pair, hs.alias_pair.data(), NL * 8));
     RB_CUDA(cudaStreamSynchronize(h->stream));
     F4 *node8 = nullptr, *tri_isect = nullptr;
     uint32_t n_nodes = 0, depth = 0;
@@ -781,6 +784,7 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     sc.cdf = d_cdf;
     sc.alias_prob = d_ap;
     sc.alias_idx = d_ai;
+    sc.alias_pair = d_pair;
     sc.n_lights = (uint32_t)NL;
     sc.n_tris = (uint32_t)n;
     sc.n_nodes = n_nodes;

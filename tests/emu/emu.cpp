@@ -260,6 +260,7 @@ int emu_upload_scene(void* h, const RbSceneDesc* sd) {
   sc.cdf = E->hs.cdf.data();
   sc.alias_prob = E->hs.alias_prob.data();
   sc.alias_idx = E->hs.alias_idx.data();
+  sc.alias_pair = reinterpret_cast<const U2*>(E->hs.alias_pair.data());
   sc.n_lights = (uint32_t)E->hs.emissive.size();
   sc.n_tris = (uint32_t)E->hs.n;
   sc.n_nodes = E->n_nodes;
