@@ -372,12 +372,8 @@ RB_HD void primary_ray(const CamState& cam, int width, int height, int x, int y,
               m[2] * d_c.x + m[6] * d_c.y + m[10] * d_c.z);
   *dir = normalize(d_w);
 }
-RB_HD GElem gbuffer_element(const FrameCtx& fc, const CamState& cam, int x, int y, uint32_t* geomID, uint32_t* primID,
-                            Cnt& cnt) {
-  V3 dir;
-  primary_ray(cam, fc.width, fc.height, x, y, &dir);
-  cnt.closest++;
-  const SurfaceHit h = intersect_surface(fc.sc, cam.pos, dir, FLT_MIN + 0.01f, FLT_MAX);  // Ray ctor defaults, P/Ray.h:8
+// the element of a pixel from its primary ray's closest hit (material fetch, emission, cached 1/I_M)
+RB_HD GElem gbuffer_from_hit(const FrameCtx& fc, const CamState& cam, const SurfaceHit& h, uint32_t* geomID, uint32_t* primID) {
   GElem e;
   e.pos = e.normal = e.diffuse = e.specular = e.emission = v3(0);
   e.shininess = e.depth = e.invIM = 0;
@@ -402,6 +398,15 @@ RB_HD GElem gbuffer_element(const FrameCtx& fc, const CamState& cam, int x, int 
   e.isEmissive = emissive3(e.emission);
   if (h.didHit && !e.isEmissive && uses_phong_brdf(e.matType)) e.invIM = inv_I_M(e.pos, e.normal, e.shininess, cam.pos);
   return e;
+}
+#define RB_PRIMARY_TNEAR (FLT_MIN + 0.01f)  // Ray ctor defaults, P/Ray.h:8
+RB_HD GElem gbuffer_element(const FrameCtx& fc, const CamState& cam, int x, int y, uint32_t* geomID, uint32_t* primID,
+                            Cnt& cnt) {
+  V3 dir;
+  primary_ray(cam, fc.width, fc.height, x, y, &dir);
+  cnt.closest++;
+  const SurfaceHit h = intersect_surface(fc.sc, cam.pos, dir, RB_PRIMARY_TNEAR, FLT_MAX);
+  return gbuffer_from_hit(fc, cam, h, geomID, primID);
 }
 // G-buffer access for pixels that may lie outside this handle's rows (multi-GPU bands, SURVEY §8e "local
 // re-trace"): the element is recomputed from that frame's camera, bit-identical to what its owner stored.
@@ -439,6 +444,23 @@ RB_HD void gbuffer_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
   uint32_t g, p;
   const GElem e = gbuffer_element(fc, fc.cam, x, y, &g, &p, cnt);
   store_gelem(fc.G, (size_t)y * fc.width + x, e, g, p);
+}
+// Wavefront halves of the G-buffer pass: the primary ray goes through the ray queue (closest-hit slot 0), the
+// resolve half builds the element from the traced hit. Same functions as the inline path, so same bits.
+RB_HD void gbuffer_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis) {
+  V3 dir;
+  primary_ray(fc.cam, fc.width, fc.height, x, y, &dir);
+  (void)vis.closest(0, fc.cam.pos, dir, RB_PRIMARY_TNEAR, FLT_MAX);
+}
+RB_HD void gbuffer_resolve_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
+  V3 dir;
+  primary_ray(fc.cam, fc.width, fc.height, x, y, &dir);
+  cnt.closest++;
+  const size_t pi = (size_t)y * fc.width + x;
+  const SurfaceHit h = surface_from_hit(fc.sc, fc.cam.pos, dir, fc.wave.hits[pi]);
+  uint32_t g, p;
+  const GElem e = gbuffer_from_hit(fc, fc.cam, h, &g, &p);
+  store_gelem(fc.G, pi, e, g, p);
 }
 
 // =====================================================================================

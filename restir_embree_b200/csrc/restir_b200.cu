@@ -61,23 +61,21 @@ RB_PIXEL_KERNEL(k_temporal_banded, InlineVis, true, 1, (temporal_pixel<InlineVis
 RB_PIXEL_KERNEL(k_spatial, InlineVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_shade, InlineVis, true, 4, shade_pixel(fc, x, y, vis, cnt))
 // wavefront halves
+RB_PIXEL_KERNEL(k_gbuffer_stream, GenVis, false, 4, gbuffer_gen_pixel(fc, x, y, vis))
+RB_PIXEL_KERNEL(k_gbuffer_resolve, ResolveVis, true, 2, gbuffer_resolve_pixel(fc, x, y, cnt))
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 2, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_stream, GenVis, false, 2, (temporal_pixel<GenVis, false>(fc, x, y, vis, cnt)))
-RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 2, (temporal_pixel<ResolveVis, false>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_stream, GenVis, false, 3, (temporal_pixel<GenVis, false>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 3, (temporal_pixel<ResolveVis, false>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, false, 1, (temporal_pixel<GenVis, true>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_temporal_resolve_banded, ResolveVis, true, 1, (temporal_pixel<ResolveVis, true>(fc, x, y, vis, cnt)))
-RB_PIXEL_KERNEL(k_spatial_stream, GenVis, false, 2, spatial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 2, spatial_pixel(fc, x, y, vis, cnt))
-// occupancy experiments (RB_OCC3=1): three resident CTAs per SM (<= 85 registers)
-RB_PIXEL_KERNEL(k_initial_resolve_o3, ResolveVis, true, 3, initial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_spatial_stream_o3, GenVis, false, 3, spatial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_spatial_resolve_o3, ResolveVis, true, 3, spatial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_stream_o3, GenVis, false, 3, (temporal_pixel<GenVis, false>(fc, x, y, vis, cnt)))
-RB_PIXEL_KERNEL(k_temporal_resolve_o3, ResolveVis, true, 3, (temporal_pixel<ResolveVis, false>(fc, x, y, vis, cnt)))
+// three resident CTAs per SM (<= 85 registers, a few spilled words) beat two for the reuse passes (measured, profiles/);
+// the initial pass is the other way round
+RB_PIXEL_KERNEL(k_spatial_stream, GenVis, false, 3, spatial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 3, spatial_pixel(fc, x, y, vis, cnt))
 
 // ---- persistent traversal kernels over the ray queue ------------------------------------------------
 // One ray per lane. Three things keep the warps full in this divergent workload:
@@ -294,7 +292,6 @@ struct RbContext {
   int numSMs = 148;
   // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
   int refillLanes = 26, postponeLanes = 8, traceBlocksPerSM = 8;
-  bool occ3 = false;  // RB_OCC3: use the 3-CTAs-per-SM instantiations of the streaming kernels
 
   // wavefront buffers
   WaveBufs wave{};
@@ -518,7 +515,6 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     if (const char* e = getenv("RB_REFILL")) h->refillLanes = atoi(e);
     if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
     if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
-    if (const char* e = getenv("RB_OCC3")) h->occ3 = atoi(e) != 0;
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
     RB_TRY(dev_alloc(h, &d, 1, h->allocs));
@@ -909,17 +905,18 @@ static void launch_rows(RbContext* h, K kernel, int ry0, int ry1) {
   kernel<<<rows_grid(f, ry0, ry1), dim3(kTileW, kTileH), 0, h->stream>>>(f);
   h->fs.launches++;
 }
-static void fs_trace(RbContext* h, bool any, int pass) {
+static void fs_trace(RbContext* h, bool any, int pass, float tnear = -1.0f) {
   const RbParams& P = h->fs.P;
+  if (tnear < 0.0f) tnear = FLT_MIN + P.tnearOffset;
   const int trace_grid = h->numSMs * h->traceBlocksPerSM;
   if (any)
     k_trace_queue<true><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
-                                                                      h->wave.count + 1, h->wave.occ, h->wave.hits,
-                                                                      FLT_MIN + P.tnearOffset, h->refillLanes, h->postponeLanes);
+                                                                      h->wave.count + 1, h->wave.occ, h->wave.hits, tnear,
+                                                                      h->refillLanes, h->postponeLanes);
   else
     k_trace_queue<false><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
-                                                                       h->wave.count + 1, h->wave.occ, h->wave.hits,
-                                                                       FLT_MIN + P.tnearOffset, h->refillLanes, h->postponeLanes);
+                                                                       h->wave.count + 1, h->wave.occ, h->wave.hits, tnear,
+                                                                       h->refillLanes, h->postponeLanes);
   h->fs.launches++;
   fs_mark(h, pass, 1);
 }
@@ -985,7 +982,15 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   fs_bind(h);
   // ---- G-buffer ------------------------------------------------------------------------------------
   fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_GBUF, 0);
-  launch_rows(h, k_gbuffer, fc.gy0, fc.gy1);
+  if (F.wave && (size_t)(fc.gy1 - fc.gy0) * fc.width <= h->waveRayCap) {
+    fs_reset_queue(h);
+    launch_rows(h, k_gbuffer_stream, fc.gy0, fc.gy1);
+    fs_mark(h, 0, 0);
+    fs_trace(h, false, 0, RB_PRIMARY_TNEAR);
+    launch_rows(h, k_gbuffer_resolve, fc.gy0, fc.gy1);
+  } else {
+    launch_rows(h, k_gbuffer, fc.gy0, fc.gy1);
+  }
   fs_mark(h, 0, 0);
   // ---- initial candidates ----------------------------------------------------------------------------
   fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_INITIAL, 0);
@@ -998,7 +1003,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     }
     // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel
     if (P.doVisibilityPass)
-      launch_rows(h, h->occ3 ? k_initial_resolve_o3 : k_initial_resolve, y0, y1);
+      launch_rows(h, k_initial_resolve, y0, y1);
     else
       launch_rows(h, k_initial_resolve_inline_shadow, y0, y1);
   } else {
@@ -1028,13 +1033,13 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       if (banded)
         launch_rows(h, k_temporal_stream_banded, y0, y1);
       else
-        launch_rows(h, h->occ3 ? k_temporal_stream_o3 : k_temporal_stream, y0, y1);
+        launch_rows(h, k_temporal_stream, y0, y1);
       fs_mark(h, 3, 0);
       fs_trace(h, true, 3);
       if (banded)
         launch_rows(h, k_temporal_resolve_banded, y0, y1);
       else
-        launch_rows(h, h->occ3 ? k_temporal_resolve_o3 : k_temporal_resolve, y0, y1);
+        launch_rows(h, k_temporal_resolve, y0, y1);
     } else {
       if (banded)
         launch_rows(h, k_temporal_banded, y0, y1);
@@ -1066,7 +1071,7 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
   fc.frame_key = rng_frame_key(h->info.seed, F.frame_idx, PASS_SPATIAL, (uint32_t)i);
   if (F.wave_spatial) {
     fs_reset_queue(h);
-    auto kss = h->occ3 ? k_spatial_stream_o3 : k_spatial_stream;
+    auto kss = k_spatial_stream;
     launch_rows(h, kss, iy0, iy1);
     if (overlap_halo) {
       RB_TRY(halo_exchange_wait(h));
@@ -1075,7 +1080,7 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
     }
     fs_mark(h, 4, 0);
     fs_trace(h, true, 4);
-    launch_rows(h, h->occ3 ? k_spatial_resolve_o3 : k_spatial_resolve, y0, y1);
+    launch_rows(h, k_spatial_resolve, y0, y1);
   } else {
     launch_rows(h, k_spatial, iy0, iy1);
     if (overlap_halo) {

@@ -305,9 +305,9 @@ extern "C" {
 static int spatial_reach(const RbParams& P) { return (int)sqrtf(std::max(P.spatialReuseRadius, 0.0f)) + 1; }
 static uint32_t PX(const FrameCtx& fc, int x, int y) { return (uint32_t)(y * fc.width + x); }
 
-static void emu_trace_queue(Emu* E, bool any) {
+static void emu_trace_queue(Emu* E, bool any, float tnear = -1.0f) {
   FrameCtx& fc = E->fc;
-  const float tnear = FLT_MIN + E->Pf.tnearOffset;
+  if (tnear < 0.0f) tnear = FLT_MIN + E->Pf.tnearOffset;
 #pragma omp parallel for schedule(dynamic, 64)
   for (int64_t i = 0; i < (int64_t)E->qcount; ++i) {
     const RayQ& r = E->rays[i];
@@ -384,7 +384,16 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
   const bool wave = E->wave;
   emu_bind(E);
   fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_GBUF, 0);
-  emu_rows(E, fc.gy0, fc.gy1, [&](int x, int y, Cnt& c) { gbuffer_pixel(fc, x, y, c); });
+  if (wave && (size_t)(fc.gy1 - fc.gy0) * fc.width <= E->rays.size()) {
+    FrameCtx save = fc;
+    fc.y0 = fc.gy0, fc.y1 = fc.gy1;
+    emu_stream(E, [&](int x, int y, Cnt&) { gbuffer_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}); });
+    emu_trace_queue(E, false, RB_PRIMARY_TNEAR);
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { gbuffer_resolve_pixel(fc, x, y, c); });
+    fc.y0 = save.y0, fc.y1 = save.y1;
+  } else {
+    emu_rows(E, fc.gy0, fc.gy1, [&](int x, int y, Cnt& c) { gbuffer_pixel(fc, x, y, c); });
+  }
   fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_INITIAL, 0);
   if (wave) {
     if (P.M_Brdf > 0 && fc.sc.n_lights > 0) {
