@@ -34,6 +34,7 @@ struct WaveBufs {
   uint8_t* occ;  // any-hit results   [slot * npix + pixel]
   HitRec* hits;  // closest results   [slot * npix + pixel]
   uint32_t npix;
+  U4* cand;      // spatial pass, constant weights: candidate records [slot * npix + pixel] (spatial_gen_pixel)
 };
 
 struct FrameCtx {
@@ -884,6 +885,134 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   }
   out.confidence = imin(out.confidence, P.confidenceCap);
   if (Vis::kStore) store_reservoir(fc.Rwrite, pi, out);
+}
+
+// ---- spatial reuse with constant weights, split for the wavefront schedule -------------------------------------
+// The stream half (spatial_gen_pixel) does everything of spatial_pixel that does not need a traced result: neighbour
+// choice, the unshadowed p-hat of every candidate, the shadow rays. It leaves one 16-byte record per candidate:
+//   { p-hat if visible, W_i, confidence_i, neighbour pixel index | flags << 27 }      (slot 0: M instead of the index)
+// The resolve half (spatial_merge_pixel) replays the reservoir updates from the records and the traced bits and
+// fetches only the selected neighbour's sample: no G-buffer access, no p-hat evaluation.
+// The arithmetic is spatial_pixel's, expression by expression (F0 * V with V in {0,1}: length(F0 * 1) and
+// length(F0 * 0) are both formed from F0 in the stream half).
+#define RB_CAND_WANTS 1u    // the reference traces a ray for this evaluation
+#define RB_CAND_RAY 2u      // a ray was queued: the value depends on the traced bit of this slot
+#define RB_CAND_PH0_NAN 4u  // length(F0 * 0) is NaN (F0 not finite)
+#define RB_CAND_COPY 8u     // emissive pixel: the reservoir is copied through (slot 0 only)
+#define RB_CAND_INDEX_BITS 27
+
+RB_HD void spatial_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const RbParams& P = fc.P;
+  const WaveBufs& wv = fc.wave;
+  const GElem thisElem = load_gelem(fc.G, pi);
+  if (thisElem.isEmissive) {
+    wv.cand[pi] = U4{0u, 0u, 0u, RB_CAND_COPY << RB_CAND_INDEX_BITS};
+    return;
+  }
+  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+  const Shading shThis = make_shading(thisElem, fc.cam.pos);
+  const int k = P.spatialReuseNeighborCount;
+  uint32_t nb[RB_MAX_NEIGHBORS + 1];
+  nb[0] = (uint32_t)pi;
+  int M = 1;
+  for (int i = 0; i < k; ++i) {  // neighbour choice: as in spatial_pixel
+    const float theta = rng_value(key, 2u * i, 0, 2.0f) * RB_PI;
+    const float r = sqrtf_(rng_value(key, 2u * i + 1, 0, P.spatialReuseRadius));
+    float sn, cs;
+    dm::sincosf_(theta, &sn, &cs);
+    const float ox = r * cs, oy = r * sn;
+    int nx = x + (int)ox, ny = y + (int)oy;
+    nx = imin(imax(nx, 0), fc.width - 1);
+    ny = imin(imax(ny, 0), fc.height - 1);
+    const size_t ni = (size_t)ny * fc.width + nx;
+    const F4 st = ld4(fc.G.spec_type + ni);
+    if (f2u(st.w) & 0x100u) continue;
+    if (P.rejectDissimilarNeighbors) {
+      const F4 nn = ld4(fc.G.normal_shin + ni);
+      const float normalSimilarity = dot(xyz(nn), thisElem.normal);
+      if (normalSimilarity < P.minNormalSimilarity) continue;
+      const float ndepth = ld4(fc.G.pos_depth + ni).w;
+      float depthRatio = 0;
+      if (ndepth > 0) depthRatio = thisElem.depth / ndepth;
+      const float halfDepthDiff = P.maxDepthDifference * 0.5f;
+      if (depthRatio < 1.0f - halfDepthDiff || depthRatio > 1.0f + halfDepthDiff) continue;
+    }
+    nb[M++] = (uint32_t)ni;
+  }
+  for (int i = 0; i < M; ++i) {
+    // only what the weight needs of the neighbour's reservoir: sample point/normal/L_i, W, confidence
+    const F4 a = ld4(fc.Rread.point_wsum + nb[i]), b = ld4(fc.Rread.normal_W + nb[i]), c = ld4(fc.Rread.Li_conf + nb[i]);
+    LightSample si;
+    si.samplePoint = xyz(a), si.sampleNormal = xyz(b), si.L_i = xyz(c), si.lightIdx = 0;
+    const float Wi = b.w;
+    const VisMode vm = vis_mode_from_W(Wi, nb[i] == (uint32_t)pi);
+    bool wants;
+    const V3 F0 = eval_F0(si, thisElem, shThis, &wants);
+    uint32_t flags = wants ? RB_CAND_WANTS : 0u;
+    if (wants) {  // shadow_F0
+      cnt.anyW += 1;
+      const bool zero = F0.x == 0.0f && F0.y == 0.0f && F0.z == 0.0f;
+      if (!zero && vm != VIS_KNOWN && !(vm == VIS_IRRELEVANT && finite3(F0))) {
+        cnt.anyT++;
+        (void)vis.visible(i, thisElem.pos, si.samplePoint);
+        flags |= RB_CAND_RAY;
+        if (!finite3(F0)) flags |= RB_CAND_PH0_NAN;
+      }
+    }
+    const float ph1 = length(F0 * 1.0f);
+    const uint32_t w3 = (i == 0 ? (uint32_t)M : nb[i]) | (flags << RB_CAND_INDEX_BITS);
+    wv.cand[(size_t)i * wv.npix + pi] = U4{f2u(ph1), f2u(Wi), f2u(c.w), w3};
+  }
+}
+
+RB_HD void spatial_merge_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const RbParams& P = fc.P;
+  const WaveBufs& wv = fc.wave;
+  const U4 r0 = wv.cand[pi];
+  if ((r0.w >> RB_CAND_INDEX_BITS) & RB_CAND_COPY) {
+    store_reservoir(fc.Rwrite, pi, load_reservoir(fc.Rread, pi));
+    return;
+  }
+  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+  const int k = P.spatialReuseNeighborCount;
+  const int M = (int)(r0.w & ((1u << RB_CAND_INDEX_BITS) - 1u));
+  const float rcpM = M > 0 ? 1.0f / (float)M : 0.0f;
+  float w_sum = 0.0f, p_sel = 0.0f;
+  int confidence = 0;
+  uint32_t sel_pixel = 0;
+  bool any_selected = false, sel_wants = false;
+  for (int i = 0; i < M; ++i) {
+    const U4 r = i == 0 ? r0 : wv.cand[(size_t)i * wv.npix + pi];
+    const uint32_t flags = r.w >> RB_CAND_INDEX_BITS;
+    float ph = u2f(r.x);
+    if ((flags & RB_CAND_RAY) && wv.occ[(size_t)i * wv.npix + pi] != 0)  // occluded: length(F0 * 0)
+      ph = (flags & RB_CAND_PH0_NAN) ? u2f(0x7FC00000u) : 0.0f;
+    const float w = rcpM * ph * u2f(r.y);
+    // Reservoir::addSample
+    w_sum += w;
+    confidence += (int)r.z;
+    if (w == 0 && w_sum == 0) continue;
+    if (rng_value(key, 2u * k + i, 0, 1) < w / w_sum) {
+      sel_pixel = i == 0 ? (uint32_t)pi : (r.w & ((1u << RB_CAND_INDEX_BITS) - 1u));
+      any_selected = true;
+      p_sel = ph;
+      sel_wants = (flags & RB_CAND_WANTS) != 0;
+    }
+  }
+  if (any_selected && sel_wants) cnt.anyW++;
+  Reservoir out = empty_reservoir();
+  if (any_selected) {
+    const F4 a = ld4(fc.Rread.point_wsum + sel_pixel), b = ld4(fc.Rread.normal_W + sel_pixel), c = ld4(fc.Rread.Li_conf + sel_pixel);
+    out.bestSample.samplePoint = xyz(a), out.bestSample.sampleNormal = xyz(b), out.bestSample.L_i = xyz(c);
+    out.bestSample.lightIdx = fc.Rread.light_idx[sel_pixel];
+  }
+  const float final_p_hat = any_selected ? p_sel : 0.0f;
+  out.w_sum = w_sum;
+  out.W = final_p_hat > 0.0f ? w_sum / final_p_hat : 0.0f;
+  out.confidence = imin(confidence, P.confidenceCap);
+  store_reservoir(fc.Rwrite, pi, out);
 }
 
 // =====================================================================================

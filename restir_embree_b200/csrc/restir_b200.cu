@@ -74,8 +74,8 @@ RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, false, 1, (temporal_pixel<GenV
 RB_PIXEL_KERNEL(k_temporal_resolve_banded, ResolveVis, true, 1, (temporal_pixel<ResolveVis, true>(fc, x, y, vis, cnt)))
 // three resident CTAs per SM (<= 85 registers, a few spilled words) beat two for the reuse passes (measured, profiles/);
 // the initial pass is the other way round
-RB_PIXEL_KERNEL(k_spatial_stream, GenVis, false, 3, spatial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 3, spatial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial_stream, GenVis, true, 3, spatial_gen_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 4, spatial_merge_pixel(fc, x, y, cnt))
 
 // ---- persistent traversal kernels over the ray queue ------------------------------------------------
 // One ray per lane. Three things keep the warps full in this divergent workload:
@@ -292,10 +292,11 @@ struct RbContext {
   int numSMs = 148;
   // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
   int refillLanes = 26, postponeLanes = 8, traceBlocksPerSM = 8;
+  bool waveGbuf = false;
 
   // wavefront buffers
   WaveBufs wave{};
-  size_t waveRayCap = 0, waveOccCap = 0, waveHitCap = 0;
+  size_t waveRayCap = 0, waveOccCap = 0, waveHitCap = 0, waveCandCap = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -515,6 +516,7 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     if (const char* e = getenv("RB_REFILL")) h->refillLanes = atoi(e);
     if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
     if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
+    if (const char* e = getenv("RB_WAVE_GBUF")) h->waveGbuf = atoi(e) != 0;
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
     RB_TRY(dev_alloc(h, &d, 1, h->allocs));
@@ -548,6 +550,7 @@ void rb_destroy(RbHandle h) {
   if (h->wave.rays) cudaFree(h->wave.rays);
   if (h->wave.occ) cudaFree(h->wave.occ);
   if (h->wave.hits) cudaFree(h->wave.hits);
+  if (h->wave.cand) cudaFree(h->wave.cand);
   if (h->wave.count) cudaFree(h->wave.count);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->commStream) cudaStreamDestroy(h->commStream);
@@ -837,8 +840,15 @@ static CamState cam_state(const RbCamera* c) {
 }
 
 // wavefront buffers sized for `slots` rays per band pixel
-static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots) {
+static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32_t cand_slots) {
   const size_t npix = (size_t)h->info.width * h->info.height;
+  if ((size_t)cand_slots * npix > h->waveCandCap) {
+    if (h->wave.cand) cudaFree(h->wave.cand);
+    h->wave.cand = nullptr;
+    h->waveCandCap = 0;
+    RB_CUDA(cudaMalloc((void**)&h->wave.cand, (size_t)cand_slots * npix * sizeof(U4)));
+    h->waveCandCap = (size_t)cand_slots * npix;
+  }
   const size_t band_px = (size_t)h->info.width * (h->info.band_y1 - h->info.band_y0);
   const size_t need_rays = band_px * std::max<uint32_t>(slots, brdf_slots);
   if (need_rays > h->waveRayCap) {
@@ -949,10 +959,12 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   // The stream -> trace -> resolve split covers the passes whose rays do not depend on visibility results:
   // BRDF-candidate rays, the visibility pass, temporal reuse, spatial reuse with constant weights.
   F.wave = P.wavefront != 0;
-  F.wave_spatial = F.wave && P.spatialWeightCalc == RB_SW_CONSTANT;
+  // (the candidate records of the split spatial pass keep a pixel index in 27 bits)
+  F.wave_spatial = F.wave && P.spatialWeightCalc == RB_SW_CONSTANT && (size_t)h->info.width * H < (1u << RB_CAND_INDEX_BITS);
   if (F.wave) {
     const uint32_t slots = std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u);
-    RB_TRY(ensure_wave(h, slots, (uint32_t)std::max(P.M_Brdf, 1)));
+    const uint32_t cand_slots = (F.wave_spatial && P.doSpatialReuse) ? (uint32_t)P.spatialReuseNeighborCount + 1u : 0u;
+    RB_TRY(ensure_wave(h, slots, (uint32_t)std::max(P.M_Brdf, 1), cand_slots));
   }
   cudaStream_t st = h->stream;
   FrameCtx& fc = F.fc;
@@ -982,7 +994,9 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   fs_bind(h);
   // ---- G-buffer ------------------------------------------------------------------------------------
   fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_GBUF, 0);
-  if (F.wave && (size_t)(fc.gy1 - fc.gy0) * fc.width <= h->waveRayCap) {
+  // primary rays are coherent: the inline kernel (0.87 ms at 1080p / 1M triangles) beats queue + persistent traversal +
+  // resolve (0.84 + 0.28 ms); the split stays available for experiments (RB_WAVE_GBUF=1)
+  if (F.wave && h->waveGbuf && (size_t)(fc.gy1 - fc.gy0) * fc.width <= h->waveRayCap) {
     fs_reset_queue(h);
     launch_rows(h, k_gbuffer_stream, fc.gy0, fc.gy1);
     fs_mark(h, 0, 0);

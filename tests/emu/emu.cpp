@@ -55,6 +55,7 @@ struct Emu {
   std::vector<RayQ> rays;
   std::vector<uint8_t> occ;
   std::vector<HitRec> hits;
+  std::vector<U4> cand;
 
   GBufPlanes gp(int i) { return GBufPlanes{gs[i].a.data(), gs[i].b.data(), gs[i].c.data(), gs[i].d.data(), gs[i].e.data(), gs[i].ids.data()}; }
   ResPlanes rp(int i) { return ResPlanes{rs[i].a.data(), rs[i].b.data(), rs[i].c.data(), rs[i].li.data()}; }
@@ -367,7 +368,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
   memset(E->counters, 0, sizeof(E->counters));
   E->frame_idx = frame_idx;
   E->wave = P.wavefront != 0;
-  E->wave_spatial = E->wave && P.spatialWeightCalc == RB_SW_CONSTANT;
+  E->wave_spatial = E->wave && P.spatialWeightCalc == RB_SW_CONSTANT && (size_t)E->width * E->height < (1u << RB_CAND_INDEX_BITS);
   const uint32_t npix = (uint32_t)(E->width * E->height);
   const uint32_t slots = std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u);
   if (E->wave) {
@@ -380,11 +381,15 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     fc.wave.occ = E->occ.data();
     fc.wave.hits = E->hits.data();
     fc.wave.npix = npix;
+    if (E->wave_spatial && P.doSpatialReuse) {
+      E->cand.assign((size_t)npix * (P.spatialReuseNeighborCount + 1), U4{0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu});
+      fc.wave.cand = E->cand.data();
+    }
   }
   const bool wave = E->wave;
   emu_bind(E);
   fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_GBUF, 0);
-  if (wave && (size_t)(fc.gy1 - fc.gy0) * fc.width <= E->rays.size()) {
+  if (wave && getenv("RB_WAVE_GBUF") && atoi(getenv("RB_WAVE_GBUF")) && (size_t)(fc.gy1 - fc.gy0) * fc.width <= E->rays.size()) {
     FrameCtx save = fc;
     fc.y0 = fc.gy0, fc.y1 = fc.gy1;
     emu_stream(E, [&](int x, int y, Cnt&) { gbuffer_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}); });
@@ -449,9 +454,10 @@ int emu_frame_spatial(void* h, int i) {
   fc.spatial_iter = i;
   fc.frame_key = rng_frame_key(E->seed, E->frame_idx, PASS_SPATIAL, (uint32_t)i);
   if (E->wave_spatial) {
-    emu_stream(E, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+    E->qcount = 0;
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
     emu_trace_queue(E, true);
-    for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_merge_pixel(fc, x, y, c); });
   } else {
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
   }
