@@ -731,6 +731,129 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
   if (Vis::kStore) store_reservoir(fc.Rwrite, pi, out);
 }
 
+// ---- temporal reuse split for the wavefront schedule (same idea as the spatial split below) -----------------------
+// Stream half: validity tests, the four unshadowed p-hat values, the shadow rays; it leaves two 16-byte records per
+// pixel: slot 0 = {A, B, C, D} (values if visible), slot 1 = {flags, 0, 0, 0} with 4 flag bits per evaluation
+// (RB_CAND_WANTS / _RAY / _PH0_NAN) and bit 16 = "keep the current reservoir" (a validity test failed).
+// Resolve half: the two-way merge from the records, the traced bits and the two reservoirs.
+#define RB_CAND_WANTS 1u    // the reference traces a ray for this evaluation
+#define RB_CAND_RAY 2u      // a ray was queued: the value depends on the traced bit of this slot
+#define RB_CAND_PH0_NAN 4u  // length(F0 * 0) is NaN (F0 not finite)
+#define RB_CAND_COPY 8u     // emissive pixel: the reservoir is copied through (spatial, slot 0 only)
+#define RB_CAND_INDEX_BITS 27
+#define RB_TEMPORAL_KEEP (1u << 16)
+template <bool BANDED>
+RB_HD void temporal_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const WaveBufs& wv = fc.wave;
+  U4* rec_flags = wv.cand + (size_t)wv.npix + pi;
+  const GElem curElem = load_gelem(fc.G, pi);
+  int px, py;
+  if (!reproject(fc.prevCam, fc.width, fc.height, curElem.pos, &px, &py)) {
+    *rec_flags = U4{RB_TEMPORAL_KEEP, 0u, 0u, 0u};
+    return;
+  }
+  const GElem prevElem = BANDED ? fetch_gelem(fc, true, px, py, cnt) : load_gelem(fc.Gprev, (size_t)py * fc.width + px);
+  const V3 curCam = fc.cam.pos, prevCam = fc.prevCam.pos;
+  const float currentDepth = length(curElem.pos - curCam);
+  const float prevDepth = length(prevElem.pos - prevCam);
+  const float depthRatio = currentDepth > prevDepth ? prevDepth / currentDepth : currentDepth / prevDepth;
+  if (depthRatio < 0.9f) {
+    *rec_flags = U4{RB_TEMPORAL_KEEP, 0u, 0u, 0u};
+    return;
+  }
+  const V3 prevPosAtCurrent = xyz(ld4(fc.Gprev.pos_depth + pi));
+  int fx, fy;
+  if (!reproject(fc.cam, fc.width, fc.height, prevPosAtCurrent, &fx, &fy)) {
+    *rec_flags = U4{RB_TEMPORAL_KEEP, 0u, 0u, 0u};
+    return;
+  }
+  const V3 fwPos = BANDED ? fetch_gpos(fc, false, fx, fy, cnt) : xyz(ld4(fc.G.pos_depth + (size_t)fy * fc.width + fx));
+  const float currentDepthP = length(prevPosAtCurrent - prevCam);
+  const float prevDepthP = length(fwPos - curCam);
+  const float depthRatioP = currentDepthP > prevDepthP ? prevDepthP / currentDepthP : currentDepthP / prevDepthP;
+  if (depthRatioP < 0.9f) {
+    *rec_flags = U4{RB_TEMPORAL_KEEP, 0u, 0u, 0u};
+    return;
+  }
+  const Reservoir cur = load_reservoir(fc.Rread, pi);
+  const Reservoir prev = load_reservoir(fc.Rlast, pi);  // same pixel, not the reprojected one (:641)
+  const Shading shCur = make_shading(curElem, curCam), shPrev = make_shading(prevElem, prevCam);
+  const VisMode modeA = vis_mode_from_W(cur.W, true);
+  const VisMode modeB = cur.W == 0.0f ? VIS_IRRELEVANT : VIS_TRACE;
+  const VisMode modeCD = prev.W == 0.0f ? VIS_IRRELEVANT : VIS_TRACE;
+  float ph[4];
+  uint32_t flags = 0;
+  for (int e = 0; e < 4; ++e) {  // A: cur sample @ cur pixel, B: cur @ prev, C: prev @ cur, D: prev @ prev
+    const LightSample& smp = e < 2 ? cur.bestSample : prev.bestSample;
+    const GElem& g = (e & 1) ? prevElem : curElem;
+    const Shading& sh = (e & 1) ? shPrev : shCur;
+    const VisMode vm = e == 0 ? modeA : e == 1 ? modeB : modeCD;
+    const int copies = (e & 1) ? 1 : 2;  // A and C stand for two evaluations of the reference each
+    bool wants;
+    const V3 F0 = eval_F0(smp, g, sh, &wants);
+    uint32_t f = wants ? RB_CAND_WANTS : 0u;
+    if (wants) {  // shadow_F0
+      cnt.anyW += (uint32_t)copies;
+      const bool zero = F0.x == 0.0f && F0.y == 0.0f && F0.z == 0.0f;
+      if (!zero && vm != VIS_KNOWN && !(vm == VIS_IRRELEVANT && finite3(F0))) {
+        cnt.anyT++;
+        (void)vis.visible(e, g.pos, smp.samplePoint);
+        f |= RB_CAND_RAY;
+        if (!finite3(F0)) f |= RB_CAND_PH0_NAN;
+      }
+    }
+    ph[e] = length(F0 * 1.0f);
+    flags |= f << (4 * e);
+  }
+  wv.cand[pi] = U4{f2u(ph[0]), f2u(ph[1]), f2u(ph[2]), f2u(ph[3])};
+  *rec_flags = U4{flags, 0u, 0u, 0u};
+}
+
+RB_HD void temporal_merge_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const RbParams& P = fc.P;
+  const WaveBufs& wv = fc.wave;
+  const uint32_t flags = wv.cand[(size_t)wv.npix + pi].x;
+  const Reservoir cur = load_reservoir(fc.Rread, pi);
+  if (flags & RB_TEMPORAL_KEEP) {
+    store_reservoir(fc.Rwrite, pi, cur);
+    return;
+  }
+  const Reservoir prev = load_reservoir(fc.Rlast, pi);
+  const U4 rec = wv.cand[pi];
+  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+  float v[4] = {u2f(rec.x), u2f(rec.y), u2f(rec.z), u2f(rec.w)};
+  for (int e = 0; e < 4; ++e) {
+    const uint32_t f = (flags >> (4 * e)) & 0xFu;
+    if ((f & RB_CAND_RAY) && wv.occ[(size_t)e * wv.npix + pi] != 0) v[e] = (f & RB_CAND_PH0_NAN) ? u2f(0x7FC00000u) : 0.0f;
+  }
+  const float A = v[0], B = v[1], C = v[2], D = v[3];
+  const bool wA = (flags & RB_CAND_WANTS) != 0, wC = ((flags >> 8) & RB_CAND_WANTS) != 0;
+
+  Reservoir out = empty_reservoir();
+  float m_cur = A * (float)cur.confidence / (A * (float)cur.confidence + B * (float)prev.confidence);
+  if (!(m_cur > 0)) m_cur = 0.0f;
+  const float w_cur = m_cur * A * cur.W;
+  int selected = -1;
+  if (add_sample(out, cur.bestSample, w_cur, cur.confidence, key, 0)) selected = 0;
+  float m_prev = D * (float)prev.confidence / (C * (float)cur.confidence + D * (float)prev.confidence);
+  if (!(m_prev > 0)) m_prev = 0.0f;
+  const float w_prev = m_prev * C * prev.W;
+  if (add_sample(out, prev.bestSample, w_prev, prev.confidence, key, 1)) selected = 1;
+  out.confidence = imin(out.confidence, P.confidenceCap);
+  float final_p_hat = 0.0f;
+  if (selected == 0) {
+    final_p_hat = A;
+    if (wA) cnt.anyW++;
+  } else if (selected == 1) {
+    final_p_hat = C;
+    if (wC) cnt.anyW++;
+  }
+  out.W = final_p_hat > 0.0f ? out.w_sum / final_p_hat : 0.0f;
+  store_reservoir(fc.Rwrite, pi, out);
+}
+
 // =====================================================================================
 // Pass 4: spatial reuse (ReSTIRIntegrator::spatialReusePass, :316-542;
 // Sampling::sampleDiskUniform P/Sampling.cpp:78-87)
@@ -895,11 +1018,6 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
 // fetches only the selected neighbour's sample: no G-buffer access, no p-hat evaluation.
 // The arithmetic is spatial_pixel's, expression by expression (F0 * V with V in {0,1}: length(F0 * 1) and
 // length(F0 * 0) are both formed from F0 in the stream half).
-#define RB_CAND_WANTS 1u    // the reference traces a ray for this evaluation
-#define RB_CAND_RAY 2u      // a ray was queued: the value depends on the traced bit of this slot
-#define RB_CAND_PH0_NAN 4u  // length(F0 * 0) is NaN (F0 not finite)
-#define RB_CAND_COPY 8u     // emissive pixel: the reservoir is copied through (slot 0 only)
-#define RB_CAND_INDEX_BITS 27
 
 RB_HD void spatial_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis, Cnt& cnt) {
   const size_t pi = (size_t)y * fc.width + x;

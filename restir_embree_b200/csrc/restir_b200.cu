@@ -68,10 +68,9 @@ RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 2, initial_pixel(fc, x, y, 
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_stream, GenVis, false, 3, (temporal_pixel<GenVis, false>(fc, x, y, vis, cnt)))
-RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 3, (temporal_pixel<ResolveVis, false>(fc, x, y, vis, cnt)))
-RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, false, 1, (temporal_pixel<GenVis, true>(fc, x, y, vis, cnt)))
-RB_PIXEL_KERNEL(k_temporal_resolve_banded, ResolveVis, true, 1, (temporal_pixel<ResolveVis, true>(fc, x, y, vis, cnt)))
+RB_PIXEL_KERNEL(k_temporal_stream, GenVis, true, 3, temporal_gen_pixel<false>(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, true, 1, temporal_gen_pixel<true>(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 4, temporal_merge_pixel(fc, x, y, cnt))
 // three resident CTAs per SM (<= 85 registers, a few spilled words) beat two for the reuse passes (measured, profiles/);
 // the initial pass is the other way round
 RB_PIXEL_KERNEL(k_spatial_stream, GenVis, true, 3, spatial_gen_pixel(fc, x, y, vis, cnt))
@@ -963,7 +962,8 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   F.wave_spatial = F.wave && P.spatialWeightCalc == RB_SW_CONSTANT && (size_t)h->info.width * H < (1u << RB_CAND_INDEX_BITS);
   if (F.wave) {
     const uint32_t slots = std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u);
-    const uint32_t cand_slots = (F.wave_spatial && P.doSpatialReuse) ? (uint32_t)P.spatialReuseNeighborCount + 1u : 0u;
+    uint32_t cand_slots = (F.wave_spatial && P.doSpatialReuse) ? (uint32_t)P.spatialReuseNeighborCount + 1u : 0u;
+    if (P.doTemporalReuse) cand_slots = std::max(cand_slots, 2u);
     RB_TRY(ensure_wave(h, slots, (uint32_t)std::max(P.M_Brdf, 1), cand_slots));
   }
   cudaStream_t st = h->stream;
@@ -1050,10 +1050,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
         launch_rows(h, k_temporal_stream, y0, y1);
       fs_mark(h, 3, 0);
       fs_trace(h, true, 3);
-      if (banded)
-        launch_rows(h, k_temporal_resolve_banded, y0, y1);
-      else
-        launch_rows(h, k_temporal_resolve, y0, y1);
+      launch_rows(h, k_temporal_resolve, y0, y1);
     } else {
       if (banded)
         launch_rows(h, k_temporal_banded, y0, y1);

@@ -381,10 +381,10 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     fc.wave.occ = E->occ.data();
     fc.wave.hits = E->hits.data();
     fc.wave.npix = npix;
-    if (E->wave_spatial && P.doSpatialReuse) {
-      E->cand.assign((size_t)npix * (P.spatialReuseNeighborCount + 1), U4{0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu});
-      fc.wave.cand = E->cand.data();
-    }
+    size_t cand_slots = (E->wave_spatial && P.doSpatialReuse) ? (size_t)P.spatialReuseNeighborCount + 1 : 0;
+    if (P.doTemporalReuse) cand_slots = std::max<size_t>(cand_slots, 2);
+    E->cand.assign((size_t)npix * cand_slots, U4{0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu});
+    fc.wave.cand = E->cand.data();
   }
   const bool wave = E->wave;
   emu_bind(E);
@@ -426,15 +426,13 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     emu_bind(E);
     fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_TEMPORAL, 0);
     if (wave) {
-      if (banded) {
-        emu_stream(E, [&](int x, int y, Cnt& c) { temporal_pixel<GenVis, true>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
-        emu_trace_queue(E, true);
-        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel<ResolveVis, true>(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
-      } else {
-        emu_stream(E, [&](int x, int y, Cnt& c) { temporal_pixel<GenVis, false>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
-        emu_trace_queue(E, true);
-        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel<ResolveVis, false>(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
-      }
+      E->qcount = 0;
+      if (banded)
+        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<true>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+      else
+        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<false>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+      emu_trace_queue(E, true);
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_merge_pixel(fc, x, y, c); });
     } else if (banded) {
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel<InlineVis, true>(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
     } else {
