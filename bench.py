@@ -213,7 +213,9 @@ def run_ours(args):
         rays["any_t"].append(t["rays_any_traced"])
         launches = t["kernel_launches"]
     # ---- end to end through the public call with a HOST frame buffer ---------------------------------
-    for _ in range(2):
+    # (the same camera path as the device-resident leg: frames 0..W-1 untimed, then K timed)
+    frame = 0
+    for _ in range(args.warmup):
         r.render_frame(camera_at(scene, frame), frame, out=out)
         frame += 1
     barrier()

@@ -77,7 +77,8 @@ RB_HD int clz64_(uint64_t x) {
 
 struct BuildCtx {
   uint32_t n;            // triangles
-  const float* tri_pos;  // [n][9] scene order
+  const float* tri_pos;  // [n][9] scene order (or the subset being built)
+  const uint32_t* id_map;  // optional: triangle index in tri_pos -> scene triangle id written into the leaves
   float pad;             // box padding (absolute)
   int* scene_bounds;     // [6] ordered ints: lo.xyz (min), hi.xyz (max)
   // per triangle, scene order
@@ -345,7 +346,7 @@ RB_HD void write_tri(const BuildCtx& c, uint32_t dst, uint32_t tri) {
   F4* o = c.tri_isect + 3 * (size_t)dst;
   o[0] = F4{p[0], p[1], p[2], e1x};
   o[1] = F4{e1y, e1z, e2x, e2y};
-  o[2] = F4{e2z, u2f(tri), 0, 0};
+  o[2] = F4{e2z, u2f(c.id_map ? c.id_map[tri] : tri), 0, 0};
 }
 
 RB_HD uint32_t pack4(const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); }

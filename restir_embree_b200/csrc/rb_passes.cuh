@@ -34,6 +34,7 @@ struct WaveBufs {
   uint8_t* occ;  // any-hit results   [slot * npix + pixel]
   HitRec* hits;  // closest results   [slot * npix + pixel]
   uint32_t npix;
+  uint32_t brdf_two_step;  // BRDF-candidate hits come from the emissive-only BVH; occ[] says whether something precedes them
   U4* cand;      // spatial pass, constant weights: candidate records [slot * npix + pixel] (spatial_gen_pixel)
 };
 
@@ -139,7 +140,11 @@ struct ResolveVisT {
   }
   RB_HD SurfaceHit closest(int slot, const V3& org, const V3& dir, float /*tnear*/, float /*tfar*/) const {
     const WaveBufs& w = fc->wave;
-    return surface_from_hit(fc->sc, org, dir, w.hits[(size_t)slot * w.npix + pixel]);
+    HitRec hr = w.hits[(size_t)slot * w.npix + pixel];
+    // two-step BRDF rays: the emitter hit only stands if nothing precedes it (a miss and a non-emissive closest hit
+    // are the same thing to brdfSampleLight, P/ReSTIRIntegrator.cpp:143)
+    if (w.brdf_two_step && hr.tri != 0xFFFFFFFFu && w.occ[(size_t)slot * w.npix + pixel] != 0) hr.tri = 0xFFFFFFFFu;
+    return surface_from_hit(fc->sc, org, dir, hr);
   }
 };
 typedef ResolveVisT<false> ResolveVis;
@@ -599,9 +604,14 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
 // closest-hit kernel, and consumed by initial_pixel through ResolveVis::closest.
 RB_HD void initial_brdf_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis) {
   const size_t pi = (size_t)y * fc.width + x;
-  const GElem g = load_gelem(fc.G, pi);
-  if (g.isEmissive || fc.sc.n_lights == 0) return;
   const RbParams& P = fc.P;
+  const GElem g = load_gelem(fc.G, pi);
+  if (g.isEmissive || fc.sc.n_lights == 0) {
+    // no ray: leave "miss" records so that the second step of the two-step scheme has nothing to do here
+    if (fc.wave.brdf_two_step)
+      for (int i = 0; i < P.M_Brdf; ++i) fc.wave.hits[(size_t)i * fc.wave.npix + pi].tri = 0xFFFFFFFFu;
+    return;
+  }
   const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
   const Shading sh = make_shading(g, fc.cam.pos);
   for (int i = 0; i < P.M_Brdf; ++i) {
@@ -610,6 +620,30 @@ RB_HD void initial_brdf_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis
     const V3 wi = brdf_sample(g, sh, key, base, &pdf);
     const V3 org = g.pos + P.normalOffset * g.normal;
     (void)vis.closest(i, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
+  }
+}
+
+// Second step of the two-step BRDF-candidate rays: where the emissive-only BVH reported a hit (t, id), ask the full
+// BVH whether anything precedes it (trace8_precedes / k_trace_queue<true, true>). Few rays reach this step: most
+// BRDF-sampled directions do not point at an emitter at all.
+RB_HD void initial_brdf_occ_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const RbParams& P = fc.P;
+  const WaveBufs& w = fc.wave;
+  bool any = false;
+  for (int i = 0; i < P.M_Brdf; ++i) any = any || w.hits[(size_t)i * w.npix + pi].tri != 0xFFFFFFFFu;
+  if (!any) return;  // (emissive pixels queued no ray and hold "miss" records)
+  const GElem g = load_gelem(fc.G, pi);
+  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+  const Shading sh = make_shading(g, fc.cam.pos);
+  for (int i = 0; i < P.M_Brdf; ++i) {
+    const HitRec hr = w.hits[(size_t)i * w.npix + pi];
+    if (hr.tri == 0xFFFFFFFFu) continue;
+    const uint32_t base = 4u * (uint32_t)(P.M_Area + i);
+    float pdf;
+    const V3 wi = brdf_sample(g, sh, key, base, &pdf);
+    const V3 org = g.pos + P.normalOffset * g.normal;
+    vis.push(i, org, wi, hr.t);
   }
 }
 

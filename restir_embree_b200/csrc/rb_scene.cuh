@@ -53,6 +53,11 @@ struct SceneDev {
   uint32_t n_nodes;
   float total_area;
   uint32_t q7_base;  // 0x43000000 (see q7f)
+  // second BVH over the emissive triangles only (leaf ids are scene triangle ids): BRDF-sampled rays only care
+  // whether their closest hit is an emitter, so they are traced against this small tree first (rb_passes.cuh)
+  const F4* em_node8;
+  const F4* em_tri_isect;
+  uint32_t em_n_nodes;
 };
 
 struct HitRec {
@@ -143,6 +148,7 @@ struct Trav {
   int sp;
   HitRec best;
   bool hit_any;
+  uint32_t tie_id;  // TIE mode only: a hit at exactly tfar counts when its triangle id is smaller than this
 #ifdef RB_TRAV_STATS
   uint32_t n_tri_tests;
 #endif
@@ -158,6 +164,7 @@ RB_HD bool trav_init(Trav& T, const SceneDev& sc, const V3& o, const V3& d, floa
   T.best.u = T.best.v = 0;
   T.best.tri = 0xFFFFFFFFu;
   T.hit_any = false;
+  T.tie_id = 0u;
 #ifdef RB_TRAV_STATS
   T.n_tri_tests = 0;
 #endif
@@ -234,7 +241,9 @@ RB_HD U2 trav_node_step(Trav& T, U2* stack, const SceneDev& sc) {
 }
 
 // Test ONE triangle of a triangle group (clears its bit). Returns true when the ray is finished by it (ANY hit).
-template <bool ANY>
+// TIE (any-hit only): the ray asks "does anything precede the hit (tfar, tie_id)?" under the closest-hit order of
+// the parity contract (smaller t, then smaller triangle id) — a hit at exactly tfar counts iff its id is smaller.
+template <bool ANY, bool TIE = false>
 RB_HD bool trav_tri_one(Trav& T, U2& tgroup, const SceneDev& sc) {
   const int ti = bfind(tgroup.y);
   tgroup.y &= ~(1u << ti);
@@ -244,8 +253,10 @@ RB_HD bool trav_tri_one(Trav& T, U2& tgroup, const SceneDev& sc) {
 #ifdef RB_TRAV_STATS
   T.n_tri_tests++;
 #endif
-  if (tri_test(T.o, T.d, a, b, c, T.tnear, T.tfar, &t, &u, &v)) {
+  const float tfar_test = TIE ? u2f(f2u(T.tfar) + 1u) : T.tfar;  // next float above tfar (tfar > 0, finite)
+  if (tri_test(T.o, T.d, a, b, c, T.tnear, tfar_test, &t, &u, &v)) {
     const uint32_t id = f2u(c.y);
+    if (TIE && !(t < T.tfar || id < T.tie_id)) return false;
     if (ANY) {
       T.best.t = t, T.best.u = u, T.best.v = v, T.best.tri = id;
       T.hit_any = true;
@@ -260,11 +271,11 @@ RB_HD bool trav_tri_one(Trav& T, U2& tgroup, const SceneDev& sc) {
 
 // Sequential step (one ray per thread, no rescheduling): node visit, then its triangles, then the next group.
 // Returns false when the ray is finished.
-template <bool ANY>
+template <bool ANY, bool TIE = false>
 RB_HD bool trav_step(Trav& T, U2* stack, const SceneDev& sc) {
   U2 tgroup = trav_node_step<ANY>(T, stack, sc);
   while (tgroup.y != 0)
-    if (trav_tri_one<ANY>(T, tgroup, sc)) return false;
+    if (trav_tri_one<ANY, TIE>(T, tgroup, sc)) return false;
   if (!has_node_work(T)) {
     if (T.sp == 0) return false;
     T.ngroup = stack[--T.sp];
@@ -283,6 +294,25 @@ RB_HD bool trace8(const SceneDev& sc, const V3& o, const V3& d, float tnear, flo
   }
   if (out) *out = T.best;
   return T.best.tri != 0xFFFFFFFFu;
+}
+// does any triangle precede the hit (tfar, tie_id) along the ray? (see trav_tri_one)
+RB_HD bool trace8_precedes(const SceneDev& sc, const V3& o, const V3& d, float tnear, float tfar, uint32_t tie_id) {
+  Trav T;
+  U2 stack[RB_STACK_MAX];
+  if (trav_init(T, sc, o, d, tnear, tfar)) {
+    T.tie_id = tie_id;
+    while (trav_step<true, true>(T, stack, sc)) {
+    }
+  }
+  return T.best.tri != 0xFFFFFFFFu;
+}
+// the same scene seen through its emissive-only BVH
+RB_HD SceneDev emissive_view(const SceneDev& sc) {
+  SceneDev e = sc;
+  e.node8 = sc.em_node8;
+  e.tri_isect = sc.em_tri_isect;
+  e.n_nodes = sc.em_n_nodes;
+  return e;
 }
 
 // Shadow ray of Intersection::testOcclusion, P/Intersection.h:43-60 (no normal offset; tnear = FLT_MIN + tnearOffset;

@@ -64,6 +64,7 @@ RB_PIXEL_KERNEL(k_shade, InlineVis, true, 4, shade_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_gbuffer_stream, GenVis, false, 4, gbuffer_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL(k_gbuffer_resolve, ResolveVis, true, 2, gbuffer_resolve_pixel(fc, x, y, cnt))
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
+RB_PIXEL_KERNEL(k_initial_brdf_occ_stream, GenVis, false, 2, initial_brdf_occ_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 2, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
@@ -92,7 +93,7 @@ constexpr int kTraceThreads = 128;
 #ifndef RB_TRACE_MINB
 #define RB_TRACE_MINB 8
 #endif
-template <bool ANY>
+template <bool ANY, bool TIE = false>
 __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(SceneDev sc, const RayQ* __restrict__ rays,
                                                                const uint32_t* __restrict__ count_ptr, uint32_t capacity,
                                                                uint32_t* __restrict__ next, uint8_t* __restrict__ occ,
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(Sc
           const float4 b = __ldg(reinterpret_cast<const float4*>(&rays[i].d_dest));
           dest = __float_as_uint(b.w);
           active = trav_init(T, sc, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), tnear, a.w);
+          if (TIE) T.tie_id = hits[dest].tri;  // the hit this ray asks about (written by the previous trace)
           tsp = RB_STACK_MAX;
           tg = U2{0u, 0u};
           if (!active) {  // cannot hit anything
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(Sc
           else if (tsp - T.sp > 2)
             stack[--tsp] = g;
           else  // stack almost full: drain this group right away
-            while (g.y != 0 && !done) done = trav_tri_one<ANY>(T, g, sc);
+            while (g.y != 0 && !done) done = trav_tri_one<ANY, TIE>(T, g, sc);
         }
         if (!has_node_work(T) && T.sp > 0) T.ngroup = stack[--T.sp];
       }
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(Sc
       const int n_node = __popc(__ballot_sync(FULL, active && !done && has_node_work(T)));
       if (n_tri != 0 && (n_tri >= tri_lanes || n_node < tri_lanes)) {
         if (has_tri) {
-          done = trav_tri_one<ANY>(T, tg, sc);
+          done = trav_tri_one<ANY, TIE>(T, tg, sc);
           if (!done && tg.y == 0 && tsp < RB_STACK_MAX) tg = stack[tsp++];
         }
       }
@@ -292,6 +294,7 @@ struct RbContext {
   // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
   int refillLanes = 26, postponeLanes = 8, traceBlocksPerSM = 8;
   bool waveGbuf = false;
+  bool twoStepBrdf = true;  // RB_TWO_STEP_BRDF=0 traces the BRDF-candidate rays against the full BVH instead
 
   // wavefront buffers
   WaveBufs wave{};
@@ -516,6 +519,7 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
     if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
     if (const char* e = getenv("RB_WAVE_GBUF")) h->waveGbuf = atoi(e) != 0;
+    if (const char* e = getenv("RB_TWO_STEP_BRDF")) h->twoStepBrdf = atoi(e) != 0;
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
     RB_TRY(dev_alloc(h, &d, 1, h->allocs));
@@ -581,13 +585,14 @@ int rb_set_params(RbHandle h, const RbParams* p) {
 // -------------------------------------------------------------------------------------
 // scene upload + BVH build
 // -------------------------------------------------------------------------------------
-static int build_bvh(RbContext* h, const float* d_tri_pos, uint32_t n, float maxabs, F4** node8_out, F4** tri_isect_out,
-                     uint32_t* n_nodes_out, uint32_t* depth_out) {
+static int build_bvh(RbContext* h, const float* d_tri_pos, const uint32_t* d_id_map, uint32_t n, float maxabs, F4** node8_out,
+                     F4** tri_isect_out, uint32_t* n_nodes_out, uint32_t* depth_out) {
   std::vector<void*> tmp;
   auto cleanup = [&]() { free_list(tmp); };
   BuildCtx c{};
   c.n = n;
   c.tri_pos = d_tri_pos;
+  c.id_map = d_id_map;
   c.pad = maxabs * (1.0f / 262144.0f) + 1e-30f;  // 2^-18 of the scene scale (DESIGN.md "conservative culling")
   auto body = [&]() -> int {
     RB_TRY(dev_alloc(h, &c.scene_bounds, 6, tmp));
@@ -767,7 +772,22 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     F4 *node8 = nullptr, *tri_isect = nullptr;
     uint32_t n_nodes = 0, depth = 0;
     RB_CUDA(cudaEventRecord(t0, h->stream));
-    if (n > 0) RB_TRY(build_bvh(h, d_pos, (uint32_t)n, maxabs, &node8, &tri_isect, &n_nodes, &depth));
+    if (n > 0) RB_TRY(build_bvh(h, d_pos, nullptr, (uint32_t)n, maxabs, &node8, &tri_isect, &n_nodes, &depth));
+    // emissive-only BVH (two-step BRDF-candidate rays): same builder over the emitter subset, leaves keep scene ids
+    F4 *em_node8 = nullptr, *em_tri_isect = nullptr;
+    uint32_t em_nodes = 0, em_depth = 0;
+    if (NL > 0) {
+      std::vector<float> epos(9 * NL);
+      for (size_t i = 0; i < NL; ++i) memcpy(&epos[9 * i], &pos[9 * (size_t)hs.emissive[i]], 36);
+      float* d_epos = nullptr;
+      uint32_t* d_emap = nullptr;
+      RB_TRY(dev_alloc(h, &d_epos, 9 * NL, tmp));
+      RB_TRY(dev_alloc(h, &d_emap, NL, tmp));
+      RB_CUDA(up(d_epos, epos.data(), epos.size() * 4));
+      RB_CUDA(up(d_emap, hs.emissive.data(), NL * 4));
+      RB_CUDA(cudaStreamSynchronize(h->stream));
+      RB_TRY(build_bvh(h, d_epos, d_emap, (uint32_t)NL, maxabs, &em_node8, &em_tri_isect, &em_nodes, &em_depth));
+    }
     RB_CUDA(cudaEventRecord(t1, h->stream));
     RB_CUDA(cudaEventSynchronize(t1));
     float ms = 0;
@@ -788,6 +808,9 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     sc.n_nodes = n_nodes;
     sc.total_area = totalSurface;
     sc.q7_base = 0x43000000u;
+    sc.em_node8 = em_node8;
+    sc.em_tri_isect = em_tri_isect;
+    sc.em_n_nodes = em_nodes;
     RbSceneStats& st = h->stats;
     memset(&st, 0, sizeof(st));
     st.n_triangles = (uint32_t)n;
@@ -914,18 +937,22 @@ static void launch_rows(RbContext* h, K kernel, int ry0, int ry1) {
   kernel<<<rows_grid(f, ry0, ry1), dim3(kTileW, kTileH), 0, h->stream>>>(f);
   h->fs.launches++;
 }
-static void fs_trace(RbContext* h, bool any, int pass, float tnear = -1.0f) {
+enum TraceMode { TRACE_CLOSEST = 0, TRACE_ANY = 1, TRACE_CLOSEST_EMISSIVE = 2, TRACE_ANY_PRECEDES = 3 };
+static void fs_trace(RbContext* h, int mode, int pass, float tnear = -1.0f) {
   const RbParams& P = h->fs.P;
   if (tnear < 0.0f) tnear = FLT_MIN + P.tnearOffset;
   const int trace_grid = h->numSMs * h->traceBlocksPerSM;
-  if (any)
-    k_trace_queue<true><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
-                                                                      h->wave.count + 1, h->wave.occ, h->wave.hits, tnear,
-                                                                      h->refillLanes, h->postponeLanes);
+  const WaveBufs& w = h->wave;
+#define RB_TRACE_ARGS(SC) SC, w.rays, w.count, w.capacity, w.count + 1, w.occ, w.hits, tnear, h->refillLanes, h->postponeLanes
+  if (mode == TRACE_ANY)
+    k_trace_queue<true><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
+  else if (mode == TRACE_CLOSEST)
+    k_trace_queue<false><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
+  else if (mode == TRACE_CLOSEST_EMISSIVE)
+    k_trace_queue<false><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(emissive_view(h->sc)));
   else
-    k_trace_queue<false><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, h->wave.rays, h->wave.count, h->wave.capacity,
-                                                                       h->wave.count + 1, h->wave.occ, h->wave.hits, tnear,
-                                                                       h->refillLanes, h->postponeLanes);
+    k_trace_queue<true, true><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
+#undef RB_TRACE_ARGS
   h->fs.launches++;
   fs_mark(h, pass, 1);
 }
@@ -961,7 +988,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   // (the candidate records of the split spatial pass keep a pixel index in 27 bits)
   F.wave_spatial = F.wave && P.spatialWeightCalc == RB_SW_CONSTANT && (size_t)h->info.width * H < (1u << RB_CAND_INDEX_BITS);
   if (F.wave) {
-    const uint32_t slots = std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u);
+    const uint32_t slots = std::max<uint32_t>(std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u), (uint32_t)P.M_Brdf);
     uint32_t cand_slots = (F.wave_spatial && P.doSpatialReuse) ? (uint32_t)P.spatialReuseNeighborCount + 1u : 0u;
     if (P.doTemporalReuse) cand_slots = std::max(cand_slots, 2u);
     RB_TRY(ensure_wave(h, slots, (uint32_t)std::max(P.M_Brdf, 1), cand_slots));
@@ -982,6 +1009,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   fc.frame = h->frame;
   fc.counters = h->counters;
   fc.wave = h->wave;
+  fc.wave.brdf_two_step = (F.wave && h->twoStepBrdf && h->sc.em_n_nodes > 0) ? 1u : 0u;
   // G-buffer rows kept by this handle: the band plus a margin that covers the spatial reach and most reprojections
   const int margin = banded ? std::max(16, spatial_reach(P)) : 0;
   fc.gy0 = std::max(0, y0 - margin);
@@ -1000,7 +1028,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     fs_reset_queue(h);
     launch_rows(h, k_gbuffer_stream, fc.gy0, fc.gy1);
     fs_mark(h, 0, 0);
-    fs_trace(h, false, 0, RB_PRIMARY_TNEAR);
+    fs_trace(h, TRACE_CLOSEST, 0, RB_PRIMARY_TNEAR);
     launch_rows(h, k_gbuffer_resolve, fc.gy0, fc.gy1);
   } else {
     launch_rows(h, k_gbuffer, fc.gy0, fc.gy1);
@@ -1013,7 +1041,16 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       fs_reset_queue(h);
       launch_rows(h, k_initial_brdf_stream, y0, y1);
       fs_mark(h, 1, 0);
-      fs_trace(h, false, 1);
+      if (fc.wave.brdf_two_step) {
+        // closest EMITTER along each ray (small BVH), then "does anything precede it?" for the few rays that found one
+        fs_trace(h, TRACE_CLOSEST_EMISSIVE, 1);
+        fs_reset_queue(h);
+        launch_rows(h, k_initial_brdf_occ_stream, y0, y1);
+        fs_mark(h, 1, 0);
+        fs_trace(h, TRACE_ANY_PRECEDES, 1);
+      } else {
+        fs_trace(h, TRACE_CLOSEST, 1);
+      }
     }
     // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel
     if (P.doVisibilityPass)
@@ -1030,7 +1067,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       fs_reset_queue(h);
       launch_rows(h, k_visibility_stream, y0, y1);
       fs_mark(h, 2, 0);
-      fs_trace(h, true, 2);
+      fs_trace(h, TRACE_ANY, 2);
       launch_rows(h, k_visibility_resolve, y0, y1);
     } else {
       launch_rows(h, k_visibility, y0, y1);
@@ -1049,7 +1086,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       else
         launch_rows(h, k_temporal_stream, y0, y1);
       fs_mark(h, 3, 0);
-      fs_trace(h, true, 3);
+      fs_trace(h, TRACE_ANY, 3);
       launch_rows(h, k_temporal_resolve, y0, y1);
     } else {
       if (banded)
@@ -1090,7 +1127,7 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
       launch_rows(h, kss, iy1, y1);
     }
     fs_mark(h, 4, 0);
-    fs_trace(h, true, 4);
+    fs_trace(h, TRACE_ANY, 4);
     launch_rows(h, k_spatial_resolve, y0, y1);
   } else {
     launch_rows(h, k_spatial, iy0, iy1);

@@ -28,7 +28,8 @@ struct Emu {
   uint32_t seed = 123;
   RbParams P{};
   HostScene hs;
-  std::vector<F4> node8, tri_isect;
+  std::vector<F4> node8, tri_isect, em_node8, em_tri_isect;
+  uint32_t em_n_nodes = 0;
   uint32_t n_nodes = 0, depth = 0;
   SceneDev sc{};
   bool haveScene = false, havePrev = false;
@@ -61,12 +62,13 @@ struct Emu {
   ResPlanes rp(int i) { return ResPlanes{rs[i].a.data(), rs[i].b.data(), rs[i].c.data(), rs[i].li.data()}; }
 };
 
-static int emu_build_bvh(Emu* E) {
-  const uint32_t n = (uint32_t)E->hs.n;
+static int emu_build_bvh_impl(const float* tri_pos, const uint32_t* id_map, uint32_t n, float maxabs, std::vector<F4>& node8_out,
+                              std::vector<F4>& tri_out, uint32_t* n_nodes_out, uint32_t* depth_out) {
   BuildCtx c{};
   c.n = n;
-  c.tri_pos = E->hs.pos.data();
-  c.pad = E->hs.maxabs * (1.0f / 262144.0f) + 1e-30f;
+  c.tri_pos = tri_pos;
+  c.id_map = id_map;
+  c.pad = maxabs * (1.0f / 262144.0f) + 1e-30f;
   int bounds[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
   c.scene_bounds = bounds;
   std::vector<F4> tlo(n), thi(n), ilo(n), ihi(n);
@@ -85,9 +87,9 @@ static int emu_build_bvh(Emu* E) {
   c.counters = counters;
   const size_t max_nodes = (size_t)n / 2 + 8;
   std::vector<F4> node8(RB_NODE_F4 * max_nodes);
-  E->tri_isect.assign(3 * (size_t)n, F4{0, 0, 0, 0});
+  tri_out.assign(3 * (size_t)n, F4{0, 0, 0, 0});
   c.node8 = node8.data();
-  c.tri_isect = E->tri_isect.data();
+  c.tri_isect = tri_out.data();
   for (uint32_t i = 0; i < n; ++i) bounds_body(c, i);
   for (uint32_t i = 0; i < n; ++i) morton_body(c, i);
   // radix sort stand-in: stable sort by key (cub::DeviceRadixSort is stable too)
@@ -213,10 +215,24 @@ static int emu_build_bvh(Emu* E) {
   }
   if (2 * depth + 2 > RB_STACK_MAX) return -4;
   node8.resize(RB_NODE_F4 * (size_t)n_nodes);
-  E->node8 = node8;
-  E->n_nodes = n_nodes;
-  E->depth = depth;
+  node8_out = node8;
+  *n_nodes_out = n_nodes;
+  *depth_out = depth;
   return 0;
+}
+static int emu_build_bvh(Emu* E) {
+  int rc = emu_build_bvh_impl(E->hs.pos.data(), nullptr, (uint32_t)E->hs.n, E->hs.maxabs, E->node8, E->tri_isect, &E->n_nodes, &E->depth);
+  if (rc != 0) return rc;
+  // emissive-only BVH (two-step BRDF-candidate rays), as rb_upload_scene builds it
+  E->em_n_nodes = 0;
+  const size_t NL = E->hs.emissive.size();
+  if (NL > 0) {
+    std::vector<float> epos(9 * NL);
+    for (size_t i = 0; i < NL; ++i) memcpy(&epos[9 * i], &E->hs.pos[9 * (size_t)E->hs.emissive[i]], 36);
+    uint32_t d = 0;
+    rc = emu_build_bvh_impl(epos.data(), E->hs.emissive.data(), (uint32_t)NL, E->hs.maxabs, E->em_node8, E->em_tri_isect, &E->em_n_nodes, &d);
+  }
+  return rc;
 }
 
 extern "C" {
@@ -267,6 +283,9 @@ int emu_upload_scene(void* h, const RbSceneDesc* sd) {
   sc.n_nodes = E->n_nodes;
   sc.total_area = E->hs.totalSurface;
   sc.q7_base = 0x43000000u;
+  sc.em_node8 = E->em_node8.data();
+  sc.em_tri_isect = E->em_tri_isect.data();
+  sc.em_n_nodes = E->em_n_nodes;
   E->haveScene = true;
   E->havePrev = false;
   return 0;
@@ -306,20 +325,24 @@ extern "C" {
 static int spatial_reach(const RbParams& P) { return (int)sqrtf(std::max(P.spatialReuseRadius, 0.0f)) + 1; }
 static uint32_t PX(const FrameCtx& fc, int x, int y) { return (uint32_t)(y * fc.width + x); }
 
-static void emu_trace_queue(Emu* E, bool any, float tnear = -1.0f) {
+enum { EMU_CLOSEST = 0, EMU_ANY = 1, EMU_CLOSEST_EMISSIVE = 2, EMU_ANY_PRECEDES = 3 };
+static void emu_trace_queue(Emu* E, int mode, float tnear = -1.0f) {
   FrameCtx& fc = E->fc;
   if (tnear < 0.0f) tnear = FLT_MIN + E->Pf.tnearOffset;
+  const SceneDev em = emissive_view(fc.sc);
 #pragma omp parallel for schedule(dynamic, 64)
   for (int64_t i = 0; i < (int64_t)E->qcount; ++i) {
     const RayQ& r = E->rays[i];
     const uint32_t dest = f2u(r.d_dest.w);
     HitRec hr;
-    const bool hit = any ? trace8<true>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr)
-                         : trace8<false>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr);
-    if (any)
-      E->occ[dest] = hit ? 1 : 0;
-    else
+    if (mode == EMU_ANY)
+      E->occ[dest] = trace8<true>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr) ? 1 : 0;
+    else if (mode == EMU_ANY_PRECEDES)
+      E->occ[dest] = trace8_precedes(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, E->hits[dest].tri) ? 1 : 0;
+    else {
+      trace8<false>(mode == EMU_CLOSEST_EMISSIVE ? em : fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr);
       E->hits[dest] = hr;
+    }
   }
 }
 template <class F>
@@ -370,7 +393,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
   E->wave = P.wavefront != 0;
   E->wave_spatial = E->wave && P.spatialWeightCalc == RB_SW_CONSTANT && (size_t)E->width * E->height < (1u << RB_CAND_INDEX_BITS);
   const uint32_t npix = (uint32_t)(E->width * E->height);
-  const uint32_t slots = std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u);
+  const uint32_t slots = std::max<uint32_t>(std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u), (uint32_t)P.M_Brdf);
   if (E->wave) {
     E->rays.resize((size_t)npix * std::max<uint32_t>(slots, (uint32_t)std::max(P.M_Brdf, 1)));
     E->occ.assign((size_t)npix * slots, 0xCD);
@@ -381,6 +404,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     fc.wave.occ = E->occ.data();
     fc.wave.hits = E->hits.data();
     fc.wave.npix = npix;
+    fc.wave.brdf_two_step = (E->em_n_nodes > 0 && !(getenv("RB_TWO_STEP_BRDF") && atoi(getenv("RB_TWO_STEP_BRDF")) == 0)) ? 1u : 0u;
     size_t cand_slots = (E->wave_spatial && P.doSpatialReuse) ? (size_t)P.spatialReuseNeighborCount + 1 : 0;
     if (P.doTemporalReuse) cand_slots = std::max<size_t>(cand_slots, 2);
     E->cand.assign((size_t)npix * cand_slots, U4{0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu});
@@ -393,7 +417,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     FrameCtx save = fc;
     fc.y0 = fc.gy0, fc.y1 = fc.gy1;
     emu_stream(E, [&](int x, int y, Cnt&) { gbuffer_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}); });
-    emu_trace_queue(E, false, RB_PRIMARY_TNEAR);
+    emu_trace_queue(E, EMU_CLOSEST, RB_PRIMARY_TNEAR);
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { gbuffer_resolve_pixel(fc, x, y, c); });
     fc.y0 = save.y0, fc.y1 = save.y1;
   } else {
@@ -403,7 +427,13 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
   if (wave) {
     if (P.M_Brdf > 0 && fc.sc.n_lights > 0) {
       emu_stream(E, [&](int x, int y, Cnt&) { initial_brdf_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}); });
-      emu_trace_queue(E, false);
+      if (fc.wave.brdf_two_step) {
+        emu_trace_queue(E, EMU_CLOSEST_EMISSIVE);
+        emu_stream(E, [&](int x, int y, Cnt&) { initial_brdf_occ_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}); });
+        emu_trace_queue(E, EMU_ANY_PRECEDES);
+      } else {
+        emu_trace_queue(E, EMU_CLOSEST);
+      }
     }
     if (P.doVisibilityPass)
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
@@ -415,7 +445,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
   if (P.doVisibilityPass) {
     if (wave) {
       emu_stream(E, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
-      emu_trace_queue(E, true);
+      emu_trace_queue(E, EMU_ANY);
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
     } else {
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
@@ -431,7 +461,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
         for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<true>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
       else
         for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<false>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
-      emu_trace_queue(E, true);
+      emu_trace_queue(E, EMU_ANY);
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_merge_pixel(fc, x, y, c); });
     } else if (banded) {
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_pixel<InlineVis, true>(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
@@ -454,7 +484,7 @@ int emu_frame_spatial(void* h, int i) {
   if (E->wave_spatial) {
     E->qcount = 0;
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
-    emu_trace_queue(E, true);
+    emu_trace_queue(E, EMU_ANY);
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_merge_pixel(fc, x, y, c); });
   } else {
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });

@@ -115,3 +115,53 @@ def test_degenerate_scene_sizes_build_and_trace(n_tris):
     # coincident triangles: the tie-break picks the smaller (geomID, primID) on both sides
     assert np.array_equal(ho["primID"], he["primID"]) and np.array_equal(bits(ho["t"]), bits(he["t"]))
     assert np.array_equal(o.trace_occluded(rays), e.trace_occluded(rays))
+
+
+def coincident_emitter_scene(emitter_first):
+    """A large emitter lying in the very plane of a non-emissive sheet (overlapping), over a glossy floor, plus a
+    small free-standing lamp. Scene order decides which of the coincident surfaces has the smaller ids."""
+    sc = abi.SceneArrays()
+    floor = sc.add_material(abi.MAT_PHONG, (0.6, 0.5, 0.4), (0.3, 0.3, 0.3), (0, 0, 0), 20.0)
+    sheet = sc.add_material(abi.MAT_PHONG, (0.2, 0.2, 0.2), (0.0, 0.0, 0.0), (0, 0, 0), 5.0)
+    em = sc.add_material(abi.MAT_PHONG, (0.5, 0.5, 0.5), (0, 0, 0), (30, 25, 20), 1.0)
+
+    def quad(x0, y0, x1, y1, z):
+        return np.float32([[[x0, y0, z], [x1, y0, z], [x1, y1, z]], [[x0, y0, z], [x1, y1, z], [x0, y1, z]]])
+
+    f = quad(-3, -3, 3, 3, 0.0)
+    sc.add_surface(f, np.broadcast_to(np.float32([0, 0, 1]), f.shape).copy(), floor)
+    big = quad(-2, -2, 2, 2, 2.0)
+    lamp = quad(-1.5, -1.5, 1.5, 1.5, 2.0)
+    order = [(lamp, em), (big, sheet)] if emitter_first else [(big, sheet), (lamp, em)]
+    for t, m in order:
+        sc.add_surface(t, np.broadcast_to(np.float32([0, 0, -1]), t.shape).copy(), m)
+    small_lamp = quad(2.2, 2.2, 2.8, 2.8, 1.0)
+    sc.add_surface(small_lamp, np.broadcast_to(np.float32([0, 0, -1]), small_lamp.shape).copy(), em)
+    return sc
+
+
+TWO_STEP_PARAMS = dict(M_Area=2, M_Brdf=3, doTemporalReuse=1, doSpatialReuse=1, doVisibilityPass=1, wavefront=1)
+
+
+@pytest.mark.parametrize("emitter_first", [True, False])
+def test_two_step_brdf_rays_with_coincident_emitter(emitter_first):
+    """BRDF-candidate rays go to the emissive-only BVH first and then ask the full BVH whether anything precedes the
+    emitter hit (same closest-hit order: smaller t, then smaller triangle id). Checked against the oracle's plain
+    closest-hit query with the emitter before and after the coincident sheet in scene order."""
+    sc = coincident_emitter_scene(emitter_first)
+    Wd, Hd = 48, 32
+    p = abi.default_params(**TWO_STEP_PARAMS)
+    o = ob.Oracle(Wd, Hd, seed=3, tracer=ob.TRACER_BRUTE)
+    e = eb.Emu(Wd, Hd, seed=3)
+    for x in (o, e):
+        x.upload_scene(sc)
+        x.set_params(p)
+    for fr in range(2):
+        cam = Camera(Wd, Hd, 70, (2.5, -2.6 + 0.1 * fr, 1.2), (0, 0, 0.3))
+        a, b = o.render_frame(cam, fr), e.render_frame(cam, fr)
+        assert np.array_equal(bits(a), bits(b)), f"frame {fr}: {(a != b).any(-1).sum()} px differ"
+        for buf in (abi.BUF_RES_POINT_WSUM, abi.BUF_RES_NORMAL_W, abi.BUF_RES_LIGHT_IDX):
+            assert np.array_equal(bits(o.readback(buf)), bits(e.readback(buf))), (fr, buf)
+    li = e.readback(abi.BUF_RES_LIGHT_IDX)[..., 0]
+    pts = e.readback(abi.BUF_RES_POINT_WSUM)
+    assert ((li >= 0) & (pts[..., 2] == 2.0)).any()  # reservoirs do hold samples on the coincident lamp

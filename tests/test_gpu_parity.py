@@ -11,7 +11,7 @@ import pytest
 import oracle_binding as ob
 from restir_embree_b200 import Camera, abi, scenes
 from restir_embree_b200.renderer import Renderer, make_rays
-from test_emu_parity import ALL_BUFS, CONFIGS, bits
+from test_emu_parity import ALL_BUFS, CONFIGS, TWO_STEP_PARAMS, bits, coincident_emitter_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -48,6 +48,27 @@ def test_gpu_frames_match_oracle_bit_for_bit(gpu, small, ci):
             oc = o.counters()
             assert oc["closest"] == t["rays_closest"] and oc["any_as_written"] == t["rays_any_as_written"]
             assert t["rays_any_traced"] <= t["rays_any_as_written"]
+
+
+@pytest.mark.parametrize("emitter_first", [True, False])
+def test_gpu_two_step_brdf_rays_with_coincident_emitter(gpu, emitter_first):
+    """The emissive-only BVH + "does anything precede it" scheme of the BRDF-candidate rays against the oracle's plain
+    closest-hit query, on an emitter that coincides with a non-emissive sheet (tie decided by triangle id)."""
+    sc = coincident_emitter_scene(emitter_first)
+    Wd, Hd = 48, 32
+    p = abi.default_params(**TWO_STEP_PARAMS)
+    o = ob.Oracle(Wd, Hd, seed=3, tracer=ob.TRACER_BRUTE)
+    o.upload_scene(sc)
+    o.set_params(p)
+    with Renderer(Wd, Hd, seed=3) as r:
+        r.upload_scene(sc)
+        r.set_params(p)
+        for fr in range(2):
+            cam = Camera(Wd, Hd, 70, (2.5, -2.6 + 0.1 * fr, 1.2), (0, 0, 0.3))
+            a, b = o.render_frame(cam, fr), r.render_frame(cam, fr)
+            assert np.array_equal(bits(a), bits(b)), f"frame {fr}: {(a != b).any(-1).sum()} px differ"
+            for buf in (abi.BUF_RES_POINT_WSUM, abi.BUF_RES_NORMAL_W, abi.BUF_RES_LIGHT_IDX):
+                assert np.array_equal(bits(o.readback(buf)), bits(r.readback(buf))), (fr, buf)
 
 
 def test_ray_seam_matches_brute_force(gpu):
