@@ -264,9 +264,17 @@ def run_ours(args):
     stream_by_pass = {n: float(sm[i]) if wave else med[n] for i, n in enumerate(names)}
     dom = max(("visibility", "temporal", "spatial", "shade"), key=lambda k: stream_by_pass[k])
     achieved = PASS_BYTES[dom] * band_px / (stream_by_pass[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if wave and os.path.exists(tpath):  # DRAM bytes per launch of the pass's two streaming kernels, from the committed ncu capture
+        tk = json.load(open(tpath))["kernels"]
+        ks = ["k_%s_stream" % dom, "k_%s_resolve" % dom] if dom != "shade" else ["k_shade"]
+        if all(k in tk for k in ks):
+            traffic = sum(tk[k]["dram_bytes_per_launch"] for k in ks) * band_px / float(WIDTH * HEIGHT)
     roof = {"bound": "hbm", "kernel": ("k_%s_stream+k_%s_resolve" % (dom, dom)) if wave else "k_" + dom,
             "achieved": achieved, "peak": hbm, "unit": "GB/s",
-            "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+            "frac": achieved / hbm, "traffic": traffic, "traffic_unit": "bytes per frame (both kernels of the pass)",
+            "algorithmic_bytes": PASS_BYTES[dom] * band_px, "peak_source": hbm_src,
             "algorithmic_bytes_per_px": PASS_BYTES[dom],
             "note": "reservoir pass with the largest streaming-kernel time; traversal runs in separate persistent kernels "
                     "(see traversal{}), which are latency/issue-bound SM work, not a bandwidth roofline" if wave else

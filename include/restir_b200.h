@@ -187,7 +187,9 @@ typedef enum RbBufferId {
   RB_BUF_FRAME_RGB = 10,       /* float3 frame_data (linear HDR)    */
   RB_BUF_ALIAS_PROB = 11,      /* float  [n_emissive]                */
   RB_BUF_ALIAS_IDX = 12,       /* uint32 [n_emissive]                */
-  RB_BUF_LIGHT_CDF = 13        /* float  [n_emissive]                */
+  RB_BUF_LIGHT_CDF = 13,       /* float  [n_emissive]                */
+  RB_BUF_ACCUMULATOR = 14,     /* float3 running mean of frame_data (rb_accumulate_display) */
+  RB_BUF_DISPLAY = 15          /* float4 tonemapped, gamma-compressed display_data          */
 } RbBufferId;
 
 /* Ray seam records.  RbRay has the 48-byte layout of RTCRay
@@ -296,6 +298,24 @@ int32_t rb_halo_rows(RbHandle h);
 size_t rb_halo_bytes(RbHandle h, int32_t rows);
 int rb_halo_export(RbHandle h, int32_t y, int32_t rows, void* dst_host);
 int rb_halo_import(RbHandle h, int32_t y, int32_t rows, const void* src_host);
+
+/* ---- The step after the path: SimpleGuiDX11::Producer's accumulate / tonemap / statistics loops,
+ * P/simpleguidx11.cpp:246-253 (accumulator = glm::mix(accumulator, frame_data, 1 / (accFrameCtr + 1))), :262-295
+ * (display_data = {compress(aces(accumulator)), 1}: Utils::aces P/utils.cpp:190-197 when RenderParams::tonemap,
+ * Utils::compress :220-230 when Raytracer::gammaCorrect) and :308-326 (accumulatorMean / accumulatorVariance over
+ * the per-pixel channel mean, in double). Runs on the frame the handle rendered last; everything stays on the
+ * device unless display_rgba_out (host, w*h*4 floats, band rows written) is given. OIDN denoising is not part
+ * of it (closed binary). With bands, the statistics are those of the band's rows: sums are returned so that a
+ * host can combine ranks. */
+typedef struct RbImageStats {
+  double sum;        /* sum over pixels of (r+g+b)/3 of the accumulator */
+  double sum_sq;     /* sum of its squares                              */
+  double mean;       /* sum / pixels            (accumulatorMean)       */
+  double variance;   /* sum_sq / pixels - mean^2 (accumulatorVariance)   */
+  uint64_t pixels;
+} RbImageStats;
+int rb_accumulate_display(RbHandle h, uint32_t acc_frame_ctr, int32_t tonemap, int32_t gamma_correct,
+                          float* display_rgba_out, RbImageStats* stats);
 
 #ifdef __cplusplus
 }

@@ -355,6 +355,22 @@ void ref_cdf_pick(void* h, float* out2) {
     if (cdf.tris[i] == &s.triangle) idx = (int)i;
   out2[0] = (float)idx, out2[1] = s.pdf;
 }
+// the Producer loop's post-path arithmetic: Utils::aces, Utils::compress (P/utils.cpp:190-197,
+// 220-230) and the accumulator update glm::mix(acc, frame, 1 / (accFrameCtr + 1)) (P/simpleguidx11.cpp:251)
+void ref_aces(float* rgb) {
+  glm::vec3 v{rgb[0], rgb[1], rgb[2]};
+  Utils::aces(v);
+  rgb[0] = v.x, rgb[1] = v.y, rgb[2] = v.z;
+}
+float ref_compress(float u) {
+  Utils::compress(u);
+  return u;
+}
+void ref_accumulate_mix(float* acc, const float* frame, int accFrameCtr) {
+  glm::vec3 a{acc[0], acc[1], acc[2]}, f{frame[0], frame[1], frame[2]};
+  a = glm::mix(a, f, 1.0f / static_cast<float>(accFrameCtr + 1));
+  acc[0] = a.x, acc[1] = a.y, acc[2] = a.z;
+}
 int ref_sanitize(float* rgb) {
   glm::vec3 v{rgb[0], rgb[1], rgb[2]};
   bool ch = Integrator::sanitize(v, false);

@@ -476,6 +476,7 @@ struct Oracle {
   std::vector<Reservoir> res[3];
   int readIdx = 0, writeIdx = 1, lastIdx = 2;
   std::vector<float> frame;
+  std::vector<float> accumulator, display;  // N1: P/simpleguidx11.h:153,156
   uint32_t frameIdx = 0;
   Counters ctrs[256];  // one slot per OpenMP thread
   std::string err;
@@ -1247,6 +1248,75 @@ int orc_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rg
   return 0;
 }
 
+// ---- after the path: the Producer loop's accumulate / tonemap / statistics ----------------------------
+// Utils::aces, P/utils.cpp:190-197 (float constants a..e; glm vec3 arithmetic is component-wise; glm::clamp)
+static void ref_aces(float* x3, const Math&) {
+  const float a = 2.51, b = 0.03, c = 2.43, d = 0.59, e = 0.14;
+  for (int i = 0; i < 3; ++i) {
+    const float x = x3[i];
+    const float v = (x * (a * x + b)) / (x * (c * x + d) + e);
+    x3[i] = std::min(std::max(v, 0.0f), 1.0f);  // glm::clamp = min(max(x, minVal), maxVal)
+  }
+}
+// Utils::compress(float&), P/utils.cpp:220-230 — note the double literal in "u <= 0.0031308"
+static void ref_compress(float& u, const Math& m) {
+  if (u <= 0.0f)
+    u = 0.0f;
+  else if (u >= 1.0f)
+    u = 1.0f;
+  else if (u <= 0.0031308)
+    u *= 12.92f;
+  else
+    u = 1.055f * m.pow(u, 1.0f / 2.4f) - 0.055f;
+}
+void orc_aces(float* rgb) { ref_aces(rgb, Math{}); }
+float orc_compress(int math_mode, float u) {
+  Math m;
+  m.mode = math_mode;
+  ref_compress(u, m);
+  return u;
+}
+// test hook: put an arbitrary image into frame_data
+int orc_set_frame(void* h, const float* rgb) {
+  Oracle* o = (Oracle*)h;
+  o->frame.assign(rgb, rgb + (size_t)o->width * o->height * 3);
+  return 0;
+}
+// P/simpleguidx11.cpp:246-253 (accumulate), :262-295 (display), :308-326 (mean / variance), over the band rows
+int orc_accumulate_display(void* h, uint32_t acc_frame_ctr, int tonemap, int gamma_correct, float* display_rgba_out, double* stats4) {
+  Oracle* o = (Oracle*)h;
+  const size_t n = (size_t)o->width * o->height;
+  if (o->accumulator.size() != n * 3) o->accumulator.assign(n * 3, 0.0f);
+  if (o->display.size() != n * 4) o->display.assign(n * 4, 0.0f);
+  if (o->frame.size() != n * 3) return -1;
+  const float a = 1.0f / static_cast<float>(acc_frame_ctr + 1);
+  double pixelSum = 0, pixelSqrSum = 0;
+  for (int y = o->band_y0; y < o->band_y1; ++y)
+    for (int x = 0; x < o->width; ++x) {
+      const size_t offset = (size_t)y * o->width + x;
+      float* acc = &o->accumulator[3 * offset];
+      const float* fr = &o->frame[3 * offset];
+      for (int c = 0; c < 3; ++c) acc[c] = acc[c] * (1.0f - a) + fr[c] * a;  // glm::mix: x * (1 - a) + y * a
+      float pix[3] = {acc[0], acc[1], acc[2]};
+      if (tonemap) ref_aces(pix, o->math);
+      if (gamma_correct)
+        for (int c = 0; c < 3; ++c) ref_compress(pix[c], o->math);
+      float* dsp = &o->display[4 * offset];
+      dsp[0] = pix[0], dsp[1] = pix[1], dsp[2] = pix[2], dsp[3] = 1.0f;
+      const float pixelMean = (acc[0] + acc[1] + acc[2]) / 3.0f;
+      pixelSum += pixelMean;
+      pixelSqrSum += pixelMean * pixelMean;
+    }
+  const double count = (double)(o->band_y1 - o->band_y0) * o->width;
+  if (stats4) {
+    stats4[0] = pixelSum, stats4[1] = pixelSqrSum;
+    stats4[2] = pixelSum / count;
+    stats4[3] = pixelSqrSum / count - stats4[2] * stats4[2];
+  }
+  if (display_rgba_out) memcpy(display_rgba_out, o->display.data(), n * 16);
+  return 0;
+}
+
 // same ids and packed layouts as rb_readback (include/restir_b200.h RbBufferId)
 int orc_readback(void* h, int id, void* dst, size_t bytes) {
   Oracle* o = (Oracle*)h;
@@ -1328,6 +1398,14 @@ int orc_readback(void* h, int id, void* dst, size_t bytes) {
     case RB_BUF_FRAME_RGB:
       if (!need(n * 12)) return -1;
       memcpy(dst, o->frame.data(), n * 12);
+      return 0;
+    case RB_BUF_ACCUMULATOR:
+      if (!need(n * 12) || o->accumulator.size() != n * 3) return -1;
+      memcpy(dst, o->accumulator.data(), n * 12);
+      return 0;
+    case RB_BUF_DISPLAY:
+      if (!need(n * 16) || o->display.size() != n * 4) return -1;
+      memcpy(dst, o->display.data(), n * 16);
       return 0;
     case RB_BUF_ALIAS_PROB:
       if (!need(o->scene.alias_prob.size() * 4)) return -1;

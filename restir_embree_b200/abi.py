@@ -18,7 +18,7 @@ LS_CDF, LS_ALIAS = 0, 1
 
 (BUF_GBUF_POS_DEPTH, BUF_GBUF_NORMAL_SHIN, BUF_GBUF_DIFFUSE_IIM, BUF_GBUF_SPEC_TYPE, BUF_GBUF_EMISSION, BUF_HIT_IDS,
  BUF_RES_POINT_WSUM, BUF_RES_NORMAL_W, BUF_RES_LI_CONF, BUF_RES_LIGHT_IDX, BUF_FRAME_RGB, BUF_ALIAS_PROB, BUF_ALIAS_IDX,
- BUF_LIGHT_CDF) = range(14)
+ BUF_LIGHT_CDF, BUF_ACCUMULATOR, BUF_DISPLAY) = range(16)
 
 # (dtype, channels) of each readback buffer, per pixel unless noted
 BUFFER_LAYOUT = {
@@ -33,6 +33,8 @@ BUFFER_LAYOUT = {
     BUF_RES_LI_CONF: (np.float32, 4),
     BUF_RES_LIGHT_IDX: (np.int32, 1),
     BUF_FRAME_RGB: (np.float32, 3),
+    BUF_ACCUMULATOR: (np.float32, 3),
+    BUF_DISPLAY: (np.float32, 4),
 }
 
 
@@ -107,6 +109,11 @@ class RbTimings(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
+class RbImageStats(C.Structure):
+    _fields_ = [("sum", C.c_double), ("sum_sq", C.c_double), ("mean", C.c_double), ("variance", C.c_double),
+                ("pixels", C.c_uint64)]
+
+
 class RbCreateInfo(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint32),
                 ("band_y0", C.c_int32), ("band_y1", C.c_int32), ("collect_timings", C.c_int32),
@@ -143,7 +150,7 @@ EXPORTED_SYMBOLS = [
     "rb_trace_closest",
     "rb_trace_occluded", "rb_trace_closest_device", "rb_trace_occluded_device", "rb_scene_stats", "rb_comm_init",
     "rb_comm_unique_id", "rb_halo_bytes", "rb_halo_export", "rb_halo_import", "rb_halo_rows", "rb_frame_begin",
-    "rb_frame_spatial", "rb_frame_end",
+    "rb_frame_spatial", "rb_frame_end", "rb_accumulate_display",
 ]
 
 

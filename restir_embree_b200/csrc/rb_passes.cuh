@@ -1193,5 +1193,33 @@ RB_HD void shade_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cn
   o[2] = pixel.z;
 }
 
+// =====================================================================================
+// After the path: accumulate, tonemap, gamma (P/simpleguidx11.cpp:246-253, 262-295;
+// Utils::aces / Utils::compress, P/utils.cpp:190-197, 220-230)
+// =====================================================================================
+RB_HD float aces1(float x) {  // one channel of Utils::aces (float constants, glm::clamp)
+  const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+  return gclamp((x * (a * x + b)) / (x * (c * x + d) + e), 0.0f, 1.0f);
+}
+RB_HD float compress1(float u) {  // Utils::compress: linear -> sRGB; the 0.0031308 comparison is in double
+  if (u <= 0.0f) return 0.0f;
+  if (u >= 1.0f) return 1.0f;
+  if ((double)u <= 0.0031308) return u * 12.92f;
+  return 1.055f * dm::powf_(u, 1.0f / 2.4f) - 0.055f;
+}
+// returns the per-pixel channel mean of the new accumulator value (for the statistics)
+RB_HD float accumulate_display_pixel(const float* frame, float* accumulator, F4* display, size_t pi, float mix_a, bool tonemap,
+                                     bool gamma) {
+  const V3 f = v3(frame[3 * pi], frame[3 * pi + 1], frame[3 * pi + 2]);
+  const V3 acc0 = v3(accumulator[3 * pi], accumulator[3 * pi + 1], accumulator[3 * pi + 2]);
+  const V3 acc = acc0 * (1.0f - mix_a) + f * mix_a;  // glm::mix(x, y, a) = x * (1 - a) + y * a
+  accumulator[3 * pi] = acc.x, accumulator[3 * pi + 1] = acc.y, accumulator[3 * pi + 2] = acc.z;
+  V3 pix = acc;
+  if (tonemap) pix = v3(aces1(pix.x), aces1(pix.y), aces1(pix.z));
+  if (gamma) pix = v3(compress1(pix.x), compress1(pix.y), compress1(pix.z));
+  st4(display + pi, f4(pix, 1.0f));
+  return (acc.x + acc.y + acc.z) / 3.0f;
+}
+
 }  // namespace rb
 #endif

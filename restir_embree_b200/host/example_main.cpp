@@ -37,7 +37,7 @@ int main() {
     raytracer.LoadScene(scene);
     raytracer.params.M_Area = 32;
     raytracer.params.doVisibilityPass = raytracer.params.doTemporalReuse = raytracer.params.doSpatialReuse = true;
-    std::vector<float> frame_data((size_t)W * H * 3);
+    std::vector<float> frame_data((size_t)W * H * 3), display_data((size_t)W * H * 4);
     Camera camera(W, H, 55.0f, {1.877986f, -7.724095f, 1.602229f}, {0, 0, 0});  // P/tutorials.cpp:35
     for (uint32_t frameCtr = 0; frameCtr < 4; ++frameCtr) {
       camera.setPosition({1.877986f + 0.05f * frameCtr, -7.724095f, 1.602229f});
@@ -50,6 +50,14 @@ int main() {
                   raytracer.timings.ms_temporal, raytracer.timings.ms_spatial, raytracer.timings.ms_shade);
       if (!(mean > 0.0) || mean != mean) {
         std::printf("FAIL: empty or NaN image\n");
+        return 1;
+      }
+      // the rest of the Producer loop: accumulate, tonemap + gamma into display_data, accumulator statistics
+      raytracer.accumulateAndDisplay(frameCtr, /*tonemap*/ true, /*gammaCorrect*/ true, display_data.data());
+      std::printf("         accumulatorMean %.6f accumulatorVariance %.6f display[0] = (%.3f %.3f %.3f %.1f)\n", raytracer.accumulatorMean,
+                  raytracer.accumulatorVariance, display_data[0], display_data[1], display_data[2], display_data[3]);
+      if (display_data[3] != 1.0f || !(raytracer.accumulatorMean > 0.0)) {
+        std::printf("FAIL: display / statistics\n");
         return 1;
       }
     }

@@ -190,6 +190,17 @@ class Renderer {
     check(rb_render_frame(h_, &c, frameCtr, frame_data, &timings), "rb_render_frame");
   }
 
+  // the rest of SimpleGuiDX11::Producer's loop body after produceRestir (P/simpleguidx11.cpp:246-326): accumulate the
+  // frame, fill display_data (width*height float4, may be null: kept on the device), update accumulatorMean /
+  // accumulatorVariance. accFrameCtr, tonemap and gammaCorrect are the reference's members of the same names.
+  void accumulateAndDisplay(uint32_t accFrameCtr, bool tonemap, bool gammaCorrect, float* display_data) {
+    RbImageStats st{};
+    check(rb_accumulate_display(h_, accFrameCtr, tonemap ? 1 : 0, gammaCorrect ? 1 : 0, display_data, &st), "rb_accumulate_display");
+    accumulatorMean = st.mean;
+    accumulatorVariance = st.variance;
+  }
+  double accumulatorMean{0}, accumulatorVariance{0};  // P/simpleguidx11.h:103-104
+
   ReSTIRIntegrator params;  // edit like the reference's statics
   RbTimings timings{};      // gBUfferFillDuration ... totalFrameDuration of P/simpleguidx11.h:120-127
   RbHandle handle() const { return h_; }

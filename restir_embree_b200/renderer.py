@@ -67,6 +67,7 @@ def load_library():
     L.rb_frame_begin.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32]
     L.rb_frame_spatial.argtypes = [H, C.c_int32]
     L.rb_frame_end.argtypes = [H, C.c_void_p, C.POINTER(abi.RbTimings)]
+    L.rb_accumulate_display.argtypes = [H, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(abi.RbImageStats)]
     if L.rb_abi_version() != 1:
         raise RestirError("librestir_b200.so ABI version mismatch")
     _lib = L
@@ -169,6 +170,17 @@ class Renderer:
         if want_timings:
             return _timings_dict(t)
         return None
+
+    def accumulate_display(self, acc_frame_ctr, tonemap=True, gamma_correct=True, fetch=False, want_stats=True):
+        """The Producer loop's step after produceRestir (P/simpleguidx11.cpp:246-326): accumulate the frame just
+        rendered, tonemap + gamma-compress into display_data, image mean / variance. Returns (display or None, stats)."""
+        out = np.zeros((self.height, self.width, 4), dtype=np.float32) if fetch else None
+        st = abi.RbImageStats() if want_stats else None
+        rc = self.L.rb_accumulate_display(self.h, int(acc_frame_ctr), int(bool(tonemap)), int(bool(gamma_correct)),
+                                          out.ctypes.data if fetch else None, C.byref(st) if want_stats else None)
+        self._check(rc, "rb_accumulate_display")
+        stats = dict(sum=st.sum, sum_sq=st.sum_sq, mean=st.mean, variance=st.variance, pixels=st.pixels) if want_stats else None
+        return out, stats
 
     def synchronize(self):
         self._check(self.L.rb_synchronize(self.h), "rb_synchronize")

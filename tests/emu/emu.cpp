@@ -43,7 +43,8 @@ struct Emu {
     std::vector<int> li;
   } rs[3];
   int gCur = 0, rRead = 0, rWrite = 1, rLast = 2;
-  std::vector<float> frame;
+  std::vector<float> frame, accumulator;
+  std::vector<F4> display;
   unsigned long long counters[8] = {0};
   CamState prevCam{};
   std::string err;
@@ -543,6 +544,25 @@ void emu_counters(void* h, uint64_t* out3) {
   out3[0] = E->counters[0], out3[1] = E->counters[1], out3[2] = E->counters[2];
 }
 
+// N1: the kernel body of k_accumulate_display, serial sums
+int emu_accumulate_display(void* h, uint32_t acc_frame_ctr, int tonemap, int gamma_correct, float* display_rgba_out, double* stats4) {
+  Emu* E = (Emu*)h;
+  const size_t n = (size_t)E->width * E->height;
+  if (E->accumulator.size() != n * 3) E->accumulator.assign(n * 3, 0.0f);
+  if (E->display.size() != n) E->display.assign(n, F4{0, 0, 0, 0});
+  const float mix_a = 1.0f / (float)(acc_frame_ctr + 1u);
+  double s = 0, s2 = 0;
+  for (size_t pi = (size_t)E->y0 * E->width; pi < (size_t)E->y1 * E->width; ++pi) {
+    const float pm = accumulate_display_pixel(E->frame.data(), E->accumulator.data(), E->display.data(), pi, mix_a, tonemap != 0, gamma_correct != 0);
+    s += (double)pm;
+    s2 += (double)(pm * pm);
+  }
+  const double count = (double)(E->y1 - E->y0) * E->width;
+  if (stats4) stats4[0] = s, stats4[1] = s2, stats4[2] = s / count, stats4[3] = s2 / count - (s / count) * (s / count);
+  if (display_rgba_out) memcpy(display_rgba_out, E->display.data(), n * 16);
+  return 0;
+}
+
 int emu_readback(void* h, int id, void* dst, size_t bytes) {
   Emu* E = (Emu*)h;
   const Emu::GStore& G = E->gs[E->gCur ^ 1];
@@ -561,6 +581,8 @@ int emu_readback(void* h, int id, void* dst, size_t bytes) {
     case RB_BUF_RES_LI_CONF: src = R.c.data(), need = R.c.size() * 16; break;
     case RB_BUF_RES_LIGHT_IDX: src = R.li.data(), need = R.li.size() * 4; break;
     case RB_BUF_FRAME_RGB: src = E->frame.data(), need = E->frame.size() * 4; break;
+    case RB_BUF_ACCUMULATOR: src = E->accumulator.data(), need = E->accumulator.size() * 4; break;
+    case RB_BUF_DISPLAY: src = E->display.data(), need = E->display.size() * 16; break;
     case RB_BUF_ALIAS_PROB: src = E->hs.alias_prob.data(), need = E->hs.alias_prob.size() * 4; break;
     case RB_BUF_ALIAS_IDX: src = E->hs.alias_idx.data(), need = E->hs.alias_idx.size() * 4; break;
     case RB_BUF_LIGHT_CDF: src = E->hs.cdf.data(), need = E->hs.cdf.size() * 4; break;

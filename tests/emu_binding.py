@@ -42,6 +42,7 @@ def lib():
         L.emu_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.emu_trace_occluded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.emu_validate_bvh.argtypes = [C.c_void_p]
+        L.emu_accumulate_display.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.emu_frame_begin.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32]
         L.emu_frame_spatial.argtypes = [C.c_void_p, C.c_int]
         L.emu_frame_end.argtypes = [C.c_void_p, C.c_void_p]
@@ -119,6 +120,13 @@ class Emu:
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         assert buf.nbytes == rows * self.width * 52
         assert self.L.emu_halo_import(self.h, y, rows, buf.ctypes.data) == 0
+
+    def accumulate_display(self, acc_frame_ctr, tonemap=True, gamma_correct=True):
+        out = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        st = np.zeros(4, dtype=np.float64)
+        assert self.L.emu_accumulate_display(self.h, int(acc_frame_ctr), int(bool(tonemap)), int(bool(gamma_correct)),
+                                             out.ctypes.data, st.ctypes.data) == 0
+        return out, dict(sum=st[0], sum_sq=st[1], mean=st[2], variance=st[3])
 
     def counters(self):
         c = np.zeros(3, dtype=np.uint64)

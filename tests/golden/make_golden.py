@@ -87,6 +87,23 @@ def main():
         pdf[i] = R.ref_phong_evalPdf(elems[i].ctypes.data, cams[i].ctypes.data, wi[i].ctypes.data)
         R.ref_phong_sampleBRDF(elems[i].ctypes.data, cams[i].ctypes.data, smp[i].ctypes.data)
     out.update(phong_elems=elems, phong_cams=cams, phong_wi=wi, phong_brdf=brdf, phong_pdf=pdf, phong_samples_seed11=smp)
+    # post-path arithmetic: Utils::aces / Utils::compress / the accumulator's glm::mix
+    rng = np.random.default_rng(21)
+    hdr = np.concatenate([rng.random((200, 3)) * np.float32(4.0), rng.random((40, 3)) * np.float32(0.01),
+                          np.float32([[0, 0, 0], [1, 1, 1], [100, 50, 3], [0.0031308, 0.0031309, 0.003]])]).astype(np.float32)
+    aces = hdr.copy()
+    for i in range(aces.shape[0]):
+        R.ref_aces(aces[i].ctypes.data)
+    u = np.concatenate([hdr.reshape(-1), np.float32([-1.0, 0.0, 1.0, 2.0, 0.0031308, 0.5])]).astype(np.float32)
+    comp = np.array([R.ref_compress(float(x)) for x in u], dtype=np.float32)
+    acc = np.zeros((16, 3), dtype=np.float32)
+    frames = (rng.random((16, 8, 3)) * 3).astype(np.float32)
+    hist = np.zeros((16, 8, 3), dtype=np.float32)
+    for p in range(16):
+        for k in range(8):
+            R.ref_accumulate_mix(acc[p].ctypes.data, frames[p, k].ctypes.data, k)
+            hist[p, k] = acc[p]
+    out.update(post_hdr=hdr, post_aces=aces, post_u=u, post_compress=comp, post_frames=frames, post_acc_hist=hist)
     cfgs = np.array([repr(c) for c in CONFIGS])
     out = {k: v for k, v in out.items() if not (isinstance(v, np.ndarray) and v.dtype == object)}
     np.savez_compressed(os.path.join(HERE, "ref_golden.npz"), configs=cfgs, **out)

@@ -40,6 +40,11 @@ def lib():
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(abi.RbParams)]
         L.orc_render_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.c_void_p]
         L.orc_readback.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.orc_accumulate_display.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_set_frame.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_aces.argtypes = [C.c_void_p]
+        L.orc_compress.restype = C.c_float
+        L.orc_compress.argtypes = [C.c_int, C.c_float]
         L.orc_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_num_emissive.argtypes = [C.c_void_p]
         L.orc_num_emissive.restype = C.c_uint32
@@ -111,6 +116,19 @@ class Oracle:
         rc = self.L.orc_render_frame(self.h, C.byref(c), frame_idx, out.ctypes.data, times.ctypes.data)
         assert rc == 0, rc
         return (out, times) if want_times else out
+
+    def set_frame(self, rgb):
+        a = np.ascontiguousarray(rgb, dtype=np.float32)
+        assert a.size == self.width * self.height * 3
+        assert self.L.orc_set_frame(self.h, a.ctypes.data) == 0
+
+    def accumulate_display(self, acc_frame_ctr, tonemap=True, gamma_correct=True):
+        out = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        st = np.zeros(4, dtype=np.float64)
+        rc = self.L.orc_accumulate_display(self.h, int(acc_frame_ctr), int(bool(tonemap)), int(bool(gamma_correct)),
+                                           out.ctypes.data, st.ctypes.data)
+        assert rc == 0, rc
+        return out, dict(sum=st[0], sum_sq=st[1], mean=st[2], variance=st[3])
 
     def readback(self, buf):
         dt, ch = abi.BUFFER_LAYOUT[buf]

@@ -41,6 +41,10 @@ def lib():
         R.ref_phong_sampleBRDF.argtypes = [C.c_void_p] * 3
         R.ref_cdf_pick.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_sanitize.argtypes = [C.c_void_p]
+        R.ref_aces.argtypes = [C.c_void_p]
+        R.ref_compress.restype = C.c_float
+        R.ref_compress.argtypes = [C.c_float]
+        R.ref_accumulate_mix.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _lib = R
     return _lib
 

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_struct_layouts_match_the_header(built):
     names = ["RbMaterial", "RbSurface", "RbSceneDesc", "RbParams", "RbCamera", "RbTimings", "RbCreateInfo", "RbRay",
-             "RbHit", "RbSceneStats"]
+             "RbHit", "RbSceneStats", "RbImageStats"]
     prog = '#include <stdio.h>\n#include "restir_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:

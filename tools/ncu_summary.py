@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (ncu --set full) into a small CSV that can be committed under profiles/.
 
-  python tools/ncu_summary.py gpurun_out/r2_prof.ncu-rep profiles/r1_full_summary.csv
+  python tools/ncu_summary.py gpurun_out/r2_prof.ncu-rep profiles/r1_full_summary.csv [profiles/traffic.json]
 
 One row per profiled launch: duration, achieved DRAM traffic, issue-slot utilisation, occupancy, SIMT
 efficiency, cache hit rates, pipe utilisation and the top stall reasons.
@@ -58,6 +58,26 @@ def main():
             st.sort(reverse=True)
             w.writerow([r[col["ID"]], name] + vals + [" ".join(f"{n}={v:.2f}" for v, n in st[:4])])
     print("wrote", out, len(data), "launches")
+    # per-kernel DRAM traffic per launch (bytes), for bench.py's roofline.traffic
+    if len(sys.argv) > 3:
+        import json
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        agg = {}
+        for r in data:
+            name = r[col["Kernel Name"]].replace("<unnamed>::", "").split("(")[0].replace("void ", "")
+            rd = float(r[col["dram__bytes_read.sum"]]) * scale[units[col["dram__bytes_read.sum"]]]
+            wr = float(r[col["dram__bytes_write.sum"]]) * scale[units[col["dram__bytes_write.sum"]]]
+            a = agg.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "time_ms": 0.0})
+            a["launches"] += 1
+            a["dram_bytes"] += rd + wr
+            tu = units[col["gpu__time_duration.sum"]]
+            a["time_ms"] += float(r[col["gpu__time_duration.sum"]]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(tu, 1.0)
+        for a in agg.values():
+            a["dram_bytes_per_launch"] = a.pop("dram_bytes") / a["launches"]
+            a["time_ms_per_launch"] = a.pop("time_ms") / a["launches"]
+        json.dump({"source": rep.split("/")[-1], "note": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch",
+                   "kernels": agg}, open(sys.argv[3], "w"), indent=1)
+        print("wrote", sys.argv[3])
 
 
 if __name__ == "__main__":
