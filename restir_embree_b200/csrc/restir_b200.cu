@@ -40,10 +40,13 @@ __device__ __forceinline__ void flush_counts(unsigned long long* ctr, const Cnt&
 // One thread per pixel, 8x4 pixels per warp. VIS is the visibility policy: InlineVis (trace on the spot),
 // GenVis (stream half: emit rays), ResolveVis (resolve half: read traced results). COUNT: whether this launch
 // contributes to the ray counters (the stream half of a pass does not: the resolve half counts the same rays).
-#define RB_PIXEL_KERNEL(NAME, VIS, COUNT, MINB, CALL)                          \
-  __global__ void __launch_bounds__(kTileW* kTileH, MINB) NAME(FrameCtx fc) {   \
+#define RB_PIXEL_KERNEL(NAME, VIS, COUNT, MINB, CALL) RB_PIXEL_KERNEL_T(NAME, VIS, COUNT, kTileW* kTileH, MINB, CALL)
+// THREADS = 8 x block height (launch_rows is told the same number): 128-thread CTAs give the register allocator a finer
+// occupancy ladder (e.g. 94 registers: two 256-thread CTAs = 16 warps, but five 128-thread CTAs = 20 warps)
+#define RB_PIXEL_KERNEL_T(NAME, VIS, COUNT, THREADS, MINB, CALL)               \
+  __global__ void __launch_bounds__(THREADS, MINB) NAME(FrameCtx fc) {         \
     const int x = blockIdx.x * kTileW + threadIdx.x;                           \
-    const int y = fc.y0 + blockIdx.y * kTileH + threadIdx.y;                   \
+    const int y = fc.y0 + blockIdx.y * blockDim.y + threadIdx.y;               \
     Cnt cnt = {0, 0, 0};                                                       \
     if (x < fc.width && y < fc.y1) {                                           \
       const VIS vis = {&fc, (uint32_t)(y * fc.width + x)};                     \
@@ -66,6 +69,8 @@ RB_PIXEL_KERNEL(k_gbuffer_resolve, ResolveVis, true, 2, gbuffer_resolve_pixel(fc
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL(k_initial_brdf_occ_stream, GenVis, false, 2, initial_brdf_occ_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 2, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL_T(k_initial_resolve_t128, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL_T(k_gbuffer_t128, InlineVis, true, 128, 5, gbuffer_pixel(fc, x, y, cnt))
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
@@ -117,13 +122,54 @@ constexpr int kTraceThreads = 128;
 #ifndef RB_TRACE_MINB
 #define RB_TRACE_MINB 8
 #endif
-template <bool ANY, bool TIE = false>
-__global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(SceneDev sc, const RayQ* __restrict__ rays,
-                                                               const uint32_t* __restrict__ count_ptr, uint32_t capacity,
-                                                               uint32_t* __restrict__ next, uint8_t* __restrict__ occ,
-                                                               HitRec* __restrict__ hits, float tnear, int refill_lanes,
-                                                               int tri_lanes) {
-  const uint32_t count = min(*count_ptr, capacity);
+// where the rays come from and where the results go: the frame's ray queue, or the RbRay / RbHit arrays of the ray seam
+struct QueueIO {
+  const RayQ* rays;
+  const uint32_t* count_ptr;
+  uint32_t capacity;
+  uint8_t* occ;
+  HitRec* hits;
+  float tnear;
+  __device__ uint32_t count() const { return min(*count_ptr, capacity); }
+  __device__ void fetch(uint32_t i, V3* o, V3* d, float* tn, float* tf, uint32_t* dest) const {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(&rays[i].o_tfar));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(&rays[i].d_dest));
+    *o = v3(a.x, a.y, a.z), *d = v3(b.x, b.y, b.z), *tn = tnear, *tf = a.w, *dest = __float_as_uint(b.w);
+  }
+  __device__ uint32_t tie_id(uint32_t dest) const { return hits[dest].tri; }  // written by the previous trace
+  __device__ void put_any(uint32_t dest, bool hit) const { occ[dest] = hit ? 1 : 0; }
+  __device__ void put_closest(const SceneDev&, uint32_t dest, const Trav& T) const { hits[dest] = T.best; }
+};
+struct SeamIO {
+  const RbRay* rays;
+  uint32_t n;
+  uint8_t* occ;
+  RbHit* hits;
+  __device__ uint32_t count() const { return n; }
+  __device__ void fetch(uint32_t i, V3* o, V3* d, float* tn, float* tf, uint32_t* dest) const {
+    const float4* p = reinterpret_cast<const float4*>(rays + i);  // RTCRay layout, 48 bytes
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const float c = __ldg(reinterpret_cast<const float*>(p + 2));
+    *o = v3(a.x, a.y, a.z), *d = v3(b.x, b.y, b.z), *tn = a.w, *tf = c, *dest = i;
+  }
+  __device__ uint32_t tie_id(uint32_t) const { return 0u; }
+  __device__ void put_any(uint32_t dest, bool hit) const { occ[dest] = hit ? 1 : 0; }
+  __device__ void put_closest(const SceneDev& sc, uint32_t dest, const Trav& T) const {
+    RbHit o;
+    if (T.best.tri != 0xFFFFFFFFu) {
+      const U4 info = sc.tri_info[T.best.tri];
+      o.t = T.best.t, o.u = T.best.u, o.v = T.best.v, o.primID = info.y, o.geomID = info.x;
+    } else {
+      o.t = T.tfar, o.u = 0, o.v = 0, o.primID = 0xFFFFFFFFu, o.geomID = 0xFFFFFFFFu;
+    }
+    hits[dest] = o;
+  }
+};
+
+template <bool ANY, bool TIE, class IO>
+__global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(SceneDev sc, IO io, uint32_t* __restrict__ next,
+                                                                              int refill_lanes, int tri_lanes) {
+  const uint32_t count = io.count();
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xFFFFFFFFu;
   Trav T;
@@ -144,18 +190,18 @@ __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(Sc
       if (!active) {
         const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
         if (i < count) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(&rays[i].o_tfar));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(&rays[i].d_dest));
-          dest = __float_as_uint(b.w);
-          active = trav_init(T, sc, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), tnear, a.w);
-          if (TIE) T.tie_id = hits[dest].tri;  // the hit this ray asks about (written by the previous trace)
+          V3 o, d;
+          float tn, tf;
+          io.fetch(i, &o, &d, &tn, &tf, &dest);
+          active = trav_init(T, sc, o, d, tn, tf);
+          if (TIE) T.tie_id = io.tie_id(dest);
           tsp = RB_STACK_MAX;
           tg = U2{0u, 0u};
           if (!active) {  // cannot hit anything
             if (ANY)
-              occ[dest] = 0;
+              io.put_any(dest, false);
             else
-              hits[dest] = T.best;
+              io.put_closest(sc, dest, T);
           }
         }
       }
@@ -192,9 +238,9 @@ __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(Sc
       // ---- finished rays ------------------------------------------------------------------------------------
       if (active && (done || (!has_node_work(T) && tg.y == 0))) {
         if (ANY)
-          occ[dest] = T.hit_any ? 1 : 0;
+          io.put_any(dest, T.hit_any);
         else
-          hits[dest] = T.best;
+          io.put_closest(sc, dest, T);
         active = false;
       }
       const int busy = __popc(__ballot_sync(FULL, active));
@@ -205,29 +251,6 @@ __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(Sc
 __global__ void k_reset_queue(uint32_t* count, uint32_t* next) {
   *count = 0;
   *next = 0;
-}
-
-// ---- ray seam ------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_trace_closest(SceneDev sc, const RbRay* rays, RbHit* hits, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const RbRay r = rays[i];
-  HitRec h;
-  const bool hit = trace8<false>(sc, v3(r.org_x, r.org_y, r.org_z), v3(r.dir_x, r.dir_y, r.dir_z), r.tnear, r.tfar, &h);
-  RbHit o;
-  if (hit) {
-    const U4 info = sc.tri_info[h.tri];
-    o.t = h.t, o.u = h.u, o.v = h.v, o.primID = info.y, o.geomID = info.x;
-  } else {
-    o.t = r.tfar, o.u = 0, o.v = 0, o.primID = 0xFFFFFFFFu, o.geomID = 0xFFFFFFFFu;
-  }
-  hits[i] = o;
-}
-__global__ void __launch_bounds__(256) k_trace_any(SceneDev sc, const RbRay* rays, uint8_t* occ, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const RbRay r = rays[i];
-  occ[i] = trace8<true>(sc, v3(r.org_x, r.org_y, r.org_z), v3(r.dir_x, r.dir_y, r.dir_z), r.tnear, r.tfar, nullptr) ? 1 : 0;
 }
 
 // ---- BVH build -----------------------------------------------------------------------
@@ -321,6 +344,7 @@ struct RbContext {
   // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
   int refillLanes = 26, postponeLanes = 8, traceBlocksPerSM = 8;
   bool waveGbuf = false;
+  int tile128 = 0;  // RB_TILE128 bit 0: G-buffer, bit 1: initial resolve in 128-thread CTAs (experiment)
   bool twoStepBrdf = true;  // RB_TWO_STEP_BRDF=0 traces the BRDF-candidate rays against the full BVH instead
 
   // wavefront buffers
@@ -551,6 +575,7 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
     if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
     if (const char* e = getenv("RB_WAVE_GBUF")) h->waveGbuf = atoi(e) != 0;
+    if (const char* e = getenv("RB_TILE128")) h->tile128 = atoi(e);
     if (const char* e = getenv("RB_TWO_STEP_BRDF")) h->twoStepBrdf = atoi(e) != 0;
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
@@ -956,17 +981,18 @@ static void fs_bind(RbContext* h) {
   fc.Rwrite = h->R[h->rWrite];
   fc.Rlast = h->R[h->rLast];
 }
-static dim3 rows_grid(const FrameCtx& fc, int ry0, int ry1) {
-  return dim3((fc.width + kTileW - 1) / kTileW, (std::max(ry1 - ry0, 0) + kTileH - 1) / kTileH);
+static dim3 rows_grid(const FrameCtx& fc, int ry0, int ry1, int tileH) {
+  return dim3((fc.width + kTileW - 1) / kTileW, (std::max(ry1 - ry0, 0) + tileH - 1) / tileH);
 }
 // launch a pixel kernel over image rows [ry0, ry1)
 template <class K>
-static void launch_rows(RbContext* h, K kernel, int ry0, int ry1) {
+static void launch_rows(RbContext* h, K kernel, int ry0, int ry1, int threads = kTileW * kTileH) {
   if (ry1 <= ry0) return;
   FrameCtx f = h->fs.fc;
   f.y0 = ry0;
   f.y1 = ry1;
-  kernel<<<rows_grid(f, ry0, ry1), dim3(kTileW, kTileH), 0, h->stream>>>(f);
+  const int tileH = threads / kTileW;
+  kernel<<<rows_grid(f, ry0, ry1, tileH), dim3(kTileW, tileH), 0, h->stream>>>(f);
   h->fs.launches++;
 }
 enum TraceMode { TRACE_CLOSEST = 0, TRACE_ANY = 1, TRACE_CLOSEST_EMISSIVE = 2, TRACE_ANY_PRECEDES = 3 };
@@ -975,15 +1001,16 @@ static void fs_trace(RbContext* h, int mode, int pass, float tnear = -1.0f) {
   if (tnear < 0.0f) tnear = FLT_MIN + P.tnearOffset;
   const int trace_grid = h->numSMs * h->traceBlocksPerSM;
   const WaveBufs& w = h->wave;
-#define RB_TRACE_ARGS(SC) SC, w.rays, w.count, w.capacity, w.count + 1, w.occ, w.hits, tnear, h->refillLanes, h->postponeLanes
+  const QueueIO io{w.rays, w.count, w.capacity, w.occ, w.hits, tnear};
+#define RB_TRACE_ARGS(SC) SC, io, w.count + 1, h->refillLanes, h->postponeLanes
   if (mode == TRACE_ANY)
-    k_trace_queue<true><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
+    k_trace_queue<true, false, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
   else if (mode == TRACE_CLOSEST)
-    k_trace_queue<false><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
+    k_trace_queue<false, false, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
   else if (mode == TRACE_CLOSEST_EMISSIVE)
-    k_trace_queue<false><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(emissive_view(h->sc)));
+    k_trace_queue<false, false, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(emissive_view(h->sc)));
   else
-    k_trace_queue<true, true><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
+    k_trace_queue<true, true, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
 #undef RB_TRACE_ARGS
   h->fs.launches++;
   fs_mark(h, pass, 1);
@@ -1063,7 +1090,10 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     fs_trace(h, TRACE_CLOSEST, 0, RB_PRIMARY_TNEAR);
     launch_rows(h, k_gbuffer_resolve, fc.gy0, fc.gy1);
   } else {
-    launch_rows(h, k_gbuffer, fc.gy0, fc.gy1);
+    if (h->tile128 & 1)
+      launch_rows(h, k_gbuffer_t128, fc.gy0, fc.gy1, 128);
+    else
+      launch_rows(h, k_gbuffer, fc.gy0, fc.gy1);
   }
   fs_mark(h, 0, 0);
   // ---- initial candidates ----------------------------------------------------------------------------
@@ -1085,7 +1115,9 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       }
     }
     // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel
-    if (P.doVisibilityPass)
+    if (P.doVisibilityPass && (h->tile128 & 2))
+      launch_rows(h, k_initial_resolve_t128, y0, y1, 128);
+    else if (P.doVisibilityPass)
       launch_rows(h, k_initial_resolve, y0, y1);
     else
       launch_rows(h, k_initial_resolve_inline_shadow, y0, y1);
@@ -1381,12 +1413,18 @@ static int trace_device(RbHandle h, const RbRay* rays, void* out, uint32_t n, bo
     if (ms_out) *ms_out = 0;
     return RB_OK;
   }
+  // the same persistent, phase-scheduled traversal kernel as the frame's ray queue, reading RTCRay records
+  if (!h->wave.count) RB_CUDA(cudaMalloc((void**)&h->wave.count, 2 * sizeof(uint32_t)));
   if (ms_out) RB_CUDA(cudaEventRecord(h->ev[14], h->stream));
-  const unsigned grid = (n + 255) / 256;
+  k_reset_queue<<<1, 1, 0, h->stream>>>(h->wave.count, h->wave.count + 1);
+  const int trace_grid = h->numSMs * h->traceBlocksPerSM;
+  const SeamIO io{rays, n, (uint8_t*)out, (RbHit*)out};
   if (any)
-    k_trace_any<<<grid, 256, 0, h->stream>>>(h->sc, rays, (uint8_t*)out, n);
+    k_trace_queue<true, false, SeamIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, h->wave.count + 1, h->refillLanes,
+                                                                                    h->postponeLanes);
   else
-    k_trace_closest<<<grid, 256, 0, h->stream>>>(h->sc, rays, (RbHit*)out, n);
+    k_trace_queue<false, false, SeamIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, h->wave.count + 1, h->refillLanes,
+                                                                                     h->postponeLanes);
   RB_CUDA(cudaGetLastError());
   if (ms_out) {
     RB_CUDA(cudaEventRecord(h->ev[15], h->stream));

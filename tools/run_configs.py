@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Runs the BASELINE.json configs other than the bench line through the C ABI on one GPU and prints one JSON line
+each (they are parity-test / microbench cases, not the headline):
+
+  python tools/run_configs.py room      configs[0] stand-in: ~200 k triangles, 1280x720, A=32 B=1, temporal + 1 spatial pass
+  python tools/run_configs.py 10m       configs[2] on ONE GPU: 10 M triangles, 100 k emitters, 3840x2160, 3 spatial passes k=5
+  python tools/run_configs.py rays      configs[3]: 33 M shadow rays (16 per 1080p pixel) against the 10 M-triangle BVH,
+                                        coherent (pixel order) and shuffled, through rb_trace_occluded_device
+  python tools/run_configs.py orbit64   configs[4]: 64-frame orbit at 1080p on the 1 M scene: fps, temporal-reuse statistics,
+                                        per-frame relMSE of sampled rows against the CPU oracle (bit-exact => 0)
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from restir_embree_b200 import Camera, abi, scenes  # noqa: E402
+from restir_embree_b200.renderer import Renderer, make_rays  # noqa: E402
+
+
+def params(**kw):
+    base = dict(M_Area=32, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1, spatialReuseNeighborCount=5,
+                spatialPassCount=1, spatialReuseRadius=30.0, lightSampler=abi.LS_ALIAS, wavefront=1)
+    base.update(kw)
+    return abi.default_params(**base)
+
+
+def frames(r, scene, W, H, n, warm=3, fov=55, cam_fn=None):
+    c = scene.meta["center"]
+    cam_fn = cam_fn or (lambda t: Camera(W, H, fov, scenes.orbit_position(c, t), c))
+    for f in range(warm):
+        r.render_frame_device(cam_fn(f), f)
+    r.synchronize()
+    r.timer_begin()
+    for f in range(warm, warm + n):
+        r.render_frame_device(cam_fn(f), f)
+    ms = r.timer_end()
+    t = r.render_frame_device(cam_fn(warm + n), warm + n, want_timings=True)
+    return ms / n, t
+
+
+def run_frames(name, scene_name, W, H, n, **pk):
+    t0 = time.time()
+    sc = scenes.scene_config(scene_name)
+    gen_s = time.time() - t0
+    with Renderer(W, H, seed=123) as r:
+        st = r.upload_scene(sc)
+        r.set_params(params(**pk))
+        ms, t = frames(r, sc, W, H, n)
+        rays = t["rays_closest"] + t["rays_any_as_written"]
+        print(json.dumps({"config": name, "width": W, "height": H, "ms_per_frame": ms, "fps": 1e3 / ms,
+                          "mrays_s_as_written": rays / (ms * 1e-3) / 1e6, "rays_traced": t["rays_closest"] + t["rays_any_traced"],
+                          "per_pass_ms": {k[3:]: t[k] for k in ("ms_gbuffer", "ms_initial", "ms_visibility", "ms_temporal", "ms_spatial", "ms_shade")},
+                          "scene": {k: st[k] for k in ("n_triangles", "n_emissive", "n_bvh_nodes", "bvh_depth", "build_ms")},
+                          "scene_generation_s": gen_s}))
+
+
+def run_rays():
+    import torch
+    sc = scenes.scene_config("10m")
+    W, H = 1920, 1080
+    with Renderer(W, H, seed=123) as r:
+        st = r.upload_scene(sc)
+        r.set_params(params())
+        c = sc.meta["center"]
+        r.render_frame(Camera(W, H, 55, scenes.orbit_position(c, 0), c), 0, fetch=False)
+        pos = r.readback(abi.BUF_GBUF_POS_DEPTH).reshape(-1, 4)
+        ids = r.readback(abi.BUF_HIT_IDS).reshape(-1, 2)
+        P = pos[ids[:, 0] != 0xFFFFFFFF, :3]
+        em = np.concatenate([p for p, _, m in sc.surfaces if sum(sc.materials[m]["emission"]) > 0], 0)
+        rng = np.random.default_rng(3)
+        per_px = 16
+        out = {"config": "rays", "scene": {k: st[k] for k in ("n_triangles", "n_bvh_nodes", "build_ms")}}
+        origins = np.repeat(P, per_px, axis=0)[: 33177600]
+        n = origins.shape[0]
+        k = rng.integers(0, len(em), n)
+        b = rng.random((n, 2), dtype=np.float32)
+        sq = np.sqrt(b[:, :1])
+        T = em[k, 0] * (1 - sq) + em[k, 1] * (sq * (1 - b[:, 1:])) + em[k, 2] * (sq * b[:, 1:])
+        rays = make_rays(origins, target=T.astype(np.float32))
+        for label, order in (("coherent", None), ("shuffled", rng.permutation(n))):
+            rr = rays if order is None else rays[order]
+            d_rays = torch.from_numpy(rr.view(np.uint8).reshape(-1)).cuda()
+            d_occ = torch.empty(n, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            ms = [r.trace_device(d_rays.data_ptr(), d_occ.data_ptr(), n, True) for _ in range(3)]
+            out[label] = {"rays": int(n), "ms": float(min(ms)), "mrays_s": n / (min(ms) * 1e-3) / 1e6,
+                          "occluded_fraction": float(d_occ.float().mean().item())}
+        print(json.dumps(out))
+
+
+def run_orbit64():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    sc = scenes.scene_config("1m")
+    W, H = 1920, 1080
+    band, margin = (500, 548), 16  # the oracle renders a band; rows `margin` inside it are valid for the first frames
+    p = params()
+    c = sc.meta["center"]
+    o = ob.Oracle(W, H, seed=123, tracer=ob.TRACER_BVH2)
+    o.upload_scene(sc)
+    o.set_params(p)
+    o.set_band(*band)
+    rows = (band[0] + margin, band[1] - margin)
+    with Renderer(W, H, seed=123) as r:
+        r.upload_scene(sc)
+        r.set_params(p)
+        worst, ms_all, keep = 0.0, [], []
+        acc = None
+        for f in range(64):
+            cam = Camera(W, H, 55, scenes.orbit_position(c, f), c)
+            img, t = r.render_frame(cam, f, want_timings=True)
+            ms_all.append(t["ms_total"])
+            r.accumulate_display(f, fetch=False, want_stats=False)
+            if f < 2:  # (band-edge effects move inwards by the reuse reach every frame)
+                ref = o.render_frame(cam, f)
+                a, b = img[rows[0]:rows[1]], ref[rows[0]:rows[1]]
+                worst = max(worst, float(ob.relmse(a, b)))
+        accum = r.readback(abi.BUF_ACCUMULATOR)
+        print(json.dumps({"config": "orbit64", "frames": 64, "fps_median": 1e3 / float(np.median(ms_all[3:])),
+                          "relmse_vs_oracle_rows_516_532_first_2_frames_max": worst,
+                          "accumulator_mean": float(accum.mean()), "accumulator_finite": bool(np.isfinite(accum).all())}))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "room"
+    if what == "room":
+        run_frames("configs[0] room stand-in", "room", 1280, 720, 20)
+    elif what == "10m":
+        run_frames("configs[2] on one GPU", "10m", 3840, 2160, 6, spatialPassCount=3)
+    elif what == "rays":
+        run_rays()
+    elif what == "orbit64":
+        run_orbit64()
+    else:
+        raise SystemExit(__doc__)
