@@ -250,6 +250,7 @@ def run_ours(args):
     n_any_w = sumr(float(np.median(rays["any_w"])))
     n_any_t = sumr(float(np.median(rays["any_t"])))
     if rank != 0:
+        shutdown(r, world)
         return
     ms_step = ms / args.steps
     fps = 1e3 / ms_step
@@ -302,9 +303,31 @@ def run_ours(args):
                     "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
                     "note": "rb_render_frame with a pinned host frame_data buffer; scene resident (uploaded once like the reference)"},
             "gpu_launches": int(launches) * args.steps}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    shutdown(r, world)
+
+
+def shutdown(renderer, world):
+    """Every rank leaves the same way: close the handle (its NCCL communicator), then tear the process group down
+    together. A rank that returned early used to leave rank 0 waiting inside destroy_process_group until the
+    launcher's timeout; a watchdog makes sure a stuck teardown cannot hold the job either."""
+    import torch.distributed as dist
     if world > 1:
-        dist.destroy_process_group()
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+    renderer.close()
+    if world > 1:
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

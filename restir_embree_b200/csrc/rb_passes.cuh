@@ -29,7 +29,8 @@ struct RayQ {
 };
 struct WaveBufs {
   RayQ* rays;
-  uint32_t* count;  // number of rays queued (device counter)
+  uint32_t* count;  // {rays queued, next ray to fetch} (device counters); two such pairs alternate between passes
+  uint32_t* reset_pair;  // stream kernels zero the pair of the PREVIOUS pass here (nullptr otherwise): no reset launches
   uint32_t capacity;
   uint8_t* occ;  // any-hit results   [slot * npix + pixel]
   HitRec* hits;  // closest results   [slot * npix + pixel]

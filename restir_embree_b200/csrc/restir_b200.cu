@@ -48,6 +48,8 @@ __device__ __forceinline__ void flush_counts(unsigned long long* ctr, const Cnt&
     const int x = blockIdx.x * kTileW + threadIdx.x;                           \
     const int y = fc.y0 + blockIdx.y * blockDim.y + threadIdx.y;               \
     Cnt cnt = {0, 0, 0};                                                       \
+    if (fc.wave.reset_pair != nullptr && (blockIdx.x | blockIdx.y | threadIdx.x | threadIdx.y) == 0)   \
+      fc.wave.reset_pair[0] = 0u, fc.wave.reset_pair[1] = 0u;                  \
     if (x < fc.width && y < fc.y1) {                                           \
       const VIS vis = {&fc, (uint32_t)(y * fc.width + x)};                     \
       (void)vis;                                                               \
@@ -350,6 +352,8 @@ struct RbContext {
   // wavefront buffers
   WaveBufs wave{};
   size_t waveRayCap = 0, waveOccCap = 0, waveHitCap = 0, waveCandCap = 0;
+  uint32_t* waveCounters = nullptr;
+  int wavePair = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -611,7 +615,7 @@ void rb_destroy(RbHandle h) {
   if (h->wave.occ) cudaFree(h->wave.occ);
   if (h->wave.hits) cudaFree(h->wave.hits);
   if (h->wave.cand) cudaFree(h->wave.cand);
-  if (h->wave.count) cudaFree(h->wave.count);
+  if (h->waveCounters) cudaFree(h->waveCounters);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->commStream) cudaStreamDestroy(h->commStream);
   if (h->evHaloReady) cudaEventDestroy(h->evHaloReady);
@@ -918,6 +922,18 @@ static CamState cam_state(const RbCamera* c) {
   return s;
 }
 
+// three {count, next} pairs: two alternate between the passes of a frame (a stream kernel zeroes the pair of the
+// previous pass, so no reset launches), the third belongs to the ray seam
+static int ensure_counters(RbContext* h) {
+  if (h->waveCounters) return RB_OK;
+  RB_CUDA(cudaMalloc((void**)&h->waveCounters, 6 * sizeof(uint32_t)));
+  RB_CUDA(cudaMemsetAsync(h->waveCounters, 0, 6 * sizeof(uint32_t), h->stream));
+  h->wavePair = 0;
+  h->wave.count = h->waveCounters;
+  h->wave.reset_pair = nullptr;
+  return RB_OK;
+}
+
 // wavefront buffers sized for `slots` rays per band pixel
 static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32_t cand_slots) {
   const size_t npix = (size_t)h->info.width * h->info.height;
@@ -953,9 +969,7 @@ static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32
     RB_CUDA(cudaMalloc((void**)&h->wave.hits, (size_t)brdf_slots * npix * sizeof(HitRec)));
     h->waveHitCap = (size_t)brdf_slots * npix;
   }
-  if (!h->wave.count) {
-    RB_CUDA(cudaMalloc((void**)&h->wave.count, 2 * sizeof(uint32_t)));
-  }
+  RB_TRY(ensure_counters(h));
   h->wave.capacity = (uint32_t)h->waveRayCap;
   h->wave.npix = (uint32_t)npix;
   return RB_OK;
@@ -1012,12 +1026,19 @@ static void fs_trace(RbContext* h, int mode, int pass, float tnear = -1.0f) {
   else
     k_trace_queue<true, true, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
 #undef RB_TRACE_ARGS
+  h->wave.reset_pair = nullptr;
+  h->fs.fc.wave.reset_pair = nullptr;
   h->fs.launches++;
   fs_mark(h, pass, 1);
 }
+// start a new ray queue: switch to the other counter pair (already zero) and let the coming stream kernel zero this one
 static void fs_reset_queue(RbContext* h) {
-  k_reset_queue<<<1, 1, 0, h->stream>>>(h->wave.count, h->wave.count + 1);
-  h->fs.launches++;
+  uint32_t* old_pair = h->waveCounters + 2 * h->wavePair;
+  h->wavePair ^= 1;
+  h->wave.count = h->waveCounters + 2 * h->wavePair;
+  h->wave.reset_pair = old_pair;
+  h->fs.fc.wave.count = h->wave.count;
+  h->fs.fc.wave.reset_pair = old_pair;
 }
 
 static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool timed) {
@@ -1414,16 +1435,17 @@ static int trace_device(RbHandle h, const RbRay* rays, void* out, uint32_t n, bo
     return RB_OK;
   }
   // the same persistent, phase-scheduled traversal kernel as the frame's ray queue, reading RTCRay records
-  if (!h->wave.count) RB_CUDA(cudaMalloc((void**)&h->wave.count, 2 * sizeof(uint32_t)));
+  RB_TRY(ensure_counters(h));
+  uint32_t* seam_pair = h->waveCounters + 4;
   if (ms_out) RB_CUDA(cudaEventRecord(h->ev[14], h->stream));
-  k_reset_queue<<<1, 1, 0, h->stream>>>(h->wave.count, h->wave.count + 1);
+  k_reset_queue<<<1, 1, 0, h->stream>>>(seam_pair, seam_pair + 1);
   const int trace_grid = h->numSMs * h->traceBlocksPerSM;
   const SeamIO io{rays, n, (uint8_t*)out, (RbHit*)out};
   if (any)
-    k_trace_queue<true, false, SeamIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, h->wave.count + 1, h->refillLanes,
+    k_trace_queue<true, false, SeamIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, seam_pair + 1, h->refillLanes,
                                                                                     h->postponeLanes);
   else
-    k_trace_queue<false, false, SeamIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, h->wave.count + 1, h->refillLanes,
+    k_trace_queue<false, false, SeamIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, seam_pair + 1, h->refillLanes,
                                                                                      h->postponeLanes);
   RB_CUDA(cudaGetLastError());
   if (ms_out) {
