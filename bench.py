@@ -201,6 +201,7 @@ def run_ours(args):
     stream_ms, trace_ms = [], []
     rays = {"closest": [], "any_w": [], "any_t": []}
     launches = 0
+    halo_ms = []
     for _ in range(max(3, min(args.steps, 10))):
         t = r.render_frame_device(camera_at(scene, frame), frame, want_timings=True)
         frame += 1
@@ -212,6 +213,7 @@ def run_ours(args):
         rays["any_w"].append(t["rays_any_as_written"])
         rays["any_t"].append(t["rays_any_traced"])
         launches = t["kernel_launches"]
+        halo_ms.append(t["ms_halo"])
     # ---- end to end through the public call with a HOST frame buffer ---------------------------------
     # (the same camera path as the device-resident leg: frames 0..W-1 untimed, then K timed)
     frame = 0
@@ -303,6 +305,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
                     "note": "rb_render_frame with a pinned host frame_data buffer; scene resident (uploaded once like the reference)"},
             "gpu_launches": int(launches) * args.steps}
+    if world > 1:
+        line["halo_exchange_ms"] = float(np.median(halo_ms))  # rank 0's NCCL send/recv group on the comm stream
     print(json.dumps(line), flush=True)
     shutdown(r, world)
 

@@ -158,7 +158,7 @@ typedef struct RbTimings {
   uint64_t rays_any_as_written; /* shadow rays the reference would issue */
   uint64_t rays_any_traced;     /* after exact-duplicate / zero-contribution elimination */
   uint32_t kernel_launches;
-  uint32_t reserved;
+  float ms_halo;                /* multi-GPU: duration of the frame's last reservoir-halo exchange on the comm stream */
 } RbTimings;
 
 typedef struct RbCreateInfo {

@@ -106,7 +106,7 @@ class RbTimings(C.Structure):
                 ("ms_total", C.c_float), ("ms_trace_any", C.c_float), ("ms_stream", C.c_float * 6),
                 ("ms_trace", C.c_float * 6), ("rays_closest", C.c_uint64),
                 ("rays_any_as_written", C.c_uint64), ("rays_any_traced", C.c_uint64), ("kernel_launches", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("ms_halo", C.c_float)]
 
 
 class RbImageStats(C.Structure):

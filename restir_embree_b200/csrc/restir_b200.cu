@@ -58,7 +58,7 @@ __device__ __forceinline__ void flush_counts(unsigned long long* ctr, const Cnt&
     if (COUNT) flush_counts(fc.counters, cnt);                                 \
   }
 
-RB_PIXEL_KERNEL(k_gbuffer, InlineVis, true, 1, gbuffer_pixel(fc, x, y, cnt))
+RB_PIXEL_KERNEL_T(k_gbuffer, InlineVis, true, 128, 5, gbuffer_pixel(fc, x, y, cnt))  // 94 regs: 5 x 4 warps instead of 2 x 8
 RB_PIXEL_KERNEL(k_initial, InlineVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility, InlineVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_temporal, InlineVis, true, 1, (temporal_pixel<InlineVis, false>(fc, x, y, vis, cnt)))
@@ -70,14 +70,12 @@ RB_PIXEL_KERNEL(k_gbuffer_stream, GenVis, false, 4, gbuffer_gen_pixel(fc, x, y, 
 RB_PIXEL_KERNEL(k_gbuffer_resolve, ResolveVis, true, 2, gbuffer_resolve_pixel(fc, x, y, cnt))
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL(k_initial_brdf_occ_stream, GenVis, false, 2, initial_brdf_occ_gen_pixel(fc, x, y, vis))
-RB_PIXEL_KERNEL(k_initial_resolve, ResolveVis, true, 2, initial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL_T(k_initial_resolve_t128, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL_T(k_gbuffer_t128, InlineVis, true, 128, 5, gbuffer_pixel(fc, x, y, cnt))
+RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))  // 95 regs, no spills
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_temporal_stream, GenVis, true, 3, temporal_gen_pixel<false>(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, true, 1, temporal_gen_pixel<true>(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, true, 3, temporal_gen_pixel<true>(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 4, temporal_merge_pixel(fc, x, y, cnt))
 // three resident CTAs per SM (<= 85 registers, a few spilled words) beat two for the reuse passes (measured, profiles/);
 // the initial pass is the other way round
@@ -330,7 +328,8 @@ struct RbContext {
   void* comm = nullptr;
   int commRank = 0, commSize = 1;
   cudaStream_t commStream = nullptr;
-  cudaEvent_t evHaloReady = nullptr, evHaloDone = nullptr;
+  cudaEvent_t evHaloReady = nullptr, evHaloDone = nullptr, evHaloT0 = nullptr;  // T0..Done time the exchange itself
+  bool haloTimed = false;
 
   // scene
   bool haveScene = false;
@@ -346,7 +345,6 @@ struct RbContext {
   // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
   int refillLanes = 26, postponeLanes = 8, traceBlocksPerSM = 8;
   bool waveGbuf = false;
-  int tile128 = 0;  // RB_TILE128 bit 0: G-buffer, bit 1: initial resolve in 128-thread CTAs (experiment)
   bool twoStepBrdf = true;  // RB_TWO_STEP_BRDF=0 traces the BRDF-candidate rays against the full BVH instead
 
   // wavefront buffers
@@ -453,6 +451,8 @@ static int halo_exchange_begin(RbContext* h) {
   const ResPlanes& P = h->R[h->rWrite];
   RB_CUDA(cudaEventRecord(h->evHaloReady, h->stream));
   RB_CUDA(cudaStreamWaitEvent(h->commStream, h->evHaloReady, 0));
+  RB_CUDA(cudaEventRecord(h->evHaloT0, h->commStream));
+  h->haloTimed = true;
   char* planes[4] = {(char*)P.point_wsum, (char*)P.normal_W, (char*)P.Li_conf, (char*)P.light_idx};
   const size_t esz[4] = {16, 16, 16, 4};
   RB_NCCL(g_nccl.GroupStart());
@@ -579,7 +579,6 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
     if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
     if (const char* e = getenv("RB_WAVE_GBUF")) h->waveGbuf = atoi(e) != 0;
-    if (const char* e = getenv("RB_TILE128")) h->tile128 = atoi(e);
     if (const char* e = getenv("RB_TWO_STEP_BRDF")) h->twoStepBrdf = atoi(e) != 0;
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
@@ -620,6 +619,7 @@ void rb_destroy(RbHandle h) {
   if (h->commStream) cudaStreamDestroy(h->commStream);
   if (h->evHaloReady) cudaEventDestroy(h->evHaloReady);
   if (h->evHaloDone) cudaEventDestroy(h->evHaloDone);
+  if (h->evHaloT0) cudaEventDestroy(h->evHaloT0);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1111,10 +1111,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     fs_trace(h, TRACE_CLOSEST, 0, RB_PRIMARY_TNEAR);
     launch_rows(h, k_gbuffer_resolve, fc.gy0, fc.gy1);
   } else {
-    if (h->tile128 & 1)
-      launch_rows(h, k_gbuffer_t128, fc.gy0, fc.gy1, 128);
-    else
-      launch_rows(h, k_gbuffer, fc.gy0, fc.gy1);
+    launch_rows(h, k_gbuffer, fc.gy0, fc.gy1, 128);
   }
   fs_mark(h, 0, 0);
   // ---- initial candidates ----------------------------------------------------------------------------
@@ -1136,10 +1133,8 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       }
     }
     // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel
-    if (P.doVisibilityPass && (h->tile128 & 2))
-      launch_rows(h, k_initial_resolve_t128, y0, y1, 128);
-    else if (P.doVisibilityPass)
-      launch_rows(h, k_initial_resolve, y0, y1);
+    if (P.doVisibilityPass)
+      launch_rows(h, k_initial_resolve, y0, y1, 128);
     else
       launch_rows(h, k_initial_resolve_inline_shadow, y0, y1);
   } else {
@@ -1270,6 +1265,7 @@ static int frame_end(RbHandle h, RbTimings* timings) {
         }
       }
       RB_CUDA(cudaEventElapsedTime(&timings->ms_total, h->fev[0], h->fev[F.marks.size()]));
+      if (h->comm && h->haloTimed) RB_CUDA(cudaEventElapsedTime(&timings->ms_halo, h->evHaloT0, h->evHaloDone));
     }
   }
   return RB_OK;
@@ -1546,7 +1542,8 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
   h->commSize = nranks;
   RB_CUDA(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
   RB_CUDA(cudaEventCreateWithFlags(&h->evHaloReady, cudaEventDisableTiming));
-  RB_CUDA(cudaEventCreateWithFlags(&h->evHaloDone, cudaEventDisableTiming));
+  RB_CUDA(cudaEventCreate(&h->evHaloDone));
+  RB_CUDA(cudaEventCreate(&h->evHaloT0));
   return RB_OK;
 }
 
