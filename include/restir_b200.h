@@ -280,7 +280,16 @@ int rb_scene_stats(RbHandle h, RbSceneStats* out);
  * top to bottom); afterwards rb_render_frame performs the halo exchange itself with grouped ncclSend/ncclRecv
  * on a side stream, overlapped with the spatial pass over the interior rows. nccl_unique_id is the 128-byte
  * ncclUniqueId made by rb_comm_unique_id on rank 0 and distributed by the launcher (torch.distributed, MPI,
- * a file). NCCL is loaded with dlopen at that point; single-GPU use needs no NCCL at all. */
+ * a file). NCCL is loaded with dlopen at that point; single-GPU use needs no NCCL at all.
+ *
+ * Load balancing: image bands do not cost the same (ceiling vs. floor), and a halo exchange is a rendezvous, so the
+ * slowest band sets the frame rate. With a communicator attached the library therefore moves the band boundaries:
+ * at every frame end each rank sends its neighbours the last-frame reservoirs of the 8 rows next to the boundary
+ * and its own frame cost (GPU time minus time spent waiting for neighbours; CUDA events), and at the next-but-one
+ * frame start both ranks that share a boundary move it by the same damped step (<= 7 rows) computed from the same
+ * two numbers. Rows that change owner find their last-frame reservoirs already there and their previous G-buffer in
+ * the margin; the image stays bit-identical to the one-band image (tools/check_nccl_bands.py). RB_BALANCE=0 turns it
+ * off; rb_get_band reports the rows currently owned (rb_render_frame writes exactly those rows of frame_rgb_out). */
 int rb_comm_unique_id(void* out_id, size_t id_bytes);
 int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes);
 
@@ -292,6 +301,12 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
  * reservoirs the next spatial pass will read (4 planes packed back to back: 16+16+16+4 bytes per pixel) to /
  * from host memory. rb_halo_rows gives the reach in rows for the current parameters. */
 int rb_frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx);
+/* Between frames a band may be moved (load balancing): the new rows must lie inside the rows whose G-buffer this
+ * handle rendered last frame (its band +- 16 rows), and the caller must first have brought over the LAST frame's
+ * reservoirs of the rows it gains (rb_halo_export / rb_halo_import outside a frame act on exactly those). With
+ * rb_comm_init the library does all of this itself (see below). */
+int rb_set_band(RbHandle h, int32_t band_y0, int32_t band_y1);
+int rb_get_band(RbHandle h, int32_t* band_y0, int32_t* band_y1); /* the rows the NEXT frame will render */
 int rb_frame_spatial(RbHandle h, int32_t pass_index);
 int rb_frame_end(RbHandle h, float* frame_rgb_out, RbTimings* timings);
 int32_t rb_halo_rows(RbHandle h);

@@ -330,6 +330,19 @@ struct RbContext {
   cudaStream_t commStream = nullptr;
   cudaEvent_t evHaloReady = nullptr, evHaloDone = nullptr, evHaloT0 = nullptr;  // T0..Done time the exchange itself
   bool haloTimed = false;
+  // load balancing of the bands (rb_comm_init): every frame end the last-frame reservoirs of kShipRows rows on both
+  // sides of each boundary and the ranks' frame costs go to the neighbours; boundaries follow the cost difference
+  static constexpr int kShipRows = 8, kBalRing = 4, kMaxStalls = 8;
+  bool balance = true;
+  uint32_t balFrame = 0;                         // frames rendered since rb_comm_init
+  cudaEvent_t evShipReady = nullptr, evShipDone = nullptr;
+  cudaEvent_t evBalCopied[kBalRing]{};           // costs of ring slot arrived in balHost
+  cudaEvent_t evFrameB[kBalRing]{}, evFrameE[kBalRing]{};
+  cudaEvent_t evStallA[kBalRing][kMaxStalls]{}, evStallB[kBalRing][kMaxStalls]{};
+  int nStalls[kBalRing]{};
+  float* balDev = nullptr;                       // [6]: {cost, rows} of this rank, of the rank above, of the rank below
+  float* balHost = nullptr;                      // pinned, [kBalRing][8]: the same three pairs as sent / received
+  bool shipPending = false;
 
   // scene
   bool haveScene = false;
@@ -475,9 +488,105 @@ static int halo_exchange_begin(RbContext* h) {
   RB_CUDA(cudaEventRecord(h->evHaloDone, h->commStream));
   return RB_OK;
 }
+// main stream waits for an event of the comm stream; the wait is bracketed by two events so that the frame's cost
+// (what the balancer equalises) can leave the time spent waiting for a slower neighbour out
+static int wait_recording_stall(RbContext* h, cudaEvent_t ev) {
+  const int slot = (int)(h->balFrame % RbContext::kBalRing);
+  const bool rec = h->balance && h->nStalls[slot] < RbContext::kMaxStalls;
+  if (rec) RB_CUDA(cudaEventRecord(h->evStallA[slot][h->nStalls[slot]], h->stream));
+  RB_CUDA(cudaStreamWaitEvent(h->stream, ev, 0));
+  if (rec) RB_CUDA(cudaEventRecord(h->evStallB[slot][h->nStalls[slot]++], h->stream));
+  return RB_OK;
+}
 static int halo_exchange_wait(RbContext* h) {
   if (!h->comm) return RB_OK;
-  RB_CUDA(cudaStreamWaitEvent(h->stream, h->evHaloDone, 0));
+  return wait_recording_stall(h, h->evHaloDone);
+}
+
+// End of frame: ship the final reservoirs (R[rLast]) of kShipRows rows on both sides of each boundary plus this
+// rank's cost of an earlier frame to the neighbours (one NCCL group on the comm stream, overlapped with the next
+// frame's G-buffer / initial / visibility passes).
+static int balance_ship_begin(RbContext* h) {
+  if (!h->comm || !h->balance) return RB_OK;
+  const int y0 = h->info.band_y0, y1 = h->info.band_y1, W = h->info.width, H = h->info.height;
+  const int S = RbContext::kShipRows;
+  const int slot = (int)(h->balFrame % RbContext::kBalRing);
+  // my cost: GPU time of the frame before last, minus its waits (its events are complete or nearly so; this also keeps
+  // the host at most two frames ahead of the device)
+  float cost = 0.0f;
+  if (h->balFrame >= 2) {
+    const int ps = (int)((h->balFrame - 2) % RbContext::kBalRing);
+    RB_CUDA(cudaEventSynchronize(h->evFrameE[ps]));
+    RB_CUDA(cudaEventElapsedTime(&cost, h->evFrameB[ps], h->evFrameE[ps]));
+    for (int i = 0; i < h->nStalls[ps]; ++i) {
+      float st = 0;
+      RB_CUDA(cudaEventElapsedTime(&st, h->evStallA[ps][i], h->evStallB[ps][i]));
+      cost -= st;
+    }
+    if (!(cost > 0.0f)) cost = 0.0f;
+  }
+  float* hostSlot = h->balHost + 8 * slot;
+  hostSlot[0] = cost, hostSlot[1] = (float)(y1 - y0);
+  hostSlot[2] = hostSlot[3] = hostSlot[4] = hostSlot[5] = -1.0f;
+  const ResPlanes& P = h->R[h->rLast];
+  RB_CUDA(cudaEventRecord(h->evShipReady, h->stream));
+  RB_CUDA(cudaStreamWaitEvent(h->commStream, h->evShipReady, 0));
+  RB_CUDA(cudaMemcpyAsync(h->balDev, hostSlot, 8, cudaMemcpyHostToDevice, h->commStream));
+  char* planes[4] = {(char*)P.point_wsum, (char*)P.normal_W, (char*)P.Li_conf, (char*)P.light_idx};
+  const size_t esz[4] = {16, 16, 16, 4};
+  RB_NCCL(g_nccl.GroupStart());
+  if (h->commRank > 0) {
+    const int r = std::min(S, y1 - y0), ru = std::min(S, y0);
+    for (int i = 0; i < 4; ++i) {
+      RB_NCCL(g_nccl.Send(planes[i] + (size_t)y0 * W * esz[i], (size_t)r * W * esz[i], 0, h->commRank - 1, h->comm, h->commStream));
+      RB_NCCL(g_nccl.Recv(planes[i] + (size_t)(y0 - ru) * W * esz[i], (size_t)ru * W * esz[i], 0, h->commRank - 1, h->comm, h->commStream));
+    }
+    RB_NCCL(g_nccl.Send(h->balDev, 8, 0, h->commRank - 1, h->comm, h->commStream));
+    RB_NCCL(g_nccl.Recv(h->balDev + 2, 8, 0, h->commRank - 1, h->comm, h->commStream));
+  }
+  if (h->commRank + 1 < h->commSize) {
+    const int r = std::min(S, y1 - y0), rd = std::min(S, H - y1);
+    for (int i = 0; i < 4; ++i) {
+      RB_NCCL(g_nccl.Send(planes[i] + (size_t)(y1 - r) * W * esz[i], (size_t)r * W * esz[i], 0, h->commRank + 1, h->comm, h->commStream));
+      RB_NCCL(g_nccl.Recv(planes[i] + (size_t)y1 * W * esz[i], (size_t)rd * W * esz[i], 0, h->commRank + 1, h->comm, h->commStream));
+    }
+    RB_NCCL(g_nccl.Send(h->balDev, 8, 0, h->commRank + 1, h->comm, h->commStream));
+    RB_NCCL(g_nccl.Recv(h->balDev + 4, 8, 0, h->commRank + 1, h->comm, h->commStream));
+  }
+  RB_NCCL(g_nccl.GroupEnd());
+  RB_CUDA(cudaMemcpyAsync(hostSlot + 2, h->balDev + 2, 16, cudaMemcpyDeviceToHost, h->commStream));
+  RB_CUDA(cudaEventRecord(h->evBalCopied[slot], h->commStream));
+  RB_CUDA(cudaEventRecord(h->evShipDone, h->commStream));
+  h->shipPending = true;
+  return RB_OK;
+}
+
+// Start of frame: move this rank's two boundaries. A boundary is moved by BOTH ranks that share it, from the same two
+// numbers (the costs the two exchanged two frame ends ago), so they always agree. A step is at most kShipRows - 1
+// rows: the rows a rank gains had their last-frame reservoirs shipped at the previous frame end and their previous
+// G-buffer rendered as margin.
+static int balance_boundary_step(float cost_up, float cost_dn, float rows_up_sent, float rows_dn_sent) {
+  if (!(cost_up > 0.0f) || !(cost_dn > 0.0f) || !(rows_up_sent > 0.0f) || !(rows_dn_sent > 0.0f)) return 0;
+  // rows the upper band should lose so that the two costs meet, damped by one half
+  const float want = 0.5f * (cost_up - cost_dn) / (cost_up + cost_dn) * (rows_up_sent + rows_dn_sent);
+  int step = (int)lrintf(0.5f * want);
+  const int lim = RbContext::kShipRows - 1;
+  step = std::max(-lim, std::min(lim, step));
+  // Keep both bands tall enough. Heights are the ones EXCHANGED with the costs (both sides hold the same numbers);
+  // since then each band can have lost at most 2 * lim rows in the one update in between, and may lose lim more at
+  // its other boundary in this one.
+  const int min_rows = 2 * RbContext::kShipRows, slack = 3 * lim;
+  step = std::min(step, std::max(0, (int)rows_up_sent - slack - min_rows));
+  step = std::max(step, -std::max(0, (int)rows_dn_sent - slack - min_rows));
+  return step;  // the boundary moves UP by `step` rows
+}
+static int balance_update_band(RbContext* h) {
+  if (!h->comm || !h->balance || h->balFrame < 4) return RB_OK;
+  const int slot = (int)((h->balFrame - 2) % RbContext::kBalRing);  // the exchange of two frame ends ago
+  RB_CUDA(cudaEventSynchronize(h->evBalCopied[slot]));
+  const float* c = h->balHost + 8 * slot;  // {cost, rows} x {this rank as sent, rank above, rank below}
+  if (h->commRank > 0) h->info.band_y0 -= balance_boundary_step(c[2], c[0], c[3], c[1]);
+  if (h->commRank + 1 < h->commSize) h->info.band_y1 -= balance_boundary_step(c[0], c[4], c[1], c[5]);
   return RB_OK;
 }
 
@@ -620,6 +729,19 @@ void rb_destroy(RbHandle h) {
   if (h->evHaloReady) cudaEventDestroy(h->evHaloReady);
   if (h->evHaloDone) cudaEventDestroy(h->evHaloDone);
   if (h->evHaloT0) cudaEventDestroy(h->evHaloT0);
+  if (h->evShipReady) cudaEventDestroy(h->evShipReady);
+  if (h->evShipDone) cudaEventDestroy(h->evShipDone);
+  for (int i = 0; i < RbContext::kBalRing; ++i) {
+    if (h->evBalCopied[i]) cudaEventDestroy(h->evBalCopied[i]);
+    if (h->evFrameB[i]) cudaEventDestroy(h->evFrameB[i]);
+    if (h->evFrameE[i]) cudaEventDestroy(h->evFrameE[i]);
+    for (int j = 0; j < RbContext::kMaxStalls; ++j) {
+      if (h->evStallA[i][j]) cudaEventDestroy(h->evStallA[i][j]);
+      if (h->evStallB[i][j]) cudaEventDestroy(h->evStallB[i][j]);
+    }
+  }
+  if (h->balDev) cudaFree(h->balDev);
+  if (h->balHost) cudaFreeHost(h->balHost);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1097,6 +1219,12 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   fc.gpy0 = h->havePrev ? h->prevGy0 : 0;
   fc.gpy1 = h->havePrev ? h->prevGy1 : 0;
 
+  const bool balancing = h->comm && h->balance;
+  const int bslot = (int)(h->balFrame % RbContext::kBalRing);
+  if (balancing) {
+    h->nStalls[bslot] = 0;
+    RB_CUDA(cudaEventRecord(h->evFrameB[bslot], st));
+  }
   RB_CUDA(cudaMemsetAsync(h->counters, 0, 64, st));
   if (timed) cudaEventRecord(h->fev[0], st);
   fs_bind(h);
@@ -1153,6 +1281,12 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       launch_rows(h, k_visibility, y0, y1);
     }
     fs_mark(h, 2, 0);
+  }
+  // the rows this band may have gained take their last-frame reservoirs from the neighbour: shipped at the previous
+  // frame end on the comm stream, needed from here on
+  if (balancing && h->shipPending) {
+    RB_TRY(wait_recording_stall(h, h->evShipDone));
+    h->shipPending = false;
   }
   // ---- temporal reuse ----------------------------------------------------------------------------------
   if (P.doTemporalReuse && frame_idx > 0 && h->havePrev) {
@@ -1240,6 +1374,11 @@ static int frame_end(RbHandle h, RbTimings* timings) {
   h->prevGy1 = fc.gy1;
   h->havePrev = true;
   F.open = false;
+  if (h->comm && h->balance) {
+    RB_CUDA(cudaEventRecord(h->evFrameE[h->balFrame % RbContext::kBalRing], st));
+    RB_TRY(balance_ship_begin(h));
+    h->balFrame++;
+  }
 
   if (timings) {
     memset(timings, 0, sizeof(*timings));
@@ -1274,6 +1413,7 @@ static int frame_end(RbHandle h, RbTimings* timings) {
 static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx, RbTimings* timings) {
   if (!h) return RB_ERR_INVALID_ARGUMENT;
   const bool timed = h->info.collect_timings != 0 && timings != nullptr;
+  RB_TRY(balance_update_band(h));
   RB_TRY(frame_begin(h, cam, frame_idx, timed));
   if (h->fs.P.doSpatialReuse)
     for (int i = 0; i < h->fs.P.spatialPassCount; ++i) RB_TRY(frame_spatial(h, i, h->comm != nullptr));
@@ -1286,6 +1426,27 @@ int rb_frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx) {
   return frame_begin(h, cam, frame_idx, h && h->info.collect_timings != 0);
 }
 int rb_frame_spatial(RbHandle h, int32_t pass_index) { return frame_spatial(h, pass_index, false); }
+int rb_get_band(RbHandle h, int32_t* y0, int32_t* y1) {
+  if (!h || !y0 || !y1) return RB_ERR_INVALID_ARGUMENT;
+  *y0 = h->info.band_y0;
+  *y1 = h->info.band_y1;
+  return RB_OK;
+}
+int rb_set_band(RbHandle h, int32_t y0, int32_t y1) {
+  if (!h || y0 < 0 || y1 > h->info.height || y0 >= y1) return RB_ERR_INVALID_ARGUMENT;
+  if (h->fs.open) {
+    h->err = "rb_set_band: a frame is open";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  // the temporal pass reads last frame's G-buffer at its own pixels without a fallback: stay inside what was rendered
+  if (h->havePrev && (y0 < h->prevGy0 || y1 > h->prevGy1)) {
+    h->err = "rb_set_band: the band may only move within the rows whose G-buffer this handle rendered last frame";
+    return RB_ERR_UNSUPPORTED;
+  }
+  h->info.band_y0 = y0;
+  h->info.band_y1 = y1;
+  return RB_OK;
+}
 int rb_frame_end(RbHandle h, float* frame_rgb_out, RbTimings* timings) {
   int rc = frame_end(h, timings);
   if (rc != RB_OK) return rc;
@@ -1544,6 +1705,22 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
   RB_CUDA(cudaEventCreateWithFlags(&h->evHaloReady, cudaEventDisableTiming));
   RB_CUDA(cudaEventCreate(&h->evHaloDone));
   RB_CUDA(cudaEventCreate(&h->evHaloT0));
+  if (const char* e = getenv("RB_BALANCE")) h->balance = atoi(e) != 0;
+  RB_CUDA(cudaEventCreateWithFlags(&h->evShipReady, cudaEventDisableTiming));
+  RB_CUDA(cudaEventCreateWithFlags(&h->evShipDone, cudaEventDisableTiming));
+  for (int i = 0; i < RbContext::kBalRing; ++i) {
+    RB_CUDA(cudaEventCreateWithFlags(&h->evBalCopied[i], cudaEventDisableTiming));
+    RB_CUDA(cudaEventCreate(&h->evFrameB[i]));
+    RB_CUDA(cudaEventCreate(&h->evFrameE[i]));
+    for (int j = 0; j < RbContext::kMaxStalls; ++j) {
+      RB_CUDA(cudaEventCreate(&h->evStallA[i][j]));
+      RB_CUDA(cudaEventCreate(&h->evStallB[i][j]));
+    }
+  }
+  RB_CUDA(cudaMalloc((void**)&h->balDev, 6 * sizeof(float)));
+  RB_CUDA(cudaMallocHost((void**)&h->balHost, RbContext::kBalRing * 8 * sizeof(float)));
+  h->balFrame = 0;
+  h->shipPending = false;
   return RB_OK;
 }
 

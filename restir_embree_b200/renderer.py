@@ -66,6 +66,8 @@ def load_library():
     L.rb_halo_rows.argtypes = [H]
     L.rb_frame_begin.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32]
     L.rb_frame_spatial.argtypes = [H, C.c_int32]
+    L.rb_set_band.argtypes = [H, C.c_int32, C.c_int32]
+    L.rb_get_band.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rb_frame_end.argtypes = [H, C.c_void_p, C.POINTER(abi.RbTimings)]
     L.rb_accumulate_display.argtypes = [H, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(abi.RbImageStats)]
     if L.rb_abi_version() != 1:
@@ -235,6 +237,16 @@ class Renderer:
     def frame_end(self, out=None):
         ptr = out.ctypes.data if out is not None else None
         self._check(self.L.rb_frame_end(self.h, ptr, None), "rb_frame_end")
+
+    def set_band(self, y0, y1):
+        self._check(self.L.rb_set_band(self.h, int(y0), int(y1)), "rb_set_band")
+        self.band = (int(y0), int(y1))
+
+    def get_band(self):
+        """Rows the next frame renders (they move when the library balances the bands, rb_comm_init)."""
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._check(self.L.rb_get_band(self.h, C.byref(a), C.byref(b)), "rb_get_band")
+        return a.value, b.value
 
     def halo_rows(self):
         return int(self.L.rb_halo_rows(self.h))

@@ -38,3 +38,17 @@ def assemble(handles, buf):
         y0, y1 = r.band
         a[y0:y1] = x[y0:y1]
     return a
+
+
+def move_boundaries(handles, new_bounds):
+    """Load balancing between frames: ship the LAST frame's reservoirs of the rows that change owner (halo_export /
+    halo_import outside a frame act on them), then move the bands. new_bounds = [0, b1, ..., height]."""
+    for k in range(len(handles) - 1):
+        up, dn = handles[k], handles[k + 1]
+        old, new = up.band[1], new_bounds[k + 1]
+        if new > old:    # the upper band grows downwards: rows [old, new) come from the lower band
+            up.halo_import(old, new - old, dn.halo_export(old, new - old))
+        elif new < old:  # the lower band grows upwards
+            dn.halo_import(new, old - new, up.halo_export(new, old - new))
+    for k, r in enumerate(handles):
+        r.set_band(new_bounds[k], new_bounds[k + 1])

@@ -519,6 +519,13 @@ int emu_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rg
   return emu_frame_end(h, rgb_out);
 }
 
+int emu_set_band(void* h, int y0, int y1) {
+  Emu* E = (Emu*)h;
+  if (y0 < 0 || y1 > E->height || y0 >= y1 || E->open) return RB_ERR_INVALID_ARGUMENT;
+  if (E->havePrev && (y0 < E->prevGy0 || y1 > E->prevGy1)) return RB_ERR_UNSUPPORTED;
+  E->y0 = y0, E->y1 = y1;
+  return 0;
+}
 int emu_halo_rows(void* h) { return spatial_reach(((Emu*)h)->open ? ((Emu*)h)->Pf : ((Emu*)h)->P); }
 // rows [y, y+rows) of the reservoirs the next spatial pass reads: 4 planes packed back to back (52 B / px)
 static int emu_halo_copy(Emu* E, int y, int rows, char* host, bool to_host) {

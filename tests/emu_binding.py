@@ -47,6 +47,7 @@ def lib():
         L.emu_frame_spatial.argtypes = [C.c_void_p, C.c_int]
         L.emu_frame_end.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_halo_rows.argtypes = [C.c_void_p]
+        L.emu_set_band.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.emu_halo_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.emu_halo_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib = L
@@ -107,6 +108,11 @@ class Emu:
 
     def frame_end(self, out=None):
         assert self.L.emu_frame_end(self.h, out.ctypes.data if out is not None else None) == 0
+
+    def set_band(self, y0, y1):
+        rc = self.L.emu_set_band(self.h, int(y0), int(y1))
+        assert rc == 0, rc
+        self.band = (int(y0), int(y1))
 
     def halo_rows(self):
         return int(self.L.emu_halo_rows(self.h))

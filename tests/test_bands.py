@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import emu_binding as eb
-from band_driver import assemble, make_bands, render_banded
+from band_driver import assemble, make_bands, move_boundaries, render_banded
 from restir_embree_b200 import Camera, abi, scenes
 from restir_embree_b200.renderer import band_rows
 
@@ -58,6 +58,35 @@ def test_emulated_bands_are_bit_identical_to_one_band(ci, n):
         assert np.array_equal(bits(a), bits(b)), f"frame {f}: {(a != b).any(-1).sum()} px differ with {n} bands"
         for buf in (abi.BUF_RES_LIGHT_IDX, abi.BUF_RES_NORMAL_W, abi.BUF_HIT_IDS):
             assert np.array_equal(bits(one.readback(buf)), bits(assemble(bands, buf))), (f, buf)
+
+
+def _moving_bounds(n, f):
+    """band boundaries that wander by up to 7 rows per frame (inside the 16-row G-buffer margin)"""
+    base = [band_rows(H, n, r)[0] for r in range(n)] + [H]
+    shift = [0] + [((-1) ** k) * ((3 * f + 2 * k) % 8) for k in range(1, n)] + [0]
+    return [b + s for b, s in zip(base, shift)]
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_emulated_bands_with_moving_boundaries_are_bit_identical_to_one_band(n):
+    """Load balancing: band boundaries move between frames; the rows that change owner take the last frame's
+    reservoirs with them, everything else is re-derived (G-buffer margin). The image must not notice."""
+    sc = scenes.scene_config("small")
+    p = abi.default_params(**CFGS[0])
+    one = eb.Emu(W, H, seed=5)
+    one.upload_scene(sc)
+    one.set_params(p)
+    bands = make_bands(eb.Emu, W, H, n, seed=5)
+    for b in bands:
+        b.upload_scene(sc)
+        b.set_params(p)
+    for f in range(5):
+        if f > 0:
+            move_boundaries(bands, _moving_bounds(n, f))
+        a = one.render_frame(cams(f), f)
+        b = render_banded(bands, cams(f), f, p)
+        assert np.array_equal(bits(a), bits(b)), f"frame {f}: {(a != b).any(-1).sum()} px differ, bands {[x.band for x in bands]}"
+        assert np.array_equal(bits(one.readback(abi.BUF_RES_NORMAL_W)), bits(assemble(bands, abi.BUF_RES_NORMAL_W))), f
 
 
 def _gloo_worker(rank, world, port, q):
@@ -126,3 +155,25 @@ def test_gpu_bands_are_bit_identical_to_one_band(gpu, n):
             assert np.array_equal(bits(one.readback(abi.BUF_RES_LIGHT_IDX)), bits(assemble(bands, abi.BUF_RES_LIGHT_IDX)))
         for r in bands + [one]:
             r.close()
+
+
+@pytest.mark.gpu
+def test_gpu_bands_with_moving_boundaries_are_bit_identical_to_one_band(gpu):
+    from restir_embree_b200.renderer import Renderer
+    sc = scenes.scene_config("small")
+    p = abi.default_params(**CFGS[0])
+    one = Renderer(W, H, seed=5)
+    one.upload_scene(sc)
+    one.set_params(p)
+    bands = make_bands(Renderer, W, H, 3, seed=5)
+    for b in bands:
+        b.upload_scene(sc)
+        b.set_params(p)
+    for f in range(5):
+        if f > 0:
+            move_boundaries(bands, _moving_bounds(3, f))
+        a = one.render_frame(cams(f), f)
+        b = render_banded(bands, cams(f), f, p)
+        assert np.array_equal(bits(a), bits(b)), f"frame {f}: {(a != b).any(-1).sum()} px differ, bands {[x.band for x in bands]}"
+    for r in bands + [one]:
+        r.close()

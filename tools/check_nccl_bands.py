@@ -38,16 +38,24 @@ def main():
         full.upload_scene(sc)
         full.set_params(p)
     ok = True
-    for f in range(4):
+    bands_seen = []
+    for f in range(int(os.environ.get("CHECK_FRAMES", "14"))):
         cam = Camera(W, H, 60, (4.2 + 0.1 * f, -4.4, 1.8 + 0.2 * f), (0, 0, 1.0 + 0.15 * f))
+        band = torch.tensor(r.get_band(), dtype=torch.int32, device="cuda")  # the library balances the bands: they move
+        allb = [torch.zeros_like(band) for _ in range(world)]
+        dist.all_gather(allb, band)
+        bands_seen.append([tuple(int(v) for v in b.tolist()) for b in allb])
         img = torch.from_numpy(r.render_frame(cam, f)).cuda()
         dist.all_reduce(img)  # bands are disjoint, zero elsewhere
         if rank == 0:
             ref = full.render_frame(cam, f)
             got = img.cpu().numpy()
             same = np.array_equal(ref.view(np.uint32), got.view(np.uint32)) or np.array_equal(ref, got)
-            print(f"frame {f}: {world} bands over NCCL vs one band: {'bit-identical' if same else 'DIFFERENT'} "
-                  f"({(ref != got).any(-1).sum()} px differ)", flush=True)
+            bb = bands_seen[-1]
+            contiguous = bb[0][0] == 0 and bb[-1][1] == H and all(a[1] == b[0] for a, b in zip(bb[:-1], bb[1:]))
+            print(f"frame {f}: {world} bands {bb} over NCCL vs one band: {'bit-identical' if same else 'DIFFERENT'} "
+                  f"({(ref != got).any(-1).sum()} px differ){'' if contiguous else ' BANDS NOT CONTIGUOUS'}", flush=True)
+            same = same and contiguous
             ok &= same
     dist.barrier()
     dist.destroy_process_group()
