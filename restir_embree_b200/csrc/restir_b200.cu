@@ -334,6 +334,8 @@ struct RbContext {
   // sides of each boundary and the ranks' frame costs go to the neighbours; boundaries follow the cost difference
   static constexpr int kShipRows = 8, kBalRing = 4, kMaxStalls = 8;
   bool balance = true;
+  int balPeriod = 8;                             // ship + decide every balPeriod frames (RB_BAL_PERIOD)
+  bool balDebug = false;                         // RB_BAL_DEBUG: print costs and bands to stderr
   uint32_t balFrame = 0;                         // frames rendered since rb_comm_init
   cudaEvent_t evShipReady = nullptr, evShipDone = nullptr;
   cudaEvent_t evBalCopied[kBalRing]{};           // costs of ring slot arrived in balHost
@@ -508,6 +510,9 @@ static int halo_exchange_wait(RbContext* h) {
 // frame's G-buffer / initial / visibility passes).
 static int balance_ship_begin(RbContext* h) {
   if (!h->comm || !h->balance) return RB_OK;
+  // once per balPeriod frames: the boundary rows' reservoirs must be those of the frame right before the move, so the
+  // exchange happens at the end of the period's last frame and is applied at the start of the next one
+  if (h->balFrame % (uint32_t)h->balPeriod != (uint32_t)h->balPeriod - 1u) return RB_OK;
   const int y0 = h->info.band_y0, y1 = h->info.band_y1, W = h->info.width, H = h->info.height;
   const int S = RbContext::kShipRows;
   const int slot = (int)(h->balFrame % RbContext::kBalRing);
@@ -562,7 +567,7 @@ static int balance_ship_begin(RbContext* h) {
 }
 
 // Start of frame: move this rank's two boundaries. A boundary is moved by BOTH ranks that share it, from the same two
-// numbers (the costs the two exchanged two frame ends ago), so they always agree. A step is at most kShipRows - 1
+// numbers (the {cost, rows} pairs the two exchanged at the previous frame end), so they always agree. A step is at most kShipRows - 1
 // rows: the rows a rank gains had their last-frame reservoirs shipped at the previous frame end and their previous
 // G-buffer rendered as margin.
 static int balance_boundary_step(float cost_up, float cost_dn, float rows_up_sent, float rows_dn_sent) {
@@ -582,11 +587,17 @@ static int balance_boundary_step(float cost_up, float cost_dn, float rows_up_sen
 }
 static int balance_update_band(RbContext* h) {
   if (!h->comm || !h->balance || h->balFrame < 4) return RB_OK;
-  const int slot = (int)((h->balFrame - 2) % RbContext::kBalRing);  // the exchange of two frame ends ago
+  // the exchange made at the end of the previous frame (the last of its period) is applied now; waiting for it drains
+  // the host/device pipeline once per period
+  if (h->balFrame % (uint32_t)h->balPeriod != 0) return RB_OK;
+  const int slot = (int)((h->balFrame - 1) % RbContext::kBalRing);
   RB_CUDA(cudaEventSynchronize(h->evBalCopied[slot]));
   const float* c = h->balHost + 8 * slot;  // {cost, rows} x {this rank as sent, rank above, rank below}
   if (h->commRank > 0) h->info.band_y0 -= balance_boundary_step(c[2], c[0], c[3], c[1]);
   if (h->commRank + 1 < h->commSize) h->info.band_y1 -= balance_boundary_step(c[0], c[4], c[1], c[5]);
+  if (h->balDebug && h->balFrame % 8 == 0)
+    fprintf(stderr, "[rb balance] rank %d frame %u: cost %.3f ms (above %.3f, below %.3f) -> band [%d, %d)\n", h->commRank, h->balFrame,
+            c[0], c[2], c[4], h->info.band_y0, h->info.band_y1);
   return RB_OK;
 }
 
@@ -1701,11 +1712,18 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
   RB_NCCL(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
   h->commRank = rank;
   h->commSize = nranks;
-  RB_CUDA(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;  // highest priority: the exchange kernels should not queue behind a frame kernel's CTAs
+    RB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const int prio = getenv("RB_COMM_PRIO") ? atoi(getenv("RB_COMM_PRIO")) : hi;
+    RB_CUDA(cudaStreamCreateWithPriority(&h->commStream, cudaStreamNonBlocking, prio));
+  }
   RB_CUDA(cudaEventCreateWithFlags(&h->evHaloReady, cudaEventDisableTiming));
   RB_CUDA(cudaEventCreate(&h->evHaloDone));
   RB_CUDA(cudaEventCreate(&h->evHaloT0));
   if (const char* e = getenv("RB_BALANCE")) h->balance = atoi(e) != 0;
+  if (const char* e = getenv("RB_BAL_PERIOD")) h->balPeriod = std::max(1, atoi(e));
+  if (const char* e = getenv("RB_BAL_DEBUG")) h->balDebug = atoi(e) != 0;
   RB_CUDA(cudaEventCreateWithFlags(&h->evShipReady, cudaEventDisableTiming));
   RB_CUDA(cudaEventCreateWithFlags(&h->evShipDone, cudaEventDisableTiming));
   for (int i = 0; i < RbContext::kBalRing; ++i) {

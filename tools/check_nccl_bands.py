@@ -31,6 +31,7 @@ def main():
     if rank == 0:
         idt.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
     dist.broadcast(idt, 0)
+    os.environ.setdefault("RB_BAL_PERIOD", "2")  # move the boundaries often: this is a correctness check
     r.comm_init(rank, world, idt.cpu().numpy().tobytes())
     full = None
     if rank == 0:
@@ -39,7 +40,7 @@ def main():
         full.set_params(p)
     ok = True
     bands_seen = []
-    for f in range(int(os.environ.get("CHECK_FRAMES", "14"))):
+    for f in range(int(os.environ.get("CHECK_FRAMES", "16"))):
         cam = Camera(W, H, 60, (4.2 + 0.1 * f, -4.4, 1.8 + 0.2 * f), (0, 0, 1.0 + 0.15 * f))
         band = torch.tensor(r.get_band(), dtype=torch.int32, device="cuda")  # the library balances the bands: they move
         allb = [torch.zeros_like(band) for _ in range(world)]
