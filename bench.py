@@ -311,7 +311,8 @@ def run_ours(args):
                     "note": "rb_render_frame with a pinned host frame_data buffer; scene resident (uploaded once like the reference)"},
             "gpu_launches": int(launches) * args.steps}
     if world > 1:
-        line["halo_exchange_ms"] = float(np.median(halo_ms))  # rank 0's NCCL send/recv group on the comm stream
+        line["halo_exchange_ms"] = float(np.median(halo_ms))  # rank 0: time its main stream waited for the neighbours' halo rows
+        line["config"]["halo_transport"] = r.comm_transport()
         line["config"]["band_rows_rank0_final"] = list(r.get_band())  # the library balances the bands by measured cost
         line["config"]["balance_settle_frames"] = settle  # untimed frames before the warm-up, for the balancer
     print(json.dumps(line), flush=True)

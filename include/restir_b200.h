@@ -277,10 +277,16 @@ int rb_scene_stats(RbHandle h, RbSceneStats* out);
  * number of bands.
  *
  * rb_comm_init attaches an NCCL communicator over the handles of all ranks (rank r owns band r; bands ordered
- * top to bottom); afterwards rb_render_frame performs the halo exchange itself with grouped ncclSend/ncclRecv
- * on a side stream, overlapped with the spatial pass over the interior rows. nccl_unique_id is the 128-byte
+ * top to bottom); afterwards rb_render_frame performs the halo exchange itself. nccl_unique_id is the 128-byte
  * ncclUniqueId made by rb_comm_unique_id on rank 0 and distributed by the launcher (torch.distributed, MPI,
  * a file). NCCL is loaded with dlopen at that point; single-GPU use needs no NCCL at all.
+ *
+ * Transport. One process per GPU on one node: rb_comm_init maps the neighbours' reservoir planes into this process
+ * (CUDA IPC handles sent through the communicator), and a halo exchange is then ONE kernel that stores this band's
+ * boundary rows straight into the neighbours' halo rows over NVLink/NVSwitch peer memory and releases a stamp in
+ * their flag word; the interior rows of the spatial pass are streamed meanwhile, and the boundary rows start once a
+ * one-thread kernel has seen both neighbours' stamps (rb_comm_transport() == 1). If the mapping fails on any rank
+ * (or RB_HALO=nccl) all ranks use grouped ncclSend/ncclRecv on a side stream instead (== 2).
  *
  * Load balancing: image bands do not cost the same (ceiling vs. floor), and a halo exchange is a rendezvous, so the
  * slowest band sets the frame rate. With a communicator attached the library therefore moves the band boundaries:
@@ -292,6 +298,7 @@ int rb_scene_stats(RbHandle h, RbSceneStats* out);
  * off; rb_get_band reports the rows currently owned (rb_render_frame writes exactly those rows of frame_rgb_out). */
 int rb_comm_unique_id(void* out_id, size_t id_bytes);
 int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes);
+int32_t rb_comm_transport(RbHandle h); /* 0 = no communicator, 1 = peer memory (CUDA IPC), 2 = NCCL send/recv */
 
 /* The same frame in phases, for hosts that move the halo rows themselves (another transport, or several
  * bands in one process):  rb_frame_begin  (G-buffer, initial candidates, visibility, temporal)

@@ -37,6 +37,10 @@ struct WaveBufs {
   uint32_t npix;
   uint32_t brdf_two_step;  // BRDF-candidate hits come from the emissive-only BVH; occ[] says whether something precedes them
   U4* cand;      // spatial pass, constant weights: candidate records [slot * npix + pixel] (spatial_gen_pixel)
+  // banded temporal stream: pixels whose reprojection leaves the G-buffer rows this handle holds are listed here and
+  // handled by a second, small launch that carries the re-derivation (traversal) code; the bulk kernel stays lean
+  uint32_t* deferred;        // pixel indices
+  uint32_t* deferred_count;  // device counter, zeroed with the frame's ray counters
 };
 
 struct FrameCtx {
@@ -777,7 +781,11 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
 #define RB_CAND_COPY 8u     // emissive pixel: the reservoir is copied through (spatial, slot 0 only)
 #define RB_CAND_INDEX_BITS 27
 #define RB_TEMPORAL_KEEP (1u << 16)
-template <bool BANDED>
+// BANDED: 0 = the handle holds the whole image; 1 = band, out-of-rows elements re-derived on the spot (fetch_*);
+// 2 = band, bulk launch: a pixel that would need a re-derivation only puts itself on the deferred list (the small
+// second launch runs those pixels with BANDED = 1). Same arithmetic in all three.
+RB_HD void temporal_defer(const WaveBufs& wv, size_t pi) { wv.deferred[queue_reserve(wv.deferred_count)] = (uint32_t)pi; }
+template <int BANDED>
 RB_HD void temporal_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis, Cnt& cnt) {
   const size_t pi = (size_t)y * fc.width + x;
   const WaveBufs& wv = fc.wave;
@@ -788,7 +796,8 @@ RB_HD void temporal_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vi
     *rec_flags = U4{RB_TEMPORAL_KEEP, 0u, 0u, 0u};
     return;
   }
-  const GElem prevElem = BANDED ? fetch_gelem(fc, true, px, py, cnt) : load_gelem(fc.Gprev, (size_t)py * fc.width + px);
+  if (BANDED == 2 && !(py >= fc.gpy0 && py < fc.gpy1)) return temporal_defer(wv, pi);
+  const GElem prevElem = BANDED == 1 ? fetch_gelem(fc, true, px, py, cnt) : load_gelem(fc.Gprev, (size_t)py * fc.width + px);
   const V3 curCam = fc.cam.pos, prevCam = fc.prevCam.pos;
   const float currentDepth = length(curElem.pos - curCam);
   const float prevDepth = length(prevElem.pos - prevCam);
@@ -803,7 +812,8 @@ RB_HD void temporal_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vi
     *rec_flags = U4{RB_TEMPORAL_KEEP, 0u, 0u, 0u};
     return;
   }
-  const V3 fwPos = BANDED ? fetch_gpos(fc, false, fx, fy, cnt) : xyz(ld4(fc.G.pos_depth + (size_t)fy * fc.width + fx));
+  if (BANDED == 2 && !(fy >= fc.gy0 && fy < fc.gy1)) return temporal_defer(wv, pi);
+  const V3 fwPos = BANDED == 1 ? fetch_gpos(fc, false, fx, fy, cnt) : xyz(ld4(fc.G.pos_depth + (size_t)fy * fc.width + fx));
   const float currentDepthP = length(prevPosAtCurrent - prevCam);
   const float prevDepthP = length(fwPos - curCam);
   const float depthRatioP = currentDepthP > prevDepthP ? prevDepthP / currentDepthP : currentDepthP / prevDepthP;

@@ -74,8 +74,20 @@ RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVis, true, 128, 5, initial_pixel(fc,
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_stream, GenVis, true, 3, temporal_gen_pixel<false>(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, true, 3, temporal_gen_pixel<true>(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_temporal_stream, GenVis, true, 3, temporal_gen_pixel<0>(fc, x, y, vis, cnt))
+// bands: the bulk launch defers the few pixels whose reprojection leaves the rows held here ...
+RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, true, 3, temporal_gen_pixel<2>(fc, x, y, vis, cnt))
+// ... to this one, which carries the G-buffer re-derivation (traversal) code; grid-stride over the deferred list
+__global__ void __launch_bounds__(128) k_temporal_stream_deferred(FrameCtx fc) {
+  const uint32_t n = *fc.wave.deferred_count;
+  Cnt cnt = {0, 0, 0};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t pi = fc.wave.deferred[i];
+    const GenVis vis = {&fc, pi};
+    temporal_gen_pixel<1>(fc, (int)(pi % (uint32_t)fc.width), (int)(pi / (uint32_t)fc.width), vis, cnt);
+  }
+  flush_counts(fc.counters, cnt);
+}
 RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 4, temporal_merge_pixel(fc, x, y, cnt))
 // three resident CTAs per SM (<= 85 registers, a few spilled words) beat two for the reuse passes (measured, profiles/);
 // the initial pass is the other way round
@@ -253,6 +265,78 @@ __global__ void k_reset_queue(uint32_t* count, uint32_t* next) {
   *next = 0;
 }
 
+// ---- band halos over peer memory --------------------------------------------------------------
+// One process per GPU; the neighbours' reservoir planes are mapped into this process with CUDA IPC (NVLink /
+// NVSwitch peer memory). k_halo_push stores this band's boundary rows of the four reservoir planes straight into
+// the halo rows of the rank above and the rank below (same row offsets on every rank) and then publishes a
+// stamp in the peer's flag word: every thread fences its peer stores system-wide, the last block to finish
+// (device-scope counter) releases the flags. The consumer's k_halo_wait polls its own flag words (they live in
+// its HBM, the peer's release store lands in its L2) before the kernels that read the halo rows are allowed to
+// start. No rendezvous and no host involvement: a rank waits only when the neighbour's rows are really late.
+struct HaloPush {
+  const char* src[4];                // this rank's planes of R[rWrite]
+  char* dst[2][4];                   // the same planes of the rank above [0] / below [1] (peer mappings), null = none
+  unsigned long long off[2][4];      // byte offset of the rows that go up / down
+  unsigned long long bytes[2][4];
+  uint32_t* flag[2];                 // peer flag words: above's "from below", below's "from above"
+  uint32_t* done;                    // local block counter (returns to zero)
+  uint32_t stamp;
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) k_halo_push(HaloPush p) {
+  const int plane = blockIdx.y & 3, dir = blockIdx.y >> 2;
+  char* dst = p.dst[dir][plane];
+  if (dst != nullptr) {
+    const size_t off = p.off[dir][plane], bytes = p.bytes[dir][plane];
+    const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    if (plane < 3) {  // 16-byte records
+      const uint4* s = reinterpret_cast<const uint4*>(p.src[plane] + off);
+      uint4* d = reinterpret_cast<uint4*>(dst + off);
+      for (size_t k = first; k < bytes / 16; k += step) d[k] = s[k];
+    } else {  // light indices: 4-byte records (a row need not be a multiple of 16 bytes)
+      const uint32_t* s = reinterpret_cast<const uint32_t*>(p.src[plane] + off);
+      uint32_t* d = reinterpret_cast<uint32_t*>(dst + off);
+      for (size_t k = first; k < bytes / 4; k += step) d[k] = s[k];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    if (atomicAdd(p.done, 1u) == total - 1u) {
+      *p.done = 0u;
+      __threadfence_system();
+      if (p.flag[0]) st_release_sys(p.flag[0], p.stamp);
+      if (p.flag[1]) st_release_sys(p.flag[1], p.stamp);
+    }
+  }
+}
+// flags[0]: stamp of the last halo pushed by the rank above, flags[1]: by the rank below. Gives up after
+// timeout_ns (a dead neighbour must not hang the GPU) and reports through *err (mapped host memory).
+__global__ void k_halo_wait(const uint32_t* flags, uint32_t stamp, int need_above, int need_below, uint32_t* err,
+                            unsigned long long timeout_ns) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int s = 0; s < 2; ++s) {
+    if (!(s == 0 ? need_above : need_below)) continue;
+    while ((int32_t)(ld_acquire_sys(flags + s) - stamp) < 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) {
+        *err = stamp ? stamp : 1u;
+        return;
+      }
+    }
+  }
+}
+
 // ---- BVH build -----------------------------------------------------------------------
 __global__ void k_bounds(BuildCtx c) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,6 +414,15 @@ struct RbContext {
   cudaStream_t commStream = nullptr;
   cudaEvent_t evHaloReady = nullptr, evHaloDone = nullptr, evHaloT0 = nullptr;  // T0..Done time the exchange itself
   bool haloTimed = false;
+  // halo rows over peer memory (k_halo_push / k_halo_wait): the neighbours' reservoir planes and flag words mapped with
+  // CUDA IPC in rb_comm_init; RB_HALO=nccl (or a failed mapping on any rank) keeps the grouped ncclSend/ncclRecv path
+  bool p2p = false;
+  void* peerBase[2][13]{};      // cudaIpcOpenMemHandle results, [above, below][12 planes + flags]
+  ResPlanes peerR[2][3]{};
+  uint32_t* peerFlags[2]{};
+  uint32_t* haloFlags = nullptr;  // [0] stamp pushed by the rank above, [1] by the rank below, [2] push block counter
+  uint32_t* haloErr = nullptr;    // mapped pinned host word: a wait that timed out leaves its stamp here
+  uint32_t haloSeq = 0;
   // load balancing of the bands (rb_comm_init): every frame end the last-frame reservoirs of kShipRows rows on both
   // sides of each boundary and the ranks' frame costs go to the neighbours; boundaries follow the cost difference
   static constexpr int kShipRows = 8, kBalRing = 4, kMaxStalls = 8;
@@ -417,6 +510,7 @@ struct NcclApi {
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -437,6 +531,7 @@ bool load_nccl(std::string& err) {
   g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
   g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
   g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
     err = "rb_comm: libnccl lacks a required symbol";
@@ -459,8 +554,11 @@ bool load_nccl(std::string& err) {
 // Exchange the halo rows of R[rWrite] with rank-1 / rank+1: one grouped send/recv pair per neighbour and plane
 // (rows of a plane are contiguous and live at the same offsets on every rank). Runs on the comm stream after the
 // producing kernels; frame_spatial streams the interior rows meanwhile.
+static int halo_push_p2p(RbContext* h);
+static int halo_wait_p2p(RbContext* h);
 static int halo_exchange_begin(RbContext* h) {
   if (!h->comm) return RB_OK;
+  if (h->p2p) return halo_push_p2p(h);
   const int y0 = h->info.band_y0, y1 = h->info.band_y1, W = h->info.width, H = h->info.height;
   const int R = spatial_reach(h->fs.P);
   const ResPlanes& P = h->R[h->rWrite];
@@ -502,7 +600,65 @@ static int wait_recording_stall(RbContext* h, cudaEvent_t ev) {
 }
 static int halo_exchange_wait(RbContext* h) {
   if (!h->comm) return RB_OK;
+  if (h->p2p) return halo_wait_p2p(h);
   return wait_recording_stall(h, h->evHaloDone);
+}
+
+// Peer-memory halo exchange: push this band's boundary rows of R[rWrite] into the neighbours' halo rows (main stream,
+// right behind the kernel that produced them) ...
+static int halo_push_p2p(RbContext* h) {
+  const int y0 = h->info.band_y0, y1 = h->info.band_y1, W = h->info.width;
+  const int R = spatial_reach(h->fs.P);
+  const int r = std::min(R, y1 - y0);
+  const ResPlanes& P = h->R[h->rWrite];
+  HaloPush a{};
+  const char* planes[4] = {(const char*)P.point_wsum, (const char*)P.normal_W, (const char*)P.Li_conf, (const char*)P.light_idx};
+  const size_t esz[4] = {16, 16, 16, 4};
+  const bool has[2] = {h->commRank > 0, h->commRank + 1 < h->commSize};
+  const int first_row[2] = {y0, y1 - r};  // rows that go up / down
+  for (int d = 0; d < 2; ++d) {
+    const ResPlanes& Q = h->peerR[d][h->rWrite];
+    char* dst[4] = {(char*)Q.point_wsum, (char*)Q.normal_W, (char*)Q.Li_conf, (char*)Q.light_idx};
+    for (int i = 0; i < 4; ++i) {
+      a.dst[d][i] = has[d] ? dst[i] : nullptr;
+      a.off[d][i] = (unsigned long long)first_row[d] * W * esz[i];
+      a.bytes[d][i] = (unsigned long long)r * W * esz[i];
+    }
+  }
+  for (int i = 0; i < 4; ++i) a.src[i] = planes[i];
+  a.flag[0] = has[0] ? h->peerFlags[0] + 1 : nullptr;  // the rank above sees me as "below"
+  a.flag[1] = has[1] ? h->peerFlags[1] + 0 : nullptr;
+  a.done = h->haloFlags + 2;
+  a.stamp = ++h->haloSeq;
+  const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>(32, ((size_t)r * W + 1023) / 1024));
+  k_halo_push<<<dim3(bx, 8), 256, 0, h->stream>>>(a);
+  h->fs.launches++;
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+// ... and, after the interior rows have been streamed, hold the main stream until both neighbours' rows are in.
+static int halo_wait_p2p(RbContext* h) {
+  if (*(volatile uint32_t*)h->haloErr != 0u) {
+    h->err = "band halo exchange: a neighbour's rows did not arrive in time (stamp " + std::to_string(*h->haloErr) + ")";
+    return RB_ERR_COMM;
+  }
+  const int slot = (int)(h->balFrame % RbContext::kBalRing);
+  const bool rec = h->balance && h->nStalls[slot] < RbContext::kMaxStalls;
+  const bool timed = h->fs.timed;
+  if (rec) RB_CUDA(cudaEventRecord(h->evStallA[slot][h->nStalls[slot]], h->stream));
+  if (timed) RB_CUDA(cudaEventRecord(h->evHaloT0, h->stream));
+  static const unsigned long long timeout_ns =
+      (unsigned long long)(getenv("RB_HALO_TIMEOUT_MS") ? atof(getenv("RB_HALO_TIMEOUT_MS")) : 5000.0) * 1000000ull;
+  k_halo_wait<<<1, 1, 0, h->stream>>>(h->haloFlags, h->haloSeq, h->commRank > 0 ? 1 : 0, h->commRank + 1 < h->commSize ? 1 : 0,
+                                      h->haloErr, timeout_ns);
+  h->fs.launches++;
+  if (timed) {
+    RB_CUDA(cudaEventRecord(h->evHaloDone, h->stream));
+    h->haloTimed = true;
+  }
+  if (rec) RB_CUDA(cudaEventRecord(h->evStallB[slot][h->nStalls[slot]++], h->stream));
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
 }
 
 // End of frame: ship the final reservoirs (R[rLast]) of kShipRows rows on both sides of each boundary plus this
@@ -601,6 +757,92 @@ static int balance_update_band(RbContext* h) {
   return RB_OK;
 }
 
+
+// Map the neighbours' reservoir planes and flag words into this process (CUDA IPC handles travel through the NCCL
+// communicator that is already up). Every rank takes part in the exchange and in the agreement, whatever its own
+// outcome: the peer-memory path is used only when it works on ALL ranks.
+static int halo_p2p_setup(RbContext* h) {
+  const char* mode = getenv("RB_HALO");
+  const bool want = !(mode && strcmp(mode, "nccl") == 0);
+  RB_CUDA(cudaMalloc((void**)&h->haloFlags, 4 * sizeof(uint32_t)));
+  RB_CUDA(cudaMemset(h->haloFlags, 0, 4 * sizeof(uint32_t)));
+  RB_CUDA(cudaHostAlloc((void**)&h->haloErr, sizeof(uint32_t), cudaHostAllocMapped));
+  *h->haloErr = 0u;
+  h->haloSeq = 0;
+  constexpr int NH = 13;
+  cudaIpcMemHandle_t mine[NH], theirs[2][NH];
+  memset(mine, 0, sizeof(mine));
+  memset(theirs, 0, sizeof(theirs));
+  void* ptrs[NH];
+  for (int b = 0; b < 3; ++b) {
+    ptrs[4 * b + 0] = h->R[b].point_wsum, ptrs[4 * b + 1] = h->R[b].normal_W, ptrs[4 * b + 2] = h->R[b].Li_conf,
+                 ptrs[4 * b + 3] = h->R[b].light_idx;
+  }
+  ptrs[12] = h->haloFlags;
+  int ok = want && g_nccl.AllReduce ? 1 : 0;
+  for (int i = 0; i < NH && ok; ++i)
+    if (cudaIpcGetMemHandle(&mine[i], ptrs[i]) != cudaSuccess) ok = 0;
+  (void)cudaGetLastError();
+  const bool has[2] = {h->commRank > 0, h->commRank + 1 < h->commSize};
+  const int peer[2] = {h->commRank - 1, h->commRank + 1};
+  char* stage = nullptr;
+  const size_t HB = sizeof(mine);
+  RB_CUDA(cudaMalloc((void**)&stage, 3 * HB + 16));
+  RB_CUDA(cudaMemcpyAsync(stage, mine, HB, cudaMemcpyHostToDevice, h->commStream));
+  RB_NCCL(g_nccl.GroupStart());
+  for (int d = 0; d < 2; ++d)
+    if (has[d]) {
+      RB_NCCL(g_nccl.Send(stage, HB, 0, peer[d], h->comm, h->commStream));
+      RB_NCCL(g_nccl.Recv(stage + (1 + d) * HB, HB, 0, peer[d], h->comm, h->commStream));
+    }
+  RB_NCCL(g_nccl.GroupEnd());
+  RB_CUDA(cudaMemcpyAsync(theirs, stage + HB, 2 * HB, cudaMemcpyDeviceToHost, h->commStream));
+  RB_CUDA(cudaStreamSynchronize(h->commStream));
+  for (int d = 0; d < 2 && ok; ++d) {
+    if (!has[d]) continue;
+    for (int i = 0; i < NH && ok; ++i)
+      if (cudaIpcOpenMemHandle(&h->peerBase[d][i], theirs[d][i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        h->peerBase[d][i] = nullptr;
+        ok = 0;
+      }
+  }
+  (void)cudaGetLastError();
+  int all_ok = 0;
+  if (g_nccl.AllReduce) {
+    int* agree = reinterpret_cast<int*>(stage + 3 * HB);
+    RB_CUDA(cudaMemcpyAsync(agree, &ok, sizeof(int), cudaMemcpyHostToDevice, h->commStream));
+    RB_NCCL(g_nccl.AllReduce(agree, agree, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, h->comm, h->commStream));
+    RB_CUDA(cudaMemcpyAsync(&all_ok, agree, sizeof(int), cudaMemcpyDeviceToHost, h->commStream));
+    RB_CUDA(cudaStreamSynchronize(h->commStream));
+  }
+  cudaFree(stage);
+  if (all_ok) {
+    for (int d = 0; d < 2; ++d) {
+      if (!has[d]) continue;
+      for (int b = 0; b < 3; ++b) {
+        h->peerR[d][b].point_wsum = (F4*)h->peerBase[d][4 * b + 0];
+        h->peerR[d][b].normal_W = (F4*)h->peerBase[d][4 * b + 1];
+        h->peerR[d][b].Li_conf = (F4*)h->peerBase[d][4 * b + 2];
+        h->peerR[d][b].light_idx = (int*)h->peerBase[d][4 * b + 3];
+      }
+      h->peerFlags[d] = (uint32_t*)h->peerBase[d][12];
+    }
+    h->p2p = true;
+  } else {
+    for (int d = 0; d < 2; ++d)
+      for (int i = 0; i < NH; ++i)
+        if (h->peerBase[d][i]) {
+          cudaIpcCloseMemHandle(h->peerBase[d][i]);
+          h->peerBase[d][i] = nullptr;
+        }
+    (void)cudaGetLastError();
+    h->p2p = false;
+    if (want && h->commRank == 0)
+      fprintf(stderr, "[rb comm] peer-memory halo exchange unavailable on at least one rank: using ncclSend/ncclRecv\n");
+  }
+  if (getenv("RB_BAL_DEBUG") && h->commRank == 0) fprintf(stderr, "[rb comm] halo exchange: %s\n", h->p2p ? "peer memory (CUDA IPC)" : "NCCL send/recv");
+  return RB_OK;
+}
 
 extern "C" {
 
@@ -734,7 +976,13 @@ void rb_destroy(RbHandle h) {
   if (h->wave.occ) cudaFree(h->wave.occ);
   if (h->wave.hits) cudaFree(h->wave.hits);
   if (h->wave.cand) cudaFree(h->wave.cand);
+  if (h->wave.deferred) cudaFree(h->wave.deferred);
   if (h->waveCounters) cudaFree(h->waveCounters);
+  for (int d = 0; d < 2; ++d)
+    for (int i = 0; i < 13; ++i)
+      if (h->peerBase[d][i]) cudaIpcCloseMemHandle(h->peerBase[d][i]);
+  if (h->haloFlags) cudaFree(h->haloFlags);
+  if (h->haloErr) cudaFreeHost(h->haloErr);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->commStream) cudaStreamDestroy(h->commStream);
   if (h->evHaloReady) cudaEventDestroy(h->evHaloReady);
@@ -1102,6 +1350,9 @@ static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32
     RB_CUDA(cudaMalloc((void**)&h->wave.hits, (size_t)brdf_slots * npix * sizeof(HitRec)));
     h->waveHitCap = (size_t)brdf_slots * npix;
   }
+  const bool banded = !(h->info.band_y0 == 0 && h->info.band_y1 == h->info.height);
+  if (banded && !h->wave.deferred) RB_CUDA(cudaMalloc((void**)&h->wave.deferred, npix * sizeof(uint32_t)));
+  h->wave.deferred_count = reinterpret_cast<uint32_t*>(h->counters + 4);  // zeroed with the ray counters at frame begin
   RB_TRY(ensure_counters(h));
   h->wave.capacity = (uint32_t)h->waveRayCap;
   h->wave.npix = (uint32_t)npix;
@@ -1306,10 +1557,13 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_TEMPORAL, 0);
     if (F.wave) {
       fs_reset_queue(h);
-      if (banded)
+      if (banded) {
         launch_rows(h, k_temporal_stream_banded, y0, y1);
-      else
+        k_temporal_stream_deferred<<<h->numSMs, 128, 0, st>>>(fc);
+        F.launches++;
+      } else {
         launch_rows(h, k_temporal_stream, y0, y1);
+      }
       fs_mark(h, 3, 0);
       fs_trace(h, TRACE_ANY, 3);
       launch_rows(h, k_temporal_resolve, y0, y1);
@@ -1703,6 +1957,7 @@ int rb_comm_unique_id(void* out_id, size_t id_bytes) {
   }
   return g_nccl.GetUniqueId(out_id) == 0 ? RB_OK : RB_ERR_COMM;
 }
+int32_t rb_comm_transport(RbHandle h) { return (!h || !h->comm) ? 0 : (h->p2p ? 1 : 2); }
 int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes) {
   if (!h || !nccl_unique_id || id_bytes < 128 || rank < 0 || rank >= nranks) return RB_ERR_INVALID_ARGUMENT;
   if (!load_nccl(h->err)) return RB_ERR_COMM;
@@ -1739,6 +1994,7 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
   RB_CUDA(cudaMallocHost((void**)&h->balHost, RbContext::kBalRing * 8 * sizeof(float)));
   h->balFrame = 0;
   h->shipPending = false;
+  RB_TRY(halo_p2p_setup(h));
   return RB_OK;
 }
 

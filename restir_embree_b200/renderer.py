@@ -62,6 +62,8 @@ def load_library():
     L.rb_halo_bytes.argtypes = [H, C.c_int32]
     L.rb_halo_export.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
     L.rb_halo_import.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
+    L.rb_comm_transport.restype = C.c_int32
+    L.rb_comm_transport.argtypes = [H]
     L.rb_halo_rows.restype = C.c_int32
     L.rb_halo_rows.argtypes = [H]
     L.rb_frame_begin.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32]
@@ -254,6 +256,10 @@ class Renderer:
     def comm_init(self, rank, nranks, unique_id_bytes):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id_bytes)[:128])
         self._check(self.L.rb_comm_init(self.h, int(rank), int(nranks), buf, 128), "rb_comm_init")
+
+    def comm_transport(self):
+        """How rb_render_frame moves the halo rows: 'peer-memory' (CUDA IPC over NVLink), 'nccl', or None."""
+        return {0: None, 1: "peer-memory", 2: "nccl"}[int(self.L.rb_comm_transport(self.h))]
 
     # -- band halos -------------------------------------------------------------------------
     def halo_export(self, y, rows):

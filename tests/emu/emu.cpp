@@ -58,6 +58,9 @@ struct Emu {
   std::vector<uint8_t> occ;
   std::vector<HitRec> hits;
   std::vector<U4> cand;
+  std::vector<uint32_t> deferred;
+  uint32_t deferred_count = 0;
+  unsigned long long n_deferred_total = 0;  // over all frames: lets a test see that the deferral path ran
 
   GBufPlanes gp(int i) { return GBufPlanes{gs[i].a.data(), gs[i].b.data(), gs[i].c.data(), gs[i].d.data(), gs[i].e.data(), gs[i].ids.data()}; }
   ResPlanes rp(int i) { return ResPlanes{rs[i].a.data(), rs[i].b.data(), rs[i].c.data(), rs[i].li.data()}; }
@@ -410,6 +413,10 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     if (P.doTemporalReuse) cand_slots = std::max<size_t>(cand_slots, 2);
     E->cand.assign((size_t)npix * cand_slots, U4{0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu});
     fc.wave.cand = E->cand.data();
+    E->deferred.assign(npix, 0xFFFFFFFFu);
+    E->deferred_count = 0;
+    fc.wave.deferred = E->deferred.data();
+    fc.wave.deferred_count = &E->deferred_count;
   }
   const bool wave = E->wave;
   emu_bind(E);
@@ -458,10 +465,20 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_TEMPORAL, 0);
     if (wave) {
       E->qcount = 0;
-      if (banded)
-        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<true>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
-      else
-        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<false>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+      if (banded) {  // as the device schedule: bulk launch with deferral, then the deferred pixels with the re-derivation code
+        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<2>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+        unsigned long long c0 = 0, c1 = 0, c2 = 0;
+        for (uint32_t i = 0; i < E->deferred_count; ++i) {
+          const uint32_t pi = E->deferred[i];
+          Cnt c = {0, 0, 0};
+          temporal_gen_pixel<1>(fc, (int)(pi % (uint32_t)fc.width), (int)(pi / (uint32_t)fc.width), GenVis{&fc, pi}, c);
+          c0 += c.closest, c1 += c.anyW, c2 += c.anyT;
+        }
+        E->counters[0] += c0, E->counters[1] += c1, E->counters[2] += c2;
+        E->n_deferred_total += E->deferred_count;
+      } else {
+        for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<0>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
+      }
       emu_trace_queue(E, EMU_ANY);
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_merge_pixel(fc, x, y, c); });
     } else if (banded) {
@@ -546,6 +563,7 @@ static int emu_halo_copy(Emu* E, int y, int rows, char* host, bool to_host) {
 int emu_halo_export(void* h, int y, int rows, void* dst) { return emu_halo_copy((Emu*)h, y, rows, (char*)dst, true); }
 int emu_halo_import(void* h, int y, int rows, const void* src) { return emu_halo_copy((Emu*)h, y, rows, (char*)src, false); }
 
+uint64_t emu_deferred_total(void* h) { return ((Emu*)h)->n_deferred_total; }
 void emu_counters(void* h, uint64_t* out3) {
   Emu* E = (Emu*)h;
   out3[0] = E->counters[0], out3[1] = E->counters[1], out3[2] = E->counters[2];

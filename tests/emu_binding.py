@@ -38,6 +38,8 @@ def lib():
         L.emu_scene_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_render_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p]
         L.emu_counters.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_deferred_total.argtypes = [C.c_void_p]
+        L.emu_deferred_total.restype = C.c_uint64
         L.emu_readback.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.emu_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.emu_trace_occluded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
@@ -133,6 +135,10 @@ class Emu:
         assert self.L.emu_accumulate_display(self.h, int(acc_frame_ctr), int(bool(tonemap)), int(bool(gamma_correct)),
                                              out.ctypes.data, st.ctypes.data) == 0
         return out, dict(sum=st[0], sum_sq=st[1], mean=st[2], variance=st[3])
+
+    def deferred_total(self):
+        """pixels the banded temporal stream pass handed to its second (re-derivation) launch, over all frames"""
+        return int(self.L.emu_deferred_total(self.h))
 
     def counters(self):
         c = np.zeros(3, dtype=np.uint64)

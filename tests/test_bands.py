@@ -60,6 +60,27 @@ def test_emulated_bands_are_bit_identical_to_one_band(ci, n):
             assert np.array_equal(bits(one.readback(buf)), bits(assemble(bands, buf))), (f, buf)
 
 
+def test_emulated_bands_fast_pan_uses_the_deferred_rederivation_launch():
+    """Thin bands + a fast vertical pan: many reprojections leave the rows a band holds (band + 16-row margin), so the
+    second, deferred launch of the banded temporal stream pass (the one with the re-derivation code) has work; the image
+    must still be bit-identical to the one-band image."""
+    sc = scenes.scene_config("small")
+    p = abi.default_params(**CFGS[0])
+    fast = lambda f: Camera(W, H, 60, (4.2, -4.4, 1.8 + 0.6 * f), (0, 0, 1.0 + 1.1 * f))
+    one = eb.Emu(W, H, seed=5)
+    one.upload_scene(sc)
+    one.set_params(p)
+    bands = make_bands(eb.Emu, W, H, 5, seed=5)
+    for b in bands:
+        b.upload_scene(sc)
+        b.set_params(p)
+    for f in range(3):
+        a = one.render_frame(fast(f), f)
+        b = render_banded(bands, fast(f), f, p)
+        assert np.array_equal(bits(a), bits(b)), f"frame {f}: {(a != b).any(-1).sum()} px differ"
+    assert sum(b.deferred_total() for b in bands) > 0
+
+
 def _moving_bounds(n, f):
     """band boundaries that wander by up to 7 rows per frame (inside the 16-row G-buffer margin)"""
     base = [band_rows(H, n, r)[0] for r in range(n)] + [H]
@@ -175,5 +196,29 @@ def test_gpu_bands_with_moving_boundaries_are_bit_identical_to_one_band(gpu):
         a = one.render_frame(cams(f), f)
         b = render_banded(bands, cams(f), f, p)
         assert np.array_equal(bits(a), bits(b)), f"frame {f}: {(a != b).any(-1).sum()} px differ, bands {[x.band for x in bands]}"
+    for r in bands + [one]:
+        r.close()
+
+
+@pytest.mark.gpu
+def test_gpu_bands_fast_pan_deferred_rederivation(gpu):
+    """GPU twin of the fast-pan test: the bulk banded temporal stream kernel defers the pixels whose reprojection
+    leaves the held rows to k_temporal_stream_deferred; image and selected lights stay bit-identical to one band."""
+    from restir_embree_b200.renderer import Renderer
+    sc = scenes.scene_config("small")
+    p = abi.default_params(**CFGS[0])
+    fast = lambda f: Camera(W, H, 60, (4.2, -4.4, 1.8 + 0.6 * f), (0, 0, 1.0 + 1.1 * f))
+    one = Renderer(W, H, seed=5)
+    one.upload_scene(sc)
+    one.set_params(p)
+    bands = make_bands(Renderer, W, H, 5, seed=5)
+    for b in bands:
+        b.upload_scene(sc)
+        b.set_params(p)
+    for f in range(3):
+        a = one.render_frame(fast(f), f)
+        b = render_banded(bands, fast(f), f, p)
+        assert np.array_equal(bits(a), bits(b)), f"frame {f}: {(a != b).any(-1).sum()} px differ"
+        assert np.array_equal(bits(one.readback(abi.BUF_RES_LIGHT_IDX)), bits(assemble(bands, abi.BUF_RES_LIGHT_IDX)))
     for r in bands + [one]:
         r.close()

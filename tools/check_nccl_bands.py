@@ -35,6 +35,7 @@ def main():
     r.comm_init(rank, world, idt.cpu().numpy().tobytes())
     full = None
     if rank == 0:
+        print("halo transport:", r.comm_transport(), flush=True)
         full = Renderer(W, H, device=local, seed=9)
         full.upload_scene(sc)
         full.set_params(p)
