@@ -180,11 +180,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     frame = 0
-    # N > 1: the library balances the band heights by measured cost (<= 7 rows per frame): let it settle first
-    settle = 32 if world > 1 else 0
-    for _ in range(settle):
-        r.render_frame_device(camera_at(scene, frame), frame)
-        frame += 1
+    # N > 1: the library balances the band heights by measured cost (<= 15 rows per period of 8 frames): let it settle first
+    # (untimed; until the bands have stopped moving for three balance periods, at most 192 frames)
+    settle = 0
+    if world > 1:
+        last, still = r.get_band(), 0
+        span = args.warmup + args.steps  # the settle frames replay the camera path of the timed region, so that every
+        while settle < 192 and still < 24:  # N measures the SAME frames (frame cost varies 2x along the orbit)
+            r.render_frame_device(camera_at(scene, frame), frame)
+            frame = (frame + 1) % span
+            settle += 1
+            now = r.get_band()
+            moved = torch.tensor([1.0 if now != last else 0.0], device="cuda")
+            if settle % 8 == 0:  # all ranks leave the loop together
+                dist.all_reduce(moved, op=dist.ReduceOp.MAX)
+                still = 0 if moved.item() > 0 else still + 8
+                last = now
+        frame = 0
     # ---- device-resident throughput ("value") ---------------------------------------------------
     for _ in range(args.warmup):
         r.render_frame_device(camera_at(scene, frame), frame)
@@ -221,7 +233,7 @@ def run_ours(args):
         halo_ms.append(t["ms_halo"])
     # ---- end to end through the public call with a HOST frame buffer ---------------------------------
     # (the same camera path as the device-resident leg: frames 0..W-1 untimed, then K timed)
-    frame = settle
+    frame = 0
     for _ in range(args.warmup):
         r.render_frame(camera_at(scene, frame), frame, out=out)
         frame += 1

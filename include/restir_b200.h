@@ -290,9 +290,9 @@ int rb_scene_stats(RbHandle h, RbSceneStats* out);
  *
  * Load balancing: image bands do not cost the same (ceiling vs. floor), and a halo exchange is a rendezvous, so the
  * slowest band sets the frame rate. With a communicator attached the library therefore moves the band boundaries:
- * every 8th frame end (RB_BAL_PERIOD) each rank sends its neighbours the last-frame reservoirs of the 8 rows next to
+ * every 8th frame end (RB_BAL_PERIOD) each rank sends its neighbours the last-frame reservoirs of the 16 rows next to
  * the boundary and its own frame cost (GPU time minus time spent waiting for neighbours; CUDA events), and at the
- * start of the next frame both ranks that share a boundary move it by the same damped step (<= 7 rows) computed from the same
+ * start of the next frame both ranks that share a boundary move it by the same damped step (<= 15 rows) computed from the same
  * two numbers. Rows that change owner find their last-frame reservoirs already there and their previous G-buffer in
  * the margin; the image stays bit-identical to the one-band image (tools/check_nccl_bands.py). RB_BALANCE=0 turns it
  * off; rb_get_band reports the rows currently owned (rb_render_frame writes exactly those rows of frame_rgb_out). */

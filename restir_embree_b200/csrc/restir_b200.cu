@@ -425,7 +425,7 @@ struct RbContext {
   uint32_t haloSeq = 0;
   // load balancing of the bands (rb_comm_init): every frame end the last-frame reservoirs of kShipRows rows on both
   // sides of each boundary and the ranks' frame costs go to the neighbours; boundaries follow the cost difference
-  static constexpr int kShipRows = 8, kBalRing = 4, kMaxStalls = 8;
+  static constexpr int kShipRows = 16, kBalRing = 8, kMaxStalls = 8;  // a boundary moves <= 15 rows per period (G-buffer margin: 16)
   bool balance = true;
   int balPeriod = 8;                             // ship + decide every balPeriod frames (RB_BAL_PERIOD)
   bool balDebug = false;                         // RB_BAL_DEBUG: print costs and bands to stderr
@@ -435,8 +435,9 @@ struct RbContext {
   cudaEvent_t evFrameB[kBalRing]{}, evFrameE[kBalRing]{};
   cudaEvent_t evStallA[kBalRing][kMaxStalls]{}, evStallB[kBalRing][kMaxStalls]{};
   int nStalls[kBalRing]{};
-  float* balDev = nullptr;                       // [6]: {cost, rows} of this rank, of the rank above, of the rank below
-  float* balHost = nullptr;                      // pinned, [kBalRing][8]: the same three pairs as sent / received
+  static constexpr int kMaxRanks = 64;
+  float* balDev = nullptr;                       // [2 + 2 * kMaxRanks]: this rank's {cost, rows}, then the all-gathered pairs
+  float* balHost = nullptr;                      // pinned, [kBalRing][2 + 2 * kMaxRanks]: the same, per ring slot
   bool shipPending = false;
 
   // scene
@@ -511,6 +512,7 @@ struct NcclApi {
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -532,6 +534,7 @@ bool load_nccl(std::string& err) {
   g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
   g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
     err = "rb_comm: libnccl lacks a required symbol";
@@ -676,19 +679,29 @@ static int balance_ship_begin(RbContext* h) {
   // the host at most two frames ahead of the device)
   float cost = 0.0f;
   if (h->balFrame >= 2) {
-    const int ps = (int)((h->balFrame - 2) % RbContext::kBalRing);
-    RB_CUDA(cudaEventSynchronize(h->evFrameE[ps]));
-    RB_CUDA(cudaEventElapsedTime(&cost, h->evFrameB[ps], h->evFrameE[ps]));
-    for (int i = 0; i < h->nStalls[ps]; ++i) {
-      float st = 0;
-      RB_CUDA(cudaEventElapsedTime(&st, h->evStallA[ps][i], h->evStallB[ps][i]));
-      cost -= st;
+    RB_CUDA(cudaEventSynchronize(h->evFrameE[(h->balFrame - 2) % RbContext::kBalRing]));
+    // mean over up to four completed frames of this period (same band): single frames are noisy
+    int used = 0;
+    for (uint32_t j = 2; j <= 5 && j <= h->balFrame; ++j) {
+      if (j > 2 && (int)j > h->balPeriod - 1) break;
+      const int ps = (int)((h->balFrame - j) % RbContext::kBalRing);
+      float t = 0;
+      RB_CUDA(cudaEventElapsedTime(&t, h->evFrameB[ps], h->evFrameE[ps]));
+      for (int i = 0; i < h->nStalls[ps]; ++i) {
+        float st = 0;
+        RB_CUDA(cudaEventElapsedTime(&st, h->evStallA[ps][i], h->evStallB[ps][i]));
+        t -= st;
+      }
+      cost += t;
+      ++used;
     }
+    cost = used ? cost / (float)used : 0.0f;
     if (!(cost > 0.0f)) cost = 0.0f;
   }
-  float* hostSlot = h->balHost + 8 * slot;
+  constexpr int BS = 2 + 2 * RbContext::kMaxRanks;
+  float* hostSlot = h->balHost + BS * slot;
   hostSlot[0] = cost, hostSlot[1] = (float)(y1 - y0);
-  hostSlot[2] = hostSlot[3] = hostSlot[4] = hostSlot[5] = -1.0f;
+  for (int i = 2; i < BS; ++i) hostSlot[i] = -1.0f;
   const ResPlanes& P = h->R[h->rLast];
   RB_CUDA(cudaEventRecord(h->evShipReady, h->stream));
   RB_CUDA(cudaStreamWaitEvent(h->commStream, h->evShipReady, 0));
@@ -702,8 +715,6 @@ static int balance_ship_begin(RbContext* h) {
       RB_NCCL(g_nccl.Send(planes[i] + (size_t)y0 * W * esz[i], (size_t)r * W * esz[i], 0, h->commRank - 1, h->comm, h->commStream));
       RB_NCCL(g_nccl.Recv(planes[i] + (size_t)(y0 - ru) * W * esz[i], (size_t)ru * W * esz[i], 0, h->commRank - 1, h->comm, h->commStream));
     }
-    RB_NCCL(g_nccl.Send(h->balDev, 8, 0, h->commRank - 1, h->comm, h->commStream));
-    RB_NCCL(g_nccl.Recv(h->balDev + 2, 8, 0, h->commRank - 1, h->comm, h->commStream));
   }
   if (h->commRank + 1 < h->commSize) {
     const int r = std::min(S, y1 - y0), rd = std::min(S, H - y1);
@@ -711,35 +722,48 @@ static int balance_ship_begin(RbContext* h) {
       RB_NCCL(g_nccl.Send(planes[i] + (size_t)(y1 - r) * W * esz[i], (size_t)r * W * esz[i], 0, h->commRank + 1, h->comm, h->commStream));
       RB_NCCL(g_nccl.Recv(planes[i] + (size_t)y1 * W * esz[i], (size_t)rd * W * esz[i], 0, h->commRank + 1, h->comm, h->commStream));
     }
-    RB_NCCL(g_nccl.Send(h->balDev, 8, 0, h->commRank + 1, h->comm, h->commStream));
-    RB_NCCL(g_nccl.Recv(h->balDev + 4, 8, 0, h->commRank + 1, h->comm, h->commStream));
   }
   RB_NCCL(g_nccl.GroupEnd());
-  RB_CUDA(cudaMemcpyAsync(hostSlot + 2, h->balDev + 2, 16, cudaMemcpyDeviceToHost, h->commStream));
+  // every rank's {cost, rows}: all ranks then derive the same new boundaries from the same numbers
+  RB_NCCL(g_nccl.AllGather(h->balDev, h->balDev + 2, 2, /*ncclFloat32*/ 7, h->comm, h->commStream));
+  RB_CUDA(cudaMemcpyAsync(hostSlot + 2, h->balDev + 2, 2 * h->commSize * sizeof(float), cudaMemcpyDeviceToHost, h->commStream));
   RB_CUDA(cudaEventRecord(h->evBalCopied[slot], h->commStream));
   RB_CUDA(cudaEventRecord(h->evShipDone, h->commStream));
   h->shipPending = true;
   return RB_OK;
 }
 
-// Start of frame: move this rank's two boundaries. A boundary is moved by BOTH ranks that share it, from the same two
-// numbers (the {cost, rows} pairs the two exchanged at the previous frame end), so they always agree. A step is at most kShipRows - 1
-// rows: the rows a rank gains had their last-frame reservoirs shipped at the previous frame end and their previous
-// G-buffer rendered as margin.
-static int balance_boundary_step(float cost_up, float cost_dn, float rows_up_sent, float rows_dn_sent) {
-  if (!(cost_up > 0.0f) || !(cost_dn > 0.0f) || !(rows_up_sent > 0.0f) || !(rows_dn_sent > 0.0f)) return 0;
-  // rows the upper band should lose so that the two costs meet, damped by one half
-  const float want = 0.5f * (cost_up - cost_dn) / (cost_up + cost_dn) * (rows_up_sent + rows_dn_sent);
-  int step = (int)lrintf(0.5f * want);
-  const int lim = RbContext::kShipRows - 1;
-  step = std::max(-lim, std::min(lim, step));
-  // Keep both bands tall enough. Heights are the ones EXCHANGED with the costs (both sides hold the same numbers);
-  // since then each band can have lost at most 2 * lim rows in the one update in between, and may lose lim more at
-  // its other boundary in this one.
-  const int min_rows = 2 * RbContext::kShipRows, slack = 3 * lim;
-  step = std::min(step, std::max(0, (int)rows_up_sent - slack - min_rows));
-  step = std::max(step, -std::max(0, (int)rows_dn_sent - slack - min_rows));
-  return step;  // the boundary moves UP by `step` rows
+// Start of frame: move the band boundaries. Every rank holds the same all-gathered {cost, rows} pairs (exchanged at the
+// previous frame end) and runs the same arithmetic on them, so all ranks agree on every boundary without another
+// message. The target partition gives every band the same share of the summed cost, taking the cost per row as uniform
+// inside each current band; a boundary moves half of the way towards its target, at most kShipRows - 1 rows per period:
+// the rows a rank gains had their last-frame reservoirs shipped at the previous frame end and their previous G-buffer
+// rendered as margin. (A global rule instead of pairwise diffusion: a chain of N bands would need O(N^2) periods.)
+static void balance_targets(const float* pairs, int n, int H, int* bounds /* n + 1, in: current, out: new */) {
+  const int lim = RbContext::kShipRows - 1, min_rows = 2 * RbContext::kShipRows;
+  double total = 0.0;
+  for (int r = 0; r < n; ++r) {
+    const float cost = pairs[2 * r], rows = pairs[2 * r + 1];
+    if (!(cost > 0.0f) || !(rows > 0.0f) || (int)rows != bounds[r + 1] - bounds[r]) return;  // not a consistent snapshot
+    if (bounds[r + 1] - bounds[r] < min_rows + 2 * lim) return;                              // bands too thin to move safely
+    total += (double)cost;
+  }
+  int nb[RbContext::kMaxRanks + 1];
+  nb[0] = 0, nb[n] = H;
+  int band = 0;
+  double before = 0.0;  // cost of the bands above `band`
+  for (int k = 1; k < n; ++k) {
+    const double want = total * (double)k / (double)n;
+    while (band < n - 1 && before + (double)pairs[2 * band] < want) before += (double)pairs[2 * band++];
+    const double frac = (want - before) / (double)pairs[2 * band];
+    const double ideal = (double)bounds[band] + frac * (double)(bounds[band + 1] - bounds[band]);
+    int step = (int)lrint(0.5 * (ideal - (double)bounds[k]));
+    step = std::max(-lim, std::min(lim, step));
+    nb[k] = bounds[k] + step;
+  }
+  for (int k = 1; k <= n; ++k)  // (cannot trigger with the thickness test above; kept as a guard)
+    if (nb[k] - nb[k - 1] < min_rows) return;
+  for (int k = 1; k < n; ++k) bounds[k] = nb[k];
 }
 static int balance_update_band(RbContext* h) {
   if (!h->comm || !h->balance || h->balFrame < 4) return RB_OK;
@@ -748,15 +772,31 @@ static int balance_update_band(RbContext* h) {
   if (h->balFrame % (uint32_t)h->balPeriod != 0) return RB_OK;
   const int slot = (int)((h->balFrame - 1) % RbContext::kBalRing);
   RB_CUDA(cudaEventSynchronize(h->evBalCopied[slot]));
-  const float* c = h->balHost + 8 * slot;  // {cost, rows} x {this rank as sent, rank above, rank below}
-  if (h->commRank > 0) h->info.band_y0 -= balance_boundary_step(c[2], c[0], c[3], c[1]);
-  if (h->commRank + 1 < h->commSize) h->info.band_y1 -= balance_boundary_step(c[0], c[4], c[1], c[5]);
-  if (h->balDebug && h->balFrame % 8 == 0)
-    fprintf(stderr, "[rb balance] rank %d frame %u: cost %.3f ms (above %.3f, below %.3f) -> band [%d, %d)\n", h->commRank, h->balFrame,
-            c[0], c[2], c[4], h->info.band_y0, h->info.band_y1);
+  constexpr int BS = 2 + 2 * RbContext::kMaxRanks;
+  const float* c = h->balHost + BS * slot;  // own {cost, rows} as sent, then all ranks' pairs
+  const int n = h->commSize;
+  // current boundaries, reconstructed from the gathered heights (the ranks' bands tile the image top to bottom)
+  int bounds[RbContext::kMaxRanks + 1];
+  bounds[0] = 0;
+  bool ok = true;
+  for (int r = 0; r < n; ++r) {
+    const float rows = c[2 + 2 * r + 1];
+    if (!(rows > 0.0f)) ok = false;
+    bounds[r + 1] = bounds[r] + (ok ? (int)rows : 0);
+  }
+  if (ok && bounds[n] == h->info.height && bounds[h->commRank] == h->info.band_y0 && bounds[h->commRank + 1] == h->info.band_y1) {
+    balance_targets(c + 2, n, h->info.height, bounds);
+    h->info.band_y0 = bounds[h->commRank];
+    h->info.band_y1 = bounds[h->commRank + 1];
+  }
+  if (h->balDebug && h->balFrame % 8 == 0) {
+    std::string all;
+    for (int r = 0; r < n; ++r) all += " " + std::to_string(c[2 + 2 * r]).substr(0, 5) + "/" + std::to_string((int)c[2 + 2 * r + 1]);
+    fprintf(stderr, "[rb balance] rank %d frame %u: cost/rows%s -> band [%d, %d)\n", h->commRank, h->balFrame, all.c_str(),
+            h->info.band_y0, h->info.band_y1);
+  }
   return RB_OK;
 }
-
 
 // Map the neighbours' reservoir planes and flag words into this process (CUDA IPC handles travel through the NCCL
 // communicator that is already up). Every rank takes part in the exchange and in the agreement, whatever its own
@@ -1990,8 +2030,12 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
       RB_CUDA(cudaEventCreate(&h->evStallB[i][j]));
     }
   }
-  RB_CUDA(cudaMalloc((void**)&h->balDev, 6 * sizeof(float)));
-  RB_CUDA(cudaMallocHost((void**)&h->balHost, RbContext::kBalRing * 8 * sizeof(float)));
+  if (nranks > RbContext::kMaxRanks) {
+    h->err = "rb_comm_init: more than 64 ranks";
+    return RB_ERR_UNSUPPORTED;
+  }
+  RB_CUDA(cudaMalloc((void**)&h->balDev, (2 + 2 * RbContext::kMaxRanks) * sizeof(float)));
+  RB_CUDA(cudaMallocHost((void**)&h->balHost, RbContext::kBalRing * (2 + 2 * RbContext::kMaxRanks) * sizeof(float)));
   h->balFrame = 0;
   h->shipPending = false;
   RB_TRY(halo_p2p_setup(h));
