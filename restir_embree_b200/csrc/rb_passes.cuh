@@ -41,6 +41,15 @@ struct WaveBufs {
   // handled by a second, small launch that carries the re-derivation (traversal) code; the bulk kernel stays lean
   uint32_t* deferred;        // pixel indices
   uint32_t* deferred_count;  // device counter, zeroed with the frame's ray counters
+  // two-step BRDF-candidate rays: the closest-EMITTER traversal itself queues the "does anything precede this hit?"
+  // ray of every ray that found an emitter (brdf_chain_push) — no stream kernel between the two traversals
+  RayQ* chain_rays;
+  uint32_t* chain_count;  // {queued, next to fetch}, zeroed with the frame's ray counters
+  uint32_t chain_capacity;
+  // visibility pass folded into its neighbours (wavefront schedule): bit 0 = the initial-pass resolve kernel queues the
+  // visibility ray of the reservoir it has just produced; bit 1 = the temporal stream kernel applies the traced result
+  // (W = 0 where occluded) before it uses the reservoir. Either bit clear = k_visibility_stream / _resolve do it.
+  uint32_t fuse_vis;
 };
 
 struct FrameCtx {
@@ -89,6 +98,15 @@ RB_HD uint32_t queue_reserve(uint32_t* counter) {
 #else
   return __atomic_fetch_add(counter, 1u, __ATOMIC_RELAXED);
 #endif
+}
+
+// step 2 of the two-step BRDF-candidate rays, queued by the traversal that found the emitter hit (t_hit, hits[dest].tri)
+RB_HD void brdf_chain_push(const WaveBufs& w, const V3& o, const V3& d, float t_hit, uint32_t dest) {
+  const uint32_t i = queue_reserve(w.chain_count);
+  if (i < w.chain_capacity) {
+    st4(&w.chain_rays[i].o_tfar, f4(o, t_hit));
+    st4(&w.chain_rays[i].d_dest, f4(d, u2f(dest)));
+  }
 }
 
 // ---- visibility / closest-hit policies ----------------------------------------------
@@ -602,6 +620,12 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   r.W = p_hat > 0.0f ? frcp_(p_hat) * r.w_sum : 0.0f;
   r.confidence = imin(r.confidence, P.confidenceCap);
   if (Vis::kStore) store_reservoir(fc.Rwrite, pi, r);
+  // stream half of the visibility pass (visibility_pixel<GenVis>) for the reservoir just produced: same origin,
+  // target and W test as the pass would read back from memory
+  if (Vis::kStore && (fc.wave.fuse_vis & 1u) && r.W != 0.0f) {
+    const GenVis gv = {&fc, (uint32_t)pi};
+    (void)gv.visible(0, g.pos, r.bestSample.samplePoint);
+  }
 }
 
 // Stream half of the initial pass: only the BRDF-sampled closest-hit rays (brdfSampleLight, :136-141). The
@@ -628,29 +652,9 @@ RB_HD void initial_brdf_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis
   }
 }
 
-// Second step of the two-step BRDF-candidate rays: where the emissive-only BVH reported a hit (t, id), ask the full
-// BVH whether anything precedes it (trace8_precedes / k_trace_queue<true, true>). Few rays reach this step: most
-// BRDF-sampled directions do not point at an emitter at all.
-RB_HD void initial_brdf_occ_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis) {
-  const size_t pi = (size_t)y * fc.width + x;
-  const RbParams& P = fc.P;
-  const WaveBufs& w = fc.wave;
-  bool any = false;
-  for (int i = 0; i < P.M_Brdf; ++i) any = any || w.hits[(size_t)i * w.npix + pi].tri != 0xFFFFFFFFu;
-  if (!any) return;  // (emissive pixels queued no ray and hold "miss" records)
-  const GElem g = load_gelem(fc.G, pi);
-  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
-  const Shading sh = make_shading(g, fc.cam.pos);
-  for (int i = 0; i < P.M_Brdf; ++i) {
-    const HitRec hr = w.hits[(size_t)i * w.npix + pi];
-    if (hr.tri == 0xFFFFFFFFu) continue;
-    const uint32_t base = 4u * (uint32_t)(P.M_Area + i);
-    float pdf;
-    const V3 wi = brdf_sample(g, sh, key, base, &pdf);
-    const V3 org = g.pos + P.normalOffset * g.normal;
-    vis.push(i, org, wi, hr.t);
-  }
-}
+// Second step of the two-step BRDF-candidate rays: where the emissive-only BVH reported a hit (t, id), the full BVH is
+// asked whether anything precedes it (trace8_precedes / k_trace_queue<true, true>). Those rays are queued by the first
+// traversal itself (brdf_chain_push); few rays reach this step: most BRDF-sampled directions do not point at an emitter.
 
 // =====================================================================================
 // Pass 2: visibility (ReSTIRIntegrator::visibilityPass, :302-312). The reference traces for every pixel, even
@@ -790,6 +794,20 @@ RB_HD void temporal_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vi
   const size_t pi = (size_t)y * fc.width + x;
   const WaveBufs& wv = fc.wave;
   U4* rec_flags = wv.cand + (size_t)wv.npix + pi;
+  if (BANDED != 1 && (wv.fuse_vis & 2u)) {
+    // resolve half of the visibility pass (visibility_pixel<ResolveVis>) on this pixel's reservoir, in place, before
+    // anything reads it: W = 0 where the ray queued by the initial pass was occluded. (Only the bulk launch does it;
+    // a deferred pixel's second run finds the reservoir already final.)
+    cnt.anyW++;
+    F4 nw = ld4(fc.Rread.normal_W + pi);
+    if (nw.w != 0.0f) {
+      cnt.anyT++;
+      if (wv.occ[pi] != 0) {
+        nw.w = 0.0f;
+        st4(fc.Rread.normal_W + pi, nw);
+      }
+    }
+  }
   const GElem curElem = load_gelem(fc.G, pi);
   int px, py;
   if (!reproject(fc.prevCam, fc.width, fc.height, curElem.pos, &px, &py)) {

@@ -69,10 +69,8 @@ RB_PIXEL_KERNEL(k_shade, InlineVis, true, 4, shade_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_gbuffer_stream, GenVis, false, 4, gbuffer_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL(k_gbuffer_resolve, ResolveVis, true, 2, gbuffer_resolve_pixel(fc, x, y, cnt))
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
-RB_PIXEL_KERNEL(k_initial_brdf_occ_stream, GenVis, false, 2, initial_brdf_occ_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))  // 95 regs, no spills
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_visibility_stream, GenVis, false, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_temporal_stream, GenVis, true, 3, temporal_gen_pixel<0>(fc, x, y, vis, cnt))
 // bands: the bulk launch defers the few pixels whose reprojection leaves the rows held here ...
@@ -142,6 +140,7 @@ struct QueueIO {
   uint8_t* occ;
   HitRec* hits;
   float tnear;
+  WaveBufs chain;  // chain.chain_rays != nullptr: a closest-hit ray that found something queues its follow-up ray there
   __device__ uint32_t count() const { return min(*count_ptr, capacity); }
   __device__ void fetch(uint32_t i, V3* o, V3* d, float* tn, float* tf, uint32_t* dest) const {
     const float4 a = __ldg(reinterpret_cast<const float4*>(&rays[i].o_tfar));
@@ -150,7 +149,10 @@ struct QueueIO {
   }
   __device__ uint32_t tie_id(uint32_t dest) const { return hits[dest].tri; }  // written by the previous trace
   __device__ void put_any(uint32_t dest, bool hit) const { occ[dest] = hit ? 1 : 0; }
-  __device__ void put_closest(const SceneDev&, uint32_t dest, const Trav& T) const { hits[dest] = T.best; }
+  __device__ void put_closest(const SceneDev&, uint32_t dest, const Trav& T) const {
+    hits[dest] = T.best;
+    if (chain.chain_rays != nullptr && T.best.tri != 0xFFFFFFFFu) brdf_chain_push(chain, T.o, T.d, T.best.t, dest);
+  }
 };
 struct SeamIO {
   const RbRay* rays;
@@ -1366,7 +1368,7 @@ static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32
     h->waveCandCap = (size_t)cand_slots * npix;
   }
   const size_t band_px = (size_t)h->info.width * (h->info.band_y1 - h->info.band_y0);
-  const size_t need_rays = band_px * std::max<uint32_t>(slots, brdf_slots);
+  const size_t need_rays = band_px * std::max<uint32_t>(slots, 2u * brdf_slots);  // (second half: the chained "precedes" rays)
   if (need_rays > h->waveRayCap) {
     if (h->wave.rays) cudaFree(h->wave.rays);
     h->wave.rays = nullptr;
@@ -1393,6 +1395,10 @@ static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32
   const bool banded = !(h->info.band_y0 == 0 && h->info.band_y1 == h->info.height);
   if (banded && !h->wave.deferred) RB_CUDA(cudaMalloc((void**)&h->wave.deferred, npix * sizeof(uint32_t)));
   h->wave.deferred_count = reinterpret_cast<uint32_t*>(h->counters + 4);  // zeroed with the ray counters at frame begin
+  h->wave.chain_count = reinterpret_cast<uint32_t*>(h->counters + 5);     // {queued, next}: likewise
+  h->wave.chain_rays = h->wave.rays + band_px * brdf_slots;
+  h->wave.chain_capacity = (uint32_t)(band_px * brdf_slots);
+  h->wave.fuse_vis = 0u;
   RB_TRY(ensure_counters(h));
   h->wave.capacity = (uint32_t)h->waveRayCap;
   h->wave.npix = (uint32_t)npix;
@@ -1439,8 +1445,14 @@ static void fs_trace(RbContext* h, int mode, int pass, float tnear = -1.0f) {
   if (tnear < 0.0f) tnear = FLT_MIN + P.tnearOffset;
   const int trace_grid = h->numSMs * h->traceBlocksPerSM;
   const WaveBufs& w = h->wave;
-  const QueueIO io{w.rays, w.count, w.capacity, w.occ, w.hits, tnear};
-#define RB_TRACE_ARGS(SC) SC, io, w.count + 1, h->refillLanes, h->postponeLanes
+  QueueIO io{w.rays, w.count, w.capacity, w.occ, w.hits, tnear, WaveBufs{}};
+  uint32_t* next = w.count + 1;
+  if (mode == TRACE_CLOSEST_EMISSIVE) io.chain = w;  // queues the "precedes" rays of its hits (brdf_chain_push) ...
+  if (mode == TRACE_ANY_PRECEDES) {                  // ... which this launch traces
+    io.rays = w.chain_rays, io.count_ptr = w.chain_count, io.capacity = w.chain_capacity;
+    next = w.chain_count + 1;
+  }
+#define RB_TRACE_ARGS(SC) SC, io, next, h->refillLanes, h->postponeLanes
   if (mode == TRACE_ANY)
     k_trace_queue<true, false, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
   else if (mode == TRACE_CLOSEST)
@@ -1552,33 +1564,36 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       launch_rows(h, k_initial_brdf_stream, y0, y1);
       fs_mark(h, 1, 0);
       if (fc.wave.brdf_two_step) {
-        // closest EMITTER along each ray (small BVH), then "does anything precede it?" for the few rays that found one
+        // closest EMITTER along each ray (small BVH); the traversal queues "does anything precede it?" for the few rays
+        // that found one, and the second launch traces those against the full BVH
         fs_trace(h, TRACE_CLOSEST_EMISSIVE, 1);
-        fs_reset_queue(h);
-        launch_rows(h, k_initial_brdf_occ_stream, y0, y1);
-        fs_mark(h, 1, 0);
         fs_trace(h, TRACE_ANY_PRECEDES, 1);
       } else {
         fs_trace(h, TRACE_CLOSEST, 1);
       }
     }
-    // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel
-    if (P.doVisibilityPass)
+    // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel; with the visibility
+    // pass on, the resolve kernel also queues that pass's ray for the reservoir it has just produced
+    if (P.doVisibilityPass) {
+      fs_reset_queue(h);
+      fc.wave.fuse_vis = 1u;
       launch_rows(h, k_initial_resolve, y0, y1, 128);
-    else
+      fc.wave.fuse_vis = 0u;
+    } else
       launch_rows(h, k_initial_resolve_inline_shadow, y0, y1);
   } else {
     launch_rows(h, k_initial, y0, y1);
   }
   fs_mark(h, 1, 0);
   // ---- visibility ---------------------------------------------------------------------------------
+  const bool temporal_runs = P.doTemporalReuse && frame_idx > 0 && h->havePrev;
+  bool vis_in_temporal = false;
   if (P.doVisibilityPass) {
     if (F.wave) {
-      fs_reset_queue(h);
-      launch_rows(h, k_visibility_stream, y0, y1);
-      fs_mark(h, 2, 0);
-      fs_trace(h, TRACE_ANY, 2);
-      launch_rows(h, k_visibility_resolve, y0, y1);
+      fs_trace(h, TRACE_ANY, 2);  // the rays were queued by k_initial_resolve
+      // the result is applied by the temporal stream kernel when there is one, else by the pass's own resolve kernel
+      vis_in_temporal = temporal_runs;
+      if (!vis_in_temporal) launch_rows(h, k_visibility_resolve, y0, y1);
     } else {
       launch_rows(h, k_visibility, y0, y1);
     }
@@ -1591,12 +1606,13 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     h->shipPending = false;
   }
   // ---- temporal reuse ----------------------------------------------------------------------------------
-  if (P.doTemporalReuse && frame_idx > 0 && h->havePrev) {
+  if (temporal_runs) {
     std::swap(h->rRead, h->rWrite);  // swapReservoirBuffers, P/simpleguidx11.h:116
     fs_bind(h);
     fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_TEMPORAL, 0);
     if (F.wave) {
       fs_reset_queue(h);
+      fc.wave.fuse_vis = vis_in_temporal ? 2u : 0u;
       if (banded) {
         launch_rows(h, k_temporal_stream_banded, y0, y1);
         k_temporal_stream_deferred<<<h->numSMs, 128, 0, st>>>(fc);
@@ -1604,6 +1620,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       } else {
         launch_rows(h, k_temporal_stream, y0, y1);
       }
+      fc.wave.fuse_vis = 0u;
       fs_mark(h, 3, 0);
       fs_trace(h, TRACE_ANY, 3);
       launch_rows(h, k_temporal_resolve, y0, y1);

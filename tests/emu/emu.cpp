@@ -58,6 +58,8 @@ struct Emu {
   std::vector<uint8_t> occ;
   std::vector<HitRec> hits;
   std::vector<U4> cand;
+  std::vector<RayQ> chain;
+  uint32_t chain_count[2] = {0, 0};
   std::vector<uint32_t> deferred;
   uint32_t deferred_count = 0;
   unsigned long long n_deferred_total = 0;  // over all frames: lets a test see that the deferral path ran
@@ -334,9 +336,12 @@ static void emu_trace_queue(Emu* E, int mode, float tnear = -1.0f) {
   FrameCtx& fc = E->fc;
   if (tnear < 0.0f) tnear = FLT_MIN + E->Pf.tnearOffset;
   const SceneDev em = emissive_view(fc.sc);
+  // the "precedes" step consumes the queue the closest-emitter step filled (brdf_chain_push), as on the device
+  const RayQ* q = mode == EMU_ANY_PRECEDES ? E->chain.data() : E->rays.data();
+  const int64_t qn = mode == EMU_ANY_PRECEDES ? (int64_t)std::min<uint32_t>(E->chain_count[0], fc.wave.chain_capacity) : (int64_t)E->qcount;
 #pragma omp parallel for schedule(dynamic, 64)
-  for (int64_t i = 0; i < (int64_t)E->qcount; ++i) {
-    const RayQ& r = E->rays[i];
+  for (int64_t i = 0; i < qn; ++i) {
+    const RayQ& r = q[i];
     const uint32_t dest = f2u(r.d_dest.w);
     HitRec hr;
     if (mode == EMU_ANY)
@@ -346,6 +351,7 @@ static void emu_trace_queue(Emu* E, int mode, float tnear = -1.0f) {
     else {
       trace8<false>(mode == EMU_CLOSEST_EMISSIVE ? em : fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr);
       E->hits[dest] = hr;
+      if (mode == EMU_CLOSEST_EMISSIVE && hr.tri != 0xFFFFFFFFu) brdf_chain_push(fc.wave, xyz(r.o_tfar), xyz(r.d_dest), hr.t, dest);
     }
   }
 }
@@ -415,6 +421,12 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     fc.wave.cand = E->cand.data();
     E->deferred.assign(npix, 0xFFFFFFFFu);
     E->deferred_count = 0;
+    E->chain.assign((size_t)npix * std::max(P.M_Brdf, 1), RayQ{});
+    E->chain_count[0] = E->chain_count[1] = 0;
+    fc.wave.chain_rays = E->chain.data();
+    fc.wave.chain_count = E->chain_count;
+    fc.wave.chain_capacity = (uint32_t)E->chain.size();
+    fc.wave.fuse_vis = 0u;
     fc.wave.deferred = E->deferred.data();
     fc.wave.deferred_count = &E->deferred_count;
   }
@@ -437,34 +449,40 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
       emu_stream(E, [&](int x, int y, Cnt&) { initial_brdf_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}); });
       if (fc.wave.brdf_two_step) {
         emu_trace_queue(E, EMU_CLOSEST_EMISSIVE);
-        emu_stream(E, [&](int x, int y, Cnt&) { initial_brdf_occ_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}); });
         emu_trace_queue(E, EMU_ANY_PRECEDES);
       } else {
         emu_trace_queue(E, EMU_CLOSEST);
       }
     }
-    if (P.doVisibilityPass)
+    if (P.doVisibilityPass) {  // the resolve kernel also queues the visibility pass's rays (fresh queue)
+      E->qcount = 0;
+      fc.wave.fuse_vis = 1u;
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
-    else
+      fc.wave.fuse_vis = 0u;
+    } else
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveInlineShadowVis{&fc, PX(fc, x, y)}, c); });
   } else {
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
   }
+  const bool temporal_runs = P.doTemporalReuse && frame_idx > 0 && E->havePrev;
+  bool vis_in_temporal = false;
   if (P.doVisibilityPass) {
     if (wave) {
-      emu_stream(E, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
-      emu_trace_queue(E, EMU_ANY);
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
+      emu_trace_queue(E, EMU_ANY);  // rays queued by the initial-pass resolve
+      vis_in_temporal = temporal_runs;  // applied by the temporal stream pass when there is one
+      if (!vis_in_temporal)
+        for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
     } else {
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { visibility_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
     }
   }
-  if (P.doTemporalReuse && frame_idx > 0 && E->havePrev) {
+  if (temporal_runs) {
     std::swap(E->rRead, E->rWrite);
     emu_bind(E);
     fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_TEMPORAL, 0);
     if (wave) {
       E->qcount = 0;
+      fc.wave.fuse_vis = vis_in_temporal ? 2u : 0u;
       if (banded) {  // as the device schedule: bulk launch with deferral, then the deferred pixels with the re-derivation code
         for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<2>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
         unsigned long long c0 = 0, c1 = 0, c2 = 0;
@@ -479,6 +497,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
       } else {
         for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_gen_pixel<0>(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
       }
+      fc.wave.fuse_vis = 0u;
       emu_trace_queue(E, EMU_ANY);
       for_pixels(E, fc, [&](int x, int y, Cnt& c) { temporal_merge_pixel(fc, x, y, c); });
     } else if (banded) {
