@@ -50,6 +50,7 @@ struct WaveBufs {
   // visibility ray of the reservoir it has just produced; bit 1 = the temporal stream kernel applies the traced result
   // (W = 0 where occluded) before it uses the reservoir. Either bit clear = k_visibility_stream / _resolve do it.
   uint32_t fuse_vis;
+  uint32_t fuse_shade;  // the last spatial pass's resolve kernel also shades the pixel (no k_shade launch)
 };
 
 struct FrameCtx {
@@ -1147,13 +1148,42 @@ RB_HD void spatial_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis
   }
 }
 
+// Final shading of one pixel from its reservoir (body of shade_pixel below, see there). The shadow ray of the
+// reference can never change the pixel: W > 0 means the sample was found unoccluded from this pixel by the pass that
+// produced the reservoir; with W == 0 or NaN every component of f * V * W is 0 or NaN for V = 0 and V = 1 alike, and a
+// NaN component zeroes the pixel in sanitize. KnownVis therefore answers "visible" without tracing (it is reached only
+// in the NaN / non-finite cases, where shadow_F0 still counts the ray the reference traces).
+struct KnownVis {
+  static constexpr bool kStore = true;
+  RB_HD bool visible(int, const V3&, const V3&) const { return true; }
+};
+RB_HD void shade_store(const FrameCtx& fc, size_t pi, const Reservoir& r, Cnt& cnt) {
+  V3 pixel;
+  if (r.w_sum > 0.0f) {  // Reservoir::hasSample
+    const GElem g = load_gelem(fc.G, pi);
+    const Shading sh = make_shading(g, fc.cam.pos);
+    const V3 f = eval_F(r.bestSample, g, sh, true, KnownVis{}, 0, cnt, 1, vis_mode_from_W(r.W, true));
+    pixel = f * r.W;
+  } else {
+    pixel = xyz(ld4(fc.G.emission + pi));
+  }
+  if (pixel.x != pixel.x || pixel.y != pixel.y || pixel.z != pixel.z) pixel = v3(0);
+  if (pixel.x < 0 || pixel.y < 0 || pixel.z < 0) pixel = v3(0);
+  float* o = fc.frame + 3 * pi;
+  o[0] = pixel.x;
+  o[1] = pixel.y;
+  o[2] = pixel.z;
+}
+
 RB_HD void spatial_merge_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
   const size_t pi = (size_t)y * fc.width + x;
   const RbParams& P = fc.P;
   const WaveBufs& wv = fc.wave;
   const U4 r0 = wv.cand[pi];
   if ((r0.w >> RB_CAND_INDEX_BITS) & RB_CAND_COPY) {
-    store_reservoir(fc.Rwrite, pi, load_reservoir(fc.Rread, pi));
+    const Reservoir keep = load_reservoir(fc.Rread, pi);
+    store_reservoir(fc.Rwrite, pi, keep);
+    if (wv.fuse_shade) shade_store(fc, pi, keep, cnt);
     return;
   }
   const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
@@ -1194,6 +1224,7 @@ RB_HD void spatial_merge_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
   out.W = final_p_hat > 0.0f ? w_sum / final_p_hat : 0.0f;
   out.confidence = imin(confidence, P.confidenceCap);
   store_reservoir(fc.Rwrite, pi, out);
+  if (wv.fuse_shade) shade_store(fc, pi, out, cnt);
 }
 
 // =====================================================================================
@@ -1202,24 +1233,9 @@ RB_HD void spatial_merge_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
 // unoccluded there, W == 0 zeroes the pixel — the reference's shadow ray never changes the result.
 // =====================================================================================
 template <class Vis>
-RB_HD void shade_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
+RB_HD void shade_pixel(const FrameCtx& fc, int x, int y, const Vis&, Cnt& cnt) {
   const size_t pi = (size_t)y * fc.width + x;
-  const Reservoir r = load_reservoir(fc.Rread, pi);
-  V3 pixel;
-  if (r.w_sum > 0.0f) {  // Reservoir::hasSample
-    const GElem g = load_gelem(fc.G, pi);
-    const Shading sh = make_shading(g, fc.cam.pos);
-    const V3 f = eval_F(r.bestSample, g, sh, true, vis, 0, cnt, 1, vis_mode_from_W(r.W, true));
-    pixel = f * r.W;
-  } else {
-    pixel = xyz(ld4(fc.G.emission + pi));
-  }
-  if (pixel.x != pixel.x || pixel.y != pixel.y || pixel.z != pixel.z) pixel = v3(0);
-  if (pixel.x < 0 || pixel.y < 0 || pixel.z < 0) pixel = v3(0);
-  float* o = fc.frame + 3 * pi;
-  o[0] = pixel.x;
-  o[1] = pixel.y;
-  o[2] = pixel.z;
+  shade_store(fc, pi, load_reservoir(fc.Rread, pi), cnt);
 }
 
 // =====================================================================================

@@ -384,6 +384,7 @@ struct FrameState {
   FrameCtx fc{};
   RbParams P{};
   bool open = false, timed = false, wave = false, wave_spatial = false;
+  bool shaded = false;  // the last spatial pass's resolve kernel has written frame_data already
   uint32_t launches = 0, frame_idx = 0;
   std::vector<FrameMark> marks;
 };
@@ -1399,6 +1400,7 @@ static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32
   h->wave.chain_rays = h->wave.rays + band_px * brdf_slots;
   h->wave.chain_capacity = (uint32_t)(band_px * brdf_slots);
   h->wave.fuse_vis = 0u;
+  h->wave.fuse_shade = 0u;
   RB_TRY(ensure_counters(h));
   h->wave.capacity = (uint32_t)h->waveRayCap;
   h->wave.npix = (uint32_t)npix;
@@ -1498,6 +1500,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   F.launches = 0;
   F.frame_idx = frame_idx;
   F.open = true;
+  F.shaded = false;
   // The stream -> trace -> resolve split covers the passes whose rays do not depend on visibility results:
   // BRDF-candidate rays, the visibility pass, temporal reuse, spatial reuse with constant weights.
   F.wave = P.wavefront != 0;
@@ -1653,8 +1656,12 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
   fs_bind(h);
   fc.spatial_iter = i;
   fc.frame_key = rng_frame_key(h->info.seed, F.frame_idx, PASS_SPATIAL, (uint32_t)i);
+  F.shaded = false;
   if (F.wave_spatial) {
     fs_reset_queue(h);
+    // the last pass's resolve kernel shades the pixel from the reservoir it holds in registers
+    F.shaded = (i == P.spatialPassCount - 1);
+    fc.wave.fuse_shade = F.shaded ? 1u : 0u;
     auto kss = k_spatial_stream;
     launch_rows(h, kss, iy0, iy1);
     if (overlap_halo) {
@@ -1665,6 +1672,7 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
     fs_mark(h, 4, 0);
     fs_trace(h, TRACE_ANY, 4);
     launch_rows(h, k_spatial_resolve, y0, y1);
+    fc.wave.fuse_shade = 0u;
   } else {
     launch_rows(h, k_spatial, iy0, iy1);
     if (overlap_halo) {
@@ -1685,7 +1693,8 @@ static int frame_end(RbHandle h, RbTimings* timings) {
   cudaStream_t st = h->stream;
   std::swap(h->rRead, h->rWrite);
   fs_bind(h);
-  launch_rows(h, k_shade, h->info.band_y0, h->info.band_y1);
+  if (!F.shaded) launch_rows(h, k_shade, h->info.band_y0, h->info.band_y1);
+  F.shaded = false;
   fs_mark(h, 5, 0);
   RB_CUDA(cudaGetLastError());
   // memcpy(reservoirsLastFrame, ...) + gBufferLastFrame.setDataFrom(gBuffer) (P/simpleguidx11.cpp:478-481) by rotation

@@ -58,6 +58,7 @@ struct Emu {
   std::vector<uint8_t> occ;
   std::vector<HitRec> hits;
   std::vector<U4> cand;
+  bool shaded = false;
   std::vector<RayQ> chain;
   uint32_t chain_count[2] = {0, 0};
   std::vector<uint32_t> deferred;
@@ -427,6 +428,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     fc.wave.chain_count = E->chain_count;
     fc.wave.chain_capacity = (uint32_t)E->chain.size();
     fc.wave.fuse_vis = 0u;
+    fc.wave.fuse_shade = 0u;
     fc.wave.deferred = E->deferred.data();
     fc.wave.deferred_count = &E->deferred_count;
   }
@@ -507,6 +509,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     }
   }
   E->open = true;
+  E->shaded = false;
   return 0;
 }
 
@@ -518,11 +521,15 @@ int emu_frame_spatial(void* h, int i) {
   emu_bind(E);
   fc.spatial_iter = i;
   fc.frame_key = rng_frame_key(E->seed, E->frame_idx, PASS_SPATIAL, (uint32_t)i);
+  E->shaded = false;
   if (E->wave_spatial) {
     E->qcount = 0;
+    E->shaded = (i == E->Pf.spatialPassCount - 1);  // the last pass's resolve also shades, as on the device
+    fc.wave.fuse_shade = E->shaded ? 1u : 0u;
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}, c); });
     emu_trace_queue(E, EMU_ANY);
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_merge_pixel(fc, x, y, c); });
+    fc.wave.fuse_shade = 0u;
   } else {
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
   }
@@ -535,7 +542,8 @@ int emu_frame_end(void* h, float* rgb_out) {
   FrameCtx& fc = E->fc;
   std::swap(E->rRead, E->rWrite);
   emu_bind(E);
-  for_pixels(E, fc, [&](int x, int y, Cnt& c) { shade_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
+  if (!E->shaded) for_pixels(E, fc, [&](int x, int y, Cnt& c) { shade_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
+  E->shaded = false;
   std::swap(E->rLast, E->rRead);
   E->gCur ^= 1;
   E->prevCam = fc.cam;
