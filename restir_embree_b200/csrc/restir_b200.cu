@@ -66,8 +66,6 @@ RB_PIXEL_KERNEL(k_temporal_banded, InlineVis, true, 1, (temporal_pixel<InlineVis
 RB_PIXEL_KERNEL(k_spatial, InlineVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_shade, InlineVis, true, 4, shade_pixel(fc, x, y, vis, cnt))
 // wavefront halves
-RB_PIXEL_KERNEL(k_gbuffer_stream, GenVis, false, 4, gbuffer_gen_pixel(fc, x, y, vis))
-RB_PIXEL_KERNEL(k_gbuffer_resolve, ResolveVis, true, 2, gbuffer_resolve_pixel(fc, x, y, cnt))
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))  // 95 regs, no spills
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
@@ -381,7 +379,8 @@ struct FrameMark {
   int pass, kind;  // kind 0 = streaming kernel, 1 = traversal kernel
 };
 struct FrameState {
-  FrameCtx fc{};
+  FrameCtx fc{};   // back half (and everything host code reads back)
+  FrameCtx ffc{};  // front half
   RbParams P{};
   bool open = false, timed = false, wave = false, wave_spatial = false;
   bool shaded = false;  // the last spatial pass's resolve kernel has written frame_data already
@@ -397,10 +396,26 @@ struct RbContext {
   std::vector<void*> allocs;
 
   // frame state
-  GBufPlanes G[2]{};
-  int gCur = 0;
-  ResPlanes R[3]{};
-  int rRead = 0, rWrite = 1, rLast = 2;
+  // Frame pipeline: a frame is a FRONT half (G-buffer, initial candidates incl. the BRDF-candidate rays; depends on the
+  // camera only) and a BACK half (visibility trace, temporal and spatial reuse, shading; depends on the previous
+  // frame's reservoirs). The front half of frame n+1 is issued on its own stream and overlaps the back half of frame
+  // n, which fills the tails and ramps at the back half's many kernel boundaries and the waits for neighbour bands.
+  // That takes one more G-buffer (3: being written / current / previous) and one more reservoir buffer (4: the front
+  // half's output + the three the back half rotates), and separate ray queues for the two halves.
+  GBufPlanes G[3]{};
+  int gCur = 2;  // G-buffer of the frame rendered last (the next frame takes (gCur + 1) % 3)
+  ResPlanes R[4]{};
+  int rRead = 0, rWrite = 1, rLast = 2, rFree = 3;
+  cudaStream_t fstream = nullptr;  // front halves (lower priority than `stream`)
+  cudaEvent_t evFrontDone = nullptr, evBackDone[2]{};
+  bool backRecorded[2]{};
+  uint32_t frameSeq = 0;
+  bool overlap = true;  // RB_OVERLAP=0: both halves on `stream`
+  WaveBufs fwave{};     // front half: BRDF-candidate rays (+ chained "precedes" rays), their hits / occlusion bytes
+  RayQ* visRays[2]{};   // visibility rays of frame parity p: queued by the front half, traced by the back half
+  size_t fwaveRayCap = 0, fwaveHitCap = 0, visRayCap = 0;
+  unsigned long long* counters2 = nullptr;  // [2][8]: per frame parity {closest, any as written, any traced, -, deferred
+                                            // count, chain queue pair, BRDF queue pair, visibility queue pair}
   float* frame = nullptr;
   float* accumulator = nullptr;  // N1: running mean of frame_data
   F4* display = nullptr;         // N1: tonemapped / gamma-compressed display_data
@@ -420,8 +435,8 @@ struct RbContext {
   // halo rows over peer memory (k_halo_push / k_halo_wait): the neighbours' reservoir planes and flag words mapped with
   // CUDA IPC in rb_comm_init; RB_HALO=nccl (or a failed mapping on any rank) keeps the grouped ncclSend/ncclRecv path
   bool p2p = false;
-  void* peerBase[2][13]{};      // cudaIpcOpenMemHandle results, [above, below][12 planes + flags]
-  ResPlanes peerR[2][3]{};
+  void* peerBase[2][17]{};      // cudaIpcOpenMemHandle results, [above, below][16 planes + flags]
+  ResPlanes peerR[2][4]{};
   uint32_t* peerFlags[2]{};
   uint32_t* haloFlags = nullptr;  // [0] stamp pushed by the rank above, [1] by the rank below, [2] push block counter
   uint32_t* haloErr = nullptr;    // mapped pinned host word: a wait that timed out leaves its stamp here
@@ -456,12 +471,11 @@ struct RbContext {
   int numSMs = 148;
   // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
   int refillLanes = 26, postponeLanes = 8, traceBlocksPerSM = 8;
-  bool waveGbuf = false;
   bool twoStepBrdf = true;  // RB_TWO_STEP_BRDF=0 traces the BRDF-candidate rays against the full BVH instead
 
   // wavefront buffers
   WaveBufs wave{};
-  size_t waveRayCap = 0, waveOccCap = 0, waveHitCap = 0, waveCandCap = 0;
+  size_t waveRayCap = 0, waveOccCap = 0, waveCandCap = 0;
   uint32_t* waveCounters = nullptr;
   int wavePair = 0;
 };
@@ -812,16 +826,16 @@ static int halo_p2p_setup(RbContext* h) {
   RB_CUDA(cudaHostAlloc((void**)&h->haloErr, sizeof(uint32_t), cudaHostAllocMapped));
   *h->haloErr = 0u;
   h->haloSeq = 0;
-  constexpr int NH = 13;
+  constexpr int NH = 17;
   cudaIpcMemHandle_t mine[NH], theirs[2][NH];
   memset(mine, 0, sizeof(mine));
   memset(theirs, 0, sizeof(theirs));
   void* ptrs[NH];
-  for (int b = 0; b < 3; ++b) {
+  for (int b = 0; b < 4; ++b) {
     ptrs[4 * b + 0] = h->R[b].point_wsum, ptrs[4 * b + 1] = h->R[b].normal_W, ptrs[4 * b + 2] = h->R[b].Li_conf,
                  ptrs[4 * b + 3] = h->R[b].light_idx;
   }
-  ptrs[12] = h->haloFlags;
+  ptrs[16] = h->haloFlags;
   int ok = want && g_nccl.AllReduce ? 1 : 0;
   for (int i = 0; i < NH && ok; ++i)
     if (cudaIpcGetMemHandle(&mine[i], ptrs[i]) != cudaSuccess) ok = 0;
@@ -862,13 +876,13 @@ static int halo_p2p_setup(RbContext* h) {
   if (all_ok) {
     for (int d = 0; d < 2; ++d) {
       if (!has[d]) continue;
-      for (int b = 0; b < 3; ++b) {
+      for (int b = 0; b < 4; ++b) {
         h->peerR[d][b].point_wsum = (F4*)h->peerBase[d][4 * b + 0];
         h->peerR[d][b].normal_W = (F4*)h->peerBase[d][4 * b + 1];
         h->peerR[d][b].Li_conf = (F4*)h->peerBase[d][4 * b + 2];
         h->peerR[d][b].light_idx = (int*)h->peerBase[d][4 * b + 3];
       }
-      h->peerFlags[d] = (uint32_t*)h->peerBase[d][12];
+      h->peerFlags[d] = (uint32_t*)h->peerBase[d][16];
     }
     h->p2p = true;
   } else {
@@ -941,9 +955,13 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
   };
   auto body = [&]() -> int {
     RB_CUDA(cudaSetDevice(info->device));
-    RB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;  // the back half (critical path) outranks the front half of the next frame
+      RB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      RB_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi));
+    }
     const size_t n = (size_t)info->width * info->height;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       RB_TRY(dev_alloc(h, &h->G[i].pos_depth, n, h->allocs));
       RB_TRY(dev_alloc(h, &h->G[i].normal_shin, n, h->allocs));
       RB_TRY(dev_alloc(h, &h->G[i].diffuse_iim, n, h->allocs));
@@ -957,7 +975,7 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
       RB_CUDA(cudaMemsetAsync(h->G[i].emission, 0, n * 16, h->stream));
       RB_CUDA(cudaMemsetAsync(h->G[i].hit_ids, 0xFF, n * 8, h->stream));
     }
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
       RB_TRY(dev_alloc(h, &h->R[i].point_wsum, n, h->allocs));
       RB_TRY(dev_alloc(h, &h->R[i].normal_W, n, h->allocs));
       RB_TRY(dev_alloc(h, &h->R[i].Li_conf, n, h->allocs));
@@ -974,8 +992,16 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     RB_TRY(dev_alloc(h, &h->display, n, h->allocs));
     RB_CUDA(cudaMemsetAsync(h->display, 0, n * 16, h->stream));
     RB_TRY(dev_alloc(h, &h->statSums, 2, h->allocs));
-    RB_TRY(dev_alloc(h, &h->counters, 8, h->allocs));
-    RB_CUDA(cudaMemsetAsync(h->counters, 0, 64, h->stream));
+    RB_TRY(dev_alloc(h, &h->counters2, 16, h->allocs));
+    RB_CUDA(cudaMemsetAsync(h->counters2, 0, 128, h->stream));
+    h->counters = h->counters2;
+    {
+      int lo = 0, hi = 0;
+      RB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      RB_CUDA(cudaStreamCreateWithPriority(&h->fstream, cudaStreamNonBlocking, lo));
+    }
+    RB_CUDA(cudaEventCreateWithFlags(&h->evFrontDone, cudaEventDisableTiming));
+    for (auto& ev : h->evBackDone) RB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : h->ev) RB_CUDA(cudaEventCreate(&ev));
     for (auto& ev : h->fev) RB_CUDA(cudaEventCreate(&ev));
     h->evCreated = true;
@@ -983,7 +1009,7 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     if (const char* e = getenv("RB_REFILL")) h->refillLanes = atoi(e);
     if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
     if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
-    if (const char* e = getenv("RB_WAVE_GBUF")) h->waveGbuf = atoi(e) != 0;
+    if (const char* e = getenv("RB_OVERLAP")) h->overlap = atoi(e) != 0;
     if (const char* e = getenv("RB_TWO_STEP_BRDF")) h->twoStepBrdf = atoi(e) != 0;
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
@@ -1017,12 +1043,23 @@ void rb_destroy(RbHandle h) {
   }
   if (h->wave.rays) cudaFree(h->wave.rays);
   if (h->wave.occ) cudaFree(h->wave.occ);
-  if (h->wave.hits) cudaFree(h->wave.hits);
+  if (h->fwave.rays) cudaFree(h->fwave.rays);
+  if (h->fwave.hits) cudaFree(h->fwave.hits);
+  if (h->fwave.occ) cudaFree(h->fwave.occ);
+  for (auto q : h->visRays)
+    if (q) cudaFree(q);
+  if (h->fstream) {
+    cudaStreamSynchronize(h->fstream);
+    cudaStreamDestroy(h->fstream);
+  }
+  if (h->evFrontDone) cudaEventDestroy(h->evFrontDone);
+  for (auto ev : h->evBackDone)
+    if (ev) cudaEventDestroy(ev);
   if (h->wave.cand) cudaFree(h->wave.cand);
   if (h->wave.deferred) cudaFree(h->wave.deferred);
   if (h->waveCounters) cudaFree(h->waveCounters);
   for (int d = 0; d < 2; ++d)
-    for (int i = 0; i < 13; ++i)
+    for (int i = 0; i < 17; ++i)
       if (h->peerBase[d][i]) cudaIpcCloseMemHandle(h->peerBase[d][i]);
   if (h->haloFlags) cudaFree(h->haloFlags);
   if (h->haloErr) cudaFreeHost(h->haloErr);
@@ -1369,7 +1406,8 @@ static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32
     h->waveCandCap = (size_t)cand_slots * npix;
   }
   const size_t band_px = (size_t)h->info.width * (h->info.band_y1 - h->info.band_y0);
-  const size_t need_rays = band_px * std::max<uint32_t>(slots, 2u * brdf_slots);  // (second half: the chained "precedes" rays)
+  // back half: the queues of the temporal and spatial passes
+  const size_t need_rays = band_px * slots;
   if (need_rays > h->waveRayCap) {
     if (h->wave.rays) cudaFree(h->wave.rays);
     h->wave.rays = nullptr;
@@ -1387,23 +1425,48 @@ static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32
     RB_CUDA(cudaMalloc((void**)&h->wave.occ, (size_t)slots * npix));
     h->waveOccCap = (size_t)slots * npix;
   }
-  if ((size_t)brdf_slots * npix > h->waveHitCap) {
-    if (h->wave.hits) cudaFree(h->wave.hits);
-    h->wave.hits = nullptr;
-    RB_CUDA(cudaMalloc((void**)&h->wave.hits, (size_t)brdf_slots * npix * sizeof(HitRec)));
-    h->waveHitCap = (size_t)brdf_slots * npix;
+  // front half: BRDF-candidate rays in the first half of its queue, the chained "precedes" rays in the second
+  const size_t need_front = band_px * 2u * brdf_slots;
+  if (need_front > h->fwaveRayCap) {
+    if (h->fwave.rays) cudaFree(h->fwave.rays);
+    h->fwave.rays = nullptr;
+    h->fwaveRayCap = 0;
+    RB_CUDA(cudaMalloc((void**)&h->fwave.rays, need_front * sizeof(RayQ)));
+    h->fwaveRayCap = need_front;
+  }
+  if ((size_t)brdf_slots * npix > h->fwaveHitCap) {
+    if (h->fwave.hits) cudaFree(h->fwave.hits);
+    if (h->fwave.occ) cudaFree(h->fwave.occ);
+    h->fwave.hits = nullptr, h->fwave.occ = nullptr;
+    h->fwaveHitCap = 0;
+    RB_CUDA(cudaMalloc((void**)&h->fwave.hits, (size_t)brdf_slots * npix * sizeof(HitRec)));
+    RB_CUDA(cudaMalloc((void**)&h->fwave.occ, (size_t)brdf_slots * npix));
+    h->fwaveHitCap = (size_t)brdf_slots * npix;
+  }
+  if (band_px > h->visRayCap) {  // visibility rays: one per pixel, one queue per frame parity
+    for (auto& q : h->visRays) {
+      if (q) cudaFree(q);
+      q = nullptr;
+    }
+    h->visRayCap = 0;
+    for (auto& q : h->visRays) RB_CUDA(cudaMalloc((void**)&q, band_px * sizeof(RayQ)));
+    h->visRayCap = band_px;
   }
   const bool banded = !(h->info.band_y0 == 0 && h->info.band_y1 == h->info.height);
   if (banded && !h->wave.deferred) RB_CUDA(cudaMalloc((void**)&h->wave.deferred, npix * sizeof(uint32_t)));
-  h->wave.deferred_count = reinterpret_cast<uint32_t*>(h->counters + 4);  // zeroed with the ray counters at frame begin
-  h->wave.chain_count = reinterpret_cast<uint32_t*>(h->counters + 5);     // {queued, next}: likewise
-  h->wave.chain_rays = h->wave.rays + band_px * brdf_slots;
-  h->wave.chain_capacity = (uint32_t)(band_px * brdf_slots);
-  h->wave.fuse_vis = 0u;
-  h->wave.fuse_shade = 0u;
   RB_TRY(ensure_counters(h));
   h->wave.capacity = (uint32_t)h->waveRayCap;
   h->wave.npix = (uint32_t)npix;
+  h->wave.fuse_vis = h->wave.fuse_shade = 0u;
+  h->wave.chain_rays = nullptr, h->wave.chain_count = nullptr, h->wave.chain_capacity = 0;
+  h->wave.hits = nullptr;
+  h->fwave.npix = (uint32_t)npix;
+  h->fwave.capacity = (uint32_t)(band_px * brdf_slots);
+  h->fwave.chain_rays = h->fwave.rays + band_px * brdf_slots;
+  h->fwave.chain_capacity = (uint32_t)(band_px * brdf_slots);
+  h->fwave.reset_pair = nullptr;
+  h->fwave.cand = nullptr, h->fwave.deferred = nullptr, h->fwave.deferred_count = nullptr;
+  h->fwave.fuse_vis = h->fwave.fuse_shade = 0u;
   return RB_OK;
 }
 
@@ -1430,23 +1493,26 @@ static void fs_bind(RbContext* h) {
 static dim3 rows_grid(const FrameCtx& fc, int ry0, int ry1, int tileH) {
   return dim3((fc.width + kTileW - 1) / kTileW, (std::max(ry1 - ry0, 0) + tileH - 1) / tileH);
 }
-// launch a pixel kernel over image rows [ry0, ry1)
+// launch a pixel kernel over image rows [ry0, ry1) — back half (h->fs.fc on h->stream) unless told otherwise
 template <class K>
-static void launch_rows(RbContext* h, K kernel, int ry0, int ry1, int threads = kTileW * kTileH) {
+static void launch_rows(RbContext* h, K kernel, int ry0, int ry1, int threads = kTileW * kTileH, const FrameCtx* ctx = nullptr,
+                        cudaStream_t st = nullptr) {
   if (ry1 <= ry0) return;
-  FrameCtx f = h->fs.fc;
+  FrameCtx f = ctx ? *ctx : h->fs.fc;
   f.y0 = ry0;
   f.y1 = ry1;
   const int tileH = threads / kTileW;
-  kernel<<<rows_grid(f, ry0, ry1, tileH), dim3(kTileW, tileH), 0, h->stream>>>(f);
+  kernel<<<rows_grid(f, ry0, ry1, tileH), dim3(kTileW, tileH), 0, st ? st : h->stream>>>(f);
   h->fs.launches++;
 }
 enum TraceMode { TRACE_CLOSEST = 0, TRACE_ANY = 1, TRACE_CLOSEST_EMISSIVE = 2, TRACE_ANY_PRECEDES = 3 };
-static void fs_trace(RbContext* h, int mode, int pass, float tnear = -1.0f) {
+// trace the queue of wave buffers `w` (the back half's by default)
+static void fs_trace(RbContext* h, int mode, int pass, float tnear = -1.0f, const WaveBufs* wsel = nullptr, cudaStream_t st = nullptr) {
   const RbParams& P = h->fs.P;
   if (tnear < 0.0f) tnear = FLT_MIN + P.tnearOffset;
   const int trace_grid = h->numSMs * h->traceBlocksPerSM;
-  const WaveBufs& w = h->wave;
+  const WaveBufs& w = wsel ? *wsel : h->wave;
+  if (!st) st = h->stream;
   QueueIO io{w.rays, w.count, w.capacity, w.occ, w.hits, tnear, WaveBufs{}};
   uint32_t* next = w.count + 1;
   if (mode == TRACE_CLOSEST_EMISSIVE) io.chain = w;  // queues the "precedes" rays of its hits (brdf_chain_push) ...
@@ -1456,16 +1522,18 @@ static void fs_trace(RbContext* h, int mode, int pass, float tnear = -1.0f) {
   }
 #define RB_TRACE_ARGS(SC) SC, io, next, h->refillLanes, h->postponeLanes
   if (mode == TRACE_ANY)
-    k_trace_queue<true, false, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
+    k_trace_queue<true, false, QueueIO><<<trace_grid, kTraceThreads, 0, st>>>(RB_TRACE_ARGS(h->sc));
   else if (mode == TRACE_CLOSEST)
-    k_trace_queue<false, false, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
+    k_trace_queue<false, false, QueueIO><<<trace_grid, kTraceThreads, 0, st>>>(RB_TRACE_ARGS(h->sc));
   else if (mode == TRACE_CLOSEST_EMISSIVE)
-    k_trace_queue<false, false, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(emissive_view(h->sc)));
+    k_trace_queue<false, false, QueueIO><<<trace_grid, kTraceThreads, 0, st>>>(RB_TRACE_ARGS(emissive_view(h->sc)));
   else
-    k_trace_queue<true, true, QueueIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(RB_TRACE_ARGS(h->sc));
+    k_trace_queue<true, true, QueueIO><<<trace_grid, kTraceThreads, 0, st>>>(RB_TRACE_ARGS(h->sc));
 #undef RB_TRACE_ARGS
-  h->wave.reset_pair = nullptr;
-  h->fs.fc.wave.reset_pair = nullptr;
+  if (!wsel) {
+    h->wave.reset_pair = nullptr;
+    h->fs.fc.wave.reset_pair = nullptr;
+  }
   h->fs.launches++;
   fs_mark(h, pass, 1);
 }
@@ -1513,6 +1581,88 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     RB_TRY(ensure_wave(h, slots, (uint32_t)std::max(P.M_Brdf, 1), cand_slots));
   }
   cudaStream_t st = h->stream;
+  // ---- FRONT half: G-buffer + initial candidates of this frame (depends on the camera only) ---------------------
+  const int par = (int)(h->frameSeq & 1u);
+  cudaStream_t sf = (h->overlap && !timed) ? h->fstream : st;
+  // its outputs (G[(gCur+1)%3], R[rFree], the parity's visibility queue and counters) were last used by the back half
+  // of the frame before last; its ray queues by the previous front half
+  if (h->backRecorded[par]) RB_CUDA(cudaStreamWaitEvent(sf, h->evBackDone[par], 0));
+  if (h->frameSeq > 0) RB_CUDA(cudaStreamWaitEvent(sf, h->evFrontDone, 0));
+  unsigned long long* ctr = h->counters2 + 8 * par;
+  h->counters = ctr;
+  RB_CUDA(cudaMemsetAsync(ctr, 0, 64, sf));
+  uint32_t* brdf_pair = reinterpret_cast<uint32_t*>(ctr + 6);
+  uint32_t* vis_pair = reinterpret_cast<uint32_t*>(ctr + 7);
+  const int gNew = (h->gCur + 1) % 3;
+  // G-buffer rows kept by this handle: the band plus a margin that covers the spatial reach and most reprojections
+  const int margin = banded ? std::max(16, spatial_reach(P)) : 0;
+  FrameCtx& ff = F.ffc;
+  ff = FrameCtx{};
+  ff.width = h->info.width;
+  ff.height = H;
+  ff.y0 = y0;
+  ff.y1 = y1;
+  ff.sc = h->sc;
+  ff.P = P;
+  ff.cam = cam_state(cam);
+  ff.prevCam = ff.cam;
+  ff.G = h->G[gNew];
+  ff.Gprev = h->G[gNew];
+  ff.Rread = ff.Rlast = ff.Rwrite = h->R[h->rFree];
+  ff.frame = h->frame;
+  ff.counters = ctr;
+  ff.gy0 = std::max(0, y0 - margin);
+  ff.gy1 = std::min(H, y1 + margin);
+  ff.wave = h->fwave;
+  ff.wave.count = brdf_pair;
+  ff.wave.chain_count = reinterpret_cast<uint32_t*>(ctr + 5);
+  ff.wave.brdf_two_step = (F.wave && h->twoStepBrdf && h->sc.em_n_nodes > 0) ? 1u : 0u;
+  if (timed) cudaEventRecord(h->fev[0], st);
+  // G-buffer: primary rays are coherent, the inline kernel beats queue + persistent traversal + resolve (measured)
+  ff.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_GBUF, 0);
+  launch_rows(h, k_gbuffer, ff.gy0, ff.gy1, 128, &ff, sf);
+  fs_mark(h, 0, 0);
+  // initial candidates
+  ff.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_INITIAL, 0);
+  if (F.wave) {
+    if (P.M_Brdf > 0 && h->sc.n_lights > 0) {
+      launch_rows(h, k_initial_brdf_stream, y0, y1, kTileW * kTileH, &ff, sf);
+      fs_mark(h, 1, 0);
+      if (ff.wave.brdf_two_step) {
+        // closest EMITTER along each ray (small BVH); the traversal queues "does anything precede it?" for the few rays
+        // that found one, and the second launch traces those against the full BVH
+        fs_trace(h, TRACE_CLOSEST_EMISSIVE, 1, -1.0f, &ff.wave, sf);
+        fs_trace(h, TRACE_ANY_PRECEDES, 1, -1.0f, &ff.wave, sf);
+      } else {
+        fs_trace(h, TRACE_CLOSEST, 1, -1.0f, &ff.wave, sf);
+      }
+    }
+    // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel; with the visibility
+    // pass on, the resolve kernel also queues that pass's ray for the reservoir it has just produced
+    if (P.doVisibilityPass) {
+      ff.wave.rays = h->visRays[par];
+      ff.wave.count = vis_pair;
+      ff.wave.capacity = (uint32_t)h->visRayCap;
+      ff.wave.fuse_vis = 1u;
+      launch_rows(h, k_initial_resolve, y0, y1, 128, &ff, sf);
+    } else {
+      launch_rows(h, k_initial_resolve_inline_shadow, y0, y1, kTileW * kTileH, &ff, sf);
+    }
+  } else {
+    launch_rows(h, k_initial, y0, y1, kTileW * kTileH, &ff, sf);
+  }
+  fs_mark(h, 1, 0);
+  RB_CUDA(cudaEventRecord(h->evFrontDone, sf));
+  RB_CUDA(cudaGetLastError());
+
+  // ---- BACK half: needs the front half and the previous frame -------------------------------------------------------
+  RB_CUDA(cudaStreamWaitEvent(st, h->evFrontDone, 0));
+  h->gCur = gNew;
+  {  // the front half's output joins the rotation as "written last"; the buffer it replaces is the next front's target
+    const int w = h->rWrite;
+    h->rWrite = h->rFree;
+    h->rFree = w;
+  }
   FrameCtx& fc = F.fc;
   fc = FrameCtx{};
   fc.width = h->info.width;
@@ -1521,18 +1671,16 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   fc.y1 = y1;
   fc.sc = h->sc;
   fc.P = P;
-  fc.cam = cam_state(cam);
+  fc.cam = ff.cam;
   fc.prevCam = h->havePrev ? h->prevCam : fc.cam;
   fc.G = h->G[h->gCur];
-  fc.Gprev = h->G[h->gCur ^ 1];
+  fc.Gprev = h->G[(h->gCur + 2) % 3];
   fc.frame = h->frame;
-  fc.counters = h->counters;
+  fc.counters = ctr;
   fc.wave = h->wave;
-  fc.wave.brdf_two_step = (F.wave && h->twoStepBrdf && h->sc.em_n_nodes > 0) ? 1u : 0u;
-  // G-buffer rows kept by this handle: the band plus a margin that covers the spatial reach and most reprojections
-  const int margin = banded ? std::max(16, spatial_reach(P)) : 0;
-  fc.gy0 = std::max(0, y0 - margin);
-  fc.gy1 = std::min(H, y1 + margin);
+  fc.wave.deferred_count = reinterpret_cast<uint32_t*>(ctr + 4);
+  fc.gy0 = ff.gy0;
+  fc.gy1 = ff.gy1;
   fc.gpy0 = h->havePrev ? h->prevGy0 : 0;
   fc.gpy1 = h->havePrev ? h->prevGy1 : 0;
 
@@ -1542,58 +1690,17 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     h->nStalls[bslot] = 0;
     RB_CUDA(cudaEventRecord(h->evFrameB[bslot], st));
   }
-  RB_CUDA(cudaMemsetAsync(h->counters, 0, 64, st));
-  if (timed) cudaEventRecord(h->fev[0], st);
   fs_bind(h);
-  // ---- G-buffer ------------------------------------------------------------------------------------
-  fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_GBUF, 0);
-  // primary rays are coherent: the inline kernel (0.87 ms at 1080p / 1M triangles) beats queue + persistent traversal +
-  // resolve (0.84 + 0.28 ms); the split stays available for experiments (RB_WAVE_GBUF=1)
-  if (F.wave && h->waveGbuf && (size_t)(fc.gy1 - fc.gy0) * fc.width <= h->waveRayCap) {
-    fs_reset_queue(h);
-    launch_rows(h, k_gbuffer_stream, fc.gy0, fc.gy1);
-    fs_mark(h, 0, 0);
-    fs_trace(h, TRACE_CLOSEST, 0, RB_PRIMARY_TNEAR);
-    launch_rows(h, k_gbuffer_resolve, fc.gy0, fc.gy1);
-  } else {
-    launch_rows(h, k_gbuffer, fc.gy0, fc.gy1, 128);
-  }
-  fs_mark(h, 0, 0);
-  // ---- initial candidates ----------------------------------------------------------------------------
-  fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_INITIAL, 0);
-  if (F.wave) {
-    if (P.M_Brdf > 0 && h->sc.n_lights > 0) {
-      fs_reset_queue(h);
-      launch_rows(h, k_initial_brdf_stream, y0, y1);
-      fs_mark(h, 1, 0);
-      if (fc.wave.brdf_two_step) {
-        // closest EMITTER along each ray (small BVH); the traversal queues "does anything precede it?" for the few rays
-        // that found one, and the second launch traces those against the full BVH
-        fs_trace(h, TRACE_CLOSEST_EMISSIVE, 1);
-        fs_trace(h, TRACE_ANY_PRECEDES, 1);
-      } else {
-        fs_trace(h, TRACE_CLOSEST, 1);
-      }
-    }
-    // shadow rays of the candidates (visibility pass off) are traced inline by the resolve kernel; with the visibility
-    // pass on, the resolve kernel also queues that pass's ray for the reservoir it has just produced
-    if (P.doVisibilityPass) {
-      fs_reset_queue(h);
-      fc.wave.fuse_vis = 1u;
-      launch_rows(h, k_initial_resolve, y0, y1, 128);
-      fc.wave.fuse_vis = 0u;
-    } else
-      launch_rows(h, k_initial_resolve_inline_shadow, y0, y1);
-  } else {
-    launch_rows(h, k_initial, y0, y1);
-  }
-  fs_mark(h, 1, 0);
   // ---- visibility ---------------------------------------------------------------------------------
   const bool temporal_runs = P.doTemporalReuse && frame_idx > 0 && h->havePrev;
   bool vis_in_temporal = false;
   if (P.doVisibilityPass) {
     if (F.wave) {
-      fs_trace(h, TRACE_ANY, 2);  // the rays were queued by k_initial_resolve
+      WaveBufs vw = h->wave;  // the rays were queued by the front half's k_initial_resolve; results go to the back half's bytes
+      vw.rays = h->visRays[par];
+      vw.count = vis_pair;
+      vw.capacity = (uint32_t)h->visRayCap;
+      fs_trace(h, TRACE_ANY, 2, -1.0f, &vw, st);
       // the result is applied by the temporal stream kernel when there is one, else by the pass's own resolve kernel
       vis_in_temporal = temporal_runs;
       if (!vis_in_temporal) launch_rows(h, k_visibility_resolve, y0, y1);
@@ -1699,12 +1806,17 @@ static int frame_end(RbHandle h, RbTimings* timings) {
   RB_CUDA(cudaGetLastError());
   // memcpy(reservoirsLastFrame, ...) + gBufferLastFrame.setDataFrom(gBuffer) (P/simpleguidx11.cpp:478-481) by rotation
   std::swap(h->rLast, h->rRead);
-  h->gCur ^= 1;
   h->prevCam = fc.cam;
   h->prevGy0 = fc.gy0;
   h->prevGy1 = fc.gy1;
   h->havePrev = true;
   F.open = false;
+  {  // the front half of the frame after next may reuse this frame's buffers once this point is reached
+    const int par = (int)(h->frameSeq & 1u);
+    RB_CUDA(cudaEventRecord(h->evBackDone[par], st));
+    h->backRecorded[par] = true;
+    h->frameSeq++;
+  }
   if (h->comm && h->balance) {
     RB_CUDA(cudaEventRecord(h->evFrameE[h->balFrame % RbContext::kBalRing], st));
     RB_TRY(balance_ship_begin(h));
@@ -1839,7 +1951,7 @@ int rb_readback(RbHandle h, int id, void* dst, size_t bytes) {
   if (!h || !dst) return RB_ERR_INVALID_ARGUMENT;
   RB_CUDA(cudaSetDevice(h->info.device));
   const size_t n = (size_t)h->info.width * h->info.height;
-  const GBufPlanes& G = h->G[h->gCur ^ 1];  // the frame just rendered (rotated to "previous")
+  const GBufPlanes& G = h->G[h->gCur];  // the frame just rendered
   const ResPlanes& R = h->R[h->rLast];
   const void* src = nullptr;
   size_t need = 0;
