@@ -265,6 +265,14 @@ def run_ours(args):
     ms = maxr(ms)
     ms_e2e = maxr(ms_e2e)
     med = {k: float(np.median(v)) for k, v in per.items()}
+    per_rank = None
+    if world > 1:  # every rank's band and per-pass times (un-overlapped timed frames), for the scaling analysis
+        mine = {"rank": rank, "band": list(r.get_band()), "halo_wait_ms": float(np.median(halo_ms)),
+                "stream_ms": [round(float(x), 4) for x in np.median(np.array(stream_ms), axis=0)],
+                "trace_ms": [round(float(x), 4) for x in np.median(np.array(trace_ms), axis=0)],
+                **{k: round(v, 4) for k, v in med.items()}}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     n_closest = sumr(float(np.median(rays["closest"])))
     n_any_w = sumr(float(np.median(rays["any_w"])))
     n_any_t = sumr(float(np.median(rays["any_t"])))
@@ -325,6 +333,7 @@ def run_ours(args):
     if world > 1:
         line["halo_exchange_ms"] = float(np.median(halo_ms))  # rank 0: time its main stream waited for the neighbours' halo rows
         line["config"]["halo_transport"] = r.comm_transport()
+        line["per_rank"] = per_rank
         line["config"]["band_rows_rank0_final"] = list(r.get_band())  # the library balances the bands by measured cost
         line["config"]["balance_settle_frames"] = settle  # untimed frames before the warm-up, for the balancer
     print(json.dumps(line), flush=True)

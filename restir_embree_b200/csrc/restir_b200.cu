@@ -411,6 +411,10 @@ struct RbContext {
   bool backRecorded[2]{};
   uint32_t frameSeq = 0;
   bool overlap = true;  // RB_OVERLAP=0: both halves on `stream`
+  // RB_OVERLAP_DEBUG=1: timestamps of the halves of the first frames, printed by rb_destroy
+  bool ovDebug = false;
+  static constexpr int kOvFrames = 24;
+  cudaEvent_t evOv[kOvFrames][4]{};  // front begin / end, back begin / end
   WaveBufs fwave{};     // front half: BRDF-candidate rays (+ chained "precedes" rays), their hits / occlusion bytes
   RayQ* visRays[2]{};   // visibility rays of frame parity p: queued by the front half, traced by the back half
   size_t fwaveRayCap = 0, fwaveHitCap = 0, visRayCap = 0;
@@ -697,13 +701,15 @@ static int balance_ship_begin(RbContext* h) {
   float cost = 0.0f;
   if (h->balFrame >= 2) {
     RB_CUDA(cudaEventSynchronize(h->evFrameE[(h->balFrame - 2) % RbContext::kBalRing]));
-    // mean over up to four completed frames of this period (same band): single frames are noisy
+    // mean over up to four completed frames of this period (same band): single frames are noisy. A frame's cost is
+    // the time between the ends of two consecutive back halves (front halves overlap the previous frame, so start-to-end
+    // times would count shared time twice) minus what its main stream spent waiting for neighbour bands.
     int used = 0;
-    for (uint32_t j = 2; j <= 5 && j <= h->balFrame; ++j) {
+    for (uint32_t j = 2; j <= 5 && j + 1 <= h->balFrame; ++j) {
       if (j > 2 && (int)j > h->balPeriod - 1) break;
-      const int ps = (int)((h->balFrame - j) % RbContext::kBalRing);
+      const int ps = (int)((h->balFrame - j) % RbContext::kBalRing), pp = (int)((h->balFrame - j - 1) % RbContext::kBalRing);
       float t = 0;
-      RB_CUDA(cudaEventElapsedTime(&t, h->evFrameB[ps], h->evFrameE[ps]));
+      RB_CUDA(cudaEventElapsedTime(&t, h->evFrameE[pp], h->evFrameE[ps]));
       for (int i = 0; i < h->nStalls[ps]; ++i) {
         float st = 0;
         RB_CUDA(cudaEventElapsedTime(&st, h->evStallA[ps][i], h->evStallB[ps][i]));
@@ -1010,6 +1016,10 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
     if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
     if (const char* e = getenv("RB_OVERLAP")) h->overlap = atoi(e) != 0;
+    if (const char* e = getenv("RB_OVERLAP_DEBUG")) h->ovDebug = atoi(e) != 0;
+    if (h->ovDebug)
+      for (auto& f : h->evOv)
+        for (auto& ev : f) RB_CUDA(cudaEventCreate(&ev));
     if (const char* e = getenv("RB_TWO_STEP_BRDF")) h->twoStepBrdf = atoi(e) != 0;
     // arithmetic self-check: implicit contraction must be off
     float* d = nullptr;
@@ -1035,6 +1045,16 @@ void rb_destroy(RbHandle h) {
   if (!h) return;
   cudaSetDevice(h->info.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->ovDebug) {
+    const int n = (int)std::min<uint32_t>(h->frameSeq, RbContext::kOvFrames);
+    for (int f = 1; f < n; ++f) {
+      float t[4];
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], h->evOv[1][0], h->evOv[f][k]);
+      fprintf(stderr, "[rb overlap] frame %2d: front %8.3f .. %8.3f   back issued %8.3f, ends %8.3f ms\n", f, t[0], t[1], t[2], t[3]);
+    }
+    for (auto& f : h->evOv)
+      for (auto& ev : f) cudaEventDestroy(ev);
+  }
   free_list(h->allocs);
   free_list(h->sceneAllocs);
   if (h->evCreated) {
@@ -1588,6 +1608,8 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   // of the frame before last; its ray queues by the previous front half
   if (h->backRecorded[par]) RB_CUDA(cudaStreamWaitEvent(sf, h->evBackDone[par], 0));
   if (h->frameSeq > 0) RB_CUDA(cudaStreamWaitEvent(sf, h->evFrontDone, 0));
+  const bool ovd = h->ovDebug && h->frameSeq < (uint32_t)RbContext::kOvFrames;
+  if (ovd) cudaEventRecord(h->evOv[h->frameSeq][0], sf);
   unsigned long long* ctr = h->counters2 + 8 * par;
   h->counters = ctr;
   RB_CUDA(cudaMemsetAsync(ctr, 0, 64, sf));
@@ -1652,10 +1674,12 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     launch_rows(h, k_initial, y0, y1, kTileW * kTileH, &ff, sf);
   }
   fs_mark(h, 1, 0);
+  if (ovd) cudaEventRecord(h->evOv[h->frameSeq][1], sf);
   RB_CUDA(cudaEventRecord(h->evFrontDone, sf));
   RB_CUDA(cudaGetLastError());
 
   // ---- BACK half: needs the front half and the previous frame -------------------------------------------------------
+  if (ovd) cudaEventRecord(h->evOv[h->frameSeq][2], st);  // (before the wait for the front half: end of the previous back half)
   RB_CUDA(cudaStreamWaitEvent(st, h->evFrontDone, 0));
   h->gCur = gNew;
   {  // the front half's output joins the rotation as "written last"; the buffer it replaces is the next front's target
@@ -1813,6 +1837,7 @@ static int frame_end(RbHandle h, RbTimings* timings) {
   F.open = false;
   {  // the front half of the frame after next may reuse this frame's buffers once this point is reached
     const int par = (int)(h->frameSeq & 1u);
+    if (h->ovDebug && h->frameSeq < (uint32_t)RbContext::kOvFrames) cudaEventRecord(h->evOv[h->frameSeq][3], st);
     RB_CUDA(cudaEventRecord(h->evBackDone[par], st));
     h->backRecorded[par] = true;
     h->frameSeq++;
