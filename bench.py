@@ -28,6 +28,11 @@ WORKLOAD = "configs[1]: synthetic 1M-triangle room, 10k emissive triangles, 1920
            "visibility pass, temporal + 1 spatial pass k=5 r=30, alias light sampler, orbit camera 0.5 deg/frame"
 # algorithmic bytes per pixel per pass (reference record sizes R=48, G=69)
 PASS_BYTES = dict(gbuffer=69, initial=117, visibility=64, temporal=306, spatial=465, shade=129)
+# The wavefront schedule folds the visibility pass into its neighbours (its ray is queued by the initial-pass resolve
+# kernel from registers, its result applied by the temporal stream kernel: + the 4-byte W write) and the shading into
+# the last spatial pass's resolve kernel (+ G 69 + rgb 12; the reservoir is not read again): compulsory bytes of the
+# fused kernels, same record sizes.
+FUSED_BYTES = dict(gbuffer=69, initial=117, visibility=0, temporal=306 + 4, spatial=465 + 69 + 12, shade=0)
 
 
 def peaks():
@@ -39,32 +44,89 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md recipe). Sampled in-process through NVML
+    (a spawned `nvidia-smi -lms` initialises NVML inside the timed region and its queries hold the driver lock long
+    enough to stall the kernel launches of every rank on the node: at N=8 that halved the measured frame rate);
+    nvidia-smi is the fallback and is then started well before the timed region."""
 
     def __init__(self, device=0):
         self.samples, self.proc, self.device = [], None, device
+        self.nvml, self.handle, self.thread, self.on = None, None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
-    def start(self):
+    def prepare(self):
+        """fallback only: spawn nvidia-smi early so that its start-up is over before the timed region"""
+        if self.nvml is not None or self.proc is not None:
+            return
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
             "clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            if self.on:
+                self.samples.append(line.strip())
+
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while self.on:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, [k for k, b in bits.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        self.on = True
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+        else:
+            self.prepare()
 
     def stop(self):
+        self.on = False
+        if self.nvml is not None:
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            if not self.samples:  # region shorter than one polling interval
+                self.on = True
+                t = threading.Thread(target=self._poll_nvml, daemon=True)
+                t.start()
+                time.sleep(0.03)
+                self.on = False
+                t.join(timeout=1.0)
+            sm = [s[0] for s in self.samples]
+            reasons = sorted({r for s in self.samples for r in s[1]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -79,7 +141,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def bench_params():
@@ -179,6 +241,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if rank == 0:
+        sampler.prepare()
     frame = 0
     # N > 1: the library balances the band heights by measured cost (<= 15 rows per period of 8 frames): let it settle first
     # (untimed; until the bands have stopped moving for three balance periods, at most 192 frames)
@@ -202,7 +267,6 @@ def run_ours(args):
         r.render_frame_device(camera_at(scene, frame), frame)
         frame += 1
     r.synchronize()
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
@@ -290,8 +354,9 @@ def run_ours(args):
     # streaming (reservoir) kernels: the stream + resolve halves of a pass; the roofline entry is the reservoir pass
     # with the largest streaming time (SURVEY 8d algorithmic bytes / CUDA-event time of its streaming kernels)
     stream_by_pass = {n: float(sm[i]) if wave else med[n] for i, n in enumerate(names)}
-    dom = max(("visibility", "temporal", "spatial", "shade"), key=lambda k: stream_by_pass[k])
-    achieved = PASS_BYTES[dom] * band_px / (stream_by_pass[dom] * 1e-3) / 1e9
+    pass_bytes = FUSED_BYTES if wave else PASS_BYTES
+    dom = max([k for k in ("visibility", "temporal", "spatial", "shade") if pass_bytes[k] > 0], key=lambda k: stream_by_pass[k])
+    achieved = pass_bytes[dom] * band_px / (stream_by_pass[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if wave and os.path.exists(tpath):  # DRAM bytes per launch of the pass's two streaming kernels, from the committed ncu capture
@@ -302,17 +367,18 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": ("k_%s_stream+k_%s_resolve" % (dom, dom)) if wave else "k_" + dom,
             "achieved": achieved, "peak": hbm, "unit": "GB/s",
             "frac": achieved / hbm, "traffic": traffic, "traffic_unit": "bytes per frame (both kernels of the pass)",
-            "algorithmic_bytes": PASS_BYTES[dom] * band_px, "peak_source": hbm_src,
-            "algorithmic_bytes_per_px": PASS_BYTES[dom],
-            "note": "reservoir pass with the largest streaming-kernel time; traversal runs in separate persistent kernels "
-                    "(see traversal{}), which are latency/issue-bound SM work, not a bandwidth roofline" if wave else
+            "algorithmic_bytes": pass_bytes[dom] * band_px, "peak_source": hbm_src,
+            "algorithmic_bytes_per_px": pass_bytes[dom],
+            "note": "reservoir pass with the largest streaming-kernel time (spatial: stream kernel + resolve kernel, which also "
+                    "shades); traversal runs in separate persistent kernels (see traversal{}), which are latency/issue-bound "
+                    "SM work, not a bandwidth roofline" if wave else
                     "inline mode: pass kernels trace their shadow rays themselves",
             "share_of_frame": stream_by_pass[dom] / max(med["total"], 1e-9),
             "per_pass_ms": med,
             "stream_ms": {n: float(sm[i]) for i, n in enumerate(names)},
             "trace_ms": {n: float(tm[i]) for i, n in enumerate(names)},
-            "stream_gbs": {n: PASS_BYTES[n] * band_px / (stream_by_pass[n] * 1e-3) / 1e9 for n in names
-                           if stream_by_pass[n] > 0}}
+            "stream_gbs": {n: pass_bytes[n] * band_px / (stream_by_pass[n] * 1e-3) / 1e9 for n in names
+                           if stream_by_pass[n] > 0 and pass_bytes[n] > 0}}
     frame_s = med["total"] * 1e-3
     trav = {"trace_kernel_ms_per_frame": float(tm.sum()), "trace_share_of_frame": float(tm.sum()) / max(med["total"], 1e-9),
             "mrays_s_as_written": (n_closest + n_any_w) / frame_s / 1e6 / max(world, 1) * world,
