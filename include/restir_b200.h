@@ -238,6 +238,22 @@ int rb_render_frame(RbHandle h, const RbCamera* cam, uint32_t frame_idx,
 int rb_render_frame_device(RbHandle h, const RbCamera* cam, uint32_t frame_idx,
                            float* frame_rgb_dev, RbTimings* timings);
 
+/* ---- Ground truth next to the path ---------------------------------------------------------
+ * One frame of the reference's one-sample MIS direct-lighting estimator — NEEPathIntegrator with "Calculate DI" on and
+ * "Calculate GI" off around DirectMISIntegrator (P/NEEPathIntegrator.cpp:76-131, P/DirectMISIntegrator.cpp:18-144), the
+ * integrator behind the author's reference images (S/mis_reference*.png.txt): primary ray (the G-buffer kernel), then a
+ * BRDF sample (Material::evaluateLightingGI + closest-hit ray) and a light sample (area pick + shadow ray), combined
+ * with the power heuristic; Integrator::sanitize on the result. Unbiased, so its running mean (rb_accumulate_display)
+ * is what ReSTIR's bias is measured against. `techniques`: bit 0 = "Sample BRDF", bit 1 = "Sample Light Sources"
+ * (P/DirectMISIntegrator.cpp:32-36; the reference default is both = 3). Uses RbParams' offsets, bgColor and
+ * lightSampler; does not touch the ReSTIR state (reservoirs, previous G-buffer), writes frame_data (band rows) and,
+ * when frame_rgb_out (host, w*h*3) is given, copies the band rows out and waits. Counter RNG pass id 4, slots:
+ * 0 lobe select, 1-2 BRDF direction, 4 light pick, 5-6 point on the emitter. Scenes with RB_MAT_DIELECTRIC
+ * materials are refused (RB_ERR_UNSUPPORTED): their evaluateLightingGI refracts. */
+#define RB_MIS_SAMPLE_BRDF 1u
+#define RB_MIS_SAMPLE_LIGHTS 2u
+int rb_render_mis_frame(RbHandle h, const RbCamera* cam, uint32_t frame_idx, uint32_t techniques, float* frame_rgb_out);
+
 int rb_readback(RbHandle h, int buffer_id /*RbBufferId*/, void* dst, size_t bytes);
 int rb_synchronize(RbHandle h);
 

@@ -14,6 +14,7 @@
 #include "stdafx.h"
 
 #include "ReSTIRIntegrator.h"
+#include "DirectMISIntegrator.h"
 #include "Intersection.h"
 #include "Sampling.h"
 #include "Scene.h"
@@ -278,6 +279,41 @@ void ref_produce_restir(void* h, float* rgb_out) {
          (size_t)width_ * height_ * sizeof(Reservoir));
   SimpleGuiDX11::gBufferLastFrame.setDataFrom(gBuffer);
   c->frameCtr++;
+  if (rgb_out) memcpy(rgb_out, c->frame.data(), c->frame.size() * sizeof(glm::vec3));
+}
+
+// N2: the reference's ground-truth estimator. Raytracer::get_pixel (P/raytracer.cpp:40-46) for every pixel
+// in the serial _DEBUG order; NEEPathIntegrator::integrateImpl2 at bounce 0 with "Calculate DI" on and "Calculate GI"
+// off (P/NEEPathIntegrator.cpp:76-131) is replayed here (its class drags in every other integrator), the estimator
+// itself is the reference's own DirectMISIntegrator::calculateDirectLighting (P/DirectMISIntegrator.cpp, compiled in
+// place) with its defaults (sample the BRDF and the light sources).
+void ref_produce_mis(void* h, float* rgb_out) {
+  RefCtx* c = (RefCtx*)h;
+  const Scene& scene = *c->scene;
+  Camera& camera_ = *c->camera;
+  const RenderParams& renderParams = ReSTIRIntegrator::renderParams;  // the offsets / bgColor ref_set_params stored
+  static DirectMISIntegrator misIntegrator;
+  for (int y = 0; y < c->h; ++y)
+    for (int x = 0; x < c->w; ++x) {
+      Ray ray{camera_.GenerateRay(glm::vec2{x, y})};
+      glm::vec3 radiance{0};
+      auto intResult = Intersection::intersectEmbree(scene, ray);
+      const HitInfo& hitInfo = intResult.hitInfo;
+      if (hitInfo.didHit) {
+        if (intResult.material->isEmitter()) {
+          radiance = intResult.material->emission;  // lastVertexType == CAMERA_VERTEX
+        } else {
+          glm::vec3 L_i_direct = misIntegrator.calculateDirectLighting(scene, ray, intResult, renderParams, {x, y});
+          Integrator::sanitize(L_i_direct, false);
+          glm::vec3 L_i_indirect{0};
+          Integrator::sanitize(L_i_indirect, false);
+          radiance = L_i_indirect + L_i_direct;
+        }
+      } else {
+        radiance = renderParams.bgColor;  // useSkybox is off in ABI v1
+      }
+      c->frame[(size_t)y * c->w + x] = radiance;
+    }
   if (rgb_out) memcpy(rgb_out, c->frame.data(), c->frame.size() * sizeof(glm::vec3));
 }
 

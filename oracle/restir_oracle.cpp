@@ -110,7 +110,7 @@ struct Math {
 // ----------------------------------------------------------------------------
 // RNG seam
 // ----------------------------------------------------------------------------
-enum Pass { PASS_GBUF = 0, PASS_INITIAL = 1, PASS_TEMPORAL = 2, PASS_SPATIAL = 3 };
+enum Pass { PASS_GBUF = 0, PASS_INITIAL = 1, PASS_TEMPORAL = 2, PASS_SPATIAL = 3, PASS_MIS = 4 };
 
 static inline uint32_t fmix32(uint32_t h) {  // murmur3 finaliser
   h ^= h >> 16;
@@ -1073,6 +1073,162 @@ struct Oracle {
     o[2] = pixel.z;
   }
 
+  // ---- N2: the ground-truth estimator ------------------------------------------------------------------
+  // NEEPathIntegrator::integrateImpl2 with calcDI, without calcGI (P/NEEPathIntegrator.cpp:76-131) around
+  // DirectMISIntegrator::calculateDirectLighting (P/DirectMISIntegrator.cpp:18-144). The material virtuals
+  // (MaterialPhong::evaluateLightingGI / evaluateBRDF / getPdfForSample, P/MaterialPhong.cpp:18-119; MaterialLambert's,
+  // P/MaterialLambert.cpp:10-31) take the primary ray's direction. Draw order as in the reference: lobe select, two
+  // direction draws, light pick, two triangle draws (counter slots 0, 1-2, 4, 5-6).
+  static float powerHeuristic(float pdf, float pdfOther) {  // :10-15
+    const float pdf_sqr = pdf * pdf;
+    const float pdfOther_sqr = pdfOther * pdfOther;
+    return pdf_sqr / (pdfOther_sqr + pdf_sqr);
+  }
+  static V3 vdiv(const V3& v, float s) { return {v.x / s, v.y / s, v.z / s}; }  // glm vec3 / scalar: true divisions
+  V3 phongBRDF_ray(const GBufferElement& e, const V3& rayDir, const V3& omega_i) const {  // MaterialPhong::evaluateBRDF, :69-92
+    V3 f_r = e.diffuseColor * kOneOverPi;
+    float nDotV = dot(-rayDir, e.worldSpaceNormal);
+    float i_m = 1.0f / calc_I_M(nDotV, e.shininess);
+    const V3 omega_r = normalize(reflect(rayDir, e.worldSpaceNormal));
+    f_r = f_r + e.specularColor * i_m * math.pow(gmax(dot(omega_i, omega_r), 0.0f), e.shininess);
+    return f_r;
+  }
+  float phongPdf_ray(const GBufferElement& e, const V3& rayDir, const V3& omega_i) const {  // ::getPdfForSample, :94-119
+    float maxDiffuse = maxComponent(e.diffuseColor);
+    float maxSpecular = maxComponent(e.specularColor);
+    float pdfFactor = maxDiffuse / (maxDiffuse + maxSpecular);
+    float pdf = cosw_pdf(e.worldSpaceNormal, omega_i) * pdfFactor;
+    const V3 omega_r = normalize(reflect(rayDir, e.worldSpaceNormal));
+    pdf += lobe_pdf(omega_i, omega_r, e.shininess) * (1.0f - pdfFactor);
+    return pdf;
+  }
+  struct GIPayload {
+    V3 omega_i, f_r;
+    float pdf;
+  };
+  GIPayload evaluateLightingGI(const GBufferElement& e, const V3& rayDir, Rng& rng) const {
+    if (e.materialType == RB_MAT_LAMBERT) {  // P/MaterialLambert.cpp:10-18
+      V3 omega_i = cosw_sample(e.worldSpaceNormal, rng, 1, 2);
+      float pdf = cosw_pdf(e.worldSpaceNormal, omega_i);
+      return {omega_i, vdiv(e.diffuseColor, kPi), pdf};
+    }
+    // P/MaterialPhong.cpp:18-67
+    float maxDiffuse = maxComponent(e.diffuseColor);
+    float maxSpecular = maxComponent(e.specularColor);
+    float r0 = rng.value(0, 0.0f, maxDiffuse + maxSpecular);
+    float pdfFactor = maxDiffuse / (maxDiffuse + maxSpecular);
+    V3 omega_i, f_r;
+    const V3 omega_r = normalize(reflect(rayDir, e.worldSpaceNormal));
+    if (r0 < maxDiffuse) {
+      omega_i = cosw_sample(e.worldSpaceNormal, rng, 1, 2);
+      f_r = e.diffuseColor * kOneOverPi;
+    } else {
+      omega_i = lobe_sample(omega_r, e.shininess, rng, 1, 2);
+      float nDotV = dot(-rayDir, e.worldSpaceNormal);
+      float i_m = 1.0f / calc_I_M(nDotV, e.shininess);
+      f_r = e.specularColor * i_m * math.pow(gmax(dot(omega_i, omega_r), 0.0f), e.shininess);
+    }
+    float pdfDiffuse = cosw_pdf(e.worldSpaceNormal, omega_i) * pdfFactor;
+    float pdfSpecular = lobe_pdf(omega_i, omega_r, e.shininess) * (1.0f - pdfFactor);
+    float pdf = pdfDiffuse + pdfSpecular;
+    if (dot(e.worldSpaceNormal, omega_i) < 0) return {omega_i, v3(0), pdf};
+    return {omega_i, f_r, pdf};
+  }
+  V3 misEvaluateBRDFSample(const GBufferElement& e, const V3& rayDir, Rng& rng) {  // P/DirectMISIntegrator.cpp:92-144
+    V3 L_direct = v3(0);
+    GIPayload payloadGI = evaluateLightingGI(e, rayDir, rng);
+    V3 org = e.worldSpacePos + P.normalOffset * e.worldSpaceNormal;
+    HitInfo hi = intersect(org, payloadGI.omega_i, FLT_MIN + P.tnearOffset, FLT_MAX);
+    if (hi.didHit) {
+      const RbMaterial& m = scene.mats[scene.tris[hi.tri].material];
+      if (m.emission[0] + m.emission[1] + m.emission[2] > 0) {  // Material::isEmissive, P/material.h:135-137
+        V3 L_i{m.emission[0], m.emission[1], m.emission[2]};
+        V3 lightDir = hi.hitPoint - e.worldSpacePos;
+        float r_sqr = dot(lightDir, lightDir);
+        lightDir = normalize(lightDir);
+        float cosThetaI = gmax(dot(lightDir, e.worldSpaceNormal), 0.0f);
+        float cosThetaY = gmax(dot(-lightDir, hi.normal), 0.0f);
+        float areaMeasureFactor = cosThetaY / r_sqr;
+        const Tri& tri = scene.tris[scene.emissive[hi.hitTriId]];
+        float brdfPdf = payloadGI.pdf;
+        float pdfAsIfLight = getPDFForTriangle(tri);
+        float brdfPdfAreaMeasure = brdfPdf * areaMeasureFactor;
+        float misWeight = powerHeuristic(brdfPdfAreaMeasure, pdfAsIfLight);
+        L_direct = vdiv(misWeight * L_i * payloadGI.f_r * cosThetaI, brdfPdf);
+      }
+    }
+    return L_direct;
+  }
+  V3 misEvaluateLightSample(const GBufferElement& e, const V3& rayDir, Rng& rng) {  // :38-90
+    V3 L_direct = v3(0);
+    if (!scene.lightsValid()) return L_direct;
+    TriPick pick = pickTriangle(rng, 4);
+    const Tri& T = scene.tris[scene.emissive[pick.emissiveIdx]];
+    float r1 = rng.value(5, 0, 1);  // Sampling::sampleTriangle, P/Sampling.cpp:63-76
+    float r2 = rng.value(6, 0, 1);
+    float bx = 1.0f - std::sqrt(r1);
+    float by = std::sqrt(r1) * (1.0f - r2);
+    float bz = std::sqrt(r1) * r2;
+    V3 samplePoint = T.p0 * bx + T.p1 * by + T.p2 * bz;
+    V3 normal = normalize(T.n0 * bx + T.n1 * by + T.n2 * bz);
+    float lightPdf = pick.pdf * (1.0f / T.area);
+    if (lightPdf == 0) return v3(0);
+    V3 lightDir = samplePoint - e.worldSpacePos;
+    float r_sqr = dot(lightDir, lightDir);
+    lightDir = normalize(lightDir);
+    if (r_sqr == 0) return v3(0);
+    float cosThetaI = gmax(dot(lightDir, e.worldSpaceNormal), 0.0f);
+    float cosThetaY = gmax(dot(-lightDir, normal), 0.0f);
+    float areaMeasureFactor = cosThetaY / r_sqr;
+    if (cosThetaI > 0 && cosThetaY > 0 && !testOcclusion(e.worldSpacePos, samplePoint)) {
+      const bool lambert = e.materialType == RB_MAT_LAMBERT;
+      float pdfAsIfBrdf = lambert ? cosw_pdf(e.worldSpaceNormal, lightDir) : phongPdf_ray(e, rayDir, lightDir);
+      float pdfAsIfBrdfAreaMeasure = pdfAsIfBrdf * areaMeasureFactor;
+      const RbMaterial& m = scene.mats[T.material];
+      V3 L_i{m.emission[0], m.emission[1], m.emission[2]};
+      float misWeight = powerHeuristic(lightPdf, pdfAsIfBrdfAreaMeasure);
+      if (misWeight > 0.0f) {
+        float G = cosThetaI * cosThetaY / r_sqr;
+        V3 f_r = lambert ? e.diffuseColor * kOneOverPi : phongBRDF_ray(e, rayDir, lightDir);
+        L_direct = vdiv(misWeight * L_i * f_r * G, lightPdf);
+      }
+    }
+    return L_direct;
+  }
+  static void sanitize(V3& l) {  // Integrator::sanitize, P/Integrator.cpp:6-23
+    if (std::isnan(l.x) || std::isnan(l.y) || std::isnan(l.z)) l = v3(0);
+    if (l.x < 0 || l.y < 0 || l.z < 0) l = v3(0);
+  }
+  // Raytracer::get_pixel (P/raytracer.cpp:40-46) for every pixel, serially in the legacy-RNG mode
+  void produceMis(const RbCamera& cam, uint32_t frame_idx, uint32_t techniques) {
+    frameIdx = frame_idx;
+    memcpy(gBuffer.viewMat, cam.viewMat, sizeof(float) * 16);
+    memcpy(gBuffer.invViewMat, cam.invViewMat, sizeof(float) * 16);
+    gBuffer.cameraPosWS = {cam.pos[0], cam.pos[1], cam.pos[2]};
+    gBuffer.focalLength = cam.focal_px;
+    forPixels([&](int x, int y) {
+      gBufferFillPass(x, y);  // Camera::GenerateRay (its two discarded draws in legacy mode) + intersectEmbree
+      const GBufferElement& e = gBuffer.px[(size_t)y * width + x];
+      V3 out;
+      if (e.geomID == 0xFFFFFFFFu || emissive(e.emission)) {
+        out = e.emission;  // background colour / emitter seen from the camera vertex
+      } else {
+        Rng crng = rngFor(PASS_GBUF, 0, x, y);
+        crng.mode = 0;  // (direction only: the draws were consumed by gBufferFillPass)
+        V3 org, dir;
+        generateRay(x, y, &org, &dir, crng);
+        Rng rng = rngFor(PASS_MIS, 0, x, y);
+        V3 L_direct = v3(0);
+        if (techniques & 1u) L_direct = L_direct + misEvaluateBRDFSample(e, dir, rng);
+        if (techniques & 2u) L_direct = L_direct + misEvaluateLightSample(e, dir, rng);
+        sanitize(L_direct);
+        out = v3(0) + L_direct;
+      }
+      float* o = &frame[3 * ((size_t)y * width + x)];
+      o[0] = out.x, o[1] = out.y, o[2] = out.z;
+    });
+  }
+
   template <class F>
   void forPixels(F&& f) {
     if (rng_mode == 1) {  // _DEBUG build: serial, y outer, x inner
@@ -1244,6 +1400,14 @@ int orc_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rg
   Oracle* o = (Oracle*)h;
   if (!o->have_scene) return -3;
   o->produceRestir(*cam, frame_idx, pass_seconds);
+  if (rgb_out) memcpy(rgb_out, o->frame.data(), o->frame.size() * sizeof(float));
+  return 0;
+}
+
+int orc_render_mis_frame(void* h, const RbCamera* cam, uint32_t frame_idx, uint32_t techniques, float* rgb_out) {
+  Oracle* o = (Oracle*)h;
+  if (!o->have_scene) return -3;
+  o->produceMis(*cam, frame_idx, techniques);
   if (rgb_out) memcpy(rgb_out, o->frame.data(), o->frame.size() * sizeof(float));
   return 0;
 }

@@ -106,7 +106,7 @@ RB_HD int imax(int a, int b) { return a > b ? a : b; }
 #define RB_NEG_FLT_MAX (-FLT_MAX)
 
 // ---- counter RNG (SURVEY §8c seam 2; same construction as the oracle's) ---------
-enum Pass : uint32_t { PASS_GBUF = 0, PASS_INITIAL = 1, PASS_TEMPORAL = 2, PASS_SPATIAL = 3 };
+enum Pass : uint32_t { PASS_GBUF = 0, PASS_INITIAL = 1, PASS_TEMPORAL = 2, PASS_SPATIAL = 3, PASS_MIS = 4 };
 
 RB_HD uint32_t fmix32(uint32_t h) {
   h ^= h >> 16;

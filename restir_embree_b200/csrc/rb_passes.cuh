@@ -69,6 +69,7 @@ struct FrameCtx {
   int gy0, gy1, gpy0, gpy1;
   unsigned long long* counters;  // [0] closest, [1] any-hit as written, [2] any-hit traced
   WaveBufs wave;
+  uint32_t mis_flags;  // mis_direct_pixel: bit 0 = sample the BRDF, bit 1 = sample the light sources
 };
 
 struct Cnt {
@@ -1236,6 +1237,156 @@ template <class Vis>
 RB_HD void shade_pixel(const FrameCtx& fc, int x, int y, const Vis&, Cnt& cnt) {
   const size_t pi = (size_t)y * fc.width + x;
   shade_store(fc, pi, load_reservoir(fc.Rread, pi), cnt);
+}
+
+// =====================================================================================
+// Ground truth next to the path: one-sample MIS direct lighting, the estimator the reference's own
+// reference images were made with — NEEPathIntegrator::integrateImpl2 with calcDI, without calcGI
+// (P/NEEPathIntegrator.cpp:76-131) around DirectMISIntegrator::calculateDirectLighting
+// (P/DirectMISIntegrator.cpp:18-144): a BRDF sample (Material::evaluateLightingGI, closest-hit ray, power
+// heuristic against the area pdf) plus a light sample (TriangleCDF / alias pick, Sampling::sampleTriangle, shadow ray,
+// power heuristic against Material::getPdfForSample). The pixel's primary hit is read from the G-buffer (same
+// Intersection::intersectEmbree result); the material virtuals take the PRIMARY RAY direction (ray.getDir()), not the
+// camera-to-hit direction the ReSTIR statics use, so omega_r and 1/I_M are formed from it here.
+// Draw order = slot map: 0 lobe select (Phong only), 1-2 BRDF direction, 4 light pick, 5-6 point on the triangle.
+// Dielectric materials refract in evaluateLightingGI and are not covered (rb_render_mis_frame refuses such scenes).
+// =====================================================================================
+RB_HD float power_heuristic(float pdf, float pdfOther) {  // DirectMISIntegrator::powerHeuristic, :10-15
+  const float pdf_sqr = pdf * pdf;
+  const float pdfOther_sqr = pdfOther * pdfOther;
+  return pdf_sqr / (pdfOther_sqr + pdf_sqr);
+}
+template <class Vis>
+RB_HD void mis_direct_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
+  const size_t pi = (size_t)y * fc.width + x;
+  const RbParams& P = fc.P;
+  float* o = fc.frame + 3 * pi;
+  const GElem g = load_gelem(fc.G, pi);
+  const bool miss = fc.G.hit_ids[pi].x == 0xFFFFFFFFu;
+  if (miss || emissive3(g.emission)) {  // background colour (:130) / Material::isEmitter at the camera vertex (:93-97)
+    const V3 e = xyz(ld4(fc.G.emission + pi));
+    o[0] = e.x, o[1] = e.y, o[2] = e.z;
+    return;
+  }
+  V3 rdir;
+  primary_ray(fc.cam, fc.width, fc.height, x, y, &rdir);
+  const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
+  const bool lambert = g.matType == RB_MAT_LAMBERT;
+  const V3 n = g.normal;
+  const V3 omega_r = normalize(reflect(rdir, n));
+  const float maxDiffuse = max_component(g.diffuse), maxSpecular = max_component(g.specular);
+  const float pdfFactor = maxDiffuse / (maxDiffuse + maxSpecular);
+  // 1 / calc_I_M(dot(-ray.getDir(), n), shininess): MaterialPhong::evaluateLightingGI :49-50 and ::evaluateBRDF :84-85
+  // spell the same expression; it is evaluated at most once here (and only where one of them would)
+  float i_m = 0.0f;
+  bool have_im = false;
+  V3 L_direct = v3(0);
+
+  if (fc.mis_flags & RB_MIS_SAMPLE_BRDF) {  // DirectMISIntegrator::evaluateBRDFSample, :92-144
+    const float r1 = rng_value(key, 1, 0, 1), r2 = rng_value(key, 2, 0, 1);
+    V3 wi, f_r;
+    float pdf;
+    if (lambert) {  // MaterialLambert::evaluateLightingGI, P/MaterialLambert.cpp:10-18
+      wi = cosw_sample(n, r1, r2);
+      pdf = cosw_pdf(n, wi);
+      f_r = v3(g.diffuse.x / RB_PI, g.diffuse.y / RB_PI, g.diffuse.z / RB_PI);
+    } else {  // MaterialPhong::evaluateLightingGI, P/MaterialPhong.cpp:18-67
+      const float r0 = rng_value(key, 0, 0.0f, maxDiffuse + maxSpecular);
+      if (r0 < maxDiffuse) {
+        wi = cosw_sample(n, r1, r2);
+        f_r = g.diffuse * RB_ONE_OVER_PI;
+      } else {
+        wi = lobe_sample(omega_r, g.shininess, r1, r2);
+        i_m = frcp_(calc_I_M(dot(-rdir, n), g.shininess));
+        have_im = true;
+        f_r = g.specular * i_m * dm::powf_(gmax(dot(wi, omega_r), 0.0f), g.shininess);
+      }
+      const float pdfDiffuse = cosw_pdf(n, wi) * pdfFactor;
+      const float pdfSpecular = ((g.shininess + 1.0f) * RB_ONE_OVER_TWO_PI * dm::powf_(gmax(0.0f, dot(wi, omega_r)), g.shininess)) *
+                                (1.0f - pdfFactor);
+      pdf = pdfDiffuse + pdfSpecular;
+      if (dot(n, wi) < 0) f_r = v3(0);
+    }
+    const V3 org = g.pos + P.normalOffset * n;
+    cnt.closest++;
+    const SurfaceHit h = vis.closest(0, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
+    if (h.didHit) {
+      const V3 Le = xyz(ldg4(fc.sc.mat + 3 * (size_t)h.material + 2));
+      if (Le.x + Le.y + Le.z > 0) {  // Material::isEmissive, P/material.h:135-137
+        V3 lightDir = h.hitPoint - g.pos;
+        const float r_sqr = dot(lightDir, lightDir);
+        lightDir = normalize(lightDir);
+        const float cosThetaI = gmax(dot(lightDir, n), 0.0f);
+        const float cosThetaY = gmax(dot(-lightDir, h.normal), 0.0f);
+        const float areaMeasureFactor = cosThetaY / r_sqr;
+        // TriangleCDF::getPDFForTriangle(*tris[hitTriId]), P/TriangleCDF.h:25-31 (hitTriId is 0 for a triangle that is
+        // not in the emissive list, P/Intersection.h:103-106)
+        const F4 l0 = ldg4(fc.sc.light + 6 * (size_t)(h.emissiveId >= 0 ? h.emissiveId : 0));
+        float pdfAsIfLight = l0.w / fc.sc.total_area;
+        pdfAsIfLight *= frcp_(l0.w);
+        const float brdfPdfAreaMeasure = pdf * areaMeasureFactor;
+        const float misWeight = power_heuristic(brdfPdfAreaMeasure, pdfAsIfLight);
+        const V3 t = (Le * misWeight) * f_r * cosThetaI;
+        L_direct = L_direct + v3(t.x / pdf, t.y / pdf, t.z / pdf);
+      }
+    }
+  }
+  if ((fc.mis_flags & RB_MIS_SAMPLE_LIGHTS) && fc.sc.n_lights > 0) {  // ::evaluateLightSample, :38-90
+    const LightPick pick = pick_light(fc.sc, P.lightSampler, key, 4u);
+    const F4* Lp = fc.sc.light + 6 * (size_t)pick.idx;
+    const F4 l0 = ldg4(Lp), l1 = ldg4(Lp + 1), l2 = ldg4(Lp + 2), l3 = ldg4(Lp + 3), l4 = ldg4(Lp + 4), l5 = ldg4(Lp + 5);
+    const float pick_pdf = P.lightSampler == RB_LS_ALIAS ? l1.w : pick.pdf;
+    const float r1 = rng_value(key, 5, 0, 1), r2 = rng_value(key, 6, 0, 1);
+    const float sq = sqrtf_(r1);
+    const float bx = 1.0f - sq, by = sq * (1.0f - r2), bz = sq * r2;
+    const V3 samplePoint = xyz(l0) * bx + xyz(l1) * by + xyz(l2) * bz;
+    const V3 triNormal = normalize(xyz(l3) * bx + xyz(l4) * by + xyz(l5) * bz);
+    const float lightPdf = pick_pdf * l2.w;
+    V3 lightDir = samplePoint - g.pos;
+    const float r_sqr = dot(lightDir, lightDir);
+    lightDir = normalize(lightDir);
+    if (lightPdf != 0.0f && r_sqr != 0.0f) {
+      const float cosThetaI = gmax(dot(lightDir, n), 0.0f);
+      const float cosThetaY = gmax(dot(-lightDir, triNormal), 0.0f);
+      const float areaMeasureFactor = cosThetaY / r_sqr;
+      bool lit = cosThetaI > 0 && cosThetaY > 0;
+      if (lit) {
+        cnt.anyW++;
+        cnt.anyT++;
+        lit = vis.visible(1, g.pos, samplePoint);
+      }
+      if (lit) {
+        float pdfAsIfBrdf = cosw_pdf(n, lightDir);  // Material::getPdfForSample
+        float lobe = 0.0f;
+        if (!lambert) {
+          lobe = dm::powf_(gmax(0.0f, dot(lightDir, omega_r)), g.shininess);
+          pdfAsIfBrdf = pdfAsIfBrdf * pdfFactor;
+          pdfAsIfBrdf += ((g.shininess + 1.0f) * RB_ONE_OVER_TWO_PI * lobe) * (1.0f - pdfFactor);
+        }
+        const float pdfAsIfBrdfAreaMeasure = pdfAsIfBrdf * areaMeasureFactor;
+        const V3 L_i = v3(l3.w, l4.w, l5.w);
+        const float misWeight = power_heuristic(lightPdf, pdfAsIfBrdfAreaMeasure);
+        if (misWeight > 0.0f) {
+          const float G = cosThetaI * cosThetaY / r_sqr;
+          V3 f_r = g.diffuse * RB_ONE_OVER_PI;  // Material::evaluateBRDF
+          if (!lambert) {
+            if (!have_im) i_m = frcp_(calc_I_M(dot(-rdir, n), g.shininess));
+            // pow(max(d, 0), n) here vs pow(max(0, d), n) in the pdf: the same value unless d is NaN
+            const float d = dot(lightDir, omega_r);
+            const float lobe_brdf = (d != d) ? dm::powf_(gmax(d, 0.0f), g.shininess) : lobe;
+            f_r = f_r + g.specular * i_m * lobe_brdf;
+          }
+          const V3 t = (L_i * misWeight) * f_r * G;
+          L_direct = L_direct + v3(t.x / lightPdf, t.y / lightPdf, t.z / lightPdf);
+        }
+      }
+    }
+  }
+  // Integrator::sanitize (P/Integrator.cpp:6-23), then L_i_indirect (= 0) + L_i_direct (:130)
+  if (L_direct.x != L_direct.x || L_direct.y != L_direct.y || L_direct.z != L_direct.z) L_direct = v3(0);
+  if (L_direct.x < 0 || L_direct.y < 0 || L_direct.z < 0) L_direct = v3(0);
+  const V3 px = v3(0) + L_direct;
+  o[0] = px.x, o[1] = px.y, o[2] = px.z;
 }
 
 // =====================================================================================

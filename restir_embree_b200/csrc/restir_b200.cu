@@ -65,6 +65,8 @@ RB_PIXEL_KERNEL(k_temporal, InlineVis, true, 1, (temporal_pixel<InlineVis, false
 RB_PIXEL_KERNEL(k_temporal_banded, InlineVis, true, 1, (temporal_pixel<InlineVis, true>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_spatial, InlineVis, true, 1, spatial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_shade, InlineVis, true, 4, shade_pixel(fc, x, y, vis, cnt))
+// N2: one-sample MIS direct lighting (ground truth next to the path); its two rays per pixel are traced inline
+RB_PIXEL_KERNEL(k_mis_direct, InlineVis, true, 1, mis_direct_pixel(fc, x, y, vis, cnt))
 // wavefront halves
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
 RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))  // 95 regs, no spills
@@ -409,6 +411,7 @@ struct RbContext {
   cudaStream_t fstream = nullptr;  // front halves (lower priority than `stream`)
   cudaEvent_t evFrontDone = nullptr, evBackDone[2]{};
   bool backRecorded[2]{};
+  bool frontRecorded = false;
   uint32_t frameSeq = 0;
   bool overlap = true;  // RB_OVERLAP=0: both halves on `stream`
   // RB_OVERLAP_DEBUG=1: timestamps of the halves of the first frames, printed by rb_destroy
@@ -464,6 +467,7 @@ struct RbContext {
 
   // scene
   bool haveScene = false;
+  bool hasDielectric = false;  // a material the N2 estimator does not cover
   SceneDev sc{};
   std::vector<void*> sceneAllocs;
   RbSceneStats stats{};
@@ -1262,6 +1266,9 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
   h->haveScene = false;
   h->havePrev = false;
 
+  h->hasDielectric = false;
+  for (uint32_t m = 0; m < sd->n_materials; ++m)
+    if (sd->materials[m].type == RB_MAT_DIELECTRIC) h->hasDielectric = true;
   HostScene hs;
   {
     int frc = flatten_scene(sd, hs, h->err);
@@ -1607,7 +1614,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   // its outputs (G[(gCur+1)%3], R[rFree], the parity's visibility queue and counters) were last used by the back half
   // of the frame before last; its ray queues by the previous front half
   if (h->backRecorded[par]) RB_CUDA(cudaStreamWaitEvent(sf, h->evBackDone[par], 0));
-  if (h->frameSeq > 0) RB_CUDA(cudaStreamWaitEvent(sf, h->evFrontDone, 0));
+  if (h->frontRecorded) RB_CUDA(cudaStreamWaitEvent(sf, h->evFrontDone, 0));
   const bool ovd = h->ovDebug && h->frameSeq < (uint32_t)RbContext::kOvFrames;
   if (ovd) cudaEventRecord(h->evOv[h->frameSeq][0], sf);
   unsigned long long* ctr = h->counters2 + 8 * par;
@@ -1676,6 +1683,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   fs_mark(h, 1, 0);
   if (ovd) cudaEventRecord(h->evOv[h->frameSeq][1], sf);
   RB_CUDA(cudaEventRecord(h->evFrontDone, sf));
+  h->frontRecorded = true;
   RB_CUDA(cudaGetLastError());
 
   // ---- BACK half: needs the front half and the previous frame -------------------------------------------------------
@@ -1950,6 +1958,59 @@ int rb_render_frame_device(RbHandle h, const RbCamera* cam, uint32_t frame_idx, 
   return RB_OK;
 }
 
+// N2: the reference's ground-truth estimator on the same boundary. Independent of the ReSTIR state: it
+// renders its own G-buffer into the buffer the next frame's front half will overwrite anyway, and writes frame_data
+// (so rb_accumulate_display converges it exactly like the reference's Producer loop does).
+int rb_render_mis_frame(RbHandle h, const RbCamera* cam, uint32_t frame_idx, uint32_t techniques, float* frame_rgb_out) {
+  if (!h || !cam || (techniques & ~3u)) return RB_ERR_INVALID_ARGUMENT;
+  if (!h->haveScene) {
+    h->err = "rb_render_mis_frame: no scene uploaded";
+    return RB_ERR_NO_SCENE;
+  }
+  if (h->fs.open) {
+    h->err = "rb_render_mis_frame: a ReSTIR frame is open (rb_frame_begin without rb_frame_end)";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  if (h->hasDielectric) {
+    h->err = "rb_render_mis_frame: dielectric materials are not covered by the MIS ground-truth estimator";
+    return RB_ERR_UNSUPPORTED;
+  }
+  RB_CUDA(cudaSetDevice(h->info.device));
+  if (h->frontRecorded) RB_CUDA(cudaStreamWaitEvent(h->stream, h->evFrontDone, 0));
+  const int y0 = h->info.band_y0, y1 = h->info.band_y1;
+  FrameCtx fc{};
+  fc.width = h->info.width;
+  fc.height = h->info.height;
+  fc.y0 = y0;
+  fc.y1 = y1;
+  fc.sc = h->sc;
+  fc.P = h->params;
+  fc.cam = cam_state(cam);
+  fc.prevCam = fc.cam;
+  fc.G = fc.Gprev = h->G[(h->gCur + 1) % 3];
+  fc.Rread = fc.Rwrite = fc.Rlast = h->R[h->rFree];
+  fc.frame = h->frame;
+  unsigned long long* ctr = h->counters2 + 8 * (h->frameSeq & 1u);
+  // (the parity block of the NEXT ReSTIR frame: its front half zeroes it again, and this stream is idle by then)
+  fc.counters = ctr;
+  fc.gy0 = y0, fc.gy1 = y1;
+  fc.mis_flags = techniques;
+  RB_CUDA(cudaMemsetAsync(ctr, 0, 64, h->stream));
+  fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_GBUF, 0);
+  launch_rows(h, k_gbuffer, y0, y1, 128, &fc);
+  fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_MIS, 0);
+  launch_rows(h, k_mis_direct, y0, y1, kTileW * kTileH, &fc);
+  RB_CUDA(cudaGetLastError());
+  // the next ReSTIR front half (other stream) must not start on this G-buffer before the MIS kernels are done
+  RB_CUDA(cudaEventRecord(h->evFrontDone, h->stream));
+  h->frontRecorded = true;
+  if (frame_rgb_out) {
+    const size_t off = (size_t)y0 * h->info.width * 3, cnt = (size_t)(y1 - y0) * h->info.width * 3;
+    RB_CUDA(cudaMemcpyAsync(frame_rgb_out + off, h->frame + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return RB_OK;
+}
 int rb_synchronize(RbHandle h) {
   if (!h) return RB_ERR_INVALID_ARGUMENT;
   RB_CUDA(cudaSetDevice(h->info.device));

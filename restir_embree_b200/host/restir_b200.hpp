@@ -190,6 +190,18 @@ class Renderer {
     check(rb_render_frame(h_, &c, frameCtr, frame_data, &timings), "rb_render_frame");
   }
 
+  // Raytracer::get_pixel over the image with the reference's ground-truth integrator selected in its GUI: NEEPathIntegrator,
+  // "Calculate DI" on, "Calculate GI" off, "MIS Sampler" (P/NEEPathIntegrator.cpp:31-52, P/DirectMISIntegrator.cpp:32-36).
+  // sampleBRDF / sampleLightSources are DirectMISIntegrator's two checkboxes. Does not touch the ReSTIR state.
+  void produceMisGroundTruth(const Camera& camera, uint32_t frameCtr, float* frame_data, bool sampleBRDF = true,
+                             bool sampleLightSources = true) {
+    RbParams p = params.toAbi();
+    check(rb_set_params(h_, &p), "rb_set_params");
+    RbCamera c = camera.toAbi();
+    const uint32_t techniques = (sampleBRDF ? RB_MIS_SAMPLE_BRDF : 0u) | (sampleLightSources ? RB_MIS_SAMPLE_LIGHTS : 0u);
+    check(rb_render_mis_frame(h_, &c, frameCtr, techniques, frame_data), "rb_render_mis_frame");
+  }
+
   // the rest of SimpleGuiDX11::Producer's loop body after produceRestir (P/simpleguidx11.cpp:246-326): accumulate the
   // frame, fill display_data (width*height float4, may be null: kept on the device), update accumulatorMean /
   // accumulatorVariance. accFrameCtr, tonemap and gammaCorrect are the reference's members of the same names.

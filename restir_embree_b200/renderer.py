@@ -47,6 +47,7 @@ def load_library():
     L.rb_set_params.argtypes = [H, C.POINTER(abi.RbParams)]
     L.rb_render_frame.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
     L.rb_render_frame_device.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
+    L.rb_render_mis_frame.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
     L.rb_readback.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
     L.rb_synchronize.argtypes = [H]
     L.rb_timer_begin.argtypes = [H]
@@ -174,6 +175,16 @@ class Renderer:
         if want_timings:
             return _timings_dict(t)
         return None
+
+    def render_mis_frame(self, cam, frame_idx, techniques=3, fetch=True):
+        """One frame of the reference's ground-truth estimator (one-sample MIS direct lighting: NEEPathIntegrator with DI
+        only around DirectMISIntegrator, P/DirectMISIntegrator.cpp:18-144). techniques: bit 0 = sample the BRDF, bit 1 =
+        sample the light sources. Leaves the ReSTIR state alone; accumulate_display() converges it."""
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        out = np.zeros((self.height, self.width, 3), dtype=np.float32) if fetch else None
+        rc = self.L.rb_render_mis_frame(self.h, C.byref(c), int(frame_idx), int(techniques), out.ctypes.data if fetch else None)
+        self._check(rc, "rb_render_mis_frame")
+        return out
 
     def accumulate_display(self, acc_frame_ctr, tonemap=True, gamma_correct=True, fetch=False, want_stats=True):
         """The Producer loop's step after produceRestir (P/simpleguidx11.cpp:246-326): accumulate the frame just

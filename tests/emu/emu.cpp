@@ -554,6 +554,33 @@ int emu_frame_end(void* h, float* rgb_out) {
   return 0;
 }
 
+// N2: the kernel bodies of rb_render_mis_frame (k_gbuffer + k_mis_direct) on the G-buffer the next frame overwrites
+int emu_render_mis_frame(void* h, const RbCamera* cam, uint32_t frame_idx, uint32_t techniques, float* rgb_out) {
+  Emu* E = (Emu*)h;
+  if (!E->haveScene) return RB_ERR_NO_SCENE;
+  FrameCtx fc{};
+  fc.width = E->width, fc.height = E->height, fc.y0 = E->y0, fc.y1 = E->y1;
+  fc.sc = E->sc;
+  fc.P = E->P;
+  fc.cam.pos = v3(cam->pos[0], cam->pos[1], cam->pos[2]);
+  fc.cam.focal = cam->focal_px;
+  memcpy(fc.cam.viewMat, cam->viewMat, 64);
+  memcpy(fc.cam.invViewMat, cam->invViewMat, 64);
+  fc.prevCam = fc.cam;
+  fc.G = fc.Gprev = E->gp(E->gCur);  // (emu: two G-buffers, gCur is the one the next frame writes)
+  fc.frame = E->frame.data();
+  fc.counters = E->counters;
+  fc.gy0 = E->y0, fc.gy1 = E->y1;
+  fc.mis_flags = techniques;
+  memset(E->counters, 0, sizeof(E->counters));
+  fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_GBUF, 0);
+  for_pixels(E, fc, [&](int x, int y, Cnt& c) { gbuffer_pixel(fc, x, y, c); });
+  fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_MIS, 0);
+  for_pixels(E, fc, [&](int x, int y, Cnt& c) { mis_direct_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
+  if (rgb_out) memcpy(rgb_out, E->frame.data(), E->frame.size() * sizeof(float));
+  return 0;
+}
+
 int emu_render_frame(void* h, const RbCamera* cam, uint32_t frame_idx, float* rgb_out) {
   Emu* E = (Emu*)h;
   int rc = emu_frame_begin(h, cam, frame_idx);

@@ -38,6 +38,7 @@ def lib():
         L.emu_scene_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_render_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p]
         L.emu_counters.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_render_mis_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
         L.emu_deferred_total.argtypes = [C.c_void_p]
         L.emu_deferred_total.restype = C.c_uint64
         L.emu_readback.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
@@ -97,6 +98,13 @@ class Emu:
         c = cam.to_abi() if hasattr(cam, "to_abi") else cam
         out = np.empty((self.height, self.width, 3), dtype=np.float32)
         rc = self.L.emu_render_frame(self.h, C.byref(c), frame_idx, out.ctypes.data)
+        assert rc == 0, rc
+        return out
+
+    def render_mis_frame(self, cam, frame_idx, techniques=3):
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        out = np.empty((self.height, self.width, 3), dtype=np.float32)
+        rc = self.L.emu_render_mis_frame(self.h, C.byref(c), frame_idx, techniques, out.ctypes.data)
         assert rc == 0, rc
         return out
 

@@ -39,6 +39,7 @@ def lib():
         L.orc_upload_scene.argtypes = [C.c_void_p, C.POINTER(abi.RbSceneDesc)]
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(abi.RbParams)]
         L.orc_render_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_render_mis_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_readback.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.orc_accumulate_display.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_set_frame.argtypes = [C.c_void_p, C.c_void_p]
@@ -116,6 +117,14 @@ class Oracle:
         rc = self.L.orc_render_frame(self.h, C.byref(c), frame_idx, out.ctypes.data, times.ctypes.data)
         assert rc == 0, rc
         return (out, times) if want_times else out
+
+    def render_mis_frame(self, cam, frame_idx, techniques=3):
+        """N2: one frame of the reference's one-sample MIS direct-lighting estimator (NEEPathIntegrator, DI only)"""
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        out = np.empty((self.height, self.width, 3), dtype=np.float32)
+        rc = self.L.orc_render_mis_frame(self.h, C.byref(c), frame_idx, techniques, out.ctypes.data)
+        assert rc == 0, rc
+        return out
 
     def set_frame(self, rgb):
         a = np.ascontiguousarray(rgb, dtype=np.float32)

@@ -29,6 +29,7 @@ def lib():
         R.ref_set_params.argtypes = [C.c_void_p, C.POINTER(abi.RbParams)]
         R.ref_camera.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(abi.RbCamera)]
         R.ref_produce_restir.argtypes = [C.c_void_p, C.c_void_p]
+        R.ref_produce_mis.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_reservoirs.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_gbuffer.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_seed.argtypes = [C.c_uint32]
@@ -71,6 +72,12 @@ class Reference:
     def produce_restir(self):
         out = np.zeros((self.height, self.width, 3), dtype=np.float32)
         self.R.ref_produce_restir(self.h, out.ctypes.data)
+        return out
+
+    def produce_mis(self):
+        """N2: Raytracer::get_pixel over the image with NEEPathIntegrator (DI only) + the reference's DirectMISIntegrator"""
+        out = np.zeros((self.height, self.width, 3), dtype=np.float32)
+        self.R.ref_produce_mis(self.h, out.ctypes.data)
         return out
 
     def reservoirs(self):
