@@ -6,6 +6,8 @@ each (they are parity-test / microbench cases, not the headline):
   python tools/run_configs.py 10m       configs[2] on ONE GPU: 10 M triangles, 100 k emitters, 3840x2160, 3 spatial passes k=5
   python tools/run_configs.py rays      configs[3]: 33 M shadow rays (16 per 1080p pixel) against the 10 M-triangle BVH,
                                         coherent (pixel order) and shuffled, through rb_trace_occluded_device
+  python tools/run_configs.py bias      static camera, 256 frames each: running mean of ReSTIR (as benchmarked, and without temporal
+                                        reuse) against the running mean of the MIS ground-truth estimator (rb_render_mis_frame, N2)
   python tools/run_configs.py orbit64   configs[4]: 64-frame orbit at 1080p on the 1 M scene: fps, temporal-reuse statistics,
                                         per-frame relMSE of sampled rows against the CPU oracle (bit-exact => 0)
 """
@@ -127,6 +129,43 @@ def run_orbit64():
                           "accumulator_mean": float(accum.mean()), "accumulator_finite": bool(np.isfinite(accum).all())}))
 
 
+def run_bias(n=256):
+    """What the author did with S/mis_reference*.png.txt vs S/temporal_*.png.txt: image means and relMSE of converged ReSTIR
+    images against the converged one-sample-MIS image (unbiased). Pixels that show emitter BACK sides differ by construction
+    (evaluateF weights the emitter cosine with abs(), the MIS integrator with max(0, .)); they are few in this scene."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    sc = scenes.scene_config("1m")
+    W, H = 1920, 1080
+    c = sc.meta["center"]
+    cam = Camera(W, H, 55, scenes.orbit_position(c, 0), c)
+    out = {"config": "bias", "frames": n}
+    with Renderer(W, H, seed=123) as r:
+        r.upload_scene(sc)
+
+        def converge(render):
+            t0 = time.time()
+            for f in range(n):
+                render(f)
+                r.accumulate_display(f, fetch=False, want_stats=False)
+            r.synchronize()
+            return r.readback(abi.BUF_ACCUMULATOR).astype(np.float64), (time.time() - t0) / n * 1e3
+
+        r.set_params(params())
+        mis, ms = converge(lambda f: r.render_mis_frame(cam, f, fetch=False))
+        out["mis_ms_per_frame"] = ms
+        mis2, _ = converge(lambda f: r.render_mis_frame(cam, 10000 + f, fetch=False))
+        out["mis_mean"] = float(mis.mean())
+        out["relmse_mis_vs_mis_other_frames"] = float(ob.relmse(mis2, mis))
+        for name, kw in (("restir_bench_settings", {}), ("restir_no_temporal", dict(doTemporalReuse=0)),
+                         ("restir_no_reuse", dict(doTemporalReuse=0, doSpatialReuse=0))):
+            r.set_params(params(**kw))
+            img, ms = converge(lambda f: r.render_frame_device(cam, f))
+            out[name] = {"mean": float(img.mean()), "mean_vs_mis": float(img.mean() / mis.mean()), "relmse_vs_mis": float(ob.relmse(img, mis)),
+                         "ms_per_frame_incl_accumulate": ms}
+    print(json.dumps(out))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "room"
     if what == "room":
@@ -137,5 +176,7 @@ if __name__ == "__main__":
         run_rays()
     elif what == "orbit64":
         run_orbit64()
+    elif what == "bias":
+        run_bias()
     else:
         raise SystemExit(__doc__)
