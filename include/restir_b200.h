@@ -315,6 +315,9 @@ int rb_scene_stats(RbHandle h, RbSceneStats* out);
 int rb_comm_unique_id(void* out_id, size_t id_bytes);
 int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes);
 int32_t rb_comm_transport(RbHandle h); /* 0 = no communicator, 1 = peer memory (CUDA IPC), 2 = NCCL send/recv */
+/* The balancer's partition rule alone (host arithmetic, no GPU): pairs = {cost, rows} per rank, rows tiling [0, height);
+ * bounds_out[n_ranks + 1] = the boundaries every rank derives from them for the next period. For tests and tuning. */
+int rb_debug_balance_step(const float* pairs, int32_t n_ranks, int32_t height, int32_t* bounds_out);
 
 /* The same frame in phases, for hosts that move the halo rows themselves (another transport, or several
  * bands in one process):  rb_frame_begin  (G-buffer, initial candidates, visibility, temporal)

@@ -2221,6 +2221,16 @@ int rb_comm_unique_id(void* out_id, size_t id_bytes) {
   }
   return g_nccl.GetUniqueId(out_id) == 0 ? RB_OK : RB_ERR_COMM;
 }
+// host-only arithmetic of the band balancer, exported so that it can be tested without GPUs: `pairs` = {cost, rows} per
+// rank (rows must tile [0, height)); bounds_out gets the n + 1 new boundaries every rank would compute
+int rb_debug_balance_step(const float* pairs, int32_t n_ranks, int32_t height, int32_t* bounds_out) {
+  if (!pairs || !bounds_out || n_ranks < 1 || n_ranks > RbContext::kMaxRanks) return RB_ERR_INVALID_ARGUMENT;
+  bounds_out[0] = 0;
+  for (int r = 0; r < n_ranks; ++r) bounds_out[r + 1] = bounds_out[r] + (int)pairs[2 * r + 1];
+  if (bounds_out[n_ranks] != height) return RB_ERR_INVALID_ARGUMENT;
+  balance_targets(pairs, n_ranks, height, bounds_out);
+  return RB_OK;
+}
 int32_t rb_comm_transport(RbHandle h) { return (!h || !h->comm) ? 0 : (h->p2p ? 1 : 2); }
 int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes) {
   if (!h || !nccl_unique_id || id_bytes < 128 || rank < 0 || rank >= nranks) return RB_ERR_INVALID_ARGUMENT;

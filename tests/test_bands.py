@@ -222,3 +222,40 @@ def test_gpu_bands_fast_pan_deferred_rederivation(gpu):
         assert np.array_equal(bits(one.readback(abi.BUF_RES_LIGHT_IDX)), bits(assemble(bands, abi.BUF_RES_LIGHT_IDX)))
     for r in bands + [one]:
         r.close()
+
+
+def _balance(pairs, height):
+    import ctypes as C
+    from restir_embree_b200.renderer import load_library
+    L = load_library()
+    n = len(pairs)
+    a = (C.c_float * (2 * n))(*[v for p in pairs for v in p])
+    out = (C.c_int32 * (n + 1))()
+    L.rb_debug_balance_step.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    assert L.rb_debug_balance_step(a, n, height, out) == 0
+    return list(out)
+
+
+def test_balancer_partition_rule():
+    """The host arithmetic of the band balancer (every rank runs it on the same all-gathered numbers): equal costs keep
+    the bands, an expensive band shrinks, a boundary moves at most 15 rows per period, repeated steps converge to the
+    equal-cost partition of a piecewise-constant cost profile, thin bands are left alone."""
+    H = 1080
+    rows = [135] * 8
+    assert _balance([(1.5, r) for r in rows], H) == [135 * i for i in range(9)]
+    # rank 0 twice as cheap per row as the others: it must grow, by at most 15 rows
+    b = _balance([(0.75, 135)] + [(1.5, 135)] * 7, H)
+    assert 135 < b[1] <= 150 and b[0] == 0 and b[8] == H
+    assert all(b[i + 1] - b[i] >= 32 for i in range(8))
+    # iterate against a synthetic per-row cost profile: ceiling rows cheap, middle rows expensive
+    prof = np.concatenate([np.full(300, 0.5), np.full(480, 1.6), np.full(300, 1.0)])
+    bounds = [135 * i for i in range(9)]
+    for _ in range(40):
+        costs = [float(prof[bounds[i]:bounds[i + 1]].sum()) for i in range(8)]
+        new = _balance([(c, bounds[i + 1] - bounds[i]) for i, c in enumerate(costs)], H)
+        assert all(abs(n - o) <= 15 for n, o in zip(new, bounds))
+        bounds = new
+    costs = np.array([prof[bounds[i]:bounds[i + 1]].sum() for i in range(8)])
+    assert costs.max() / costs.mean() < 1.03, (bounds, costs)
+    # bands too thin to move safely: unchanged
+    assert _balance([(1.0, 27), (3.0, 27), (1.0, 26)], 80) == [0, 27, 54, 80]
