@@ -476,24 +476,6 @@ RB_HD void gbuffer_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
   const GElem e = gbuffer_element(fc, fc.cam, x, y, &g, &p, cnt);
   store_gelem(fc.G, (size_t)y * fc.width + x, e, g, p);
 }
-// Wavefront halves of the G-buffer pass: the primary ray goes through the ray queue (closest-hit slot 0), the
-// resolve half builds the element from the traced hit. Same functions as the inline path, so same bits.
-RB_HD void gbuffer_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis) {
-  V3 dir;
-  primary_ray(fc.cam, fc.width, fc.height, x, y, &dir);
-  (void)vis.closest(0, fc.cam.pos, dir, RB_PRIMARY_TNEAR, FLT_MAX);
-}
-RB_HD void gbuffer_resolve_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
-  V3 dir;
-  primary_ray(fc.cam, fc.width, fc.height, x, y, &dir);
-  cnt.closest++;
-  const size_t pi = (size_t)y * fc.width + x;
-  const SurfaceHit h = surface_from_hit(fc.sc, fc.cam.pos, dir, fc.wave.hits[pi]);
-  uint32_t g, p;
-  const GElem e = gbuffer_from_hit(fc, fc.cam, h, &g, &p);
-  store_gelem(fc.G, pi, e, g, p);
-}
-
 // =====================================================================================
 // Pass 1: initial candidates (ReSTIRIntegrator::initialRenderPass, :236-298;
 // areaSampleLight :89-124; brdfSampleLight :126-177; Sampling::sampleTriangle P/Sampling.cpp:63-76)

@@ -435,16 +435,7 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
   const bool wave = E->wave;
   emu_bind(E);
   fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_GBUF, 0);
-  if (wave && getenv("RB_WAVE_GBUF") && atoi(getenv("RB_WAVE_GBUF")) && (size_t)(fc.gy1 - fc.gy0) * fc.width <= E->rays.size()) {
-    FrameCtx save = fc;
-    fc.y0 = fc.gy0, fc.y1 = fc.gy1;
-    emu_stream(E, [&](int x, int y, Cnt&) { gbuffer_gen_pixel(fc, x, y, GenVis{&fc, PX(fc, x, y)}); });
-    emu_trace_queue(E, EMU_CLOSEST, RB_PRIMARY_TNEAR);
-    for_pixels(E, fc, [&](int x, int y, Cnt& c) { gbuffer_resolve_pixel(fc, x, y, c); });
-    fc.y0 = save.y0, fc.y1 = save.y1;
-  } else {
-    emu_rows(E, fc.gy0, fc.gy1, [&](int x, int y, Cnt& c) { gbuffer_pixel(fc, x, y, c); });
-  }
+  emu_rows(E, fc.gy0, fc.gy1, [&](int x, int y, Cnt& c) { gbuffer_pixel(fc, x, y, c); });
   fc.frame_key = rng_frame_key(E->seed, frame_idx, PASS_INITIAL, 0);
   if (wave) {
     if (P.M_Brdf > 0 && fc.sc.n_lights > 0) {

@@ -207,3 +207,24 @@ def test_gpu_mis_between_restir_frames_and_accumulation(gpu):
             acc = acc + (img - acc) * np.float32(1.0 / (f + 1))
         got = mixed.readback(abi.BUF_ACCUMULATOR)
         assert np.allclose(got, acc, rtol=1e-5, atol=1e-6)
+
+
+def test_mis_frame_on_bands_equals_the_full_frame():
+    """The estimator is a per-pixel map keyed on the global pixel index: bands need no exchange at all."""
+    from band_driver import make_bands
+    sc = scenes.scene_config("tiny")
+    w, h = 64, 48
+    p = abi.default_params(lightSampler=abi.LS_ALIAS)
+    cam = Camera(w, h, 60, (2.2, -2.4, 1.4), (0, 0, 1.0))
+    one = eb.Emu(w, h, seed=5)
+    one.upload_scene(sc)
+    one.set_params(p)
+    full = one.render_mis_frame(cam, 3)
+    bands = make_bands(eb.Emu, w, h, 3, seed=5)
+    got = np.zeros_like(full)
+    for b in bands:
+        b.upload_scene(sc)
+        b.set_params(p)
+        y0, y1 = b.band
+        got[y0:y1] = b.render_mis_frame(cam, 3)[y0:y1]
+    assert np.array_equal(bits(full), bits(got))
