@@ -284,6 +284,24 @@ typedef struct RbSceneStats {
 } RbSceneStats;
 int rb_scene_stats(RbHandle h, RbSceneStats* out);
 
+/* ---- Scene ingestion (first half) -------------------------------------------------------------
+ * Where the reference constructs `Scene{file_name, device}` (P/raytracer.cpp:36, ModelLoader::loadScene /
+ * loadOBJ / loadMaterials, P/ModelLoader.cpp:41-321) through ASSIMP, rb_obj_load parses a Wavefront OBJ + MTL itself
+ * and ends in the RbSceneDesc rb_upload_scene takes (host-only, no GPU needed). Kept from the reference: material type
+ * from the MTL key `Pc` (0..5 = P/enums.h MaterialType, else UNSUPPORTED), Kd/Ks expanded from sRGB when gamma_correct
+ * (Raytracer::gammaCorrect, default on; Utils::expand), Ke/Ns/Ni as written, ASSIMP's OBJ defaults for absent keys,
+ * materials in MTL order, one non-indexed surface per material in order of first use, faces without a material are an
+ * error (the reference indexes materials with mMaterialIndex - 1). Not pinnable without an ASSIMP binary: polygon
+ * triangulation (a fan here), mesh order of files that interleave materials, tangents (none; textures are not part of
+ * ABI v1 — the MTL's texture file names are available through rb_obj_texture_name, slots 0..3 = map_Kd, map_Ks,
+ * map_Ns, map_Kn/bump). Faces without normals get the flat face normal. err (optional) receives a message. */
+typedef struct RbObjScene RbObjScene;
+int rb_obj_load(const char* obj_path, int32_t gamma_correct, RbObjScene** out, char* err, size_t err_bytes);
+const RbSceneDesc* rb_obj_scene_desc(const RbObjScene* s); /* valid until rb_obj_free */
+const char* rb_obj_material_name(const RbObjScene* s, uint32_t material);
+const char* rb_obj_texture_name(const RbObjScene* s, uint32_t material, int32_t slot);
+void rb_obj_free(RbObjScene* s);
+
 /* ---- Multi-GPU bands -----------------------------------------------------------------
  * One handle per GPU renders the image rows [band_y0, band_y1); scene and BVH are replicated. The only
  * cross-band data are the reservoir rows within the spatial-reuse reach of a band edge ("halo rows"), which are

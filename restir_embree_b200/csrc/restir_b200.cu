@@ -15,6 +15,7 @@
 
 #include "rb_build.cuh"
 #include "rb_host_scene.h"
+#include "rb_obj_loader.h"
 #include "rb_passes.cuh"
 
 using namespace rb;
@@ -2231,6 +2232,36 @@ int rb_debug_balance_step(const float* pairs, int32_t n_ranks, int32_t height, i
   balance_targets(pairs, n_ranks, height, bounds_out);
   return RB_OK;
 }
+// ---- scene ingestion (first half): Wavefront OBJ / MTL with the reference's conventions ------------
+struct RbObjScene {
+  rbobj::Scene sc;
+};
+int rb_obj_load(const char* obj_path, int32_t gamma_correct, RbObjScene** out, char* err, size_t err_bytes) {
+  if (!obj_path || !out) return RB_ERR_INVALID_ARGUMENT;
+  RbObjScene* s = new RbObjScene();
+  std::string e;
+  if (!rbobj::load_obj(obj_path, gamma_correct != 0, s->sc, e)) {
+    if (err && err_bytes) {
+      strncpy(err, e.c_str(), err_bytes - 1);
+      err[err_bytes - 1] = 0;
+    }
+    delete s;
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  *out = s;
+  return RB_OK;
+}
+const RbSceneDesc* rb_obj_scene_desc(const RbObjScene* s) { return s ? &s->sc.desc : nullptr; }
+const char* rb_obj_material_name(const RbObjScene* s, uint32_t i) {
+  return (s && i < s->sc.material_names.size()) ? s->sc.material_names[i].c_str() : nullptr;
+}
+const char* rb_obj_texture_name(const RbObjScene* s, uint32_t i, int32_t slot) {
+  if (!s || i >= s->sc.materials.size()) return nullptr;
+  const std::vector<std::string>* v[4] = {&s->sc.map_kd, &s->sc.map_ks, &s->sc.map_ns, &s->sc.map_kn};
+  return (slot >= 0 && slot < 4) ? (*v[slot])[i].c_str() : nullptr;
+}
+void rb_obj_free(RbObjScene* s) { delete s; }
+
 int32_t rb_comm_transport(RbHandle h) { return (!h || !h->comm) ? 0 : (h->p2p ? 1 : 2); }
 int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes) {
   if (!h || !nccl_unique_id || id_bytes < 128 || rank < 0 || rank >= nranks) return RB_ERR_INVALID_ARGUMENT;

@@ -182,6 +182,19 @@ class Renderer {
     check(rb_upload_scene(h_, &d), "rb_upload_scene");
   }
 
+  // Raytracer::LoadScene(file_name) (P/raytracer.cpp:35-39): `scene = Scene{file_name, device_}` goes through
+  // ModelLoader::loadScene / loadOBJ / loadMaterials; here the library's own OBJ / MTL parser with the same conventions
+  // (rb_obj_load, see include/restir_b200.h). gammaCorrect = Raytracer::gammaCorrect.
+  void LoadScene(const std::string& file_name, bool gammaCorrect = true) {
+    RbObjScene* s = nullptr;
+    char err[512] = {0};
+    if (rb_obj_load(file_name.c_str(), gammaCorrect ? 1 : 0, &s, err, sizeof(err)) != RB_OK)
+      throw std::runtime_error(std::string("rb_obj_load: ") + err);
+    const int rc = rb_upload_scene(h_, rb_obj_scene_desc(s));
+    rb_obj_free(s);
+    check(rc, "rb_upload_scene");
+  }
+
   // SimpleGuiDX11::produceRestir: frame_data is width*height float3 (linear HDR), owned by the caller
   void produceRestir(const Camera& camera, uint32_t frameCtr, float* frame_data) {
     RbParams p = params.toAbi();

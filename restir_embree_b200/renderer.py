@@ -284,6 +284,50 @@ class Renderer:
         self._check(self.L.rb_halo_import(self.h, y, rows, buf.ctypes.data), "rb_halo_import")
 
 
+def load_obj_scene(path, gamma_correct=True):
+    """Wavefront OBJ + MTL -> SceneArrays through the library's own parser (rb_obj_load: the conventions of the
+    reference's ModelLoader, P/ModelLoader.cpp:41-321). Host-only: works without a GPU. meta carries the material names
+    and the texture file names of the MTL (textures themselves are not part of ABI v1)."""
+    L = load_library()
+    L.rb_obj_load.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    L.rb_obj_scene_desc.restype = C.POINTER(abi.RbSceneDesc)
+    L.rb_obj_scene_desc.argtypes = [C.c_void_p]
+    L.rb_obj_material_name.restype = C.c_char_p
+    L.rb_obj_material_name.argtypes = [C.c_void_p, C.c_uint32]
+    L.rb_obj_texture_name.restype = C.c_char_p
+    L.rb_obj_texture_name.argtypes = [C.c_void_p, C.c_uint32, C.c_int32]
+    L.rb_obj_free.argtypes = [C.c_void_p]
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = L.rb_obj_load(os.fsencode(path), int(bool(gamma_correct)), C.byref(h), err, len(err))
+    if rc != abi.RB_OK:
+        raise RestirError(f"rb_obj_load failed ({rc}): {err.value.decode(errors='replace')}")
+    try:
+        d = L.rb_obj_scene_desc(h).contents
+        sc = abi.SceneArrays()
+        names, textures = [], []
+        for i in range(d.n_materials):
+            m = d.materials[i]
+            sc.add_material(int(m.type), tuple(m.diffuse), tuple(m.specular), tuple(m.emission), float(m.shininess), float(m.ior))
+            names.append(L.rb_obj_material_name(h, i).decode())
+            textures.append([L.rb_obj_texture_name(h, i, s).decode() for s in range(4)])
+        uvs = []
+        for i in range(d.n_surfaces):
+            sf = d.surfaces[i]
+            n = int(sf.n_tris)
+            pos = np.ctypeslib.as_array(sf.pos, shape=(n, 3, 3)).copy()
+            nrm = np.ctypeslib.as_array(sf.normal, shape=(n, 3, 3)).copy()
+            uvs.append(np.ctypeslib.as_array(sf.uv, shape=(n, 3, 2)).copy())
+            sc.add_surface(pos, nrm, int(sf.material))
+        lo = np.min([s[0].reshape(-1, 3).min(0) for s in sc.surfaces], axis=0)
+        hi = np.max([s[0].reshape(-1, 3).max(0) for s in sc.surfaces], axis=0)
+        sc.meta = dict(kind="obj", path=str(path), material_names=names, texture_names=textures, uv=uvs,
+                       center=tuple(float(v) for v in (lo + hi) / 2), bounds=(lo.tolist(), hi.tolist()))
+        return sc
+    finally:
+        L.rb_obj_free(h)
+
+
 def comm_unique_id():
     """ncclGetUniqueId through the library (rank 0); 128 bytes to hand to every rank's Renderer.comm_init."""
     L = load_library()
