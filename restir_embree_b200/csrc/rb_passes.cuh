@@ -102,6 +102,30 @@ RB_HD uint32_t queue_reserve(uint32_t* counter) {
 #endif
 }
 
+// reserve n queue slots (n may differ per lane, n < 64); on the device ONE atomic for the converged lanes: the per-lane
+// offsets come from ballots of the bits of n (no shuffle chain, no dependence on the atomic's result until the end)
+RB_HD uint32_t queue_reserve_n(uint32_t* counter, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x + threadIdx.y * blockDim.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    const unsigned bal = __ballot_sync(m, (n >> b) & 1u);
+    before += (uint32_t)__popc(bal & lt) << b;
+    total += (uint32_t)__popc(bal) << b;
+  }
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader && total != 0) base = atomicAdd(counter, total);
+  base = __shfl_sync(m, base, leader);
+  return base + before;
+#else
+  return __atomic_fetch_add(counter, n, __ATOMIC_RELAXED);
+#endif
+}
+
 // step 2 of the two-step BRDF-candidate rays, queued by the traversal that found the emitter hit (t_hit, hits[dest].tri)
 RB_HD void brdf_chain_push(const WaveBufs& w, const V3& o, const V3& d, float t_hit, uint32_t dest) {
   const uint32_t i = queue_reserve(w.chain_count);
@@ -148,6 +172,19 @@ struct GenVis {
   RB_HD SurfaceHit closest(int slot, const V3& org, const V3& dir, float /*tnear*/, float tfar) const {
     push(slot, org, dir, tfar);
     return no_hit();
+  }
+  // the same shadow ray as visible(), into a slot reserved beforehand (reserve: all of a pixel's rays with one atomic
+  // per warp instead of one per ray — the reservation round trip was the largest stall of the reuse stream kernels)
+  RB_HD uint32_t reserve(uint32_t n) const { return queue_reserve_n(fc->wave.count, n); }
+  RB_HD void visible_at(uint32_t i, int slot, const V3& from, const V3& to) const {
+    V3 dir;
+    float tfar;
+    shadow_ray(from, to, fc->P.tfarOffset, &dir, &tfar);
+    const WaveBufs& w = fc->wave;
+    if (i < w.capacity) {
+      st4(&w.rays[i].o_tfar, f4(from, tfar));
+      st4(&w.rays[i].d_dest, f4(dir, u2f((uint32_t)slot * w.npix + pixel)));
+    }
   }
 };
 // ResolveVis: the resolve half. The same queries, in the same order, read the traced results.
@@ -830,7 +867,7 @@ RB_HD void temporal_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vi
   const VisMode modeB = cur.W == 0.0f ? VIS_IRRELEVANT : VIS_TRACE;
   const VisMode modeCD = prev.W == 0.0f ? VIS_IRRELEVANT : VIS_TRACE;
   float ph[4];
-  uint32_t flags = 0;
+  uint32_t flags = 0, raymask = 0;
   for (int e = 0; e < 4; ++e) {  // A: cur sample @ cur pixel, B: cur @ prev, C: prev @ cur, D: prev @ prev
     const LightSample& smp = e < 2 ? cur.bestSample : prev.bestSample;
     const GElem& g = (e & 1) ? prevElem : curElem;
@@ -845,13 +882,19 @@ RB_HD void temporal_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vi
       const bool zero = F0.x == 0.0f && F0.y == 0.0f && F0.z == 0.0f;
       if (!zero && vm != VIS_KNOWN && !(vm == VIS_IRRELEVANT && finite3(F0))) {
         cnt.anyT++;
-        (void)vis.visible(e, g.pos, smp.samplePoint);
+        raymask |= 1u << e;
         f |= RB_CAND_RAY;
         if (!finite3(F0)) f |= RB_CAND_PH0_NAN;
       }
     }
     ph[e] = length(F0 * 1.0f);
     flags |= f << (4 * e);
+  }
+  {  // the rays of this pixel, one queue reservation
+    uint32_t qi = vis.reserve((uint32_t)popc(raymask));
+    for (int e = 0; e < 4; ++e)
+      if (raymask & (1u << e))
+        vis.visible_at(qi++, e, ((e & 1) ? prevElem : curElem).pos, (e < 2 ? cur.bestSample : prev.bestSample).samplePoint);
   }
   wv.cand[pi] = U4{f2u(ph[0]), f2u(ph[1]), f2u(ph[2]), f2u(ph[3])};
   *rec_flags = U4{flags, 0u, 0u, 0u};
@@ -1105,6 +1148,7 @@ RB_HD void spatial_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis
     }
     nb[M++] = (uint32_t)ni;
   }
+  uint64_t raymask = 0;
   for (int i = 0; i < M; ++i) {
     // only what the weight needs of the neighbour's reservoir: sample point/normal/L_i, W, confidence
     const F4 a = ld4(fc.Rread.point_wsum + nb[i]), b = ld4(fc.Rread.normal_W + nb[i]), c = ld4(fc.Rread.Li_conf + nb[i]);
@@ -1120,7 +1164,7 @@ RB_HD void spatial_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis
       const bool zero = F0.x == 0.0f && F0.y == 0.0f && F0.z == 0.0f;
       if (!zero && vm != VIS_KNOWN && !(vm == VIS_IRRELEVANT && finite3(F0))) {
         cnt.anyT++;
-        (void)vis.visible(i, thisElem.pos, si.samplePoint);
+        raymask |= 1ull << i;
         flags |= RB_CAND_RAY;
         if (!finite3(F0)) flags |= RB_CAND_PH0_NAN;
       }
@@ -1129,6 +1173,12 @@ RB_HD void spatial_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vis
     const uint32_t w3 = (i == 0 ? (uint32_t)M : nb[i]) | (flags << RB_CAND_INDEX_BITS);
     wv.cand[(size_t)i * wv.npix + pi] = U4{f2u(ph1), f2u(Wi), f2u(c.w), w3};
   }
+  // the rays of this pixel, one queue reservation; the sample points are read again (they are in L1 / L2)
+  uint32_t n_rays = 0;
+  for (uint64_t m = raymask; m; m &= m - 1) ++n_rays;
+  uint32_t qi = vis.reserve(n_rays);
+  for (int i = 0; i < M; ++i)
+    if ((raymask >> i) & 1ull) vis.visible_at(qi++, i, thisElem.pos, xyz(ld4(fc.Rread.point_wsum + nb[i])));
 }
 
 // Final shading of one pixel from its reservoir (body of shade_pixel below, see there). The shadow ray of the
