@@ -451,6 +451,10 @@ struct GBuffer {
 
 struct alignas(64) Counters {
   uint64_t closest = 0, any_written = 0, any_traced = 0;
+  // temporal pass outcome per pixel: [0] backward reprojection failed (:644), [1] depth test
+  // at the reprojected pixel failed (:660), [2] forward reprojection failed (:671), [3] depth test at the
+  // forward-reprojected pixel failed (:686), [4] merged with the previous frame's reservoir
+  uint64_t temporal[5] = {0, 0, 0, 0, 0};
 };
 static inline int thread_id() {
 #ifdef _OPENMP
@@ -889,7 +893,9 @@ struct Oracle {
     const LightSample& currentSample = currentReservoir.bestSample;
     const Reservoir prevReservoir = R_last(x, y);  // same pixel, not the reprojected one (:641)
     const LightSample& prevSample = prevReservoir.bestSample;
+    uint64_t* tstat = ctrs[thread_id()].temporal;
     if (!ok) {
+      tstat[0]++;
       R_write(x, y) = currentReservoir;
       return;
     }
@@ -899,12 +905,14 @@ struct Oracle {
     float prevDepth = length(prevElem.worldSpacePos - prevCamPos);
     float depthRatio = currentDepth > prevDepth ? prevDepth / currentDepth : currentDepth / prevDepth;
     if (depthRatio < 0.9f) {
+      tstat[1]++;
       R_write(x, y) = currentReservoir;
       return;
     }
     const GBufferElement prevElemAtCurrent = gBufferLastFrame.px[(size_t)y * width + x];
     int fx, fy;
     if (!reproject(gBuffer, prevElemAtCurrent.worldSpacePos, &fx, &fy)) {
+      tstat[2]++;
       R_write(x, y) = currentReservoir;
       return;
     }
@@ -913,9 +921,11 @@ struct Oracle {
     float prevDepthP = length(fwReprojected.worldSpacePos - currentCamPos);
     float depthRatioP = currentDepthP > prevDepthP ? prevDepthP / currentDepthP : currentDepthP / prevDepthP;
     if (depthRatioP < 0.9f) {
+      tstat[3]++;
       R_write(x, y) = currentReservoir;
       return;
     }
+    tstat[4]++;
     float p_cur = evaluatePHat(currentSample, currentCamPos, currentElem, true);
     float p_prev = evaluatePHat(currentSample, prevCamPos, prevElem, true);
     float m_cur = p_cur * (float)currentReservoir.confidence /
@@ -1596,6 +1606,15 @@ void orc_counters(void* h, uint64_t* out3, int reset) {
     out3[2] += c.any_traced;
     if (reset) c = Counters{};
   }
+}
+void orc_temporal_stats(void* h, uint64_t* out5, int reset) {
+  Oracle* o = (Oracle*)h;
+  for (int k = 0; k < 5; ++k) out5[k] = 0;
+  for (auto& c : o->ctrs)
+    for (int k = 0; k < 5; ++k) {
+      out5[k] += c.temporal[k];
+      if (reset) c.temporal[k] = 0;
+    }
 }
 uint32_t orc_num_emissive(void* h) { return (uint32_t)((Oracle*)h)->scene.emissive.size(); }
 uint32_t orc_num_triangles(void* h) { return (uint32_t)((Oracle*)h)->scene.tris.size(); }

@@ -39,6 +39,7 @@ def lib():
         L.orc_upload_scene.argtypes = [C.c_void_p, C.POINTER(abi.RbSceneDesc)]
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(abi.RbParams)]
         L.orc_render_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_temporal_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_render_mis_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_readback.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.orc_accumulate_display.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -125,6 +126,14 @@ class Oracle:
         rc = self.L.orc_render_mis_frame(self.h, C.byref(c), frame_idx, techniques, out.ctypes.data)
         assert rc == 0, rc
         return out
+
+    def temporal_stats(self, reset=True):
+        """pixels per outcome of the temporal pass since the last reset: backward reprojection failed, depth test at the
+        reprojected pixel failed, forward reprojection failed, depth test at the forward-reprojected pixel failed, merged"""
+        c = np.zeros(5, dtype=np.uint64)
+        self.L.orc_temporal_stats(self.h, c.ctypes.data, int(bool(reset)))
+        keys = ("reproject_backward_failed", "depth_backward_failed", "reproject_forward_failed", "depth_forward_failed", "merged")
+        return dict(zip(keys, (int(v) for v in c)))
 
     def set_frame(self, rgb):
         a = np.ascontiguousarray(rgb, dtype=np.float32)

@@ -6,6 +6,8 @@ each (they are parity-test / microbench cases, not the headline):
   python tools/run_configs.py 10m       configs[2] on ONE GPU: 10 M triangles, 100 k emitters, 3840x2160, 3 spatial passes k=5
   python tools/run_configs.py rays      configs[3]: 33 M shadow rays (16 per 1080p pixel) against the 10 M-triangle BVH,
                                         coherent (pixel order) and shuffled, through rb_trace_occluded_device
+  python tools/run_configs.py temporal-branches   CPU only (oracle, a 48-row band of the 1080p orbit): fraction of pixels taking each
+                                        temporal-reject branch (P/ReSTIRIntegrator.cpp:644,660,671,686) over the 64-frame orbit
   python tools/run_configs.py bias      static camera, 256 frames each: running mean of ReSTIR (as benchmarked, and without temporal
                                         reuse) against the running mean of the MIS ground-truth estimator (rb_render_mis_frame, N2)
   python tools/run_configs.py orbit64   configs[4]: 64-frame orbit at 1080p on the 1 M scene: fps, temporal-reuse statistics,
@@ -22,7 +24,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 from restir_embree_b200 import Camera, abi, scenes  # noqa: E402
-from restir_embree_b200.renderer import Renderer, make_rays  # noqa: E402
+from restir_embree_b200.renderer import Renderer, make_rays  # noqa: E402  (the library loads without a GPU)
 
 
 def params(**kw):
@@ -129,6 +131,26 @@ def run_orbit64():
                           "accumulator_mean": float(accum.mean()), "accumulator_finite": bool(np.isfinite(accum).all())}))
 
 
+def run_temporal_branches(frames=64):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    sc = scenes.scene_config("1m")
+    W, H = 1920, 1080
+    band = (516, 564)
+    o = ob.Oracle(W, H, seed=123, tracer=ob.TRACER_BVH2)
+    o.upload_scene(sc)
+    o.set_params(params())
+    o.set_band(*band)
+    c = sc.meta["center"]
+    o.temporal_stats()
+    for f in range(frames):
+        o.render_frame(Camera(W, H, 55, scenes.orbit_position(c, f), c), f)
+    st = o.temporal_stats()
+    total = sum(st.values())
+    print(json.dumps({"config": "configs[4] temporal branches (oracle, rows %d-%d, %d frames, 0.5 deg/frame orbit)" % (band[0], band[1], frames),
+                      "pixels": total, "fractions": {k: v / total for k, v in st.items()}}))
+
+
 def run_bias(n=256):
     """What the author did with S/mis_reference*.png.txt vs S/temporal_*.png.txt: image means and relMSE of converged ReSTIR
     images against the converged one-sample-MIS image (unbiased). Pixels that show emitter BACK sides differ by construction
@@ -178,5 +200,7 @@ if __name__ == "__main__":
         run_orbit64()
     elif what == "bias":
         run_bias()
+    elif what == "temporal-branches":
+        run_temporal_branches()
     else:
         raise SystemExit(__doc__)
