@@ -85,8 +85,8 @@ typedef struct RbMaterial {
 /* One surface == one Embree geometry (geomID = index, attach order),
  * exactly what ModelLoader::loadScene hands Embree, P/ModelLoader.cpp:227-318:
  * non-indexed triangle soup, 3*n_tris vertices, identity index buffer (:297-299).
- * uv / tangent may be NULL (treated as zero; only used by textured / normal-
- * mapped materials, which are out of scope of this ABI version). */
+ * uv may be NULL (treated as zero; read by textured materials, rb_set_textures); tangent is accepted and ignored
+ * (normal maps are out of scope of this ABI version). */
 typedef struct RbSurface {
   uint32_t n_tris;
   uint32_t material;    /* index into RbSceneDesc.materials */
@@ -283,6 +283,30 @@ typedef struct RbSceneStats {
   float bounds_hi[3];
 } RbSceneStats;
 int rb_scene_stats(RbHandle h, RbSceneStats* out);
+
+/* ---- Textured materials (second half) -------------------------------------------------------------
+ * Material::getDiffuseColor / getSpecularColor / getShininess (P/material.cpp:105-134) read a texture where the material
+ * has one (Material::set_texture, slots kDiffuseMapSlot / kSpecularMapSlot / kShininessMapSlot); the G-buffer pass calls
+ * them with the hit's interpolated uv (P/ReSTIRIntegrator.cpp:225-228). rb_set_textures hands the library the texel
+ * arrays the host's image loader produced — exactly Texture's members (P/Texture.h:44-48): width, height, bytes per row,
+ * bytes per pixel (3 or 4: 8-bit B,G,R[,A] as FreeImage delivers them, value / 255; 12 or 16: float R,G,B[,A]) and the
+ * data, row 0 first — and, per material, a texture index per slot (-1 = the material constant). Sampling is
+ * Texture::get_texel(uv) as ModelLoader::TextureProxy configures it (BILINEAR, REPEAT; P/Texture.cpp:72-107,170-194):
+ * pixel = (u * w, (1 - v) * h), four get_texel(x, y) with abs(x % w), glm::mix in x then y. The shininess map is a
+ * roughness map: n = 2 / r^2 - 2 (P/material.cpp:124-131). Call after rb_upload_scene (whose surfaces must carry uv);
+ * a new rb_upload_scene drops the textures. Data is copied. Normal maps (kNormalMapSlot) are not part of this version:
+ * `normal` must be -1. */
+typedef struct RbTexture {
+  int32_t width, height;
+  int32_t scan_width; /* bytes per row */
+  int32_t pixel_size; /* bytes per texel: 3, 4 (8-bit BGR[A]) or 12, 16 (float RGB[A]) */
+  const void* data;
+} RbTexture;
+typedef struct RbMaterialTextures {
+  int32_t diffuse, specular, shininess, normal; /* index into the texture array or -1 */
+} RbMaterialTextures;
+int rb_set_textures(RbHandle h, const RbTexture* textures, uint32_t n_textures, const RbMaterialTextures* per_material,
+                    uint32_t n_materials);
 
 /* ---- Scene ingestion (first half) -------------------------------------------------------------
  * Where the reference constructs `Scene{file_name, device}` (P/raytracer.cpp:36, ModelLoader::loadScene /

@@ -49,6 +49,7 @@ struct FakeGeometry {
   unsigned geomID;
   void* userData;
   std::vector<glm::vec3> normals;  // attribute slot 0, 3 per triangle
+  std::vector<glm::vec2> uvs;      // attribute slot 1 (empty: zero)
   std::vector<float> ids;          // attribute slot 2
 };
 struct FakeScene {
@@ -86,6 +87,9 @@ void rtcInterpolate(const struct RTCInterpolateArguments* a) {
   if (a->bufferSlot == 0) {  // shading normal: w*n0 + u*n1 + v*n2 (parity contract; Embree's own order is not public API)
     const glm::vec3 n = g->normals[3 * a->primID] * w + g->normals[3 * a->primID + 1] * u + g->normals[3 * a->primID + 2] * v;
     a->P[0] = n.x, a->P[1] = n.y, a->P[2] = n.z;
+  } else if (a->bufferSlot == 1 && !g->uvs.empty()) {  // texture coordinates, same interpolation contract
+    const glm::vec2 t = g->uvs[3 * a->primID] * w + g->uvs[3 * a->primID + 1] * u + g->uvs[3 * a->primID + 2] * v;
+    a->P[0] = t.x, a->P[1] = t.y;
   } else if (a->bufferSlot == 2) {
     a->P[0] = g->ids[3 * a->primID] * w + g->ids[3 * a->primID + 1] * u + g->ids[3 * a->primID + 2] * v;
   } else {
@@ -132,6 +136,7 @@ Scene::Scene(const char*, const RTCDevice&) {
         const float* n = sf.normal + 9 * (size_t)i + 3 * k;
         v[k] = Vertex(glm::vec3{p[0], p[1], p[2]}, glm::vec3{n[0], n[1], n[2]}, glm::vec3{0}, glm::vec3{0});
         g->normals.push_back(glm::vec3{n[0], n[1], n[2]});
+        if (sf.uv) g->uvs.push_back(glm::vec2{sf.uv[6 * (size_t)i + 2 * k], sf.uv[6 * (size_t)i + 2 * k + 1]});
         g->ids.push_back(materials[sf.material]->isEmissive() ? static_cast<float>(triIdCtr) : 0.0f);
       }
       surface->get_triangle(i) = Triangle(v[0], v[1], v[2], surface);
@@ -154,9 +159,7 @@ const RTCScene& Scene::getRTCScene() const { return scene; }
 const Sky& Scene::getSkybox() const { return *skybox; }
 const TriangleCDF& Scene::getEmissiveCDF() const { return cdf; }
 
-// Texture is never instantiated (untextured scenes) but material.cpp references it
-glm::vec3 Texture::get_texel(const glm::vec2&) const { return glm::vec3{0}; }
-Texture::~Texture() {}
+// (Texture is the reference's own P/Texture.cpp, compiled in place against stubs/freeimage.h)
 
 // ---- C interface -------------------------------------------------------------------------------------
 struct RefCtx {
@@ -190,6 +193,28 @@ void* ref_create(int width, int height, const RbSceneDesc* sd) {
   c->frame.assign((size_t)width * height, glm::vec3{0});
   Utils::generator.seed(123);  // P/utils.cpp:175
   return c;
+}
+
+// Material::set_texture with Texture objects whose members are filled from the RbTexture arrays (what the constructor
+// stores after FreeImage_ConvertToRawBits), configured like ModelLoader::TextureProxy does: BILINEAR, REPEAT
+void ref_set_textures(void* h, const RbTexture* textures, uint32_t n_textures, const RbMaterialTextures* per_material, uint32_t n_materials) {
+  RefCtx* c = (RefCtx*)h;
+  std::vector<Texture*> tex(n_textures);
+  for (uint32_t t = 0; t < n_textures; ++t) {
+    Texture* T = new Texture("", BILINEAR, REPEAT);
+    T->width_ = textures[t].width, T->height_ = textures[t].height;
+    T->scan_width_ = textures[t].scan_width, T->pixel_size_ = textures[t].pixel_size;
+    T->data_ = new BYTE[(size_t)T->scan_width_ * T->height_];
+    memcpy(T->data_, textures[t].data, (size_t)T->scan_width_ * T->height_);
+    tex[t] = T;
+  }
+  const std::vector<Material*>& mats = c->scene->materials;
+  for (uint32_t m = 0; m < n_materials && m < mats.size(); ++m) {
+    const RbMaterialTextures& s = per_material[m];
+    if (s.diffuse >= 0) mats[m]->set_texture(Material::kDiffuseMapSlot, tex[s.diffuse]);
+    if (s.specular >= 0) mats[m]->set_texture(Material::kSpecularMapSlot, tex[s.specular]);
+    if (s.shininess >= 0) mats[m]->set_texture(Material::kShininessMapSlot, tex[s.shininess]);
+  }
 }
 
 void ref_set_params(void*, const RbParams* p) {

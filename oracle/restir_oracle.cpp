@@ -149,6 +149,7 @@ struct Tri {
   V3 p0, p1, p2;
   V3 n0, n1, n2;
   V3 e1, e2;
+  float uv[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // attribute slot 1 (P/ModelLoader.cpp:282-283)
   uint32_t geom, prim, material;
   int emissive_id;  // running id over emissive triangles (P/ModelLoader.cpp:255-257,301-306), -1 if none
   float area;       // Triangle ctor, P/triangle.cpp:13-16
@@ -198,6 +199,13 @@ static inline bool tri_test(const V3& o, const V3& d, const Tri& T, float tnear,
 struct Scene {
   std::vector<Tri> tris;
   std::vector<RbMaterial> mats;
+  // textured materials (rb_set_textures seam): Texture's members (P/Texture.h:44-48) + Material::textures_ slots
+  struct Tex {
+    int width = 0, height = 0, scan_width = 0, pixel_size = 0;
+    std::vector<unsigned char> data;
+  };
+  std::vector<Tex> textures;
+  std::vector<RbMaterialTextures> mat_tex;  // empty = untextured
   std::vector<int> emissive;  // TriangleCDF::tris (indices into tris)
   // TriangleCDF, P/TriangleCDF.cpp:8-34
   float totalSurface = 0;
@@ -629,6 +637,7 @@ struct Oracle {
     float dst = FLT_MAX;
     uint32_t hitTriId = 0;
     int tri = -1;
+    float uv[2] = {0, 0};
   };
   // Intersection::intersectEmbree + getGeometryAttributes, :8-41, 85-113 (untextured: no normal map)
   HitInfo intersect(const V3& org, const V3& dir, float tnear, float tfar) {
@@ -643,6 +652,9 @@ struct Oracle {
       n = normalize(n);
       if (dot(-dir, n) <= 0.0f) n = n * -1.0f;
       h.normal = n;
+      // rtcInterpolate0 of attribute slot 1 (P/Intersection.h:99-100), same contract as the normal
+      h.uv[0] = T.uv[0][0] * w + T.uv[1][0] * hit.u + T.uv[2][0] * hit.v;
+      h.uv[1] = T.uv[0][1] * w + T.uv[1][1] * hit.u + T.uv[2][1] * hit.v;
       h.didHit = true;
       h.hitPoint = org + dir * hit.t;
       h.dst = hit.t;
@@ -780,6 +792,30 @@ struct Oracle {
   }
 
   // ---- passes ---------------------------------------------------------------
+  // Texture::get_texel(x, y), REPEAT, P/Texture.cpp:72-107
+  static V3 texel(const Scene::Tex& T, int x, int y) {
+    int c_x = std::abs(x % T.width), c_y = std::abs(y % T.height);
+    const int offset = c_y * T.scan_width + c_x * T.pixel_size;
+    if (T.pixel_size > 4) {
+      float f[3];
+      memcpy(f, T.data.data() + offset, 12);
+      return {f[0], f[1], f[2]};
+    }
+    const float b = T.data[offset] / 255.0f, g = T.data[offset + 1] / 255.0f, r = T.data[offset + 2] / 255.0f;
+    return {r, g, b};
+  }
+  static V3 mix3(const V3& x, const V3& y, float a) { return x * (1.0f - a) + y * a; }  // glm::mix
+  // Texture::getTexelBilinear, :170-194
+  static V3 texSample(const Scene::Tex& T, const float* uv) {
+    const float pcx = uv[0] * T.width, pcy = (1 - uv[1]) * T.height;
+    const float flx = std::floor(pcx), fly = std::floor(pcy);
+    const float tx = pcx - flx, ty = pcy - fly;
+    V3 x0y0 = texel(T, flx, fly), x1y0 = texel(T, flx + 1, fly), x0y1 = texel(T, flx, fly + 1), x1y1 = texel(T, flx + 1, fly + 1);
+    V3 x1 = mix3(x0y0, x1y0, tx);
+    V3 x2 = mix3(x0y1, x1y1, tx);
+    return mix3(x1, x2, ty);
+  }
+
   // ReSTIRIntegrator::gBufferFillPass, :213-234
   void gBufferFillPass(int x, int y) {
     Rng rng = rngFor(PASS_GBUF, 0, x, y);
@@ -798,6 +834,15 @@ struct Oracle {
       e.specularColor = {m.specular[0], m.specular[1], m.specular[2]};
       e.emission = {m.emission[0], m.emission[1], m.emission[2]};
       e.shininess = m.shininess;
+      if (!scene.mat_tex.empty()) {  // Material::getDiffuseColor / getSpecularColor / getShininess, P/material.cpp:105-134
+        const RbMaterialTextures& sl = scene.mat_tex[T.material];
+        if (sl.diffuse >= 0) e.diffuseColor = texSample(scene.textures[sl.diffuse], hi.uv);
+        if (sl.specular >= 0) e.specularColor = texSample(scene.textures[sl.specular], hi.uv);
+        if (sl.shininess >= 0) {
+          V3 tx = texSample(scene.textures[sl.shininess], hi.uv);
+          e.shininess = 2.0f / (tx.x * tx.x) - 2.0f;
+        }
+      }
       e.geomID = T.geom;
       e.primID = T.prim;
       if (cache_iim && !emissive(e.emission) && (e.materialType == RB_MAT_PHONG || e.materialType == RB_MAT_DIELECTRIC))
@@ -1363,6 +1408,8 @@ int orc_upload_scene(void* h, const RbSceneDesc* sd) {
   S.tris.clear();
   S.emissive.clear();
   S.mats.assign(sd->materials, sd->materials + sd->n_materials);
+  S.textures.clear();
+  S.mat_tex.clear();
   int triIdCtr = 0;
   for (uint32_t s = 0; s < sd->n_surfaces; ++s) {
     const RbSurface& sf = sd->surfaces[s];
@@ -1379,6 +1426,10 @@ int orc_upload_scene(void* h, const RbSceneDesc* sd) {
       T.n0 = {n[0], n[1], n[2]};
       T.n1 = {n[3], n[4], n[5]};
       T.n2 = {n[6], n[7], n[8]};
+      if (sf.uv) {
+        const float* w = sf.uv + 6 * (size_t)i;
+        for (int k = 0; k < 3; ++k) T.uv[k][0] = w[2 * k], T.uv[k][1] = w[2 * k + 1];
+      }
       T.e1 = T.p1 - T.p0;
       T.e2 = T.p2 - T.p0;
       T.geom = s;
@@ -1396,6 +1447,22 @@ int orc_upload_scene(void* h, const RbSceneDesc* sd) {
   S.buildLights();
   if (S.tracer == 1) S.buildBvh();
   o->have_scene = true;
+  return 0;
+}
+
+int orc_set_textures(void* h, const RbTexture* textures, uint32_t n_textures, const RbMaterialTextures* per_material, uint32_t n_materials) {
+  Oracle* o = (Oracle*)h;
+  Scene& S = o->scene;
+  if (n_materials != S.mats.size()) return -1;
+  S.textures.resize(n_textures);
+  for (uint32_t t = 0; t < n_textures; ++t) {
+    const RbTexture& T = textures[t];
+    S.textures[t].width = T.width, S.textures[t].height = T.height;
+    S.textures[t].scan_width = T.scan_width, S.textures[t].pixel_size = T.pixel_size;
+    const unsigned char* d = (const unsigned char*)T.data;
+    S.textures[t].data.assign(d, d + (size_t)T.scan_width * T.height);
+  }
+  S.mat_tex.assign(per_material, per_material + n_materials);
   return 0;
 }
 

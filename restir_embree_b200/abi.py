@@ -48,6 +48,35 @@ class RbSurface(C.Structure):
                 ("normal", C.POINTER(C.c_float)), ("uv", C.POINTER(C.c_float)), ("tangent", C.POINTER(C.c_float))]
 
 
+class RbTexture(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("scan_width", C.c_int32), ("pixel_size", C.c_int32),
+                ("data", C.c_void_p)]
+
+
+class RbMaterialTextures(C.Structure):
+    _fields_ = [("diffuse", C.c_int32), ("specular", C.c_int32), ("shininess", C.c_int32), ("normal", C.c_int32)]
+
+
+def texture_tables(textures, slots, n_materials):
+    """textures: list of numpy arrays [h, w, 3|4] uint8 (B,G,R[,A] as FreeImage delivers them) or float32 (R,G,B[,A]);
+    slots: {material index: dict(diffuse=i, specular=i, shininess=i)}. Returns (RbTexture[], n, RbMaterialTextures[], keep)."""
+    import numpy as _np
+    keep = [_np.ascontiguousarray(t) for t in textures]
+    tex = (RbTexture * max(len(keep), 1))()
+    for i, a in enumerate(keep):
+        assert a.ndim == 3 and a.dtype in (_np.uint8, _np.float32) and a.shape[2] in (3, 4)
+        tex[i].height, tex[i].width = a.shape[0], a.shape[1]
+        tex[i].pixel_size = a.shape[2] * a.dtype.itemsize
+        tex[i].scan_width = a.strides[0]
+        tex[i].data = a.ctypes.data
+    per = (RbMaterialTextures * n_materials)()
+    for m in range(n_materials):
+        d = slots.get(m, {})
+        per[m].diffuse, per[m].specular = d.get("diffuse", -1), d.get("specular", -1)
+        per[m].shininess, per[m].normal = d.get("shininess", -1), d.get("normal", -1)
+    return tex, len(keep), per, keep
+
+
 class RbSceneDesc(C.Structure):
     _fields_ = [("n_surfaces", C.c_uint32), ("surfaces", C.POINTER(RbSurface)), ("n_materials", C.c_uint32),
                 ("materials", C.POINTER(RbMaterial))]
@@ -146,7 +175,7 @@ assert HIT_DTYPE.itemsize == C.sizeof(RbHit) == 20
 # Every symbol include/restir_b200.h declares (checked by tests/test_abi.py).
 EXPORTED_SYMBOLS = [
     "rb_abi_version", "rb_last_error", "rb_default_params", "rb_create", "rb_destroy", "rb_upload_scene",
-    "rb_set_params", "rb_render_frame", "rb_render_frame_device", "rb_render_mis_frame", "rb_readback", "rb_synchronize", "rb_timer_begin", "rb_timer_end",
+    "rb_set_params", "rb_set_textures", "rb_render_frame", "rb_render_frame_device", "rb_render_mis_frame", "rb_readback", "rb_synchronize", "rb_timer_begin", "rb_timer_end",
     "rb_trace_closest",
     "rb_trace_occluded", "rb_trace_closest_device", "rb_trace_occluded_device", "rb_scene_stats", "rb_comm_init",
     "rb_comm_unique_id", "rb_comm_transport", "rb_debug_balance_step", "rb_obj_load", "rb_obj_scene_desc",
@@ -174,12 +203,17 @@ class SceneArrays:
                                    emission=tuple(map(float, emission)), shininess=float(shininess), ior=float(ior)))
         return len(self.materials) - 1
 
-    def add_surface(self, pos, normal, material):
+    def add_surface(self, pos, normal, material, uv=None):
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3, 3)
         normal = np.ascontiguousarray(normal, dtype=np.float32).reshape(-1, 3, 3)
         assert pos.shape == normal.shape and pos.shape[0] > 0
         assert 0 <= material < len(self.materials)
         self.surfaces.append((pos, normal, int(material)))
+        if uv is not None:  # texture coordinates [n, 3, 2] (attribute slot 1 of the reference's Embree geometry)
+            uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 3, 2)
+            assert uv.shape[0] == pos.shape[0]
+            self.uvs = getattr(self, "uvs", {})
+            self.uvs[len(self.surfaces) - 1] = uv
         return len(self.surfaces) - 1
 
     @property
@@ -207,7 +241,8 @@ class SceneArrays:
             surfs[i].material = mat
             surfs[i].pos = fptr(pos)
             surfs[i].normal = fptr(nrm)
-            surfs[i].uv = None
+            uv = getattr(self, "uvs", {}).get(i)
+            surfs[i].uv = fptr(uv) if uv is not None else None
             surfs[i].tangent = None
         d = RbSceneDesc()
         d.n_surfaces = len(self.surfaces)

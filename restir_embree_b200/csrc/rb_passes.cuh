@@ -85,6 +85,7 @@ RB_HD SurfaceHit no_hit() {
   h.tri = h.geomID = h.primID = 0xFFFFFFFFu;
   h.material = 0;
   h.emissiveId = -1;
+  h.tex_u = h.tex_v = 0.0f;
   return h;
 }
 // reserve one queue slot; on the device the atomic is aggregated over the currently converged lanes
@@ -458,6 +459,15 @@ RB_HD GElem gbuffer_from_hit(const FrameCtx& fc, const CamState& cam, const Surf
     e.specular = xyz(m1);
     e.emission = xyz(m2);
     e.shininess = m0.w;
+    if (fc.sc.mat_tex != nullptr) {  // Material::getDiffuseColor / getSpecularColor / getShininess, P/material.cpp:105-134
+      const I4 slots = fc.sc.mat_tex[h.material];
+      if (slots.x >= 0) e.diffuse = tex_sample(fc.sc.tex[slots.x], h.tex_u, h.tex_v);
+      if (slots.y >= 0) e.specular = tex_sample(fc.sc.tex[slots.y], h.tex_u, h.tex_v);
+      if (slots.z >= 0) {  // roughness -> shininess
+        const V3 texel = tex_sample(fc.sc.tex[slots.z], h.tex_u, h.tex_v);
+        e.shininess = 2.0f / (texel.x * texel.x) - 2.0f;
+      }
+    }
     *geomID = h.geomID;
     *primID = h.primID;
   } else {

@@ -35,6 +35,7 @@ namespace rb {
 #define RB_NODE_F4 6  // 16-byte records per node (96 B)
 #define RB_STACK_MAX 48  // >= 2 * tree depth + 2: a node visit pushes at most a node group and a triangle group
 
+struct I4;
 struct SceneDev {
   // geometry
   const F4* node8;        // [RB_NODE_F4 * n_nodes]
@@ -58,6 +59,18 @@ struct SceneDev {
   const F4* em_node8;
   const F4* em_tri_isect;
   uint32_t em_n_nodes;
+  // textured materials (rb_set_textures): per-triangle texture coordinates, texture table, per-material slots
+  const F4* tri_uv;     // [2 * n_tris] scene order: {u0,v0,u1,v1} {u2,v2,0,0}; null = no surface carries uv
+  const struct TexDev* tex;  // [n_tex]
+  const I4* mat_tex;    // [n_mat]: {diffuse, specular, shininess, normal} texture index or -1; null = untextured scene
+};
+struct I4 {
+  int x, y, z, w;
+};
+// Texture's members, P/Texture.h:44-48
+struct TexDev {
+  const unsigned char* data;
+  int width, height, scan_width, pixel_size;
 };
 
 struct HitRec {
@@ -330,9 +343,37 @@ RB_HD bool test_occlusion(const SceneDev& sc, const V3& from, const V3& to, floa
 
 // Intersection::intersectEmbree + getGeometryAttributes, :8-41, 85-113, for untextured materials:
 // interpolated normalised shading normal flipped to face the ray, hit point = org + dir * t.
+// Texture::get_texel(x, y) with REPEAT (P/Texture.cpp:72-107): abs(x % w), 8-bit B,G,R / 255 or float R,G,B
+RB_HD V3 tex_texel(const TexDev& T, int x, int y) {
+  int cx = x % T.width, cy = y % T.height;
+  cx = cx < 0 ? -cx : cx;
+  cy = cy < 0 ? -cy : cy;
+  const unsigned char* p = T.data + (size_t)cy * T.scan_width + (size_t)cx * T.pixel_size;
+  if (T.pixel_size > 4) {
+    const float* f = reinterpret_cast<const float*>(p);
+    return v3(f[0], f[1], f[2]);
+  }
+  const float b = (float)p[0] / 255.0f, g = (float)p[1] / 255.0f, r = (float)p[2] / 255.0f;
+  return v3(r, g, b);
+}
+// Texture::getTexelBilinear (:170-194): pixel = (u * w, (1 - v) * h); glm::mix(a, b, t) = a * (1 - t) + b * t
+RB_HD V3 tex_sample(const TexDev& T, float u, float v) {
+  const float px = u * (float)T.width, py = (1.0f - v) * (float)T.height;
+  const float fx = floorf(px), fy = floorf(py);
+  const float tx = px - fx, ty = py - fy;
+  const V3 x0y0 = tex_texel(T, (int)fx, (int)fy);
+  const V3 x1y0 = tex_texel(T, (int)(fx + 1.0f), (int)fy);
+  const V3 x0y1 = tex_texel(T, (int)fx, (int)(fy + 1.0f));
+  const V3 x1y1 = tex_texel(T, (int)(fx + 1.0f), (int)(fy + 1.0f));
+  const V3 x1 = x0y0 * (1.0f - tx) + x1y0 * tx;
+  const V3 x2 = x0y1 * (1.0f - tx) + x1y1 * tx;
+  return x1 * (1.0f - ty) + x2 * ty;
+}
+
 struct SurfaceHit {
   bool didHit;
   V3 normal, hitPoint;
+  float tex_u, tex_v;  // rtcInterpolate0 of attribute slot 1 (P/Intersection.h:99-100); 0 when the scene has no uv
   float t;
   uint32_t tri, geomID, primID, material;
   int emissiveId;
@@ -346,6 +387,7 @@ RB_HD SurfaceHit surface_from_hit(const SceneDev& sc, const V3& org, const V3& d
   h.tri = h.geomID = h.primID = 0xFFFFFFFFu;
   h.material = 0;
   h.emissiveId = -1;
+  h.tex_u = h.tex_v = 0.0f;
   if (r.tri == 0xFFFFFFFFu) return h;
   const F4* np = sc.tri_normals + 3 * (size_t)r.tri;
   const F4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
@@ -354,6 +396,11 @@ RB_HD SurfaceHit surface_from_hit(const SceneDev& sc, const V3& org, const V3& d
   V3 n = n0 * w + n1 * r.u + n2 * r.v;  // rtcInterpolate0 of attribute slot 0
   n = normalize(n);
   if (dot(-dir, n) <= 0.0f) n = n * -1.0f;
+  if (sc.tri_uv != nullptr) {  // same interpolation contract as the normal: w * a0 + u * a1 + v * a2
+    const F4 q0 = ldg4(sc.tri_uv + 2 * (size_t)r.tri), q1 = ldg4(sc.tri_uv + 2 * (size_t)r.tri + 1);
+    h.tex_u = q0.x * w + q0.z * r.u + q1.x * r.v;
+    h.tex_v = q0.y * w + q0.w * r.u + q1.y * r.v;
+  }
   const U4 info = sc.tri_info[r.tri];
   h.didHit = true;
   h.normal = n;

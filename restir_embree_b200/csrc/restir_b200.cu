@@ -469,6 +469,9 @@ struct RbContext {
   // scene
   bool haveScene = false;
   bool hasDielectric = false;  // a material the N2 estimator does not cover
+  F4* sceneUv = nullptr;       // per-triangle texture coordinates (owned by sceneAllocs), null = none uploaded
+  uint32_t nMaterials = 0;
+  std::vector<void*> texAllocs;  // rb_set_textures
   SceneDev sc{};
   std::vector<void*> sceneAllocs;
   RbSceneStats stats{};
@@ -1062,6 +1065,7 @@ void rb_destroy(RbHandle h) {
   }
   free_list(h->allocs);
   free_list(h->sceneAllocs);
+  free_list(h->texAllocs);
   if (h->evCreated) {
     for (auto& ev : h->ev) cudaEventDestroy(ev);
     for (auto& ev : h->fev) cudaEventDestroy(ev);
@@ -1264,6 +1268,7 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
   RB_CUDA(cudaSetDevice(h->info.device));
   RB_CUDA(cudaStreamSynchronize(h->stream));
   free_list(h->sceneAllocs);
+  free_list(h->texAllocs);
   h->haveScene = false;
   h->havePrev = false;
 
@@ -1318,6 +1323,13 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     RB_CUDA(up(d_ap, alias_prob.data(), NL * 4));
     RB_CUDA(up(d_ai, alias_idx.data(), NL * 4));
     RB_CUDA(up(d_pair, hs.alias_pair.data(), NL * 8));
+    F4* d_uv = nullptr;
+    if (!hs.uv.empty()) {
+      RB_TRY(dev_alloc(h, &d_uv, hs.uv.size(), h->sceneAllocs));
+      RB_CUDA(up(d_uv, hs.uv.data(), hs.uv.size() * 16));
+    }
+    h->sceneUv = d_uv;
+    h->nMaterials = sd->n_materials;
     RB_CUDA(cudaStreamSynchronize(h->stream));
     F4 *node8 = nullptr, *tri_isect = nullptr;
     uint32_t n_nodes = 0, depth = 0;
@@ -1361,6 +1373,9 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     sc.em_node8 = em_node8;
     sc.em_tri_isect = em_tri_isect;
     sc.em_n_nodes = em_nodes;
+    sc.tri_uv = h->sceneUv;
+    sc.tex = nullptr;  // a new scene drops the textures (rb_set_textures)
+    sc.mat_tex = nullptr;
     RbSceneStats& st = h->stats;
     memset(&st, 0, sizeof(st));
     st.n_triangles = (uint32_t)n;
@@ -1386,6 +1401,75 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     return rc;
   }
   h->haveScene = true;
+  return RB_OK;
+}
+
+// Textured materials: texel arrays and per-material slots; see include/restir_b200.h
+int rb_set_textures(RbHandle h, const RbTexture* textures, uint32_t n_textures, const RbMaterialTextures* per_material,
+                    uint32_t n_materials) {
+  if (!h || (n_textures && !textures) || !per_material) return RB_ERR_INVALID_ARGUMENT;
+  if (!h->haveScene) {
+    h->err = "rb_set_textures: no scene uploaded";
+    return RB_ERR_NO_SCENE;
+  }
+  if (n_materials != h->nMaterials) {
+    h->err = "rb_set_textures: one RbMaterialTextures per material of the uploaded scene is required";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  bool any = false;
+  for (uint32_t m = 0; m < n_materials; ++m) {
+    const int32_t s[4] = {per_material[m].diffuse, per_material[m].specular, per_material[m].shininess, per_material[m].normal};
+    for (int k = 0; k < 4; ++k) {
+      if (s[k] >= (int32_t)n_textures || s[k] < -1) {
+        h->err = "rb_set_textures: texture index out of range";
+        return RB_ERR_INVALID_ARGUMENT;
+      }
+      any = any || s[k] >= 0;
+    }
+    if (s[3] >= 0) {
+      h->err = "rb_set_textures: normal maps are not part of this ABI version";
+      return RB_ERR_UNSUPPORTED;
+    }
+  }
+  for (uint32_t t = 0; t < n_textures; ++t) {
+    const RbTexture& T = textures[t];
+    const bool fmt = T.pixel_size == 3 || T.pixel_size == 4 || T.pixel_size == 12 || T.pixel_size == 16;
+    if (T.width <= 0 || T.height <= 0 || !fmt || T.scan_width < T.width * T.pixel_size || !T.data) {
+      h->err = "rb_set_textures: bad texture " + std::to_string(t);
+      return RB_ERR_INVALID_ARGUMENT;
+    }
+  }
+  if (any && !h->sceneUv) {
+    h->err = "rb_set_textures: the uploaded scene carries no texture coordinates (RbSurface.uv)";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  RB_CUDA(cudaSetDevice(h->info.device));
+  RB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->fstream) RB_CUDA(cudaStreamSynchronize(h->fstream));
+  free_list(h->texAllocs);
+  h->sc.tex = nullptr;
+  h->sc.mat_tex = nullptr;
+  if (!any) return RB_OK;
+  std::vector<TexDev> tab(n_textures);
+  for (uint32_t t = 0; t < n_textures; ++t) {
+    const RbTexture& T = textures[t];
+    unsigned char* d = nullptr;
+    const size_t bytes = (size_t)T.scan_width * T.height;
+    RB_TRY(dev_alloc(h, &d, bytes, h->texAllocs));
+    RB_CUDA(cudaMemcpyAsync(d, T.data, bytes, cudaMemcpyHostToDevice, h->stream));
+    tab[t] = TexDev{d, T.width, T.height, T.scan_width, T.pixel_size};
+  }
+  TexDev* d_tab = nullptr;
+  I4* d_slots = nullptr;
+  RB_TRY(dev_alloc(h, &d_tab, std::max<uint32_t>(n_textures, 1), h->texAllocs));
+  RB_TRY(dev_alloc(h, &d_slots, n_materials, h->texAllocs));
+  RB_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(TexDev), cudaMemcpyHostToDevice, h->stream));
+  static_assert(sizeof(RbMaterialTextures) == sizeof(I4), "slot record layout");
+  RB_CUDA(cudaMemcpyAsync(d_slots, per_material, n_materials * sizeof(I4), cudaMemcpyHostToDevice, h->stream));
+  RB_CUDA(cudaStreamSynchronize(h->stream));
+  h->sc.tex = d_tab;
+  h->sc.mat_tex = d_slots;
+  h->havePrev = false;  // the previous frame's G-buffer was made with other materials
   return RB_OK;
 }
 

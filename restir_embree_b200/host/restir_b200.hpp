@@ -195,6 +195,13 @@ class Renderer {
     check(rc, "rb_upload_scene");
   }
 
+  // Material::set_texture for the uploaded scene (P/material.h:79-84): the texel arrays of the host's Texture objects
+  // (width_, height_, scan_width_, pixel_size_, data_) and, per material, the texture index of each slot or -1
+  void setTextures(const std::vector<RbTexture>& textures, const std::vector<RbMaterialTextures>& perMaterial) {
+    check(rb_set_textures(h_, textures.data(), (uint32_t)textures.size(), perMaterial.data(), (uint32_t)perMaterial.size()),
+          "rb_set_textures");
+  }
+
   // SimpleGuiDX11::produceRestir: frame_data is width*height float3 (linear HDR), owned by the caller
   void produceRestir(const Camera& camera, uint32_t frameCtr, float* frame_data) {
     RbParams p = params.toAbi();

@@ -45,6 +45,7 @@ def load_library():
     L.rb_destroy.argtypes = [H]
     L.rb_upload_scene.argtypes = [H, C.POINTER(abi.RbSceneDesc)]
     L.rb_set_params.argtypes = [H, C.POINTER(abi.RbParams)]
+    L.rb_set_textures.argtypes = [H, C.POINTER(abi.RbTexture), C.c_uint32, C.POINTER(abi.RbMaterialTextures), C.c_uint32]
     L.rb_render_frame.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
     L.rb_render_frame_device.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
     L.rb_render_mis_frame.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
@@ -148,6 +149,12 @@ class Renderer:
     def set_params(self, p):
         self._check(self.L.rb_set_params(self.h, C.byref(p)), "rb_set_params")
         self.params = p
+
+    def set_textures(self, textures, slots, n_materials):
+        """Material::set_texture for the uploaded scene: `textures` = texel arrays ([h, w, 3|4] uint8 B,G,R[,A] or float32
+        R,G,B[,A]), `slots` = {material index: dict(diffuse=, specular=, shininess=)} (abi.texture_tables)."""
+        tex, n, per, keep = abi.texture_tables(textures, slots, n_materials)
+        self._check(self.L.rb_set_textures(self.h, tex, n, per, n_materials), "rb_set_textures")
 
     # -- frames -------------------------------------------------------------------------
     def render_frame(self, cam, frame_idx, out=None, want_timings=False, fetch=True):

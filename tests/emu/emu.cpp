@@ -59,6 +59,9 @@ struct Emu {
   std::vector<HitRec> hits;
   std::vector<U4> cand;
   bool shaded = false;
+  std::vector<TexDev> tex_tab;  // rb_set_textures mirror
+  std::vector<std::vector<unsigned char>> tex_data;
+  std::vector<I4> tex_slots;
   std::vector<RayQ> chain;
   uint32_t chain_count[2] = {0, 0};
   std::vector<uint32_t> deferred;
@@ -293,6 +296,10 @@ int emu_upload_scene(void* h, const RbSceneDesc* sd) {
   sc.em_node8 = E->em_node8.data();
   sc.em_tri_isect = E->em_tri_isect.data();
   sc.em_n_nodes = E->em_n_nodes;
+  sc.tri_uv = E->hs.uv.empty() ? nullptr : E->hs.uv.data();
+  sc.tex = nullptr;
+  sc.mat_tex = nullptr;
+  E->tex_tab.clear(), E->tex_data.clear(), E->tex_slots.clear();
   E->haveScene = true;
   E->havePrev = false;
   return 0;
@@ -542,6 +549,26 @@ int emu_frame_end(void* h, float* rgb_out) {
   E->havePrev = true;
   E->open = false;
   if (rgb_out) memcpy(rgb_out, E->frame.data(), E->frame.size() * sizeof(float));
+  return 0;
+}
+
+// textured materials: the tables rb_set_textures uploads, on the host
+int emu_set_textures(void* h, const RbTexture* textures, uint32_t n_textures, const RbMaterialTextures* per_material, uint32_t n_materials) {
+  Emu* E = (Emu*)h;
+  if (!E->haveScene || n_materials * 3 != E->hs.mat.size()) return -1;
+  E->tex_tab.resize(n_textures);
+  E->tex_data.resize(n_textures);
+  for (uint32_t t = 0; t < n_textures; ++t) {
+    const RbTexture& T = textures[t];
+    const unsigned char* d = (const unsigned char*)T.data;
+    E->tex_data[t].assign(d, d + (size_t)T.scan_width * T.height);
+    E->tex_tab[t] = TexDev{E->tex_data[t].data(), T.width, T.height, T.scan_width, T.pixel_size};
+  }
+  E->tex_slots.resize(n_materials);
+  memcpy(E->tex_slots.data(), per_material, n_materials * sizeof(I4));
+  E->sc.tex = E->tex_tab.data();
+  E->sc.mat_tex = E->tex_slots.data();
+  E->havePrev = false;
   return 0;
 }
 

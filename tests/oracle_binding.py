@@ -39,6 +39,7 @@ def lib():
         L.orc_upload_scene.argtypes = [C.c_void_p, C.POINTER(abi.RbSceneDesc)]
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(abi.RbParams)]
         L.orc_render_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_set_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.orc_temporal_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_render_mis_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_readback.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
@@ -126,6 +127,10 @@ class Oracle:
         rc = self.L.orc_render_mis_frame(self.h, C.byref(c), frame_idx, techniques, out.ctypes.data)
         assert rc == 0, rc
         return out
+
+    def set_textures(self, textures, slots, n_materials):
+        tex, n, per, keep = abi.texture_tables(textures, slots, n_materials)
+        assert self.L.orc_set_textures(self.h, tex, n, per, n_materials) == 0
 
     def temporal_stats(self, reset=True):
         """pixels per outcome of the temporal pass since the last reset: backward reprojection failed, depth test at the

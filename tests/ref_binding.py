@@ -30,6 +30,7 @@ def lib():
         R.ref_camera.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(abi.RbCamera)]
         R.ref_produce_restir.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_produce_mis.argtypes = [C.c_void_p, C.c_void_p]
+        R.ref_set_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         R.ref_reservoirs.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_gbuffer.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_seed.argtypes = [C.c_uint32]
@@ -73,6 +74,11 @@ class Reference:
         out = np.zeros((self.height, self.width, 3), dtype=np.float32)
         self.R.ref_produce_restir(self.h, out.ctypes.data)
         return out
+
+    def set_textures(self, textures, slots, n_materials):
+        """Material::set_texture with the reference's own Texture objects (P/Texture.cpp compiled in place)"""
+        tex, n, per, keep = abi.texture_tables(textures, slots, n_materials)
+        self.R.ref_set_textures(self.h, tex, n, per, n_materials)
 
     def produce_mis(self):
         """N2: Raytracer::get_pixel over the image with NEEPathIntegrator (DI only) + the reference's DirectMISIntegrator"""
