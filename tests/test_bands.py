@@ -236,7 +236,7 @@ def _balance(pairs, height):
     return list(out)
 
 
-def test_balancer_partition_rule():
+def test_balancer_partition_rule(built):
     """The host arithmetic of the band balancer (every rank runs it on the same all-gathered numbers): equal costs keep
     the bands, an expensive band shrinks, a boundary moves at most 15 rows per period, repeated steps converge to the
     equal-cost partition of a piecewise-constant cost profile, thin bands are left alone."""

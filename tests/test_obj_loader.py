@@ -27,7 +27,7 @@ def srgb_expand(u):  # Utils::expand, P/utils.cpp:209-218
     return np.float32(np.power(np.float32((u + np.float32(0.055)) / np.float32(1.055)), np.float32(2.4)))
 
 
-def test_materials_follow_the_reference_conventions():
+def test_materials_follow_the_reference_conventions(built):
     sc = load_obj_scene(OBJ)
     names = sc.meta["material_names"]
     assert names == ["floor", "matte red", "LAMP_EMITTER_mat", "untouched_defaults"]  # MTL order, names with blanks
@@ -48,7 +48,7 @@ def test_materials_follow_the_reference_conventions():
     assert np.allclose(raw.materials[0]["diffuse"], [0.735357] * 3)
 
 
-def test_geometry_one_surface_per_material_fan_triangulation_flat_normals():
+def test_geometry_one_surface_per_material_fan_triangulation_flat_normals(built):
     sc = load_obj_scene(OBJ)
     assert [s[2] for s in sc.surfaces] == [0, 1, 2]  # order of first use; "untouched_defaults" is never used
     floor, red, lamp = (s[0] for s in sc.surfaces)
@@ -62,7 +62,7 @@ def test_geometry_one_surface_per_material_fan_triangulation_flat_normals():
     assert np.allclose(sc.surfaces[2][1], [0, 0, -1])  # lamp faces down (v//vn form)
 
 
-def test_errors_are_reported_not_thrown_across_the_abi(tmp_path):
+def test_errors_are_reported_not_thrown_across_the_abi(built, tmp_path):
     with pytest.raises(RestirError, match="cannot open"):
         load_obj_scene(os.path.join(DATA, "missing.obj"))
     p = tmp_path / "nomat.obj"
@@ -77,7 +77,7 @@ def test_errors_are_reported_not_thrown_across_the_abi(tmp_path):
         load_obj_scene(str(p))
 
 
-def test_loaded_scene_renders_identically_in_kernel_bodies_and_oracle():
+def test_loaded_scene_renders_identically_in_kernel_bodies_and_oracle(built):
     sc = load_obj_scene(OBJ)
     w, h = 80, 60
     p = abi.default_params(M_Area=4, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1, lightSampler=abi.LS_ALIAS)
