@@ -294,8 +294,12 @@ int rb_scene_stats(RbHandle h, RbSceneStats* out);
  * Texture::get_texel(uv) as ModelLoader::TextureProxy configures it (BILINEAR, REPEAT; P/Texture.cpp:72-107,170-194):
  * pixel = (u * w, (1 - v) * h), four get_texel(x, y) with abs(x % w), glm::mix in x then y. The shininess map is a
  * roughness map: n = 2 / r^2 - 2 (P/material.cpp:124-131). Call after rb_upload_scene (whose surfaces must carry uv);
- * a new rb_upload_scene drops the textures. Data is copied. Normal maps (kNormalMapSlot) are not part of this version:
- * `normal` must be -1. */
+ * a new rb_upload_scene drops the textures. Data is copied.
+ * Normal maps (Material::kNormalMapSlot): where the hit's material has one, EVERY closest-hit query of the path (G-buffer,
+ * BRDF-sampled candidates, rb_render_mis_frame) replaces the interpolated normal — already flipped towards the ray — by
+ * mat3(T, B, n) * (texel * 2 - 1) with T = normalize(tangent - dot(tangent, n) * n), B = normalize(cross(n, T)) and the
+ * tangent interpolated from RbSurface.tangent, exactly Intersection::intersectEmbree (P/Intersection.h:25-39): no
+ * re-normalisation, no second flip. A scene uploaded without tangents cannot take a normal map (invalid argument). */
 typedef struct RbTexture {
   int32_t width, height;
   int32_t scan_width; /* bytes per row */

@@ -51,6 +51,7 @@ struct FakeGeometry {
   std::vector<glm::vec3> normals;  // attribute slot 0, 3 per triangle
   std::vector<glm::vec2> uvs;      // attribute slot 1 (empty: zero)
   std::vector<float> ids;          // attribute slot 2
+  std::vector<glm::vec3> tangents; // attribute slot 3 (empty: zero)
 };
 struct FakeScene {
   void* tracer = nullptr;  // oracle handle
@@ -92,6 +93,9 @@ void rtcInterpolate(const struct RTCInterpolateArguments* a) {
     a->P[0] = t.x, a->P[1] = t.y;
   } else if (a->bufferSlot == 2) {
     a->P[0] = g->ids[3 * a->primID] * w + g->ids[3 * a->primID + 1] * u + g->ids[3 * a->primID + 2] * v;
+  } else if (a->bufferSlot == 3 && !g->tangents.empty()) {  // tangent (read by normal-mapped materials), same contract
+    const glm::vec3 t = g->tangents[3 * a->primID] * w + g->tangents[3 * a->primID + 1] * u + g->tangents[3 * a->primID + 2] * v;
+    a->P[0] = t.x, a->P[1] = t.y, a->P[2] = t.z;
   } else {
     for (unsigned i = 0; i < a->valueCount; ++i) a->P[i] = 0.0f;  // uv, tangent: unused by untextured materials
   }
@@ -137,6 +141,10 @@ Scene::Scene(const char*, const RTCDevice&) {
         v[k] = Vertex(glm::vec3{p[0], p[1], p[2]}, glm::vec3{n[0], n[1], n[2]}, glm::vec3{0}, glm::vec3{0});
         g->normals.push_back(glm::vec3{n[0], n[1], n[2]});
         if (sf.uv) g->uvs.push_back(glm::vec2{sf.uv[6 * (size_t)i + 2 * k], sf.uv[6 * (size_t)i + 2 * k + 1]});
+        if (sf.tangent) {
+          const float* tg = sf.tangent + 9 * (size_t)i + 3 * k;
+          g->tangents.push_back(glm::vec3{tg[0], tg[1], tg[2]});
+        }
         g->ids.push_back(materials[sf.material]->isEmissive() ? static_cast<float>(triIdCtr) : 0.0f);
       }
       surface->get_triangle(i) = Triangle(v[0], v[1], v[2], surface);
@@ -214,6 +222,7 @@ void ref_set_textures(void* h, const RbTexture* textures, uint32_t n_textures, c
     if (s.diffuse >= 0) mats[m]->set_texture(Material::kDiffuseMapSlot, tex[s.diffuse]);
     if (s.specular >= 0) mats[m]->set_texture(Material::kSpecularMapSlot, tex[s.specular]);
     if (s.shininess >= 0) mats[m]->set_texture(Material::kShininessMapSlot, tex[s.shininess]);
+    if (s.normal >= 0) mats[m]->set_texture(Material::kNormalMapSlot, tex[s.normal]);
   }
 }
 

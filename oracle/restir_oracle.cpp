@@ -206,6 +206,7 @@ struct Scene {
   };
   std::vector<Tex> textures;
   std::vector<RbMaterialTextures> mat_tex;  // empty = untextured
+  std::vector<V3> tangents;  // [3 * n_tris] attribute slot 3 (P/ModelLoader.cpp:286-287), read by normal maps only; empty = none
   std::vector<int> emissive;  // TriangleCDF::tris (indices into tris)
   // TriangleCDF, P/TriangleCDF.cpp:8-34
   float totalSurface = 0;
@@ -639,7 +640,7 @@ struct Oracle {
     int tri = -1;
     float uv[2] = {0, 0};
   };
-  // Intersection::intersectEmbree + getGeometryAttributes, :8-41, 85-113 (untextured: no normal map)
+  // Intersection::intersectEmbree + getGeometryAttributes, :8-41, 85-113
   HitInfo intersect(const V3& org, const V3& dir, float tnear, float tfar) {
     HitInfo h;
     ctrs[thread_id()].closest++;
@@ -655,6 +656,18 @@ struct Oracle {
       // rtcInterpolate0 of attribute slot 1 (P/Intersection.h:99-100), same contract as the normal
       h.uv[0] = T.uv[0][0] * w + T.uv[1][0] * hit.u + T.uv[2][0] * hit.v;
       h.uv[1] = T.uv[0][1] * w + T.uv[1][1] * hit.u + T.uv[2][1] * hit.v;
+      // normal map (:25-39): TBN from the interpolated tangent (slot 3) and the flipped normal, texel * 2 - 1; the
+      // result is neither re-normalised nor flipped again
+      if (!scene.mat_tex.empty() && scene.mat_tex[T.material].normal >= 0 && !scene.tangents.empty()) {
+        const V3* tn = scene.tangents.data() + 3 * (size_t)hit.tri;
+        V3 tangent = tn[0] * w + tn[1] * hit.u + tn[2] * hit.v;
+        V3 Tt = tangent - dot(tangent, h.normal) * h.normal;
+        Tt = normalize(Tt);
+        V3 B = normalize(cross(h.normal, Tt));
+        V3 N = texSample(scene.textures[scene.mat_tex[T.material].normal], h.uv) * 2.0f - V3{1.0f, 1.0f, 1.0f};
+        const V3 n0 = h.normal;  // glm mat3 * vec3: (m0 * x + m1 * y) + m2 * z per component
+        h.normal = {Tt.x * N.x + B.x * N.y + n0.x * N.z, Tt.y * N.x + B.y * N.y + n0.y * N.z, Tt.z * N.x + B.z * N.y + n0.z * N.z};
+      }
       h.didHit = true;
       h.hitPoint = org + dir * hit.t;
       h.dst = hit.t;
@@ -1407,6 +1420,9 @@ int orc_upload_scene(void* h, const RbSceneDesc* sd) {
   Scene& S = o->scene;
   S.tris.clear();
   S.emissive.clear();
+  S.tangents.clear();
+  bool any_tan = false;
+  for (uint32_t s = 0; s < sd->n_surfaces; ++s) any_tan = any_tan || (sd->surfaces[s].tangent && sd->surfaces[s].n_tris);
   S.mats.assign(sd->materials, sd->materials + sd->n_materials);
   S.textures.clear();
   S.mat_tex.clear();
@@ -1429,6 +1445,10 @@ int orc_upload_scene(void* h, const RbSceneDesc* sd) {
       if (sf.uv) {
         const float* w = sf.uv + 6 * (size_t)i;
         for (int k = 0; k < 3; ++k) T.uv[k][0] = w[2 * k], T.uv[k][1] = w[2 * k + 1];
+      }
+      if (any_tan) {
+        const float* w = sf.tangent ? sf.tangent + 9 * (size_t)i : nullptr;
+        for (int k = 0; k < 3; ++k) S.tangents.push_back(w ? V3{w[3 * k], w[3 * k + 1], w[3 * k + 2]} : V3{0, 0, 0});
       }
       T.e1 = T.p1 - T.p0;
       T.e2 = T.p2 - T.p0;

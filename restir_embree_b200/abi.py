@@ -203,7 +203,7 @@ class SceneArrays:
                                    emission=tuple(map(float, emission)), shininess=float(shininess), ior=float(ior)))
         return len(self.materials) - 1
 
-    def add_surface(self, pos, normal, material, uv=None):
+    def add_surface(self, pos, normal, material, uv=None, tangent=None):
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3, 3)
         normal = np.ascontiguousarray(normal, dtype=np.float32).reshape(-1, 3, 3)
         assert pos.shape == normal.shape and pos.shape[0] > 0
@@ -214,6 +214,11 @@ class SceneArrays:
             assert uv.shape[0] == pos.shape[0]
             self.uvs = getattr(self, "uvs", {})
             self.uvs[len(self.surfaces) - 1] = uv
+        if tangent is not None:  # per-vertex tangents [n, 3, 3] (attribute slot 3; read by normal-mapped materials)
+            tangent = np.ascontiguousarray(tangent, dtype=np.float32).reshape(-1, 3, 3)
+            assert tangent.shape == pos.shape
+            self.tangents = getattr(self, "tangents", {})
+            self.tangents[len(self.surfaces) - 1] = tangent
         return len(self.surfaces) - 1
 
     @property
@@ -243,7 +248,8 @@ class SceneArrays:
             surfs[i].normal = fptr(nrm)
             uv = getattr(self, "uvs", {}).get(i)
             surfs[i].uv = fptr(uv) if uv is not None else None
-            surfs[i].tangent = None
+            tg = getattr(self, "tangents", {}).get(i)
+            surfs[i].tangent = fptr(tg) if tg is not None else None
         d = RbSceneDesc()
         d.n_surfaces = len(self.surfaces)
         d.surfaces = surfs

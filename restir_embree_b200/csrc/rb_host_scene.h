@@ -19,6 +19,7 @@ struct HostScene {
   std::vector<float> pos;        // [n][9]
   std::vector<F4> nrm;           // [3n]
   std::vector<F4> uv;            // [2n]: {u0,v0,u1,v1} {u2,v2,0,0}; empty when no surface carries texture coordinates
+  std::vector<F4> tan;           // [3n] packed like nrm; empty when no surface carries tangents (normal maps only)
   std::vector<U4> info;          // [n]
   std::vector<F4> mat;           // [3 * n_mat]
   std::vector<uint32_t> emissive;
@@ -55,6 +56,10 @@ inline int flatten_scene(const RbSceneDesc* sd, HostScene& hs, std::string& err)
   for (uint32_t s = 0; s < sd->n_surfaces; ++s) any_uv = any_uv || (sd->surfaces[s].uv != nullptr && sd->surfaces[s].n_tris > 0);
   hs.uv.clear();
   if (any_uv) hs.uv.assign(2 * n, F4{0, 0, 0, 0});
+  bool any_tan = false;
+  for (uint32_t s = 0; s < sd->n_surfaces; ++s) any_tan = any_tan || (sd->surfaces[s].tangent != nullptr && sd->surfaces[s].n_tris > 0);
+  hs.tan.clear();
+  if (any_tan) hs.tan.assign(3 * n, F4{0, 0, 0, 0});
   info.assign(n, U4{0, 0, 0, 0});
   mat.assign(3 * (size_t)sd->n_materials, F4{0, 0, 0, 0});
   for (uint32_t m = 0; m < sd->n_materials; ++m) {
@@ -82,6 +87,12 @@ inline int flatten_scene(const RbSceneDesc* sd, HostScene& hs, std::string& err)
           const float* w = sf.uv + 6 * (size_t)i;
           hs.uv[2 * t + 0] = F4{w[0], w[1], w[2], w[3]};
           hs.uv[2 * t + 1] = F4{w[4], w[5], 0, 0};
+        }
+        if (any_tan && sf.tangent) {
+          const float* w = sf.tangent + 9 * (size_t)i;
+          hs.tan[3 * t + 0] = F4{w[0], w[1], w[2], w[3]};
+          hs.tan[3 * t + 1] = F4{w[4], w[5], w[6], w[7]};
+          hs.tan[3 * t + 2] = F4{w[8], 0, 0, 0};
         }
         int eid = -1;
         if (isEmissive) {

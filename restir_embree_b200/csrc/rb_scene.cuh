@@ -63,6 +63,10 @@ struct SceneDev {
   const F4* tri_uv;     // [2 * n_tris] scene order: {u0,v0,u1,v1} {u2,v2,0,0}; null = no surface carries uv
   const struct TexDev* tex;  // [n_tex]
   const I4* mat_tex;    // [n_mat]: {diffuse, specular, shininess, normal} texture index or -1; null = untextured scene
+  // normal maps (Material::kNormalMapSlot): per-vertex tangents, attribute slot 3 of the reference's Embree geometry
+  // (P/ModelLoader.cpp:286-287). Non-null ONLY while some material of the scene has a normal map, so that every other
+  // scene pays one uniform pointer test per hit.
+  const F4* tri_tan;    // [3 * n_tris] scene order, packed like tri_normals
 };
 struct I4 {
   int x, y, z, w;
@@ -341,8 +345,8 @@ RB_HD bool test_occlusion(const SceneDev& sc, const V3& from, const V3& to, floa
   return trace8<true>(sc, from, dir, FLT_MIN + tnearOffset, tfar, nullptr);
 }
 
-// Intersection::intersectEmbree + getGeometryAttributes, :8-41, 85-113, for untextured materials:
-// interpolated normalised shading normal flipped to face the ray, hit point = org + dir * t.
+// Intersection::intersectEmbree + getGeometryAttributes, :8-41, 85-113: interpolated normalised shading normal
+// flipped to face the ray, hit point = org + dir * t, texture coordinates, normal map (TBN) where the material has one.
 // Texture::get_texel(x, y) with REPEAT (P/Texture.cpp:72-107): abs(x % w), 8-bit B,G,R / 255 or float R,G,B
 RB_HD V3 tex_texel(const TexDev& T, int x, int y) {
   int cx = x % T.width, cy = y % T.height;
@@ -368,6 +372,26 @@ RB_HD V3 tex_sample(const TexDev& T, float u, float v) {
   const V3 x1 = x0y0 * (1.0f - tx) + x1y0 * tx;
   const V3 x2 = x0y1 * (1.0f - tx) + x1y1 * tx;
   return x1 * (1.0f - ty) + x2 * ty;
+}
+
+// Normal map, Intersection::intersectEmbree :25-39 (glm operation order: dot = (x+y)+z, normalize = v * inversesqrt(dot),
+// cross = (a.y*b.z - b.y*a.z, a.z*b.x - b.z*a.x, a.x*b.y - b.x*a.y), mat3 * vec3 = (m0*x + m1*y) + m2*z):
+//   T = normalize(tangent - dot(tangent, n) * n);  B = normalize(cross(n, T));  n' = mat3(T, B, n) * (texel * 2 - 1)
+// `n` is the interpolated normal AFTER the flip towards the ray; the tangent is the raw interpolation of slot 3; the
+// result is neither re-normalised nor flipped again. Out of line: the callers' register budget is that of the scenes
+// without normal maps.
+RB_HD_NOINLINE void apply_normal_map(const SceneDev& sc, uint32_t tri, int slot, float w, float u, float v, float tex_u,
+                                     float tex_v, V3* normal) {
+  const F4* tp = sc.tri_tan + 3 * (size_t)tri;
+  const F4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+  const V3 t0 = xyz(a), t1 = v3(a.w, b.x, b.y), t2 = v3(b.z, b.w, c.x);
+  const V3 tangent = t0 * w + t1 * u + t2 * v;  // rtcInterpolate0 of attribute slot 3 (P/Intersection.h:106-107)
+  const V3 n = *normal;
+  V3 T = tangent - n * dot(tangent, n);
+  T = normalize(T);
+  const V3 B = normalize(cross(n, T));
+  const V3 N = tex_sample(sc.tex[slot], tex_u, tex_v) * 2.0f - v3(1.0f);
+  *normal = v3(T.x * N.x + B.x * N.y + n.x * N.z, T.y * N.x + B.y * N.y + n.y * N.z, T.z * N.x + B.z * N.y + n.z * N.z);
 }
 
 struct SurfaceHit {
@@ -402,6 +426,10 @@ RB_HD SurfaceHit surface_from_hit(const SceneDev& sc, const V3& org, const V3& d
     h.tex_v = q0.y * w + q0.w * r.u + q1.y * r.v;
   }
   const U4 info = sc.tri_info[r.tri];
+  if (sc.tri_tan != nullptr) {  // some material of the scene has a normal map
+    const int slot = sc.mat_tex[info.z].w;
+    if (slot >= 0) apply_normal_map(sc, r.tri, slot, w, r.u, r.v, h.tex_u, h.tex_v, &n);
+  }
   h.didHit = true;
   h.normal = n;
   h.hitPoint = org + dir * r.t;

@@ -470,6 +470,7 @@ struct RbContext {
   bool haveScene = false;
   bool hasDielectric = false;  // a material the N2 estimator does not cover
   F4* sceneUv = nullptr;       // per-triangle texture coordinates (owned by sceneAllocs), null = none uploaded
+  F4* sceneTan = nullptr;      // per-triangle tangents (owned by sceneAllocs), null = none uploaded
   uint32_t nMaterials = 0;
   std::vector<void*> texAllocs;  // rb_set_textures
   SceneDev sc{};
@@ -1329,6 +1330,12 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
       RB_CUDA(up(d_uv, hs.uv.data(), hs.uv.size() * 16));
     }
     h->sceneUv = d_uv;
+    F4* d_tan = nullptr;
+    if (!hs.tan.empty()) {
+      RB_TRY(dev_alloc(h, &d_tan, hs.tan.size(), h->sceneAllocs));
+      RB_CUDA(up(d_tan, hs.tan.data(), hs.tan.size() * 16));
+    }
+    h->sceneTan = d_tan;
     h->nMaterials = sd->n_materials;
     RB_CUDA(cudaStreamSynchronize(h->stream));
     F4 *node8 = nullptr, *tri_isect = nullptr;
@@ -1376,6 +1383,7 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     sc.tri_uv = h->sceneUv;
     sc.tex = nullptr;  // a new scene drops the textures (rb_set_textures)
     sc.mat_tex = nullptr;
+    sc.tri_tan = nullptr;
     RbSceneStats& st = h->stats;
     memset(&st, 0, sizeof(st));
     st.n_triangles = (uint32_t)n;
@@ -1416,7 +1424,7 @@ int rb_set_textures(RbHandle h, const RbTexture* textures, uint32_t n_textures, 
     h->err = "rb_set_textures: one RbMaterialTextures per material of the uploaded scene is required";
     return RB_ERR_INVALID_ARGUMENT;
   }
-  bool any = false;
+  bool any = false, any_normal = false;
   for (uint32_t m = 0; m < n_materials; ++m) {
     const int32_t s[4] = {per_material[m].diffuse, per_material[m].specular, per_material[m].shininess, per_material[m].normal};
     for (int k = 0; k < 4; ++k) {
@@ -1426,10 +1434,7 @@ int rb_set_textures(RbHandle h, const RbTexture* textures, uint32_t n_textures, 
       }
       any = any || s[k] >= 0;
     }
-    if (s[3] >= 0) {
-      h->err = "rb_set_textures: normal maps are not part of this ABI version";
-      return RB_ERR_UNSUPPORTED;
-    }
+    any_normal = any_normal || s[3] >= 0;
   }
   for (uint32_t t = 0; t < n_textures; ++t) {
     const RbTexture& T = textures[t];
@@ -1443,12 +1448,17 @@ int rb_set_textures(RbHandle h, const RbTexture* textures, uint32_t n_textures, 
     h->err = "rb_set_textures: the uploaded scene carries no texture coordinates (RbSurface.uv)";
     return RB_ERR_INVALID_ARGUMENT;
   }
+  if (any_normal && !h->sceneTan) {
+    h->err = "rb_set_textures: normal maps need the per-vertex tangents of the uploaded scene (RbSurface.tangent)";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
   RB_CUDA(cudaSetDevice(h->info.device));
   RB_CUDA(cudaStreamSynchronize(h->stream));
   if (h->fstream) RB_CUDA(cudaStreamSynchronize(h->fstream));
   free_list(h->texAllocs);
   h->sc.tex = nullptr;
   h->sc.mat_tex = nullptr;
+  h->sc.tri_tan = nullptr;
   if (!any) return RB_OK;
   std::vector<TexDev> tab(n_textures);
   for (uint32_t t = 0; t < n_textures; ++t) {
@@ -1469,6 +1479,7 @@ int rb_set_textures(RbHandle h, const RbTexture* textures, uint32_t n_textures, 
   RB_CUDA(cudaStreamSynchronize(h->stream));
   h->sc.tex = d_tab;
   h->sc.mat_tex = d_slots;
+  h->sc.tri_tan = any_normal ? h->sceneTan : nullptr;
   h->havePrev = false;  // the previous frame's G-buffer was made with other materials
   return RB_OK;
 }

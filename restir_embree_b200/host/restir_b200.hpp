@@ -139,6 +139,8 @@ struct Material {
 struct Surface {
   std::vector<float> positions;  // 9 floats per triangle
   std::vector<float> normals;    // 9 floats per triangle
+  std::vector<float> uvs;        // 6 floats per triangle or empty (Vertex::texture_coords, P/vertex.h)
+  std::vector<float> tangents;   // 9 floats per triangle or empty (Vertex::tangent; read by normal-mapped materials)
   uint32_t material{0};
   size_t no_triangles() const { return positions.size() / 9; }
 };
@@ -176,7 +178,9 @@ class Renderer {
       const Surface& a = scene.surfaces[i];
       s[i].n_tris = (uint32_t)a.no_triangles();
       s[i].material = a.material;
-      s[i].pos = a.positions.data(), s[i].normal = a.normals.data(), s[i].uv = nullptr, s[i].tangent = nullptr;
+      s[i].pos = a.positions.data(), s[i].normal = a.normals.data();
+      s[i].uv = a.uvs.size() == 6 * a.no_triangles() && !a.uvs.empty() ? a.uvs.data() : nullptr;
+      s[i].tangent = a.tangents.size() == 9 * a.no_triangles() && !a.tangents.empty() ? a.tangents.data() : nullptr;
     }
     RbSceneDesc d{(uint32_t)s.size(), s.data(), (uint32_t)m.size(), m.data()};
     check(rb_upload_scene(h_, &d), "rb_upload_scene");

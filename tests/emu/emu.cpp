@@ -299,6 +299,7 @@ int emu_upload_scene(void* h, const RbSceneDesc* sd) {
   sc.tri_uv = E->hs.uv.empty() ? nullptr : E->hs.uv.data();
   sc.tex = nullptr;
   sc.mat_tex = nullptr;
+  sc.tri_tan = nullptr;
   E->tex_tab.clear(), E->tex_data.clear(), E->tex_slots.clear();
   E->haveScene = true;
   E->havePrev = false;
@@ -568,6 +569,10 @@ int emu_set_textures(void* h, const RbTexture* textures, uint32_t n_textures, co
   memcpy(E->tex_slots.data(), per_material, n_materials * sizeof(I4));
   E->sc.tex = E->tex_tab.data();
   E->sc.mat_tex = E->tex_slots.data();
+  bool any_normal = false;
+  for (uint32_t m = 0; m < n_materials; ++m) any_normal = any_normal || per_material[m].normal >= 0;
+  if (any_normal && E->hs.tan.empty()) return RB_ERR_INVALID_ARGUMENT;
+  E->sc.tri_tan = any_normal ? E->hs.tan.data() : nullptr;
   E->havePrev = false;
   return 0;
 }
