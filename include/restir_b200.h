@@ -124,7 +124,7 @@ typedef struct RbParams {
   float tfarOffset;                  /* 0.001 */
   float normalOffset;                /* 0.001 */
   float bgColor[3];                  /* 0.5   */
-  int32_t useSkybox;                 /* reference default 1; sky texture is not part of ABI v1 -> must be 0 */
+  int32_t useSkybox;                 /* reference default 1; here 0 until a sky texture was given (rb_set_sky) */
   int32_t lightSampler;              /* RbLightSampler; reference = CDF */
   int32_t wavefront;                 /* 0: every pass traces its rays inline; 1: stream->trace->resolve split */
 } RbParams;
@@ -311,6 +311,20 @@ typedef struct RbMaterialTextures {
 } RbMaterialTextures;
 int rb_set_textures(RbHandle h, const RbTexture* textures, uint32_t n_textures, const RbMaterialTextures* per_material,
                     uint32_t n_materials);
+
+/* ---- Sky ---------------------------------------------------------------------------------
+ * With RenderParams::useSkybox (the reference's default), a primary ray that misses the scene writes
+ * scene.getSkybox().getTexel(ray.getDir()) into the G-buffer's emission (P/ReSTIRIntegrator.cpp:231) — which is what
+ * the frame shows for that pixel (P/simpleguidx11.cpp:466-467) and what rb_render_mis_frame returns for it
+ * (P/NEEPathIntegrator.cpp:131). The sky is a SphericalMap (P/SphericalMap.cpp:10-14): x = 0.5f + 0.5f * atan2f(d.y, d.x)
+ * / pi, y = 1.0f - acos(d.z) / pi (float products, the constant 1 / pi and the sums in double), then
+ * Texture::get_texel(uv) with the Texture constructor's defaults: BILINEAR, CLAMP_TO_EDGE. rb_set_sky replaces
+ * Scene::setSkybox (P/Scene.cpp:47-50): it takes the texel array of the decoded image (normally float R,G,B from an .hdr /
+ * .exr; the formats of RbTexture) and copies it; NULL removes the sky. The sky belongs to the handle and survives
+ * rb_upload_scene. rb_set_params with useSkybox = 1 fails until a sky was set. atan2f / acos are evaluated by
+ * det_math.h (correctly rounded in 4e6 random samples), so the texel coordinates can differ from a libm's in the last
+ * bit in rare cases; everything else is the reference's arithmetic. */
+int rb_set_sky(RbHandle h, const RbTexture* sky);
 
 /* ---- Scene ingestion (first half) -------------------------------------------------------------
  * Where the reference constructs `Scene{file_name, device}` (P/raytracer.cpp:36, ModelLoader::loadScene /

@@ -18,6 +18,7 @@
 #include "Intersection.h"
 #include "Sampling.h"
 #include "Scene.h"
+#include "SphericalMap.h"
 #include "camera.h"
 #include "simpleguidx11.h"
 #include "Utils.h"
@@ -226,6 +227,20 @@ void ref_set_textures(void* h, const RbTexture* textures, uint32_t n_textures, c
   }
 }
 
+// Scene::setSkybox (P/Scene.cpp:47-50): a SphericalMap whose Texture (constructor defaults: BILINEAR, CLAMP_TO_EDGE; the
+// FreeImage stand-in leaves it empty) gets its members from the RbTexture
+void ref_set_sky(void* h, const RbTexture* sky) {
+  RefCtx* c = (RefCtx*)h;
+  std::unique_ptr<SphericalMap> map = std::make_unique<SphericalMap>("");
+  Texture* T = map->texture.get();
+  T->width_ = sky->width, T->height_ = sky->height;
+  T->scan_width_ = sky->scan_width, T->pixel_size_ = sky->pixel_size;
+  T->data_ = new BYTE[(size_t)T->scan_width_ * T->height_];
+  memcpy(T->data_, sky->data, (size_t)T->scan_width_ * T->height_);
+  std::unique_ptr<Sky> newSky = std::move(map);
+  std::swap(c->scene->skybox, newSky);
+}
+
 void ref_set_params(void*, const RbParams* p) {
   ReSTIRIntegrator::M_Area = p->M_Area;
   ReSTIRIntegrator::M_Brdf = p->M_Brdf;
@@ -245,7 +260,7 @@ void ref_set_params(void*, const RbParams* p) {
   ReSTIRIntegrator::renderParams.tfarOffset = p->tfarOffset;
   ReSTIRIntegrator::renderParams.normalOffset = p->normalOffset;
   ReSTIRIntegrator::renderParams.bgColor = {p->bgColor[0], p->bgColor[1], p->bgColor[2]};
-  ReSTIRIntegrator::renderParams.useSkybox = false;
+  ReSTIRIntegrator::renderParams.useSkybox = p->useSkybox != 0;
 }
 
 // the reference Camera's own matrices (glm::lookAt / glm::inverse), exported so the oracle gets identical inputs
@@ -344,7 +359,7 @@ void ref_produce_mis(void* h, float* rgb_out) {
           radiance = L_i_indirect + L_i_direct;
         }
       } else {
-        radiance = renderParams.bgColor;  // useSkybox is off in ABI v1
+        radiance = renderParams.useSkybox ? scene.getSkybox().getTexel(ray.getDir()) : renderParams.bgColor;  // P/NEEPathIntegrator.cpp:131
       }
       c->frame[(size_t)y * c->w + x] = radiance;
     }

@@ -99,6 +99,8 @@ struct Math {
   float sin(float x) const { return mode ? std::sin(x) : dm::sinf_(x); }
   float exp(float x) const { return mode ? std::exp(x) : dm::expf_(x); }
   float lgamma(float x) const { return mode ? std::lgamma(x) : dm::lgammaf_(x); }
+  float atan2(float y, float x) const { return mode ? ::atan2f(y, x) : dm::atan2f_(y, x); }  // P/SphericalMap.cpp:11
+  float acos(float x) const { return mode ? ::acosf(x) : dm::acosf_(x); }  // :12, the float overload (MSVC's global acos(float))
   float ibeta(float x, float a, float b) const {  // MaterialPhong::ibeta(x,a,b), P/MaterialPhong.cpp:246-248
 #ifdef ORACLE_HAVE_BOOST
     if (mode) return boost::math::beta(a, b, x);
@@ -203,8 +205,10 @@ struct Scene {
   struct Tex {
     int width = 0, height = 0, scan_width = 0, pixel_size = 0;
     std::vector<unsigned char> data;
+    bool clamp = false;  // TextureClamp: REPEAT (materials, ModelLoader::TextureProxy) / CLAMP_TO_EDGE (Texture's default: the sky)
   };
   std::vector<Tex> textures;
+  Tex sky;  // SphericalMap::texture (rb_set_sky seam); width == 0 = none
   std::vector<RbMaterialTextures> mat_tex;  // empty = untextured
   std::vector<V3> tangents;  // [3 * n_tris] attribute slot 3 (P/ModelLoader.cpp:286-287), read by normal maps only; empty = none
   std::vector<int> emissive;  // TriangleCDF::tris (indices into tris)
@@ -808,6 +812,10 @@ struct Oracle {
   // Texture::get_texel(x, y), REPEAT, P/Texture.cpp:72-107
   static V3 texel(const Scene::Tex& T, int x, int y) {
     int c_x = std::abs(x % T.width), c_y = std::abs(y % T.height);
+    if (T.clamp) {  // CLAMP_TO_EDGE: glm::clamp(x, 0, width_ - 1)
+      c_x = std::min(std::max(x, 0), T.width - 1);
+      c_y = std::min(std::max(y, 0), T.height - 1);
+    }
     const int offset = c_y * T.scan_width + c_x * T.pixel_size;
     if (T.pixel_size > 4) {
       float f[3];
@@ -827,6 +835,16 @@ struct Oracle {
     V3 x1 = mix3(x0y0, x1y0, tx);
     V3 x2 = mix3(x0y1, x1y1, tx);
     return mix3(x1, x2, ty);
+  }
+
+  // SphericalMap::getTexel, P/SphericalMap.cpp:10-14. INVPI is the double 1.0 / M_PI: the float products are promoted,
+  // the sums are formed in double and rounded once when they are stored into `const float x, y`.
+  V3 skyTexel(const V3& dir) const {
+    const double INVPI = 1.0 / 3.14159265358979323846;
+    const float x = (float)(0.5f + (double)(0.5f * math.atan2(dir.y, dir.x)) * INVPI);
+    const float y = (float)(1.0f - (double)math.acos(dir.z) * INVPI);
+    const float uv[2] = {x, y};
+    return texSample(scene.sky, uv);
   }
 
   // ReSTIRIntegrator::gBufferFillPass, :213-234
@@ -861,7 +879,7 @@ struct Oracle {
       if (cache_iim && !emissive(e.emission) && (e.materialType == RB_MAT_PHONG || e.materialType == RB_MAT_DIELECTRIC))
         e.invIM = inv_I_M(e, gBuffer.cameraPosWS);
     } else {
-      e.emission = {P.bgColor[0], P.bgColor[1], P.bgColor[2]};  // useSkybox == 0 in ABI v1
+      e.emission = P.useSkybox ? skyTexel(dir) : V3{P.bgColor[0], P.bgColor[1], P.bgColor[2]};  // :231
     }
     gBuffer.px[(size_t)y * width + x] = e;
   }
@@ -1488,8 +1506,24 @@ int orc_set_textures(void* h, const RbTexture* textures, uint32_t n_textures, co
 
 int orc_set_params(void* h, const RbParams* p) {
   Oracle* o = (Oracle*)h;
-  if (p->useSkybox) return -4;
+  if (p->useSkybox && o->scene.sky.width == 0) return -4;  // the reference would dereference a null skybox
   o->P = *p;
+  return 0;
+}
+
+// Scene::setSkybox (P/Scene.cpp:47-50): SphericalMap over a Texture with the constructor's defaults (BILINEAR, CLAMP_TO_EDGE)
+int orc_set_sky(void* h, const RbTexture* sky) {
+  Oracle* o = (Oracle*)h;
+  Scene::Tex& T = o->scene.sky;
+  T = Scene::Tex{};
+  if (!sky) {
+    o->P.useSkybox = 0;
+    return 0;
+  }
+  T.width = sky->width, T.height = sky->height, T.scan_width = sky->scan_width, T.pixel_size = sky->pixel_size;
+  const unsigned char* d = (const unsigned char*)sky->data;
+  T.data.assign(d, d + (size_t)sky->scan_width * sky->height);
+  T.clamp = true;
   return 0;
 }
 
@@ -1742,6 +1776,8 @@ float orc_dm_cos(float x) { return dm::cosf_(x); }
 float orc_dm_exp(float x) { return dm::expf_(x); }
 float orc_dm_lgamma(float x) { return dm::lgammaf_(x); }
 float orc_dm_ibeta(float a, float b, float x) { return dm::ibetaf_(a, b, x); }
+float orc_dm_atan2(float y, float x) { return dm::atan2f_(y, x); }
+float orc_dm_acos(float x) { return dm::acosf_(x); }
 uint32_t orc_rng_bits(uint32_t seed, uint32_t frame, uint32_t pass, uint32_t iter, uint32_t pixel, uint32_t slot) {
   return rng_bits(rng_key(seed, frame, pass, iter, pixel), slot);
 }

@@ -77,6 +77,13 @@ def texture_tables(textures, slots, n_materials):
     return tex, len(keep), per, keep
 
 
+def sky_table(sky):
+    """sky: numpy array [h, w, 3|4] float32 (R,G,B[,A], the usual .hdr / .exr case) or uint8 (B,G,R[,A]). Returns
+    (RbTexture, keep)."""
+    tex, _, _, keep = texture_tables([sky], {}, 0)
+    return tex[0], (tex, keep)
+
+
 class RbSceneDesc(C.Structure):
     _fields_ = [("n_surfaces", C.c_uint32), ("surfaces", C.POINTER(RbSurface)), ("n_materials", C.c_uint32),
                 ("materials", C.POINTER(RbMaterial))]
@@ -95,7 +102,7 @@ class RbParams(C.Structure):
 
 def default_params(**overrides):
     """Reference defaults (P/ReSTIRIntegrator.cpp:13-35, P/RenderParams.h:8-17) except useSkybox=0
-    (the sky texture is not part of ABI v1)."""
+    (it needs a sky texture first: rb_set_sky)."""
     p = RbParams()
     p.M_Area, p.M_Brdf = 1, 1
     p.spatialReuseNeighborCount, p.spatialPassCount, p.confidenceCap = 5, 1, 20
@@ -175,7 +182,7 @@ assert HIT_DTYPE.itemsize == C.sizeof(RbHit) == 20
 # Every symbol include/restir_b200.h declares (checked by tests/test_abi.py).
 EXPORTED_SYMBOLS = [
     "rb_abi_version", "rb_last_error", "rb_default_params", "rb_create", "rb_destroy", "rb_upload_scene",
-    "rb_set_params", "rb_set_textures", "rb_render_frame", "rb_render_frame_device", "rb_render_mis_frame", "rb_readback", "rb_synchronize", "rb_timer_begin", "rb_timer_end",
+    "rb_set_params", "rb_set_textures", "rb_set_sky", "rb_render_frame", "rb_render_frame_device", "rb_render_mis_frame", "rb_readback", "rb_synchronize", "rb_timer_begin", "rb_timer_end",
     "rb_trace_closest",
     "rb_trace_occluded", "rb_trace_closest_device", "rb_trace_occluded_device", "rb_scene_stats", "rb_comm_init",
     "rb_comm_unique_id", "rb_comm_transport", "rb_debug_balance_step", "rb_obj_load", "rb_obj_scene_desc",

@@ -9,6 +9,7 @@
 //   cos / sin  P/Distribution.h:14-15,47-48, P/Sampling.cpp:83-84
 //   std::lgamma, std::exp  P/MaterialPhong.cpp:224-226
 //   boost::math::beta(a,b,x)  P/MaterialPhong.cpp:246-248
+//   atan2f, acos  P/SphericalMap.cpp:11-12 (sky lookup)
 // Results are within 1 float ulp of the correctly rounded value (checked against
 // glibc and Boost in tests/test_det_math.py), which is what makes bit-exact
 // CPU-oracle vs GPU parity possible for every discrete decision downstream.
@@ -330,6 +331,69 @@ DM_HD_NOINLINE double ibeta_full(double a, double b, double x) {
   return exp_(lbeta) - exp_(lfront) * ibeta_cf(b, a, 1.0 - x) / b;
 }
 DM_HD float ibetaf_(float a, float b, float x) { return (float)ibeta_full((double)a, (double)b, (double)x); }
+
+// ---- atan2 / acos (sky lookup, P/SphericalMap.cpp:11-12) ------------------------------------------------------
+DM_HD double sqrt_(double x) {
+#if defined(__CUDA_ARCH__)
+  return __dsqrt_rn(x);
+#else
+  return __builtin_sqrt(x);
+#endif
+}
+// atan of a finite double t in [0, 1]: t > tan(pi/12) is folded by atan(t) = pi/6 + atan((t*sqrt3 - 1) / (sqrt3 + t)),
+// then the Taylor series in z^2, |z| <= tan(pi/12) = 0.268 (17 terms: 0.0718^17 / 35 < 1e-20). ~2e-16 relative.
+DM_HD double atan_unit(double t) {
+  const double sqrt3 = 1.7320508075688772;
+  const double pi_6 = 0.52359877559829887;
+  double base = 0.0, z = t;
+  if (t > 0.2679491924311227) {
+    z = fma_(t, sqrt3, -1.0) / (sqrt3 + t);
+    base = pi_6;
+  }
+  const double z2 = z * z;
+  double p = 1.0 / 35.0;
+  p = fma_(p, -z2, 1.0 / 33.0);
+  p = fma_(p, -z2, 1.0 / 31.0);
+  p = fma_(p, -z2, 1.0 / 29.0);
+  p = fma_(p, -z2, 1.0 / 27.0);
+  p = fma_(p, -z2, 1.0 / 25.0);
+  p = fma_(p, -z2, 1.0 / 23.0);
+  p = fma_(p, -z2, 1.0 / 21.0);
+  p = fma_(p, -z2, 1.0 / 19.0);
+  p = fma_(p, -z2, 1.0 / 17.0);
+  p = fma_(p, -z2, 1.0 / 15.0);
+  p = fma_(p, -z2, 1.0 / 13.0);
+  p = fma_(p, -z2, 1.0 / 11.0);
+  p = fma_(p, -z2, 1.0 / 9.0);
+  p = fma_(p, -z2, 1.0 / 7.0);
+  p = fma_(p, -z2, 1.0 / 5.0);
+  p = fma_(p, -z2, 1.0 / 3.0);
+  // atan(z) = z - z^3 * p
+  return base + fma_(-(z * z2), p, z);
+}
+// atan2 for finite arguments (NaN in -> NaN out; infinities are not produced by the path)
+DM_HD double atan2_(double y, double x) {
+  const double pi = 3.14159265358979323846, pi_2 = 1.57079632679489661923;
+  if (isnan_(x) || isnan_(y)) return nan_();
+  const bool xneg = (d2u(x) >> 63) != 0, yneg = (d2u(y) >> 63) != 0;
+  const double ax = xneg ? -x : x, ay = yneg ? -y : y;
+  double r;
+  if (ay == 0.0 && ax == 0.0)
+    r = 0.0;  // atan2(+-0, +0) = +-0, atan2(+-0, -0) = +-pi
+  else if (ay <= ax)
+    r = atan_unit(ay / ax);
+  else
+    r = pi_2 - atan_unit(ax / ay);
+  if (xneg) r = pi - r;
+  return yneg ? -r : r;
+}
+DM_HD float atan2f_(float y, float x) { return (float)atan2_((double)y, (double)x); }
+// acos(x) = atan2(sqrt((1 - x)(1 + x)), x); NaN outside [-1, 1]
+DM_HD double acos_(double x) {
+  if (!(x >= -1.0 && x <= 1.0)) return nan_();
+  return atan2_(sqrt_((1.0 - x) * (1.0 + x)), x);
+}
+DM_HD float acosf_(float x) { return (float)acos_((double)x); }
 
 }  // namespace dm
 #endif  // RB_DET_MATH_H_

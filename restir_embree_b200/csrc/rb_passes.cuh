@@ -442,7 +442,8 @@ RB_HD void primary_ray(const CamState& cam, int width, int height, int x, int y,
   *dir = normalize(d_w);
 }
 // the element of a pixel from its primary ray's closest hit (material fetch, emission, cached 1/I_M)
-RB_HD GElem gbuffer_from_hit(const FrameCtx& fc, const CamState& cam, const SurfaceHit& h, uint32_t* geomID, uint32_t* primID) {
+RB_HD GElem gbuffer_from_hit(const FrameCtx& fc, const CamState& cam, const V3& dir, const SurfaceHit& h, uint32_t* geomID,
+                             uint32_t* primID) {
   GElem e;
   e.pos = e.normal = e.diffuse = e.specular = e.emission = v3(0);
   e.shininess = e.depth = e.invIM = 0;
@@ -470,6 +471,8 @@ RB_HD GElem gbuffer_from_hit(const FrameCtx& fc, const CamState& cam, const Surf
     }
     *geomID = h.geomID;
     *primID = h.primID;
+  } else if (fc.P.useSkybox) {  // scene.getSkybox().getTexel(ray.getDir()), :231
+    sky_texel(fc.sc.sky, dir, &e.emission);
   } else {
     e.emission = v3(fc.P.bgColor[0], fc.P.bgColor[1], fc.P.bgColor[2]);
   }
@@ -484,7 +487,7 @@ RB_HD GElem gbuffer_element(const FrameCtx& fc, const CamState& cam, int x, int 
   primary_ray(cam, fc.width, fc.height, x, y, &dir);
   cnt.closest++;
   const SurfaceHit h = intersect_surface(fc.sc, cam.pos, dir, RB_PRIMARY_TNEAR, FLT_MAX);
-  return gbuffer_from_hit(fc, cam, h, geomID, primID);
+  return gbuffer_from_hit(fc, cam, dir, h, geomID, primID);
 }
 // G-buffer access for pixels that may lie outside this handle's rows (multi-GPU bands, SURVEY §8e "local
 // re-trace"): the element is recomputed from that frame's camera, bit-identical to what its owner stored.

@@ -35,7 +35,15 @@ namespace rb {
 #define RB_NODE_F4 6  // 16-byte records per node (96 B)
 #define RB_STACK_MAX 48  // >= 2 * tree depth + 2: a node visit pushes at most a node group and a triangle group
 
-struct I4;
+struct I4 {
+  int x, y, z, w;
+};
+// Texture's members, P/Texture.h:44-50
+struct TexDev {
+  const unsigned char* data;
+  int width, height, scan_width, pixel_size;
+  int clamp;  // TextureClamp: 0 = REPEAT (material maps, ModelLoader::TextureProxy), 1 = CLAMP_TO_EDGE (the sky)
+};
 struct SceneDev {
   // geometry
   const F4* node8;        // [RB_NODE_F4 * n_nodes]
@@ -67,14 +75,8 @@ struct SceneDev {
   // (P/ModelLoader.cpp:286-287). Non-null ONLY while some material of the scene has a normal map, so that every other
   // scene pays one uniform pointer test per hit.
   const F4* tri_tan;    // [3 * n_tris] scene order, packed like tri_normals
-};
-struct I4 {
-  int x, y, z, w;
-};
-// Texture's members, P/Texture.h:44-48
-struct TexDev {
-  const unsigned char* data;
-  int width, height, scan_width, pixel_size;
+  // sky (rb_set_sky): SphericalMap::texture, P/SphericalMap.h:16; data == nullptr = none
+  TexDev sky;
 };
 
 struct HitRec {
@@ -347,11 +349,16 @@ RB_HD bool test_occlusion(const SceneDev& sc, const V3& from, const V3& to, floa
 
 // Intersection::intersectEmbree + getGeometryAttributes, :8-41, 85-113: interpolated normalised shading normal
 // flipped to face the ray, hit point = org + dir * t, texture coordinates, normal map (TBN) where the material has one.
-// Texture::get_texel(x, y) with REPEAT (P/Texture.cpp:72-107): abs(x % w), 8-bit B,G,R / 255 or float R,G,B
+// Texture::get_texel(x, y) (P/Texture.cpp:72-107): REPEAT abs(x % w) / CLAMP_TO_EDGE clamp(x, 0, w - 1); 8-bit B,G,R / 255
+// or float R,G,B
 RB_HD V3 tex_texel(const TexDev& T, int x, int y) {
   int cx = x % T.width, cy = y % T.height;
   cx = cx < 0 ? -cx : cx;
   cy = cy < 0 ? -cy : cy;
+  if (T.clamp) {
+    cx = x < 0 ? 0 : (x > T.width - 1 ? T.width - 1 : x);
+    cy = y < 0 ? 0 : (y > T.height - 1 ? T.height - 1 : y);
+  }
   const unsigned char* p = T.data + (size_t)cy * T.scan_width + (size_t)cx * T.pixel_size;
   if (T.pixel_size > 4) {
     const float* f = reinterpret_cast<const float*>(p);
@@ -372,6 +379,16 @@ RB_HD V3 tex_sample(const TexDev& T, float u, float v) {
   const V3 x1 = x0y0 * (1.0f - tx) + x1y0 * tx;
   const V3 x2 = x0y1 * (1.0f - tx) + x1y1 * tx;
   return x1 * (1.0f - ty) + x2 * ty;
+}
+
+// SphericalMap::getTexel (P/SphericalMap.cpp:10-14): x = 0.5f + 0.5f * atan2f(d.y, d.x) * INVPI, y = 1.0f - acos(d.z) * INVPI
+// with the DOUBLE constant INVPI = 1.0 / M_PI — float products promoted, sums formed in double, rounded once on the store
+// to float; atan2f / acosf are det_math's. Out of line (one call per primary-ray miss).
+RB_HD_NOINLINE void sky_texel(const TexDev& sky, const V3& dir, V3* out) {
+  const double INVPI = 1.0 / 3.14159265358979323846;
+  const float x = (float)(0.5f + (double)(0.5f * dm::atan2f_(dir.y, dir.x)) * INVPI);
+  const float y = (float)(1.0f - (double)dm::acosf_(dir.z) * INVPI);
+  *out = tex_sample(sky, x, y);
 }
 
 // Normal map, Intersection::intersectEmbree :25-39 (glm operation order: dot = (x+y)+z, normalize = v * inversesqrt(dot),

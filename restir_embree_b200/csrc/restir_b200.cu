@@ -473,6 +473,7 @@ struct RbContext {
   F4* sceneTan = nullptr;      // per-triangle tangents (owned by sceneAllocs), null = none uploaded
   uint32_t nMaterials = 0;
   std::vector<void*> texAllocs;  // rb_set_textures
+  std::vector<void*> skyAllocs;  // rb_set_sky
   SceneDev sc{};
   std::vector<void*> sceneAllocs;
   RbSceneStats stats{};
@@ -1067,6 +1068,7 @@ void rb_destroy(RbHandle h) {
   free_list(h->allocs);
   free_list(h->sceneAllocs);
   free_list(h->texAllocs);
+  free_list(h->skyAllocs);
   if (h->evCreated) {
     for (auto& ev : h->ev) cudaEventDestroy(ev);
     for (auto& ev : h->fev) cudaEventDestroy(ev);
@@ -1117,9 +1119,9 @@ void rb_destroy(RbHandle h) {
 
 int rb_set_params(RbHandle h, const RbParams* p) {
   if (!h || !p) return RB_ERR_INVALID_ARGUMENT;
-  if (p->useSkybox) {
-    h->err = "rb_set_params: useSkybox=1 needs the sky texture (not part of ABI v1)";
-    return RB_ERR_UNSUPPORTED;
+  if (p->useSkybox && h->sc.sky.data == nullptr) {  // the reference would dereference a null Scene::skybox
+    h->err = "rb_set_params: useSkybox=1 needs the sky texture (rb_set_sky)";
+    return RB_ERR_INVALID_ARGUMENT;
   }
   if (p->M_Area < 0 || p->M_Brdf < 0 || p->spatialReuseNeighborCount < 0 || p->spatialPassCount < 0 ||
       p->spatialWeightCalc < 0 || p->spatialWeightCalc > 4 || p->lightSampler < 0 || p->lightSampler > 1) {
@@ -1481,6 +1483,36 @@ int rb_set_textures(RbHandle h, const RbTexture* textures, uint32_t n_textures, 
   h->sc.mat_tex = d_slots;
   h->sc.tri_tan = any_normal ? h->sceneTan : nullptr;
   h->havePrev = false;  // the previous frame's G-buffer was made with other materials
+  return RB_OK;
+}
+
+// Sky texture (Scene::setSkybox, P/Scene.cpp:47-50; SphericalMap::getTexel, P/SphericalMap.cpp:10-14); see include/restir_b200.h
+int rb_set_sky(RbHandle h, const RbTexture* sky) {
+  if (!h) return RB_ERR_INVALID_ARGUMENT;
+  if (!sky && h->params.useSkybox) {
+    h->err = "rb_set_sky: the sky cannot be removed while useSkybox=1 (rb_set_params first)";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  if (sky) {
+    const bool fmt = sky->pixel_size == 3 || sky->pixel_size == 4 || sky->pixel_size == 12 || sky->pixel_size == 16;
+    if (sky->width <= 0 || sky->height <= 0 || !fmt || sky->scan_width < sky->width * sky->pixel_size || !sky->data) {
+      h->err = "rb_set_sky: bad texture";
+      return RB_ERR_INVALID_ARGUMENT;
+    }
+  }
+  RB_CUDA(cudaSetDevice(h->info.device));
+  RB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->fstream) RB_CUDA(cudaStreamSynchronize(h->fstream));
+  free_list(h->skyAllocs);
+  h->sc.sky = TexDev{nullptr, 0, 0, 0, 0, 0};
+  h->havePrev = false;  // the previous frame's G-buffer was made with another background
+  if (!sky) return RB_OK;
+  unsigned char* d = nullptr;
+  const size_t bytes = (size_t)sky->scan_width * sky->height;
+  RB_TRY(dev_alloc(h, &d, bytes, h->skyAllocs));
+  RB_CUDA(cudaMemcpyAsync(d, sky->data, bytes, cudaMemcpyHostToDevice, h->stream));
+  RB_CUDA(cudaStreamSynchronize(h->stream));
+  h->sc.sky = TexDev{d, sky->width, sky->height, sky->scan_width, sky->pixel_size, /*CLAMP_TO_EDGE*/ 1};
   return RB_OK;
 }
 

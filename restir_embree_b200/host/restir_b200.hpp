@@ -52,7 +52,7 @@ struct ReSTIRIntegrator {
   struct {
     float tnearOffset{0.01f}, tfarOffset{0.001f}, normalOffset{0.001f};
     vec3 bgColor{0.5f, 0.5f, 0.5f};
-    bool useSkybox{false};  // the sky texture is not part of ABI v1
+    bool useSkybox{false};  // the reference's default is true; here it needs Renderer::setSkybox first
   } renderParams;
   // seams added by this build
   bool aliasLightSampler{true};
@@ -205,6 +205,10 @@ class Renderer {
     check(rb_set_textures(h_, textures.data(), (uint32_t)textures.size(), perMaterial.data(), (uint32_t)perMaterial.size()),
           "rb_set_textures");
   }
+
+  // Scene::setSkybox (P/Scene.cpp:47-50): the texel array of the decoded sky image; nullptr removes it. Needed before
+  // params.renderParams.useSkybox = true.
+  void setSkybox(const RbTexture* sky) { check(rb_set_sky(h_, sky), "rb_set_sky"); }
 
   // SimpleGuiDX11::produceRestir: frame_data is width*height float3 (linear HDR), owned by the caller
   void produceRestir(const Camera& camera, uint32_t frameCtr, float* frame_data) {

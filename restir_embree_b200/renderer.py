@@ -46,6 +46,7 @@ def load_library():
     L.rb_upload_scene.argtypes = [H, C.POINTER(abi.RbSceneDesc)]
     L.rb_set_params.argtypes = [H, C.POINTER(abi.RbParams)]
     L.rb_set_textures.argtypes = [H, C.POINTER(abi.RbTexture), C.c_uint32, C.POINTER(abi.RbMaterialTextures), C.c_uint32]
+    L.rb_set_sky.argtypes = [H, C.POINTER(abi.RbTexture)]
     L.rb_render_frame.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
     L.rb_render_frame_device.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
     L.rb_render_mis_frame.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
@@ -155,6 +156,15 @@ class Renderer:
         R,G,B[,A]), `slots` = {material index: dict(diffuse=, specular=, shininess=)} (abi.texture_tables)."""
         tex, n, per, keep = abi.texture_tables(textures, slots, n_materials)
         self._check(self.L.rb_set_textures(self.h, tex, n, per, n_materials), "rb_set_textures")
+
+    def set_sky(self, sky):
+        """Scene::setSkybox (P/Scene.cpp:47-50): `sky` = the decoded image's texel array ([h, w, 3|4] float32 R,G,B[,A] or
+        uint8 B,G,R[,A]) or None to remove it. Needed before set_params(useSkybox=1)."""
+        if sky is None:
+            self._check(self.L.rb_set_sky(self.h, None), "rb_set_sky")
+            return
+        tex, keep = abi.sky_table(sky)
+        self._check(self.L.rb_set_sky(self.h, C.byref(tex)), "rb_set_sky")
 
     # -- frames -------------------------------------------------------------------------
     def render_frame(self, cam, frame_idx, out=None, want_timings=False, fetch=True):

@@ -62,6 +62,7 @@ struct Emu {
   std::vector<TexDev> tex_tab;  // rb_set_textures mirror
   std::vector<std::vector<unsigned char>> tex_data;
   std::vector<I4> tex_slots;
+  std::vector<unsigned char> sky_data;  // rb_set_sky mirror
   std::vector<RayQ> chain;
   uint32_t chain_count[2] = {0, 0};
   std::vector<uint32_t> deferred;
@@ -307,7 +308,7 @@ int emu_upload_scene(void* h, const RbSceneDesc* sd) {
 }
 int emu_set_params(void* h, const RbParams* p) {
   Emu* E = (Emu*)h;
-  if (p->useSkybox) return RB_ERR_UNSUPPORTED;
+  if (p->useSkybox && E->sc.sky.data == nullptr) return RB_ERR_INVALID_ARGUMENT;
   if (p->spatialReuseNeighborCount > RB_MAX_NEIGHBORS) return RB_ERR_UNSUPPORTED;
   E->P = *p;
   return 0;
@@ -574,6 +575,19 @@ int emu_set_textures(void* h, const RbTexture* textures, uint32_t n_textures, co
   if (any_normal && E->hs.tan.empty()) return RB_ERR_INVALID_ARGUMENT;
   E->sc.tri_tan = any_normal ? E->hs.tan.data() : nullptr;
   E->havePrev = false;
+  return 0;
+}
+
+// sky: the record rb_set_sky uploads, on the host
+int emu_set_sky(void* h, const RbTexture* sky) {
+  Emu* E = (Emu*)h;
+  E->sky_data.clear();
+  E->sc.sky = TexDev{nullptr, 0, 0, 0, 0, 0};
+  E->havePrev = false;
+  if (!sky) return 0;
+  const unsigned char* d = (const unsigned char*)sky->data;
+  E->sky_data.assign(d, d + (size_t)sky->scan_width * sky->height);
+  E->sc.sky = TexDev{E->sky_data.data(), sky->width, sky->height, sky->scan_width, sky->pixel_size, 1};
   return 0;
 }
 

@@ -39,6 +39,7 @@ def lib():
         L.emu_render_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p]
         L.emu_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_set_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.emu_set_sky.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_render_mis_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
         L.emu_deferred_total.argtypes = [C.c_void_p]
         L.emu_deferred_total.restype = C.c_uint64
@@ -105,6 +106,13 @@ class Emu:
     def set_textures(self, textures, slots, n_materials):
         tex, n, per, keep = abi.texture_tables(textures, slots, n_materials)
         assert self.L.emu_set_textures(self.h, tex, n, per, n_materials) == 0
+
+    def set_sky(self, sky):
+        if sky is None:
+            assert self.L.emu_set_sky(self.h, None) == 0
+            return
+        tex, keep = abi.sky_table(sky)
+        assert self.L.emu_set_sky(self.h, C.byref(tex)) == 0
 
     def render_mis_frame(self, cam, frame_idx, techniques=3):
         c = cam.to_abi() if hasattr(cam, "to_abi") else cam

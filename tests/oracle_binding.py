@@ -40,6 +40,11 @@ def lib():
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(abi.RbParams)]
         L.orc_render_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.c_void_p]
         L.orc_set_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.orc_set_sky.argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("orc_dm_atan2", "orc_dm_acos"):
+            getattr(L, name).restype = C.c_float
+        L.orc_dm_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_dm_acos.argtypes = [C.c_float]
         L.orc_temporal_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_render_mis_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_readback.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
@@ -131,6 +136,13 @@ class Oracle:
     def set_textures(self, textures, slots, n_materials):
         tex, n, per, keep = abi.texture_tables(textures, slots, n_materials)
         assert self.L.orc_set_textures(self.h, tex, n, per, n_materials) == 0
+
+    def set_sky(self, sky):
+        if sky is None:
+            assert self.L.orc_set_sky(self.h, None) == 0
+            return
+        tex, keep = abi.sky_table(sky)
+        assert self.L.orc_set_sky(self.h, C.byref(tex)) == 0
 
     def temporal_stats(self, reset=True):
         """pixels per outcome of the temporal pass since the last reset: backward reprojection failed, depth test at the

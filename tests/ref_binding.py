@@ -31,6 +31,7 @@ def lib():
         R.ref_produce_restir.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_produce_mis.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_set_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        R.ref_set_sky.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_reservoirs.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_gbuffer.argtypes = [C.c_void_p, C.c_void_p]
         R.ref_seed.argtypes = [C.c_uint32]
@@ -79,6 +80,11 @@ class Reference:
         """Material::set_texture with the reference's own Texture objects (P/Texture.cpp compiled in place)"""
         tex, n, per, keep = abi.texture_tables(textures, slots, n_materials)
         self.R.ref_set_textures(self.h, tex, n, per, n_materials)
+
+    def set_sky(self, sky):
+        """Scene::skybox = SphericalMap over the reference's own Texture (BILINEAR, CLAMP_TO_EDGE), members filled from `sky`"""
+        tex, keep = abi.sky_table(sky)
+        self.R.ref_set_sky(self.h, C.byref(tex))
 
     def produce_mis(self):
         """N2: Raytracer::get_pixel over the image with NEEPathIntegrator (DI only) + the reference's DirectMISIntegrator"""

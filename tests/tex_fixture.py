@@ -86,3 +86,18 @@ def normal_map_arrays():
 
 NMAP_SLOTS = {0: dict(diffuse=0, specular=2, shininess=3, normal=4), 2: dict(normal=5), 3: dict(normal=5, diffuse=1)}
 NMAP_N_MATERIALS = 4
+
+
+# ---- sky (SphericalMap over a CLAMP_TO_EDGE bilinear Texture, P/SphericalMap.cpp:10-14) ----------------------------------
+def sky_arrays():
+    """a float R,G,B latitude-longitude map (the .hdr case) and an 8-bit B,G,R,A one"""
+    rng = np.random.default_rng(23)
+    hdr = (rng.random((9, 16, 3), dtype=np.float32) * np.float32(3.0)).astype(np.float32)
+    hdr[0] = 0.0  # a black row at v = 0: sky pixels whose emission is exactly (0, 0, 0) run the light passes like hits do
+    ldr = rng.integers(0, 256, (6, 11, 4), dtype=np.uint8)
+    return hdr, ldr
+
+
+def sky_camera_path(f):
+    """looks over the floor's edge, up and then down: zenith, horizon and nadir directions, all four atan2 quadrants"""
+    return (2.5 + 0.1 * f, -4.0, 2.0), [(0.0, 0.5, 2.6), (-4.0, 3.0, 0.2), (0.5, -3.5, -3.0)][f % 3]
