@@ -334,9 +334,10 @@ int rb_set_sky(RbHandle h, const RbTexture* sky);
  * (Raytracer::gammaCorrect, default on; Utils::expand), Ke/Ns/Ni as written, ASSIMP's OBJ defaults for absent keys,
  * materials in MTL order, one non-indexed surface per material in order of first use, faces without a material are an
  * error (the reference indexes materials with mMaterialIndex - 1). Not pinnable without an ASSIMP binary: polygon
- * triangulation (a fan here), mesh order of files that interleave materials, tangents (none; textures are not part of
- * ABI v1 — the MTL's texture file names are available through rb_obj_texture_name, slots 0..3 = map_Kd, map_Ks,
- * map_Ns, map_Kn/bump). Faces without normals get the flat face normal. err (optional) receives a message. */
+ * triangulation (a fan here), mesh order of files that interleave materials, tangents (generated only when a material
+ * names a normal map, by the per-face step of ASSIMP's CalcTangentSpace without its smoothing across faces). The MTL's
+ * texture file names are available through rb_obj_texture_name, slots 0..3 = map_Kd, map_Ks, map_Ns, map_Kn/bump; the
+ * host decodes them and calls rb_set_textures. Faces without normals get the flat face normal. err (optional) receives a message. */
 typedef struct RbObjScene RbObjScene;
 int rb_obj_load(const char* obj_path, int32_t gamma_correct, RbObjScene** out, char* err, size_t err_bytes);
 const RbSceneDesc* rb_obj_scene_desc(const RbObjScene* s); /* valid until rb_obj_free */

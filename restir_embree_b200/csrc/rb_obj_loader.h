@@ -16,9 +16,13 @@
 //   * one surface per material (what OptimizeMeshes leaves), in order of first use; non-indexed vertices with position,
 //     normal and uv; geomID = surface index, primID = triangle index inside it; emitters are found downstream from Ke.
 // What cannot be pinned without ASSIMP (stated in DESIGN.md): polygon triangulation (here: a fan from the first
-// vertex), mesh order for files that interleave materials, and generated tangents (unused: textures are not part of
-// ABI v1; texture file names are kept per material for a host that wants them). Faces without normals get the flat face
-// normal (the reference dereferences a null mNormals there).
+// vertex), mesh order for files that interleave materials, and the generated tangents: when some material names a
+// normal map (map_Kn / bump / map_bump), every surface gets per-vertex tangents by the PER-FACE step of ASSIMP's
+// CalcTangentSpace (uv-gradient tangent, projected into the plane of each vertex normal, normalised; degenerate uv
+// -> the default uv directions) — ASSIMP's later smoothing of tangents across faces that share a vertex is not
+// reproduced (Intersection::intersectEmbree re-orthonormalises per hit anyway, so only the in-plane direction matters).
+// Texture file names are kept per material for the host's image loader. Faces without normals get the flat face normal
+// (the reference dereferences a null mNormals there).
 #ifndef RB_OBJ_LOADER_H_
 #define RB_OBJ_LOADER_H_
 
@@ -39,6 +43,7 @@ namespace rbobj {
 struct Surface {
   uint32_t material = 0;
   std::vector<float> pos, normal, uv;  // 3 vertices per triangle
+  std::vector<float> tangent;          // 3 vertices per triangle, only when a material of the scene has a normal map
 };
 struct Scene {
   std::vector<RbMaterial> materials;
@@ -49,6 +54,38 @@ struct Scene {
   RbSceneDesc desc{};
   uint64_t n_triangles = 0;
 };
+
+// The per-face step of ASSIMP's CalcTangentsProcess::ProcessMesh (aiProcess_CalcTangentSpace, P/ModelLoader.cpp:167):
+// v = p1 - p0, w = p2 - p0, (sx, sy) = uv1 - uv0, (tx, ty) = uv2 - uv0; tangent = (w * sy - v * ty) * sign(tx*sy - ty*sx)
+// (default directions when the uv triangle is degenerate); per vertex: project into the normal's plane, normalise.
+inline void calc_tangents(Surface& S) {
+  const size_t n = S.pos.size() / 9;
+  S.tangent.assign(9 * n, 0.0f);
+  for (size_t f = 0; f < n; ++f) {
+    const float* p = &S.pos[9 * f];
+    const float* t = &S.uv[6 * f];
+    const float v[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]}, w[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+    float sx = t[2] - t[0], sy = t[3] - t[1], tx = t[4] - t[0], ty = t[5] - t[1];
+    const float dir = (tx * sy - ty * sx) < 0.0f ? -1.0f : 1.0f;
+    if (sx * ty == sy * tx) sx = 0.0f, sy = 1.0f, tx = 1.0f, ty = 0.0f;
+    const float tg[3] = {(w[0] * sy - v[0] * ty) * dir, (w[1] * sy - v[1] * ty) * dir, (w[2] * sy - v[2] * ty) * dir};
+    for (int c = 0; c < 3; ++c) {
+      const float* nn = &S.normal[9 * f + 3 * c];
+      const float d = tg[0] * nn[0] + tg[1] * nn[1] + tg[2] * nn[2];
+      float l[3] = {tg[0] - nn[0] * d, tg[1] - nn[1] * d, tg[2] - nn[2] * d};
+      float len = std::sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+      if (!(len > 0.0f) || !std::isfinite(len)) {  // tangent parallel to the normal / zero-area face: any in-plane direction
+        const float a[3] = {std::fabs(nn[0]) < 0.9f ? 1.0f : 0.0f, std::fabs(nn[0]) < 0.9f ? 0.0f : 1.0f, 0.0f};
+        const float da = a[0] * nn[0] + a[1] * nn[1] + a[2] * nn[2];
+        l[0] = a[0] - nn[0] * da, l[1] = a[1] - nn[1] * da, l[2] = a[2] - nn[2] * da;
+        len = std::sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+        if (!(len > 0.0f)) l[0] = 1.0f, l[1] = l[2] = 0.0f, len = 1.0f;
+      }
+      float* o = &S.tangent[9 * f + 3 * c];
+      o[0] = l[0] / len, o[1] = l[1] / len, o[2] = l[2] / len;
+    }
+  }
+}
 
 inline void expand_srgb(float& u) {  // Utils::expand, P/utils.cpp:209-218
   if (u <= 0.0f)
@@ -267,6 +304,10 @@ inline bool load_obj(const std::string& path, bool gamma, Scene& sc, std::string
     err = path + ": no triangles";
     return false;
   }
+  bool any_normal_map = false;
+  for (const std::string& s : sc.map_kn) any_normal_map = any_normal_map || !s.empty();
+  if (any_normal_map)
+    for (Surface& S : sc.surfaces) calc_tangents(S);
   sc.abi_surfaces.resize(sc.surfaces.size());
   for (size_t i = 0; i < sc.surfaces.size(); ++i) {
     RbSurface& a = sc.abi_surfaces[i];
@@ -275,7 +316,7 @@ inline bool load_obj(const std::string& path, bool gamma, Scene& sc, std::string
     a.pos = sc.surfaces[i].pos.data();
     a.normal = sc.surfaces[i].normal.data();
     a.uv = sc.surfaces[i].uv.data();
-    a.tangent = nullptr;
+    a.tangent = sc.surfaces[i].tangent.empty() ? nullptr : sc.surfaces[i].tangent.data();
   }
   sc.desc.n_surfaces = (uint32_t)sc.abi_surfaces.size();
   sc.desc.surfaces = sc.abi_surfaces.data();

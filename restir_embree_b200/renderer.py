@@ -304,7 +304,8 @@ class Renderer:
 def load_obj_scene(path, gamma_correct=True):
     """Wavefront OBJ + MTL -> SceneArrays through the library's own parser (rb_obj_load: the conventions of the
     reference's ModelLoader, P/ModelLoader.cpp:41-321). Host-only: works without a GPU. meta carries the material names
-    and the texture file names of the MTL (textures themselves are not part of ABI v1)."""
+    and the texture file names of the MTL (the host decodes them and calls set_textures); surfaces carry uv, and tangents when a
+    material names a normal map."""
     L = load_library()
     L.rb_obj_load.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
     L.rb_obj_scene_desc.restype = C.POINTER(abi.RbSceneDesc)
@@ -335,7 +336,8 @@ def load_obj_scene(path, gamma_correct=True):
             pos = np.ctypeslib.as_array(sf.pos, shape=(n, 3, 3)).copy()
             nrm = np.ctypeslib.as_array(sf.normal, shape=(n, 3, 3)).copy()
             uvs.append(np.ctypeslib.as_array(sf.uv, shape=(n, 3, 2)).copy())
-            sc.add_surface(pos, nrm, int(sf.material))
+            tan = np.ctypeslib.as_array(sf.tangent, shape=(n, 3, 3)).copy() if sf.tangent else None
+            sc.add_surface(pos, nrm, int(sf.material), uv=uvs[-1], tangent=tan)
         lo = np.min([s[0].reshape(-1, 3).min(0) for s in sc.surfaces], axis=0)
         hi = np.max([s[0].reshape(-1, 3).max(0) for s in sc.surfaces], axis=0)
         sc.meta = dict(kind="obj", path=str(path), material_names=names, texture_names=textures, uv=uvs,

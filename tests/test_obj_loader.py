@@ -95,6 +95,54 @@ def test_loaded_scene_renders_identically_in_kernel_bodies_and_oracle(built):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_tangents_are_generated_when_a_material_names_a_normal_map(built, tmp_path):
+    """the per-face step of ASSIMP's CalcTangentSpace: tangent along +u in model space, projected into the normal's
+    plane, unit length; degenerate uv (the pentagon has none) -> the default directions, still finite and in-plane"""
+    sc = load_obj_scene(OBJ)  # the floor's material has map_Kn
+    tans = getattr(sc, "tangents", {})
+    assert sorted(tans) == [0, 1, 2]  # every surface, since SceneDev's tangent array spans the scene
+    for i, (pos, nrm, _) in enumerate(sc.surfaces):
+        t = tans[i]
+        assert np.isfinite(t).all()
+        assert np.allclose(np.linalg.norm(t, axis=-1), 1, atol=1e-6)
+        assert np.allclose((t * nrm).sum(-1), 0, atol=1e-6)
+    # floor quad: u runs along +x (vt 0 0 -> 1 0 between v1 and v2)
+    assert np.allclose(tans[0][:2], [1, 0, 0])
+    # mirrored uv flips nothing in the tangent's defining property: it still points where u increases
+    obj = tmp_path / "m.obj"
+    (tmp_path / "m.mtl").write_text("newmtl a\nKd 0.5 0.5 0.5\nPc 2\nmap_Kn n.png\nnewmtl lamp\nKe 5 5 5\nPc 2\n")
+    obj.write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nvn 0 0 1\nvt 1 0\nvt 0 0\nvt 0 1\nusemtl a\nf 1/1/1 2/2/1 3/3/1\n"
+                   "v 0 0 2\nv 1 0 2\nv 1 1 2\nvn 0 0 -1\nusemtl lamp\nf 4//2 6//2 5//2\n")
+    m = load_obj_scene(str(obj))
+    assert np.allclose(m.tangents[0][0], [-1, 0, 0])
+    # without a normal map in the MTL no tangents are made (and none are uploaded)
+    (tmp_path / "m.mtl").write_text("newmtl a\nKd 0.5 0.5 0.5\nPc 2\nnewmtl lamp\nKe 5 5 5\nPc 2\n")
+    assert not getattr(load_obj_scene(str(obj)), "tangents", {})
+
+
+def test_loaded_scene_with_its_normal_map_in_kernel_bodies_and_oracle(built):
+    """OBJ -> rb_obj_load tangents -> rb_set_textures(normal=...) -> frames: emulated kernel bodies = oracle"""
+    sc = load_obj_scene(OBJ)
+    rng = np.random.default_rng(2)
+    nmap = np.empty((8, 8, 3), dtype=np.float32)
+    nmap[..., :2] = 0.5 + (rng.random((8, 8, 2), dtype=np.float32) - 0.5) * 0.6
+    nmap[..., 2] = 0.9
+    w, h = 80, 60
+    p = abi.default_params(M_Area=4, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1, lightSampler=abi.LS_ALIAS)
+    e = eb.Emu(w, h, seed=3)
+    o = ob.Oracle(w, h, seed=3, tracer=ob.TRACER_BRUTE)
+    for r in (e, o):
+        r.upload_scene(sc)
+        r.set_params(p)
+        r.set_textures([nmap], {0: dict(normal=0)}, len(sc.materials))
+    for f in range(2):
+        cam = Camera(w, h, 60, (0.5 + 0.1 * f, -6.0, 2.0), (0.5, 0.0, 1.0))
+        a, b = e.render_frame(cam, f), o.render_frame(cam, f)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"frame {f}"
+    n = e.readback(abi.BUF_GBUF_NORMAL_SHIN)[..., :3].reshape(-1, 3)
+    assert len(np.unique(n, axis=0)) > 300  # the floor's normals follow the map
+
+
 @pytest.mark.gpu
 def test_gpu_renders_the_loaded_scene_like_the_oracle(gpu):
     from restir_embree_b200.renderer import Renderer
