@@ -191,7 +191,7 @@ struct GenVis {
 // ResolveVis: the resolve half. The same queries, in the same order, read the traced results.
 // INLINE_SHADOW: shadow rays are traced on the spot instead (initial pass with the visibility pass off, whose
 // 33 rays per pixel are not queued); closest-hit queries are always looked up.
-template <bool INLINE_SHADOW>
+template <bool INLINE_SHADOW, bool NMAP = true>
 struct ResolveVisT {
   static constexpr bool kStore = true;
   const FrameCtx* fc;
@@ -207,10 +207,11 @@ struct ResolveVisT {
     // two-step BRDF rays: the emitter hit only stands if nothing precedes it (a miss and a non-emissive closest hit
     // are the same thing to brdfSampleLight, P/ReSTIRIntegrator.cpp:143)
     if (w.brdf_two_step && hr.tri != 0xFFFFFFFFu && w.occ[(size_t)slot * w.npix + pixel] != 0) hr.tri = 0xFFFFFFFFu;
-    return surface_from_hit(fc->sc, org, dir, hr);
+    return surface_from_hit<NMAP>(fc->sc, org, dir, hr);
   }
 };
 typedef ResolveVisT<false> ResolveVis;
+typedef ResolveVisT<false, false> ResolveVisFlat;  // scenes without normal maps (see surface_from_hit)
 typedef ResolveVisT<true> ResolveInlineShadowVis;
 
 // ---- Phong / Lambert statics (P/MaterialPhong.cpp:122-248, P/MaterialLambert.cpp:33-53,
@@ -472,7 +473,7 @@ RB_HD GElem gbuffer_from_hit(const FrameCtx& fc, const CamState& cam, const V3& 
     *geomID = h.geomID;
     *primID = h.primID;
   } else if (fc.P.useSkybox) {  // scene.getSkybox().getTexel(ray.getDir()), :231
-    sky_texel(fc.sc.sky, dir, &e.emission);
+    e.emission = sky_texel(fc.sc.sky, dir);
   } else {
     e.emission = v3(fc.P.bgColor[0], fc.P.bgColor[1], fc.P.bgColor[2]);
   }

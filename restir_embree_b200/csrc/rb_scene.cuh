@@ -383,12 +383,13 @@ RB_HD V3 tex_sample(const TexDev& T, float u, float v) {
 
 // SphericalMap::getTexel (P/SphericalMap.cpp:10-14): x = 0.5f + 0.5f * atan2f(d.y, d.x) * INVPI, y = 1.0f - acos(d.z) * INVPI
 // with the DOUBLE constant INVPI = 1.0 / M_PI — float products promoted, sums formed in double, rounded once on the store
-// to float; atan2f / acosf are det_math's. Out of line (one call per primary-ray miss).
-RB_HD_NOINLINE void sky_texel(const TexDev& sky, const V3& dir, V3* out) {
+// to float; atan2f / acosf are det_math's. Out of line (one call per primary-ray miss); everything by VALUE: a
+// reference into the kernel's parameter block would make the compiler copy the whole FrameCtx to local memory.
+RB_HD_NOINLINE V3 sky_texel(TexDev sky, V3 dir) {
   const double INVPI = 1.0 / 3.14159265358979323846;
   const float x = (float)(0.5f + (double)(0.5f * dm::atan2f_(dir.y, dir.x)) * INVPI);
   const float y = (float)(1.0f - (double)dm::acosf_(dir.z) * INVPI);
-  *out = tex_sample(sky, x, y);
+  return tex_sample(sky, x, y);
 }
 
 // Normal map, Intersection::intersectEmbree :25-39 (glm operation order: dot = (x+y)+z, normalize = v * inversesqrt(dot),
@@ -396,19 +397,16 @@ RB_HD_NOINLINE void sky_texel(const TexDev& sky, const V3& dir, V3* out) {
 //   T = normalize(tangent - dot(tangent, n) * n);  B = normalize(cross(n, T));  n' = mat3(T, B, n) * (texel * 2 - 1)
 // `n` is the interpolated normal AFTER the flip towards the ray; the tangent is the raw interpolation of slot 3; the
 // result is neither re-normalised nor flipped again. Out of line: the callers' register budget is that of the scenes
-// without normal maps.
-RB_HD_NOINLINE void apply_normal_map(const SceneDev& sc, uint32_t tri, int slot, float w, float u, float v, float tex_u,
-                                     float tex_v, V3* normal) {
-  const F4* tp = sc.tri_tan + 3 * (size_t)tri;
+// without normal maps; arguments by value / plain device pointers (see sky_texel).
+RB_HD_NOINLINE V3 apply_normal_map(const F4* tp, const TexDev* map, float w, float u, float v, float tex_u, float tex_v, V3 n) {
   const F4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
   const V3 t0 = xyz(a), t1 = v3(a.w, b.x, b.y), t2 = v3(b.z, b.w, c.x);
   const V3 tangent = t0 * w + t1 * u + t2 * v;  // rtcInterpolate0 of attribute slot 3 (P/Intersection.h:106-107)
-  const V3 n = *normal;
   V3 T = tangent - n * dot(tangent, n);
   T = normalize(T);
   const V3 B = normalize(cross(n, T));
-  const V3 N = tex_sample(sc.tex[slot], tex_u, tex_v) * 2.0f - v3(1.0f);
-  *normal = v3(T.x * N.x + B.x * N.y + n.x * N.z, T.y * N.x + B.y * N.y + n.y * N.z, T.z * N.x + B.z * N.y + n.z * N.z);
+  const V3 N = tex_sample(*map, tex_u, tex_v) * 2.0f - v3(1.0f);
+  return v3(T.x * N.x + B.x * N.y + n.x * N.z, T.y * N.x + B.y * N.y + n.y * N.z, T.z * N.x + B.z * N.y + n.z * N.z);
 }
 
 struct SurfaceHit {
@@ -419,6 +417,9 @@ struct SurfaceHit {
   uint32_t tri, geomID, primID, material;
   int emissiveId;
 };
+// NMAP = false: an instantiation without the normal-map branch, for a kernel whose register budget has no room for it
+// (k_initial_resolve); the host launches it only while sc.tri_tan == nullptr, where the two are the same function.
+template <bool NMAP = true>
 RB_HD SurfaceHit surface_from_hit(const SceneDev& sc, const V3& org, const V3& dir, const HitRec& r) {
   SurfaceHit h;
   h.didHit = false;
@@ -443,9 +444,9 @@ RB_HD SurfaceHit surface_from_hit(const SceneDev& sc, const V3& org, const V3& d
     h.tex_v = q0.y * w + q0.w * r.u + q1.y * r.v;
   }
   const U4 info = sc.tri_info[r.tri];
-  if (sc.tri_tan != nullptr) {  // some material of the scene has a normal map
+  if (NMAP && sc.tri_tan != nullptr) {  // some material of the scene has a normal map
     const int slot = sc.mat_tex[info.z].w;
-    if (slot >= 0) apply_normal_map(sc, r.tri, slot, w, r.u, r.v, h.tex_u, h.tex_v, &n);
+    if (slot >= 0) n = apply_normal_map(sc.tri_tan + 3 * (size_t)r.tri, sc.tex + slot, w, r.u, r.v, h.tex_u, h.tex_v, n);
   }
   h.didHit = true;
   h.normal = n;

@@ -70,7 +70,10 @@ RB_PIXEL_KERNEL(k_shade, InlineVis, true, 4, shade_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_mis_direct, InlineVis, true, 1, mis_direct_pixel(fc, x, y, vis, cnt))
 // wavefront halves
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
-RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))  // 95 regs, no spills
+// 92 regs, no spills; the normal-map branch of the candidates' emitter hits would not fit (96 + spills), so the frame
+// launches the second instantiation only while a material of the scene has a normal map
+RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVisFlat, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL_T(k_initial_resolve_nmap, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_temporal_stream, GenVis, true, 3, temporal_gen_pixel<0>(fc, x, y, vis, cnt))
@@ -1801,7 +1804,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       ff.wave.count = vis_pair;
       ff.wave.capacity = (uint32_t)h->visRayCap;
       ff.wave.fuse_vis = 1u;
-      launch_rows(h, k_initial_resolve, y0, y1, 128, &ff, sf);
+      launch_rows(h, ff.sc.tri_tan != nullptr ? k_initial_resolve_nmap : k_initial_resolve, y0, y1, 128, &ff, sf);
     } else {
       launch_rows(h, k_initial_resolve_inline_shadow, y0, y1, kTileW * kTileH, &ff, sf);
     }
