@@ -99,8 +99,8 @@ def test_live_reference_normal_maps_other_slots():
 def test_kernel_bodies_match_oracle_with_normal_maps():
     sc = tf.normal_mapped_scene()
     w, h = 96, 64
-    for wavefront in (1, 0):
-        p = abi.default_params(doVisibilityPass=1, lightSampler=abi.LS_ALIAS, wavefront=wavefront, **PARAMS)
+    for wavefront, params in ((1, PARAMS), (1, dict(PARAMS, M_Brdf=1)), (0, PARAMS)):
+        p = abi.default_params(doVisibilityPass=1, lightSampler=abi.LS_ALIAS, wavefront=wavefront, **params)
         e = eb.Emu(w, h, seed=3)
         o = ob.Oracle(w, h, seed=3, tracer=ob.TRACER_BRUTE)
         for r in (e, o):
@@ -141,12 +141,11 @@ def test_bands_with_normal_maps_are_band_count_invariant():
         assert np.array_equal(bits(a), bits(b)), f"frame {f}"
 
 
-@pytest.mark.gpu
-def test_gpu_normal_maps_match_oracle_bit_for_bit(gpu):
-    from restir_embree_b200.renderer import Renderer, RestirError
+def _gpu_against_oracle(params):
+    from restir_embree_b200.renderer import Renderer
     sc = tf.normal_mapped_scene()
     w, h = 160, 96
-    p = abi.default_params(doVisibilityPass=1, lightSampler=abi.LS_ALIAS, wavefront=1, **PARAMS)
+    p = abi.default_params(doVisibilityPass=1, lightSampler=abi.LS_ALIAS, wavefront=1, **params)
     o = ob.Oracle(w, h, seed=3, tracer=ob.TRACER_BRUTE)
     o.upload_scene(sc)
     o.set_params(p)
@@ -162,7 +161,19 @@ def test_gpu_normal_maps_match_oracle_bit_for_bit(gpu):
         for buf in BUFS:
             assert np.array_equal(bits(r.readback(buf)), bits(o.readback(buf))), buf
         assert np.array_equal(bits(r.render_mis_frame(cam, 9)), bits(o.render_mis_frame(cam, 9)))
-        # a scene without tangents cannot take a normal map
+
+
+@pytest.mark.gpu
+def test_gpu_normal_maps_match_oracle_bit_for_bit(gpu):
+    from restir_embree_b200.renderer import Renderer, RestirError
+    _gpu_against_oracle(dict(PARAMS, M_Brdf=1))
+    with Renderer(64, 48, seed=3) as r:  # a scene without tangents cannot take a normal map
         r.upload_scene(tf.textured_scene())
         with pytest.raises(RestirError, match="normal maps"):
             r.set_textures(tf.texel_arrays(), {0: dict(normal=0)}, tf.N_MATERIALS)
+
+
+@pytest.mark.gpu
+def test_gpu_normal_maps_two_brdf_candidates(gpu):
+    """M_Brdf = 2 with the visibility pass in the wavefront schedule (k_initial_resolve_nmap with two hit slots per pixel)"""
+    _gpu_against_oracle(PARAMS)
