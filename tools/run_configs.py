@@ -10,6 +10,9 @@ each (they are parity-test / microbench cases, not the headline):
                                         temporal-reject branch (P/ReSTIRIntegrator.cpp:644,660,671,686) over the 64-frame orbit
   python tools/run_configs.py bias      static camera, 256 frames each: running mean of ReSTIR (as benchmarked, and without temporal
                                         reuse) against the running mean of the MIS ground-truth estimator (rb_render_mis_frame, N2)
+  python tools/run_configs.py textured  the bench scene (1 M triangles, 1080p) four times: plain / + diffuse, specular and roughness
+                                        maps / + normal maps / + sky (open ceiling is not modelled: the sky shows through the
+                                        camera's misses only) — what rb_set_textures and rb_set_sky cost per frame
   python tools/run_configs.py orbit64   configs[4]: 64-frame orbit at 1080p on the 1 M scene: fps, temporal-reuse statistics,
                                         per-frame relMSE of sampled rows against the CPU oracle (bit-exact => 0)
 """
@@ -188,6 +191,46 @@ def run_bias(n=256):
     print(json.dumps(out))
 
 
+def with_uv_and_tangents(sc):
+    """the procedural scene with planar texture coordinates (xy, 2 repeats per metre) and one tangent direction that is
+    parallel to no face normal of the generator's axis-aligned room and icosphere blobs"""
+    out = abi.SceneArrays()
+    out.materials = list(sc.materials)
+    out.meta = dict(sc.meta)
+    t = np.array((1.0, 0.31, 0.17), dtype=np.float32)
+    for pos, nrm, m in sc.surfaces:
+        out.add_surface(pos, nrm, m, uv=(pos[:, :, :2] * 2.0).astype(np.float32), tangent=np.broadcast_to(t, pos.shape))
+    return out
+
+
+def run_textured(n=20):
+    W, H = 1920, 1080
+    sc = with_uv_and_tangents(scenes.scene_config("1m"))
+    rng = np.random.default_rng(1)
+    tex = [rng.integers(0, 256, (512, 512, 3), dtype=np.uint8), rng.random((512, 512, 3), dtype=np.float32),
+           (rng.random((256, 256, 3), dtype=np.float32) * 0.5 + 0.3).astype(np.float32)]
+    nmap = np.empty((512, 512, 3), dtype=np.float32)
+    nmap[..., :2] = 0.5 + (rng.random((512, 512, 2), dtype=np.float32) - 0.5) * 0.4
+    nmap[..., 2] = 0.9
+    sky = (rng.random((512, 1024, 3), dtype=np.float32) * 2.0).astype(np.float32)
+    receivers = [i for i, m in enumerate(sc.materials) if sum(m["emission"]) == 0]
+    maps = {i: dict(diffuse=0, specular=1, shininess=2) for i in receivers}
+    maps_n = {i: dict(diffuse=0, specular=1, shininess=2, normal=3) for i in receivers}
+    out = {"config": "textured (1M triangles, 1080p, bench parameters)", "frames": n}
+    with Renderer(W, H, seed=123) as r:
+        r.upload_scene(sc)
+        r.set_params(params())
+        out["plain_ms"] = frames(r, sc, W, H, n)[0]
+        r.set_textures(tex + [nmap], maps, len(sc.materials))
+        out["maps_ms"] = frames(r, sc, W, H, n)[0]
+        r.set_textures(tex + [nmap], maps_n, len(sc.materials))
+        out["maps_and_normal_maps_ms"] = frames(r, sc, W, H, n)[0]
+        r.set_sky(sky)
+        r.set_params(params(useSkybox=1))
+        out["maps_normal_maps_sky_ms"] = frames(r, sc, W, H, n)[0]
+    print(json.dumps(out))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "room"
     if what == "room":
@@ -198,6 +241,8 @@ if __name__ == "__main__":
         run_rays()
     elif what == "orbit64":
         run_orbit64()
+    elif what == "textured":
+        run_textured()
     elif what == "bias":
         run_bias()
     elif what == "temporal-branches":
