@@ -70,6 +70,17 @@ def main():
     print("shadow   any-hit: %.2f node visits/ray, %.2f tri tests/ray, occluded %.1f%%" % (s, tt, 100 * occ.mean()))
     s = L.emu_trace_steps(e.h, rays.ctypes.data, len(rays), 0)
     print("shadow   closest: %.2f node visits/ray, %.2f tri tests/ray" % (s, L.emu_last_tri_tests()))
+    # how much of the any-hit cost is the visiting ORDER: the same segments traced from the light towards the surface
+    # (front-to-back from the other end), and split into occluded / unoccluded rays
+    back = make_rays(T.astype(np.float32), target=P)
+    s = L.emu_trace_steps(e.h, back.ctypes.data, len(back), 1)
+    print("shadow   any-hit, light -> surface: %.2f node visits/ray, %.2f tri tests/ray" % (s, L.emu_last_tri_tests()))
+    for name, sel in (("occluded", occ != 0), ("unoccluded", occ == 0)):
+        sub = np.ascontiguousarray(rays[sel])
+        a = L.emu_trace_steps(e.h, sub.ctypes.data, len(sub), 1)
+        ta = L.emu_last_tri_tests()
+        c = L.emu_trace_steps(e.h, sub.ctypes.data, len(sub), 0)
+        print("shadow   %-10s any-hit %.2f visits + %.2f tri tests; closest %.2f + %.2f" % (name, a, ta, c, L.emu_last_tri_tests()))
 
 
 if __name__ == "__main__":
