@@ -349,20 +349,29 @@ static void emu_trace_queue(Emu* E, int mode, float tnear = -1.0f) {
   // the "precedes" step consumes the queue the closest-emitter step filled (brdf_chain_push), as on the device
   const RayQ* q = mode == EMU_ANY_PRECEDES ? E->chain.data() : E->rays.data();
   const int64_t qn = mode == EMU_ANY_PRECEDES ? (int64_t)std::min<uint32_t>(E->chain_count[0], fc.wave.chain_capacity) : (int64_t)E->qcount;
-#pragma omp parallel for schedule(dynamic, 64)
+  // EMU_QUEUE_STATS=1: size of every traced queue and how many of its any-hit rays were occluded (tools/queue_stats.py)
+  static const bool stats = getenv("EMU_QUEUE_STATS") != nullptr;
+  int64_t n_occ = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : n_occ)
   for (int64_t i = 0; i < qn; ++i) {
     const RayQ& r = q[i];
     const uint32_t dest = f2u(r.d_dest.w);
     HitRec hr;
-    if (mode == EMU_ANY)
+    if (mode == EMU_ANY) {
       E->occ[dest] = trace8<true>(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr) ? 1 : 0;
-    else if (mode == EMU_ANY_PRECEDES)
+      n_occ += E->occ[dest];
+    } else if (mode == EMU_ANY_PRECEDES) {
       E->occ[dest] = trace8_precedes(fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, E->hits[dest].tri) ? 1 : 0;
-    else {
+      n_occ += E->occ[dest];
+    } else {
       trace8<false>(mode == EMU_CLOSEST_EMISSIVE ? em : fc.sc, xyz(r.o_tfar), xyz(r.d_dest), tnear, r.o_tfar.w, &hr);
       E->hits[dest] = hr;
       if (mode == EMU_CLOSEST_EMISSIVE && hr.tri != 0xFFFFFFFFu) brdf_chain_push(fc.wave, xyz(r.o_tfar), xyz(r.d_dest), hr.t, dest);
     }
+  }
+  if (stats) {
+    static const char* names[] = {"closest", "any", "closest_emissive", "any_precedes"};
+    fprintf(stderr, "[emu queue] %s rays %lld occluded %lld\n", names[mode], (long long)qn, (long long)n_occ);
   }
 }
 template <class F>
