@@ -202,6 +202,8 @@ class SceneArrays:
     def __init__(self):
         self.materials = []  # dicts: type, diffuse, specular, emission, shininess, ior
         self.surfaces = []   # (pos[n,3,3] f32, normal[n,3,3] f32, material_index)
+        self.uvs = {}        # surface index -> uv[n,3,2] f32 (attribute slot 1; textured materials)
+        self.tangents = {}   # surface index -> tangent[n,3,3] f32 (attribute slot 3; normal-mapped materials)
         self.meta = {}
 
     def add_material(self, type=MAT_PHONG, diffuse=(0.5, 0.5, 0.5), specular=(0.0, 0.0, 0.0), emission=(0, 0, 0),
@@ -219,12 +221,10 @@ class SceneArrays:
         if uv is not None:  # texture coordinates [n, 3, 2] (attribute slot 1 of the reference's Embree geometry)
             uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 3, 2)
             assert uv.shape[0] == pos.shape[0]
-            self.uvs = getattr(self, "uvs", {})
             self.uvs[len(self.surfaces) - 1] = uv
         if tangent is not None:  # per-vertex tangents [n, 3, 3] (attribute slot 3; read by normal-mapped materials)
             tangent = np.ascontiguousarray(tangent, dtype=np.float32).reshape(-1, 3, 3)
             assert tangent.shape == pos.shape
-            self.tangents = getattr(self, "tangents", {})
             self.tangents[len(self.surfaces) - 1] = tangent
         return len(self.surfaces) - 1
 
@@ -253,9 +253,9 @@ class SceneArrays:
             surfs[i].material = mat
             surfs[i].pos = fptr(pos)
             surfs[i].normal = fptr(nrm)
-            uv = getattr(self, "uvs", {}).get(i)
+            uv = self.uvs.get(i)
             surfs[i].uv = fptr(uv) if uv is not None else None
-            tg = getattr(self, "tangents", {}).get(i)
+            tg = self.tangents.get(i)
             surfs[i].tangent = fptr(tg) if tg is not None else None
         d = RbSceneDesc()
         d.n_surfaces = len(self.surfaces)
