@@ -16,6 +16,9 @@
 #include "ReSTIRIntegrator.h"
 #include "DirectMISIntegrator.h"
 #include "Intersection.h"
+#include "MaterialMirror.h"
+#include "MaterialNormal.h"
+#include "MaterialTransparent.h"
 #include "Sampling.h"
 #include "Scene.h"
 #include "SphericalMap.h"
@@ -118,6 +121,12 @@ Scene::Scene(const char*, const RTCDevice&) {
       mat = new MaterialLambert();
     else if (M.type == RB_MAT_DIELECTRIC)
       mat = new MaterialDielectric();
+    else if (M.type == RB_MAT_MIRROR)  // the ReSTIR statics dispatch on getType() only (P/ReSTIRIntegrator.h:32-59)
+      mat = new MaterialMirror();
+    else if (M.type == RB_MAT_NORMAL)
+      mat = new MaterialNormal();
+    else if (M.type == RB_MAT_DIELECTRIC_TRANSPARENT)
+      mat = new MaterialTransparent();
     else
       mat = new MaterialPhong();
     mat->diffuse = {M.diffuse[0], M.diffuse[1], M.diffuse[2]};

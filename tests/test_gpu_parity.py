@@ -144,13 +144,15 @@ def test_one_million_triangles_traversal_vs_oracle_bvh(gpu, scene_1m):
         assert 0.05 < oo.mean() < 0.95
 
 
-def test_full_hd_frame_sampled_rows_and_properties(gpu, scene_1m):
+@pytest.mark.parametrize("wavefront", [1, 0])
+def test_full_hd_frame_sampled_rows_and_properties(gpu, scene_1m, wavefront):
     """BASELINE config 2 at full size (1920x1080, 1M triangles, 10k emitters, A=32 B=1, temporal + spatial,
-    visibility pass). The oracle renders a band of rows of the same frames; rows far enough from the band
+    visibility pass), with the wavefront schedule bench.py runs (stream -> trace -> resolve kernels) and with the
+    inline kernels. The oracle renders a band of rows of the same frames; rows far enough from the band
     edge (spatial reach, reprojection) must be bit-identical. Plus size-independent properties."""
     Wf, Hf = 1920, 1080
     p = abi.default_params(M_Area=32, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1,
-                           lightSampler=abi.LS_ALIAS)
+                           lightSampler=abi.LS_ALIAS, wavefront=wavefront)
     y0, y1, margin = 500, 548, 16
     o = ob.Oracle(Wf, Hf, seed=123, tracer=ob.TRACER_BVH2)
     o.upload_scene(scene_1m)
@@ -175,6 +177,80 @@ def test_full_hd_frame_sampled_rows_and_properties(gpu, scene_1m):
             emissive = (r.readback(abi.BUF_GBUF_SPEC_TYPE)[..., 3].view(np.uint32) & 0x100) != 0
             assert t["rays_closest"] == Wf * Hf + int((~emissive).sum()) * p.M_Brdf
             assert ob.relmse(b[rows], a[rows]) <= 1e-3
+
+
+def test_full_hd_pipelined_frames_without_sync_match_oracle(gpu, scene_1m):
+    """The benchmarked path exactly as bench.py drives it: 1080p / 1M triangles / A=32 B=1 / visibility + temporal +
+    spatial, wavefront kernels, EIGHT consecutive rb_render_frame_device calls with no synchronisation in between — the
+    front half of frame n+1 (second stream) overlaps the back half of frame n, three G-buffers and four reservoir
+    buffers rotate, per-parity queues and counters alternate — on bench.py's camera path (0.5 deg per frame). The last
+    frame, its reservoirs (incl. selected-light indices) and hit ids are compared with the oracle, which renders a band
+    of the same eight frames; its edges erode by the spatial reach + reprojection shift per frame (measured with the
+    oracle: 33 rows after eight frames), so the middle rows are exact."""
+    Wf, Hf, n_frames = 1920, 1080, 8
+    p = abi.default_params(M_Area=32, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1,
+                           lightSampler=abi.LS_ALIAS, wavefront=1)
+    y0, y1, margin = 460, 620, 48
+    o = ob.Oracle(Wf, Hf, seed=123, tracer=ob.TRACER_BVH2)
+    o.upload_scene(scene_1m)
+    o.set_params(p)
+    o.set_band(y0, y1)
+    center = scene_1m.meta["center"]
+    cams = [Camera(Wf, Hf, 55, scenes.orbit_position(center, f), center) for f in range(n_frames)]
+    for f in range(n_frames):
+        a = o.render_frame(cams[f], f)
+    with Renderer(Wf, Hf, seed=123, collect_timings=False) as r:
+        r.upload_scene(scene_1m)
+        r.set_params(p)
+        for f in range(n_frames):
+            r.render_frame_device(cams[f], f)  # no sync, no readback: frames pipeline
+        b = r.readback(abi.BUF_FRAME_RGB)
+        rows = slice(y0 + margin, y1 - margin)
+        assert np.array_equal(bits(a[rows]), bits(b[rows])), f"{(a[rows] != b[rows]).any(-1).sum()} px of the sampled rows differ"
+        for buf in (abi.BUF_HIT_IDS, abi.BUF_RES_LIGHT_IDX, abi.BUF_RES_POINT_WSUM, abi.BUF_RES_NORMAL_W, abi.BUF_RES_LI_CONF):
+            assert np.array_equal(bits(o.readback(buf)[rows]), bits(r.readback(buf)[rows])), buf
+        assert np.isfinite(b).all() and (b >= 0).all()
+        # the same eight frames with a synchronisation after every frame (no overlap in effect): identical image
+        with Renderer(Wf, Hf, seed=123) as r2:
+            r2.upload_scene(scene_1m)
+            r2.set_params(p)
+            for f in range(n_frames):
+                b2 = r2.render_frame(cams[f], f)
+            assert np.array_equal(bits(b), bits(b2)), "pipelined and synchronised frame loops differ"
+
+
+def test_orbit_64_frames_every_frame_bit_identical_and_converged_relmse(gpu, small):
+    """BASELINE configs[4] at oracle size: 64-frame orbit, temporal + spatial reuse, wavefront kernels, frames issued
+    without synchronisation (the frame is fetched with rb_readback). Every frame equals the oracle's bit for bit, hence
+    the 64-frame running mean (the reference's accumulator, P/simpleguidx11.cpp:246-253) has relMSE 0 <= 1e-4."""
+    Wd, Hd, n_frames = 160, 96, 64
+    p = abi.default_params(M_Area=8, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1,
+                           lightSampler=abi.LS_ALIAS, wavefront=1)
+    o = ob.Oracle(Wd, Hd, seed=5, tracer=ob.TRACER_BVH2)
+    o.upload_scene(small)
+    o.set_params(p)
+    acc_o = np.zeros((Hd, Wd, 3), dtype=np.float64)
+    acc_g = np.zeros((Hd, Wd, 3), dtype=np.float64)
+    with Renderer(Wd, Hd, seed=5, collect_timings=False) as r:
+        r.upload_scene(small)
+        r.set_params(p)
+        for f in range(n_frames):
+            cam = Camera(Wd, Hd, 55, scenes.orbit_position((0, 0, 1.0), f, radius=4.5), (0, 0, 1.0))
+            a = o.render_frame(cam, f)
+            r.render_frame_device(cam, f)
+            b = r.readback(abi.BUF_FRAME_RGB)
+            assert np.array_equal(bits(a), bits(b)), f"frame {f}: {(a != b).any(-1).sum()} px differ"
+            assert ob.relmse(b, a) <= 1e-3
+            acc_o += a
+            acc_g += b
+            _, st = r.accumulate_display(f)
+        assert np.array_equal(bits(o.readback(abi.BUF_RES_LIGHT_IDX)), bits(r.readback(abi.BUF_RES_LIGHT_IDX)))
+        assert ob.relmse(acc_g / n_frames, acc_o / n_frames) <= 1e-4
+        # the library's own accumulator (N1) holds the same running mean (float, glm::mix order) to float accuracy
+        acc_lib = r.readback(abi.BUF_ACCUMULATOR)
+        assert ob.relmse(acc_lib, acc_o / n_frames) <= 1e-8
+    ts = o.temporal_stats()
+    assert ts["merged"] > 0.5 * Wd * Hd * (n_frames - 1) * 0.5  # the orbit keeps most pixels reprojectable
 
 
 def test_cpp_host_mirror_example(gpu):
