@@ -480,6 +480,7 @@ static inline int thread_id() {
 struct Oracle {
   int width = 0, height = 0;
   int band_y0 = 0, band_y1 = 0;
+  std::vector<int> rows;  // bench sampling only (orc_set_row_segments): render these rows instead of [band_y0, band_y1)
   uint32_t seed = 123;
   Math math;
   int rng_mode = 0;
@@ -1320,6 +1321,11 @@ struct Oracle {
     if (rng_mode == 1) {  // _DEBUG build: serial, y outer, x inner
       for (int y = band_y0; y < band_y1; ++y)
         for (int x = 0; x < width; ++x) f(x, y);
+    } else if (!rows.empty()) {
+      const int n = (int)rows.size();
+#pragma omp parallel for schedule(dynamic, 1)
+      for (int i = 0; i < n; ++i)
+        for (int x = 0; x < width; ++x) f(x, rows[i]);
     } else {
 #pragma omp parallel for schedule(dynamic, 1)
       for (int y = band_y0; y < band_y1; ++y)
@@ -1430,8 +1436,24 @@ int orc_set_band(void* h, int y0, int y1) {
   if (y0 < 0 || y1 > o->height || y0 > y1) return -1;
   o->band_y0 = y0;
   o->band_y1 = y1;
+  o->rows.clear();
   return 0;
 }
+// bench.py's bounded sample of a frame: several row segments spread over the image (frame cost varies along y)
+int orc_set_row_segments(void* h, const int* y0y1, int n_segments) {
+  Oracle* o = (Oracle*)h;
+  o->rows.clear();
+  for (int s = 0; s < n_segments; ++s) {
+    if (y0y1[2 * s] < 0 || y0y1[2 * s + 1] > o->height || y0y1[2 * s] > y0y1[2 * s + 1]) return -1;
+    for (int y = y0y1[2 * s]; y < y0y1[2 * s + 1]; ++y) o->rows.push_back(y);
+  }
+  return 0;
+}
+// torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU arm sets its thread count explicitly
+void orc_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+int orc_max_threads(void) { return omp_get_max_threads(); }
 
 int orc_upload_scene(void* h, const RbSceneDesc* sd) {
   Oracle* o = (Oracle*)h;

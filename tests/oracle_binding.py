@@ -36,6 +36,9 @@ def lib():
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_band.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_set_row_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_max_threads.restype = C.c_int
         L.orc_upload_scene.argtypes = [C.c_void_p, C.POINTER(abi.RbSceneDesc)]
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(abi.RbParams)]
         L.orc_render_frame.argtypes = [C.c_void_p, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.c_void_p]
@@ -106,6 +109,11 @@ class Oracle:
 
     def set_band(self, y0, y1):
         assert self.L.orc_set_band(self.h, y0, y1) == 0
+
+    def set_row_segments(self, segments):
+        """bench sampling: render only these [y0, y1) row segments of every frame"""
+        a = np.ascontiguousarray(segments, dtype=np.int32).reshape(-1, 2)
+        assert self.L.orc_set_row_segments(self.h, a.ctypes.data, a.shape[0]) == 0
 
     def upload_scene(self, scene):
         d, keep = scene.desc()
@@ -194,6 +202,14 @@ class Oracle:
         occ = np.empty(rays.shape[0], dtype=np.uint8)
         assert self.L.orc_trace_occluded(self.h, rays.ctypes.data, occ.ctypes.data, rays.shape[0]) == 0
         return occ
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+
+
+def max_threads():
+    return int(lib().orc_max_threads())
 
 
 def relmse(img, ref):
