@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 1
+#define RB_ABI_VERSION 2
 
 typedef enum RbStatus {
   RB_OK = 0,
@@ -237,6 +237,16 @@ int rb_render_frame(RbHandle h, const RbCamera* cam, uint32_t frame_idx,
 /* Same, output left in / written to DEVICE memory (frame_rgb_dev may be NULL). */
 int rb_render_frame_device(RbHandle h, const RbCamera* cam, uint32_t frame_idx,
                            float* frame_rgb_dev, RbTimings* timings);
+
+/* Pipelined form for a Producer loop that double-buffers frame_data (P/simpleguidx11.cpp:240-253 consumes the frame
+ * right after produceRestir; with two buffers it can consume frame n-1 while frame n renders): the frame is issued and
+ * its rows are copied into frame_rgb_out (HOST memory; page-locked for a truly asynchronous copy) on a copy stream
+ * behind the frame's last kernel; the call returns without waiting, so the next frame's kernels overlap the copy.
+ * rb_frame_wait(h, k) blocks until at most k of the frames issued this way are still in flight (k = 0: every buffer
+ * is complete; k = 1: the buffer of the frame before the latest is complete). The caller must not reuse a buffer
+ * before its frame has been waited for. ABI version 2. */
+int rb_render_frame_async(RbHandle h, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_out);
+int rb_frame_wait(RbHandle h, uint32_t frames_in_flight);
 
 /* ---- Ground truth next to the path ---------------------------------------------------------
  * One frame of the reference's one-sample MIS direct-lighting estimator — NEEPathIntegrator with "Calculate DI" on and

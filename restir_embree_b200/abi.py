@@ -182,7 +182,7 @@ assert HIT_DTYPE.itemsize == C.sizeof(RbHit) == 20
 # Every symbol include/restir_b200.h declares (checked by tests/test_abi.py).
 EXPORTED_SYMBOLS = [
     "rb_abi_version", "rb_last_error", "rb_default_params", "rb_create", "rb_destroy", "rb_upload_scene",
-    "rb_set_params", "rb_set_textures", "rb_set_sky", "rb_render_frame", "rb_render_frame_device", "rb_render_mis_frame", "rb_readback", "rb_synchronize", "rb_timer_begin", "rb_timer_end",
+    "rb_set_params", "rb_set_textures", "rb_set_sky", "rb_render_frame", "rb_render_frame_device", "rb_render_frame_async", "rb_frame_wait", "rb_render_mis_frame", "rb_readback", "rb_synchronize", "rb_timer_begin", "rb_timer_end",
     "rb_trace_closest",
     "rb_trace_occluded", "rb_trace_closest_device", "rb_trace_occluded_device", "rb_scene_stats", "rb_comm_init",
     "rb_comm_unique_id", "rb_comm_transport", "rb_debug_balance_step", "rb_obj_load", "rb_obj_scene_desc",

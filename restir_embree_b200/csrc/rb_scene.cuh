@@ -201,15 +201,34 @@ RB_HD bool trav_init(Trav& T, const SceneDev& sc, const V3& o, const V3& d, floa
   return true;
 }
 
-#define RB_CHILD_TEST(I, WX0, WX1, WY0, WY1, WZ0, WZ1, HW)                                             \
+// Box test of child I, result = d##I = tmax - tmin (a subtraction on the FMA pipe): the box is hit iff d is not negative.
+// The traversal kernels are bound by the ALU pipe (compare / select / logic / permute / min-max, profiles/), so the
+// hit masks are formed without compares: ONE byte permute in sign-replicate mode turns the sign bits of the two
+// children that share a hit word into a 16 + 16-bit MISS mask, one LOP3 applies it — 8 ALU-pipe instructions per node
+// where compare + select + mask + or took 29. (A difference is -0 only for x - x with x = -0... never: x - x = +0 in
+// round-to-nearest; an invalid inf - inf gives the positive canonical NaN on the device and min() drops NaN operands,
+// i.e. "hit": culling stays conservative, and hit SETS do not depend on culling.)
+#define RB_CHILD_TEST(I, WX0, WX1, WY0, WY1, WZ0, WZ1)                                                \
+  float d##I;                                                                                         \
   {                                                                                                   \
     const float t0x = fmaf_(q7f<(I)&3>(WX0, c43), ax, bx), t1x = fmaf_(q7f<(I)&3>(WX1, c43), ax, bx); \
     const float t0y = fmaf_(q7f<(I)&3>(WY0, c43), ay, by), t1y = fmaf_(q7f<(I)&3>(WY1, c43), ay, by); \
     const float t0z = fmaf_(q7f<(I)&3>(WZ0, c43), az, bz), t1z = fmaf_(q7f<(I)&3>(WZ1, c43), az, bz); \
-    const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, T.tnear));                                   \
-    const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tcull));                                     \
-    if (tmin <= tmax) acc |= f2u(HW) & ((I) < 4 ? 0x0000FFFFu : 0xFFFF0000u);                         \
+    /* [lo, hi] must meet [tnear, tcull]: hi - lo, tcull - lo and hi - tnear all non-negative. Three subtractions  \
+       (FMA pipe) and one three-input minimum instead of two more min / max on the ALU pipe. */        \
+    const float lo = fmaxf(fmaxf(t0x, t0y), t0z), hi = fminf(fminf(t1x, t1y), t1z);                   \
+    d##I = fminf(fminf(hi - lo, tcull - lo), hi - T.tnear);                                           \
   }
+// hit-word bits of the slot pair (k, k + 4) that survive: low half unless d_lo < 0, high half unless d_hi < 0
+RB_HD uint32_t hit_halves(uint32_t word, float d_lo, float d_hi) {
+#if defined(__CUDA_ARCH__)
+  uint32_t miss;  // bytes 0,1 = sign of d_lo replicated, bytes 2,3 = sign of d_hi replicated
+  asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(miss) : "r"(__float_as_uint(d_lo)), "r"(__float_as_uint(d_hi)));
+  return word & ~miss;
+#else
+  return word & ((d_lo >= 0.0f || d_lo != d_lo ? 0x0000FFFFu : 0u) | (d_hi >= 0.0f || d_hi != d_hi ? 0xFFFF0000u : 0u));
+#endif
+}
 
 // ---- traversal primitives ---------------------------------------------------------------------------
 // A node group is {child_base, hit bits << 24 | imask}; a triangle group is {tri_base, triangle hit bits}.
@@ -219,13 +238,26 @@ RB_HD bool has_node_work(const Trav& T) { return T.ngroup.y > 0x00FFFFFFu; }
 
 // Visit the nearest pending child of the current node group: test its eight child boxes. Leaves the hit
 // internal children in T.ngroup (pushing the remainder of the old group), returns the hit leaf triangles.
-template <bool ANY>
-RB_HD U2 trav_node_step(Trav& T, U2* stack, const SceneDev& sc) {
+// Stack: U2* (per-thread array in local memory) or SmemStack (k_trace_queue: entry i of this thread sits at
+// base[i * stride] in shared memory — conflict-free, no local-memory round trip for the push / pop of every visit)
+struct SmemStack {
+  U2* base;
+  int stride;
+  RB_HD U2& operator[](int i) const { return base[i * stride]; }
+};
+template <bool ANY, class Stack>
+RB_HD U2 trav_node_step(Trav& T, Stack stack, const SceneDev& sc) {
   const uint32_t hits = T.ngroup.y;
   const int bit = bfind(hits);
   T.ngroup.y &= ~(1u << bit);
   if (T.ngroup.y > 0x00FFFFFFu) stack[T.sp++] = T.ngroup;
+#ifndef RB_ANY_ORDERED
+  // any-hit rays: the visiting order cannot change the answer, and 85 % of the frame's shadow rays are unoccluded (every
+  // hit child is visited whatever the order) — slot order saves the octant permutation of the hit byte
+  const uint32_t slot = ANY ? (uint32_t)(bit - 24) : ((uint32_t)(bit - 24)) ^ T.oct_inv;
+#else
   const uint32_t slot = ((uint32_t)(bit - 24)) ^ T.oct_inv;
+#endif
   const uint32_t node_index = T.ngroup.x + popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
 
   const F4* np = sc.node8 + RB_NODE_F4 * (size_t)node_index;
@@ -242,18 +274,24 @@ RB_HD U2 trav_node_step(Trav& T, U2* stack, const SceneDev& sc) {
   const uint32_t x0a = f2u(nx ? n3.z : n2.x), x0b = f2u(nx ? n3.w : n2.y), x1a = f2u(nx ? n2.x : n3.z), x1b = f2u(nx ? n2.y : n3.w);
   const uint32_t y0a = f2u(ny ? n4.x : n2.z), y0b = f2u(ny ? n4.y : n2.w), y1a = f2u(ny ? n2.z : n4.x), y1b = f2u(ny ? n2.w : n4.y);
   const uint32_t z0a = f2u(nz ? n4.z : n3.x), z0b = f2u(nz ? n4.w : n3.y), z1a = f2u(nz ? n3.x : n4.z), z1b = f2u(nz ? n3.y : n4.w);
-  uint32_t acc = 0;
   const uint32_t c43 = sc.q7_base;
-  RB_CHILD_TEST(0, x0a, x1a, y0a, y1a, z0a, z1a, n5.x)
-  RB_CHILD_TEST(1, x0a, x1a, y0a, y1a, z0a, z1a, n5.y)
-  RB_CHILD_TEST(2, x0a, x1a, y0a, y1a, z0a, z1a, n5.z)
-  RB_CHILD_TEST(3, x0a, x1a, y0a, y1a, z0a, z1a, n5.w)
-  RB_CHILD_TEST(4, x0b, x1b, y0b, y1b, z0b, z1b, n5.x)
-  RB_CHILD_TEST(5, x0b, x1b, y0b, y1b, z0b, z1b, n5.y)
-  RB_CHILD_TEST(6, x0b, x1b, y0b, y1b, z0b, z1b, n5.z)
-  RB_CHILD_TEST(7, x0b, x1b, y0b, y1b, z0b, z1b, n5.w)
+  RB_CHILD_TEST(0, x0a, x1a, y0a, y1a, z0a, z1a)
+  RB_CHILD_TEST(1, x0a, x1a, y0a, y1a, z0a, z1a)
+  RB_CHILD_TEST(2, x0a, x1a, y0a, y1a, z0a, z1a)
+  RB_CHILD_TEST(3, x0a, x1a, y0a, y1a, z0a, z1a)
+  RB_CHILD_TEST(4, x0b, x1b, y0b, y1b, z0b, z1b)
+  RB_CHILD_TEST(5, x0b, x1b, y0b, y1b, z0b, z1b)
+  RB_CHILD_TEST(6, x0b, x1b, y0b, y1b, z0b, z1b)
+  RB_CHILD_TEST(7, x0b, x1b, y0b, y1b, z0b, z1b)
+  const uint32_t acc = hit_halves(f2u(n5.x), d0, d4) | hit_halves(f2u(n5.y), d1, d5) | hit_halves(f2u(n5.z), d2, d6) |
+                       hit_halves(f2u(n5.w), d3, d7);
   const uint32_t tri_bits = (acc & 0xFFFu) | (((acc >> 16) & 0xFFFu) << (f2u(n1.z) & 31u));
+#ifndef RB_ANY_ORDERED
+  const uint32_t ihits_slot = ((acc >> 12) & 0xFu) | ((acc >> 28) << 4);
+  const uint32_t ihits = ANY ? ihits_slot : perm8(ihits_slot, T.oct_inv);  // closest-hit: front to back
+#else
   const uint32_t ihits = perm8(((acc >> 12) & 0xFu) | ((acc >> 28) << 4), T.oct_inv);  // front to back
+#endif
   T.ngroup.x = f2u(n1.x);
   T.ngroup.y = (ihits << 24) | imask;
   return U2{f2u(n1.y), tri_bits};
@@ -292,7 +330,7 @@ RB_HD bool trav_tri_one(Trav& T, U2& tgroup, const SceneDev& sc) {
 // Returns false when the ray is finished.
 template <bool ANY, bool TIE = false>
 RB_HD bool trav_step(Trav& T, U2* stack, const SceneDev& sc) {
-  U2 tgroup = trav_node_step<ANY>(T, stack, sc);
+  U2 tgroup = trav_node_step<ANY, U2*>(T, stack, sc);
   while (tgroup.y != 0)
     if (trav_tri_one<ANY, TIE>(T, tgroup, sc)) return false;
   if (!has_node_work(T)) {

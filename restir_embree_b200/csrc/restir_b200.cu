@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -72,7 +73,10 @@ RB_PIXEL_KERNEL(k_mis_direct, InlineVis, true, 1, mis_direct_pixel(fc, x, y, vis
 RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(fc, x, y, vis))
 // 92 regs, no spills; the normal-map branch of the candidates' emitter hits would not fit (96 + spills), so the frame
 // launches the second instantiation only while a material of the scene has a normal map
-RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVisFlat, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))
+#ifndef RB_INIT_MINB
+#define RB_INIT_MINB 5
+#endif
+RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVisFlat, true, 128, RB_INIT_MINB, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL_T(k_initial_resolve_nmap, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
@@ -184,15 +188,25 @@ struct SeamIO {
   }
 };
 
-template <bool ANY, bool TIE, class IO>
+// SMEM: the per-lane stack lives in dynamic shared memory, stack_n entries of kTraceThreads x 8 bytes (the host passes
+// 2 * tree depth + 2, what a traversal can need); otherwise in local memory (deep trees: RB_STACK_MAX entries).
+template <bool ANY, bool TIE, class IO, bool SMEM>
 __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(SceneDev sc, IO io, uint32_t* __restrict__ next,
-                                                                              int refill_lanes, int tri_lanes) {
+                                                                              int refill_lanes, int tri_lanes, int stack_n) {
   const uint32_t count = io.count();
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xFFFFFFFFu;
   Trav T;
-  U2 stack[RB_STACK_MAX];  // node groups grow up from 0 (T.sp), pending triangle groups grow down from the top (tsp)
-  int tsp = RB_STACK_MAX;
+  // node groups grow up from 0 (T.sp), pending triangle groups grow down from the top (tsp)
+  extern __shared__ U2 smem_stack[];
+  U2 local_stack[SMEM ? 1 : RB_STACK_MAX];
+  typename std::conditional<SMEM, SmemStack, U2*>::type stack;
+  if constexpr (SMEM)
+    stack = SmemStack{smem_stack + threadIdx.x, kTraceThreads};
+  else
+    stack = local_stack;
+  const int STACK_TOP = SMEM ? stack_n : RB_STACK_MAX;
+  int tsp = STACK_TOP;
   U2 tg = U2{0u, 0u};  // triangle group currently being consumed
   bool active = false;
   bool exhausted = false;  // warp-uniform
@@ -213,7 +227,7 @@ __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(Sc
           io.fetch(i, &o, &d, &tn, &tf, &dest);
           active = trav_init(T, sc, o, d, tn, tf);
           if (TIE) T.tie_id = io.tie_id(dest);
-          tsp = RB_STACK_MAX;
+          tsp = STACK_TOP;
           tg = U2{0u, 0u};
           if (!active) {  // cannot hit anything
             if (ANY)
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(kTraceThreads, RB_TRACE_MINB) k_trace_queue(Sc
       if (n_tri != 0 && (n_tri >= tri_lanes || n_node < tri_lanes)) {
         if (has_tri) {
           done = trav_tri_one<ANY, TIE>(T, tg, sc);
-          if (!done && tg.y == 0 && tsp < RB_STACK_MAX) tg = stack[tsp++];
+          if (!done && tg.y == 0 && tsp < STACK_TOP) tg = stack[tsp++];
         }
       }
       // ---- finished rays ------------------------------------------------------------------------------------
@@ -428,6 +442,13 @@ struct RbContext {
   unsigned long long* counters2 = nullptr;  // [2][8]: per frame parity {closest, any as written, any traced, -, deferred
                                             // count, chain queue pair, BRDF queue pair, visibility queue pair}
   float* frame = nullptr;
+  // rb_render_frame_async: the frame's rows go to the host on a copy stream while the next frame renders. The kernel
+  // that writes frame_data of the NEXT frame (the last resolve / k_shade) waits for the copy; nothing else does.
+  cudaStream_t copyStream = nullptr;
+  static constexpr int kCopyRing = 4;
+  cudaEvent_t evCopyDone[kCopyRing]{}, evFrameReady = nullptr;
+  uint32_t asyncSeq = 0;       // async frames issued so far
+  bool copyPending = false;    // the latest async copy may still be reading h->frame
   float* accumulator = nullptr;  // N1: running mean of frame_data
   F4* display = nullptr;         // N1: tonemapped / gamma-compressed display_data
   double* statSums = nullptr;
@@ -488,6 +509,11 @@ struct RbContext {
   int numSMs = 148;
   // traversal tuning (overridable for experiments: RB_REFILL, RB_POSTPONE, RB_TRACE_BLOCKS)
   int refillLanes = 26, postponeLanes = 8, traceBlocksPerSM = 8;
+  // RB_SMEM_STACK=1: per-lane traversal stack in shared memory. Measured (profiles/r2_experiments.md): the traversal
+  // launches take the same time with either stack (the L1-resident local stack's latency is hidden), but 24 KB per CTA
+  // crowd the other stream's kernels out of the SMs (frame pipeline: 126.0 instead of 129.3 fps) — off by default
+  bool smemStack = false;
+  int smemStackEntries = 0;  // per-lane stack entries in shared memory for the uploaded scene (0 = local-memory stack)
   bool twoStepBrdf = true;  // RB_TWO_STEP_BRDF=0 traces the BRDF-candidate rays against the full BVH instead
 
   // wavefront buffers
@@ -1028,6 +1054,7 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     if (const char* e = getenv("RB_REFILL")) h->refillLanes = atoi(e);
     if (const char* e = getenv("RB_POSTPONE")) h->postponeLanes = atoi(e);
     if (const char* e = getenv("RB_TRACE_BLOCKS")) h->traceBlocksPerSM = std::max(1, atoi(e));
+    if (const char* e = getenv("RB_SMEM_STACK")) h->smemStack = atoi(e) != 0;
     if (const char* e = getenv("RB_OVERLAP")) h->overlap = atoi(e) != 0;
     if (const char* e = getenv("RB_OVERLAP_DEBUG")) h->ovDebug = atoi(e) != 0;
     if (h->ovDebug)
@@ -1087,6 +1114,13 @@ void rb_destroy(RbHandle h) {
     cudaStreamSynchronize(h->fstream);
     cudaStreamDestroy(h->fstream);
   }
+  if (h->copyStream) {
+    cudaStreamSynchronize(h->copyStream);
+    cudaStreamDestroy(h->copyStream);
+  }
+  for (auto ev : h->evCopyDone)
+    if (ev) cudaEventDestroy(ev);
+  if (h->evFrameReady) cudaEventDestroy(h->evFrameReady);
   if (h->evFrontDone) cudaEventDestroy(h->evFrontDone);
   for (auto ev : h->evBackDone)
     if (ev) cudaEventDestroy(ev);
@@ -1395,6 +1429,12 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     st.n_emissive = (uint32_t)NL;
     st.n_bvh_nodes = n_nodes;
     st.bvh_depth = depth;
+    {  // shared-memory traversal stack: 2 * depth + 2 entries per lane (what build_bvh checks against RB_STACK_MAX), if
+       // that fits next to the other resident CTAs of an SM (227 KB, 1 KB reserved per CTA)
+      const int need = 2 * (int)std::max(depth, em_depth) + 2;
+      const size_t per_cta = (size_t)need * kTraceThreads * sizeof(U2) + 1024;
+      h->smemStackEntries = (h->smemStack && per_cta * (size_t)h->traceBlocksPerSM <= 227u * 1024u) ? need : 0;
+    }
     st.build_ms = ms;
     st.total_emissive_area = totalSurface;
     for (int a = 0; a < 3; ++a) st.bounds_lo[a] = FLT_MAX, st.bounds_hi[a] = -FLT_MAX;
@@ -1678,16 +1718,25 @@ static void fs_trace(RbContext* h, int mode, int pass, float tnear = -1.0f, cons
     io.rays = w.chain_rays, io.count_ptr = w.chain_count, io.capacity = w.chain_capacity;
     next = w.chain_count + 1;
   }
-#define RB_TRACE_ARGS(SC) SC, io, next, h->refillLanes, h->postponeLanes
+  // the per-lane stack goes to shared memory when 2 * depth + 2 entries of every resident CTA fit (h->smemStackEntries)
+  const int sn = h->smemStackEntries;
+  const size_t sb = (size_t)sn * kTraceThreads * sizeof(U2);
+#define RB_TRACE_LAUNCH(ANY, TIE, SC)                                                                                     \
+  do {                                                                                                                    \
+    if (sn > 0)                                                                                                           \
+      k_trace_queue<ANY, TIE, QueueIO, true><<<trace_grid, kTraceThreads, sb, st>>>(SC, io, next, h->refillLanes, h->postponeLanes, sn); \
+    else                                                                                                                  \
+      k_trace_queue<ANY, TIE, QueueIO, false><<<trace_grid, kTraceThreads, 0, st>>>(SC, io, next, h->refillLanes, h->postponeLanes, 0); \
+  } while (0)
   if (mode == TRACE_ANY)
-    k_trace_queue<true, false, QueueIO><<<trace_grid, kTraceThreads, 0, st>>>(RB_TRACE_ARGS(h->sc));
+    RB_TRACE_LAUNCH(true, false, h->sc);
   else if (mode == TRACE_CLOSEST)
-    k_trace_queue<false, false, QueueIO><<<trace_grid, kTraceThreads, 0, st>>>(RB_TRACE_ARGS(h->sc));
+    RB_TRACE_LAUNCH(false, false, h->sc);
   else if (mode == TRACE_CLOSEST_EMISSIVE)
-    k_trace_queue<false, false, QueueIO><<<trace_grid, kTraceThreads, 0, st>>>(RB_TRACE_ARGS(emissive_view(h->sc)));
+    RB_TRACE_LAUNCH(false, false, emissive_view(h->sc));
   else
-    k_trace_queue<true, true, QueueIO><<<trace_grid, kTraceThreads, 0, st>>>(RB_TRACE_ARGS(h->sc));
-#undef RB_TRACE_ARGS
+    RB_TRACE_LAUNCH(true, true, h->sc);
+#undef RB_TRACE_LAUNCH
   if (!wsel) {
     h->wave.reset_pair = nullptr;
     h->fs.fc.wave.reset_pair = nullptr;
@@ -1703,6 +1752,14 @@ static void fs_reset_queue(RbContext* h) {
   h->wave.reset_pair = old_pair;
   h->fs.fc.wave.count = h->wave.count;
   h->fs.fc.wave.reset_pair = old_pair;
+}
+
+// frame_data is about to be overwritten: an asynchronous copy of the previous frame (rb_render_frame_async) must be through
+static int wait_frame_copy(RbContext* h) {
+  if (!h->copyPending) return RB_OK;
+  RB_CUDA(cudaStreamWaitEvent(h->stream, h->evCopyDone[(h->asyncSeq - 1u) % RbContext::kCopyRing], 0));
+  h->copyPending = false;
+  return RB_OK;
 }
 
 static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool timed) {
@@ -1941,6 +1998,7 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
     }
     fs_mark(h, 4, 0);
     fs_trace(h, TRACE_ANY, 4);
+    if (F.shaded) RB_TRY(wait_frame_copy(h));
     launch_rows(h, k_spatial_resolve, y0, y1);
     fc.wave.fuse_shade = 0u;
   } else {
@@ -1963,7 +2021,10 @@ static int frame_end(RbHandle h, RbTimings* timings) {
   cudaStream_t st = h->stream;
   std::swap(h->rRead, h->rWrite);
   fs_bind(h);
-  if (!F.shaded) launch_rows(h, k_shade, h->info.band_y0, h->info.band_y1);
+  if (!F.shaded) {
+    RB_TRY(wait_frame_copy(h));
+    launch_rows(h, k_shade, h->info.band_y0, h->info.band_y1);
+  }
   F.shaded = false;
   fs_mark(h, 5, 0);
   RB_CUDA(cudaGetLastError());
@@ -2078,6 +2139,40 @@ int rb_render_frame(RbHandle h, const RbCamera* cam, uint32_t frame_idx, float* 
   return RB_OK;
 }
 
+// Pipelined form of rb_render_frame (include/restir_b200.h): the frame is issued, its rows are copied to the host on a
+// copy stream behind the back half, and the call returns. The next frame's kernels overlap the copy.
+int rb_render_frame_async(RbHandle h, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_out) {
+  if (!h || !frame_rgb_out) return RB_ERR_INVALID_ARGUMENT;
+  if (!h->copyStream) {
+    RB_CUDA(cudaSetDevice(h->info.device));
+    RB_CUDA(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+    for (auto& ev : h->evCopyDone) RB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    RB_CUDA(cudaEventCreateWithFlags(&h->evFrameReady, cudaEventDisableTiming));
+  }
+  int rc = render_frame_impl(h, cam, frame_idx, nullptr);
+  if (rc != RB_OK) return rc;
+  const size_t row = (size_t)h->info.width * 3;
+  const size_t off = row * h->info.band_y0, cnt = row * (h->info.band_y1 - h->info.band_y0);
+  RB_CUDA(cudaEventRecord(h->evFrameReady, h->stream));
+  RB_CUDA(cudaStreamWaitEvent(h->copyStream, h->evFrameReady, 0));
+  RB_CUDA(cudaMemcpyAsync(frame_rgb_out + off, h->frame + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->copyStream));
+  RB_CUDA(cudaEventRecord(h->evCopyDone[h->asyncSeq % RbContext::kCopyRing], h->copyStream));
+  h->asyncSeq++;
+  h->copyPending = true;
+  return RB_OK;
+}
+int rb_frame_wait(RbHandle h, uint32_t frames_in_flight) {
+  if (!h) return RB_ERR_INVALID_ARGUMENT;
+  if (!h->copyStream || h->asyncSeq <= frames_in_flight) return RB_OK;
+  if (frames_in_flight >= (uint32_t)RbContext::kCopyRing) {
+    h->err = "rb_frame_wait: at most 3 frames can be left in flight";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  RB_CUDA(cudaSetDevice(h->info.device));
+  RB_CUDA(cudaEventSynchronize(h->evCopyDone[(h->asyncSeq - 1u - frames_in_flight) % RbContext::kCopyRing]));
+  return RB_OK;
+}
+
 int rb_render_frame_device(RbHandle h, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_dev, RbTimings* timings) {
   int rc = render_frame_impl(h, cam, frame_idx, timings);
   if (rc != RB_OK) return rc;
@@ -2130,6 +2225,7 @@ int rb_render_mis_frame(RbHandle h, const RbCamera* cam, uint32_t frame_idx, uin
   fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_GBUF, 0);
   launch_rows(h, k_gbuffer, y0, y1, 128, &fc);
   fc.frame_key = rng_frame_key(h->info.seed, frame_idx, PASS_MIS, 0);
+  RB_TRY(wait_frame_copy(h));
   launch_rows(h, k_mis_direct, y0, y1, kTileW * kTileH, &fc);
   RB_CUDA(cudaGetLastError());
   // the next ReSTIR front half (other stream) must not start on this G-buffer before the MIS kernels are done
@@ -2258,12 +2354,16 @@ static int trace_device(RbHandle h, const RbRay* rays, void* out, uint32_t n, bo
   k_reset_queue<<<1, 1, 0, h->stream>>>(seam_pair, seam_pair + 1);
   const int trace_grid = h->numSMs * h->traceBlocksPerSM;
   const SeamIO io{rays, n, (uint8_t*)out, (RbHit*)out};
-  if (any)
-    k_trace_queue<true, false, SeamIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, seam_pair + 1, h->refillLanes,
-                                                                                    h->postponeLanes);
+  const int sn = h->smemStackEntries;
+  const size_t sb = (size_t)sn * kTraceThreads * sizeof(U2);
+  if (any && sn > 0)
+    k_trace_queue<true, false, SeamIO, true><<<trace_grid, kTraceThreads, sb, h->stream>>>(h->sc, io, seam_pair + 1, h->refillLanes, h->postponeLanes, sn);
+  else if (any)
+    k_trace_queue<true, false, SeamIO, false><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, seam_pair + 1, h->refillLanes, h->postponeLanes, 0);
+  else if (sn > 0)
+    k_trace_queue<false, false, SeamIO, true><<<trace_grid, kTraceThreads, sb, h->stream>>>(h->sc, io, seam_pair + 1, h->refillLanes, h->postponeLanes, sn);
   else
-    k_trace_queue<false, false, SeamIO><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, seam_pair + 1, h->refillLanes,
-                                                                                     h->postponeLanes);
+    k_trace_queue<false, false, SeamIO, false><<<trace_grid, kTraceThreads, 0, h->stream>>>(h->sc, io, seam_pair + 1, h->refillLanes, h->postponeLanes, 0);
   RB_CUDA(cudaGetLastError());
   if (ms_out) {
     RB_CUDA(cudaEventRecord(h->ev[15], h->stream));

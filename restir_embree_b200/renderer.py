@@ -49,6 +49,8 @@ def load_library():
     L.rb_set_sky.argtypes = [H, C.POINTER(abi.RbTexture)]
     L.rb_render_frame.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
     L.rb_render_frame_device.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p, C.POINTER(abi.RbTimings)]
+    L.rb_render_frame_async.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p]
+    L.rb_frame_wait.argtypes = [H, C.c_uint32]
     L.rb_render_mis_frame.argtypes = [H, C.POINTER(abi.RbCamera), C.c_uint32, C.c_uint32, C.c_void_p]
     L.rb_readback.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
     L.rb_synchronize.argtypes = [H]
@@ -75,7 +77,7 @@ def load_library():
     L.rb_get_band.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rb_frame_end.argtypes = [H, C.c_void_p, C.POINTER(abi.RbTimings)]
     L.rb_accumulate_display.argtypes = [H, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(abi.RbImageStats)]
-    if L.rb_abi_version() != 1:
+    if L.rb_abi_version() != 2:
         raise RestirError("librestir_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -192,6 +194,16 @@ class Renderer:
         if want_timings:
             return _timings_dict(t)
         return None
+
+    def render_frame_async(self, cam, frame_idx, out):
+        """rb_render_frame_async: issue the frame and the copy of its rows into `out` (host array, pinned for a truly
+        asynchronous copy); returns at once. frame_wait(k) blocks until at most k such frames are in flight."""
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        assert out.dtype == np.float32 and out.size == self.width * self.height * 3 and out.flags["C_CONTIGUOUS"]
+        self._check(self.L.rb_render_frame_async(self.h, C.byref(c), int(frame_idx), out.ctypes.data), "rb_render_frame_async")
+
+    def frame_wait(self, frames_in_flight=0):
+        self._check(self.L.rb_frame_wait(self.h, int(frames_in_flight)), "rb_frame_wait")
 
     def render_mis_frame(self, cam, frame_idx, techniques=3, fetch=True):
         """One frame of the reference's ground-truth estimator (one-sample MIS direct lighting: NEEPathIntegrator with DI

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(built):
     L = renderer.load_library()
     for name in _declared_functions():
         assert hasattr(L, name), name
-    assert L.rb_abi_version() == 1
+    assert L.rb_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(built):

@@ -253,6 +253,34 @@ def test_orbit_64_frames_every_frame_bit_identical_and_converged_relmse(gpu, sma
     assert ts["merged"] > 0.5 * Wd * Hd * (n_frames - 1) * 0.5  # the orbit keeps most pixels reprojectable
 
 
+def test_async_frames_into_two_host_buffers_equal_blocking_frames(gpu, small):
+    """rb_render_frame_async / rb_frame_wait (the double-buffered Producer loop bench.py's e2e leg times): every frame that
+    lands in the host buffers equals the frame the blocking rb_render_frame returns, which the oracle checks elsewhere."""
+    import torch
+    Wd, Hd, n = 256, 144, 10
+    p = abi.default_params(M_Area=8, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1,
+                           lightSampler=abi.LS_ALIAS, wavefront=1)
+    cams = [Camera(Wd, Hd, 55, scenes.orbit_position((0, 0, 1.0), f, radius=4.5), (0, 0, 1.0)) for f in range(n)]
+    with Renderer(Wd, Hd, seed=9) as r:
+        r.upload_scene(small)
+        r.set_params(p)
+        want = [r.render_frame(cams[f], f).copy() for f in range(n)]
+    bufs = [torch.empty((Hd, Wd, 3), dtype=torch.float32, pin_memory=True).numpy() for _ in range(2)]
+    got = []
+    with Renderer(Wd, Hd, seed=9, collect_timings=False) as r:
+        r.upload_scene(small)
+        r.set_params(p)
+        for f in range(n):
+            r.render_frame_async(cams[f], f, bufs[f & 1])
+            r.frame_wait(1)
+            if f > 0:
+                got.append(bufs[(f - 1) & 1].copy())
+        r.frame_wait(0)
+        got.append(bufs[(n - 1) & 1].copy())
+    for f in range(n):
+        assert np.array_equal(bits(want[f]), bits(got[f])), f"async frame {f} differs"
+
+
 def test_cpp_host_mirror_example(gpu):
     """The C++ mirror of the reference interface (restir_embree_b200/host/restir_b200.hpp) renders through the C ABI."""
     import os
