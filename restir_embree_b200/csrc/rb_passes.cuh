@@ -1241,24 +1241,41 @@ RB_HD void spatial_merge_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
   int confidence = 0;
   uint32_t sel_pixel = 0;
   bool any_selected = false, sel_wants = false;
-  for (int i = 0; i < M; ++i) {
-    const U4 r = i == 0 ? r0 : wv.cand[(size_t)i * wv.npix + pi];
+  // Reservoir::addSample replayed from one candidate record and its traced bit
+  auto replay = [&](int i, const U4& r, uint32_t occluded) {
     const uint32_t flags = r.w >> RB_CAND_INDEX_BITS;
     float ph = u2f(r.x);
-    if ((flags & RB_CAND_RAY) && wv.occ[(size_t)i * wv.npix + pi] != 0)  // occluded: length(F0 * 0)
+    if ((flags & RB_CAND_RAY) && occluded != 0)  // occluded: length(F0 * 0)
       ph = (flags & RB_CAND_PH0_NAN) ? u2f(0x7FC00000u) : 0.0f;
     const float w = rcpM * ph * u2f(r.y);
-    // Reservoir::addSample
     w_sum += w;
     confidence += (int)r.z;
-    if (w == 0 && w_sum == 0) continue;
+    if (w == 0 && w_sum == 0) return;
     if (rng_value(key, 2u * k + i, 0, 1) < w / w_sum) {
       sel_pixel = i == 0 ? (uint32_t)pi : (r.w & ((1u << RB_CAND_INDEX_BITS) - 1u));
       any_selected = true;
       p_sel = ph;
       sel_wants = (flags & RB_CAND_WANTS) != 0;
     }
+  };
+  // The kernel is a chain of dependent loads (record -> traced byte -> next record ...) at DRAM latency; the first
+  // kPre records and bytes are fetched up front, independently of each other (slots >= M hold stale but allocated
+  // data that is never used: the stream half allocated k + 1 slots per pixel).
+  constexpr int kPre = 6;
+  U4 pre[kPre];
+  uint32_t pocc[kPre];
+  pre[0] = r0;
+  pocc[0] = wv.occ[pi];
+#pragma unroll
+  for (int i = 1; i < kPre; ++i) {
+    const bool have = i <= k;
+    pre[i] = have ? wv.cand[(size_t)i * wv.npix + pi] : U4{0u, 0u, 0u, 0u};
+    pocc[i] = have ? (uint32_t)wv.occ[(size_t)i * wv.npix + pi] : 0u;
   }
+#pragma unroll
+  for (int i = 0; i < kPre; ++i)
+    if (i < M) replay(i, pre[i], pocc[i]);
+  for (int i = kPre; i < M; ++i) replay(i, wv.cand[(size_t)i * wv.npix + pi], wv.occ[(size_t)i * wv.npix + pi]);
   if (any_selected && sel_wants) cnt.anyW++;
   Reservoir out = empty_reservoir();
   if (any_selected) {
