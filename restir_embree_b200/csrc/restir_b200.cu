@@ -480,7 +480,7 @@ struct RbContext {
   int balPeriod = 8;                             // ship + decide every balPeriod frames (RB_BAL_PERIOD)
   bool balDebug = false;                         // RB_BAL_DEBUG: print costs and bands to stderr
   uint32_t balFrame = 0;                         // frames rendered since rb_comm_init
-  cudaEvent_t evShipReady = nullptr, evShipDone = nullptr;
+  cudaEvent_t evShipReady = nullptr, evShipDone = nullptr, evAccMoved = nullptr;
   cudaEvent_t evBalCopied[kBalRing]{};           // costs of ring slot arrived in balHost
   cudaEvent_t evFrameB[kBalRing]{}, evFrameE[kBalRing]{};
   cudaEvent_t evStallA[kBalRing][kMaxStalls]{}, evStallB[kBalRing][kMaxStalls]{};
@@ -596,7 +596,8 @@ bool load_nccl(std::string& err) {
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
   g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart ||
+      !g_nccl.GroupEnd || !g_nccl.AllReduce || !g_nccl.AllGather) {  // the balancer and the transport agreement need the collectives
     err = "rb_comm: libnccl lacks a required symbol";
     return false;
   }
@@ -700,18 +701,29 @@ static int halo_push_p2p(RbContext* h) {
   return RB_OK;
 }
 // ... and, after the interior rows have been streamed, hold the main stream until both neighbours' rows are in.
+// A k_halo_wait that gave up leaves its stamp in mapped host memory. Checked wherever the host has just synchronised
+// with the frame's stream (and before the next exchange): the frame whose boundary rows read stale halo rows is reported
+// as failed, and the word is cleared so that a transient stall does not poison the handle for good.
+static int halo_check(RbContext* h) {
+  if (!h->haloErr) return RB_OK;
+  const uint32_t stamp = *(volatile uint32_t*)h->haloErr;
+  if (stamp == 0u) return RB_OK;
+  *(volatile uint32_t*)h->haloErr = 0u;
+  h->err = "band halo exchange: a neighbour's rows did not arrive in time (exchange " + std::to_string(stamp) +
+           "); the frame's boundary rows are invalid";
+  return RB_ERR_COMM;
+}
 static int halo_wait_p2p(RbContext* h) {
-  if (*(volatile uint32_t*)h->haloErr != 0u) {
-    h->err = "band halo exchange: a neighbour's rows did not arrive in time (stamp " + std::to_string(*h->haloErr) + ")";
-    return RB_ERR_COMM;
-  }
+  RB_TRY(halo_check(h));
   const int slot = (int)(h->balFrame % RbContext::kBalRing);
   const bool rec = h->balance && h->nStalls[slot] < RbContext::kMaxStalls;
   const bool timed = h->fs.timed;
   if (rec) RB_CUDA(cudaEventRecord(h->evStallA[slot][h->nStalls[slot]], h->stream));
   if (timed) RB_CUDA(cudaEventRecord(h->evHaloT0, h->stream));
-  static const unsigned long long timeout_ns =
-      (unsigned long long)(getenv("RB_HALO_TIMEOUT_MS") ? atof(getenv("RB_HALO_TIMEOUT_MS")) : 5000.0) * 1000000ull;
+  // RB_HALO_TIMEOUT_MS (default 5 s); the first exchanges wait 12 x longer: ranks allocate their wavefront buffers and
+  // NCCL sets its channels up during the first frames
+  static const double timeout_ms = getenv("RB_HALO_TIMEOUT_MS") ? atof(getenv("RB_HALO_TIMEOUT_MS")) : 5000.0;
+  const unsigned long long timeout_ns = (unsigned long long)(timeout_ms * (h->haloSeq <= 8u ? 12.0 : 1.0) * 1.0e6);
   k_halo_wait<<<1, 1, 0, h->stream>>>(h->haloFlags, h->haloSeq, h->commRank > 0 ? 1 : 0, h->commRank + 1 < h->commSize ? 1 : 0,
                                       h->haloErr, timeout_ns);
   h->fs.launches++;
@@ -848,8 +860,30 @@ static int balance_update_band(RbContext* h) {
   }
   if (ok && bounds[n] == h->info.height && bounds[h->commRank] == h->info.band_y0 && bounds[h->commRank + 1] == h->info.band_y1) {
     balance_targets(c + 2, n, h->info.height, bounds);
-    h->info.band_y0 = bounds[h->commRank];
-    h->info.band_y1 = bounds[h->commRank + 1];
+    // Rows that change owner take their ACCUMULATOR along (rb_accumulate_display keeps the running mean per band):
+    // every rank derives the same new boundaries, so both sides of a boundary know which rows move and in which
+    // direction. One grouped send / recv on the comm stream, ordered after whatever the main stream did to the
+    // accumulator so far; the main stream continues once the rows are in (they are <= 15 rows, once per period).
+    const int oy0 = h->info.band_y0, oy1 = h->info.band_y1, ny0 = bounds[h->commRank], ny1 = bounds[h->commRank + 1];
+    if (ny0 != oy0 || ny1 != oy1) {
+      const size_t row = (size_t)h->info.width * 3;
+      RB_CUDA(cudaEventRecord(h->evShipReady, h->stream));
+      RB_CUDA(cudaStreamWaitEvent(h->commStream, h->evShipReady, 0));
+      RB_NCCL(g_nccl.GroupStart());
+      if (ny0 > oy0)  // rows [oy0, ny0) go to the rank above
+        RB_NCCL(g_nccl.Send(h->accumulator + row * oy0, row * (size_t)(ny0 - oy0), /*ncclFloat32*/ 7, h->commRank - 1, h->comm, h->commStream));
+      if (ny0 < oy0)  // rows [ny0, oy0) come from the rank above
+        RB_NCCL(g_nccl.Recv(h->accumulator + row * ny0, row * (size_t)(oy0 - ny0), 7, h->commRank - 1, h->comm, h->commStream));
+      if (ny1 < oy1)  // rows [ny1, oy1) go to the rank below
+        RB_NCCL(g_nccl.Send(h->accumulator + row * ny1, row * (size_t)(oy1 - ny1), 7, h->commRank + 1, h->comm, h->commStream));
+      if (ny1 > oy1)  // rows [oy1, ny1) come from the rank below
+        RB_NCCL(g_nccl.Recv(h->accumulator + row * oy1, row * (size_t)(ny1 - oy1), 7, h->commRank + 1, h->comm, h->commStream));
+      RB_NCCL(g_nccl.GroupEnd());
+      RB_CUDA(cudaEventRecord(h->evAccMoved, h->commStream));
+      RB_CUDA(cudaStreamWaitEvent(h->stream, h->evAccMoved, 0));
+    }
+    h->info.band_y0 = ny0;
+    h->info.band_y1 = ny1;
   }
   if (h->balDebug && h->balFrame % 8 == 0) {
     std::string all;
@@ -890,6 +924,13 @@ static int halo_p2p_setup(RbContext* h) {
   char* stage = nullptr;
   const size_t HB = sizeof(mine);
   RB_CUDA(cudaMalloc((void**)&stage, 3 * HB + 16));
+  struct StageGuard {  // freed on every path out of this function
+    char*& p;
+    ~StageGuard() {
+      if (p) cudaFree(p);
+      p = nullptr;
+    }
+  } stage_guard{stage};
   RB_CUDA(cudaMemcpyAsync(stage, mine, HB, cudaMemcpyHostToDevice, h->commStream));
   RB_NCCL(g_nccl.GroupStart());
   for (int d = 0; d < 2; ++d)
@@ -917,7 +958,6 @@ static int halo_p2p_setup(RbContext* h) {
     RB_CUDA(cudaMemcpyAsync(&all_ok, agree, sizeof(int), cudaMemcpyDeviceToHost, h->commStream));
     RB_CUDA(cudaStreamSynchronize(h->commStream));
   }
-  cudaFree(stage);
   if (all_ok) {
     for (int d = 0; d < 2; ++d) {
       if (!has[d]) continue;
@@ -944,6 +984,58 @@ static int halo_p2p_setup(RbContext* h) {
   }
   if (getenv("RB_BAL_DEBUG") && h->commRank == 0) fprintf(stderr, "[rb comm] halo exchange: %s\n", h->p2p ? "peer memory (CUDA IPC)" : "NCCL send/recv");
   return RB_OK;
+}
+
+// Everything rb_comm_init made, in reverse. `barrier`: a normal shutdown — all ranks meet (one small all-reduce) after
+// their own streams have drained and BEFORE any peer mapping is closed or any plane freed, so that no neighbour can
+// still be storing halo rows into this rank's memory. (Skipped when tearing down a failed init: peers may be gone.)
+static void comm_teardown(RbContext* h, bool barrier) {
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->fstream) cudaStreamSynchronize(h->fstream);
+  if (h->commStream) cudaStreamSynchronize(h->commStream);
+  if (barrier && h->comm && h->commStream && h->balDev && g_nccl.AllReduce) {
+    if (g_nccl.AllReduce(h->balDev, h->balDev, 1, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, h->commStream) == 0)
+      cudaStreamSynchronize(h->commStream);
+  }
+  for (int d = 0; d < 2; ++d)
+    for (int i = 0; i < 17; ++i)
+      if (h->peerBase[d][i]) {
+        cudaIpcCloseMemHandle(h->peerBase[d][i]);
+        h->peerBase[d][i] = nullptr;
+      }
+  h->p2p = false;
+  if (h->haloFlags) cudaFree(h->haloFlags);
+  if (h->haloErr) cudaFreeHost(h->haloErr);
+  h->haloFlags = nullptr, h->haloErr = nullptr;
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;
+  h->commRank = 0, h->commSize = 1;
+  if (h->commStream) cudaStreamDestroy(h->commStream);
+  h->commStream = nullptr;
+  cudaEvent_t* single[] = {&h->evHaloReady, &h->evHaloDone, &h->evHaloT0, &h->evShipReady, &h->evShipDone, &h->evAccMoved};
+  for (cudaEvent_t* e : single)
+    if (*e) {
+      cudaEventDestroy(*e);
+      *e = nullptr;
+    }
+  for (int i = 0; i < RbContext::kBalRing; ++i) {
+    cudaEvent_t* ring[] = {&h->evBalCopied[i], &h->evFrameB[i], &h->evFrameE[i]};
+    for (cudaEvent_t* e : ring)
+      if (*e) {
+        cudaEventDestroy(*e);
+        *e = nullptr;
+      }
+    for (int j = 0; j < RbContext::kMaxStalls; ++j) {
+      if (h->evStallA[i][j]) cudaEventDestroy(h->evStallA[i][j]);
+      if (h->evStallB[i][j]) cudaEventDestroy(h->evStallB[i][j]);
+      h->evStallA[i][j] = h->evStallB[i][j] = nullptr;
+    }
+  }
+  if (h->balDev) cudaFree(h->balDev);
+  if (h->balHost) cudaFreeHost(h->balHost);
+  h->balDev = nullptr, h->balHost = nullptr;
+  h->shipPending = false;
+  (void)cudaGetLastError();
 }
 
 extern "C" {
@@ -1085,6 +1177,7 @@ void rb_destroy(RbHandle h) {
   if (!h) return;
   cudaSetDevice(h->info.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  comm_teardown(h, /*barrier=*/true);  // first: the ranks meet before any plane a neighbour may still write is freed
   if (h->ovDebug) {
     const int n = (int)std::min<uint32_t>(h->frameSeq, RbContext::kOvFrames);
     for (int f = 1; f < n; ++f) {
@@ -1127,29 +1220,6 @@ void rb_destroy(RbHandle h) {
   if (h->wave.cand) cudaFree(h->wave.cand);
   if (h->wave.deferred) cudaFree(h->wave.deferred);
   if (h->waveCounters) cudaFree(h->waveCounters);
-  for (int d = 0; d < 2; ++d)
-    for (int i = 0; i < 17; ++i)
-      if (h->peerBase[d][i]) cudaIpcCloseMemHandle(h->peerBase[d][i]);
-  if (h->haloFlags) cudaFree(h->haloFlags);
-  if (h->haloErr) cudaFreeHost(h->haloErr);
-  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  if (h->commStream) cudaStreamDestroy(h->commStream);
-  if (h->evHaloReady) cudaEventDestroy(h->evHaloReady);
-  if (h->evHaloDone) cudaEventDestroy(h->evHaloDone);
-  if (h->evHaloT0) cudaEventDestroy(h->evHaloT0);
-  if (h->evShipReady) cudaEventDestroy(h->evShipReady);
-  if (h->evShipDone) cudaEventDestroy(h->evShipDone);
-  for (int i = 0; i < RbContext::kBalRing; ++i) {
-    if (h->evBalCopied[i]) cudaEventDestroy(h->evBalCopied[i]);
-    if (h->evFrameB[i]) cudaEventDestroy(h->evFrameB[i]);
-    if (h->evFrameE[i]) cudaEventDestroy(h->evFrameE[i]);
-    for (int j = 0; j < RbContext::kMaxStalls; ++j) {
-      if (h->evStallA[i][j]) cudaEventDestroy(h->evStallA[i][j]);
-      if (h->evStallB[i][j]) cudaEventDestroy(h->evStallB[i][j]);
-    }
-  }
-  if (h->balDev) cudaFree(h->balDev);
-  if (h->balHost) cudaFreeHost(h->balHost);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -2053,6 +2123,7 @@ static int frame_end(RbHandle h, RbTimings* timings) {
     unsigned long long hc[8];
     RB_CUDA(cudaMemcpyAsync(hc, h->counters, 64, cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
+    RB_TRY(halo_check(h));
     timings->rays_closest = hc[0];
     timings->rays_any_as_written = hc[1];
     timings->rays_any_traced = hc[2];
@@ -2123,6 +2194,7 @@ int rb_frame_end(RbHandle h, float* frame_rgb_out, RbTimings* timings) {
     const size_t off = row * h->info.band_y0, cnt = row * (h->info.band_y1 - h->info.band_y0);
     RB_CUDA(cudaMemcpyAsync(frame_rgb_out + off, h->frame + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     RB_CUDA(cudaStreamSynchronize(h->stream));
+    RB_TRY(halo_check(h));
   }
   return RB_OK;
 }
@@ -2135,6 +2207,7 @@ int rb_render_frame(RbHandle h, const RbCamera* cam, uint32_t frame_idx, float* 
     const size_t off = row * h->info.band_y0, cnt = row * (h->info.band_y1 - h->info.band_y0);
     RB_CUDA(cudaMemcpyAsync(frame_rgb_out + off, h->frame + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     RB_CUDA(cudaStreamSynchronize(h->stream));
+    RB_TRY(halo_check(h));
   }
   return RB_OK;
 }
@@ -2170,7 +2243,7 @@ int rb_frame_wait(RbHandle h, uint32_t frames_in_flight) {
   }
   RB_CUDA(cudaSetDevice(h->info.device));
   RB_CUDA(cudaEventSynchronize(h->evCopyDone[(h->asyncSeq - 1u - frames_in_flight) % RbContext::kCopyRing]));
-  return RB_OK;
+  return halo_check(h);
 }
 
 int rb_render_frame_device(RbHandle h, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_dev, RbTimings* timings) {
@@ -2242,7 +2315,7 @@ int rb_synchronize(RbHandle h) {
   if (!h) return RB_ERR_INVALID_ARGUMENT;
   RB_CUDA(cudaSetDevice(h->info.device));
   RB_CUDA(cudaStreamSynchronize(h->stream));
-  return RB_OK;
+  return halo_check(h);
 }
 
 int rb_timer_begin(RbHandle h) {
@@ -2297,7 +2370,7 @@ int rb_readback(RbHandle h, int id, void* dst, size_t bytes) {
   }
   if (need) RB_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, h->stream));
   RB_CUDA(cudaStreamSynchronize(h->stream));
-  return RB_OK;
+  return halo_check(h);
 }
 
 // -------------------------------------------------------------------------------------
@@ -2493,9 +2566,7 @@ const char* rb_obj_texture_name(const RbObjScene* s, uint32_t i, int32_t slot) {
 void rb_obj_free(RbObjScene* s) { delete s; }
 
 int32_t rb_comm_transport(RbHandle h) { return (!h || !h->comm) ? 0 : (h->p2p ? 1 : 2); }
-int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes) {
-  if (!h || !nccl_unique_id || id_bytes < 128 || rank < 0 || rank >= nranks) return RB_ERR_INVALID_ARGUMENT;
-  if (!load_nccl(h->err)) return RB_ERR_COMM;
+static int comm_init_body(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id) {
   RB_CUDA(cudaSetDevice(h->info.device));
   NcclId128 id;
   memcpy(id.b, nccl_unique_id, 128);
@@ -2511,11 +2582,13 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
   RB_CUDA(cudaEventCreateWithFlags(&h->evHaloReady, cudaEventDisableTiming));
   RB_CUDA(cudaEventCreate(&h->evHaloDone));
   RB_CUDA(cudaEventCreate(&h->evHaloT0));
+  h->balance = true;
   if (const char* e = getenv("RB_BALANCE")) h->balance = atoi(e) != 0;
   if (const char* e = getenv("RB_BAL_PERIOD")) h->balPeriod = std::max(1, atoi(e));
   if (const char* e = getenv("RB_BAL_DEBUG")) h->balDebug = atoi(e) != 0;
   RB_CUDA(cudaEventCreateWithFlags(&h->evShipReady, cudaEventDisableTiming));
   RB_CUDA(cudaEventCreateWithFlags(&h->evShipDone, cudaEventDisableTiming));
+  RB_CUDA(cudaEventCreateWithFlags(&h->evAccMoved, cudaEventDisableTiming));
   for (int i = 0; i < RbContext::kBalRing; ++i) {
     RB_CUDA(cudaEventCreateWithFlags(&h->evBalCopied[i], cudaEventDisableTiming));
     RB_CUDA(cudaEventCreate(&h->evFrameB[i]));
@@ -2525,16 +2598,50 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
       RB_CUDA(cudaEventCreate(&h->evStallB[i][j]));
     }
   }
-  if (nranks > RbContext::kMaxRanks) {
-    h->err = "rb_comm_init: more than 64 ranks";
-    return RB_ERR_UNSUPPORTED;
-  }
   RB_CUDA(cudaMalloc((void**)&h->balDev, (2 + 2 * RbContext::kMaxRanks) * sizeof(float)));
   RB_CUDA(cudaMallocHost((void**)&h->balHost, RbContext::kBalRing * (2 + 2 * RbContext::kMaxRanks) * sizeof(float)));
   h->balFrame = 0;
   h->shipPending = false;
+  {  // The balancer ships kShipRows rows across every boundary with matching send / recv counts, which needs every band
+     // to be at least that thick (and it refuses to move bands thinner than 2 * kShipRows + 2 * 15 anyway): decided
+     // once, for all ranks together — either every rank balances or none does.
+    int rows = h->info.band_y1 - h->info.band_y0, min_rows = 0;
+    int* d = reinterpret_cast<int*>(h->balDev);
+    RB_CUDA(cudaMemcpyAsync(d, &rows, sizeof(int), cudaMemcpyHostToDevice, h->commStream));
+    RB_NCCL(g_nccl.AllReduce(d, d, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, h->comm, h->commStream));
+    RB_CUDA(cudaMemcpyAsync(&min_rows, d, sizeof(int), cudaMemcpyDeviceToHost, h->commStream));
+    RB_CUDA(cudaStreamSynchronize(h->commStream));
+    if (min_rows < 2 * RbContext::kShipRows) {
+      if (h->balance && rank == 0)
+        fprintf(stderr, "[rb comm] thinnest band has %d rows (< %d): band balancing is off\n", min_rows, 2 * RbContext::kShipRows);
+      h->balance = false;
+    }
+  }
   RB_TRY(halo_p2p_setup(h));
   return RB_OK;
+}
+int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes) {
+  if (!h || !nccl_unique_id || id_bytes < 128 || rank < 0 || rank >= nranks) return RB_ERR_INVALID_ARGUMENT;
+  if (nranks > RbContext::kMaxRanks) {
+    h->err = "rb_comm_init: more than 64 ranks";
+    return RB_ERR_UNSUPPORTED;
+  }
+  if (h->comm) {
+    h->err = "rb_comm_init: this handle already has a communicator";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  if (h->fs.open) {
+    h->err = "rb_comm_init: a frame is open";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  if (!load_nccl(h->err)) return RB_ERR_COMM;
+  const int rc = comm_init_body(h, rank, nranks, nccl_unique_id);
+  if (rc != RB_OK) {  // leave the handle as it was: single-band, no half-made communicator
+    const std::string keep = h->err;
+    comm_teardown(h, /*barrier=*/false);
+    h->err = keep;
+  }
+  return rc;
 }
 
 }  // extern "C"

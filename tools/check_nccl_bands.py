@@ -48,9 +48,11 @@ def main():
         dist.all_gather(allb, band)
         bands_seen.append([tuple(int(v) for v in b.tolist()) for b in allb])
         img = torch.from_numpy(r.render_frame(cam, f)).cuda()
+        r.accumulate_display(f, want_stats=False)  # the running mean must follow the rows when boundaries move
         dist.all_reduce(img)  # bands are disjoint, zero elsewhere
         if rank == 0:
             ref = full.render_frame(cam, f)
+            full.accumulate_display(f, want_stats=False)
             got = img.cpu().numpy()
             same = np.array_equal(ref.view(np.uint32), got.view(np.uint32)) or np.array_equal(ref, got)
             bb = bands_seen[-1]
@@ -59,7 +61,22 @@ def main():
                   f"({(ref != got).any(-1).sum()} px differ){'' if contiguous else ' BANDS NOT CONTIGUOUS'}", flush=True)
             same = same and contiguous
             ok &= same
+    # the accumulator (rb_accumulate_display, N1): every rank contributes the rows it owns NOW
+    y0, y1 = r.get_band()
+    acc = np.zeros((H, W, 3), dtype=np.float32)
+    acc[y0:y1] = r.readback(abi.BUF_ACCUMULATOR)[y0:y1]
+    acc_t = torch.from_numpy(acc).cuda()
+    dist.all_reduce(acc_t)
+    if rank == 0:
+        ref_acc = full.readback(abi.BUF_ACCUMULATOR)
+        got_acc = acc_t.cpu().numpy()
+        same = np.array_equal(ref_acc.view(np.uint32), got_acc.view(np.uint32)) or np.array_equal(ref_acc, got_acc)
+        moved = len({tuple(b) for b in bands_seen})
+        print(f"accumulator after {len(bands_seen)} frames ({moved} different band layouts): "
+              f"{'bit-identical' if same else 'DIFFERENT'} ({(ref_acc != got_acc).any(-1).sum()} px differ)", flush=True)
+        ok &= same
     dist.barrier()
+    r.close()
     dist.destroy_process_group()
     if rank == 0 and not ok:
         sys.exit(1)
