@@ -24,8 +24,20 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 WIDTH, HEIGHT = 1920, 1080
+SCENE, SPATIAL_PASSES = "1m", 1
 WORKLOAD = "configs[1]: synthetic 1M-triangle room, 10k emissive triangles, 1920x1080, ReSTIR DI A=32 B=1, " \
            "visibility pass, temporal + 1 spatial pass k=5 r=30, alias light sampler, orbit camera 0.5 deg/frame"
+
+
+def select_config(name):
+    """--config 10m: BASELINE configs[2] (a parity / scaling case, not the headline): 10M triangles, 100k emitters,
+    3840x2160, 3 spatial passes k=5, band-partitioned with halo exchange at 2/4/8 GPUs."""
+    global WIDTH, HEIGHT, SCENE, SPATIAL_PASSES, WORKLOAD, SAMPLE_SEGMENTS
+    if name == "10m":
+        WIDTH, HEIGHT, SCENE, SPATIAL_PASSES = 3840, 2160, "10m", 3
+        WORKLOAD = "configs[2]: synthetic 10M-triangle room, 100k emissive triangles, 3840x2160, ReSTIR DI A=32 B=1, " \
+                   "visibility pass, temporal + 3 spatial passes k=5 r=30, alias light sampler, orbit camera 0.5 deg/frame"
+        SAMPLE_SEGMENTS = [(266, 274), (806, 814), (1346, 1354), (1886, 1894)]
 # SURVEY §8(d): algorithmic bytes per pixel per pass (reference record sizes R=48, G=69)
 PASS_BYTES = dict(gbuffer=69, initial=117, visibility=64, temporal=306, spatial=465, shade=129)
 # The wavefront schedule folds the visibility pass into its neighbours (its ray is queued by the initial-pass resolve
@@ -147,7 +159,7 @@ class ClockSampler:
 def bench_params():
     from restir_embree_b200 import abi
     return abi.default_params(M_Area=32, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1,
-                              spatialReuseNeighborCount=5, spatialPassCount=1, spatialReuseRadius=30.0,
+                              spatialReuseNeighborCount=5, spatialPassCount=SPATIAL_PASSES, spatialReuseRadius=30.0,
                               lightSampler=abi.LS_ALIAS, wavefront=int(os.environ.get("RB_WAVEFRONT", "1")))
 
 
@@ -178,7 +190,7 @@ def cpu_reference(steps, warmup, segments=SAMPLE_SEGMENTS):
     from restir_embree_b200 import scenes
     ob.set_num_threads(host_threads())
     threads = ob.max_threads()
-    scene = scenes.scene_config("1m")
+    scene = scenes.scene_config(SCENE)
     o = ob.Oracle(WIDTH, HEIGHT, seed=123, tracer=ob.TRACER_BVH2, cache_iim=0)
     o.upload_scene(scene)
     o.set_params(bench_params())
@@ -232,7 +244,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
-    scene = scenes.scene_config("1m")
+    scene = scenes.scene_config(SCENE)
     from restir_embree_b200.renderer import band_rows
     band = band_rows(HEIGHT, world, rank)
     r = Renderer(WIDTH, HEIGHT, device=local, seed=123, band=band, collect_timings=True)
@@ -426,7 +438,9 @@ def run_ours(args):
     # streaming (reservoir) kernels: the stream + resolve halves of a pass; the roofline entry is the reservoir pass
     # with the largest streaming time (SURVEY 8d algorithmic bytes / CUDA-event time of its streaming kernels)
     stream_by_pass = {n: float(sm[i]) if wave else med[n] for i, n in enumerate(names)}
-    pass_bytes = FUSED_BYTES if wave else PASS_BYTES
+    pass_bytes = dict(FUSED_BYTES if wave else PASS_BYTES)
+    if SPATIAL_PASSES != 1:  # every pass reads / writes its 465 B/px; only the last one shades (wavefront: + 81)
+        pass_bytes["spatial"] = PASS_BYTES["spatial"] * SPATIAL_PASSES + (FUSED_BYTES["spatial"] - PASS_BYTES["spatial"] if wave else 0)
     gbs = {n: pass_bytes[n] * band_px / (stream_by_pass[n] * 1e-3) / 1e9 for n in names
            if stream_by_pass[n] > 0 and pass_bytes[n] > 0}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -522,7 +536,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="1m", choices=["1m", "10m"], help="1m = BASELINE configs[1] (the bench line); "
+                    "10m = configs[2] (4K, 10M triangles, 3 spatial passes), for the band-scaling runs")
     args = ap.parse_args()
+    select_config(args.config)
+    if args.config != "1m":
+        args.no_cpu = True
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
