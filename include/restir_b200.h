@@ -389,6 +389,12 @@ int32_t rb_comm_transport(RbHandle h); /* 0 = no communicator, 1 = peer memory (
 /* The balancer's partition rule alone (host arithmetic, no GPU): pairs = {cost, rows} per rank, rows tiling [0, height);
  * bounds_out[n_ranks + 1] = the boundaries every rank derives from them for the next period. For tests and tuning. */
 int rb_debug_balance_step(const float* pairs, int32_t n_ranks, int32_t height, int32_t* bounds_out);
+/* The rays a frame REALLY traces, for traversal measurements on the path's own ray mix (BASELINE configs[3]; replaces
+ * nothing in the reference — the counterpart is the stream of rtcOccluded1 calls under P/Intersection.h:43-60). Between
+ * the phases of an open frame in wavefront mode: which = 0 the back half's current queue (after rb_frame_begin: the
+ * temporal pass's shadow rays; after rb_frame_spatial(i): that pass's), which = 1 the visibility pass's rays. Copies up to
+ * `capacity` rays in queue order into dst (RTCRay layout; dst may be NULL to ask for the count only). */
+int rb_debug_ray_queue(RbHandle h, int32_t which, RbRay* dst, uint32_t capacity, uint32_t* count_out);
 
 /* The same frame in phases, for hosts that move the halo rows themselves (another transport, or several
  * bands in one process):  rb_frame_begin  (G-buffer, initial candidates, visibility, temporal)

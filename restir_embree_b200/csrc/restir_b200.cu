@@ -2543,6 +2543,43 @@ int rb_comm_unique_id(void* out_id, size_t id_bytes) {
 }
 // host-only arithmetic of the band balancer, exported so that it can be tested without GPUs: `pairs` = {cost, rows} per
 // rank (rows must tile [0, height)); bounds_out gets the n + 1 new boundaries every rank would compute
+// The frame's ray queues, for measurements on the rays the path REALLY traces (BASELINE configs[3]): which = 0 the back
+// half's current queue (after rb_frame_begin: the temporal pass's rays; after rb_frame_spatial(i): that pass's), 1 = the
+// visibility rays of the open frame. Rays come out in RTCRay layout, queue order. Only between the phases of an open
+// frame (rb_frame_begin .. rb_frame_end), wavefront mode.
+int rb_debug_ray_queue(RbHandle h, int32_t which, RbRay* dst, uint32_t capacity, uint32_t* count_out) {
+  if (!h || !count_out || which < 0 || which > 1) return RB_ERR_INVALID_ARGUMENT;
+  if (!h->fs.open || !h->fs.wave) {
+    h->err = "rb_debug_ray_queue: needs an open frame in wavefront mode";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  RB_CUDA(cudaSetDevice(h->info.device));
+  RB_CUDA(cudaStreamSynchronize(h->stream));
+  const int par = (int)(h->frameSeq & 1u);
+  const RayQ* src = which == 0 ? h->wave.rays : h->visRays[par];
+  const uint32_t* cnt = which == 0 ? h->wave.count : reinterpret_cast<const uint32_t*>(h->counters2 + 8 * par + 7);
+  const uint32_t cap = which == 0 ? (uint32_t)h->waveRayCap : (uint32_t)h->visRayCap;
+  uint32_t n = 0;
+  RB_CUDA(cudaMemcpy(&n, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  n = std::min(n, cap);
+  *count_out = n;
+  if (!dst || n == 0) return RB_OK;
+  const uint32_t m = std::min(n, capacity);
+  std::vector<RayQ> tmp(m);
+  RB_CUDA(cudaMemcpy(tmp.data(), src, (size_t)m * sizeof(RayQ), cudaMemcpyDeviceToHost));
+  const float tnear = FLT_MIN + h->fs.P.tnearOffset;
+  for (uint32_t i = 0; i < m; ++i) {
+    RbRay r;
+    memset(&r, 0, sizeof(r));
+    r.org_x = tmp[i].o_tfar.x, r.org_y = tmp[i].o_tfar.y, r.org_z = tmp[i].o_tfar.z;
+    r.dir_x = tmp[i].d_dest.x, r.dir_y = tmp[i].d_dest.y, r.dir_z = tmp[i].d_dest.z;
+    r.tnear = tnear;
+    r.tfar = tmp[i].o_tfar.w;
+    r.mask = 0xFFFFFFFFu;
+    dst[i] = r;
+  }
+  return RB_OK;
+}
 int rb_debug_balance_step(const float* pairs, int32_t n_ranks, int32_t height, int32_t* bounds_out) {
   if (!pairs || !bounds_out || n_ranks < 1 || n_ranks > RbContext::kMaxRanks) return RB_ERR_INVALID_ARGUMENT;
   bounds_out[0] = 0;

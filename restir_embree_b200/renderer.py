@@ -76,6 +76,7 @@ def load_library():
     L.rb_set_band.argtypes = [H, C.c_int32, C.c_int32]
     L.rb_get_band.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rb_frame_end.argtypes = [H, C.c_void_p, C.POINTER(abi.RbTimings)]
+    L.rb_debug_ray_queue.argtypes = [H, C.c_int32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.rb_accumulate_display.argtypes = [H, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(abi.RbImageStats)]
     if L.rb_abi_version() != 2:
         raise RestirError("librestir_b200.so ABI version mismatch")
@@ -279,6 +280,16 @@ class Renderer:
     def frame_end(self, out=None):
         ptr = out.ctypes.data if out is not None else None
         self._check(self.L.rb_frame_end(self.h, ptr, None), "rb_frame_end")
+
+    def debug_ray_queue(self, which):
+        """The rays of the open frame's current queue (which=0: temporal after frame_begin / spatial after frame_spatial)
+        or of its visibility pass (which=1), RTCRay layout, queue order (rb_debug_ray_queue)."""
+        n = C.c_uint32(0)
+        self._check(self.L.rb_debug_ray_queue(self.h, int(which), None, 0, C.byref(n)), "rb_debug_ray_queue")
+        rays = np.zeros(n.value, dtype=abi.RAY_DTYPE)
+        if n.value:
+            self._check(self.L.rb_debug_ray_queue(self.h, int(which), rays.ctypes.data, n.value, C.byref(n)), "rb_debug_ray_queue")
+        return rays
 
     def set_band(self, y0, y1):
         self._check(self.L.rb_set_band(self.h, int(y0), int(y1)), "rb_set_band")

@@ -4,8 +4,9 @@ each (they are parity-test / microbench cases, not the headline):
 
   python tools/run_configs.py room      configs[0] stand-in: ~200 k triangles, 1280x720, A=32 B=1, temporal + 1 spatial pass
   python tools/run_configs.py 10m       configs[2] on ONE GPU: 10 M triangles, 100 k emitters, 3840x2160, 3 spatial passes k=5
-  python tools/run_configs.py rays      configs[3]: 33 M shadow rays (16 per 1080p pixel) against the 10 M-triangle BVH,
-                                        coherent (pixel order) and shuffled, through rb_trace_occluded_device
+  python tools/run_configs.py rays      configs[3]: 33 M shadow rays against the 10 M-triangle BVH — the rays the path really traces
+                                        (visibility / temporal / spatial queues of consecutive 1080p frames), as queued, shuffled
+                                        and sorted, through rb_trace_occluded_device; CPU leg: oracle BVH2 on all host cores
   python tools/run_configs.py temporal-branches   CPU only (oracle, a 48-row band of the 1080p orbit): fraction of pixels taking each
                                         temporal-reject branch (P/ReSTIRIntegrator.cpp:644,660,671,686) over the 64-frame orbit
   python tools/run_configs.py bias      static camera, 256 frames each: running mean of ReSTIR (as benchmarked, and without temporal
@@ -67,38 +68,81 @@ def run_frames(name, scene_name, W, H, n, **pk):
                           "scene_generation_s": gen_s}))
 
 
-def run_rays():
+def run_rays(scene_name="10m", target=33177600, cpu_sample=400000):
+    """configs[3]: shadow-ray-only throughput on the 10M-triangle BVH with the rays the path REALLY traces — the
+    visibility / temporal / spatial queues of consecutive 1080p frames (captured with rb_debug_ray_queue between the
+    phases of the frame), about 33 M of them = 16 as-written rays per pixel. Orders: as queued (pixel order: coherent
+    origins, a pixel's rays adjacent), shuffled (incoherent), and sorted by direction octant + origin Morton cell (what a
+    ray-reordering pass could achieve at best). CPU leg beside it: the oracle's BVH2 any-hit traversal
+    (Intersection::testOcclusion's arithmetic, P/Intersection.h:43-60) on all host cores over a random sample."""
     import torch
-    sc = scenes.scene_config("10m")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    sc = scenes.scene_config(scene_name)
     W, H = 1920, 1080
+    out = {"config": "rays (configs[3])"}
     with Renderer(W, H, seed=123) as r:
         st = r.upload_scene(sc)
+        out["scene"] = {k: st[k] for k in ("n_triangles", "n_emissive", "n_bvh_nodes", "bvh_depth", "build_ms")}
         r.set_params(params())
         c = sc.meta["center"]
-        r.render_frame(Camera(W, H, 55, scenes.orbit_position(c, 0), c), 0, fetch=False)
-        pos = r.readback(abi.BUF_GBUF_POS_DEPTH).reshape(-1, 4)
-        ids = r.readback(abi.BUF_HIT_IDS).reshape(-1, 2)
-        P = pos[ids[:, 0] != 0xFFFFFFFF, :3]
-        em = np.concatenate([p for p, _, m in sc.surfaces if sum(sc.materials[m]["emission"]) > 0], 0)
+        parts, mix, f = [], {"visibility": 0, "temporal": 0, "spatial": 0}, 0
+        while sum(len(p) for p in parts) < target and f < 8:
+            r.frame_begin(Camera(W, H, 55, scenes.orbit_position(c, f), c), f)
+            qv, qt = r.debug_ray_queue(1), (r.debug_ray_queue(0) if f > 0 else None)
+            r.frame_spatial(0)
+            qs = r.debug_ray_queue(0)
+            r.frame_end()
+            for name, q in (("visibility", qv), ("temporal", qt), ("spatial", qs)):
+                if q is not None and len(q):
+                    parts.append(q)
+                    mix[name] += len(q)
+            f += 1
+        rays = np.concatenate(parts)[:target]
+        n = rays.shape[0]
+        out.update(rays=int(n), frames_captured=f, queue_mix=mix)
         rng = np.random.default_rng(3)
-        per_px = 16
-        out = {"config": "rays", "scene": {k: st[k] for k in ("n_triangles", "n_bvh_nodes", "build_ms")}}
-        origins = np.repeat(P, per_px, axis=0)[: 33177600]
-        n = origins.shape[0]
-        k = rng.integers(0, len(em), n)
-        b = rng.random((n, 2), dtype=np.float32)
-        sq = np.sqrt(b[:, :1])
-        T = em[k, 0] * (1 - sq) + em[k, 1] * (sq * (1 - b[:, 1:])) + em[k, 2] * (sq * b[:, 1:])
-        rays = make_rays(origins, target=T.astype(np.float32))
-        for label, order in (("coherent", None), ("shuffled", rng.permutation(n))):
+        # direction octant (3 bits) + 30-bit Morton code of the origin cell
+        lo = rays["org"].min(0)
+        ext = np.maximum(rays["org"].max(0) - lo, 1e-6)
+        g = np.minimum(((rays["org"] - lo) / ext * 1024).astype(np.uint64), 1023)
+
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            return (v | (v << 2)) & 0x09249249
+        morton = spread(g[:, 0]) | (spread(g[:, 1]) << 1) | (spread(g[:, 2]) << 2)
+        octant = ((rays["dir"][:, 0] < 0).astype(np.uint64) | ((rays["dir"][:, 1] < 0).astype(np.uint64) << 1) |
+                  ((rays["dir"][:, 2] < 0).astype(np.uint64) << 2))
+        orders = (("as_queued", None), ("shuffled", rng.permutation(n)), ("sorted_octant_morton", np.argsort((octant << 30) | morton, kind="stable")))
+        for label, order in orders:
             rr = rays if order is None else rays[order]
             d_rays = torch.from_numpy(rr.view(np.uint8).reshape(-1)).cuda()
             d_occ = torch.empty(n, dtype=torch.uint8, device="cuda")
             torch.cuda.synchronize()
             ms = [r.trace_device(d_rays.data_ptr(), d_occ.data_ptr(), n, True) for _ in range(3)]
-            out[label] = {"rays": int(n), "ms": float(min(ms)), "mrays_s": n / (min(ms) * 1e-3) / 1e6,
-                          "occluded_fraction": float(d_occ.float().mean().item())}
-        print(json.dumps(out))
+            out[label] = {"ms": float(min(ms)), "mrays_s": n / (min(ms) * 1e-3) / 1e6, "occluded_fraction": float(d_occ.float().mean().item())}
+            if order is None:
+                occ_gpu = d_occ.cpu().numpy()
+            del d_rays, d_occ
+    # CPU leg: the oracle's BVH2 any-hit query on all host cores, random sample of the same rays
+    ob.set_num_threads(len(os.sched_getaffinity(0)))
+    o = ob.Oracle(8, 8, tracer=ob.TRACER_BVH2)
+    t0 = time.time()
+    o.upload_scene(sc)
+    build_s = time.time() - t0
+    idx = np.sort(rng.choice(n, size=min(cpu_sample, n), replace=False))
+    sample = np.ascontiguousarray(rays[idx])
+    o.trace_occluded(sample[:20000])  # warm the caches / thread pool
+    t0 = time.time()
+    occ_cpu = o.trace_occluded(sample)
+    dt = time.time() - t0
+    out["cpu"] = {"kind": "port (oracle BVH2, OpenMP)", "cores": ob.max_threads(), "rays": int(len(sample)), "ms": dt * 1e3,
+                  "mrays_s": len(sample) / dt / 1e6, "occluded_fraction": float(occ_cpu.mean()), "bvh2_build_s": build_s,
+                  "agrees_with_gpu": bool(np.array_equal(occ_cpu, occ_gpu[idx]))}
+    out["gpu_over_cpu_as_queued"] = out["as_queued"]["mrays_s"] / out["cpu"]["mrays_s"]
+    print(json.dumps(out))
 
 
 def run_orbit64():
@@ -239,6 +283,10 @@ if __name__ == "__main__":
         run_frames("configs[2] on one GPU", "10m", 3840, 2160, 6, spatialPassCount=3)
     elif what == "rays":
         run_rays()
+    elif what == "rays-1m":  # the same measurement on the bench scene
+        run_rays("1m")
+    elif what == "rays-small":  # quick functional check of the measurement itself
+        run_rays("small", target=2000000, cpu_sample=100000)
     elif what == "orbit64":
         run_orbit64()
     elif what == "textured":
