@@ -142,6 +142,7 @@ struct InlineVis {
   static constexpr bool kStore = true;
   const FrameCtx* fc;
   uint32_t pixel;
+  RB_HD void begin_post_selection() const {}
   RB_HD bool visible(int /*slot*/, const V3& from, const V3& to) const {
     return !test_occlusion(fc->sc, from, to, fc->P.tnearOffset, fc->P.tfarOffset);
   }
@@ -155,6 +156,7 @@ struct GenVis {
   static constexpr bool kStore = false;
   const FrameCtx* fc;
   uint32_t pixel;
+  RB_HD void begin_post_selection() const {}
   RB_HD void push(int slot, const V3& o, const V3& d, float tfar) const {
     const WaveBufs& w = fc->wave;
     const uint32_t i = queue_reserve(w.count);
@@ -196,6 +198,7 @@ struct ResolveVisT {
   static constexpr bool kStore = true;
   const FrameCtx* fc;
   uint32_t pixel;
+  RB_HD void begin_post_selection() const {}
   RB_HD bool visible(int slot, const V3& from, const V3& to) const {
     const WaveBufs& w = fc->wave;
     if (INLINE_SHADOW) return !test_occlusion(fc->sc, from, to, fc->P.tnearOffset, fc->P.tfarOffset);
@@ -210,6 +213,48 @@ struct ResolveVisT {
     return surface_from_hit<NMAP>(fc->sc, org, dir, hr);
   }
 };
+// StagedVis: the wavefront schedule of the spatial MIS modes whose ray count is not k + 1 (BALANCE_HEURISTIC: every
+// sample at every source pixel, O(k^2); PAIRWISE_MIS: O(k); the two CONSTANT_DEBIAS modes: k + 1 more rays that depend on
+// which sample was selected, P/ReSTIRIntegrator.cpp:407-467,494-538). spatial_pixel itself is run two or three times
+// with this policy; every visibility query takes the next slot of the pixel (the sequence of queries is the same in every
+// stage: before the selection it depends on the inputs only, after it on a selection that stages 2 and 3 both make from
+// traced answers):
+//   stage 1  queues the rays asked for before the selection, answers "visible"; rays after it are not queued;
+//   stage 2  (debias modes only) answers the former from the traced bytes — so the selection is the real one — and
+//            queues the rays asked for after it;
+//   stage 3  answers everything from the traced bytes and stores the reservoir.
+// The arithmetic is spatial_pixel's own in every stage, so the result is the inline kernel's bit for bit.
+template <int STAGE>
+struct StagedVis {
+  static constexpr bool kStore = STAGE == 3;
+  const FrameCtx* fc;
+  uint32_t pixel;
+  mutable uint32_t seq;
+  mutable bool post;
+  RB_HD void begin_post_selection() const { post = true; }
+  RB_HD bool visible(int /*slot*/, const V3& from, const V3& to) const {
+    const WaveBufs& w = fc->wave;
+    const uint32_t dest_slot = seq++;
+    if (STAGE == 3 || (STAGE == 2 && !post)) return w.occ[(size_t)dest_slot * w.npix + pixel] == 0;
+    if ((STAGE == 1 && !post) || (STAGE == 2 && post)) {
+      V3 dir;
+      float tfar;
+      shadow_ray(from, to, fc->P.tfarOffset, &dir, &tfar);
+      const uint32_t i = queue_reserve(w.count);
+      if (i < w.capacity) {
+        st4(&w.rays[i].o_tfar, f4(from, tfar));
+        st4(&w.rays[i].d_dest, f4(dir, u2f(dest_slot * w.npix + pixel)));
+      }
+    }
+    return true;
+  }
+};
+// visibility queries spatial_pixel can make per pixel with n = k + 1 resampling sources (slots of the staged schedule)
+RB_HD uint32_t spatial_staged_slots(int mode, uint32_t n) {
+  if (mode == RB_SW_BALANCE_HEURISTIC) return n * n + n;
+  if (mode == RB_SW_PAIRWISE_MIS) return 4u * n;
+  return 2u * n;  // CONSTANT_DEBIAS_Z_TERM / _CONTRIB: n resampling rays + n after the selection
+}
 typedef ResolveVisT<false> ResolveVis;
 typedef ResolveVisT<false, false> ResolveVisFlat;  // scenes without normal maps (see surface_from_hit)
 typedef ResolveVisT<true> ResolveInlineShadowVis;
@@ -1087,6 +1132,7 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   } else if (mode == RB_SW_CONSTANT_DEBIAS_Z_TERM) {
     int Z = 0;
     float correctionFactor = 1.0f;
+    vis.begin_post_selection();
     for (int i = 0; i < n; ++i) {
       const V3 pj = xyz(ld4(fc.G.pos_depth + nb[i]));
       cnt.anyW++;
@@ -1096,6 +1142,7 @@ RB_HD void spatial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
     if (Z > 0 && M > 0) correctionFactor = (1.0f / (float)Z) / rcpM;
     out.W = final_p_hat > 0.0f ? correctionFactor * out.w_sum / final_p_hat : 0.0f;
   } else if (mode == RB_SW_CONSTANT_DEBIAS_CONTRIB) {
+    vis.begin_post_selection();
     const Reservoir rs = load_reservoir(fc.Rread, nb[selectedSampleIndex]);
     float misNom = 0, misDenom = 0, contribWeight = 0, correctionFactor = 0;
     for (int i = 0; i < n; ++i) {

@@ -99,6 +99,23 @@ RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 4, temporal_merge_pixel(fc
 // the initial pass is the other way round
 RB_PIXEL_KERNEL(k_spatial_stream, GenVis, true, 3, spatial_gen_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 4, spatial_merge_pixel(fc, x, y, cnt))
+// the other spatial MIS modes in the wavefront schedule: spatial_pixel staged (StagedVis, rb_passes.cuh)
+#define RB_STAGED_KERNEL(NAME, STAGE, COUNT)                                                           \
+  __global__ void __launch_bounds__(kTileW* kTileH, 2) NAME(FrameCtx fc) {                            \
+    const int x = blockIdx.x * kTileW + threadIdx.x;                                                   \
+    const int y = fc.y0 + blockIdx.y * blockDim.y + threadIdx.y;                                       \
+    Cnt cnt = {0, 0, 0};                                                                               \
+    if (fc.wave.reset_pair != nullptr && (blockIdx.x | blockIdx.y | threadIdx.x | threadIdx.y) == 0)   \
+      fc.wave.reset_pair[0] = 0u, fc.wave.reset_pair[1] = 0u;                                          \
+    if (x < fc.width && y < fc.y1) {                                                                   \
+      const StagedVis<STAGE> vis = {&fc, (uint32_t)(y * fc.width + x), 0u, false};                     \
+      spatial_pixel(fc, x, y, vis, cnt);                                                               \
+    }                                                                                                  \
+    if (COUNT) flush_counts(fc.counters, cnt);                                                         \
+  }
+RB_STAGED_KERNEL(k_spatial_mis_stage1, 1, false)
+RB_STAGED_KERNEL(k_spatial_mis_stage2, 2, false)
+RB_STAGED_KERNEL(k_spatial_mis_stage3, 3, true)
 
 // accumulate + tonemap + gamma + statistics (N1). One thread per pixel; the two double sums are reduced per warp
 // and added with one atomic pair per warp (summation order is not fixed: results agree with a serial sum to
@@ -403,6 +420,7 @@ struct FrameState {
   FrameCtx ffc{};  // front half
   RbParams P{};
   bool open = false, timed = false, wave = false, wave_spatial = false;
+  bool wave_spatial_staged = false;  // non-constant spatial MIS mode in the wavefront schedule (StagedVis)
   bool shaded = false;  // the last spatial pass's resolve kernel has written frame_data already
   uint32_t launches = 0, frame_idx = 0;
   std::vector<FrameMark> marks;
@@ -1869,8 +1887,14 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   F.wave = P.wavefront != 0;
   // (the candidate records of the split spatial pass keep a pixel index in 27 bits)
   F.wave_spatial = F.wave && P.spatialWeightCalc == RB_SW_CONSTANT && (size_t)h->info.width * H < (1u << RB_CAND_INDEX_BITS);
+  // ... and, staged, the other spatial MIS modes while their slots per pixel stay moderate (BALANCE_HEURISTIC needs
+  // (k + 1)^2 + k + 1: up to k = 6; beyond that the pass traces inline as before)
+  const uint32_t staged_slots = spatial_staged_slots(P.spatialWeightCalc, (uint32_t)P.spatialReuseNeighborCount + 1u);
+  F.wave_spatial_staged = F.wave && P.doSpatialReuse && P.spatialWeightCalc != RB_SW_CONSTANT && staged_slots <= 64u &&
+                          (size_t)staged_slots * h->info.width * H < 0xFFFFFFF0ull && getenv("RB_STAGED_SPATIAL_OFF") == nullptr;
   if (F.wave) {
-    const uint32_t slots = std::max<uint32_t>(std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u), (uint32_t)P.M_Brdf);
+    uint32_t slots = std::max<uint32_t>(std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u), (uint32_t)P.M_Brdf);
+    if (F.wave_spatial_staged) slots = std::max(slots, staged_slots);
     uint32_t cand_slots = (F.wave_spatial && P.doSpatialReuse) ? (uint32_t)P.spatialReuseNeighborCount + 1u : 0u;
     if (P.doTemporalReuse) cand_slots = std::max(cand_slots, 2u);
     RB_TRY(ensure_wave(h, slots, (uint32_t)std::max(P.M_Brdf, 1), cand_slots));
@@ -2087,6 +2111,25 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
     if (F.shaded) RB_TRY(wait_frame_copy(h));
     launch_rows(h, k_spatial_resolve, y0, y1);
     fc.wave.fuse_shade = 0u;
+  } else if (F.wave_spatial_staged) {
+    // stage 1 (rays asked for before the selection) -> trace -> [debias modes: stage 2 (rays that depend on the
+    // selection) -> trace] -> stage 3 (everything answered, reservoir stored)
+    fs_reset_queue(h);
+    launch_rows(h, k_spatial_mis_stage1, iy0, iy1);
+    if (overlap_halo) {
+      RB_TRY(halo_exchange_wait(h));
+      launch_rows(h, k_spatial_mis_stage1, y0, iy0);
+      launch_rows(h, k_spatial_mis_stage1, iy1, y1);
+    }
+    fs_mark(h, 4, 0);
+    fs_trace(h, TRACE_ANY, 4);
+    if (P.spatialWeightCalc == RB_SW_CONSTANT_DEBIAS_Z_TERM || P.spatialWeightCalc == RB_SW_CONSTANT_DEBIAS_CONTRIB) {
+      fs_reset_queue(h);
+      launch_rows(h, k_spatial_mis_stage2, y0, y1);
+      fs_mark(h, 4, 0);
+      fs_trace(h, TRACE_ANY, 4);
+    }
+    launch_rows(h, k_spatial_mis_stage3, y0, y1);
   } else {
     launch_rows(h, k_spatial, iy0, iy1);
     if (overlap_halo) {

@@ -51,7 +51,7 @@ struct Emu {
   // in-flight frame (phases) and band bookkeeping
   FrameCtx fc{};
   RbParams Pf{};
-  bool open = false, wave = false, wave_spatial = false;
+  bool open = false, wave = false, wave_spatial = false, wave_spatial_staged = false;
   uint32_t frame_idx = 0, qcount = 0;
   int prevGy0 = 0, prevGy1 = 0;
   std::vector<RayQ> rays;
@@ -422,7 +422,10 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
   E->wave = P.wavefront != 0;
   E->wave_spatial = E->wave && P.spatialWeightCalc == RB_SW_CONSTANT && (size_t)E->width * E->height < (1u << RB_CAND_INDEX_BITS);
   const uint32_t npix = (uint32_t)(E->width * E->height);
-  const uint32_t slots = std::max<uint32_t>(std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u), (uint32_t)P.M_Brdf);
+  uint32_t slots = std::max<uint32_t>(std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u), (uint32_t)P.M_Brdf);
+  const uint32_t staged_slots = spatial_staged_slots(P.spatialWeightCalc, (uint32_t)P.spatialReuseNeighborCount + 1u);
+  E->wave_spatial_staged = E->wave && P.doSpatialReuse && P.spatialWeightCalc != RB_SW_CONSTANT && staged_slots <= 64u;
+  if (E->wave_spatial_staged) slots = std::max(slots, staged_slots);
   if (E->wave) {
     E->rays.resize((size_t)npix * std::max<uint32_t>(slots, (uint32_t)std::max(P.M_Brdf, 1)));
     E->occ.assign((size_t)npix * slots, 0xCD);
@@ -539,6 +542,15 @@ int emu_frame_spatial(void* h, int i) {
     emu_trace_queue(E, EMU_ANY);
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_merge_pixel(fc, x, y, c); });
     fc.wave.fuse_shade = 0u;
+  } else if (E->wave_spatial_staged) {  // as frame_spatial of restir_b200.cu: spatial_pixel staged (StagedVis)
+    const int mode = E->Pf.spatialWeightCalc;
+    emu_stream(E, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, StagedVis<1>{&fc, PX(fc, x, y), 0u, false}, c); });
+    emu_trace_queue(E, EMU_ANY);
+    if (mode == RB_SW_CONSTANT_DEBIAS_Z_TERM || mode == RB_SW_CONSTANT_DEBIAS_CONTRIB) {
+      emu_stream(E, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, StagedVis<2>{&fc, PX(fc, x, y), 0u, false}, c); });
+      emu_trace_queue(E, EMU_ANY);
+    }
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, StagedVis<3>{&fc, PX(fc, x, y), 0u, false}, c); });
   } else {
     for_pixels(E, fc, [&](int x, int y, Cnt& c) { spatial_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
   }

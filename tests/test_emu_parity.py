@@ -26,6 +26,13 @@ CONFIGS = [
     dict(M_Area=2, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, spatialWeightCalc=4, doVisibilityPass=1, wavefront=1),
     dict(M_Area=4, M_Brdf=0, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1, spatialReuseNeighborCount=8,
          rejectDissimilarNeighbors=1, wavefront=1),
+    # the other spatial MIS modes in the wavefront schedule (spatial_pixel staged: StagedVis)
+    dict(M_Area=3, M_Brdf=2, doSpatialReuse=1, doTemporalReuse=1, spatialWeightCalc=1, spatialPassCount=2, wavefront=1),
+    dict(M_Area=3, M_Brdf=2, doSpatialReuse=1, spatialWeightCalc=2, rejectDissimilarNeighbors=1, wavefront=1),
+    dict(M_Area=2, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, spatialWeightCalc=3, spatialReuseNeighborCount=3, wavefront=1),
+    dict(M_Area=2, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, spatialWeightCalc=4, spatialPassCount=2, wavefront=1),
+    # BALANCE_HEURISTIC with k = 7: 72 slots per pixel, over the staged schedule's limit -> the pass traces inline
+    dict(M_Area=2, M_Brdf=1, doSpatialReuse=1, spatialWeightCalc=1, spatialReuseNeighborCount=7, wavefront=1),
 ]
 
 ALL_BUFS = (abi.BUF_HIT_IDS, abi.BUF_GBUF_POS_DEPTH, abi.BUF_GBUF_NORMAL_SHIN, abi.BUF_GBUF_DIFFUSE_IIM,

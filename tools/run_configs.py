@@ -145,6 +145,40 @@ def run_rays(scene_name="10m", target=33177600, cpu_sample=400000):
     print(json.dumps(out))
 
 
+def run_modes():
+    """the five spatial MIS modes (P/ReSTIRIntegrator.h:19-25) at the bench settings (1080p, 1M triangles, A=32 B=1,
+    visibility + temporal + 1 spatial pass k=5), each in the wavefront schedule (CONSTANT: stream / trace / resolve kernels; the
+    others: spatial_pixel staged, StagedVis) and with the spatial pass traced inline (RB_STAGED_SPATIAL_OFF=1, round 1's path).
+    The reference's own timings of the O(k^2) and O(k) modes: S/s_k_gris_5.png.txt 1.156 s, S/s_k_pair_5.png.txt 0.851 s (640x480,
+    A=1 B=1, spatial only, unknown CPU)."""
+    sc = scenes.scene_config("1m")
+    W, H = 1920, 1080
+    names = ["CONSTANT", "BALANCE_HEURISTIC", "PAIRWISE_MIS", "CONSTANT_DEBIAS_Z_TERM", "CONSTANT_DEBIAS_CONTRIB"]
+    out = {"config": "spatial MIS modes (N4)", "width": W, "height": H, "modes": {}}
+    for staged in (True, False):
+        if staged:
+            os.environ.pop("RB_STAGED_SPATIAL_OFF", None)
+        else:
+            os.environ["RB_STAGED_SPATIAL_OFF"] = "1"
+        with Renderer(W, H, seed=123) as r:
+            r.upload_scene(sc)
+            for m, name in enumerate(names):
+                if m == 0 and not staged:
+                    continue
+                r.set_params(params(spatialWeightCalc=m))
+                ms, t = frames(r, sc, W, H, 12)
+                d = out["modes"].setdefault(name, {})
+                key = "wavefront" if staged else "inline_spatial"
+                d[key] = {"ms_per_frame": ms, "fps": 1e3 / ms, "ms_spatial_pass": t["ms_spatial"],
+                          "rays_any_traced": t["rays_any_traced"], "rays_any_as_written": t["rays_any_as_written"]}
+    for name, d in out["modes"].items():
+        if "inline_spatial" in d:
+            d["speedup_spatial_pass"] = d["inline_spatial"]["ms_spatial_pass"] / d["wavefront"]["ms_spatial_pass"]
+    out["reference_seconds_640x480_A1_B1_spatial_only_k5"] = {"CONSTANT (st_k_spatial)": 0.954, "BALANCE_HEURISTIC (s_k_gris_5)": 1.156,
+                                                             "PAIRWISE_MIS (s_k_pair_5)": 0.851}
+    print(json.dumps(out))
+
+
 def run_orbit64():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
@@ -289,6 +323,8 @@ if __name__ == "__main__":
         run_rays("small", target=2000000, cpu_sample=100000)
     elif what == "orbit64":
         run_orbit64()
+    elif what == "modes":
+        run_modes()
     elif what == "textured":
         run_textured()
     elif what == "bias":
