@@ -127,6 +127,11 @@ typedef struct RbParams {
   int32_t useSkybox;                 /* reference default 1; here 0 until a sky texture was given (rb_set_sky) */
   int32_t lightSampler;              /* RbLightSampler; reference = CDF */
   int32_t wavefront;                 /* 0: every pass traces its rays inline; 1: stream->trace->resolve split */
+  int32_t temporalFetchReprojected;  /* 0 = the reference: temporal reuse merges last frame's reservoir of the SAME pixel
+                                        (getReservoirLastFrame(pixelCoords), P/ReSTIRIntegrator.cpp:641), although it
+                                        validates the reprojected one; 1 = the repaired variant: the reservoir of the
+                                        backward-reprojected pixel. Single band only (bands would need last-frame
+                                        reservoir halos): rb_render_frame refuses 1 on a banded handle. ABI version 2. */
 } RbParams;
 
 /* What produceRestir copies out of Camera into GBuffer each frame

@@ -968,7 +968,8 @@ struct Oracle {
     bool ok = reproject(gBufferLastFrame, currentElem.worldSpacePos, &px, &py);
     const Reservoir currentReservoir = R_read(x, y);
     const LightSample& currentSample = currentReservoir.bestSample;
-    const Reservoir prevReservoir = R_last(x, y);  // same pixel, not the reprojected one (:641)
+    // same pixel, not the reprojected one (:641); temporalFetchReprojected = the repaired variant (no reference behaviour)
+    const Reservoir prevReservoir = (P.temporalFetchReprojected && ok) ? R_last(px, py) : R_last(x, y);
     const LightSample& prevSample = prevReservoir.bestSample;
     uint64_t* tstat = ctrs[thread_id()].temporal;
     if (!ok) {

@@ -97,7 +97,7 @@ class RbParams(C.Structure):
                 ("rejectDissimilarNeighbors", C.c_int32), ("spatialWeightCalc", C.c_int32),
                 ("tnearOffset", C.c_float), ("tfarOffset", C.c_float), ("normalOffset", C.c_float),
                 ("bgColor", C.c_float * 3), ("useSkybox", C.c_int32), ("lightSampler", C.c_int32),
-                ("wavefront", C.c_int32)]
+                ("wavefront", C.c_int32), ("temporalFetchReprojected", C.c_int32)]
 
 
 def default_params(**overrides):
@@ -114,6 +114,7 @@ def default_params(**overrides):
     p.useSkybox = 0
     p.lightSampler = LS_CDF
     p.wavefront = 0
+    p.temporalFetchReprojected = 0
     for k, v in overrides.items():
         if not hasattr(p, k):
             raise AttributeError(k)

@@ -815,7 +815,8 @@ RB_HD void temporal_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt&
     if (Vis::kStore) store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
-  const Reservoir prev = load_reservoir(fc.Rlast, pi);  // same pixel, not the reprojected one (:641)
+  // same pixel, not the reprojected one (:641) — unless the repaired variant is asked for
+  const Reservoir prev = load_reservoir(fc.Rlast, P.temporalFetchReprojected ? (size_t)py * fc.width + px : pi);
   const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
   const Shading shCur = make_shading(curElem, curCam), shPrev = make_shading(prevElem, prevCam);
 
@@ -920,7 +921,10 @@ RB_HD void temporal_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vi
     return;
   }
   const Reservoir cur = load_reservoir(fc.Rread, pi);
-  const Reservoir prev = load_reservoir(fc.Rlast, pi);  // same pixel, not the reprojected one (:641)
+  // same pixel, not the reprojected one (:641) — unless the repaired variant is asked for (the resolve half finds the
+  // pixel index in the flags record)
+  const uint32_t prev_pi = fc.P.temporalFetchReprojected ? (uint32_t)(py * fc.width + px) : (uint32_t)pi;
+  const Reservoir prev = load_reservoir(fc.Rlast, prev_pi);
   const Shading shCur = make_shading(curElem, curCam), shPrev = make_shading(prevElem, prevCam);
   const VisMode modeA = vis_mode_from_W(cur.W, true);
   const VisMode modeB = cur.W == 0.0f ? VIS_IRRELEVANT : VIS_TRACE;
@@ -956,20 +960,21 @@ RB_HD void temporal_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis& vi
         vis.visible_at(qi++, e, ((e & 1) ? prevElem : curElem).pos, (e < 2 ? cur.bestSample : prev.bestSample).samplePoint);
   }
   wv.cand[pi] = U4{f2u(ph[0]), f2u(ph[1]), f2u(ph[2]), f2u(ph[3])};
-  *rec_flags = U4{flags, 0u, 0u, 0u};
+  *rec_flags = U4{flags, prev_pi, 0u, 0u};
 }
 
 RB_HD void temporal_merge_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
   const size_t pi = (size_t)y * fc.width + x;
   const RbParams& P = fc.P;
   const WaveBufs& wv = fc.wave;
-  const uint32_t flags = wv.cand[(size_t)wv.npix + pi].x;
+  const U4 frec = wv.cand[(size_t)wv.npix + pi];
+  const uint32_t flags = frec.x;
   const Reservoir cur = load_reservoir(fc.Rread, pi);
   if (flags & RB_TEMPORAL_KEEP) {
     store_reservoir(fc.Rwrite, pi, cur);
     return;
   }
-  const Reservoir prev = load_reservoir(fc.Rlast, pi);
+  const Reservoir prev = load_reservoir(fc.Rlast, P.temporalFetchReprojected ? (size_t)frec.y : pi);
   const U4 rec = wv.cand[pi];
   const uint32_t key = rng_pixel_key(fc.frame_key, (uint32_t)pi);
   float v[4] = {u2f(rec.x), u2f(rec.y), u2f(rec.z), u2f(rec.w)};

@@ -1876,6 +1876,10 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
     h->err = "rb_render_frame: band is thinner than the spatial reuse reach";
     return RB_ERR_UNSUPPORTED;
   }
+  if (banded && P.doTemporalReuse && P.temporalFetchReprojected) {
+    h->err = "rb_render_frame: temporalFetchReprojected needs the whole image on one handle (last-frame reservoirs of other bands)";
+    return RB_ERR_UNSUPPORTED;
+  }
   F.timed = timed;
   F.marks.clear();
   F.launches = 0;

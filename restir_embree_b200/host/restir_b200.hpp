@@ -57,6 +57,7 @@ struct ReSTIRIntegrator {
   // seams added by this build
   bool aliasLightSampler{true};
   bool wavefront{true};
+  bool temporalFetchReprojected{false};  // true: merge the reservoir of the reprojected pixel (the reference reads the same pixel, :641)
 
   RbParams toAbi() const {
     RbParams p;
@@ -73,6 +74,7 @@ struct ReSTIRIntegrator {
     p.useSkybox = renderParams.useSkybox;
     p.lightSampler = aliasLightSampler ? RB_LS_ALIAS : RB_LS_CDF;
     p.wavefront = wavefront;
+    p.temporalFetchReprojected = temporalFetchReprojected;
     return p;
   }
 };

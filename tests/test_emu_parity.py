@@ -31,6 +31,9 @@ CONFIGS = [
     dict(M_Area=3, M_Brdf=2, doSpatialReuse=1, spatialWeightCalc=2, rejectDissimilarNeighbors=1, wavefront=1),
     dict(M_Area=2, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, spatialWeightCalc=3, spatialReuseNeighborCount=3, wavefront=1),
     dict(M_Area=2, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, spatialWeightCalc=4, spatialPassCount=2, wavefront=1),
+    # the repaired temporal fetch (last frame's reservoir of the REPROJECTED pixel; the reference reads the same pixel, :641)
+    dict(M_Area=4, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, temporalFetchReprojected=1),
+    dict(M_Area=4, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1, temporalFetchReprojected=1, wavefront=1),
     # BALANCE_HEURISTIC with k = 7: 72 slots per pixel, over the staged schedule's limit -> the pass traces inline
     dict(M_Area=2, M_Brdf=1, doSpatialReuse=1, spatialWeightCalc=1, spatialReuseNeighborCount=7, wavefront=1),
 ]
@@ -67,6 +70,19 @@ def test_emulated_kernels_match_oracle_bit_for_bit(small, ci):
         oc, ec = o.counters(), e.counters()
         assert oc["closest"] == ec["closest"] and oc["any_as_written"] == ec["any_as_written"]
         assert ec["any_traced"] <= ec["any_as_written"]
+
+
+def test_temporal_fetch_reprojected_is_a_different_estimator_under_camera_motion(small):
+    """the flag must actually change what is merged (otherwise the two configs above would pass vacuously)"""
+    imgs = []
+    for flag in (0, 1):
+        e = eb.Emu(W, H, seed=7)
+        e.upload_scene(small)
+        e.set_params(abi.default_params(M_Area=4, M_Brdf=1, doTemporalReuse=1, temporalFetchReprojected=flag))
+        for f in range(3):
+            img = e.render_frame(Camera(W, H, 60, (4.2 + 0.4 * f, -4.4, 1.8), (0, 0, 1.0)), f)
+        imgs.append(img)
+    assert (imgs[0] != imgs[1]).any(-1).mean() > 0.05
 
 
 def test_emulated_traversal_matches_brute_force_on_random_rays():
