@@ -85,8 +85,9 @@ typedef struct RbMaterial {
 /* One surface == one Embree geometry (geomID = index, attach order),
  * exactly what ModelLoader::loadScene hands Embree, P/ModelLoader.cpp:227-318:
  * non-indexed triangle soup, 3*n_tris vertices, identity index buffer (:297-299).
- * uv may be NULL (treated as zero; read by textured materials, rb_set_textures); tangent is accepted and ignored
- * (normal maps are out of scope of this ABI version). */
+ * uv may be NULL (treated as zero; read by textured materials, rb_set_textures); tangent may be NULL (attribute slot 3 of
+ * the reference's geometry, P/ModelLoader.cpp:286-287: kept at upload and read by materials with a normal map, which
+ * rb_set_textures refuses for a scene uploaded without tangents). */
 typedef struct RbSurface {
   uint32_t n_tris;
   uint32_t material;    /* index into RbSceneDesc.materials */
@@ -112,7 +113,7 @@ typedef struct RbParams {
   int32_t spatialReuseNeighborCount; /* 5  */
   int32_t spatialPassCount;          /* 1  */
   int32_t confidenceCap;             /* 20 */
-  float spatialReuseRadius;          /* 30 (reach is floor(sqrt(radius)) px, P/Sampling.cpp:78-87) */
+  float spatialReuseRadius;          /* 30 (offsets are < sqrt(radius) px, P/Sampling.cpp:78-87; halo reach = floor(sqrt(radius)) + 1 rows) */
   float minNormalSimilarity;         /* 0.85 */
   float maxDepthDifference;          /* 0.2  */
   int32_t doSpatialReuse;            /* 0 */
@@ -382,12 +383,18 @@ void rb_obj_free(RbObjScene* s);
  *
  * Load balancing: image bands do not cost the same (ceiling vs. floor), and a halo exchange is a rendezvous, so the
  * slowest band sets the frame rate. With a communicator attached the library therefore moves the band boundaries:
- * every 8th frame end (RB_BAL_PERIOD) each rank sends its neighbours the last-frame reservoirs of the 16 rows next to
- * the boundary and its own frame cost (GPU time minus time spent waiting for neighbours; CUDA events), and at the
- * start of the next frame both ranks that share a boundary move it by the same damped step (<= 15 rows) computed from the same
- * two numbers. Rows that change owner find their last-frame reservoirs already there and their previous G-buffer in
- * the margin; the image stays bit-identical to the one-band image (tools/check_nccl_bands.py). RB_BALANCE=0 turns it
- * off; rb_get_band reports the rows currently owned (rb_render_frame writes exactly those rows of frame_rgb_out). */
+ * at the end of every 8th frame (RB_BAL_PERIOD) each rank sends its neighbours the last-frame reservoirs of the 16 rows
+ * next to each boundary and ALL ranks all-gather {cost, rows} (cost = GPU time between the ends of two consecutive back
+ * halves minus the time spent waiting for neighbours, CUDA events, mean of up to four frames). At the start of the next
+ * frame every rank computes the same equal-cost partition from the same gathered numbers and moves each boundary half of
+ * the way towards its target, at most 15 rows. Rows that change owner find their last-frame reservoirs already there,
+ * their previous G-buffer in the over-rendered margin, and their ACCUMULATOR rows (rb_accumulate_display) are sent along
+ * when the move is applied; the image and the running mean stay bit-identical to the one-band ones
+ * (tools/check_nccl_bands.py). Balancing is switched off for all ranks together when any band is thinner than 32 rows.
+ * RB_BALANCE=0 turns it off; rb_get_band reports the rows currently owned (rb_render_frame writes exactly those rows of
+ * frame_rgb_out). A halo wait that times out (RB_HALO_TIMEOUT_MS, default 5 s; 60 s for the first exchanges) fails
+ * the frame at its next synchronisation point (rb_render_frame, rb_frame_wait, rb_synchronize, rb_readback) with
+ * RB_ERR_COMM and is then forgotten: the next frame may succeed. A second rb_comm_init on a handle is refused. */
 int rb_comm_unique_id(void* out_id, size_t id_bytes);
 int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id, size_t id_bytes);
 int32_t rb_comm_transport(RbHandle h); /* 0 = no communicator, 1 = peer memory (CUDA IPC), 2 = NCCL send/recv */
@@ -422,6 +429,37 @@ size_t rb_halo_bytes(RbHandle h, int32_t rows);
 int rb_halo_export(RbHandle h, int32_t y, int32_t rows, void* dst_host);
 int rb_halo_import(RbHandle h, int32_t y, int32_t rows, const void* src_host);
 
+/* ---- One handle, several GPUs, one host thread -----------------------------------------------------
+ * The reference is ONE process whose single Producer thread calls produceRestir (P/simpleguidx11.cpp:240-241, thread
+ * created :499). rb_multi_* is the same seam for a host that wants N GPUs without N processes and without handing an
+ * ncclUniqueId around: rb_multi_create makes one band handle per listed device (bands of ceil(height / n) rows, top to
+ * bottom; the same ordinal may be listed several times — several bands on one GPU, used by the tests), connects
+ * neighbours with peer access (cudaDeviceEnablePeerAccess: the halo rows are stored straight into the neighbour's
+ * planes by the same k_halo_push / k_halo_wait kernels as between processes; no NCCL, no IPC), and every call below
+ * fans out from the calling thread. rb_multi_render_frame[_async] issues the frame on every device and copies every
+ * band's rows into the ONE host buffer frame_rgb_out (w*h*3 floats): the caller holds the assembled frame, as the
+ * Producer expects. The image is bit-identical to the single-handle image. Bands are static in this mode (the cost
+ * balancer of rb_comm_init moves rows between processes through NCCL; an in-process equivalent is not built).
+ * rb_multi_member gives the band handle of device i for queries the family does not wrap (rb_scene_stats,
+ * rb_get_band, rb_trace_*). Errors: rb_multi_last_error (NULL: of the last failed rb_multi_create). ABI version 2. */
+typedef struct RbMulti* RbMultiHandle;
+int rb_multi_create(const RbCreateInfo* info /* device, band_y0/1 ignored */, const int32_t* device_ordinals, int32_t n_devices,
+                    RbMultiHandle* out);
+void rb_multi_destroy(RbMultiHandle m);
+const char* rb_multi_last_error(RbMultiHandle m);
+int32_t rb_multi_device_count(RbMultiHandle m);
+RbHandle rb_multi_member(RbMultiHandle m, int32_t i);
+int rb_multi_upload_scene(RbMultiHandle m, const RbSceneDesc* scene);
+int rb_multi_set_params(RbMultiHandle m, const RbParams* params);
+int rb_multi_set_textures(RbMultiHandle m, const RbTexture* textures, uint32_t n_textures, const RbMaterialTextures* per_material,
+                          uint32_t n_materials);
+int rb_multi_set_sky(RbMultiHandle m, const RbTexture* sky);
+int rb_multi_render_frame(RbMultiHandle m, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_out);
+int rb_multi_render_frame_async(RbMultiHandle m, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_out);
+int rb_multi_frame_wait(RbMultiHandle m, uint32_t frames_in_flight);
+int rb_multi_synchronize(RbMultiHandle m);
+int rb_multi_readback(RbMultiHandle m, int buffer_id, void* dst, size_t bytes); /* bands assembled */
+
 /* ---- The step after the path: SimpleGuiDX11::Producer's accumulate / tonemap / statistics loops,
  * P/simpleguidx11.cpp:246-253 (accumulator = glm::mix(accumulator, frame_data, 1 / (accFrameCtr + 1))), :262-295
  * (display_data = {compress(aces(accumulator)), 1}: Utils::aces P/utils.cpp:190-197 when RenderParams::tonemap,
@@ -439,6 +477,8 @@ typedef struct RbImageStats {
 } RbImageStats;
 int rb_accumulate_display(RbHandle h, uint32_t acc_frame_ctr, int32_t tonemap, int32_t gamma_correct,
                           float* display_rgba_out, RbImageStats* stats);
+int rb_multi_accumulate_display(RbMultiHandle m, uint32_t acc_frame_ctr, int32_t tonemap, int32_t gamma_correct,
+                                float* display_rgba_out, RbImageStats* stats); /* all bands; statistics of the whole image */
 
 #ifdef __cplusplus
 }

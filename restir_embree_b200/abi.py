@@ -186,7 +186,7 @@ EXPORTED_SYMBOLS = [
     "rb_set_params", "rb_set_textures", "rb_set_sky", "rb_render_frame", "rb_render_frame_device", "rb_render_frame_async", "rb_frame_wait", "rb_render_mis_frame", "rb_readback", "rb_synchronize", "rb_timer_begin", "rb_timer_end",
     "rb_trace_closest",
     "rb_trace_occluded", "rb_trace_closest_device", "rb_trace_occluded_device", "rb_scene_stats", "rb_comm_init",
-    "rb_comm_unique_id", "rb_comm_transport", "rb_debug_balance_step", "rb_debug_ray_queue", "rb_obj_load", "rb_obj_scene_desc",
+    "rb_comm_unique_id", "rb_comm_transport", "rb_debug_balance_step", "rb_debug_ray_queue", "rb_multi_create", "rb_multi_destroy", "rb_multi_last_error", "rb_multi_device_count", "rb_multi_member", "rb_multi_upload_scene", "rb_multi_set_params", "rb_multi_set_textures", "rb_multi_set_sky", "rb_multi_render_frame", "rb_multi_render_frame_async", "rb_multi_frame_wait", "rb_multi_synchronize", "rb_multi_readback", "rb_multi_accumulate_display", "rb_obj_load", "rb_obj_scene_desc",
     "rb_obj_material_name", "rb_obj_texture_name", "rb_obj_free", "rb_halo_bytes", "rb_halo_export", "rb_halo_import", "rb_halo_rows", "rb_frame_begin",
     "rb_frame_spatial", "rb_frame_end", "rb_accumulate_display", "rb_set_band", "rb_get_band",
 ]

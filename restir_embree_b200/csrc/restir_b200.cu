@@ -486,6 +486,9 @@ struct RbContext {
   // halo rows over peer memory (k_halo_push / k_halo_wait): the neighbours' reservoir planes and flag words mapped with
   // CUDA IPC in rb_comm_init; RB_HALO=nccl (or a failed mapping on any rank) keeps the grouped ncclSend/ncclRecv path
   bool p2p = false;
+  // member of an in-process multi-device group (rb_multi_create): the neighbours' planes are plain peer pointers
+  // (cudaDeviceEnablePeerAccess), no communicator, no IPC mappings; static bands (no balancer)
+  bool localGroup = false;
   void* peerBase[2][17]{};      // cudaIpcOpenMemHandle results, [above, below][16 planes + flags]
   ResPlanes peerR[2][4]{};
   uint32_t* peerFlags[2]{};
@@ -640,7 +643,7 @@ bool load_nccl(std::string& err) {
 static int halo_push_p2p(RbContext* h);
 static int halo_wait_p2p(RbContext* h);
 static int halo_exchange_begin(RbContext* h) {
-  if (!h->comm) return RB_OK;
+  if (!h->comm && !h->localGroup) return RB_OK;
   if (h->p2p) return halo_push_p2p(h);
   const int y0 = h->info.band_y0, y1 = h->info.band_y1, W = h->info.width, H = h->info.height;
   const int R = spatial_reach(h->fs.P);
@@ -682,7 +685,7 @@ static int wait_recording_stall(RbContext* h, cudaEvent_t ev) {
   return RB_OK;
 }
 static int halo_exchange_wait(RbContext* h) {
-  if (!h->comm) return RB_OK;
+  if (!h->comm && !h->localGroup) return RB_OK;
   if (h->p2p) return halo_wait_p2p(h);
   return wait_recording_stall(h, h->evHaloDone);
 }
@@ -1860,6 +1863,31 @@ static int wait_frame_copy(RbContext* h) {
   return RB_OK;
 }
 
+// everything a frame may have to ALLOCATE for the current parameters (wavefront queues); frame_begin repeats the call,
+// which is then a no-op. rb_multi_render_frame_async runs it on every device before it queues the first kernel.
+static uint32_t frame_wave_slots(const RbContext* h, const RbParams& P, uint32_t* brdf_slots, uint32_t* cand_slots, bool* staged) {
+  const int H = h->info.height;
+  const bool wave = P.wavefront != 0;
+  const bool wave_spatial = wave && P.spatialWeightCalc == RB_SW_CONSTANT && (size_t)h->info.width * H < (1u << RB_CAND_INDEX_BITS);
+  const uint32_t staged_slots = spatial_staged_slots(P.spatialWeightCalc, (uint32_t)P.spatialReuseNeighborCount + 1u);
+  *staged = wave && P.doSpatialReuse && P.spatialWeightCalc != RB_SW_CONSTANT && staged_slots <= 64u &&
+            (size_t)staged_slots * h->info.width * H < 0xFFFFFFF0ull && getenv("RB_STAGED_SPATIAL_OFF") == nullptr;
+  uint32_t slots = std::max<uint32_t>(std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u), (uint32_t)P.M_Brdf);
+  if (*staged) slots = std::max(slots, staged_slots);
+  *cand_slots = (wave_spatial && P.doSpatialReuse) ? (uint32_t)P.spatialReuseNeighborCount + 1u : 0u;
+  if (P.doTemporalReuse) *cand_slots = std::max(*cand_slots, 2u);
+  *brdf_slots = (uint32_t)std::max(P.M_Brdf, 1);
+  return slots;
+}
+static int frame_prepare(RbContext* h) {
+  if (!h->haveScene || !h->params.wavefront) return RB_OK;
+  RB_CUDA(cudaSetDevice(h->info.device));
+  uint32_t brdf_slots = 1, cand_slots = 0;
+  bool staged = false;
+  const uint32_t slots = frame_wave_slots(h, h->params, &brdf_slots, &cand_slots, &staged);
+  return ensure_wave(h, slots, brdf_slots, cand_slots);
+}
+
 static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool timed) {
   if (!h || !cam) return RB_ERR_INVALID_ARGUMENT;
   if (!h->haveScene) {
@@ -1893,15 +1921,10 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   F.wave_spatial = F.wave && P.spatialWeightCalc == RB_SW_CONSTANT && (size_t)h->info.width * H < (1u << RB_CAND_INDEX_BITS);
   // ... and, staged, the other spatial MIS modes while their slots per pixel stay moderate (BALANCE_HEURISTIC needs
   // (k + 1)^2 + k + 1: up to k = 6; beyond that the pass traces inline as before)
-  const uint32_t staged_slots = spatial_staged_slots(P.spatialWeightCalc, (uint32_t)P.spatialReuseNeighborCount + 1u);
-  F.wave_spatial_staged = F.wave && P.doSpatialReuse && P.spatialWeightCalc != RB_SW_CONSTANT && staged_slots <= 64u &&
-                          (size_t)staged_slots * h->info.width * H < 0xFFFFFFF0ull && getenv("RB_STAGED_SPATIAL_OFF") == nullptr;
-  if (F.wave) {
-    uint32_t slots = std::max<uint32_t>(std::max<uint32_t>(4u, (uint32_t)P.spatialReuseNeighborCount + 1u), (uint32_t)P.M_Brdf);
-    if (F.wave_spatial_staged) slots = std::max(slots, staged_slots);
-    uint32_t cand_slots = (F.wave_spatial && P.doSpatialReuse) ? (uint32_t)P.spatialReuseNeighborCount + 1u : 0u;
-    if (P.doTemporalReuse) cand_slots = std::max(cand_slots, 2u);
-    RB_TRY(ensure_wave(h, slots, (uint32_t)std::max(P.M_Brdf, 1), cand_slots));
+  {
+    uint32_t brdf_slots = 1, cand_slots = 0;
+    const uint32_t slots = frame_wave_slots(h, P, &brdf_slots, &cand_slots, &F.wave_spatial_staged);
+    if (F.wave) RB_TRY(ensure_wave(h, slots, brdf_slots, cand_slots));
   }
   cudaStream_t st = h->stream;
   // ---- FRONT half: G-buffer + initial candidates of this frame (depends on the camera only) ---------------------
@@ -2218,7 +2241,7 @@ static int render_frame_impl(RbHandle h, const RbCamera* cam, uint32_t frame_idx
   RB_TRY(balance_update_band(h));
   RB_TRY(frame_begin(h, cam, frame_idx, timed));
   if (h->fs.P.doSpatialReuse)
-    for (int i = 0; i < h->fs.P.spatialPassCount; ++i) RB_TRY(frame_spatial(h, i, h->comm != nullptr));
+    for (int i = 0; i < h->fs.P.spatialPassCount; ++i) RB_TRY(frame_spatial(h, i, h->comm != nullptr || h->localGroup));
   return frame_end(h, timings);
 }
 
@@ -2665,7 +2688,7 @@ const char* rb_obj_texture_name(const RbObjScene* s, uint32_t i, int32_t slot) {
 }
 void rb_obj_free(RbObjScene* s) { delete s; }
 
-int32_t rb_comm_transport(RbHandle h) { return (!h || !h->comm) ? 0 : (h->p2p ? 1 : 2); }
+int32_t rb_comm_transport(RbHandle h) { return !h ? 0 : (h->localGroup ? 1 : (!h->comm ? 0 : (h->p2p ? 1 : 2))); }
 static int comm_init_body(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_unique_id) {
   RB_CUDA(cudaSetDevice(h->info.device));
   NcclId128 id;
@@ -2726,8 +2749,8 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
     h->err = "rb_comm_init: more than 64 ranks";
     return RB_ERR_UNSUPPORTED;
   }
-  if (h->comm) {
-    h->err = "rb_comm_init: this handle already has a communicator";
+  if (h->comm || h->localGroup) {
+    h->err = "rb_comm_init: this handle already has a communicator (or belongs to an rb_multi group)";
     return RB_ERR_INVALID_ARGUMENT;
   }
   if (h->fs.open) {
@@ -2745,3 +2768,214 @@ int rb_comm_init(RbHandle h, int32_t rank, int32_t nranks, const void* nccl_uniq
 }
 
 }  // extern "C"
+
+// -------------------------------------------------------------------------------------
+// one handle, several GPUs, one host thread (the reference is ONE process with ONE Producer thread,
+// P/simpleguidx11.cpp:499). rb_multi_* drives N band handles — one per listed device — from the calling thread: the
+// scene is uploaded to every device, a frame is issued band by band (everything asynchronous), the halo rows travel
+// through the same k_halo_push / k_halo_wait kernels as between processes, over plain peer pointers
+// (cudaDeviceEnablePeerAccess; no NCCL, no IPC), and every band's rows land in ONE host frame_data buffer.
+// Static bands of equal height (the in-process balancer is not built: rows that change owner would have to take
+// their last-frame reservoirs and accumulator rows along, which rb_comm_init's balancer does through NCCL).
+// -------------------------------------------------------------------------------------
+struct RbMulti {
+  std::vector<RbContext*> m;
+  std::string err;
+  int width = 0, height = 0;
+};
+static thread_local std::string g_multi_create_error;
+
+static int multi_fail(RbMulti* M, RbContext* h, int rc) {
+  M->err = h ? h->err : std::string("rb_multi: invalid argument");
+  return rc;
+}
+// neighbours see each other's reservoir planes and flag words directly
+static int local_group_link(RbMulti* M) {
+  const int n = (int)M->m.size();
+  for (int i = 0; i < n; ++i) {
+    RbContext* h = M->m[i];
+    RB_CUDA(cudaSetDevice(h->info.device));
+    RB_CUDA(cudaMalloc((void**)&h->haloFlags, 4 * sizeof(uint32_t)));
+    RB_CUDA(cudaMemset(h->haloFlags, 0, 4 * sizeof(uint32_t)));
+    RB_CUDA(cudaHostAlloc((void**)&h->haloErr, sizeof(uint32_t), cudaHostAllocMapped));
+    *h->haloErr = 0u;
+    h->haloSeq = 0;
+    h->commRank = i;
+    h->commSize = n;
+    h->localGroup = true;
+    h->balance = false;
+    h->p2p = true;
+  }
+  for (int i = 0; i < n; ++i) {
+    RbContext* h = M->m[i];
+    RB_CUDA(cudaSetDevice(h->info.device));
+    for (int d = 0; d < 2; ++d) {
+      const int j = d == 0 ? i - 1 : i + 1;
+      if (j < 0 || j >= n) continue;
+      RbContext* q = M->m[j];
+      if (q->info.device != h->info.device) {
+        int can = 0;
+        RB_CUDA(cudaDeviceCanAccessPeer(&can, h->info.device, q->info.device));
+        if (!can) {
+          h->err = "rb_multi_create: devices " + std::to_string(h->info.device) + " and " + std::to_string(q->info.device) + " have no peer access";
+          return RB_ERR_UNSUPPORTED;
+        }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(q->info.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          h->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+          return RB_ERR_CUDA;
+        }
+        (void)cudaGetLastError();
+      }
+      for (int b = 0; b < 4; ++b) h->peerR[d][b] = q->R[b];
+      h->peerFlags[d] = q->haloFlags;
+    }
+  }
+  return RB_OK;
+}
+
+extern "C" {
+
+const char* rb_multi_last_error(RbMulti* M) { return M ? M->err.c_str() : g_multi_create_error.c_str(); }
+int32_t rb_multi_device_count(RbMulti* M) { return M ? (int32_t)M->m.size() : 0; }
+RbHandle rb_multi_member(RbMulti* M, int32_t i) { return (M && i >= 0 && i < (int32_t)M->m.size()) ? M->m[i] : nullptr; }
+
+void rb_multi_destroy(RbMulti* M) {
+  if (!M) return;
+  for (RbContext* h : M->m) {  // every device idle before any plane a neighbour may still be writing is freed
+    cudaSetDevice(h->info.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->fstream) cudaStreamSynchronize(h->fstream);
+  }
+  for (RbContext* h : M->m) rb_destroy(h);
+  delete M;
+}
+
+int rb_multi_create(const RbCreateInfo* info, const int32_t* device_ordinals, int32_t n_devices, RbMulti** out) {
+  if (!info || !device_ordinals || !out || n_devices < 1 || n_devices > RbContext::kMaxRanks || info->height < n_devices) {
+    g_multi_create_error = "rb_multi_create: invalid argument";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  RbMulti* M = new RbMulti();
+  M->width = info->width, M->height = info->height;
+  const int rows = (info->height + n_devices - 1) / n_devices;
+  for (int i = 0; i < n_devices; ++i) {
+    RbCreateInfo ci = *info;
+    ci.device = device_ordinals[i];
+    ci.band_y0 = std::min(info->height, i * rows);
+    ci.band_y1 = std::min(info->height, (i + 1) * rows);
+    RbContext* h = nullptr;
+    const int rc = ci.band_y0 < ci.band_y1 ? rb_create(&ci, &h) : RB_ERR_INVALID_ARGUMENT;
+    if (rc != RB_OK) {
+      g_multi_create_error = rc == RB_ERR_INVALID_ARGUMENT && ci.band_y0 >= ci.band_y1 ? "rb_multi_create: more devices than band rows"
+                                                                                       : g_create_error;
+      rb_multi_destroy(M);
+      return rc;
+    }
+    M->m.push_back(h);
+  }
+  if (n_devices > 1) {
+    auto link = [&]() -> int {
+      RbContext* h = M->m[0];  // (RB_CUDA reports through a context)
+      int rc = local_group_link(M);
+      if (rc != RB_OK)
+        for (RbContext* q : M->m)
+          if (!q->err.empty()) h->err = q->err;
+      return rc;
+    };
+    const int rc = link();
+    if (rc != RB_OK) {
+      g_multi_create_error = M->m[0]->err;
+      rb_multi_destroy(M);
+      return rc;
+    }
+  }
+  *out = M;
+  return RB_OK;
+}
+
+#define RB_MULTI_EACH(CALL)                          \
+  do {                                               \
+    if (!M) return RB_ERR_INVALID_ARGUMENT;          \
+    for (RbContext* h : M->m) {                      \
+      const int rc__ = (CALL);                       \
+      if (rc__ != RB_OK) return multi_fail(M, h, rc__); \
+    }                                                \
+    return RB_OK;                                    \
+  } while (0)
+
+int rb_multi_upload_scene(RbMulti* M, const RbSceneDesc* sd) { RB_MULTI_EACH(rb_upload_scene(h, sd)); }
+int rb_multi_set_params(RbMulti* M, const RbParams* p) { RB_MULTI_EACH(rb_set_params(h, p)); }
+int rb_multi_set_textures(RbMulti* M, const RbTexture* textures, uint32_t n_textures, const RbMaterialTextures* per_material,
+                          uint32_t n_materials) {
+  RB_MULTI_EACH(rb_set_textures(h, textures, n_textures, per_material, n_materials));
+}
+int rb_multi_set_sky(RbMulti* M, const RbTexture* sky) { RB_MULTI_EACH(rb_set_sky(h, sky)); }
+int rb_multi_synchronize(RbMulti* M) { RB_MULTI_EACH(rb_synchronize(h)); }
+int rb_multi_frame_wait(RbMulti* M, uint32_t frames_in_flight) { RB_MULTI_EACH(rb_frame_wait(h, frames_in_flight)); }
+int rb_multi_accumulate_display(RbMulti* M, uint32_t acc_frame_ctr, int32_t tonemap, int32_t gamma_correct, float* display_rgba_out,
+                                RbImageStats* stats) {
+  if (!M) return RB_ERR_INVALID_ARGUMENT;
+  RbImageStats total{};
+  for (RbContext* h : M->m) {  // every band writes its own rows of display_rgba_out; the sums combine
+    RbImageStats st{};
+    const int rc = rb_accumulate_display(h, acc_frame_ctr, tonemap, gamma_correct, display_rgba_out, stats ? &st : nullptr);
+    if (rc != RB_OK) return multi_fail(M, h, rc);
+    total.sum += st.sum, total.sum_sq += st.sum_sq, total.pixels += st.pixels;
+  }
+  if (stats) {
+    total.mean = total.pixels ? total.sum / (double)total.pixels : 0.0;
+    total.variance = total.pixels ? total.sum_sq / (double)total.pixels - total.mean * total.mean : 0.0;
+    *stats = total;
+  }
+  return RB_OK;
+}
+
+// Issue one frame on every device: first everything that may allocate (a device-wide synchronisation must not meet a
+// neighbour's halo wait that is still spinning for rows this thread has not queued yet), then the frames themselves,
+// band by band, each followed by the asynchronous copy of its rows into the ONE host buffer.
+int rb_multi_render_frame_async(RbMulti* M, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_out) {
+  if (!M || !cam || !frame_rgb_out) return RB_ERR_INVALID_ARGUMENT;
+  for (RbContext* h : M->m) {
+    const int rc = frame_prepare(h);
+    if (rc != RB_OK) return multi_fail(M, h, rc);
+  }
+  for (RbContext* h : M->m) {
+    const int rc = rb_render_frame_async(h, cam, frame_idx, frame_rgb_out);
+    if (rc != RB_OK) return multi_fail(M, h, rc);
+  }
+  return RB_OK;
+}
+int rb_multi_render_frame(RbMulti* M, const RbCamera* cam, uint32_t frame_idx, float* frame_rgb_out) {
+  const int rc = rb_multi_render_frame_async(M, cam, frame_idx, frame_rgb_out);
+  if (rc != RB_OK) return rc;
+  return rb_multi_frame_wait(M, 0);
+}
+// per-pixel buffers: every device contributes the rows of its band (the ids of rb_readback; light tables from device 0)
+int rb_multi_readback(RbMulti* M, int id, void* dst, size_t bytes) {
+  if (!M || !dst) return RB_ERR_INVALID_ARGUMENT;
+  if (id >= RB_BUF_ALIAS_PROB && id <= RB_BUF_LIGHT_CDF) {
+    const int rc = rb_readback(M->m[0], id, dst, bytes);
+    return rc == RB_OK ? rc : multi_fail(M, M->m[0], rc);
+  }
+  const size_t n = (size_t)M->width * M->height;
+  size_t px = 16;
+  if (id == RB_BUF_HIT_IDS) px = 8;
+  if (id == RB_BUF_RES_LIGHT_IDX) px = 4;
+  if (id == RB_BUF_FRAME_RGB || id == RB_BUF_ACCUMULATOR) px = 12;
+  if (bytes < n * px) {
+    M->err = "rb_multi_readback: destination too small";
+    return RB_ERR_INVALID_ARGUMENT;
+  }
+  std::vector<char> tmp(n * px);
+  for (RbContext* h : M->m) {
+    const int rc = rb_readback(h, id, tmp.data(), tmp.size());
+    if (rc != RB_OK) return multi_fail(M, h, rc);
+    const size_t off = (size_t)h->info.band_y0 * M->width * px, cnt = (size_t)(h->info.band_y1 - h->info.band_y0) * M->width * px;
+    memcpy((char*)dst + off, tmp.data() + off, cnt);
+  }
+  return RB_OK;
+}
+
+}  // extern "C"
+

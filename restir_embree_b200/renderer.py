@@ -324,6 +324,110 @@ class Renderer:
         self._check(self.L.rb_halo_import(self.h, y, rows, buf.ctypes.data), "rb_halo_import")
 
 
+class MultiRenderer:
+    """One handle, several GPUs, one host thread (rb_multi_*): the frame driver of `Renderer` over N devices. The scene
+    goes to every device, a frame is issued band by band from the calling thread, halo rows travel over peer memory,
+    and render_frame returns the ASSEMBLED frame_data. `devices` may name the same ordinal several times (several
+    bands on one GPU: what the single-GPU tests use)."""
+
+    def __init__(self, width, height, devices, seed=123):
+        self.L = L = load_library()
+        M = C.c_void_p
+        L.rb_multi_create.argtypes = [C.POINTER(abi.RbCreateInfo), C.POINTER(C.c_int32), C.c_int32, C.POINTER(M)]
+        L.rb_multi_destroy.argtypes = [M]
+        L.rb_multi_last_error.restype = C.c_char_p
+        L.rb_multi_last_error.argtypes = [M]
+        L.rb_multi_device_count.argtypes = [M]
+        L.rb_multi_member.restype = C.c_void_p
+        L.rb_multi_member.argtypes = [M, C.c_int32]
+        L.rb_multi_upload_scene.argtypes = [M, C.POINTER(abi.RbSceneDesc)]
+        L.rb_multi_set_params.argtypes = [M, C.POINTER(abi.RbParams)]
+        L.rb_multi_render_frame.argtypes = [M, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p]
+        L.rb_multi_render_frame_async.argtypes = [M, C.POINTER(abi.RbCamera), C.c_uint32, C.c_void_p]
+        L.rb_multi_frame_wait.argtypes = [M, C.c_uint32]
+        L.rb_multi_synchronize.argtypes = [M]
+        L.rb_multi_readback.argtypes = [M, C.c_int, C.c_void_p, C.c_size_t]
+        L.rb_multi_accumulate_display.argtypes = [M, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(abi.RbImageStats)]
+        self.width, self.height = int(width), int(height)
+        info = abi.RbCreateInfo()
+        info.width, info.height, info.seed, info.collect_timings = self.width, self.height, int(seed), 0
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        self.m = C.c_void_p()
+        rc = L.rb_multi_create(C.byref(info), devs, len(devices), C.byref(self.m))
+        if rc != abi.RB_OK:
+            msg = L.rb_multi_last_error(None)
+            self.m = None
+            raise RestirError(f"rb_multi_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.n = len(devices)
+
+    def close(self):
+        if getattr(self, "m", None):
+            self.L.rb_multi_destroy(self.m)
+            self.m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != abi.RB_OK:
+            msg = self.L.rb_multi_last_error(self.m)
+            raise RestirError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def upload_scene(self, scene):
+        d, keep = scene.desc()
+        self._check(self.L.rb_multi_upload_scene(self.m, C.byref(d)), "rb_multi_upload_scene")
+        del keep
+
+    def set_params(self, p):
+        self._check(self.L.rb_multi_set_params(self.m, C.byref(p)), "rb_multi_set_params")
+
+    def bands(self):
+        out = []
+        for i in range(self.n):
+            a, b = C.c_int32(0), C.c_int32(0)
+            self.L.rb_get_band(C.c_void_p(self.L.rb_multi_member(self.m, i)), C.byref(a), C.byref(b))
+            out.append((a.value, b.value))
+        return out
+
+    def render_frame(self, cam, frame_idx, out=None):
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        if out is None:
+            out = np.zeros((self.height, self.width, 3), dtype=np.float32)
+        self._check(self.L.rb_multi_render_frame(self.m, C.byref(c), int(frame_idx), out.ctypes.data), "rb_multi_render_frame")
+        return out
+
+    def render_frame_async(self, cam, frame_idx, out):
+        c = cam.to_abi() if hasattr(cam, "to_abi") else cam
+        self._check(self.L.rb_multi_render_frame_async(self.m, C.byref(c), int(frame_idx), out.ctypes.data), "rb_multi_render_frame_async")
+
+    def frame_wait(self, frames_in_flight=0):
+        self._check(self.L.rb_multi_frame_wait(self.m, int(frames_in_flight)), "rb_multi_frame_wait")
+
+    def synchronize(self):
+        self._check(self.L.rb_multi_synchronize(self.m), "rb_multi_synchronize")
+
+    def readback(self, buf):
+        dt, ch = abi.BUFFER_LAYOUT[buf]
+        a = np.empty((self.height, self.width, ch), dtype=dt)
+        self._check(self.L.rb_multi_readback(self.m, buf, a.ctypes.data, a.nbytes), "rb_multi_readback")
+        return a
+
+    def accumulate_display(self, acc_frame_ctr, tonemap=True, gamma_correct=True):
+        st = abi.RbImageStats()
+        self._check(self.L.rb_multi_accumulate_display(self.m, int(acc_frame_ctr), int(bool(tonemap)), int(bool(gamma_correct)), None,
+                                                       C.byref(st)), "rb_multi_accumulate_display")
+        return dict(sum=st.sum, sum_sq=st.sum_sq, mean=st.mean, variance=st.variance, pixels=st.pixels)
+
+
 def load_obj_scene(path, gamma_correct=True):
     """Wavefront OBJ + MTL -> SceneArrays through the library's own parser (rb_obj_load: the conventions of the
     reference's ModelLoader, P/ModelLoader.cpp:41-321). Host-only: works without a GPU. meta carries the material names

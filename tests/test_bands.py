@@ -259,3 +259,45 @@ def test_balancer_partition_rule(built):
     assert costs.max() / costs.mean() < 1.03, (bounds, costs)
     # bands too thin to move safely: unchanged
     assert _balance([(1.0, 27), (3.0, 27), (1.0, 26)], 80) == [0, 27, 54, 80]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_bands", [2, 3])
+def test_multi_handle_one_thread_assembles_the_frame_bit_identical(gpu, n_bands):
+    """rb_multi_* (one handle, several devices, one host thread — SURVEY 8b): here all bands sit on device 0, which runs the
+    same code as N GPUs (peer pointers instead of peer mappings): the frames assembled in ONE host buffer, the reservoir
+    planes and the accumulator equal the single-handle ones bit for bit, with blocking and with pipelined calls."""
+    import torch
+    from restir_embree_b200.renderer import MultiRenderer, Renderer
+    sc = scenes.scene_config("small")
+    Wd, Hd, n = 160, 96, 6
+    p = abi.default_params(M_Area=6, M_Brdf=1, doSpatialReuse=1, doTemporalReuse=1, doVisibilityPass=1, spatialPassCount=2,
+                           lightSampler=abi.LS_ALIAS, wavefront=1)
+    cams = [Camera(Wd, Hd, 55, scenes.orbit_position((0, 0, 1.0), 3 * f, radius=4.5), (0, 0, 1.0)) for f in range(n)]
+    with Renderer(Wd, Hd, seed=4) as one:
+        one.upload_scene(sc)
+        one.set_params(p)
+        want = []
+        for f in range(n):
+            want.append(one.render_frame(cams[f], f).copy())
+            one.accumulate_display(f, want_stats=False)
+        want_res = [one.readback(b) for b in (abi.BUF_RES_POINT_WSUM, abi.BUF_RES_NORMAL_W, abi.BUF_RES_LIGHT_IDX, abi.BUF_HIT_IDS)]
+        want_acc = one.readback(abi.BUF_ACCUMULATOR)
+    with MultiRenderer(Wd, Hd, [0] * n_bands, seed=4) as m:
+        assert len(m.bands()) == n_bands and m.bands()[0][0] == 0 and m.bands()[-1][1] == Hd
+        m.upload_scene(sc)
+        m.set_params(p)
+        bufs = [torch.empty((Hd, Wd, 3), dtype=torch.float32, pin_memory=True).numpy() for _ in range(2)]
+        for f in range(n):
+            if f < 3:  # blocking calls ...
+                got = m.render_frame(cams[f], f, out=bufs[f & 1])
+            else:      # ... then pipelined ones into two host buffers
+                m.render_frame_async(cams[f], f, bufs[f & 1])
+                m.frame_wait(0)
+                got = bufs[f & 1]
+            assert np.array_equal(bits(want[f]), bits(got)), f"frame {f}: {(want[f] != got).any(-1).sum()} px differ"
+            st = m.accumulate_display(f)
+        for b, w in zip((abi.BUF_RES_POINT_WSUM, abi.BUF_RES_NORMAL_W, abi.BUF_RES_LIGHT_IDX, abi.BUF_HIT_IDS), want_res):
+            assert np.array_equal(bits(w), bits(m.readback(b))), b
+        assert np.array_equal(bits(want_acc), bits(m.readback(abi.BUF_ACCUMULATOR)))
+        assert st["pixels"] == Wd * Hd and abs(st["mean"] - float(want_acc.astype(np.float64).mean())) < 1e-6 * max(1.0, st["mean"])
