@@ -96,6 +96,13 @@ RB_HD float gmax(float a, float b) { return (a < b) ? b : a; }  // glm::max
 RB_HD float gmin(float a, float b) { return (b < a) ? b : a; }  // glm::min
 RB_HD float gclamp(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
 RB_HD int imin(int a, int b) { return a < b ? a : b; }
+RB_HD int lowest_bit(uint32_t m) {  // index of the lowest set bit, m != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
 RB_HD int imax(int a, int b) { return a > b ? a : b; }
 
 #define RB_PI 3.14159265358979323846264338327950288f

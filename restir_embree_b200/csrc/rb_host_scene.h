@@ -6,7 +6,9 @@
 #define RB_HOST_SCENE_H_
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -27,6 +29,7 @@ struct HostScene {
   std::vector<uint32_t> alias_idx;
   std::vector<uint32_t> alias_pair;  // [2 * n_lights]: {bits(alias_prob[i]), alias_idx[i]} — one 8-byte load per pick
   std::vector<F4> light;  // [6 * n_lights]
+  std::vector<F4> light_cull;  // [n_lights]: {bounding sphere centre, radius} for initial_pixel's horizon pre-test; radius = +inf: never
   float maxabs = 0, totalSurface = 0;
 };
 
@@ -168,6 +171,36 @@ inline int flatten_scene(const RbSceneDesc* sd, HostScene& hs, std::string& err)
     light[6 * i + 3] = F4{nrm[3 * t].x, nrm[3 * t].y, nrm[3 * t].z, M.emission[0]};
     light[6 * i + 4] = F4{nrm[3 * t].w, nrm[3 * t + 1].x, nrm[3 * t + 1].y, M.emission[1]};
     light[6 * i + 5] = F4{nrm[3 * t + 1].z, nrm[3 * t + 1].w, nrm[3 * t + 2].x, M.emission[2]};
+  }
+
+  // Bounding spheres for the horizon pre-test of the initial pass (rb_passes.cuh: surely_below_horizon). A light is
+  // eligible only when everything the exact cull test of initial_pixel asks of the LIGHT holds for every point of it:
+  // pick probability, 1/area and emission finite and positive, and vertex normals whose every convex combination can
+  // be normalised (all three of length 0.5..2 and within 75 degrees of the first). Everything else gets radius = +inf.
+  hs.light_cull.assign(NL, F4{0, 0, 0, std::numeric_limits<float>::infinity()});
+  for (size_t i = 0; i < NL; ++i) {
+    const F4* L = &light[6 * i];
+    auto fin = [](float x) { return std::isfinite(x); };
+    bool ok = L[1].w > 0.0f && fin(L[1].w) && L[2].w > 0.0f && fin(L[2].w);
+    ok = ok && fin(L[3].w) && fin(L[4].w) && fin(L[5].w) && (L[3].w > 0.0f || L[4].w > 0.0f || L[5].w > 0.0f);
+    double nl[3];
+    for (int k = 0; k < 3 && ok; ++k) {
+      nl[k] = std::sqrt((double)L[3 + k].x * L[3 + k].x + (double)L[3 + k].y * L[3 + k].y + (double)L[3 + k].z * L[3 + k].z);
+      ok = nl[k] >= 0.5 && nl[k] <= 2.0;
+      const double d0 = (double)L[3 + k].x * L[3].x + (double)L[3 + k].y * L[3].y + (double)L[3 + k].z * L[3].z;
+      ok = ok && d0 >= 0.25 * nl[k] * nl[0];
+    }
+    if (!ok) continue;
+    const double cx = ((double)L[0].x + L[1].x + L[2].x) / 3.0, cy = ((double)L[0].y + L[1].y + L[2].y) / 3.0,
+                 cz = ((double)L[0].z + L[1].z + L[2].z) / 3.0;
+    const float fx = (float)cx, fy = (float)cy, fz = (float)cz;  // the radius is measured from the rounded centre
+    double r2 = 0;
+    for (int k = 0; k < 3; ++k) {
+      const double dx = (double)L[k].x - fx, dy = (double)L[k].y - fy, dz = (double)L[k].z - fz;
+      r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+    }
+    const float rad = (float)(std::sqrt(r2) * 1.00001) ;
+    hs.light_cull[i] = F4{fx, fy, fz, std::nextafter(rad, std::numeric_limits<float>::infinity())};
   }
 
   hs.maxabs = maxabs;

@@ -34,6 +34,8 @@ struct WaveBufs {
   uint32_t capacity;
   uint8_t* occ;  // any-hit results   [slot * npix + pixel]
   HitRec* hits;  // closest results   [slot * npix + pixel]
+  F4* brdf_dir;  // {omega_i, pdf} of the BRDF-sampled candidates [slot * npix + pixel]: written by the stream half of the
+                 // initial pass, read by its resolve half (which then carries no sampleBRDF code)
   uint32_t npix;
   uint32_t brdf_two_step;  // BRDF-candidate hits come from the emissive-only BVH; occ[] says whether something precedes them
   U4* cand;      // spatial pass, constant weights: candidate records [slot * npix + pixel] (spatial_gen_pixel)
@@ -149,6 +151,8 @@ struct InlineVis {
   RB_HD SurfaceHit closest(int /*slot*/, const V3& org, const V3& dir, float tnear, float tfar) const {
     return intersect_surface(fc->sc, org, dir, tnear, tfar);
   }
+  RB_HD void put_brdf_sample(int, const V3&, float) const {}
+  RB_HD bool get_brdf_sample(int, V3*, float*) const { return false; }
 };
 // GenVis: the stream half. Queries are appended to the ray queue and answered "visible" / "miss"; the pass body
 // runs only to enumerate its rays, its stores are suppressed (kStore).
@@ -176,6 +180,10 @@ struct GenVis {
     push(slot, org, dir, tfar);
     return no_hit();
   }
+  RB_HD void put_brdf_sample(int slot, const V3& wi, float pdf) const {
+    st4(fc->wave.brdf_dir + (size_t)slot * fc->wave.npix + pixel, f4(wi, pdf));
+  }
+  RB_HD bool get_brdf_sample(int, V3*, float*) const { return false; }
   // the same shadow ray as visible(), into a slot reserved beforehand (reserve: all of a pixel's rays with one atomic
   // per warp instead of one per ray — the reservation round trip was the largest stall of the reuse stream kernels)
   RB_HD uint32_t reserve(uint32_t n) const { return queue_reserve_n(fc->wave.count, n); }
@@ -211,6 +219,12 @@ struct ResolveVisT {
     // are the same thing to brdfSampleLight, P/ReSTIRIntegrator.cpp:143)
     if (w.brdf_two_step && hr.tri != 0xFFFFFFFFu && w.occ[(size_t)slot * w.npix + pixel] != 0) hr.tri = 0xFFFFFFFFu;
     return surface_from_hit<NMAP>(fc->sc, org, dir, hr);
+  }
+  RB_HD void put_brdf_sample(int, const V3&, float) const {}
+  RB_HD bool get_brdf_sample(int slot, V3* wi, float* pdf) const {  // what the stream half computed (same bits, not recomputed)
+    const F4 v = ld4(fc->wave.brdf_dir + (size_t)slot * fc->wave.npix + pixel);
+    *wi = xyz(v), *pdf = v.w;
+    return true;
   }
 };
 // StagedVis: the wavefront schedule of the spatial MIS modes whose ray count is not k + 1 (BALANCE_HEURISTIC: every
@@ -577,8 +591,178 @@ RB_HD void gbuffer_pixel(const FrameCtx& fc, int x, int y, Cnt& cnt) {
 // areaSampleLight :89-124; brdfSampleLight :126-177; Sampling::sampleTriangle P/Sampling.cpp:63-76)
 // RNG slots: candidate c uses 4c..4c+3 = {pick | lobe, r1, r2, accept}.
 // =====================================================================================
+// Where initial_pixel parks the light indices of a chunk of candidates between its two loops: one word per candidate,
+// `stride` words apart (kernels: shared memory, [candidate][thread]; host: a local array).
+struct PickStore {
+  uint32_t* p;
+  int stride;
+  RB_HD void put(int j, uint32_t v) const { p[j * stride] = v; }
+  RB_HD uint32_t get(int j) const { return p[j * stride]; }
+};
+constexpr int kPickChunk = 32;
+#ifndef RB_PICK_BATCH
+#define RB_PICK_BATCH 2
+#endif
+constexpr int kPickBatch = RB_PICK_BATCH;  // divides kPickChunk
+// P/TriangleCDF.cpp:36-54: the probability of the triangle a CDF pick returned (pick_light's own expression)
+RB_HD float cdf_pick_pdf(const SceneDev& sc, uint32_t index) { return index == 0 ? sc.cdf[0] : sc.cdf[index] - sc.cdf[index - 1]; }
+
+// Horizon pre-test of the initial pass. The loop below gives a candidate the weight +0 without evaluating it when
+// its EXACT cull test holds (cosThetaI == 0 and everything finite). Half of the candidates of a typical pixel end there,
+// but only after the sample point, both normalisations and the cosines were computed, and — one pixel per lane — the
+// warp pays for the full evaluation as long as one lane needs it. This test decides from the light's bounding sphere
+// {c, R} alone and is SUFFICIENT for the exact test (never the other way round: a candidate it lets through is simply
+// handled as before), so the result cannot change. With M >= every |coordinate| of the light's vertices and of pos,
+// n1 = |n.x| + |n.y| + |n.z| >= |n|, u = 2^-24, and H = (c - pos).n + R n1 >= (v - pos).n for every point v of the light:
+//   * the computed sample point is sum(b_i v_i) + e with computed weights b_i >= 0, |sum(b_i) - 1| <= 4u, |e| <= 5uM
+//     per component; lightDir = fl(point - pos) adds <= 2uM; so (computed lightDir).n <= (1 - 4u) H + 11 u M n1;
+//   * normalising multiplies by a positive number, and the computed dot of the unit vector with n is off by <= 4 u n1;
+//   so H < -2^-14 M n1 (a thousand times the error terms, including those of evaluating H itself in float) makes the
+//   computed dot(lightDir, n) negative: cosThetaI = max(., 0) == 0. Also |lightDir| >= 2^-15 M, so r_sqr is a normal,
+//   finite number for 1e-12 < M < 1e15, and lightDir's unit vector is finite;
+//   * R is finite only for lights whose pick probability, 1/area and emission are finite and positive and whose vertex
+//     normals interpolate to something normalisable (rb_host_scene.h), which makes d_ny finite and the sample valid.
+struct HorizonCull {
+  bool on;
+  float n1, pad;
+};
+RB_HD HorizonCull make_horizon_cull(const SceneDev& sc, const GElem& g, const Shading& sh) {
+  HorizonCull hc;
+  const float M = gmax(gmax(sc.maxabs, fabsf_(g.pos.x)), gmax(fabsf_(g.pos.y), fabsf_(g.pos.z)));
+  hc.n1 = fabsf_(g.normal.x) + fabsf_(g.normal.y) + fabsf_(g.normal.z);
+  hc.pad = M * (1.0f / 16384.0f);
+  hc.on = sh.finite && sc.light_cull != nullptr && M > 1e-12f && M < 1e15f && hc.n1 < 1e15f;
+  return hc;
+}
+RB_HD bool surely_below_horizon(const HorizonCull& hc, const F4& sphere, const GElem& g) {
+  const float H = dot(xyz(sphere) - g.pos, g.normal) + (sphere.w + hc.pad) * hc.n1;
+  return H < 0.0f;  // false for R = +inf and for NaN
+}
+
+// One area-sampled candidate of initialRenderPass (areaSampleLight :89-124 + evaluatePHat :180-211 + the weight, :247-262):
+// light `idx` was picked for candidate i. Returns false when the candidate's weight is exactly +0 by the horizon
+// argument below (it then only counts); otherwise the sample, its weight w for addSample, p-hat and validity.
+struct AreaEval {
+  LightSample s;
+  float w, p_hat;
+  bool valid;
+};
 template <class Vis>
-RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt) {
+RB_HD bool eval_area_candidate(const FrameCtx& fc, const GElem& g, const Shading& sh, uint32_t key, int i, uint32_t idx,
+                               float inv_MArea, bool testVis, const Vis& vis, Cnt& cnt, AreaEval* out) {
+  const RbParams& P = fc.P;
+  const uint32_t base = 4u * (uint32_t)i;
+  const F4* L = fc.sc.light + 6 * (size_t)idx;
+  const F4 l0 = ldg4(L), l1 = ldg4(L + 1), l2 = ldg4(L + 2), l3 = ldg4(L + 3), l4 = ldg4(L + 4), l5 = ldg4(L + 5);
+  const float pick_pdf = P.lightSampler == RB_LS_ALIAS ? l1.w : cdf_pick_pdf(fc.sc, idx);
+  const float r1 = rng_value(key, base + 1, 0, 1), r2 = rng_value(key, base + 2, 0, 1);
+  const float sq = sqrtf_(r1);
+  const float bx = 1.0f - sq;
+  const float by = sq * (1.0f - r2);
+  const float bz = sq * r2;
+  LightSample& s = out->s;
+  s.samplePoint = xyz(l0) * bx + xyz(l1) * by + xyz(l2) * bz;
+  s.sampleNormal = normalize(xyz(l3) * bx + xyz(l4) * by + xyz(l5) * bz);
+  s.L_i = v3(l3.w, l4.w, l5.w);
+  s.lightIdx = (int)idx;
+  // shared by areaSampleLight (:102-107) and evaluateF (:192-199): same expressions, same bits
+  V3 lightDir = s.samplePoint - g.pos;
+  const float r_sqr = dot(lightDir, lightDir);
+  lightDir = normalize(lightDir);
+  const float d_ny = dot(-lightDir, s.sampleNormal);
+  const float cosThetaI = gmax(dot(lightDir, g.normal), 0.0f);
+  const bool valid = sample_valid(s);  // false only for a non-positive emission
+  out->valid = valid;
+  if (valid && testVis) cnt.anyW++;
+  // A light below the horizon has G == 0: with finite BRDF, pdf and weights the candidate's w is exactly +0,
+  // so addSample only counts it (w_sum += 0; no draw consumed affects the result: rand < 0 is false).
+  if (sh.finite && cosThetaI == 0.0f && r_sqr > 0.0f && finitef_(r_sqr) && pick_pdf > 0.0f && finitef_(l2.w) && l2.w > 0.0f &&
+      finitef_(d_ny) && finite3(s.L_i))
+    return false;
+  const float triPointPdf = l2.w;  // 1.0f / area, computed with the same division at upload
+  const float pdf_area = pick_pdf * triPointPdf;
+  const float cosThetaY_pdf = gmax(d_ny, 0.0f);
+  const float areaMeasureFactor = cosThetaY_pdf / r_sqr;
+  const Lobe lobe = phong_lobe(g, sh, lightDir);
+  const float pdfAsIfBrdfAreaMeasure = pdf_from_lobe(g, sh, lightDir, lobe.pdf) * areaMeasureFactor;
+  const float W = frcp_(pdf_area);
+  const float misWeight = m_area(P, pdf_area, pdfAsIfBrdfAreaMeasure);
+  // evaluatePHat(sample, pixel)
+  float p_hat = 0.0f;
+  if (valid) {
+    const float cosThetaY = fabsf_(d_ny);
+    const float G = cosThetaI * cosThetaY / r_sqr;
+    const V3 f_r = brdf_from_lobe(g, sh, lobe.brdf);
+    V3 F = s.L_i * f_r * G;
+    if (testVis) {
+      cnt.anyW--;  // shadow_F0 counts it again
+      F = shadow_F0(F, g.pos, s.samplePoint, vis, i, cnt, 1, VIS_TRACE);
+    }
+    p_hat = length(F);
+  }
+  out->p_hat = p_hat;
+  out->w = (P.M_Brdf > 0) ? misWeight * p_hat * W : inv_MArea * p_hat * W;
+  return true;
+}
+template <class Vis>
+RB_HD void initial_finish(const FrameCtx& fc, size_t pi, const GElem& g, const Shading& sh, uint32_t key, bool testVis, Reservoir& r,
+                          float p_sel, bool sel_wants, const Vis& vis, Cnt& cnt);
+
+#if !defined(__CUDACC__)
+// Host builds only (tests/emu): with check_mode set, a pre-culled candidate is evaluated all the same and the exact test
+// must cull it too; counts = {pre-culled, confirmed by the exact test, violations, candidates,
+// culled by the exact test (with or without the pre-test)}.
+struct HorizonCullCheck {
+  int check_mode = 0;
+  unsigned long long counts[5] = {0, 0, 0, 0, 0};
+};
+inline HorizonCullCheck g_horizon_cull_check;
+#define RB_CULL_CHECK(...) __VA_ARGS__
+#else
+#define RB_CULL_CHECK(...)
+#endif
+
+// First loop of the initial pass over candidates c0 .. c0 + cn - 1: picks every candidate's light (parked in `picks`) and
+// runs the horizon pre-test. Returns the mask of the candidates that are left to evaluate; a pre-culled one only counts.
+RB_HD uint32_t pick_and_precull(const FrameCtx& fc, const GElem& g, const HorizonCull& hc, uint32_t key, int c0, int cn,
+                                const PickStore& picks, bool testVis, int& confidence, Cnt& cnt, uint32_t* pre_out) {
+  const RbParams& P = fc.P;
+  uint32_t todo = 0;
+  RB_CULL_CHECK(uint32_t pre = 0;)
+  // kPickBatch candidates at a time: their alias records, then their bounding spheres, are independent gathers
+  for (int j0 = 0; j0 < cn; j0 += kPickBatch) {
+    LightPick pk[kPickBatch];
+    F4 sphere[kPickBatch];
+#pragma unroll
+    for (int u = 0; u < kPickBatch; ++u) pk[u] = pick_light(fc.sc, P.lightSampler, key, 4u * (uint32_t)(c0 + imin(j0 + u, cn - 1)));
+#pragma unroll
+    for (int u = 0; u < kPickBatch; ++u)
+      if (hc.on) sphere[u] = ldg4(fc.sc.light_cull + pk[u].idx);
+#pragma unroll
+    for (int u = 0; u < kPickBatch; ++u) {
+      const int j = j0 + u;
+      if (j >= cn) break;
+      picks.put(j, pk[u].idx);
+      bool culled = false;
+      if (hc.on) culled = surely_below_horizon(hc, sphere[u], g) && (P.lightSampler == RB_LS_ALIAS || pk[u].pdf > 0.0f);
+      RB_CULL_CHECK(__atomic_fetch_add(&g_horizon_cull_check.counts[3], 1ull, __ATOMIC_RELAXED);
+                    if (culled) __atomic_fetch_add(&g_horizon_cull_check.counts[0], 1ull, __ATOMIC_RELAXED);
+                    if (culled && g_horizon_cull_check.check_mode) pre |= 1u << j, culled = false;)
+      if (culled) {
+        confidence += 1;
+        if (testVis) cnt.anyW++;  // the sample is valid (eligible lights emit), the reference would have traced
+      } else {
+        todo |= 1u << j;
+      }
+    }
+  }
+  RB_CULL_CHECK(*pre_out = pre;)
+  (void)pre_out;
+  return todo;
+}
+
+template <class Vis>
+RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& cnt, const PickStore& picks) {
   const size_t pi = (size_t)y * fc.width + x;
   const GElem g = load_gelem(fc.G, pi);
   Reservoir r = empty_reservoir();
@@ -594,74 +778,49 @@ RB_HD void initial_pixel(const FrameCtx& fc, int x, int y, const Vis& vis, Cnt& 
   bool sel_wants = false;
 
   const float inv_MArea = P.M_Area > 0 ? 1.0f / (float)P.M_Area : 0.0f;
-  // The pick of candidate i + 1 is issued before candidate i is evaluated: the alias-table lookup and the light
-  // record gather are dependent loads, and the counter RNG makes the next pick independent of this candidate.
-  LightPick next_pick = {0u, 0.0f};
-  if (P.M_Area > 0) next_pick = pick_light(fc.sc, P.lightSampler, key, 0u);
-  for (int i = 0; i < P.M_Area; ++i) {
-    const uint32_t base = 4u * (uint32_t)i;
-    const LightPick pick = next_pick;
-    const F4* L = fc.sc.light + 6 * (size_t)pick.idx;
-    const F4 l0 = ldg4(L), l1 = ldg4(L + 1), l2 = ldg4(L + 2), l3 = ldg4(L + 3), l4 = ldg4(L + 4), l5 = ldg4(L + 5);
-    if (i + 1 < P.M_Area) next_pick = pick_light(fc.sc, P.lightSampler, key, base + 4u);
-    const float pick_pdf = P.lightSampler == RB_LS_ALIAS ? l1.w : pick.pdf;
-    const float r1 = rng_value(key, base + 1, 0, 1), r2 = rng_value(key, base + 2, 0, 1);
-    const float sq = sqrtf_(r1);
-    const float bx = 1.0f - sq;
-    const float by = sq * (1.0f - r2);
-    const float bz = sq * r2;
-    LightSample s;
-    s.samplePoint = xyz(l0) * bx + xyz(l1) * by + xyz(l2) * bz;
-    s.sampleNormal = normalize(xyz(l3) * bx + xyz(l4) * by + xyz(l5) * bz);
-    s.L_i = v3(l3.w, l4.w, l5.w);
-    s.lightIdx = (int)pick.idx;
-    // shared by areaSampleLight (:102-107) and evaluateF (:192-199): same expressions, same bits
-    V3 lightDir = s.samplePoint - g.pos;
-    const float r_sqr = dot(lightDir, lightDir);
-    lightDir = normalize(lightDir);
-    const float d_ny = dot(-lightDir, s.sampleNormal);
-    const float cosThetaI = gmax(dot(lightDir, g.normal), 0.0f);
-    const bool valid = sample_valid(s);  // false only for a non-positive emission
-    if (valid && testVis) cnt.anyW++;
-    // A light below the horizon has G == 0: with finite BRDF, pdf and weights the candidate's w is exactly +0,
-    // so addSample only counts it (w_sum += 0; no draw consumed affects the result: rand < 0 is false).
-    if (sh.finite && cosThetaI == 0.0f && r_sqr > 0.0f && finitef_(r_sqr) && pick_pdf > 0.0f && finitef_(l2.w) && l2.w > 0.0f &&
-        finitef_(d_ny) && finite3(s.L_i)) {
-      r.confidence += 1;
-      continue;
-    }
-    const float triPointPdf = l2.w;  // 1.0f / area, computed with the same division at upload
-    const float pdf_area = pick_pdf * triPointPdf;
-    const float cosThetaY_pdf = gmax(d_ny, 0.0f);
-    const float areaMeasureFactor = cosThetaY_pdf / r_sqr;
-    const Lobe lobe = phong_lobe(g, sh, lightDir);
-    const float pdfAsIfBrdfAreaMeasure = pdf_from_lobe(g, sh, lightDir, lobe.pdf) * areaMeasureFactor;
-    const float W = frcp_(pdf_area);
-    const float misWeight = m_area(P, pdf_area, pdfAsIfBrdfAreaMeasure);
-    // evaluatePHat(sample, pixel)
-    float p_hat = 0.0f;
-    if (valid) {
-      const float cosThetaY = fabsf_(d_ny);
-      const float G = cosThetaI * cosThetaY / r_sqr;
-      const V3 f_r = brdf_from_lobe(g, sh, lobe.brdf);
-      V3 F = s.L_i * f_r * G;
-      if (testVis) {
-        cnt.anyW--;  // shadow_F0 counts it again
-        F = shadow_F0(F, g.pos, s.samplePoint, vis, i, cnt, 1, VIS_TRACE);
+  const HorizonCull hc = make_horizon_cull(fc.sc, g, sh);
+  // Two loops per chunk of candidates. The first picks every candidate's light (the counter RNG makes the picks
+  // independent of each other and of the reservoir) and runs the horizon pre-test: cheap and the same for every lane.
+  // The second evaluates only the candidates that are left, in candidate order, so addSample sees the same sequence of
+  // non-zero weights; a pre-culled candidate only counts (w == +0: w_sum += 0, no draw can select it).
+  for (int c0 = 0; c0 < P.M_Area; c0 += kPickChunk) {
+    const int cn = imin(kPickChunk, P.M_Area - c0);
+    uint32_t pre = 0;
+    uint32_t todo = pick_and_precull(fc, g, hc, key, c0, cn, picks, testVis, r.confidence, cnt, &pre);
+    (void)pre;
+    while (todo != 0) {
+      const int j = lowest_bit(todo);
+      todo &= todo - 1u;
+      const int i = c0 + j;
+      AreaEval e;
+      if (!eval_area_candidate(fc, g, sh, key, i, picks.get(j), inv_MArea, testVis, vis, cnt, &e)) {
+        RB_CULL_CHECK(if (pre >> j & 1u) __atomic_fetch_add(&g_horizon_cull_check.counts[1], 1ull, __ATOMIC_RELAXED);
+                      __atomic_fetch_add(&g_horizon_cull_check.counts[4], 1ull, __ATOMIC_RELAXED);)
+        r.confidence += 1;
+        continue;
       }
-      p_hat = length(F);
-    }
-    const float w = (P.M_Brdf > 0) ? misWeight * p_hat * W : inv_MArea * p_hat * W;
-    if (add_sample(r, s, w, 1, key, base + 3)) {
-      p_sel = p_hat;
-      sel_wants = valid;
+      RB_CULL_CHECK(if (pre >> j & 1u) __atomic_fetch_add(&g_horizon_cull_check.counts[2], 1ull, __ATOMIC_RELAXED);)
+      if (add_sample(r, e.s, e.w, 1, key, 4u * (uint32_t)i + 3u)) {
+        p_sel = e.p_hat;
+        sel_wants = e.valid;
+      }
     }
   }
+  initial_finish(fc, pi, g, sh, key, testVis, r, p_sel, sel_wants, vis, cnt);
+}
+
+// The rest of initialRenderPass after the area candidates: the BRDF-sampled candidates (:266-286), the final W (:288-291),
+// the store and — fused — the stream half of the visibility pass.
+template <class Vis>
+RB_HD void initial_finish(const FrameCtx& fc, size_t pi, const GElem& g, const Shading& sh, uint32_t key, bool testVis, Reservoir& r,
+                          float p_sel, bool sel_wants, const Vis& vis, Cnt& cnt) {
+  const RbParams& P = fc.P;
   const float inv_MBrdf = P.M_Brdf > 0 ? 1.0f / (float)P.M_Brdf : 0.0f;
   for (int i = 0; i < P.M_Brdf; ++i) {
     const uint32_t base = 4u * (uint32_t)(P.M_Area + i);
     float pdf;
-    const V3 wi = brdf_sample(g, sh, key, base, &pdf);
+    V3 wi;
+    if (!vis.get_brdf_sample(i, &wi, &pdf)) wi = brdf_sample(g, sh, key, base, &pdf);
     const V3 org = g.pos + P.normalOffset * g.normal;
     cnt.closest++;
     const SurfaceHit h = vis.closest(i, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
@@ -728,6 +887,7 @@ RB_HD void initial_brdf_gen_pixel(const FrameCtx& fc, int x, int y, const GenVis
     float pdf;
     const V3 wi = brdf_sample(g, sh, key, base, &pdf);
     const V3 org = g.pos + P.normalOffset * g.normal;
+    vis.put_brdf_sample(i, wi, pdf);
     (void)vis.closest(i, org, wi, FLT_MIN + P.tnearOffset, FLT_MAX);
   }
 }

@@ -57,6 +57,8 @@ struct SceneDev {
   const float* alias_prob;
   const uint32_t* alias_idx;
   const U2* alias_pair;  // {bits(alias_prob[i]), alias_idx[i]}
+  const F4* light_cull;  // [n_lights]: {bounding sphere centre, radius | +inf = not eligible} (rb_host_scene.h); may be null
+  float maxabs;          // largest |coordinate| of any vertex of the scene
   uint32_t n_lights;
   uint32_t n_tris;
   uint32_t n_nodes;

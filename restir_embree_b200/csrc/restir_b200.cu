@@ -60,8 +60,15 @@ __device__ __forceinline__ void flush_counts(unsigned long long* ctr, const Cnt&
     if (COUNT) flush_counts(fc.counters, cnt);                                 \
   }
 
+// initial_pixel's per-thread list of picked lights: [candidate][thread] words of shared memory (conflict-free)
+template <int THREADS>
+__device__ __forceinline__ PickStore smem_picks() {
+  __shared__ uint32_t s_pick[kPickChunk * THREADS];
+  return PickStore{s_pick + threadIdx.y * blockDim.x + threadIdx.x, THREADS};
+}
+
 RB_PIXEL_KERNEL_T(k_gbuffer, InlineVis, true, 128, 5, gbuffer_pixel(fc, x, y, cnt))  // 94 regs: 5 x 4 warps instead of 2 x 8
-RB_PIXEL_KERNEL(k_initial, InlineVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL(k_initial, InlineVis, true, 1, initial_pixel(fc, x, y, vis, cnt, smem_picks<kTileW * kTileH>()))
 RB_PIXEL_KERNEL(k_visibility, InlineVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_temporal, InlineVis, true, 1, (temporal_pixel<InlineVis, false>(fc, x, y, vis, cnt)))
 RB_PIXEL_KERNEL(k_temporal_banded, InlineVis, true, 1, (temporal_pixel<InlineVis, true>(fc, x, y, vis, cnt)))
@@ -76,9 +83,10 @@ RB_PIXEL_KERNEL(k_initial_brdf_stream, GenVis, false, 1, initial_brdf_gen_pixel(
 #ifndef RB_INIT_MINB
 #define RB_INIT_MINB 5
 #endif
-RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVisFlat, true, 128, RB_INIT_MINB, initial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL_T(k_initial_resolve_nmap, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL_T(k_initial_resolve, ResolveVisFlat, true, 128, RB_INIT_MINB, initial_pixel(fc, x, y, vis, cnt, smem_picks<128>()))
+RB_PIXEL_KERNEL_T(k_initial_resolve_nmap, ResolveVis, true, 128, 5, initial_pixel(fc, x, y, vis, cnt, smem_picks<128>()))
+
+RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt, smem_picks<kTileW * kTileH>()))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_temporal_stream, GenVis, true, 3, temporal_gen_pixel<0>(fc, x, y, vis, cnt))
 // bands: the bulk launch defers the few pixels whose reprojection leaves the rows held here ...
@@ -1224,6 +1232,7 @@ void rb_destroy(RbHandle h) {
   if (h->fwave.rays) cudaFree(h->fwave.rays);
   if (h->fwave.hits) cudaFree(h->fwave.hits);
   if (h->fwave.occ) cudaFree(h->fwave.occ);
+  if (h->fwave.brdf_dir) cudaFree(h->fwave.brdf_dir);
   for (auto q : h->visRays)
     if (q) cudaFree(q);
   if (h->fstream) {
@@ -1456,6 +1465,9 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     RB_CUDA(up(d_ap, alias_prob.data(), NL * 4));
     RB_CUDA(up(d_ai, alias_idx.data(), NL * 4));
     RB_CUDA(up(d_pair, hs.alias_pair.data(), NL * 8));
+    F4* d_cull = nullptr;
+    RB_TRY(dev_alloc(h, &d_cull, NL, h->sceneAllocs));
+    RB_CUDA(up(d_cull, hs.light_cull.data(), NL * 16));
     F4* d_uv = nullptr;
     if (!hs.uv.empty()) {
       RB_TRY(dev_alloc(h, &d_uv, hs.uv.size(), h->sceneAllocs));
@@ -1504,6 +1516,8 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     sc.alias_prob = d_ap;
     sc.alias_idx = d_ai;
     sc.alias_pair = d_pair;
+    sc.light_cull = d_cull;
+    sc.maxabs = maxabs;
     sc.n_lights = (uint32_t)NL;
     sc.n_tris = (uint32_t)n;
     sc.n_nodes = n_nodes;
@@ -1736,8 +1750,10 @@ static int ensure_wave(RbContext* h, uint32_t slots, uint32_t brdf_slots, uint32
   if ((size_t)brdf_slots * npix > h->fwaveHitCap) {
     if (h->fwave.hits) cudaFree(h->fwave.hits);
     if (h->fwave.occ) cudaFree(h->fwave.occ);
-    h->fwave.hits = nullptr, h->fwave.occ = nullptr;
+    if (h->fwave.brdf_dir) cudaFree(h->fwave.brdf_dir);
+    h->fwave.hits = nullptr, h->fwave.occ = nullptr, h->fwave.brdf_dir = nullptr;
     h->fwaveHitCap = 0;
+    RB_CUDA(cudaMalloc((void**)&h->fwave.brdf_dir, (size_t)brdf_slots * npix * sizeof(F4)));
     RB_CUDA(cudaMalloc((void**)&h->fwave.hits, (size_t)brdf_slots * npix * sizeof(HitRec)));
     RB_CUDA(cudaMalloc((void**)&h->fwave.occ, (size_t)brdf_slots * npix));
     h->fwaveHitCap = (size_t)brdf_slots * npix;

@@ -57,6 +57,7 @@ struct Emu {
   std::vector<RayQ> rays;
   std::vector<uint8_t> occ;
   std::vector<HitRec> hits;
+  std::vector<F4> brdf_dir;
   std::vector<U4> cand;
   bool shaded = false;
   std::vector<TexDev> tex_tab;  // rb_set_textures mirror
@@ -289,6 +290,8 @@ int emu_upload_scene(void* h, const RbSceneDesc* sd) {
   sc.alias_prob = E->hs.alias_prob.data();
   sc.alias_idx = E->hs.alias_idx.data();
   sc.alias_pair = reinterpret_cast<const U2*>(E->hs.alias_pair.data());
+  sc.light_cull = E->hs.light_cull.data();
+  sc.maxabs = E->hs.maxabs;
   sc.n_lights = (uint32_t)E->hs.emissive.size();
   sc.n_tris = (uint32_t)E->hs.n;
   sc.n_nodes = E->n_nodes;
@@ -435,6 +438,8 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     fc.wave.capacity = (uint32_t)E->rays.size();
     fc.wave.occ = E->occ.data();
     fc.wave.hits = E->hits.data();
+    E->brdf_dir.resize((size_t)npix * std::max(P.M_Brdf, 1));
+    fc.wave.brdf_dir = E->brdf_dir.data();
     fc.wave.npix = npix;
     fc.wave.brdf_two_step = (E->em_n_nodes > 0 && !(getenv("RB_TWO_STEP_BRDF") && atoi(getenv("RB_TWO_STEP_BRDF")) == 0)) ? 1u : 0u;
     size_t cand_slots = (E->wave_spatial && P.doSpatialReuse) ? (size_t)P.spatialReuseNeighborCount + 1 : 0;
@@ -471,12 +476,12 @@ int emu_frame_begin(void* h, const RbCamera* cam, uint32_t frame_idx) {
     if (P.doVisibilityPass) {  // the resolve kernel also queues the visibility pass's rays (fresh queue)
       E->qcount = 0;
       fc.wave.fuse_vis = 1u;
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c); });
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { { uint32_t pk[kPickChunk]; initial_pixel(fc, x, y, ResolveVis{&fc, PX(fc, x, y)}, c, PickStore{pk, 1}); } });
       fc.wave.fuse_vis = 0u;
     } else
-      for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, ResolveInlineShadowVis{&fc, PX(fc, x, y)}, c); });
+      for_pixels(E, fc, [&](int x, int y, Cnt& c) { { uint32_t pk[kPickChunk]; initial_pixel(fc, x, y, ResolveInlineShadowVis{&fc, PX(fc, x, y)}, c, PickStore{pk, 1}); } });
   } else {
-    for_pixels(E, fc, [&](int x, int y, Cnt& c) { initial_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c); });
+    for_pixels(E, fc, [&](int x, int y, Cnt& c) { { uint32_t pk[kPickChunk]; initial_pixel(fc, x, y, InlineVis{&fc, PX(fc, x, y)}, c, PickStore{pk, 1}); } });
   }
   const bool temporal_runs = P.doTemporalReuse && frame_idx > 0 && E->havePrev;
   bool vis_in_temporal = false;
@@ -676,6 +681,15 @@ int emu_halo_export(void* h, int y, int rows, void* dst) { return emu_halo_copy(
 int emu_halo_import(void* h, int y, int rows, const void* src) { return emu_halo_copy((Emu*)h, y, rows, (char*)src, false); }
 
 uint64_t emu_deferred_total(void* h) { return ((Emu*)h)->n_deferred_total; }
+// horizon pre-test of initial_pixel (rb_passes.cuh): switch the check mode, return and reset
+// {pre-culled, confirmed by the exact test, violations, candidates, culled by the exact test}
+void emu_horizon_cull_check(int mode, uint64_t* out4) {
+  for (int i = 0; i < 5; ++i) {
+    if (out4) out4[i] = g_horizon_cull_check.counts[i];
+    g_horizon_cull_check.counts[i] = 0;
+  }
+  g_horizon_cull_check.check_mode = mode;
+}
 void emu_counters(void* h, uint64_t* out3) {
   Emu* E = (Emu*)h;
   out3[0] = E->counters[0], out3[1] = E->counters[1], out3[2] = E->counters[2];

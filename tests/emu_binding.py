@@ -52,11 +52,19 @@ def lib():
         L.emu_frame_spatial.argtypes = [C.c_void_p, C.c_int]
         L.emu_frame_end.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_halo_rows.argtypes = [C.c_void_p]
+        L.emu_horizon_cull_check.argtypes = [C.c_int, C.c_void_p]
         L.emu_set_band.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.emu_halo_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.emu_halo_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
+
+
+def horizon_cull_check(mode):
+    """switch the check mode of initial_pixel's horizon pre-test (process-wide); returns and resets the counts so far"""
+    c = np.zeros(5, dtype=np.uint64)
+    lib().emu_horizon_cull_check(int(mode), c.ctypes.data)
+    return dict(pre_culled=int(c[0]), confirmed=int(c[1]), violations=int(c[2]), candidates=int(c[3]), exact_culled=int(c[4]))
 
 
 class Emu:
