@@ -319,9 +319,11 @@ DM_HD double ibeta_cf(double a, double b, double x) {
   }
   return A1 / B1;
 }
-DM_HD_NOINLINE double ibeta_full(double a, double b, double x) {
+// log B(a, b): depends on the exponents only (a material constant where a = shininess / 2, b = 1/2)
+DM_HD double ibeta_lbeta(double a, double b) { return lgamma_pos(a) + lgamma_pos(b) - lgamma_pos(a + b); }
+// ibeta_full with log B(a, b) supplied by the caller (the same number ibeta_lbeta returns)
+DM_HD_NOINLINE double ibeta_full_lb(double a, double b, double x, double lbeta) {
   if (x <= 0.0) return 0.0;
-  double lbeta = lgamma_pos(a) + lgamma_pos(b) - lgamma_pos(a + b);
   if (x >= 1.0) return exp_(lbeta);
   // x^a (1-x)^b
   double lfront = a * log_pos(x) + b * log_pos(1.0 - x);
@@ -329,6 +331,10 @@ DM_HD_NOINLINE double ibeta_full(double a, double b, double x) {
     return exp_(lfront) * ibeta_cf(a, b, x) / a;
   }
   return exp_(lbeta) - exp_(lfront) * ibeta_cf(b, a, 1.0 - x) / b;
+}
+DM_HD double ibeta_full(double a, double b, double x) {
+  if (x <= 0.0) return 0.0;
+  return ibeta_full_lb(a, b, x, ibeta_lbeta(a, b));
 }
 DM_HD float ibetaf_(float a, float b, float x) { return (float)ibeta_full((double)a, (double)b, (double)x); }
 

@@ -277,20 +277,41 @@ typedef ResolveVisT<true> ResolveInlineShadowVis;
 //      P/Distribution.h) ------------------------------------------------------------
 RB_HD float max_component(const V3& v) { return gmax(gmax(v.x, v.y), v.z); }  // P/utils.h:61-63
 
-RB_HD_NOINLINE float calc_I_M(float nDotV, float n) {  // MaterialPhong::calc_I_M, :228-244
+// The parts of calc_I_M that depend on the shininess alone — log B(n/2, 1/2) inside the incomplete beta function and the
+// gamma quotient: five lgamma evaluations and an exp, half of the function's cost — are material constants. They are
+// computed once per material at upload BY THESE SAME FUNCTIONS (on the device for the library, on the host for the
+// host build), so a pixel that uses them gets the bits it would have computed itself; a pixel whose shininess does not
+// come from the material constant (roughness map) computes them as before.
+RB_HD double im_lbeta(float n) { return dm::ibeta_lbeta((double)(0.5f * n), (double)0.5f); }
+RB_HD float im_gamma_quot(float n) {  // gamma_quot(halfn + 0.5, halfn + 1), P/MaterialPhong.cpp:224-226
+  const float halfn = 0.5f * n;
+  return dm::expf_(dm::lgammaf_(halfn + 0.5f) - dm::lgammaf_(halfn + 1.0f));
+}
+RB_HD MatConst make_mat_const(float n) {
+  MatConst c;
+  c.lbeta = n >= 1e-18f ? im_lbeta(n) : 0.0;
+  c.gq = im_gamma_quot(n);
+  c.shininess = n;
+  return c;
+}
+RB_HD_NOINLINE float calc_I_M(float nDotV, float n, const MatConst* mc = nullptr) {  // MaterialPhong::calc_I_M, :228-244
   float costerm = nDotV;
   float sinterm_sq = 1.0f - costerm * costerm;
   float halfn = 0.5f * n;
   float negterm = costerm;
   sinterm_sq = gclamp(sinterm_sq, 0.0f, 1.0f);
-  if (n >= 1e-18f) negterm *= halfn * dm::ibetaf_(halfn, 0.5f, sinterm_sq);
-  float gq = dm::expf_(dm::lgammaf_(halfn + 0.5f) - dm::lgammaf_(halfn + 1.0f));  // gamma_quot, :224-226
+  const bool known = mc != nullptr && f2u(mc->shininess) == f2u(n);
+  if (n >= 1e-18f) {
+    const double lbeta = known ? mc->lbeta : im_lbeta(n);
+    negterm *= halfn * (float)dm::ibeta_full_lb((double)halfn, (double)0.5f, (double)sinterm_sq, lbeta);
+  }
+  const float gq = known ? mc->gq : im_gamma_quot(n);
   return (RB_TWO_PI * costerm + RB_ROOT_PI * gq * (dm::powf_(sinterm_sq, halfn) - negterm)) / (n + 2.0f);
 }
-RB_HD float inv_I_M(const V3& pos, const V3& normal, float shininess, const V3& camPos) {
+RB_HD float inv_I_M(const V3& pos, const V3& normal, float shininess, const V3& camPos, const MatConst* mc = nullptr) {
   const V3 V = normalize(camPos - pos);
   float nDotV = dot(V, normal);
-  return frcp_(calc_I_M(nDotV, shininess));
+  return frcp_(calc_I_M(nDotV, shininess, mc));
 }
 RB_HD bool uses_phong_brdf(uint32_t t) { return t == RB_MAT_PHONG || t == RB_MAT_DIELECTRIC; }
 
@@ -537,7 +558,8 @@ RB_HD GElem gbuffer_from_hit(const FrameCtx& fc, const CamState& cam, const V3& 
     e.emission = v3(fc.P.bgColor[0], fc.P.bgColor[1], fc.P.bgColor[2]);
   }
   e.isEmissive = emissive3(e.emission);
-  if (h.didHit && !e.isEmissive && uses_phong_brdf(e.matType)) e.invIM = inv_I_M(e.pos, e.normal, e.shininess, cam.pos);
+  if (h.didHit && !e.isEmissive && uses_phong_brdf(e.matType))
+    e.invIM = inv_I_M(e.pos, e.normal, e.shininess, cam.pos, fc.sc.mat_const != nullptr ? fc.sc.mat_const + h.material : nullptr);
   return e;
 }
 #define RB_PRIMARY_TNEAR (FLT_MIN + 0.01f)  // Ray ctor defaults, P/Ray.h:8

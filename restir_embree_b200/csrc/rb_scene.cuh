@@ -44,6 +44,12 @@ struct TexDev {
   int width, height, scan_width, pixel_size;
   int clamp;  // TextureClamp: 0 = REPEAT (material maps, ModelLoader::TextureProxy), 1 = CLAMP_TO_EDGE (the sky)
 };
+// per-material constants of MaterialPhong::calc_I_M (rb_passes.cuh: make_mat_const)
+struct MatConst {
+  double lbeta;     // log B(shininess / 2, 1/2)
+  float gq;         // gamma(shininess / 2 + 1/2) / gamma(shininess / 2 + 1)
+  float shininess;  // the value both were computed for (bit compare: a textured shininess falls back to computing them)
+};
 struct SceneDev {
   // geometry
   const F4* node8;        // [RB_NODE_F4 * n_nodes]
@@ -51,6 +57,7 @@ struct SceneDev {
   const F4* tri_normals;  // [3 * n_tris] scene order: {n0.xyz,n1.x} {n1.y,n1.z,n2.x,n2.y} {n2.z,0,0,0}
   const U4* tri_info;     // [n_tris] scene order: {geomID, primID, material, emissive id (int, -1 none)}
   const F4* mat;          // [3 * n_mat]: {diffuse.rgb, shininess} {specular.rgb, bits(type)} {emission.rgb, ior}
+  const MatConst* mat_const;  // [n_mat] or null
   // emissive triangles (TriangleCDF::tris order, P/ModelLoader.cpp:301-306)
   const F4* light;  // [6 * n_lights]: {p0,area} {p1,area/total} {p2,1/area} {n0,Le.r} {n1,Le.g} {n2,Le.b}
   const float* cdf;

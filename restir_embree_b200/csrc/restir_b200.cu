@@ -149,6 +149,12 @@ __global__ void __launch_bounds__(256) k_accumulate_display(const float* __restr
   }
 }
 
+// calc_I_M's per-material constants, computed on the device by the functions the pixels would call (same bits)
+__global__ void k_material_constants(const F4* __restrict__ mat, MatConst* __restrict__ out, uint32_t n_mat) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_mat) out[i] = make_mat_const(mat[3 * (size_t)i].w);
+}
+
 // ---- persistent traversal kernels over the ray queue ------------------------------------------------
 // One ray per lane. Three things keep the warps full in this divergent workload:
 //   * dynamic fetch: warps pull rays from the queue with one aggregated atomic and refill the lanes whose rays
@@ -1481,6 +1487,11 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     }
     h->sceneTan = d_tan;
     h->nMaterials = sd->n_materials;
+    MatConst* d_mc = nullptr;
+    if (sd->n_materials > 0) {
+      RB_TRY(dev_alloc(h, &d_mc, sd->n_materials, h->sceneAllocs));
+      k_material_constants<<<(sd->n_materials + 127) / 128, 128, 0, h->stream>>>(d_mat, d_mc, sd->n_materials);
+    }
     RB_CUDA(cudaStreamSynchronize(h->stream));
     F4 *node8 = nullptr, *tri_isect = nullptr;
     uint32_t n_nodes = 0, depth = 0;
@@ -1511,6 +1522,7 @@ int rb_upload_scene(RbHandle h, const RbSceneDesc* sd) {
     sc.tri_normals = d_nrm;
     sc.tri_info = d_info;
     sc.mat = d_mat;
+    sc.mat_const = d_mc;
     sc.light = d_light;
     sc.cdf = d_cdf;
     sc.alias_prob = d_ap;

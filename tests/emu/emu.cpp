@@ -58,6 +58,7 @@ struct Emu {
   std::vector<uint8_t> occ;
   std::vector<HitRec> hits;
   std::vector<F4> brdf_dir;
+  std::vector<MatConst> mat_const;
   std::vector<U4> cand;
   bool shaded = false;
   std::vector<TexDev> tex_tab;  // rb_set_textures mirror
@@ -285,6 +286,9 @@ int emu_upload_scene(void* h, const RbSceneDesc* sd) {
   sc.tri_normals = E->hs.nrm.data();
   sc.tri_info = E->hs.info.data();
   sc.mat = E->hs.mat.data();
+  E->mat_const.resize(E->hs.mat.size() / 3);
+  for (size_t i = 0; i < E->mat_const.size(); ++i) E->mat_const[i] = make_mat_const(E->hs.mat[3 * i].w);
+  sc.mat_const = E->mat_const.data();
   sc.light = E->hs.light.data();
   sc.cdf = E->hs.cdf.data();
   sc.alias_prob = E->hs.alias_prob.data();
