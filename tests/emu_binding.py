@@ -14,7 +14,21 @@ LIB_PATH = os.path.join(ROOT, "tests", "emu", "libemu.so")
 CSRC = os.path.join(ROOT, "restir_embree_b200", "csrc")
 
 
+def build_emu_sanitized():
+    """the same translation unit with AddressSanitizer + UndefinedBehaviorSanitizer (tests/test_emu_sanitized.py)"""
+    out = os.path.join(ROOT, "tests", "emu", "libemu_asan.so")
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-g", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-fPIC",
+                           "-std=c++17", "-DRB_TRAV_STATS", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                           "-x", "c++", "-shared", "-o", out, SRC])
+    return out
+
+
 def build_emu(force=False):
+    if os.environ.get("RB_EMU_LIB"):  # an alternative build of the same source (sanitized), made by the caller
+        return
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return
@@ -29,7 +43,7 @@ def lib():
     global _lib
     if _lib is None:
         build_emu()
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(os.environ.get("RB_EMU_LIB", LIB_PATH))
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int]
         L.emu_destroy.argtypes = [C.c_void_p]
