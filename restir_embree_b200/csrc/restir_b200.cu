@@ -67,7 +67,11 @@ __device__ __forceinline__ PickStore smem_picks() {
   return PickStore{s_pick + threadIdx.y * blockDim.x + threadIdx.x, THREADS};
 }
 
-RB_PIXEL_KERNEL_T(k_gbuffer, InlineVis, true, 128, 5, gbuffer_pixel(fc, x, y, cnt))  // 94 regs: 5 x 4 warps instead of 2 x 8
+#ifndef RB_GB_MINB
+#define RB_GB_MINB 7
+#endif
+// 128-thread CTAs, seven per SM (72 registers, no spills): measured 0.85 (96 regs, 5 CTAs) -> 0.72 ms with the material constants
+RB_PIXEL_KERNEL_T(k_gbuffer, InlineVis, true, 128, RB_GB_MINB, gbuffer_pixel(fc, x, y, cnt))
 RB_PIXEL_KERNEL(k_initial, InlineVis, true, 1, initial_pixel(fc, x, y, vis, cnt, smem_picks<kTileW * kTileH>()))
 RB_PIXEL_KERNEL(k_visibility, InlineVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_temporal, InlineVis, true, 1, (temporal_pixel<InlineVis, false>(fc, x, y, vis, cnt)))
@@ -88,9 +92,14 @@ RB_PIXEL_KERNEL_T(k_initial_resolve_nmap, ResolveVis, true, 128, 5, initial_pixe
 
 RB_PIXEL_KERNEL(k_initial_resolve_inline_shadow, ResolveInlineShadowVis, true, 1, initial_pixel(fc, x, y, vis, cnt, smem_picks<kTileW * kTileH>()))
 RB_PIXEL_KERNEL(k_visibility_resolve, ResolveVis, true, 1, visibility_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_temporal_stream, GenVis, true, 3, temporal_gen_pixel<0>(fc, x, y, vis, cnt))
+// 128-thread CTAs give the register allocator a finer occupancy ladder: seven per SM at 72 registers (0.265 -> 0.256 ms)
+#ifndef RB_TS_THREADS
+#define RB_TS_THREADS 128
+#define RB_TS_MINB 7
+#endif
+RB_PIXEL_KERNEL_T(k_temporal_stream, GenVis, true, RB_TS_THREADS, RB_TS_MINB, temporal_gen_pixel<0>(fc, x, y, vis, cnt))
 // bands: the bulk launch defers the few pixels whose reprojection leaves the rows held here ...
-RB_PIXEL_KERNEL(k_temporal_stream_banded, GenVis, true, 3, temporal_gen_pixel<2>(fc, x, y, vis, cnt))
+RB_PIXEL_KERNEL_T(k_temporal_stream_banded, GenVis, true, RB_TS_THREADS, RB_TS_MINB, temporal_gen_pixel<2>(fc, x, y, vis, cnt))
 // ... to this one, which carries the G-buffer re-derivation (traversal) code; grid-stride over the deferred list
 __global__ void __launch_bounds__(128) k_temporal_stream_deferred(FrameCtx fc) {
   const uint32_t n = *fc.wave.deferred_count;
@@ -103,9 +112,12 @@ __global__ void __launch_bounds__(128) k_temporal_stream_deferred(FrameCtx fc) {
   flush_counts(fc.counters, cnt);
 }
 RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 4, temporal_merge_pixel(fc, x, y, cnt))
-// three resident CTAs per SM (<= 85 registers, a few spilled words) beat two for the reuse passes (measured, profiles/);
-// the initial pass is the other way round
-RB_PIXEL_KERNEL(k_spatial_stream, GenVis, true, 3, spatial_gen_pixel(fc, x, y, vis, cnt))
+// eight 128-thread CTAs per SM at 62 registers, no spills (0.42 -> 0.375 ms against three 256-thread CTAs)
+#ifndef RB_SS_THREADS
+#define RB_SS_THREADS 128
+#define RB_SS_MINB 8
+#endif
+RB_PIXEL_KERNEL_T(k_spatial_stream, GenVis, true, RB_SS_THREADS, RB_SS_MINB, spatial_gen_pixel(fc, x, y, vis, cnt))
 RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 4, spatial_merge_pixel(fc, x, y, cnt))
 // the other spatial MIS modes in the wavefront schedule: spatial_pixel staged (StagedVis, rb_passes.cuh)
 #define RB_STAGED_KERNEL(NAME, STAGE, COUNT)                                                           \
@@ -2109,11 +2121,11 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       fs_reset_queue(h);
       fc.wave.fuse_vis = vis_in_temporal ? 2u : 0u;
       if (banded) {
-        launch_rows(h, k_temporal_stream_banded, y0, y1);
+        launch_rows(h, k_temporal_stream_banded, y0, y1, RB_TS_THREADS);
         k_temporal_stream_deferred<<<h->numSMs, 128, 0, st>>>(fc);
         F.launches++;
       } else {
-        launch_rows(h, k_temporal_stream, y0, y1);
+        launch_rows(h, k_temporal_stream, y0, y1, RB_TS_THREADS);
       }
       fc.wave.fuse_vis = 0u;
       fs_mark(h, 3, 0);
@@ -2155,11 +2167,11 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
     F.shaded = (i == P.spatialPassCount - 1);
     fc.wave.fuse_shade = F.shaded ? 1u : 0u;
     auto kss = k_spatial_stream;
-    launch_rows(h, kss, iy0, iy1);
+    launch_rows(h, kss, iy0, iy1, RB_SS_THREADS);
     if (overlap_halo) {
       RB_TRY(halo_exchange_wait(h));
-      launch_rows(h, kss, y0, iy0);
-      launch_rows(h, kss, iy1, y1);
+      launch_rows(h, kss, y0, iy0, RB_SS_THREADS);
+      launch_rows(h, kss, iy1, y1, RB_SS_THREADS);
     }
     fs_mark(h, 4, 0);
     fs_trace(h, TRACE_ANY, 4);
