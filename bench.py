@@ -247,6 +247,10 @@ def run_ours(args):
     scene = scenes.scene_config(SCENE)
     from restir_embree_b200.renderer import band_rows
     band = band_rows(HEIGHT, world, rank)
+    if world == 1 and os.environ.get("RB_BENCH_BAND"):
+        # experiments only (tools/exp.py): ONE band of an N-band run on one GPU, no neighbours (halo rows stale) - the
+        # per-pass times are those of a rank of the N-GPU run, the frame rate is not a bench value
+        band = tuple(int(v) for v in os.environ["RB_BENCH_BAND"].replace("-", ",").split(","))
     r = Renderer(WIDTH, HEIGHT, device=local, seed=123, band=band, collect_timings=True)
     stats = r.upload_scene(scene)
     p = bench_params()
@@ -488,6 +492,7 @@ def run_ours(args):
                        "exceeds the 126 MB L2; camera moves every frame", "bands": world,
                        "scene": {k: stats[k] for k in ("n_triangles", "n_emissive", "n_bvh_nodes", "bvh_depth", "build_ms")}},
             "roofline": roof, "roofline_best": roof_best, "traversal": trav, "cpu_baseline": cb, "clocks": clocks,
+            **({"experiment_band_only": list(band)} if (world == 1 and tuple(band) != (0, HEIGHT)) else {}),
             "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "frames/s", "h2d_bytes_per_step": 144,
                     "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
                     "blocking_call_value": 1e3 / (ms_e2e_blocking / args.steps),

@@ -1989,7 +1989,8 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
   uint32_t* vis_pair = reinterpret_cast<uint32_t*>(ctr + 7);
   const int gNew = (h->gCur + 1) % 3;
   // G-buffer rows kept by this handle: the band plus a margin that covers the spatial reach and most reprojections
-  const int margin = banded ? std::max(16, spatial_reach(P)) : 0;
+  static const int margin_env = getenv("RB_GBUF_MARGIN") ? atoi(getenv("RB_GBUF_MARGIN")) : 16;
+  const int margin = banded ? std::max(margin_env, spatial_reach(P)) : 0;
   FrameCtx& ff = F.ffc;
   ff = FrameCtx{};
   ff.width = h->info.width;
