@@ -129,3 +129,36 @@ def test_pre_test_on_the_bench_scene_removes_what_the_exact_test_removed():
     assert stats["violations"] == 0 and stats["confirmed"] == stats["pre_culled"]
     assert stats["exact_culled"] > 0.5 * stats["candidates"], stats
     assert stats["pre_culled"] > 0.95 * stats["exact_culled"], stats
+
+
+# ---- GPU tier: the same margin scenes through the C ABI ------------------------------------------------------------
+GPU_PARAMS = [
+    dict(M_Area=32, M_Brdf=1, doVisibilityPass=1, lightSampler=1, wavefront=1, doTemporalReuse=1, doSpatialReuse=1),
+    dict(M_Area=40, M_Brdf=0, lightSampler=0, wavefront=1),  # CDF sampler, two chunks of candidates, inline shadow rays
+    dict(M_Area=7, M_Brdf=2, doTemporalReuse=1, doSpatialReuse=1, lightSampler=1),  # inline kernels
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", range(len(CASES)))
+@pytest.mark.parametrize("pi", range(len(GPU_PARAMS)))
+def test_gpu_initial_pass_on_margin_scenes_matches_oracle_bit_for_bit(gpu, ci, pi):
+    from restir_embree_b200.renderer import Renderer
+
+    case = CASES[ci]
+    sc = horizon_scene(**case)
+    p = abi.default_params(**GPU_PARAMS[pi])
+    o = ob.Oracle(W, H, seed=11, tracer=ob.TRACER_BVH2)
+    o.upload_scene(sc)
+    o.set_params(p)
+    with Renderer(W, H, seed=11) as r:
+        r.upload_scene(sc)
+        r.set_params(p)
+        for f in range(2):
+            cam = cam_for(case["scale"], case["offset"], f)
+            a = o.render_frame(cam, f)
+            b, t = r.render_frame(cam, f, want_timings=True)
+            assert np.array_equal(bits(a), bits(b)), f"frame {f}: {(a != b).any(-1).sum()} px differ"
+            for buf in ALL_BUFS:
+                assert np.array_equal(bits(o.readback(buf)), bits(r.readback(buf))), (f, buf)
+            assert o.counters()["any_as_written"] == t["rays_any_as_written"]
