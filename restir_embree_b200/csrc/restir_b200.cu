@@ -111,14 +111,22 @@ __global__ void __launch_bounds__(128) k_temporal_stream_deferred(FrameCtx fc) {
   }
   flush_counts(fc.counters, cnt);
 }
-RB_PIXEL_KERNEL(k_temporal_resolve, ResolveVis, true, 4, temporal_merge_pixel(fc, x, y, cnt))
+#ifndef RB_TR_THREADS
+#define RB_TR_THREADS 256
+#define RB_TR_MINB 4
+#endif
+RB_PIXEL_KERNEL_T(k_temporal_resolve, ResolveVis, true, RB_TR_THREADS, RB_TR_MINB, temporal_merge_pixel(fc, x, y, cnt))
 // eight 128-thread CTAs per SM at 62 registers, no spills (0.42 -> 0.375 ms against three 256-thread CTAs)
 #ifndef RB_SS_THREADS
 #define RB_SS_THREADS 128
 #define RB_SS_MINB 8
 #endif
 RB_PIXEL_KERNEL_T(k_spatial_stream, GenVis, true, RB_SS_THREADS, RB_SS_MINB, spatial_gen_pixel(fc, x, y, vis, cnt))
-RB_PIXEL_KERNEL(k_spatial_resolve, ResolveVis, true, 4, spatial_merge_pixel(fc, x, y, cnt))
+#ifndef RB_SR_THREADS
+#define RB_SR_THREADS 256
+#define RB_SR_MINB 4
+#endif
+RB_PIXEL_KERNEL_T(k_spatial_resolve, ResolveVis, true, RB_SR_THREADS, RB_SR_MINB, spatial_merge_pixel(fc, x, y, cnt))
 // the other spatial MIS modes in the wavefront schedule: spatial_pixel staged (StagedVis, rb_passes.cuh)
 #define RB_STAGED_KERNEL(NAME, STAGE, COUNT)                                                           \
   __global__ void __launch_bounds__(kTileW* kTileH, 2) NAME(FrameCtx fc) {                            \
@@ -2131,7 +2139,7 @@ static int frame_begin(RbHandle h, const RbCamera* cam, uint32_t frame_idx, bool
       fc.wave.fuse_vis = 0u;
       fs_mark(h, 3, 0);
       fs_trace(h, TRACE_ANY, 3);
-      launch_rows(h, k_temporal_resolve, y0, y1);
+      launch_rows(h, k_temporal_resolve, y0, y1, RB_TR_THREADS);
     } else {
       if (banded)
         launch_rows(h, k_temporal_banded, y0, y1);
@@ -2177,7 +2185,7 @@ static int frame_spatial(RbHandle h, int i, bool overlap_halo) {
     fs_mark(h, 4, 0);
     fs_trace(h, TRACE_ANY, 4);
     if (F.shaded) RB_TRY(wait_frame_copy(h));
-    launch_rows(h, k_spatial_resolve, y0, y1);
+    launch_rows(h, k_spatial_resolve, y0, y1, RB_SR_THREADS);
     fc.wave.fuse_shade = 0u;
   } else if (F.wave_spatial_staged) {
     // stage 1 (rays asked for before the selection) -> trace -> [debias modes: stage 2 (rays that depend on the
