@@ -685,6 +685,12 @@ int emu_halo_export(void* h, int y, int rows, void* dst) { return emu_halo_copy(
 int emu_halo_import(void* h, int y, int rows, const void* src) { return emu_halo_copy((Emu*)h, y, rows, (char*)src, false); }
 
 uint64_t emu_deferred_total(void* h) { return ((Emu*)h)->n_deferred_total; }
+// calc_I_M with (use_const = 1) and without the per-material constants of make_mat_const: must be the same bits
+float emu_calc_I_M(float nDotV, float n, int use_const) {
+  if (!use_const) return calc_I_M(nDotV, n, nullptr);
+  const MatConst mc = make_mat_const(n);
+  return calc_I_M(nDotV, n, &mc);
+}
 // horizon pre-test of initial_pixel (rb_passes.cuh): switch the check mode, return and reset
 // {pre-culled, confirmed by the exact test, violations, candidates, culled by the exact test}
 void emu_horizon_cull_check(int mode, uint64_t* out4) {

@@ -67,6 +67,8 @@ def lib():
         L.emu_frame_end.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_halo_rows.argtypes = [C.c_void_p]
         L.emu_horizon_cull_check.argtypes = [C.c_int, C.c_void_p]
+        L.emu_calc_I_M.argtypes = [C.c_float, C.c_float, C.c_int]
+        L.emu_calc_I_M.restype = C.c_float
         L.emu_set_band.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.emu_halo_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.emu_halo_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]

@@ -88,3 +88,24 @@ def test_mt19937_stream_matches_survey_probe():
     out = np.zeros(3, dtype=np.float32)
     L.orc_legacy_floats(123, 3, out.ctypes.data)
     assert np.allclose(out, [0.696469188, 0.712955296, 0.286139339], atol=1e-8)
+
+
+def test_calc_I_M_with_material_constants_is_the_same_function():
+    """rb_passes.cuh: log B(n/2, 1/2) and the gamma quotient are computed once per material (make_mat_const) — the result
+    must be calc_I_M's own bits for every shininess and angle, including the values around its special cases"""
+    import struct
+
+    import emu_binding as eb
+    L = eb.lib()
+    rng = np.random.default_rng(9)
+    shin = np.concatenate([[0.0, 1e-20, 1e-18, 0.5, 1.0, 2.0, 3.0, 5.0, 20.0, 31.0, 80.0, 250.0, 1000.0, 4096.0, 1e5],
+                           rng.uniform(0.0, 300.0, 40), np.exp(rng.uniform(-3, 9, 40))]).astype(np.float32)
+    cosv = np.concatenate([[-1.0, -0.5, 0.0, 1e-8, 0.3, 0.7071068, 0.999999, 1.0], rng.uniform(-1, 1, 60)]).astype(np.float32)
+    n = 0
+    for s in shin:
+        for c in cosv:
+            a = L.emu_calc_I_M(float(c), float(s), 0)
+            b = L.emu_calc_I_M(float(c), float(s), 1)
+            assert struct.pack("f", a) == struct.pack("f", b), (float(c), float(s), a, b)
+            n += 1
+    assert n > 6000
