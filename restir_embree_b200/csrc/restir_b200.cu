@@ -1191,7 +1191,9 @@ int rb_create(const RbCreateInfo* info, RbHandle* out) {
     {
       int lo = 0, hi = 0;
       RB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      RB_CUDA(cudaStreamCreateWithPriority(&h->fstream, cudaStreamNonBlocking, lo));
+      // the front half yields to the back half (RB_FRONT_PRIO=1: same priority — measured, no better)
+      const bool same = getenv("RB_FRONT_PRIO") && atoi(getenv("RB_FRONT_PRIO")) != 0;
+      RB_CUDA(cudaStreamCreateWithPriority(&h->fstream, cudaStreamNonBlocking, same ? hi : lo));
     }
     RB_CUDA(cudaEventCreateWithFlags(&h->evFrontDone, cudaEventDisableTiming));
     for (auto& ev : h->evBackDone) RB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
